@@ -173,6 +173,43 @@ def write_fcidump(path: str, sp: ActiveSpace, tol: float = 0.0) -> None:
         fh.write(f"{sp.core_energy:28.20e}    0    0    0    0\n")
 
 
+def save_sparse_npz(path: str, sp: ActiveSpace) -> None:
+    """Compact fixture format: unique non-zero (pq|rs), p>=q, r>=s, pq>=rs, plus T's lower
+    triangle -- i.e. exactly the information content of a FCIDUMP file."""
+    n = sp.norb
+    V = sp.V.reshape(n, n, n, n)
+    vals, idx = [], []
+    for p in range(n):
+        for q in range(p + 1):
+            pq = p * (p + 1) // 2 + q
+            for r in range(p + 1):
+                for s in range(r + 1):
+                    if r * (r + 1) // 2 + s > pq:
+                        continue
+                    v = V[p, q, r, s]
+                    if v != 0.0:
+                        vals.append(v)
+                        idx.append((p, q, r, s))
+    np.savez_compressed(path, norb=n, nalpha=sp.nalpha, nbeta=sp.nbeta, core=sp.core_energy,
+                        name=sp.name, T=sp.T, vals=np.array(vals),
+                        idx=np.array(idx, dtype=np.int8))
+
+
+def load_sparse_npz(path: str) -> ActiveSpace:
+    z = np.load(path)
+    n = int(z["norb"])
+    V = np.zeros((n, n, n, n))
+    idx = z["idx"].astype(np.int64)
+    vals = z["vals"]
+    p, q, r, s = idx[:, 0], idx[:, 1], idx[:, 2], idx[:, 3]
+    for (a, b, c, d) in ((p, q, r, s), (p, q, s, r), (q, p, r, s), (q, p, s, r),
+                         (r, s, p, q), (s, r, p, q), (r, s, q, p), (s, r, q, p)):
+        V[a, b, c, d] = vals
+    return ActiveSpace(str(z["name"]), n, int(z["nalpha"]), int(z["nbeta"]),
+                       np.ascontiguousarray(z["T"]), np.ascontiguousarray(V.reshape(-1)),
+                       float(z["core"]))
+
+
 def save_npz(path: str, sp: ActiveSpace) -> None:
     np.savez_compressed(path, norb=sp.norb, nalpha=sp.nalpha, nbeta=sp.nbeta, T=sp.T,
                         V=sp.V, core=sp.core_energy, name=sp.name)

@@ -1,0 +1,156 @@
+"""Pins the plain-C oracle (oracle/port) against the reference's golden vectors and the
+fixtures generated from the compiled reference (tests/golden/make_golden.py). CPU only."""
+import os
+
+import numpy as np
+import pytest
+
+from oracle import port
+from qdk_chemistry_b200 import workloads as W
+from helpers import EPS, check_csr_against_golden, cisd_space, sha
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def test_water_hf_energy(water, golden_meta):
+    # external/macis/tests/double_loop.cxx:59-63 (tolerance 1e-6: FCIDUMP text precision)
+    h = port.Ham(water.norb, water.T, water.V)
+    e = h.matrix_element(31, 31, 31, 31) + water.core_energy
+    assert abs(e - golden_meta["known_answers"]["water_hf_total"]) < 1e-6
+
+
+def test_water_cisd_pattern_matches_reference_blob(water, golden_meta, golden_arrays):
+    # external/macis/tests/csr_hamiltonian.cxx:76-99: n, nnz and EXACT rowptr
+    a, b = cisd_space(24, 5, 5)
+    h = port.Ham(water.norb, water.T, water.V)
+    rp, ci, nz = h.hbuild(a, b, 1e-16)
+    ka = golden_meta["known_answers"]
+    assert len(a) == ka["water_cisd_n"] and rp[-1] == ka["water_cisd_nnz"]
+    blob = np.fromfile(os.path.join(GOLDEN, "h2o.ccpvdz.cisd.rowptr.bin"), dtype=np.int32)
+    assert np.array_equal(rp, blob.astype(np.int64))
+    check_csr_against_golden(golden_meta, golden_arrays, "water_cisd_1e-16", rp, ci, nz)
+
+
+@pytest.mark.parametrize("tag,thr", [("eps", EPS), ("zero", 0.0)])
+def test_water_cisd_threshold_semantics(water, golden_meta, golden_arrays, tag, thr):
+    # post-filter keeps |h| > thr and is skipped for thr == 0 (sorted_double_loop.hpp:421)
+    a, b = cisd_space(24, 5, 5)
+    h = port.Ham(water.norb, water.T, water.V)
+    rp, ci, nz = h.hbuild(a, b, thr)
+    check_csr_against_golden(golden_meta, golden_arrays, f"water_cisd_{tag}", rp, ci, nz)
+
+
+def test_water_cisd_davidson(water, golden_meta, golden_arrays):
+    # external/macis/tests/davidson.cxx:48-72
+    a, b = cisd_space(24, 5, 5)
+    h = port.Ham(water.norb, water.T, water.V)
+    rp, ci, nz = h.hbuild(a, b, 1e-16)
+    E, X, niter, _ = port.davidson(rp, ci, nz, 15, 1e-8, guess_policy=False)
+    ka = golden_meta["known_answers"]
+    assert abs(E + water.core_energy - ka["water_cisd_davidson_total"]) < 1e-8
+    rec = golden_meta["water_cisd_1e-16"]["davidson"]
+    assert abs(E - rec["E"]) < 1e-10 and niter == rec["niter"]
+    assert abs(X @ X - 1.0) < 1e-12
+    assert abs(X @ port.spmv(rp, ci, nz, X) - E) < 1e-12
+    assert abs(abs(X @ golden_arrays["water_cisd_1e-16.davidson_X"]) - 1.0) < 1e-10
+
+
+@pytest.mark.parametrize("name", ["tiny_cas6", "small_cas8", "hubbard_3x2", "hubbard_4x2"])
+@pytest.mark.parametrize("tag,thr", [("eps", EPS), ("zero", 0.0)])
+def test_fci_csr_and_davidson(golden_meta, golden_arrays, name, tag, thr):
+    sp = W.config(name)
+    a, b = port.generate_hilbert_space(sp.norb, sp.nalpha, sp.nbeta)
+    assert sha(port.pack(a, b)) == golden_meta[f"{name}_dets_sha"]
+    h = port.Ham(sp.norb, sp.T, sp.V)
+    rp, ci, nz = h.hbuild(a, b, thr)
+    check_csr_against_golden(golden_meta, golden_arrays, f"{name}_{tag}", rp, ci, nz)
+    if tag == "eps":
+        rec = golden_meta[f"{name}_eps"]["davidson"]
+        E, X, niter, _ = port.davidson(rp, ci, nz, 200, 1e-8, guess_policy=False)
+        assert abs(E - rec["E"]) < 1e-9
+        assert abs(niter - rec["niter"]) <= 1
+
+
+def test_row_block_build_equals_full(golden_meta):
+    sp = W.config("tiny_cas6")
+    a, b = port.generate_hilbert_space(sp.norb, sp.nalpha, sp.nbeta)
+    h = port.Ham(sp.norb, sp.T, sp.V)
+    rp, ci, nz = h.hbuild(a, b, EPS)
+    r0, r1 = 137, 301
+    rpb, cib, nzb = h.hbuild(a, b, EPS, rows=(r0, r1))
+    assert np.array_equal(rpb, rp[r0:r1 + 1] - rp[r0])
+    assert np.array_equal(cib, ci[rp[r0]:rp[r1]]) and np.array_equal(nzb, nz[rp[r0]:rp[r1]])
+
+
+def test_alpha_zero_rows_are_empty():
+    # SDL skips determinants with an empty alpha string (sorted_double_loop.hpp:147,156)
+    sp = W.synthetic_molecular("x", 5, 0, 2, 5, 6)
+    a, b = port.generate_hilbert_space(5, 0, 2)
+    h = port.Ham(sp.norb, sp.T, sp.V)
+    rp, ci, nz = h.hbuild(a, b, 0.0)
+    assert rp[-1] == 0
+
+
+def test_n2_6e6o_casci(n2_6, golden_meta):
+    # external/macis/python/tests/test_pymacis.py:114-126
+    a, b = port.generate_hilbert_space(6, 3, 3)
+    h = port.Ham(n2_6.norb, n2_6.T, n2_6.V)
+    rp, ci, nz = h.hbuild(a, b, EPS)
+    E, X, niter, _ = port.davidson(rp, ci, nz, 200, 1e-8)
+    assert np.isclose(E, golden_meta["known_answers"]["n2_6e6o_casci"])
+    assert abs(E - golden_meta["n2_6e6o_casci_ref"]["E"]) < 1e-9
+
+
+def test_water_asci_search_selection_is_identical(water, golden_meta, golden_arrays):
+    # one asci_search call (determinant_search.hpp:808-1123) on reference-made inputs
+    h = port.Ham(water.norb, water.T, water.V)
+    m = golden_meta["water_search"]
+    sa, sb, stats = h.asci_search(golden_arrays["water_search.core_alpha"],
+                                  golden_arrays["water_search.core_beta"],
+                                  golden_arrays["water_search.core_C"], m["E0"], m["ndets_max"])
+    got = np.sort(port.pack(sa, sb))
+    assert np.array_equal(got, golden_arrays["water_search.selected"])
+    # the cut does not sit inside accumulated rounding: relative gap >> 1e-13
+    assert (stats[2] - stats[3]) / stats[2] > 1e-10
+
+
+def test_water_asci_grow_and_refine_energies(water, golden_meta):
+    # external/macis/tests/asci.cxx:541-558
+    h = port.Ham(water.norb, water.T, water.V)
+    ka = golden_meta["known_answers"]
+    E, a, b, X = port.asci_run(h, 5, 5, refine=False, core_selection_strategy="fixed",
+                               ntdets_max=10000)
+    assert len(a) == 10000 and abs(X @ X - 1) < 1e-12
+    assert abs(E - ka["water_asci_grow"]) < 1e-8
+    E2, a2, b2, X2 = port.asci_run(h, 5, 5, refine=True, core_selection_strategy="fixed",
+                                   ntdets_max=10000)
+    assert abs(E2 - ka["water_asci_refine"]) < 1e-8
+    assert sha(np.sort(port.pack(a2, b2))) == golden_meta["water_asci_refine_ref"]["dets_sha"]
+
+
+def test_n2_14e18o_asci_2000(n2_18, golden_meta, golden_arrays):
+    # external/macis/python/tests/test_pymacis.py:158-188 (percentage core selection)
+    h = port.Ham(n2_18.norb, n2_18.T, n2_18.V)
+    E, a, b, X = port.asci_run(h, 7, 7, refine=True, ntdets_max=2000, grow_factor=2.0,
+                               max_refine_iter=15, ci_max_subspace=1000)
+    assert np.isclose(E, golden_meta["known_answers"]["n2_14e18o_asci2000"])
+    assert abs(E - golden_meta["n2_14e18o_asci2000_ref"]["E"]) < 1e-8
+    # A singlet's spin-flip partners (alpha <-> beta) carry |c| and |rv| that are equal in
+    # exact arithmetic; which partner survives a cut that splits such a pair is decided by
+    # the reference's unstable std::sort / rounding (determinant_sort.hpp:51-52,115-136), so
+    # selections are compared modulo spin-flip partners of dropped determinants.
+    got = set(port.pack(a, b).tolist())
+    want = set(golden_arrays["n2_14e18o_asci2000.dets"].tolist())
+    flip = lambda k: ((k & 0xFFFFFFFF) << 32) | (k >> 32)
+    assert len(got) == len(want) == 2000
+    assert all(flip(k) in (want - got) for k in (got - want))
+    assert len(got - want) <= 40
+
+
+def test_syev_small():
+    rng = np.random.default_rng(3)
+    A = rng.normal(size=(17, 17))
+    A = A + A.T
+    W_, Q = port.syev_lower(A)
+    assert np.allclose(W_, np.linalg.eigvalsh(A), atol=1e-12)
+    assert np.allclose(Q.T @ A @ Q, np.diag(W_), atol=1e-11)
