@@ -1,0 +1,512 @@
+// ASCI connected-determinant search on the device.
+//
+// Replaces macis::asci_search / asci_contributions_constraint (external/macis/include/macis/
+// asci/determinant_search.hpp:349-771, 808-1123) and the contribution emitters
+// (asci/determinant_contributions.hpp:93-297 == asci/mask_constraints.hpp:400-670 term by
+// term). The reference partitions the excited space by alpha-string constraints so every
+// CPU thread can sort/accumulate its share; on the GPU that partition is unnecessary:
+//
+//   1. per core determinant: orbital energies (fast_diagonals.ipp:29-49) and <D|H|D>
+//   2. count pass / fill pass: one CTA per core determinant enumerates its singles, same-spin
+//      doubles and opposite-spin doubles, keeps |c*h| >= h_el_tol, and writes
+//      (bitstring key, c*h, E0 - <Q|H|Q>) records parent-major (deterministic offsets)
+//   3. stable LSD radix sort of (key, record index)              [radix.cu]
+//   4. per unique key: sequential sum of c*h in parent order, h_diag of the first parent
+//      (accumulate_asci_pairs, determinant_sort.hpp:115-136, in canonical order)
+//   5. drop core determinants (rv = inf sentinel, determinant_search.hpp:659-660,970-974)
+//      and |rv| <= rv_prune_tol (:676-681); radix-select the k-th largest |rv| and keep
+//      every candidate >= it (ties retained, :994-1080); append the core determinants.
+#include <cmath>
+#include <cstring>
+
+#include "common.cuh"
+#include "slater.cuh"
+
+namespace b2ci {
+
+void radix_sort_pairs(b2ci_ctx* ctx, uint64_t* keys, uint64_t* keys_alt, uint32_t* vals,
+                      uint32_t* vals_alt, int64_t n, const std::vector<int>& shifts);
+void iota_u32(b2ci_ctx* ctx, uint32_t* v, int64_t n);
+double select_kth_largest(b2ci_ctx* ctx, const double* score, int64_t n, int64_t k);
+
+namespace {
+
+constexpr int GEN_THREADS = 256;
+constexpr int MAX_PAIRS = 2016;  // C(64, 2)
+
+__global__ void k_core_pre(IntsView I, const uint64_t* __restrict__ ca,
+                           const uint64_t* __restrict__ cb, int64_t nc,
+                           double* __restrict__ eps_a, double* __restrict__ eps_b,
+                           double* __restrict__ root) {
+  const int64_t t = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+  const int n = I.n;
+  if (t >= nc * n) return;
+  const int64_t c = t / n;
+  const unsigned i = unsigned(t % n);
+  const uint64_t a = ca[c], b = cb[c];
+  eps_a[t] = orbital_energy(I, i, a, b);
+  eps_b[t] = orbital_energy(I, i, b, a);
+  if (i == 0) root[c] = me_diag(I, a, b);
+}
+
+struct GenArgs {
+  IntsView I;
+  const uint64_t* ca;
+  const uint64_t* cb;
+  const double* coeff;
+  const double* eps_a;
+  const double* eps_b;
+  const double* root;
+  double E0, tol;
+  int just_singles;
+  int packed;              // 1: key = beta << 32 | alpha (norb <= 32); 0: key = alpha, key2 = beta
+  int32_t* count;          // count pass
+  const int64_t* base;     // fill pass
+  uint64_t* key;
+  uint64_t* key2;
+  double* cm;
+  double* hd;
+};
+
+__device__ __forceinline__ void pair_from_index(int p, int m, int& ii, int& jj) {
+  // p-th pair (ii < jj) of m items in the order of the reference's nested loops
+  int i = 0, rem = p;
+  while (rem >= m - 1 - i) { rem -= m - 1 - i; ++i; }
+  ii = i;
+  jj = i + 1 + rem;
+}
+
+#define G2_(p, q) ldg(A.I.G2 + (p) + size_t(q) * n)
+#define V2_(p, q) ldg(A.I.V2 + (p) + size_t(q) * n)
+
+template <bool FILL>
+__global__ void __launch_bounds__(GEN_THREADS)
+k_generate(const GenArgs A) {
+  __shared__ unsigned char occ_a[64], vir_a[64], occ_b[64], vir_b[64];
+  __shared__ unsigned short po_a[MAX_PAIRS], pv_a[MAX_PAIRS], po_b[MAX_PAIRS], pv_b[MAX_PAIRS];
+  __shared__ int s_cnt;
+  __shared__ int s_red[GEN_THREADS / 32];
+  const int64_t c = blockIdx.x;
+  const size_t n = A.I.n, n2 = n * n;
+  const uint64_t sa = A.ca[c], sb = A.cb[c];
+  const int na = __popcll(sa), nb = __popcll(sb);
+  const int nva = int(n) - na, nvb = int(n) - nb;
+  if (threadIdx.x == 0) {
+    int k = 0;
+    for (uint64_t s = sa; s; s &= s - 1) occ_a[k++] = (unsigned char)lsb64(s);
+    k = 0;
+    for (uint64_t s = ~sa & low_mask(int(n)); s; s &= s - 1) vir_a[k++] = (unsigned char)lsb64(s);
+    k = 0;
+    for (uint64_t s = sb; s; s &= s - 1) occ_b[k++] = (unsigned char)lsb64(s);
+    k = 0;
+    for (uint64_t s = ~sb & low_mask(int(n)); s; s &= s - 1) vir_b[k++] = (unsigned char)lsb64(s);
+    s_cnt = 0;
+  }
+  const int npo_a = na * (na - 1) / 2, npv_a = nva * (nva - 1) / 2;
+  const int npo_b = nb * (nb - 1) / 2, npv_b = nvb * (nvb - 1) / 2;
+  if (!A.just_singles) {
+    for (int p = threadIdx.x; p < npo_a; p += GEN_THREADS) { int i, j; pair_from_index(p, na, i, j); po_a[p] = (unsigned short)((i << 8) | j); }
+    for (int p = threadIdx.x; p < npv_a; p += GEN_THREADS) { int i, j; pair_from_index(p, nva, i, j); pv_a[p] = (unsigned short)((i << 8) | j); }
+    for (int p = threadIdx.x; p < npo_b; p += GEN_THREADS) { int i, j; pair_from_index(p, nb, i, j); po_b[p] = (unsigned short)((i << 8) | j); }
+    for (int p = threadIdx.x; p < npv_b; p += GEN_THREADS) { int i, j; pair_from_index(p, nvb, i, j); pv_b[p] = (unsigned short)((i << 8) | j); }
+  }
+  __syncthreads();
+
+  const double coeff = A.coeff[c];
+  const double root = A.root[c];
+  const double* eps_a = A.eps_a + c * n;
+  const double* eps_b = A.eps_b + c * n;
+  const int64_t nSa = int64_t(na) * nva, nSb = int64_t(nb) * nvb;
+  const int64_t nDa = A.just_singles ? 0 : int64_t(npo_a) * npv_a;
+  const int64_t nDb = A.just_singles ? 0 : int64_t(npo_b) * npv_b;
+  const int64_t nOS = A.just_singles ? 0 : nSa * nSb;
+  const int64_t o1 = nSa, o2 = o1 + nSb, o3 = o2 + nDa, o4 = o3 + nDb, o5 = o4 + nOS;
+  const int64_t total = o5 + 1;  // + the "no excitation" sentinel
+  const int64_t base = FILL ? A.base[c] : 0;
+  int mycount = 0;
+
+  for (int64_t t = threadIdx.x; t < total; t += GEN_THREADS) {
+    bool emit = false;
+    uint64_t ea = sa, eb = sb;
+    double cmv = 0., hdv = 0.;
+    if (t < o2) {
+      // ---- single excitation, alpha (t < o1) or beta
+      const bool is_a = t < o1;
+      const int64_t u = is_a ? t : t - o1;
+      const int nv = is_a ? nva : nvb;
+      const unsigned i = is_a ? occ_a[u / nv] : occ_b[u / nv];
+      const unsigned a = is_a ? vir_a[u % nv] : vir_b[u % nv];
+      const uint64_t same = is_a ? sa : sb, othr = is_a ? sb : sa;
+      const double* eps = is_a ? eps_a : eps_b;
+      double h_el = ldg(A.I.T + a + i * n);
+      const double* G = A.I.G + a * n + i * n2;
+      const double* Vr = A.I.Vr + a * n + i * n2;
+      for (uint64_t s = same; s; s &= s - 1) h_el += ldg(G + lsb64(s));
+      for (uint64_t s = othr; s; s &= s - 1) h_el += ldg(Vr + lsb64(s));
+      if (!(fabs(coeff * h_el) < A.tol)) {
+        const double sign = sx_sign(same, a, i);
+        h_el *= sign;
+        const double h_diag = root + eps[a] - eps[i] - G2_(a, i) - G2_(i, a);
+        const uint64_t ex = same ^ (uint64_t(1) << i) ^ (uint64_t(1) << a);
+        if (is_a) ea = ex; else eb = ex;
+        cmv = coeff * h_el;
+        hdv = A.E0 - h_diag;
+        emit = true;
+      }
+    } else if (t < o4) {
+      // ---- same-spin double, alpha (t < o3) or beta
+      const bool is_a = t < o3;
+      const int64_t u = is_a ? t - o2 : t - o3;
+      const int npv = is_a ? npv_a : npv_b;
+      const unsigned short po = is_a ? po_a[u / npv] : po_b[u / npv];
+      const unsigned short pv = is_a ? pv_a[u % npv] : pv_b[u % npv];
+      const unsigned i = is_a ? occ_a[po >> 8] : occ_b[po >> 8];
+      const unsigned j = is_a ? occ_a[po & 0xFF] : occ_b[po & 0xFF];
+      const unsigned a = is_a ? vir_a[pv >> 8] : vir_b[pv >> 8];
+      const unsigned b = is_a ? vir_a[pv & 0xFF] : vir_b[pv & 0xFF];
+      const uint64_t same = is_a ? sa : sb;
+      const double* eps = is_a ? eps_a : eps_b;
+      const double V_aibj = ldg(A.I.V + (a + i * n) * n2 + (b + j * n));
+      const double V_ajbi = ldg(A.I.V + (a + j * n) * n2 + (b + i * n));
+      const double G_aibj = V_aibj - V_ajbi;
+      if (!(fabs(coeff * G_aibj) < A.tol)) {
+        const uint64_t full_ex = (uint64_t(1) << i) | (uint64_t(1) << j) | (uint64_t(1) << a) | (uint64_t(1) << b);
+        const uint64_t ex_spin = same ^ full_ex;
+        unsigned x1, y1, x2, y2;
+        double sign;
+        dx_sign_indices(same, ex_spin, full_ex, x1, y1, x2, y2, sign);
+        const double h_el = sign * G_aibj;
+        const double h_diag = root + eps[a] + eps[b] - eps[i] - eps[j] + G2_(i, j) + G2_(j, i) +
+                              G2_(a, b) + G2_(b, a) - G2_(a, i) - G2_(i, a) - G2_(b, i) - G2_(i, b) -
+                              G2_(a, j) - G2_(j, a) - G2_(b, j) - G2_(j, b);
+        if (is_a) ea = ex_spin; else eb = ex_spin;
+        cmv = coeff * h_el;
+        hdv = A.E0 - h_diag;
+        emit = true;
+      }
+    } else if (t < o5) {
+      // ---- opposite-spin double
+      const int64_t u = t - o4;
+      const int64_t ua = u / nSb, ub = u % nSb;
+      const unsigned i = occ_a[ua / nva], a = vir_a[ua % nva];
+      const unsigned j = occ_b[ub / nvb], b = vir_b[ub % nvb];
+      const double V_aibj = ldg(A.I.V + a + i * n + (b + j * n) * n2);
+      if (!(fabs(coeff * V_aibj) < A.tol)) {
+        const double sign_a = sx_sign(sa, a, i);
+        const double sign_b = sx_sign(sb, b, j);
+        const double sign = sign_a * sign_b;
+        const double h_el = sign * V_aibj;
+        const double h_diag = root + eps_a[a] + eps_b[b] - eps_a[i] - eps_b[j] + V2_(i, j) + V2_(a, b) -
+                              G2_(a, i) - G2_(i, a) - G2_(b, j) - G2_(j, b) - V2_(a, j) - V2_(i, b);
+        ea = sa ^ (uint64_t(1) << i) ^ (uint64_t(1) << a);
+        eb = sb ^ (uint64_t(1) << j) ^ (uint64_t(1) << b);
+        cmv = coeff * h_el;
+        hdv = A.E0 - h_diag;
+        emit = true;
+      }
+    } else {
+      // ---- the core determinant itself: infinite score marks it for removal
+      cmv = INFINITY;
+      hdv = 1.0;
+      emit = true;
+    }
+    if (emit) {
+      if (FILL) {
+        const int64_t pos = base + atomicAdd(&s_cnt, 1);
+        if (A.packed) A.key[pos] = (eb << 32) | ea;
+        else { A.key[pos] = ea; A.key2[pos] = eb; }
+        A.cm[pos] = cmv;
+        A.hd[pos] = hdv;
+      } else {
+        ++mycount;
+      }
+    }
+  }
+  if (!FILL) {
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) mycount += __shfl_down_sync(0xffffffffu, mycount, d);
+    if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5] = mycount;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      int s = 0;
+      for (int k = 0; k < GEN_THREADS / 32; ++k) s += s_red[k];
+      A.count[c] = s;
+    }
+  }
+}
+#undef G2_
+#undef V2_
+
+__global__ void k_gather_u64(const uint64_t* __restrict__ src, const uint32_t* __restrict__ idx,
+                             int64_t n, uint64_t* __restrict__ dst) {
+  const int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i < n) dst[i] = src[idx[i]];
+}
+// head flags of equal-key segments (two-word keys supported)
+__global__ void k_seg_flags(const uint64_t* __restrict__ k1, const uint64_t* __restrict__ k2,
+                            int64_t n, int32_t* __restrict__ flag) {
+  const int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  bool head = (i == 0) || (k1[i] != k1[i - 1]);
+  if (!head && k2) head = k2[i] != k2[i - 1];
+  flag[i] = head ? 1 : 0;
+}
+// one thread per segment head: sequential (parent-ordered) accumulation
+__global__ void k_seg_accumulate(const uint64_t* __restrict__ k1, const uint64_t* __restrict__ k2,
+                                 const uint32_t* __restrict__ idx, const int32_t* __restrict__ flag,
+                                 const int64_t* __restrict__ seg_of, int64_t n,
+                                 const double* __restrict__ cm, const double* __restrict__ hd,
+                                 uint64_t* __restrict__ sk1, uint64_t* __restrict__ sk2,
+                                 double* __restrict__ scm, double* __restrict__ shd) {
+  const int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= n || !flag[i]) return;
+  const int64_t s = seg_of[i];
+  double acc = cm[idx[i]];
+  for (int64_t j = i + 1; j < n && !flag[j]; ++j) acc += cm[idx[j]];
+  sk1[s] = k1[i];
+  if (sk2) sk2[s] = k2[i];
+  scm[s] = acc;
+  shd[s] = hd[idx[i]];
+}
+// candidate filter: finite rv and |rv| > prune tol
+__global__ void k_score(const double* __restrict__ scm, const double* __restrict__ shd, int64_t n,
+                        double prune, int32_t* __restrict__ keep, double* __restrict__ score) {
+  const int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const double rv = scm[i] / shd[i];
+  const double a = fabs(rv);
+  const bool k = (a > prune) && !isinf(rv);
+  keep[i] = k ? 1 : 0;
+  score[i] = k ? a : 0.0;
+}
+__global__ void k_compact(const int32_t* __restrict__ keep, const int64_t* __restrict__ pos, int64_t n,
+                          const uint64_t* __restrict__ sk1, const uint64_t* __restrict__ sk2,
+                          const double* __restrict__ score, uint64_t* __restrict__ ok1,
+                          uint64_t* __restrict__ ok2, double* __restrict__ oscore) {
+  const int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= n || !keep[i]) return;
+  const int64_t p = pos[i];
+  ok1[p] = sk1[i];
+  if (ok2) ok2[p] = sk2[i];
+  if (oscore) oscore[p] = score[i];
+}
+__global__ void k_keep_ge(const double* __restrict__ score, int64_t n, double kth,
+                          int32_t* __restrict__ keep) {
+  const int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i < n) keep[i] = score[i] >= kth ? 1 : 0;
+}
+__global__ void k_max_below(const double* __restrict__ score, int64_t n, double kth,
+                            unsigned long long* __restrict__ out) {
+  const int64_t stride = int64_t(gridDim.x) * blockDim.x;
+  unsigned long long best = 0;
+  for (int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += stride) {
+    const double s = score[i];
+    if (s < kth) {
+      const unsigned long long b = (unsigned long long)__double_as_longlong(s);
+      best = b > best ? b : best;
+    }
+  }
+  atomicMax(out, best);
+}
+
+unsigned grid1d(int64_t n, int threads = 256) { return unsigned((n + threads - 1) / threads); }
+
+}  // namespace
+
+int asci_search(b2ci_ctx* ctx, const b2ci_asci_search_opts* o, const uint64_t* core_words, int wpd,
+                const double* coeffs, int64_t nc, double E0, uint64_t* out_words, int64_t cap,
+                int64_t* n_out, double* stats, uint64_t* cand_words, double* cand_cm,
+                double* cand_hd, int64_t* cand_n, bool candidates_only) {
+  if (!ctx->ints_dev) throw Error("b2ci_asci_search: integrals not uploaded");
+  if (!o || !core_words || !coeffs || nc < 1) throw Error("b2ci_asci_search: bad arguments");
+  if (wpd != 1 && wpd != 2) throw Error("b2ci_asci_search: words_per_det must be 1 or 2");
+  const int n = ctx->norb;
+  if (wpd == 1 && n > 32) throw Error("b2ci_asci_search: wfn_t<64> holds at most 32 orbitals per spin");
+  cudaStream_t st = ctx->stream;
+  auto& T = ctx->timers;
+  T["asci_search.PAIR_DUR"] = T["asci_search.SORT_ACC_DUR"] = T["asci_search.TOPK_DUR"] = 0.;
+
+  // the reference insists on spin-sorted core determinants (determinant_search.hpp:363-364)
+  for (int64_t i = 1; i < nc; ++i) {
+    uint64_t a0, b0, a1, b1;
+    if (wpd == 1) { a0 = core_words[i - 1] & 0xFFFFFFFFull; b0 = core_words[i - 1] >> 32; a1 = core_words[i] & 0xFFFFFFFFull; b1 = core_words[i] >> 32; }
+    else { a0 = core_words[2 * i - 2]; b0 = core_words[2 * i - 1]; a1 = core_words[2 * i]; b1 = core_words[2 * i + 1]; }
+    if (a1 < a0 || (a1 == a0 && b1 < b0)) throw Error("ASCI Search Only Works with Sorted Wfns");
+  }
+
+  b2ci_dets core;
+  void dets_from_words(b2ci_ctx*, const uint64_t*, int, int64_t, b2ci_dets*);
+  dets_from_words(ctx, core_words, wpd, nc, &core);
+  DevBuf<uint64_t> ca_own, cb_own;  // adopt for RAII
+  ca_own.p = core.alpha; ca_own.n = nc;
+  cb_own.p = core.beta; cb_own.n = nc;
+  DevBuf<double> dcoeff(nc), eps_a(size_t(nc) * n), eps_b(size_t(nc) * n), root(nc);
+  B2_CUDA(cudaMemcpyAsync(dcoeff, coeffs, size_t(nc) * 8, cudaMemcpyHostToDevice, st));
+
+  // Keys are the wfn_t<64> word itself (beta << 32 | alpha): numeric order == bitset_less.
+  // Two-word keys (32 < norb <= 64, wfn_t<128>) need a second sort phase that is not part of
+  // this build; the H build and Davidson paths have no such limit.
+  if (n > 32) throw Error("b2ci_asci_search: norb > 32 (wfn_t<128> keys) is not supported by this build");
+  const bool packed = true;
+  int64_t M = 0;
+  DevBuf<uint64_t> key, key2;
+  DevBuf<double> cm, hd;
+  {
+    ScopedTimer t(ctx, "asci_search.PAIR_DUR");
+    k_core_pre<<<grid1d(nc * n), 256, 0, st>>>(ctx->ints, core.alpha, core.beta, nc, eps_a, eps_b, root);
+    ctx->launches++;
+    B2_CHECK_LAUNCH();
+    GenArgs A;
+    A.I = ctx->ints;
+    A.ca = core.alpha; A.cb = core.beta; A.coeff = dcoeff;
+    A.eps_a = eps_a; A.eps_b = eps_b; A.root = root;
+    A.E0 = E0; A.tol = o->h_el_tol; A.just_singles = o->just_singles;
+    A.packed = packed ? 1 : 0;
+    DevBuf<int32_t> count(nc);
+    DevBuf<int64_t> base(nc + 1);
+    A.count = count; A.base = nullptr; A.key = nullptr; A.key2 = nullptr; A.cm = nullptr; A.hd = nullptr;
+    k_generate<false><<<unsigned(nc), GEN_THREADS, 0, st>>>(A);
+    ctx->launches++;
+    B2_CHECK_LAUNCH();
+    exclusive_scan_i32_to_i64(ctx, count, base, nc);
+    B2_CUDA(cudaMemcpyAsync(&M, base.p + nc, 8, cudaMemcpyDeviceToHost, st));
+    B2_CUDA(cudaStreamSynchronize(st));
+    if (M >= (int64_t(1) << 32)) throw Error("b2ci_asci_search: more than 2^32 contributions in one batch");
+    size_t free_b = 0, total_b = 0;
+    B2_CUDA(cudaMemGetInfo(&free_b, &total_b));
+    const size_t need = size_t(M) * (packed ? 56 : 80);
+    if (need > free_b)
+      throw Error("b2ci_asci_search: " + std::to_string(M) + " contributions need " +
+                  std::to_string(need >> 20) + " MiB of device memory, " + std::to_string(free_b >> 20) + " MiB free");
+    key.alloc(M);
+    if (!packed) key2.alloc(M);
+    cm.alloc(M);
+    hd.alloc(M);
+    A.count = nullptr; A.base = base; A.key = key; A.key2 = packed ? nullptr : key2.p; A.cm = cm; A.hd = hd;
+    k_generate<true><<<unsigned(nc), GEN_THREADS, 0, st>>>(A);
+    ctx->launches++;
+    B2_CHECK_LAUNCH();
+    B2_CUDA(cudaStreamSynchronize(st));
+  }
+
+  // ---- sort + accumulate
+  int64_t nseg = 0;
+  DevBuf<uint64_t> sk1, sk2;
+  DevBuf<double> scm, shd;
+  {
+    ScopedTimer t(ctx, "asci_search.SORT_ACC_DUR");
+    DevBuf<uint64_t> kalt(M);
+    DevBuf<uint32_t> idx(M), idx_alt(M);
+    iota_u32(ctx, idx, M);
+    const int ndig = (n + 7) / 8;
+    std::vector<int> shifts;
+    if (packed) {
+      for (int d = 0; d < ndig; ++d) shifts.push_back(8 * d);        // alpha bits
+      for (int d = 0; d < ndig; ++d) shifts.push_back(32 + 8 * d);   // beta bits (high half)
+      radix_sort_pairs(ctx, key, kalt, idx, idx_alt, M, shifts);
+    }
+    DevBuf<int32_t> flag(M);
+    DevBuf<int64_t> seg_of(M + 1);
+    k_seg_flags<<<grid1d(M), 256, 0, st>>>(key, nullptr, M, flag);
+    ctx->launches++;
+    B2_CHECK_LAUNCH();
+    exclusive_scan_i32_to_i64(ctx, flag, seg_of, M);
+    B2_CUDA(cudaMemcpyAsync(&nseg, seg_of.p + M, 8, cudaMemcpyDeviceToHost, st));
+    B2_CUDA(cudaStreamSynchronize(st));
+    sk1.alloc(nseg);
+    scm.alloc(nseg);
+    shd.alloc(nseg);
+    // seg_of[i] (exclusive scan) is the segment id of a head at i
+    k_seg_accumulate<<<grid1d(M), 256, 0, st>>>(key, nullptr, idx, flag, seg_of, M, cm, hd, sk1, nullptr, scm, shd);
+    ctx->launches++;
+    B2_CHECK_LAUNCH();
+    B2_CUDA(cudaStreamSynchronize(st));
+  }
+  key.release(); cm.release(); hd.release();
+
+  auto unpack_keys_to_words = [&](const uint64_t* dk1, int64_t cnt, uint64_t* host_words) {
+    // packed key == wfn_t<64> word; for words_per_det == 2 split into (alpha, beta)
+    std::vector<uint64_t> tmp(cnt);
+    B2_CUDA(cudaMemcpyAsync(tmp.data(), dk1, size_t(cnt) * 8, cudaMemcpyDeviceToHost, st));
+    B2_CUDA(cudaStreamSynchronize(st));
+    if (wpd == 1) memcpy(host_words, tmp.data(), size_t(cnt) * 8);
+    else
+      for (int64_t i = 0; i < cnt; ++i) { host_words[2 * i] = tmp[i] & 0xFFFFFFFFull; host_words[2 * i + 1] = tmp[i] >> 32; }
+  };
+
+  if (candidates_only) {
+    if (cand_n) *cand_n = nseg;
+    if (cand_words) {
+      unpack_keys_to_words(sk1, nseg, cand_words);
+      B2_CUDA(cudaMemcpyAsync(cand_cm, scm, size_t(nseg) * 8, cudaMemcpyDeviceToHost, st));
+      B2_CUDA(cudaMemcpyAsync(cand_hd, shd, size_t(nseg) * 8, cudaMemcpyDeviceToHost, st));
+      B2_CUDA(cudaStreamSynchronize(st));
+    }
+    return 0;
+  }
+
+  // ---- prune, top-k, output
+  int64_t m = 0, nkeep = 0;
+  double kth = 0., below = 0.;
+  DevBuf<uint64_t> sel;
+  {
+    ScopedTimer t(ctx, "asci_search.TOPK_DUR");
+    DevBuf<int32_t> keep(nseg);
+    DevBuf<double> score(nseg);
+    DevBuf<int64_t> pos(nseg + 1);
+    k_score<<<grid1d(nseg), 256, 0, st>>>(scm, shd, nseg, o->rv_prune_tol, keep, score);
+    ctx->launches++;
+    B2_CHECK_LAUNCH();
+    exclusive_scan_i32_to_i64(ctx, keep, pos, nseg);
+    B2_CUDA(cudaMemcpyAsync(&m, pos.p + nseg, 8, cudaMemcpyDeviceToHost, st));
+    B2_CUDA(cudaStreamSynchronize(st));
+    DevBuf<uint64_t> ck(m > 0 ? m : 1);
+    DevBuf<double> cs(m > 0 ? m : 1);
+    if (m) {
+      k_compact<<<grid1d(nseg), 256, 0, st>>>(keep, pos, nseg, sk1, nullptr, score, ck, nullptr, cs);
+      ctx->launches++;
+      B2_CHECK_LAUNCH();
+    }
+    const int64_t top_k = o->ndets_max - nc;
+    nkeep = m;
+    if (o->ndets_max >= nc && m > top_k) {
+      // top_k == 0: the reference's max_element over an empty range lands on element 0 after
+      // nth_element, i.e. the largest score (determinant_search.hpp:1056-1062)
+      kth = select_kth_largest(ctx, cs, m, top_k > 0 ? top_k : 1);
+      DevBuf<int32_t> keep2(m);
+      DevBuf<int64_t> pos2(m + 1);
+      k_keep_ge<<<grid1d(m), 256, 0, st>>>(cs, m, kth, keep2);
+      ctx->launches++;
+      exclusive_scan_i32_to_i64(ctx, keep2, pos2, m);
+      B2_CUDA(cudaMemcpyAsync(&nkeep, pos2.p + m, 8, cudaMemcpyDeviceToHost, st));
+      DevBuf<unsigned long long> mb(1);
+      B2_CUDA(cudaMemsetAsync(mb, 0, 8, st));
+      k_max_below<<<(unsigned)std::max<int64_t>(1, std::min<int64_t>(ctx->sm_count * 4, (m + 255) / 256)), 256, 0, st>>>(cs, m, kth, mb);
+      ctx->launches++;
+      unsigned long long mbh = 0;
+      B2_CUDA(cudaMemcpyAsync(&mbh, mb, 8, cudaMemcpyDeviceToHost, st));
+      B2_CUDA(cudaStreamSynchronize(st));
+      memcpy(&below, &mbh, 8);
+      sel.alloc(nkeep > 0 ? nkeep : 1);
+      if (nkeep) {
+        k_compact<<<grid1d(m), 256, 0, st>>>(keep2, pos2, m, ck, nullptr, nullptr, sel, nullptr, nullptr);
+        ctx->launches++;
+        B2_CHECK_LAUNCH();
+      }
+    } else {
+      sel = std::move(ck);
+    }
+    B2_CUDA(cudaStreamSynchronize(st));
+  }
+  if (stats) {
+    stats[0] = double(M); stats[1] = double(nseg); stats[2] = kth; stats[3] = below; stats[4] = double(nkeep);
+  }
+  const int64_t total = nkeep + nc;
+  if (n_out) *n_out = total;
+  if (total > cap) throw Error("b2ci_asci_search: output capacity " + std::to_string(cap) + " < " + std::to_string(total), 4);
+  if (nkeep) unpack_keys_to_words(sel, nkeep, out_words);
+  memcpy(out_words + size_t(nkeep) * wpd, core_words, size_t(nc) * wpd * 8);
+  return 0;
+}
+
+}  // namespace b2ci

@@ -1,0 +1,178 @@
+// Shared declarations of the b2ci CUDA library (sm_100a). Internal header.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <map>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "../../include/b2ci.h"
+
+namespace b2ci {
+
+void set_error(const std::string& msg);
+
+struct Error : std::runtime_error {
+  int code;
+  explicit Error(const std::string& m, int c = 1) : std::runtime_error(m), code(c) {}
+};
+
+#define B2_CUDA(expr)                                                                    \
+  do {                                                                                   \
+    cudaError_t _e = (expr);                                                             \
+    if (_e != cudaSuccess)                                                               \
+      throw ::b2ci::Error(std::string(#expr) + ": " + cudaGetErrorString(_e) + " (" +    \
+                          __FILE__ + ":" + std::to_string(__LINE__) + ")");              \
+  } while (0)
+
+#define B2_CHECK_LAUNCH() B2_CUDA(cudaGetLastError())
+
+// Integral tables on the device, one contiguous allocation so the small ones can be staged
+// into shared memory with a single bulk copy:
+//   [ T n^2 | G2_red n^2 | V2_red n^2 | G_red n^3 | V_red n^3 | V n^4 ]
+struct IntsView {
+  int n;
+  const double* T;
+  const double* G2;
+  const double* V2;
+  const double* G;   // G_red(k,i,j) at k + i n + j n^2
+  const double* Vr;  // V_red(k,i,j)
+  const double* V;   // (pq|rs) at p + q n + r n^2 + s n^3
+};
+
+inline size_t ints_small_doubles(int n) {  // T, G2, V2, G_red, V_red
+  size_t n2 = size_t(n) * n;
+  return 3 * n2 + 2 * n2 * n;
+}
+inline size_t ints_total_doubles(int n) {
+  size_t n2 = size_t(n) * n;
+  return ints_small_doubles(n) + n2 * n2;
+}
+inline IntsView make_view(int n, const double* base) {
+  size_t n2 = size_t(n) * n, n3 = n2 * n;
+  IntsView v;
+  v.n = n;
+  v.T = base;
+  v.G2 = base + n2;
+  v.V2 = base + 2 * n2;
+  v.G = base + 3 * n2;
+  v.Vr = base + 3 * n2 + n3;
+  v.V = base + 3 * n2 + 2 * n3;
+  return v;
+}
+
+struct EventTimer {
+  cudaEvent_t a = nullptr, b = nullptr;
+};
+
+struct NcclApi;  // comm.cu
+
+}  // namespace b2ci
+
+struct b2ci_ctx {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  int sm_count = 148;
+  int norb = 0;
+  double* ints_dev = nullptr;  // layout above
+  b2ci::IntsView ints{};
+  std::vector<double> ints_host;  // same layout, host copy (host-side evaluation / ASCI driver)
+  int64_t launches = 0;
+  std::map<std::string, double> timers;
+  // multi-GPU
+  void* nccl_comm = nullptr;
+  int rank = 0, nranks = 1;
+};
+
+struct b2ci_dets {
+  int64_t n = 0;
+  uint64_t* alpha = nullptr;  // device
+  uint64_t* beta = nullptr;   // device
+};
+
+struct b2ci_csr {
+  int64_t nrows = 0, ncols = 0, nnz = 0, row_begin = 0;
+  int64_t* rowptr = nullptr;  // device, nrows + 1, local offsets (rowptr[0] == 0)
+  int32_t* colind = nullptr;  // device, global column indices
+  double* nzval = nullptr;    // device
+};
+
+namespace b2ci {
+
+// RAII device buffer
+template <typename T>
+struct DevBuf {
+  T* p = nullptr;
+  size_t n = 0;
+  DevBuf() = default;
+  explicit DevBuf(size_t count) { alloc(count); }
+  DevBuf(const DevBuf&) = delete;
+  DevBuf& operator=(const DevBuf&) = delete;
+  DevBuf(DevBuf&& o) noexcept : p(o.p), n(o.n) { o.p = nullptr; o.n = 0; }
+  DevBuf& operator=(DevBuf&& o) noexcept {
+    if (this != &o) { release(); p = o.p; n = o.n; o.p = nullptr; o.n = 0; }
+    return *this;
+  }
+  ~DevBuf() { release(); }
+  void alloc(size_t count) {
+    release();
+    n = count;
+    if (count) {
+      cudaError_t e = cudaMalloc((void**)&p, count * sizeof(T));
+      if (e != cudaSuccess) {
+        p = nullptr;
+        throw Error("cudaMalloc of " + std::to_string(count * sizeof(T)) + " bytes failed: " +
+                    cudaGetErrorString(e));
+      }
+    }
+  }
+  void release() {
+    if (p) cudaFree(p);
+    p = nullptr;
+    n = 0;
+  }
+  T* take() { T* q = p; p = nullptr; n = 0; return q; }
+  operator T*() const { return p; }
+};
+
+struct ScopedTimer {  // CUDA-event timing of a phase on the context stream
+  b2ci_ctx* ctx;
+  std::string name;
+  cudaEvent_t a, b;
+  bool accumulate;
+  ScopedTimer(b2ci_ctx* c, const char* nm, bool acc = false) : ctx(c), name(nm), accumulate(acc) {
+    cudaEventCreate(&a);
+    cudaEventCreate(&b);
+    cudaEventRecord(a, ctx->stream);
+  }
+  ~ScopedTimer() {
+    cudaEventRecord(b, ctx->stream);
+    cudaEventSynchronize(b);
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, a, b);
+    if (accumulate) ctx->timers[name] += ms; else ctx->timers[name] = ms;
+    cudaEventDestroy(a);
+    cudaEventDestroy(b);
+  }
+};
+
+// scan.cu : out has n + 1 entries, out[n] = total
+void exclusive_scan_i32_to_i64(b2ci_ctx* ctx, const int32_t* in, int64_t* out, int64_t n);
+void exclusive_scan_i32(b2ci_ctx* ctx, const int32_t* in, int32_t* out, int64_t n);
+
+// spmv.cu
+void spmv_launch(b2ci_ctx* ctx, const b2ci_csr* m, const double* x, double* y);
+
+// eig.cpp-ish (davidson.cu): symmetric eigensolver, lower triangle, ascending
+void sym_eig_lower(int n, double* A, int lda, double* W);
+
+// comm.cu
+void comm_allgather_rows(b2ci_ctx* ctx, const double* local, double* full,
+                         const std::vector<int64_t>& row_offsets);
+void comm_allreduce_sum(b2ci_ctx* ctx, double* dev_buf, int64_t n);
+void comm_allreduce_sum_i64_host(b2ci_ctx* ctx, int64_t* host_vals, int n);
+void comm_allgather_i64_host(b2ci_ctx* ctx, int64_t local, std::vector<int64_t>& all);
+
+}  // namespace b2ci

@@ -1,0 +1,519 @@
+// Single-root Davidson eigensolver with all O(N) work on the device.
+//
+// Replaces macis::davidson (external/macis/include/macis/solvers/davidson.hpp:259-372),
+// gram_schmidt (:185-238), lobpcgxx::rayleigh_ritz (external/macis/src/lobpcgxx/include/
+// lobpcgxx/rayleigh_ritz.hpp:70-77), diagonal_guess (:106-113) and the guess policy of
+// serial_selected_ci_diag (solvers/selected_ci_diag.hpp:111-158). Semantics kept: no
+// restart, max_m = min(max_m, N), CGS2 with the canonical-basis fallback, diagonal
+// preconditioner with the 1e-12 denominator clamp, non-convergence is an error.
+//
+// Differences that do not change the mathematics: the Rayleigh-Ritz matrix V^T A V is
+// extended by one row per iteration (O(N k)) instead of being recomputed (O(N k^2)); the
+// k x k symmetric eigenproblem is solved on the host (Householder + implicit QL) and
+// replicated on every rank instead of rank-0 + broadcast (davidson.hpp:501-531).
+// Row-sharded operation (one process per GPU): V/AV hold the local rows only, the trial
+// vector is all-gathered before each sigma and every inner product is all-reduced.
+#include <cmath>
+#include <cstring>
+
+#include "common.cuh"
+
+namespace b2ci {
+
+// ---------------------------------------------------------------- host eigen solver
+// Symmetric eigenproblem, lower triangle of column-major A (lda), eigenvalues ascending in W,
+// eigenvectors returned in the columns of A. Householder tridiagonalisation followed by the
+// implicit QL algorithm (the classic EISPACK tred2/tql2 pair).
+void sym_eig_lower(int n, double* A, int lda, double* W) {
+  if (n <= 0) return;
+  std::vector<double> Vm(size_t(n) * n), d(n), e(n);
+  auto V = [&](int i, int j) -> double& { return Vm[size_t(i) * n + j]; };
+  for (int j = 0; j < n; ++j)
+    for (int i = j; i < n; ++i) V(i, j) = V(j, i) = A[i + size_t(j) * lda];
+  // --- tridiagonalise
+  for (int j = 0; j < n; ++j) d[j] = V(n - 1, j);
+  for (int i = n - 1; i > 0; --i) {
+    double scale = 0., h = 0.;
+    for (int k = 0; k < i; ++k) scale += std::fabs(d[k]);
+    if (scale == 0.) {
+      e[i] = d[i - 1];
+      for (int j = 0; j < i; ++j) { d[j] = V(i - 1, j); V(i, j) = 0.; V(j, i) = 0.; }
+    } else {
+      for (int k = 0; k < i; ++k) { d[k] /= scale; h += d[k] * d[k]; }
+      double f = d[i - 1];
+      double g = std::sqrt(h);
+      if (f > 0) g = -g;
+      e[i] = scale * g;
+      h -= f * g;
+      d[i - 1] = f - g;
+      for (int j = 0; j < i; ++j) e[j] = 0.;
+      for (int j = 0; j < i; ++j) {
+        f = d[j];
+        V(j, i) = f;
+        g = e[j] + V(j, j) * f;
+        for (int k = j + 1; k <= i - 1; ++k) { g += V(k, j) * d[k]; e[k] += V(k, j) * f; }
+        e[j] = g;
+      }
+      f = 0.;
+      for (int j = 0; j < i; ++j) { e[j] /= h; f += e[j] * d[j]; }
+      const double hh = f / (h + h);
+      for (int j = 0; j < i; ++j) e[j] -= hh * d[j];
+      for (int j = 0; j < i; ++j) {
+        f = d[j];
+        g = e[j];
+        for (int k = j; k <= i - 1; ++k) V(k, j) -= (f * e[k] + g * d[k]);
+        d[j] = V(i - 1, j);
+        V(i, j) = 0.;
+      }
+    }
+    d[i] = h;
+  }
+  for (int i = 0; i < n - 1; ++i) {
+    V(n - 1, i) = V(i, i);
+    V(i, i) = 1.;
+    const double h = d[i + 1];
+    if (h != 0.) {
+      for (int k = 0; k <= i; ++k) d[k] = V(k, i + 1) / h;
+      for (int j = 0; j <= i; ++j) {
+        double g = 0.;
+        for (int k = 0; k <= i; ++k) g += V(k, i + 1) * V(k, j);
+        for (int k = 0; k <= i; ++k) V(k, j) -= g * d[k];
+      }
+    }
+    for (int k = 0; k <= i; ++k) V(k, i + 1) = 0.;
+  }
+  for (int j = 0; j < n; ++j) { d[j] = V(n - 1, j); V(n - 1, j) = 0.; }
+  V(n - 1, n - 1) = 1.;
+  e[0] = 0.;
+  // --- implicit QL
+  for (int i = 1; i < n; ++i) e[i - 1] = e[i];
+  e[n - 1] = 0.;
+  double f = 0., tst1 = 0.;
+  const double eps = std::ldexp(1.0, -52);
+  for (int l = 0; l < n; ++l) {
+    tst1 = std::fmax(tst1, std::fabs(d[l]) + std::fabs(e[l]));
+    int m = l;
+    while (m < n) {
+      if (std::fabs(e[m]) <= eps * tst1) break;
+      ++m;
+    }
+    if (m > l) {
+      int iter = 0;
+      do {
+        ++iter;
+        double g = d[l];
+        double p = (d[l + 1] - g) / (2. * e[l]);
+        double r = std::hypot(p, 1.);
+        if (p < 0) r = -r;
+        d[l] = e[l] / (p + r);
+        d[l + 1] = e[l] * (p + r);
+        const double dl1 = d[l + 1];
+        double h = g - d[l];
+        for (int i = l + 2; i < n; ++i) d[i] -= h;
+        f += h;
+        p = d[m];
+        double c = 1., c2 = c, c3 = c;
+        const double el1 = e[l + 1];
+        double s = 0., s2 = 0.;
+        for (int i = m - 1; i >= l; --i) {
+          c3 = c2;
+          c2 = c;
+          s2 = s;
+          g = c * e[i];
+          h = c * p;
+          r = std::hypot(p, e[i]);
+          e[i + 1] = s * r;
+          s = e[i] / r;
+          c = p / r;
+          p = c * d[i] - s * g;
+          d[i + 1] = h + s * (c * g + s * d[i]);
+          for (int k = 0; k < n; ++k) {
+            h = V(k, i + 1);
+            V(k, i + 1) = s * V(k, i) + c * h;
+            V(k, i) = c * V(k, i) - s * h;
+          }
+        }
+        p = -s * s2 * c3 * el1 * e[l] / dl1;
+        e[l] = s * p;
+        d[l] = c * p;
+      } while (std::fabs(e[l]) > eps * tst1 && iter < 200);
+    }
+    d[l] += f;
+    e[l] = 0.;
+  }
+  // --- ascending order
+  for (int i = 0; i < n - 1; ++i) {
+    int k = i;
+    double p = d[i];
+    for (int j = i + 1; j < n; ++j)
+      if (d[j] < p) { k = j; p = d[j]; }
+    if (k != i) {
+      d[k] = d[i];
+      d[i] = p;
+      for (int j = 0; j < n; ++j) std::swap(V(j, i), V(j, k));
+    }
+  }
+  for (int j = 0; j < n; ++j) {
+    W[j] = d[j];
+    for (int i = 0; i < n; ++i) A[i + size_t(j) * lda] = V(i, j);
+  }
+}
+
+namespace {
+
+constexpr int DOT_THREADS = 256;
+constexpr int DOT_CG = 8;  // columns per register group
+
+// partial[b*k + j] = sum over the rows of CTA b of A[i + j*ld] * w[i]
+__global__ void __launch_bounds__(DOT_THREADS)
+k_multi_dot(int64_t N, int k, const double* __restrict__ A, int64_t ld,
+            const double* __restrict__ w, double* __restrict__ partial) {
+  __shared__ double red[DOT_CG][DOT_THREADS / 32];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int64_t stride = int64_t(gridDim.x) * DOT_THREADS;
+  for (int j0 = 0; j0 < k; j0 += DOT_CG) {
+    double acc[DOT_CG];
+#pragma unroll
+    for (int c = 0; c < DOT_CG; ++c) acc[c] = 0.;
+    const int nc = min(DOT_CG, k - j0);
+    for (int64_t i = int64_t(blockIdx.x) * DOT_THREADS + threadIdx.x; i < N; i += stride) {
+      const double wi = w[i];
+#pragma unroll
+      for (int c = 0; c < DOT_CG; ++c)
+        if (c < nc) acc[c] = fma(A[i + int64_t(j0 + c) * ld], wi, acc[c]);
+    }
+#pragma unroll
+    for (int c = 0; c < DOT_CG; ++c) {
+      double v = acc[c];
+#pragma unroll
+      for (int d = 16; d > 0; d >>= 1) v += __shfl_down_sync(0xffffffffu, v, d);
+      if (lane == 0) red[c][warp] = v;
+    }
+    __syncthreads();
+    if (threadIdx.x < nc) {
+      double s = 0.;
+#pragma unroll
+      for (int wv = 0; wv < DOT_THREADS / 32; ++wv) s += red[threadIdx.x][wv];
+      partial[int64_t(blockIdx.x) * k + j0 + threadIdx.x] = s;
+    }
+    __syncthreads();
+  }
+}
+__global__ void k_reduce_partials(int nblocks, int k, const double* __restrict__ partial,
+                                  double* __restrict__ out) {
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= k) return;
+  double s = 0.;
+  for (int b = 0; b < nblocks; ++b) s += partial[int64_t(b) * k + j];
+  out[j] = s;
+}
+// w[i] -= sum_j V[i + j*ld] * h[j]
+__global__ void __launch_bounds__(256)
+k_project_out(int64_t N, int k, const double* __restrict__ V, int64_t ld,
+              const double* __restrict__ h, double* __restrict__ w) {
+  extern __shared__ double hs[];
+  for (int j = threadIdx.x; j < k; j += blockDim.x) hs[j] = h[j];
+  __syncthreads();
+  const int64_t stride = int64_t(gridDim.x) * blockDim.x;
+  for (int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < N; i += stride) {
+    double s = 0.;
+    for (int j = 0; j < k; ++j) s = fma(V[i + int64_t(j) * ld], hs[j], s);
+    w[i] -= s;
+  }
+}
+__global__ void k_scale(int64_t N, double a, double* __restrict__ w) {
+  const int64_t stride = int64_t(gridDim.x) * blockDim.x;
+  for (int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < N; i += stride) w[i] *= a;
+}
+__global__ void k_set_unit(int64_t N, int64_t row0, int64_t idx, double* __restrict__ w) {
+  const int64_t stride = int64_t(gridDim.x) * blockDim.x;
+  for (int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < N; i += stride)
+    w[i] = (row0 + i == idx) ? 1.0 : 0.0;
+}
+// X = V c ; R = AV c - lam X ; partial ||R||^2 ; W = -R / clamp(D - lam)
+__global__ void __launch_bounds__(256)
+k_residual(int64_t N, int k, const double* __restrict__ V, const double* __restrict__ AV,
+           int64_t ld, const double* __restrict__ c, double lam, const double* __restrict__ D,
+           double* __restrict__ X, double* __restrict__ Wout, double* __restrict__ partial) {
+  extern __shared__ double cs[];
+  __shared__ double red[8];
+  for (int j = threadIdx.x; j < k; j += blockDim.x) cs[j] = c[j];
+  __syncthreads();
+  const int64_t stride = int64_t(gridDim.x) * blockDim.x;
+  double nrm = 0.;
+  for (int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < N; i += stride) {
+    double x = 0., ax = 0.;
+    for (int j = 0; j < k; ++j) {
+      x = fma(V[i + int64_t(j) * ld], cs[j], x);
+      ax = fma(AV[i + int64_t(j) * ld], cs[j], ax);
+    }
+    const double r = ax - lam * x;
+    nrm = fma(r, r, nrm);
+    double denom = D[i] - lam;
+    if (fabs(denom) < 1e-12) denom = (denom >= 0) ? 1e-12 : -1e-12;
+    X[i] = x;
+    Wout[i] = -r / denom;
+  }
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) nrm += __shfl_down_sync(0xffffffffu, nrm, d);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = nrm;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double s = 0.;
+    for (int wv = 0; wv < 8; ++wv) s += red[wv];
+    partial[blockIdx.x] = s;
+  }
+}
+// extract_diagonal_elements: first entry of the row whose column is the row's global index
+__global__ void k_diag(int64_t nrows, int64_t row_begin, const int64_t* __restrict__ rowptr,
+                       const int32_t* __restrict__ colind, const double* __restrict__ nzval,
+                       double* __restrict__ D) {
+  const int64_t r = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (r >= nrows) return;
+  const int64_t g = row_begin + r;
+  double d = 0.;
+  for (int64_t p = rowptr[r]; p < rowptr[r + 1]; ++p)
+    if (colind[p] == g) { d = nzval[p]; break; }
+  D[r] = d;
+}
+
+struct Work {
+  b2ci_ctx* ctx;
+  int64_t N, ld;
+  int nblocks;
+  DevBuf<double> partial, small;  // small: k-sized device scratch
+  std::vector<double> host_small;
+};
+
+void dots(Work& W, int k, const double* A, const double* w, double* host_out) {
+  b2ci_ctx* ctx = W.ctx;
+  k_multi_dot<<<W.nblocks, DOT_THREADS, 0, ctx->stream>>>(W.N, k, A, W.ld, w, W.partial);
+  ctx->launches++;
+  k_reduce_partials<<<(k + 127) / 128, 128, 0, ctx->stream>>>(W.nblocks, k, W.partial, W.small);
+  ctx->launches++;
+  B2_CHECK_LAUNCH();
+  if (ctx->nranks > 1) comm_allreduce_sum(ctx, W.small, k);
+  if (host_out) {
+    B2_CUDA(cudaMemcpyAsync(host_out, W.small, size_t(k) * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    B2_CUDA(cudaStreamSynchronize(ctx->stream));
+  }
+}
+double norm2(Work& W, const double* w) {
+  double s = 0.;
+  dots(W, 1, w, w, &s);
+  return std::sqrt(s);
+}
+void project(Work& W, int k, const double* V, double* w) {
+  b2ci_ctx* ctx = W.ctx;
+  dots(W, k, V, w, nullptr);  // h stays on the device (W.small)
+  k_project_out<<<W.nblocks, 256, size_t(k) * 8, ctx->stream>>>(W.N, k, V, W.ld, W.small, w);
+  ctx->launches++;
+  B2_CHECK_LAUNCH();
+}
+void scale(Work& W, double a, double* w) {
+  k_scale<<<W.nblocks, 256, 0, W.ctx->stream>>>(W.N, a, w);
+  W.ctx->launches++;
+  B2_CHECK_LAUNCH();
+}
+// gram_schmidt (davidson.hpp:185-238)
+void gram_schmidt(Work& W, int k, const double* V, double* w, int64_t row0, int64_t Nglobal) {
+  const double min_norm = 1e-12;
+  if (k <= 0) {
+    const double nrm = norm2(W, w);
+    if (nrm > min_norm) scale(W, 1. / nrm, w);
+    return;
+  }
+  project(W, k, V, w);
+  project(W, k, V, w);
+  double nrm = norm2(W, w);
+  if (nrm > min_norm) {
+    scale(W, 1. / nrm, w);
+    return;
+  }
+  for (int64_t idx = 0; idx < Nglobal; ++idx) {
+    k_set_unit<<<W.nblocks, 256, 0, W.ctx->stream>>>(W.N, row0, idx, w);
+    W.ctx->launches++;
+    project(W, k, V, w);
+    nrm = norm2(W, w);
+    if (nrm > min_norm) {
+      scale(W, 1. / nrm, w);
+      return;
+    }
+  }
+  throw Error("gram_schmidt: Unable to find orthogonal vector - subspace may already span the entire space");
+}
+
+}  // namespace
+
+void csr_diagonal_dev(b2ci_ctx* ctx, const b2ci_csr* m, double* D_dev) {
+  if (!m->nrows) return;
+  k_diag<<<unsigned((m->nrows + 255) / 256), 256, 0, ctx->stream>>>(m->nrows, m->row_begin, m->rowptr,
+                                                                   m->colind, m->nzval, D_dev);
+  ctx->launches++;
+  B2_CHECK_LAUNCH();
+}
+
+int davidson(b2ci_ctx* ctx, const b2ci_csr* m, int64_t max_m, double tol, double* X_host,
+             int use_guess_policy, int64_t* niter_out, double* eig_out, double* trace) {
+  const int64_t Nloc = m->nrows, N = m->ncols, row0 = m->row_begin;
+  if (!X_host) throw Error("Davidson: No Guess Provided");
+  if (N <= 0) throw Error("Davidson: empty matrix");
+  cudaStream_t st = ctx->stream;
+  auto& T = ctx->timers;
+  T["davidson.OP_DUR"] = T["davidson.RR_DUR"] = T["davidson.RES_DUR"] = T["davidson.GS_DUR"] = 0.;
+  T["davidson.OP_CALLS"] = 0.;
+
+  // row offsets of every rank (rank order tiles [0, N))
+  std::vector<int64_t> row_offsets;
+  if (ctx->nranks > 1) {
+    std::vector<int64_t> counts;
+    comm_allgather_i64_host(ctx, Nloc, counts);
+    row_offsets.assign(ctx->nranks + 1, 0);
+    for (int r = 0; r < ctx->nranks; ++r) row_offsets[r + 1] = row_offsets[r] + counts[r];
+    if (row_offsets[ctx->rank] != row0 || row_offsets[ctx->nranks] != N)
+      throw Error("b2ci_davidson: row blocks of the ranks do not tile [0, ncols) in rank order");
+  } else if (Nloc != N || row0 != 0) {
+    throw Error("b2ci_davidson: matrix is a row block but no communicator was initialised");
+  }
+
+  // diagonal
+  DevBuf<double> D(Nloc > 0 ? Nloc : 1);
+  csr_diagonal_dev(ctx, m, D);
+
+  // guess policy (selected_ci_diag.hpp:128-142)
+  if (use_guess_policy) {
+    double max_c = 0.;
+    for (int64_t i = 0; i < N; ++i) max_c = std::fmax(max_c, std::fabs(X_host[i]));
+    if (!(max_c > 1. / double(N))) {
+      DevBuf<double> Dfull;
+      const double* dsrc = D;
+      if (ctx->nranks > 1) {
+        Dfull.alloc(N);
+        comm_allgather_rows(ctx, D, Dfull, row_offsets);
+        dsrc = Dfull;
+      }
+      std::vector<double> Dh(N);
+      B2_CUDA(cudaMemcpyAsync(Dh.data(), dsrc, size_t(N) * 8, cudaMemcpyDeviceToHost, st));
+      B2_CUDA(cudaStreamSynchronize(st));
+      int64_t mi = 0;
+      for (int64_t i = 1; i < N; ++i)
+        if (Dh[i] < Dh[mi]) mi = i;
+      X_host[mi] = 1.;
+    }
+  }
+
+  max_m = std::min<int64_t>(max_m, N);
+  DevBuf<double> xfull(N);  // gathered trial vector / final X
+  if (N == 1) {
+    X_host[0] = 1.0;
+    DevBuf<double> ax(1);
+    B2_CUDA(cudaMemcpyAsync(xfull, X_host, 8, cudaMemcpyHostToDevice, st));
+    spmv_launch(ctx, m, xfull, ax);
+    double AX = 0.;
+    B2_CUDA(cudaMemcpyAsync(&AX, ax, 8, cudaMemcpyDeviceToHost, st));
+    B2_CUDA(cudaStreamSynchronize(st));
+    *niter_out = 0;
+    *eig_out = AX;
+    return 0;
+  }
+  if (max_m < 1) throw Error("Davidson: max_m must be >= 1");
+
+  Work W;
+  W.ctx = ctx;
+  W.N = Nloc;
+  W.ld = Nloc > 0 ? Nloc : 1;
+  W.nblocks = (int)std::max<int64_t>(1, std::min<int64_t>(int64_t(ctx->sm_count) * 2, (Nloc + 255) / 256));
+  W.partial.alloc(size_t(W.nblocks) * (max_m + 2));
+  W.small.alloc(max_m + 2);
+  const int64_t ld = W.ld;
+
+  // The reference allocates N x (max_m + 1) for V and AV up front (davidson.hpp:293-294).
+  size_t free_b = 0, total_b = 0;
+  B2_CUDA(cudaMemGetInfo(&free_b, &total_b));
+  const size_t need = size_t(ld) * size_t(max_m + 1) * 8 * 2;
+  if (need > free_b)
+    throw Error("Davidson: subspace storage 2 x N x (max_m+1) doubles (" + std::to_string(need >> 20) +
+                " MiB) exceeds free device memory (" + std::to_string(free_b >> 20) + " MiB); lower max_m");
+  DevBuf<double> V(size_t(ld) * (max_m + 1)), AV(size_t(ld) * (max_m + 1));
+  DevBuf<double> cdev(max_m + 2);
+  std::vector<double> C(size_t(max_m + 1) * (max_m + 1), 0.), Cw, LAM(max_m + 1, 0.), crow(max_m + 2);
+
+  auto sigma = [&](const double* v_local, double* av_local) {
+    ScopedTimer t(ctx, "davidson.OP_DUR", true);
+    const double* xin = v_local;
+    if (ctx->nranks > 1) {
+      comm_allgather_rows(ctx, v_local, xfull, row_offsets);
+      xin = xfull;
+    }
+    spmv_launch(ctx, m, xin, av_local);
+    T["davidson.OP_CALLS"] += 1.;
+  };
+
+  // V(:,0) = X (local rows)
+  B2_CUDA(cudaMemcpyAsync(V, X_host + row0, size_t(Nloc) * 8, cudaMemcpyHostToDevice, st));
+  sigma(V, AV);
+  B2_CUDA(cudaMemcpyAsync(V + ld, AV, size_t(Nloc) * 8, cudaMemcpyDeviceToDevice, st));
+  gram_schmidt(W, 1, V, V + ld, row0, N);
+
+  bool converged = false;
+  int64_t iter = 1;
+  double lam = 0.;
+  // C accumulates the lower triangle of V^T A V; row 0 (= V0^T A V0) first
+  dots(W, 1, AV, V, crow.data());
+  C[0] = crow[0];
+  for (int64_t i = 1; i < max_m; ++i, ++iter) {
+    const int k = int(i + 1);
+    sigma(V + i * ld, AV + i * ld);
+    {
+      ScopedTimer t(ctx, "davidson.RR_DUR", true);
+      // new row of the lower triangle: C(i, j) = V_i^T (A V_j), j = 0..i
+      dots(W, k, AV, V + i * ld, crow.data());
+      for (int j = 0; j < k; ++j) C[i + size_t(j) * (max_m + 1)] = crow[j];
+      Cw.assign(size_t(k) * k, 0.);
+      for (int b = 0; b < k; ++b)
+        for (int a = b; a < k; ++a) Cw[a + size_t(b) * k] = C[a + size_t(b) * (max_m + 1)];
+      sym_eig_lower(k, Cw.data(), k, LAM.data());
+      lam = LAM[0];
+      B2_CUDA(cudaMemcpyAsync(cdev, Cw.data(), size_t(k) * 8, cudaMemcpyHostToDevice, st));
+    }
+    double res_nrm;
+    {
+      ScopedTimer t(ctx, "davidson.RES_DUR", true);
+      double* R = V + (i + 1) * ld;
+      k_residual<<<W.nblocks, 256, size_t(k) * 8, st>>>(Nloc, k, V, AV, ld, cdev, lam, D,
+                                                        xfull + row0, R, W.partial);
+      ctx->launches++;
+      k_reduce_partials<<<1, 128, 0, st>>>(W.nblocks, 1, W.partial, W.small);
+      ctx->launches++;
+      B2_CHECK_LAUNCH();
+      if (ctx->nranks > 1) comm_allreduce_sum(ctx, W.small, 1);
+      double s = 0.;
+      B2_CUDA(cudaMemcpyAsync(&s, W.small, 8, cudaMemcpyDeviceToHost, st));
+      B2_CUDA(cudaStreamSynchronize(st));
+      res_nrm = std::sqrt(s);
+    }
+    if (trace) { trace[2 * (i - 1)] = lam; trace[2 * (i - 1) + 1] = res_nrm; }
+    if (res_nrm < tol) { converged = true; break; }
+    {
+      ScopedTimer t(ctx, "davidson.GS_DUR", true);
+      gram_schmidt(W, k, V, V + (i + 1) * ld, row0, N);
+    }
+  }
+  // X (local rows live in xfull + row0) -> host, full vector on every rank
+  if (ctx->nranks > 1) {
+    DevBuf<double> xl(Nloc > 0 ? Nloc : 1);
+    B2_CUDA(cudaMemcpyAsync(xl, xfull + row0, size_t(Nloc) * 8, cudaMemcpyDeviceToDevice, st));
+    comm_allgather_rows(ctx, xl, xfull, row_offsets);
+  }
+  B2_CUDA(cudaMemcpyAsync(X_host, xfull, size_t(N) * 8, cudaMemcpyDeviceToHost, st));
+  B2_CUDA(cudaStreamSynchronize(st));
+  *niter_out = iter;
+  *eig_out = lam;
+  if (!converged) {
+    set_error("Davidson Did Not Converge!");
+    return B2CI_NOT_CONVERGED;
+  }
+  return 0;
+}
+
+}  // namespace b2ci

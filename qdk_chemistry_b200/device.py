@@ -1,0 +1,282 @@
+"""Thin object wrappers over the b2ci C ABI (numpy in / numpy out, device-resident handles).
+
+Everything here forwards to libb2ci.so; no arithmetic happens in Python.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional, Tuple
+
+import numpy as np
+
+from . import _lib
+from ._lib import AsciSearchOpts, B2ciError, check, lib
+
+
+def _p(a):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+def words_per_det_for_norb(norb: int) -> int:
+    """dispatch_by_norb (cpp/src/qdk/chemistry/algorithms/microsoft/macis_base.hpp:80-100)
+    restricted to the widths this build instantiates: wfn_t<64> and wfn_t<128>."""
+    if norb < 32:
+        return 1
+    if norb < 64:
+        return 2
+    raise ValueError("active spaces with 64 or more orbitals need wfn_t<256+>, not built")
+
+
+class Context:
+    """Device + stream + integrals (+ optional NCCL communicator)."""
+
+    def __init__(self, device: int = 0, stream: Optional[int] = None):
+        h = C.c_void_p()
+        check(lib().b2ci_ctx_create(device, C.c_void_p(stream or 0), C.byref(h)))
+        self.h = h
+        self.device = device
+        self.norb = 0
+
+    def close(self):
+        if getattr(self, "h", None):
+            lib().b2ci_ctx_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # -- plumbing
+    def synchronize(self):
+        check(lib().b2ci_ctx_synchronize(self.h))
+
+    @property
+    def launch_count(self) -> int:
+        return lib().b2ci_ctx_launch_count(self.h)
+
+    def timer_ms(self, name: str) -> float:
+        return lib().b2ci_timer_ms(self.h, name.encode())
+
+    @staticmethod
+    def comm_unique_id() -> bytes:
+        buf = (C.c_char * 128)()
+        check(lib().b2ci_comm_unique_id(buf))
+        return bytes(buf)
+
+    def comm_init(self, unique_id: bytes, rank: int, nranks: int):
+        assert len(unique_id) == 128
+        buf = (C.c_char * 128).from_buffer_copy(unique_id)
+        check(lib().b2ci_comm_init(self.h, buf, rank, nranks))
+
+    # -- integrals
+    def upload_integrals(self, norb: int, T: np.ndarray, V: np.ndarray):
+        T = np.ascontiguousarray(T, dtype=np.float64)
+        V = np.ascontiguousarray(V, dtype=np.float64).reshape(-1)
+        if T.size != norb * norb or V.size != norb ** 4:
+            raise ValueError("T must have norb^2 and V norb^4 entries")
+        check(lib().b2ci_integrals_upload(self.h, norb, _p(T), _p(V)))
+        self.norb = norb
+
+    def download_intermediates(self):
+        n = self.norb
+        G, Vr, G2, V2 = np.empty(n ** 3), np.empty(n ** 3), np.empty(n * n), np.empty(n * n)
+        check(lib().b2ci_integrals_download(self.h, _p(G), _p(Vr), _p(G2), _p(V2)))
+        return G, Vr, G2, V2
+
+    # -- determinants
+    def upload_dets(self, words: np.ndarray, words_per_det: int = 1) -> "DetList":
+        w = np.ascontiguousarray(words, dtype=np.uint64)
+        h = C.c_void_p()
+        check(lib().b2ci_dets_upload(self.h, _p(w), words_per_det, w.size // words_per_det,
+                                     C.byref(h)))
+        return DetList(self, h)
+
+    def generate_fci(self, norb: int, nalpha: int, nbeta: int) -> "DetList":
+        h = C.c_void_p()
+        check(lib().b2ci_dets_generate_fci(self.h, norb, nalpha, nbeta, C.byref(h)))
+        return DetList(self, h)
+
+    # -- matrices
+    def hbuild(self, dets: "DetList", h_thresh: float, rows: Optional[Tuple[int, int]] = None
+               ) -> "CsrMatrix":
+        r0, r1 = rows if rows is not None else (0, len(dets))
+        h = C.c_void_p()
+        check(lib().b2ci_hbuild_csr(self.h, dets.h, r0, r1, h_thresh, C.byref(h)))
+        return CsrMatrix(self, h)
+
+    def upload_csr(self, rowptr, colind, nzval) -> "CsrMatrix":
+        rp = np.ascontiguousarray(rowptr, dtype=np.int64)
+        ci = np.ascontiguousarray(colind, dtype=np.int64)
+        nz = np.ascontiguousarray(nzval, dtype=np.float64)
+        h = C.c_void_p()
+        check(lib().b2ci_csr_upload(self.h, rp.size - 1, ci.size, _p(rp), _p(ci), _p(nz),
+                                    C.byref(h)))
+        return CsrMatrix(self, h)
+
+    # -- ASCI search
+    def asci_search(self, core_words: np.ndarray, core_coeffs: np.ndarray, E0: float,
+                    ndets_max: int, h_el_tol: float = 1e-8, rv_prune_tol: float = 1e-8,
+                    just_singles: bool = False, words_per_det: int = 1):
+        cw = np.ascontiguousarray(core_words, dtype=np.uint64)
+        cc = np.ascontiguousarray(core_coeffs, dtype=np.float64)
+        nc = cw.size // words_per_det
+        o = AsciSearchOpts(int(ndets_max), h_el_tol, rv_prune_tol, int(just_singles), 0)
+        cap = int(ndets_max) + nc + 4096
+        stats = np.zeros(8)
+        n_out = C.c_int64(0)
+        while True:
+            out = np.empty(cap * words_per_det, dtype=np.uint64)
+            rc = lib().b2ci_asci_search(self.h, C.byref(o), _p(cw), words_per_det, _p(cc), nc, E0,
+                                        _p(out), cap, C.byref(n_out), _p(stats))
+            if rc == 4 and n_out.value > cap:  # capacity (ties at the cut can exceed ndets_max)
+                cap = n_out.value
+                continue
+            check(rc)
+            return out[: n_out.value * words_per_det].copy(), stats
+
+    def asci_candidates(self, core_words, core_coeffs, E0, h_el_tol=1e-8, just_singles=False,
+                        words_per_det: int = 1):
+        cw = np.ascontiguousarray(core_words, dtype=np.uint64)
+        cc = np.ascontiguousarray(core_coeffs, dtype=np.float64)
+        nc = cw.size // words_per_det
+        o = AsciSearchOpts(0, h_el_tol, 0.0, int(just_singles), 0)
+        n_out = C.c_int64(0)
+        check(lib().b2ci_asci_candidates(self.h, C.byref(o), _p(cw), words_per_det, _p(cc), nc, E0,
+                                         None, None, None, C.byref(n_out)))
+        n = n_out.value
+        words = np.empty(n * words_per_det, dtype=np.uint64)
+        cm, hd = np.empty(n), np.empty(n)
+        check(lib().b2ci_asci_candidates(self.h, C.byref(o), _p(cw), words_per_det, _p(cc), nc, E0,
+                                         _p(words), _p(cm), _p(hd), C.byref(n_out)))
+        return words, cm, hd
+
+
+class DetList:
+    def __init__(self, ctx: Context, handle):
+        self.ctx, self.h = ctx, handle
+
+    def __len__(self) -> int:
+        n = C.c_int64(0)
+        check(lib().b2ci_dets_size(self.h, C.byref(n)))
+        return n.value
+
+    def download(self, words_per_det: int = 1) -> np.ndarray:
+        out = np.empty(len(self) * words_per_det, dtype=np.uint64)
+        check(lib().b2ci_dets_download(self.ctx.h, self.h, _p(out), words_per_det))
+        return out
+
+    def free(self):
+        if self.h and self.ctx.h:
+            lib().b2ci_dets_free(self.ctx.h, self.h)
+        self.h = None
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+
+class CsrMatrix:
+    def __init__(self, ctx: Context, handle):
+        self.ctx, self.h = ctx, handle
+
+    def info(self):
+        a, b, c, d = C.c_int64(0), C.c_int64(0), C.c_int64(0), C.c_int64(0)
+        check(lib().b2ci_csr_info(self.h, C.byref(a), C.byref(b), C.byref(c), C.byref(d)))
+        return a.value, b.value, c.value, d.value
+
+    @property
+    def nrows(self):
+        return self.info()[0]
+
+    @property
+    def ncols(self):
+        return self.info()[1]
+
+    @property
+    def nnz(self):
+        return self.info()[2]
+
+    @property
+    def row_begin(self):
+        return self.info()[3]
+
+    def download(self):
+        nrows, _, nnz, _ = self.info()
+        rp = np.empty(nrows + 1, dtype=np.int64)
+        ci = np.empty(nnz, dtype=np.int64)
+        nz = np.empty(nnz, dtype=np.float64)
+        check(lib().b2ci_csr_download(self.ctx.h, self.h, _p(rp), _p(ci), _p(nz)))
+        return rp, ci, nz
+
+    def download_rowptr(self):
+        rp = np.empty(self.nrows + 1, dtype=np.int64)
+        check(lib().b2ci_csr_download(self.ctx.h, self.h, _p(rp), None, None))
+        return rp
+
+    def device_ptrs(self):
+        a, b, c = C.c_void_p(), C.c_void_p(), C.c_void_p()
+        check(lib().b2ci_csr_device_ptrs(self.h, C.byref(a), C.byref(b), C.byref(c)))
+        return a.value, b.value, c.value
+
+    def spmv(self, x: np.ndarray) -> np.ndarray:
+        """sigma with HOST buffers (copies inside the call)."""
+        x = np.ascontiguousarray(x, dtype=np.float64)
+        if x.size != self.ncols:
+            raise ValueError("x must have ncols entries")
+        y = np.empty(self.nrows, dtype=np.float64)
+        check(lib().b2ci_spmv_host(self.ctx.h, self.h, _p(x), _p(y)))
+        return y
+
+    def spmv_device(self, x_ptr: int, y_ptr: int):
+        """sigma on DEVICE pointers (e.g. torch tensors' data_ptr())."""
+        check(lib().b2ci_spmv(self.ctx.h, self.h, C.c_void_p(x_ptr), C.c_void_p(y_ptr)))
+
+    def diagonal(self) -> np.ndarray:
+        d = np.empty(self.nrows, dtype=np.float64)
+        check(lib().b2ci_csr_diagonal(self.ctx.h, self.h, _p(d)))
+        return d
+
+    def davidson(self, max_m: int, tol: float, x0: Optional[np.ndarray] = None,
+                 guess_policy: bool = True):
+        """Returns (E, X, niter, trace). Raises B2ciError("Davidson Did Not Converge!")."""
+        n = self.ncols
+        X = np.zeros(n) if x0 is None else np.array(x0, dtype=np.float64, copy=True)
+        if X.size != n:
+            raise ValueError("guess must have ncols entries")
+        if not guess_policy and x0 is None:
+            raise ValueError("Davidson: No Guess Provided")
+        niter, eig = C.c_int64(0), C.c_double(0.0)
+        trace = np.zeros(2 * (max_m + 1))
+        check(lib().b2ci_davidson(self.ctx.h, self.h, max_m, tol, _p(X), 1 if guess_policy else 0,
+                                  C.byref(niter), C.byref(eig), _p(trace)))
+        return eig.value, X, niter.value, trace.reshape(-1, 2)
+
+    def free(self):
+        if self.h and self.ctx.h:
+            lib().b2ci_csr_free(self.ctx.h, self.h)
+        self.h = None
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+
+def host_matrix_element(norb, T, V, bra_a, bra_b, ket_a, ket_b) -> float:
+    T = np.ascontiguousarray(T, dtype=np.float64)
+    V = np.ascontiguousarray(V, dtype=np.float64).reshape(-1)
+    return lib().b2ci_host_matrix_element(norb, _p(T), _p(V), int(bra_a), int(bra_b), int(ket_a),
+                                          int(ket_b))
+
+
+def host_sym_eig_lower(A: np.ndarray):
+    n = A.shape[0]
+    M = np.array(A, dtype=np.float64, order="F", copy=True)
+    W = np.empty(n)
+    check(lib().b2ci_host_sym_eig_lower(n, _p(M), n, _p(W)))
+    return W, M

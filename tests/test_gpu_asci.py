@@ -1,0 +1,90 @@
+"""GPU parity of the ASCI search (generation, sort/accumulate, top-k) through the C ABI."""
+import numpy as np
+import pytest
+
+from oracle import port
+from qdk_chemistry_b200 import device
+from qdk_chemistry_b200 import workloads as W
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    c = device.Context(0)
+    yield c
+    c.close()
+
+
+def _core_from_fci(sp, ncore, seed=0):
+    """A spin-sorted core set with a normalised random-sign coefficient vector."""
+    a, b = port.generate_hilbert_space(sp.norb, sp.nalpha, sp.nbeta)
+    rng = np.random.default_rng(seed)
+    pick = np.sort(rng.choice(len(a), size=min(ncore, len(a)), replace=False))
+    ca, cb = a[pick], b[pick]
+    o = port.spin_sort_order(ca, cb)
+    ca, cb = ca[o], cb[o]
+    c = rng.normal(size=len(ca)) * np.exp(-np.arange(len(ca)) / 7.0)
+    return ca, cb, c / np.linalg.norm(c)
+
+
+@pytest.mark.parametrize("name,ncore", [("small_cas8", 1), ("small_cas8", 37), ("hubbard_4x2", 20),
+                                        ("n2_cas10", 64)])
+def test_candidate_table_bit_exact(ctx, name, ncore):
+    sp = W.config(name)
+    ca, cb, c = _core_from_fci(sp, ncore)
+    E0 = -3.25
+    ctx.upload_integrals(sp.norb, sp.T, sp.V)
+    words, cm, hd = ctx.asci_candidates(port.pack(ca, cb), c, E0, h_el_tol=1e-8)
+    oa, ob, ocm, ohd = port.Ham(sp.norb, sp.T, sp.V).asci_candidates(ca, cb, c, E0, 1e-8)
+    assert np.array_equal(words, port.pack(oa, ob))     # same keys, same (beta, alpha) order
+    assert np.array_equal(hd, ohd)                       # first-parent h_diag, bit exact
+    fin = np.isfinite(ocm)
+    assert np.array_equal(np.isfinite(cm), fin)
+    assert np.array_equal(cm[fin], ocm[fin])            # parent-ordered sums, bit exact
+
+
+def test_water_search_selection_matches_reference(ctx, water, golden_meta, golden_arrays):
+    # inputs and expected selection were produced by the compiled reference (make_golden.py)
+    m = golden_meta["water_search"]
+    ca, cb = golden_arrays["water_search.core_alpha"], golden_arrays["water_search.core_beta"]
+    ctx.upload_integrals(water.norb, water.T, water.V)
+    out, stats = ctx.asci_search(port.pack(ca, cb), golden_arrays["water_search.core_C"], m["E0"],
+                                 m["ndets_max"])
+    assert len(out) == m["n_selected"]
+    assert np.array_equal(np.sort(out), golden_arrays["water_search.selected"])
+    # core determinants are appended last, in the order given (determinant_search.hpp:1107-1114)
+    assert np.array_equal(out[-len(ca):], port.pack(ca, cb))
+    sa, sb, ostats = port.Ham(water.norb, water.T, water.V).asci_search(
+        ca, cb, golden_arrays["water_search.core_C"], m["E0"], m["ndets_max"])
+    assert np.array_equal(stats[:5], ostats[:5])         # counts, pivot and gap identical
+
+
+@pytest.mark.parametrize("ndets_max", [30, 31, 200, 100000])
+def test_topk_edge_cases(ctx, ndets_max):
+    sp = W.config("small_cas8")
+    ca, cb, c = _core_from_fci(sp, 30, seed=3)
+    ctx.upload_integrals(sp.norb, sp.T, sp.V)
+    out, stats = ctx.asci_search(port.pack(ca, cb), c, -2.0, ndets_max)
+    sa, sb, ostats = port.Ham(sp.norb, sp.T, sp.V).asci_search(ca, cb, c, -2.0, ndets_max)
+    assert np.array_equal(out, port.pack(sa, sb))
+    assert np.array_equal(stats[:5], ostats[:5])
+
+
+def test_just_singles_and_tolerances(ctx):
+    sp = W.config("small_cas8")
+    ca, cb, c = _core_from_fci(sp, 25, seed=4)
+    ctx.upload_integrals(sp.norb, sp.T, sp.V)
+    for kw in (dict(just_singles=True), dict(h_el_tol=1e-3), dict(rv_prune_tol=1e-2)):
+        out, _ = ctx.asci_search(port.pack(ca, cb), c, -2.0, 500, **kw)
+        sa, sb, _ = port.Ham(sp.norb, sp.T, sp.V).asci_search(ca, cb, c, -2.0, 500, **kw)
+        assert np.array_equal(out, port.pack(sa, sb))
+
+
+def test_unsorted_core_is_rejected(ctx):
+    sp = W.config("small_cas8")
+    ca, cb, c = _core_from_fci(sp, 10, seed=5)
+    ctx.upload_integrals(sp.norb, sp.T, sp.V)
+    with pytest.raises(device.B2ciError) as e:
+        ctx.asci_search(port.pack(ca[::-1], cb[::-1]), c, -2.0, 100)
+    assert "Sorted" in str(e.value)

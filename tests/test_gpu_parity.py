@@ -1,0 +1,241 @@
+"""GPU parity tests proper: every call goes through the C ABI (libb2ci.so) and is compared
+with the plain-C oracle on the same inputs and with the fixtures generated from the compiled
+reference. Bit-exact for patterns / indices / matrix elements; FP tolerances are written
+next to each assertion."""
+import os
+
+import numpy as np
+import pytest
+
+from oracle import port
+from qdk_chemistry_b200 import device
+from qdk_chemistry_b200 import workloads as W
+from helpers import EPS, check_csr_against_golden, cisd_space, sha
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    c = device.Context(0)
+    yield c
+    c.close()
+
+
+def _build(ctx, sp, a, b, thr, rows=None):
+    ctx.upload_integrals(sp.norb, sp.T, sp.V)
+    dets = ctx.upload_dets(port.pack(a, b), 1)
+    H = ctx.hbuild(dets, thr, rows)
+    return dets, H
+
+
+def test_intermediates_bit_exact(ctx):
+    sp = W.config("small_cas8")
+    ctx.upload_integrals(sp.norb, sp.T, sp.V)
+    got = ctx.download_intermediates()
+    ref = port.Ham(sp.norb, sp.T, sp.V).intermediates()
+    for g, r in zip(got, ref):
+        assert np.array_equal(g, r)
+
+
+@pytest.mark.parametrize("cfg", [(6, 3, 3), (8, 4, 3), (7, 0, 3), (5, 5, 2), (12, 6, 6), (26, 2, 1)])
+def test_generate_hilbert_space_order(ctx, cfg):
+    norb, na, nb = cfg
+    a, b = port.generate_hilbert_space(norb, na, nb)
+    d = ctx.generate_fci(norb, na, nb)
+    assert np.array_equal(d.download(1), port.pack(a, b))
+    assert np.array_equal(d.download(2), port.pack(a, b, 128))
+
+
+@pytest.mark.parametrize("name", ["tiny_cas6", "small_cas8", "hubbard_3x2", "hubbard_4x2"])
+@pytest.mark.parametrize("tag,thr", [("eps", EPS), ("zero", 0.0)])
+def test_fci_csr_bit_exact(ctx, golden_meta, golden_arrays, name, tag, thr):
+    sp = W.config(name)
+    a, b = port.generate_hilbert_space(sp.norb, sp.nalpha, sp.nbeta)
+    dets, H = _build(ctx, sp, a, b, thr)
+    rp, ci, nz = H.download()
+    # against the reference-made fixture (pattern AND values bit-exact)
+    check_csr_against_golden(golden_meta, golden_arrays, f"{name}_{tag}", rp, ci, nz)
+    # and against the oracle run now
+    orp, oci, onz = port.Ham(sp.norb, sp.T, sp.V).hbuild(a, b, thr)
+    assert np.array_equal(rp, orp) and np.array_equal(ci, oci) and np.array_equal(nz, onz)
+
+
+def test_water_cisd_csr_matches_reference_golden(ctx, water, golden_meta, golden_arrays):
+    # external/macis/tests/csr_hamiltonian.cxx:76-99
+    a, b = cisd_space(24, 5, 5)
+    dets, H = _build(ctx, water, a, b, 1e-16)
+    rp, ci, nz = H.download()
+    blob = np.fromfile(os.path.join(os.path.dirname(__file__), "golden", "h2o.ccpvdz.cisd.rowptr.bin"),
+                       dtype=np.int32)
+    assert H.nrows == 12636 and H.nnz == 3517816
+    assert np.array_equal(rp, blob.astype(np.int64))
+    check_csr_against_golden(golden_meta, golden_arrays, "water_cisd_1e-16", rp, ci, nz)
+
+
+@pytest.mark.parametrize("tag,thr", [("eps", EPS), ("zero", 0.0)])
+def test_water_cisd_threshold_semantics(ctx, water, golden_meta, golden_arrays, tag, thr):
+    a, b = cisd_space(24, 5, 5)
+    dets, H = _build(ctx, water, a, b, thr)
+    rp, ci, nz = H.download()
+    check_csr_against_golden(golden_meta, golden_arrays, f"water_cisd_{tag}", rp, ci, nz)
+
+
+def test_n2_cas10_csr_bit_exact_config0(ctx, golden_meta, golden_arrays):
+    # BASELINE.json configs[0] shape: CAS(10e,10o), 63,504 determinants
+    sp = W.config("n2_cas10")
+    d = ctx.generate_fci(10, 5, 5)
+    assert sha(d.download(1)) == golden_meta["n2_cas10_dets_sha"]
+    ctx.upload_integrals(sp.norb, sp.T, sp.V)
+    H = ctx.hbuild(d, EPS)
+    rp, ci, nz = H.download()
+    check_csr_against_golden(golden_meta, golden_arrays, "n2_cas10_eps", rp, ci, nz)
+
+
+def test_row_block_build_equals_full(ctx):
+    sp = W.config("small_cas8")
+    a, b = port.generate_hilbert_space(sp.norb, sp.nalpha, sp.nbeta)
+    dets, H = _build(ctx, sp, a, b, EPS)
+    rp, ci, nz = H.download()
+    for r0, r1 in [(0, 1), (137, 2001), (3919, 3920), (500, 500)]:
+        Hb = ctx.hbuild(dets, EPS, (r0, r1))
+        rpb, cib, nzb = Hb.download()
+        assert Hb.row_begin == r0 and Hb.ncols == len(a)
+        assert np.array_equal(rpb, rp[r0:r1 + 1] - rp[r0])
+        assert np.array_equal(cib, ci[rp[r0]:rp[r1]]) and np.array_equal(nzb, nz[rp[r0]:rp[r1]])
+
+
+def test_edge_cases(ctx):
+    # empty list, single determinant, alpha-empty determinants (rows skipped by SDL)
+    sp = W.synthetic_molecular("x", 5, 0, 2, 5, 6)
+    ctx.upload_integrals(sp.norb, sp.T, sp.V)
+    a, b = port.generate_hilbert_space(5, 0, 2)
+    H = ctx.hbuild(ctx.upload_dets(port.pack(a, b)), 0.0)
+    assert H.nnz == 0 and np.all(H.download()[0] == 0)
+    H1 = ctx.hbuild(ctx.upload_dets(np.array([0b00111 | (0b00011 << 32)], dtype=np.uint64)), 0.0)
+    rp, ci, nz = H1.download()
+    assert H1.nnz == 1 and ci[0] == 0
+    assert nz[0] == port.Ham(sp.norb, sp.T, sp.V).matrix_element(7, 3, 7, 3)
+    H0 = ctx.hbuild(ctx.upload_dets(np.zeros(0, dtype=np.uint64)), 0.0)
+    assert H0.nrows == 0 and H0.nnz == 0
+    # unsorted / repeated alpha runs still give the pairwise pattern (run-length encoder)
+    sp2 = W.config("tiny_cas6")
+    a2, b2 = port.generate_hilbert_space(6, 3, 3)
+    perm = np.random.default_rng(5).permutation(len(a2))
+    ctx.upload_integrals(sp2.norb, sp2.T, sp2.V)
+    Hp = ctx.hbuild(ctx.upload_dets(port.pack(a2[perm], b2[perm])), EPS)
+    orp, oci, onz = port.Ham(sp2.norb, sp2.T, sp2.V).hbuild(a2[perm], b2[perm], EPS)
+    rp, ci, nz = Hp.download()
+    assert np.array_equal(rp, orp) and np.array_equal(ci, oci) and np.array_equal(nz, onz)
+
+
+def test_wfn128_words(ctx):
+    # two-word determinants (wfn_t<128> layout) give the same matrix
+    sp = W.config("tiny_cas6")
+    a, b = port.generate_hilbert_space(6, 3, 3)
+    ctx.upload_integrals(sp.norb, sp.T, sp.V)
+    H1 = ctx.hbuild(ctx.upload_dets(port.pack(a, b), 1), EPS).download()
+    H2 = ctx.hbuild(ctx.upload_dets(port.pack(a, b, 128), 2), EPS).download()
+    for x, y in zip(H1, H2):
+        assert np.array_equal(x, y)
+
+
+@pytest.mark.parametrize("name", ["small_cas8", "hubbard_4x2"])
+def test_sigma_matches_oracle(ctx, name):
+    sp = W.config(name)
+    a, b = port.generate_hilbert_space(sp.norb, sp.nalpha, sp.nbeta)
+    dets, H = _build(ctx, sp, a, b, EPS)
+    rp, ci, nz = H.download()
+    rng = np.random.default_rng(1)
+    for _ in range(3):
+        x = rng.normal(size=len(a))
+        y = H.spmv(x)
+        yo = port.spmv(rp, ci, nz, x)
+        # FP64 sums in a different association order: |dy| <= 1e-13 * sum|h||x| per row
+        bound = 1e-13 * port.spmv(rp, ci, np.abs(nz), np.abs(x)) + 1e-300
+        assert np.all(np.abs(y - yo) <= bound)
+    # linearity (size-independent property)
+    x1, x2 = rng.normal(size=len(a)), rng.normal(size=len(a))
+    assert np.allclose(H.spmv(2.0 * x1 - 3.0 * x2), 2.0 * H.spmv(x1) - 3.0 * H.spmv(x2), rtol=0, atol=1e-10)
+
+
+def test_sigma_on_uploaded_csr_all_row_shapes(ctx):
+    # ragged rows incl. empty ones: exercises every threads-per-row variant + head/tail paths
+    rng = np.random.default_rng(9)
+    n = 3000
+    for mean in (1, 5, 17, 40, 70, 200):
+        lens = rng.poisson(mean, size=n)
+        lens[rng.integers(0, n, 50)] = 0
+        rp = np.concatenate([[0], np.cumsum(lens)]).astype(np.int64)
+        ci = np.concatenate([np.sort(rng.choice(n, size=l, replace=False)) for l in lens] + [np.zeros(0, int)]).astype(np.int64)
+        nz = rng.normal(size=rp[-1])
+        M = ctx.upload_csr(rp, ci, nz)
+        x = rng.normal(size=n)
+        y = M.spmv(x)
+        yo = port.spmv(rp, ci, nz, x)
+        assert np.allclose(y, yo, rtol=0, atol=1e-11)
+        rp2, ci2, nz2 = M.download()
+        assert np.array_equal(rp2, rp) and np.array_equal(ci2, ci) and np.array_equal(nz2, nz)
+
+
+def test_diagonal(ctx):
+    sp = W.config("small_cas8")
+    a, b = port.generate_hilbert_space(sp.norb, sp.nalpha, sp.nbeta)
+    dets, H = _build(ctx, sp, a, b, EPS)
+    rp, ci, nz = H.download()
+    assert np.array_equal(H.diagonal(), port.extract_diagonal(rp, ci, nz))
+
+
+@pytest.mark.parametrize("name", ["tiny_cas6", "small_cas8", "hubbard_3x2", "hubbard_4x2"])
+def test_davidson_energy_and_iterations(ctx, golden_meta, name):
+    sp = W.config(name)
+    a, b = port.generate_hilbert_space(sp.norb, sp.nalpha, sp.nbeta)
+    dets, H = _build(ctx, sp, a, b, EPS)
+    E, X, niter, trace = H.davidson(200, 1e-8)
+    rec = golden_meta[f"{name}_eps"]["davidson"]
+    assert abs(E - rec["E"]) < 1e-8          # north_star: energies within 1e-8 Eh
+    assert abs(niter - rec["niter"]) <= 1     # same iteration count as the reference (+-1)
+    assert abs(X @ X - 1.0) < 1e-12           # davidson.cxx:62-72 properties
+    rp, ci, nz = H.download()
+    assert abs(X @ port.spmv(rp, ci, nz, X) - E) < 1e-11
+    Eo, Xo, nito, _ = port.davidson(rp, ci, nz, 200, 1e-8)
+    assert abs(E - Eo) < 1e-9 and abs(niter - nito) <= 1
+
+
+def test_davidson_water_cisd_golden(ctx, water, golden_meta, golden_arrays):
+    # external/macis/tests/davidson.cxx:20-75 (max_m = 15, tol = 1e-8)
+    a, b = cisd_space(24, 5, 5)
+    dets, H = _build(ctx, water, a, b, 1e-16)
+    E, X, niter, trace = H.davidson(15, 1e-8)
+    ka = golden_meta["known_answers"]
+    assert abs(E + water.core_energy - ka["water_cisd_davidson_total"]) < 1e-8
+    rec = golden_meta["water_cisd_1e-16"]["davidson"]
+    assert abs(E - rec["E"]) < 1e-9 and niter == rec["niter"]
+    assert abs(abs(X @ golden_arrays["water_cisd_1e-16.davidson_X"]) - 1.0) < 1e-9
+
+
+def test_davidson_not_converged_raises(ctx):
+    sp = W.config("small_cas8")
+    a, b = port.generate_hilbert_space(sp.norb, sp.nalpha, sp.nbeta)
+    dets, H = _build(ctx, sp, a, b, EPS)
+    with pytest.raises(device.B2ciError) as e:
+        H.davidson(3, 1e-12)
+    assert "Davidson Did Not Converge!" in str(e.value)
+
+
+def test_davidson_uploaded_matrices(ctx):
+    # python/tests/test_davidson_solver.py: 6x6 tridiagonal with analytic eigenpair, 1x1 case
+    n = 6
+    rp, ci, nz = [0], [], []
+    for i in range(n):
+        for j in (i - 1, i, i + 1):
+            if 0 <= j < n:
+                ci.append(j)
+                nz.append(2.0 if i == j else -1.0)
+        rp.append(len(ci))
+    M = ctx.upload_csr(rp, ci, nz)
+    E, X, niter, _ = M.davidson(20, 1e-10)
+    assert abs(E - (2 - 2 * np.cos(np.pi / (n + 1)))) < 1e-10
+    M1 = ctx.upload_csr([0, 1], [0], [-3.5])
+    E1, X1, nit1, _ = M1.davidson(20, 1e-8)
+    assert E1 == -3.5 and X1[0] == 1.0 and nit1 == 0
