@@ -1,0 +1,442 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the CI hot path (H build + Davidson sigma).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload NAME] [--impl b200|reference]
+
+A *step* is one pass of the hot path over one synthetic workload: the Hamiltonian build of
+this rank's row block (b2ci_hbuild_csr) followed by one sigma = H c application
+(b2ci_sigma_sharded: NCCL all-gather of the trial vector + SpMV). The default workload is
+BASELINE.json configs[1] (2D extended Hubbard 4x3, 6a6b, 853,776 determinants); the other FCI
+configs are selectable with --workload.
+
+Metric (BASELINE.json: "H-build nnz/s and Davidson sigma-iter time (ms)"): `value` is the
+whole-job H-build throughput in nnz/s with the determinant list and integrals resident in
+HBM; the sigma half of the metric is reported beside it (`sigma_iter_ms`, `roofline_sigma`).
+`e2e` is the same H-build throughput measured through the C ABI with HOST buffers
+(integrals + determinant words uploaded, row pointer read back, inside the timed region).
+Rows are sharded over the N ranks (strong scaling: the problem is fixed); timing is CUDA
+events on the library's stream, max over ranks. `--impl reference` times the reference's own
+CPU implementation (oracle/_ref = MACIS compiled unmodified, else the plain-C oracle port) on
+a bounded sample of the same workload.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+EPS = float(np.finfo(np.float64).eps)
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as fh:
+            d = json.load(fh)
+        return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+
+    def __init__(self, index: int):
+        self.index = index
+        self.samples = []
+        self.proc = None
+
+    def start(self):
+        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+             "clocks_event_reasons.sw_power_cap")
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--id={self.index}", f"--query-gpu={q}", "--format=csv,noheader,nounits",
+                 "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.samples.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for s in self.samples:
+            f = [x.strip() for x in s.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0]))
+                mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": float(np.median(sm)) if sm else None,
+                "sm_max_mhz": float(max(mx)) if mx else None, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def fci_workload(name):
+    from qdk_chemistry_b200 import workloads as W
+    sp = W.config(name)
+    return sp
+
+
+def split_rows(n, nranks):
+    """contiguous equal row blocks, remainder spread over the first ranks"""
+    base, rem = divmod(n, nranks)
+    offs = [0]
+    for r in range(nranks):
+        offs.append(offs[-1] + base + (1 if r < rem else 0))
+    return offs
+
+
+# ---------------------------------------------------------------------------------------
+# CPU legs (oracle/ is only ever the checker / the baseline, never the product path)
+# ---------------------------------------------------------------------------------------
+def cpu_sample(sp, budget_rows_frac=None, target_seconds=12.0):
+    """Reference CPU implementation on a bounded sample of the workload: H build of the rows
+    of a few alpha blocks spread over the list against ALL kets (make_csr_hamiltonian_block),
+    then gespmbv on those rows. Returns dict with nnz/s, sigma ms (scaled to the full matrix)."""
+    from oracle import port
+    try:
+        from oracle import ref
+        use_ref = ref.available()
+    except Exception:
+        use_ref = False
+    a, b = port.generate_hilbert_space(sp.norb, sp.nalpha, sp.nbeta)
+    n = len(a)
+    nbeta_str = int(np.count_nonzero(a == a[0]))
+    nruns = n // nbeta_str
+    words = port.pack(a, b)
+    out = {}
+    if use_ref:
+        hg = ref.HamGen(sp.norb, sp.T, sp.V)
+        cores = ref.num_threads()
+        kind = "reference"
+
+        def build(rows_idx):
+            H, sec = hg.hbuild(words[rows_idx], EPS, kets=words)
+            return H, sec
+    else:
+        hp = port.Ham(sp.norb, sp.T, sp.V)
+        cores = port.lib().op_num_threads()
+        kind = "port"
+    # calibrate with one alpha block, then size the sample for ~target_seconds
+    def rows_of(runs):
+        return np.concatenate([np.arange(r * nbeta_str, (r + 1) * nbeta_str) for r in runs])
+
+    def timed_build(runs):
+        idx = rows_of(runs)
+        if use_ref:
+            H, sec = build(idx)
+            return H, sec, H.nnz, idx
+        t0 = time.perf_counter()
+        nnz = 0
+        for r in runs:  # contiguous row blocks for the port
+            rp, ci, nz = hp.hbuild(a, b, EPS, rows=(r * nbeta_str, (r + 1) * nbeta_str))
+            nnz += int(rp[-1])
+        return None, time.perf_counter() - t0, nnz, idx
+
+    # the reference parallelises over bra alpha blocks (omp for, sorted_double_loop.hpp:145):
+    # the sample must hold several blocks per thread or the cores idle
+    ncal = int(min(nruns, max(16, 2 * cores)))
+    cal_runs = sorted(set(np.linspace(0, nruns - 1, ncal).astype(int).tolist()))
+    _, t1, nnz1, _ = timed_build(cal_runs)
+    nsample = int(max(ncal, min(nruns, round(len(cal_runs) * target_seconds / max(t1, 1e-3)))))
+    runs = sorted(set(np.linspace(0, nruns - 1, nsample).astype(int).tolist()))
+    H, sec, nnz, idx = timed_build(runs)
+    out["hbuild_nnz_per_s"] = nnz / sec
+    out["hbuild_sample_seconds"] = sec
+    out["sample_rows"] = int(len(idx))
+    out["sample_nnz"] = int(nnz)
+    out["cores"] = int(cores)
+    out["kind"] = kind
+    out["sample"] = (f"{len(runs)} of {nruns} alpha blocks ({len(idx)} of {n} rows, all {n} kets), "
+                     f"make_csr_hamiltonian_block<int64>, H_thresh=eps; non-mirrored row block")
+    # sigma on the sampled rows (rectangular block), scaled by rows to the full matrix
+    if use_ref and H is not None and H.nnz > 0:
+        x = np.random.default_rng(0).normal(size=n)
+        # the block is rows x n: gespmbv reads V of length n and writes len(rows)
+        H.spmv(x, nrep=2)
+        _, tsp = H.spmv(x, nrep=10)
+        out["sigma_ms_sample"] = tsp * 1e3
+        out["sigma_nnz_per_s"] = H.nnz / tsp
+        out["sigma_ms_full_est"] = tsp * 1e3 * (n / len(idx))
+    return out
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    sp = fci_workload(args.workload)
+    vals, sig = [], []
+    info = None
+    for it in range(args.warmup + args.steps):
+        info = cpu_sample(sp, target_seconds=args.cpu_seconds)
+        if it >= args.warmup:
+            vals.append(info["hbuild_nnz_per_s"])
+            sig.append(info.get("sigma_ms_full_est"))
+    v = float(np.mean(vals))
+    line = {
+        "impl": "reference", "metric": "hbuild_nnz_per_s", "value": v, "unit": "nnz/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": float(info["hbuild_sample_seconds"] * 1e3), "higher_is_better": True,
+        "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": args.workload, "norb": sp.norb, "nalpha": sp.nalpha, "nbeta": sp.nbeta,
+                   "ndets": sp.fci_dimension, "h_thresh": EPS},
+        "sigma_iter_ms": float(np.mean([s for s in sig if s is not None])) if any(sig) else None,
+        "cpu_baseline": {"value": v, "unit": "nnz/s", "cores": info["cores"], "kind": info["kind"],
+                         "sample": info["sample"]},
+        "e2e": {"value": v, "unit": "nnz/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+# ---------------------------------------------------------------------------------------
+# GPU arm
+# ---------------------------------------------------------------------------------------
+def run_b200(args):
+    import torch
+    import torch.distributed as dist
+    from qdk_chemistry_b200 import device
+    from oracle import port  # only for the cpu_baseline leg and the packed determinant order
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus and world > 1:
+        raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    stream = torch.cuda.current_stream().cuda_stream
+    ctx = device.Context(local_rank, stream)
+    if world > 1:
+        idt = torch.zeros(128, dtype=torch.uint8, device="cuda")
+        if rank == 0:
+            idt.copy_(torch.frombuffer(bytearray(device.Context.comm_unique_id()), dtype=torch.uint8))
+        dist.broadcast(idt, 0)
+        ctx.comm_init(bytes(idt.cpu().numpy().tobytes()), rank, world)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x):
+        if world == 1:
+            return float(x)
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def sum_over_ranks(x):
+        if world == 1:
+            return float(x)
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        return float(t.item())
+
+    sp = fci_workload(args.workload)
+    n = sp.fci_dimension
+    offs = split_rows(n, world)
+    r0, r1 = offs[rank], offs[rank + 1]
+    hbm_peak, peak_src = measured_peaks()
+
+    # resident inputs
+    ctx.upload_integrals(sp.norb, sp.T, sp.V)
+    dets = ctx.generate_fci(sp.norb, sp.nalpha, sp.nbeta)
+    words_host = dets.download(1)  # host copy for the e2e leg (pageable -> pinned below)
+    words_pinned = torch.from_numpy(words_host.view(np.int64)).pin_memory()
+    x_local = torch.randn(r1 - r0, dtype=torch.float64, device="cuda")
+    x_full = torch.empty(n, dtype=torch.float64, device="cuda")
+    y_local = torch.empty(r1 - r0, dtype=torch.float64, device="cuda")
+    flush = torch.empty(192 * 1024 * 1024 // 4, dtype=torch.float32, device="cuda")  # > L2 (126 MB)
+
+    ev = lambda: torch.cuda.Event(enable_timing=True)
+    t_build, t_fill, t_count, t_sigma, t_step, t_e2e = [], [], [], [], [], []
+    launches0 = None
+    nnz_local = 0
+    H = None
+    sampler = ClockSampler(local_rank)
+    for it in range(args.warmup + args.steps):
+        timed = it >= args.warmup
+        if it == args.warmup:
+            barrier()
+            launches0 = ctx.launch_count
+            if rank == 0:
+                sampler.start()
+            wall0 = time.perf_counter()
+        if H is not None:
+            H.free()
+        flush.zero_()  # evict L2 between iterations (outside the timed events)
+        e0, e1, e2, e3 = ev(), ev(), ev(), ev()
+        e0.record()
+        H = ctx.hbuild(dets, EPS, (r0, r1))
+        e1.record()
+        flush.zero_()
+        e2.record()
+        H.sigma_sharded(x_local.data_ptr(), x_full.data_ptr(), y_local.data_ptr())
+        e3.record()
+        torch.cuda.synchronize()
+        if timed:
+            t_build.append(e0.elapsed_time(e1))
+            t_sigma.append(e2.elapsed_time(e3))
+            t_step.append(e0.elapsed_time(e1) + e2.elapsed_time(e3))
+            t_count.append(ctx.timer_ms("h_build.count"))
+            t_fill.append(ctx.timer_ms("h_build.fill"))
+        nnz_local = H.nnz
+    barrier()
+    wall1 = time.perf_counter()
+    clocks = sampler.stop() if rank == 0 else None
+    launches = ctx.launch_count - launches0
+
+    # e2e leg: same H build through the C ABI with HOST buffers (pinned), result read back
+    for it in range(max(1, args.warmup // 2) + max(1, args.steps // 2)):
+        timed = it >= max(1, args.warmup // 2)
+        H.free()
+        H = None
+        flush.zero_()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        ctx.upload_integrals(sp.norb, sp.T, sp.V)
+        d2 = ctx.upload_dets(words_pinned.numpy().view(np.uint64), 1)
+        H = ctx.hbuild(d2, EPS, (r0, r1))
+        rp = H.download_rowptr()
+        torch.cuda.synchronize()
+        t1 = time.perf_counter()
+        d2.free()
+        if timed:
+            t_e2e.append((t1 - t0) * 1e3)
+    h2d = sp.T.nbytes + sp.V.nbytes + words_host.nbytes
+    d2h = (r1 - r0 + 1) * 8
+
+    nnz_total = sum_over_ranks(nnz_local)
+    build_ms = max_over_ranks(float(np.mean(t_build)))
+    fill_ms = max_over_ranks(float(np.mean(t_fill)))
+    count_ms = max_over_ranks(float(np.mean(t_count)))
+    sigma_ms = max_over_ranks(float(np.mean(t_sigma)))
+    step_ms = max_over_ranks(float(np.mean(t_step)))
+    e2e_ms = max_over_ranks(float(np.mean(t_e2e)))
+
+    # algorithmic bytes: per GPU launch
+    nrows = r1 - r0
+    B_sigma = nnz_local * 12 + (nrows + 1) * 8 + n * 8 + nrows * 8
+    B_fill = n * 16 + nnz_local * 12 + (nrows + 1) * 8
+    sig_gbs = B_sigma / (float(np.mean(t_sigma)) * 1e-3) / 1e9
+    fill_gbs = B_fill / (float(np.mean(t_fill)) * 1e-3) / 1e9
+
+    # ground-state energy of the workload (Davidson to 1e-8 Eh) -- outside the timed region
+    energy = None
+    dav = None
+    if args.davidson:
+        try:
+            E, X, niter, _ = H.davidson(args.max_m, 1e-8)
+            energy = E + sp.core_energy
+            ncalls = max(1.0, ctx.timer_ms("davidson.OP_CALLS"))
+            dav = {"niter": int(niter), "E0_electronic": E, "E0_total": energy,
+                   "sigma_ms_mean": ctx.timer_ms("davidson.OP_DUR") / ncalls,
+                   "rr_ms_total": ctx.timer_ms("davidson.RR_DUR"),
+                   "res_ms_total": ctx.timer_ms("davidson.RES_DUR"),
+                   "gs_ms_total": ctx.timer_ms("davidson.GS_DUR")}
+        except device.B2ciError as e:
+            dav = {"error": str(e)}
+
+    cpu = None
+    if rank == 0 and world == 1 and args.cpu_seconds > 0:
+        try:
+            cpu = cpu_sample(sp, target_seconds=args.cpu_seconds)
+        except Exception as e:  # the baseline is reported, never required
+            cpu = {"error": repr(e)}
+
+    if rank == 0:
+        line = {
+            "metric": "hbuild_nnz_per_s", "value": nnz_total / (build_ms * 1e-3), "unit": "nnz/s",
+            "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": step_ms,
+            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
+            "data": "synthetic",
+            "config": {"workload": args.workload, "norb": sp.norb, "nalpha": sp.nalpha,
+                       "nbeta": sp.nbeta, "ndets": n, "nnz": int(nnz_total), "h_thresh": EPS,
+                       "row_sharding": f"{world} contiguous row blocks",
+                       "l2": "192 MiB buffer rewritten between timed kernels"},
+            "hbuild_ms": build_ms, "hbuild_count_ms": count_ms, "hbuild_fill_ms": fill_ms,
+            "sigma_iter_ms": sigma_ms, "sigma_nnz_per_s": nnz_total / (sigma_ms * 1e-3),
+            "roofline": {"kernel": "k_rows<FILL> (H-build fill pass)", "bound": "hbm",
+                         "achieved": fill_gbs, "peak": hbm_peak, "unit": "GB/s",
+                         "frac": fill_gbs / hbm_peak, "traffic": None, "peak_source": peak_src,
+                         "note": "integer/latency bound (XOR/popcount scan); bytes = dets + CSR written"},
+            "roofline_sigma": {"kernel": "k_spmv", "bound": "hbm", "achieved": sig_gbs,
+                               "peak": hbm_peak, "unit": "GB/s", "frac": sig_gbs / hbm_peak,
+                               "traffic": None, "bytes_per_launch": int(B_sigma)},
+            "e2e": {"value": nnz_total / (e2e_ms * 1e-3), "unit": "nnz/s", "ms": e2e_ms,
+                    "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h)},
+            "gpu_launches": int(launches), "clocks": clocks, "davidson": dav,
+            "energy_total": energy, "wall_s_timed_region": wall1 - wall0,
+        }
+        if cpu is not None:
+            if "error" in cpu:
+                line["cpu_baseline"] = cpu
+            else:
+                line["cpu_baseline"] = {"value": cpu["hbuild_nnz_per_s"], "unit": "nnz/s",
+                                        "cores": cpu["cores"], "kind": cpu["kind"],
+                                        "sample": cpu["sample"],
+                                        "sigma_ms_full_est": cpu.get("sigma_ms_full_est"),
+                                        "sigma_nnz_per_s": cpu.get("sigma_nnz_per_s")}
+        print(json.dumps(line))
+    if H is not None:
+        H.free()
+    ctx.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="hubbard_4x3",
+                    choices=["hubbard_4x3", "cr2_cas12", "n2_cas10", "small_cas8", "hubbard_4x2"])
+    ap.add_argument("--max-m", type=int, default=100, dest="max_m")
+    ap.add_argument("--no-davidson", action="store_false", dest="davidson")
+    ap.add_argument("--cpu-seconds", type=float, default=12.0, dest="cpu_seconds",
+                    help="CPU work budget of the cpu_baseline sample (0 disables)")
+    args = ap.parse_args()
+    if args.warmup < 3:
+        args.warmup = 3
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_b200(args)
+
+
+if __name__ == "__main__":
+    main()

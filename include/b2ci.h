@@ -89,6 +89,12 @@ int b2ci_csr_free(b2ci_ctx* ctx, b2ci_csr* m);
 int b2ci_spmv(b2ci_ctx* ctx, const b2ci_csr* m, const double* x_dev, double* y_dev);
 /* same with HOST buffers (copies inside) */
 int b2ci_spmv_host(b2ci_ctx* ctx, const b2ci_csr* m, const double* x, double* y);
+/* Row-sharded sigma: all-gather of the local trial-vector blocks into x_full_dev (ncols
+ * entries, scratch owned by the caller) followed by the local SpMV -- the NCCL counterpart of
+ * sparsexx::spblas::pgespmv (sparsexx/spblas/pspmbv.hpp:316-405). Without a communicator it
+ * is b2ci_spmv(x_local_dev). DEVICE pointers. */
+int b2ci_sigma_sharded(b2ci_ctx* ctx, const b2ci_csr* m, const double* x_local_dev,
+                       double* x_full_dev, double* y_local_dev);
 /* extract_diagonal_elements (sparsexx/util/submatrix.hpp:354-383); host output, nrows */
 int b2ci_csr_diagonal(b2ci_ctx* ctx, const b2ci_csr* m, double* D);
 

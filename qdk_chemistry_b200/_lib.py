@@ -67,6 +67,7 @@ def lib():
     L.b2ci_csr_free.argtypes = [vp, vp]
     L.b2ci_spmv.argtypes = [vp, vp, vp, vp]
     L.b2ci_spmv_host.argtypes = [vp, vp, vp, vp]
+    L.b2ci_sigma_sharded.argtypes = [vp, vp, vp, vp, vp]
     L.b2ci_csr_diagonal.argtypes = [vp, vp, vp]
     L.b2ci_davidson.argtypes = [vp, vp, i64, dbl, vp, i32, pi64, C.POINTER(dbl), vp]
     L.b2ci_timer_ms.restype = dbl

@@ -274,6 +274,27 @@ int b2ci_spmv_host(b2ci_ctx* ctx, const b2ci_csr* m, const double* x, double* y)
   return 0;
   B2_CATCH
 }
+int b2ci_sigma_sharded(b2ci_ctx* ctx, const b2ci_csr* m, const double* x_local_dev,
+                       double* x_full_dev, double* y_local_dev) {
+  B2_TRY
+  if (ctx->nranks == 1) {
+    spmv_launch(ctx, m, x_local_dev, y_local_dev);
+    return 0;
+  }
+  b2ci_csr* mm = const_cast<b2ci_csr*>(m);
+  if (mm->row_offsets.empty()) {
+    std::vector<int64_t> counts;
+    comm_allgather_i64_host(ctx, m->nrows, counts);
+    mm->row_offsets.assign(ctx->nranks + 1, 0);
+    for (int r = 0; r < ctx->nranks; ++r) mm->row_offsets[r + 1] = mm->row_offsets[r] + counts[r];
+    if (mm->row_offsets[ctx->rank] != m->row_begin || mm->row_offsets[ctx->nranks] != m->ncols)
+      throw Error("b2ci_sigma_sharded: row blocks of the ranks do not tile [0, ncols) in rank order");
+  }
+  comm_allgather_rows(ctx, x_local_dev, x_full_dev, mm->row_offsets);
+  spmv_launch(ctx, m, x_full_dev, y_local_dev);
+  return 0;
+  B2_CATCH
+}
 int b2ci_csr_diagonal(b2ci_ctx* ctx, const b2ci_csr* m, double* D) {
   B2_TRY
   DevBuf<double> d(m->nrows > 0 ? m->nrows : 1);

@@ -97,6 +97,7 @@ struct b2ci_csr {
   int64_t* rowptr = nullptr;  // device, nrows + 1, local offsets (rowptr[0] == 0)
   int32_t* colind = nullptr;  // device, global column indices
   double* nzval = nullptr;    // device
+  std::vector<int64_t> row_offsets;  // multi-GPU: row offsets of all ranks (lazy)
 };
 
 namespace b2ci {

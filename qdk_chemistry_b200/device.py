@@ -235,6 +235,11 @@ class CsrMatrix:
         """sigma on DEVICE pointers (e.g. torch tensors' data_ptr())."""
         check(lib().b2ci_spmv(self.ctx.h, self.h, C.c_void_p(x_ptr), C.c_void_p(y_ptr)))
 
+    def sigma_sharded(self, x_local_ptr: int, x_full_ptr: int, y_local_ptr: int):
+        """all-gather of the row-sharded trial vector + local SpMV (DEVICE pointers)."""
+        check(lib().b2ci_sigma_sharded(self.ctx.h, self.h, C.c_void_p(x_local_ptr),
+                                       C.c_void_p(x_full_ptr), C.c_void_p(y_local_ptr)))
+
     def diagonal(self) -> np.ndarray:
         d = np.empty(self.nrows, dtype=np.float64)
         check(lib().b2ci_csr_diagonal(self.ctx.h, self.h, _p(d)))
