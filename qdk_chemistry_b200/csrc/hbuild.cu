@@ -16,6 +16,8 @@
 //                   per-row sort, no atomics, both triangles computed with the SAME
 //                   (bra = lower index, ket = higher index) roles as the reference so the
 //                   values are bit-identical to its mirrored entries.
+#include <cstdlib>
+
 #include "common.cuh"
 #include "slater.cuh"
 
@@ -45,35 +47,47 @@ __global__ void k_run_scatter(const uint64_t* __restrict__ alpha, int64_t n,
   if (i == n - 1) run_start[nruns] = n;
 }
 
-// adjacency between alpha runs; entry = (run index << 2) | (popcount / 2)
+// adjacency between bit strings (alpha runs, or the beta template of a rectangular list):
+// entry = (string index << 2) | (popcount / 2), ascending in the string index. skip_zero drops
+// empty strings on either side (the reference skips alpha-empty determinants, beta-empty ones
+// are kept). deg_cnt (count pass, optional): per string the number of neighbours at distance
+// 0, 2 and 4.
 template <bool FILL>
 __global__ void __launch_bounds__(256)
-k_run_adjacency(const uint64_t* __restrict__ run_alpha, int32_t nruns,
-                int32_t* __restrict__ cnt, const int64_t* __restrict__ adj_ptr,
-                uint32_t* __restrict__ adj) {
+k_string_adjacency(const uint64_t* __restrict__ str, int32_t nstr, int maxd, int skip_zero,
+                   int32_t* __restrict__ cnt, int32_t* __restrict__ deg_cnt,
+                   const int64_t* __restrict__ adj_ptr, uint32_t* __restrict__ adj) {
   const int lane = threadIdx.x & 31;
   const int64_t r = (int64_t(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
-  if (r >= nruns) return;
-  const uint64_t a = run_alpha[r];
+  if (r >= nstr) return;
+  const uint64_t a = str[r];
   int64_t out = FILL ? adj_ptr[r] : 0;
-  int32_t c = 0;
-  if (a != 0) {
-    for (int32_t r0 = 0; r0 < nruns; r0 += 32) {
+  int32_t c = 0, c0 = 0, c2 = 0, c4 = 0;
+  if (!(skip_zero && a == 0)) {
+    for (int32_t r0 = 0; r0 < nstr; r0 += 32) {
       const int32_t r2 = r0 + lane;
       bool ok = false;
       int d = 0;
-      if (r2 < nruns) {
-        const uint64_t a2 = run_alpha[r2];
+      if (r2 < nstr) {
+        const uint64_t a2 = str[r2];
         d = __popcll(a ^ a2);
-        ok = (a2 != 0) && d <= 4;
+        ok = !(skip_zero && a2 == 0) && d <= maxd;
       }
       const unsigned m = __ballot_sync(0xffffffffu, ok);
       if (FILL && ok) adj[out + __popc(m & ((1u << lane) - 1u))] = (uint32_t(r2) << 2) | uint32_t(d >> 1);
       out += __popc(m);
       c += __popc(m);
+      if (!FILL && deg_cnt) {
+        c0 += __popc(__ballot_sync(0xffffffffu, ok && d == 0));
+        c2 += __popc(__ballot_sync(0xffffffffu, ok && d == 2));
+        c4 += __popc(__ballot_sync(0xffffffffu, ok && d == 4));
+      }
     }
   }
-  if (!FILL && lane == 0) cnt[r] = c;
+  if (!FILL && lane == 0) {
+    cnt[r] = c;
+    if (deg_cnt) { deg_cnt[3 * r] = c0; deg_cnt[3 * r + 1] = c2; deg_cnt[3 * r + 2] = c4; }
+  }
 }
 
 struct RowArgs {
@@ -166,6 +180,253 @@ k_rows(const RowArgs A) {
     if (qn > 0) process_batch<FILL, EVAL>(A, i, ai, bi, q, qn, lane, out, cnt);
   }
   if (!FILL && lane == 0) A.row_cnt[row] = cnt;
+}
+
+// ------------------------------------------------------------------ rectangular lists
+// A determinant list is "rectangular" when it is the product of R alpha strings and one common
+// sequence of Nb beta strings (index = r * Nb + k) -- every list generate_hilbert_space makes.
+// Then no beta scan is needed at all: with alpha-run adjacency A(r) and beta adjacency lists
+// B2(k) (distance <= 2) and B4(k) (distance <= 4), row (r, k) is exactly
+//   { (r', k') : r' in A(r), k' in B_{4 - d_alpha(r, r')}(k) },
+// already in ascending column order. Every lane evaluates a real matrix element.
+__global__ void k_check_rect(const uint64_t* __restrict__ alpha, const uint64_t* __restrict__ beta,
+                             int64_t n, int64_t nb, int* __restrict__ bad) {
+  const int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int64_t r = i / nb, k = i % nb;
+  bool ok = beta[i] == beta[k] && alpha[i] == alpha[r * nb];
+  if (k == 0 && r > 0) ok = ok && alpha[i] != alpha[i - 1];
+  if (!ok) atomicOr(bad, 1);
+}
+
+// Per-pair metadata, computed once per (alpha run pair) / (beta template pair) instead of once
+// per matrix element. Same-spin doubles depend on one spin string pair only, so their VALUE is
+// precomputed; for single excitations the (hole, particle, sign) triple is precomputed so an
+// opposite-spin double costs one integral load:  sign_a * sign_b * V(v1,o1,v2,o2)
+// (matrix_elements.hpp:140-151). Orientation: bra = lower determinant index, as the reference.
+//   meta = o | v << 8 | (sign < 0) << 16 | dead << 17
+// dead (h_thresh > 0 only): a same-spin double with |value| <= thr, or an alpha single whose
+// integrals V(v,o,*,*) are all <= thr, i.e. every opposite-spin double through it is dropped.
+__global__ void k_dead_ov(IntsView I, double thr, unsigned char* __restrict__ dead /* n*n */) {
+  const int n = I.n;
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= n * n) return;
+  const size_t n2 = size_t(n) * n;
+  bool all_small = thr > 0.0;
+  for (size_t pq = 0; pq < n2 && all_small; ++pq) all_small = fabs(I.V[t + pq * n2]) <= thr;
+  dead[t] = all_small ? 1 : 0;
+}
+// one warp per string; IS_ALPHA: entries of the alpha-run adjacency (orientation by run index),
+// else entries of a beta adjacency list (orientation by template index)
+template <bool IS_ALPHA>
+__global__ void __launch_bounds__(256)
+k_pair_meta(IntsView I, const uint64_t* __restrict__ str, int32_t nstr,
+            const int64_t* __restrict__ adj_ptr, const uint32_t* __restrict__ adj, double thr,
+            const unsigned char* __restrict__ dead_ov, uint32_t* __restrict__ meta,
+            double* __restrict__ val, int32_t* __restrict__ deg4 /* alpha: 4 per run */) {
+  const int lane = threadIdx.x & 31;
+  const int64_t r = (int64_t(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+  if (r >= nstr) return;
+  const uint64_t s = str[r];
+  int c0 = 0, c2live = 0, c2dead = 0, c4live = 0;
+  for (int64_t e = adj_ptr[r] + lane; e < adj_ptr[r + 1]; e += 32) {
+    const uint32_t pk = adj[e];
+    const int64_t r2 = pk >> 2;
+    const int dc = int(pk & 3u);
+    const uint64_t s2 = str[r2];
+    const uint64_t bra = r < r2 ? s : s2, ket = r < r2 ? s2 : s;
+    uint32_t m = 0;
+    double v = 0.;
+    if (dc == 2) {
+      v = me4(I, bra, ket, bra ^ ket);
+      const bool dd = thr > 0.0 && !(fabs(v) > thr);
+      m = dd ? (1u << 17) : 0u;
+      if (!dd) ++c4live;
+    } else if (dc == 1) {
+      unsigned o, vv;
+      double sg;
+      sx_sign_indices(bra, ket, bra ^ ket, o, vv, sg);
+      const bool dd = dead_ov[vv + o * I.n] != 0;
+      m = o | (vv << 8) | (sg < 0 ? (1u << 16) : 0u) | (dd ? (1u << 17) : 0u);
+      if (dd) ++c2dead; else ++c2live;
+    } else {
+      ++c0;
+    }
+    meta[e] = m;
+    if (val) val[e] = v;
+  }
+  if (IS_ALPHA) {
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) {
+      c0 += __shfl_down_sync(0xffffffffu, c0, d);
+      c2live += __shfl_down_sync(0xffffffffu, c2live, d);
+      c2dead += __shfl_down_sync(0xffffffffu, c2dead, d);
+      c4live += __shfl_down_sync(0xffffffffu, c4live, d);
+    }
+    if (lane == 0) {
+      deg4[4 * r] = c0; deg4[4 * r + 1] = c2live; deg4[4 * r + 2] = c2dead; deg4[4 * r + 3] = c4live;
+    }
+  }
+}
+
+struct ProdArgs {
+  IntsView I;
+  const uint64_t* run_alpha;  // R
+  const uint64_t* tmpl_beta;  // Nb
+  const int64_t* adj_ptr;     // alpha-run adjacency
+  const uint32_t* adj;
+  const uint32_t* a_meta;     // per alpha adjacency entry
+  const double* a_val;        // same-spin (alpha) double values
+  const int32_t* run_deg;     // 4 per run: d0, d2 live, d2 dead, d4 live
+  const int64_t* b2_ptr;      // beta adjacency, distance <= 2
+  const uint32_t* b2;
+  const uint32_t* b2_meta;
+  const int64_t* b4_ptr;      // distance <= 4
+  const uint32_t* b4;
+  const double* b4_val;       // same-spin (beta) double values
+  int64_t nb;
+  int64_t row_begin;
+  int64_t nrows;
+  double thr;
+  int32_t* row_cnt;           // structural count (count kernel) / surviving count (fill kernel)
+  const int64_t* rowptr;      // slot offsets of the fill kernel
+  int32_t* colind;
+  double* nzval;
+};
+
+__global__ void k_prod_struct_count(const ProdArgs A) {
+  const int64_t row = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (row >= A.nrows) return;
+  const int64_t i = A.row_begin + row;
+  const int64_t r = i / A.nb, k = i % A.nb;
+  const int64_t l2 = A.b2_ptr[k + 1] - A.b2_ptr[k], l4 = A.b4_ptr[k + 1] - A.b4_ptr[k];
+  const int32_t* d = A.run_deg + 4 * r;
+  const int64_t c = int64_t(d[0]) * l4 + int64_t(d[1]) * l2 + int64_t(d[2]) + int64_t(d[3]);
+  A.row_cnt[row] = int32_t(c);
+}
+
+template <bool EVAL>
+__global__ void __launch_bounds__(ROW_WARPS * 32)
+k_rows_product(const ProdArgs A) {
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int64_t row = int64_t(blockIdx.x) * ROW_WARPS + w;
+  if (row >= A.nrows) return;
+  const int64_t i = A.row_begin + row;
+  const int64_t r = i / A.nb, k = i % A.nb;
+  const uint64_t ai = A.run_alpha[r], bi = A.tmpl_beta[k];
+  const int64_t b2s = A.b2_ptr[k], b4s = A.b4_ptr[k];
+  const int len2 = int(A.b2_ptr[k + 1] - b2s), len4 = int(A.b4_ptr[k + 1] - b4s);
+  const size_t n = A.I.n, n2 = n * n, n3 = n2 * n;
+  int64_t out = A.rowptr[row];
+  const int64_t out0 = out;
+  const unsigned lt = (1u << lane) - 1u;
+  if (ai != 0) {
+    const int64_t e0 = A.adj_ptr[r], e1 = A.adj_ptr[r + 1];
+    for (int64_t eb = e0; eb < e1; eb += 32) {
+      const int64_t e = eb + lane;
+      const bool ev = e < e1;
+      const uint32_t pk = ev ? A.adj[e] : 0u;
+      const uint32_t am = ev ? A.a_meta[e] : 0u;
+      const int dc = int(pk & 3u);  // alpha distance / 2
+      const bool adead = (am >> 17) & 1u;
+      const int len = !ev ? 0 : (dc == 2 ? (adead ? 0 : 1) : (dc == 1 ? (adead ? 1 : len2) : len4));
+      int incl = len;
+#pragma unroll
+      for (int d = 1; d < 32; d <<= 1) {
+        const int t = __shfl_up_sync(0xffffffffu, incl, d);
+        if (lane >= d) incl += t;
+      }
+      const int excl = incl - len;
+      const int total = __shfl_sync(0xffffffffu, incl, 31);
+      for (int c0 = 0; c0 < total; c0 += 32) {
+        const int c = c0 + lane;
+        const bool act = c < total;
+        // owner entry: the last lane whose exclusive offset is <= c
+        int lo = 0;
+#pragma unroll
+        for (int step = 16; step > 0; step >>= 1) {
+          const int mid = lo + step;
+          const int ex_mid = __shfl_sync(0xffffffffu, excl, mid & 31);
+          if (mid < 32 && ex_mid <= c) lo = mid;
+        }
+        const uint32_t pks = __shfl_sync(0xffffffffu, pk, lo);
+        const uint32_t ams = __shfl_sync(0xffffffffu, am, lo);
+        const int exs = __shfl_sync(0xffffffffu, excl, lo);
+        int32_t j = 0;
+        double v = 0.;
+        bool keep = false;
+        if (act) {
+          const int dcs = int(pks & 3u);
+          const int64_t r2 = pks >> 2;
+          const int t = c - exs;
+          const uint64_t aj = A.run_alpha[r2];
+          if (dcs == 2) {
+            // alpha double: value precomputed per run pair
+            j = int32_t(r2 * A.nb + k);
+            v = A.a_val[eb + lo];
+          } else if (dcs == 1) {
+            if ((ams >> 17) & 1u) {
+              // every opposite-spin double through this alpha single vanishes: k' = k only
+              j = int32_t(r2 * A.nb + k);
+              v = (r < r2) ? matel(A.I, ai, bi, aj, bi) : matel(A.I, aj, bi, ai, bi);
+            } else {
+              const uint32_t bpk = A.b2[b2s + t];
+              const int64_t k2 = bpk >> 2;
+              j = int32_t(r2 * A.nb + k2);
+              if ((bpk & 3u) == 0) {
+                v = (r < r2) ? matel(A.I, ai, bi, aj, bi) : matel(A.I, aj, bi, ai, bi);
+              } else {
+                const uint32_t bm = A.b2_meta[b2s + t];
+                const unsigned o1 = ams & 0xFFu, v1 = (ams >> 8) & 0xFFu;
+                unsigned o2 = bm & 0xFFu, v2 = (bm >> 8) & 0xFFu;  // stored with bra = lower template index
+                const bool swap_b = (r < r2) != (k < k2);          // bra determinant holds beta_k2
+                if (swap_b) { const unsigned tmp = o2; o2 = v2; v2 = tmp; }
+                const double sa = ((ams >> 16) & 1u) ? -1. : 1.;
+                const double sb = ((bm >> 16) & 1u) ? -1. : 1.;
+                const double sign = sa * sb;
+                v = sign * ldg(A.I.V + v1 + o1 * n + v2 * n2 + o2 * n3);
+              }
+            }
+          } else {
+            const uint32_t bpk = A.b4[b4s + t];
+            const int64_t k2 = bpk >> 2;
+            j = int32_t(r2 * A.nb + k2);
+            if ((bpk & 3u) == 2) {
+              v = A.b4_val[b4s + t];  // beta double: value precomputed per template pair
+            } else {
+              const uint64_t bj = A.tmpl_beta[k2];
+              v = (i <= int64_t(j)) ? matel(A.I, ai, bi, aj, bj) : matel(A.I, aj, bj, ai, bi);
+            }
+          }
+          keep = EVAL ? (fabs(v) > A.thr) : true;
+        }
+        const unsigned km = __ballot_sync(0xffffffffu, keep);
+        if (keep) {
+          const int64_t pos = out + __popc(km & lt);
+          A.colind[pos] = j;
+          A.nzval[pos] = v;
+        }
+        out += __popc(km);
+      }
+    }
+  }
+  if (lane == 0) A.row_cnt[row] = int32_t(out - out0);
+}
+
+// move the surviving prefix of every structural row slot to its final position
+__global__ void __launch_bounds__(ROW_WARPS * 32)
+k_compact_rows(int64_t nrows, const int64_t* __restrict__ slot_ptr,
+               const int64_t* __restrict__ rowptr, const int32_t* __restrict__ ci_in,
+               const double* __restrict__ nz_in, int32_t* __restrict__ ci_out,
+               double* __restrict__ nz_out) {
+  const int lane = threadIdx.x & 31;
+  const int64_t row = (int64_t(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+  if (row >= nrows) return;
+  const int64_t src = slot_ptr[row], dst = rowptr[row], len = rowptr[row + 1] - dst;
+  for (int64_t t = lane; t < len; t += 32) {
+    ci_out[dst + t] = ci_in[src + t];
+    nz_out[dst + t] = nz_in[src + t];
+  }
 }
 
 __global__ void k_unpack_dets(const uint64_t* __restrict__ words, int wpd, int64_t n,
@@ -280,11 +541,13 @@ void hbuild_csr(b2ci_ctx* ctx, const b2ci_dets* dets, int64_t row_begin, int64_t
   const int64_t nrows = row_end - row_begin;
   cudaStream_t st = ctx->stream;
   ctx->timers["h_build.setup"] = ctx->timers["h_build.count"] = ctx->timers["h_build.fill"] = 0.;
+  ctx->timers["h_build.thresh"] = 0.;
 
   DevBuf<int32_t> run_of(n > 0 ? n : 1);
   DevBuf<int64_t> run_start, adj_ptr;
   DevBuf<uint64_t> run_alpha;
   DevBuf<uint32_t> adj;
+  DevBuf<int32_t> run_deg;  // per run: neighbours at alpha distance 0 / 2 / 4
   int32_t nruns = 0;
   out->nrows = nrows;
   out->ncols = n;
@@ -314,9 +577,10 @@ void hbuild_csr(b2ci_ctx* ctx, const b2ci_dets* dets, int64_t row_begin, int64_t
     B2_CHECK_LAUNCH();
     // run adjacency (count, scan, fill)
     DevBuf<int32_t> acnt(nruns);
+    run_deg.alloc(size_t(nruns) * 3);
     adj_ptr.alloc(nruns + 1);
     const unsigned ga = unsigned((int64_t(nruns) * 32 + 255) / 256);
-    k_run_adjacency<false><<<ga, 256, 0, st>>>(run_alpha, nruns, acnt, nullptr, nullptr);
+    k_string_adjacency<false><<<ga, 256, 0, st>>>(run_alpha, nruns, 4, 1, acnt, run_deg, nullptr, nullptr);
     ctx->launches++;
     B2_CHECK_LAUNCH();
     exclusive_scan_i32_to_i64(ctx, acnt, adj_ptr, nruns);
@@ -324,9 +588,148 @@ void hbuild_csr(b2ci_ctx* ctx, const b2ci_dets* dets, int64_t row_begin, int64_t
     B2_CUDA(cudaMemcpyAsync(&nadj, adj_ptr.p + nruns, 8, cudaMemcpyDeviceToHost, st));
     B2_CUDA(cudaStreamSynchronize(st));
     adj.alloc(nadj > 0 ? nadj : 1);
-    k_run_adjacency<true><<<ga, 256, 0, st>>>(run_alpha, nruns, nullptr, adj_ptr, adj);
+    k_string_adjacency<true><<<ga, 256, 0, st>>>(run_alpha, nruns, 4, 1, nullptr, nullptr, adj_ptr, adj);
     ctx->launches++;
     B2_CHECK_LAUNCH();
+  }
+
+  // ---- rectangular (FCI-shaped) lists: product enumeration, no beta scan
+  int64_t nb = 0;
+  bool rect = false;
+  if (nruns > 0 && n % nruns == 0 && !getenv("B2CI_HBUILD_FORCE_SCAN")) {
+    nb = n / nruns;
+    if (nb < (int64_t(1) << 29)) {
+      DevBuf<int> bad(1);
+      B2_CUDA(cudaMemsetAsync(bad, 0, sizeof(int), st));
+      k_check_rect<<<unsigned((n + 255) / 256), 256, 0, st>>>(dets->alpha, dets->beta, n, nb, bad);
+      ctx->launches++;
+      B2_CHECK_LAUNCH();
+      int hbad = 1;
+      B2_CUDA(cudaMemcpyAsync(&hbad, bad, sizeof(int), cudaMemcpyDeviceToHost, st));
+      B2_CUDA(cudaStreamSynchronize(st));
+      rect = hbad == 0;
+    }
+  }
+  ctx->timers["h_build.rectangular"] = rect ? 1. : 0.;
+  if (rect) {
+    DevBuf<int64_t> b2_ptr(nb + 1), b4_ptr(nb + 1);
+    DevBuf<uint32_t> b2, b4;
+    {
+      ScopedTimer t(ctx, "h_build.setup", true);
+      const unsigned gb = unsigned((nb * 32 + 255) / 256);
+      DevBuf<int32_t> bc(nb);
+      for (int pass = 0; pass < 2; ++pass) {
+        const int maxd = pass == 0 ? 2 : 4;
+        DevBuf<int64_t>& ptr = pass == 0 ? b2_ptr : b4_ptr;
+        DevBuf<uint32_t>& lst = pass == 0 ? b2 : b4;
+        k_string_adjacency<false><<<gb, 256, 0, st>>>(dets->beta, int32_t(nb), maxd, 0, bc, nullptr, nullptr, nullptr);
+        ctx->launches++;
+        B2_CHECK_LAUNCH();
+        exclusive_scan_i32_to_i64(ctx, bc, ptr, nb);
+        int64_t tot = 0;
+        B2_CUDA(cudaMemcpyAsync(&tot, ptr.p + nb, 8, cudaMemcpyDeviceToHost, st));
+        B2_CUDA(cudaStreamSynchronize(st));
+        lst.alloc(tot > 0 ? tot : 1);
+        k_string_adjacency<true><<<gb, 256, 0, st>>>(dets->beta, int32_t(nb), maxd, 0, nullptr, nullptr, ptr, lst);
+        ctx->launches++;
+        B2_CHECK_LAUNCH();
+      }
+    }
+    // per-pair metadata (values of same-spin doubles, hole/particle/sign of singles)
+    int64_t nadj_h = 0, nb2_h = 0, nb4_h = 0;
+    B2_CUDA(cudaMemcpyAsync(&nadj_h, adj_ptr.p + nruns, 8, cudaMemcpyDeviceToHost, st));
+    B2_CUDA(cudaMemcpyAsync(&nb2_h, b2_ptr.p + nb, 8, cudaMemcpyDeviceToHost, st));
+    B2_CUDA(cudaMemcpyAsync(&nb4_h, b4_ptr.p + nb, 8, cudaMemcpyDeviceToHost, st));
+    B2_CUDA(cudaStreamSynchronize(st));
+    DevBuf<unsigned char> dead_ov(size_t(ctx->norb) * ctx->norb);
+    DevBuf<uint32_t> a_meta(nadj_h > 0 ? nadj_h : 1), b2_meta(nb2_h > 0 ? nb2_h : 1), b4_meta(nb4_h > 0 ? nb4_h : 1);
+    DevBuf<double> a_val(nadj_h > 0 ? nadj_h : 1), b4_val(nb4_h > 0 ? nb4_h : 1);
+    DevBuf<int32_t> deg4(size_t(nruns) * 4);
+    {
+      ScopedTimer t(ctx, "h_build.setup", true);
+      const int nn = ctx->norb * ctx->norb;
+      k_dead_ov<<<(nn + 127) / 128, 128, 0, st>>>(ctx->ints, thr, dead_ov);
+      k_pair_meta<true><<<unsigned((int64_t(nruns) * 32 + 255) / 256), 256, 0, st>>>(
+          ctx->ints, run_alpha, nruns, adj_ptr, adj, thr, dead_ov, a_meta, a_val, deg4);
+      const unsigned gb = unsigned((nb * 32 + 255) / 256);
+      k_pair_meta<false><<<gb, 256, 0, st>>>(ctx->ints, dets->beta, int32_t(nb), b2_ptr, b2, thr, dead_ov,
+                                             b2_meta, nullptr, nullptr);
+      k_pair_meta<false><<<gb, 256, 0, st>>>(ctx->ints, dets->beta, int32_t(nb), b4_ptr, b4, thr, dead_ov,
+                                             b4_meta, b4_val, nullptr);
+      ctx->launches += 4;
+      B2_CHECK_LAUNCH();
+    }
+    ProdArgs P;
+    P.I = ctx->ints;
+    P.run_alpha = run_alpha;
+    P.tmpl_beta = dets->beta;
+    P.adj_ptr = adj_ptr;
+    P.adj = adj;
+    P.a_meta = a_meta;
+    P.a_val = a_val;
+    P.run_deg = deg4;
+    P.b2_ptr = b2_ptr; P.b2 = b2; P.b2_meta = b2_meta;
+    P.b4_ptr = b4_ptr; P.b4 = b4; P.b4_val = b4_val;
+    P.nb = nb;
+    P.row_begin = row_begin;
+    P.nrows = nrows;
+    P.thr = thr;
+    P.rowptr = nullptr; P.colind = nullptr; P.nzval = nullptr;
+    DevBuf<int64_t> slot_ptr(nrows + 1);
+    int64_t nslots = 0;
+    {
+      ScopedTimer t(ctx, "h_build.count");
+      DevBuf<int32_t> scnt(nrows);
+      P.row_cnt = scnt;
+      k_prod_struct_count<<<unsigned((nrows + 255) / 256), 256, 0, st>>>(P);
+      ctx->launches++;
+      B2_CHECK_LAUNCH();
+      exclusive_scan_i32_to_i64(ctx, scnt, slot_ptr, nrows);
+      B2_CUDA(cudaMemcpyAsync(&nslots, slot_ptr.p + nrows, 8, cudaMemcpyDeviceToHost, st));
+      B2_CUDA(cudaStreamSynchronize(st));
+    }
+    DevBuf<int32_t> ci_s(nslots > 0 ? nslots : 1), kept(nrows);
+    DevBuf<double> nz_s(nslots > 0 ? nslots : 1);
+    {
+      ScopedTimer t(ctx, "h_build.fill");
+      P.row_cnt = kept;
+      P.rowptr = slot_ptr;
+      P.colind = ci_s;
+      P.nzval = nz_s;
+      const unsigned grid = unsigned((nrows + ROW_WARPS - 1) / ROW_WARPS);
+      if (thr > 0.0) k_rows_product<true><<<grid, ROW_WARPS * 32, 0, st>>>(P);
+      else k_rows_product<false><<<grid, ROW_WARPS * 32, 0, st>>>(P);
+      ctx->launches++;
+      B2_CHECK_LAUNCH();
+    }
+    int64_t nnz = nslots;
+    if (thr > 0.0) {
+      // threshold_parallel equivalent: rows were written compacted inside their structural
+      // slots; when something was dropped, pack the rows (csr_matrix.hpp:317-370)
+      ScopedTimer t(ctx, "h_build.thresh");
+      exclusive_scan_i32_to_i64(ctx, kept, rowptr, nrows);
+      B2_CUDA(cudaMemcpyAsync(&nnz, rowptr.p + nrows, 8, cudaMemcpyDeviceToHost, st));
+      B2_CUDA(cudaStreamSynchronize(st));
+      if (nnz != nslots) {
+        DevBuf<int32_t> ci_f(nnz > 0 ? nnz : 1);
+        DevBuf<double> nz_f(nnz > 0 ? nnz : 1);
+        k_compact_rows<<<unsigned((nrows * 32 + ROW_WARPS * 32 - 1) / (ROW_WARPS * 32)), ROW_WARPS * 32, 0, st>>>(
+            nrows, slot_ptr, rowptr, ci_s, nz_s, ci_f, nz_f);
+        ctx->launches++;
+        B2_CHECK_LAUNCH();
+        B2_CUDA(cudaStreamSynchronize(st));
+        ci_s = std::move(ci_f);
+        nz_s = std::move(nz_f);
+      }
+    } else {
+      rowptr = std::move(slot_ptr);
+    }
+    B2_CUDA(cudaStreamSynchronize(st));
+    out->nnz = nnz;
+    out->rowptr = rowptr.take();
+    out->colind = ci_s.take();
+    out->nzval = nz_s.take();
+    return;
   }
 
   RowArgs A;

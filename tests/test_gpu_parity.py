@@ -239,3 +239,32 @@ def test_davidson_uploaded_matrices(ctx):
     M1 = ctx.upload_csr([0, 1], [0], [-3.5])
     E1, X1, nit1, _ = M1.davidson(20, 1e-8)
     assert E1 == -3.5 and X1[0] == 1.0 and nit1 == 0
+
+
+@pytest.mark.parametrize("name", ["small_cas8", "hubbard_4x2", "tiny_cas6"])
+@pytest.mark.parametrize("thr", [EPS, 0.0, 1e-3])
+def test_scan_and_product_paths_agree(ctx, name, thr):
+    """FCI-shaped lists take the product enumeration; B2CI_HBUILD_FORCE_SCAN=1 forces the
+    general XOR/popcount beta scan. Both must give the oracle's matrix bit for bit."""
+    sp = W.config(name)
+    a, b = port.generate_hilbert_space(sp.norb, sp.nalpha, sp.nbeta)
+    ctx.upload_integrals(sp.norb, sp.T, sp.V)
+    dets = ctx.upload_dets(port.pack(a, b), 1)
+    Hp = ctx.hbuild(dets, thr)
+    assert ctx.timer_ms("h_build.rectangular") == 1.0
+    os.environ["B2CI_HBUILD_FORCE_SCAN"] = "1"
+    try:
+        Hs = ctx.hbuild(dets, thr)
+        assert ctx.timer_ms("h_build.rectangular") == 0.0
+    finally:
+        del os.environ["B2CI_HBUILD_FORCE_SCAN"]
+    orp, oci, onz = port.Ham(sp.norb, sp.T, sp.V).hbuild(a, b, thr)
+    for H in (Hp, Hs):
+        rp, ci, nz = H.download()
+        assert np.array_equal(rp, orp) and np.array_equal(ci, oci) and np.array_equal(nz, onz)
+    # row blocks through the product path
+    r0, r1 = len(a) // 3, len(a) // 3 + 777
+    rpb, cib, nzb = ctx.hbuild(dets, thr, (r0, min(r1, len(a)))).download()
+    r1 = min(r1, len(a))
+    assert np.array_equal(rpb, orp[r0:r1 + 1] - orp[r0])
+    assert np.array_equal(cib, oci[orp[r0]:orp[r1]]) and np.array_equal(nzb, onz[orp[r0]:orp[r1]])
