@@ -282,6 +282,7 @@ def run_b200(args):
 
     ev = lambda: torch.cuda.Event(enable_timing=True)
     t_build, t_fill, t_count, t_sigma, t_step, t_e2e = [], [], [], [], [], []
+    t_setup, t_thresh = [], []
     launches0 = None
     nnz_local = 0
     H = None
@@ -312,6 +313,8 @@ def run_b200(args):
             t_step.append(e0.elapsed_time(e1) + e2.elapsed_time(e3))
             t_count.append(ctx.timer_ms("h_build.count"))
             t_fill.append(ctx.timer_ms("h_build.fill"))
+            t_setup.append(ctx.timer_ms("h_build.setup"))
+            t_thresh.append(ctx.timer_ms("h_build.thresh"))
         nnz_local = H.nnz
     barrier()
     wall1 = time.perf_counter()
@@ -387,6 +390,7 @@ def run_b200(args):
                        "row_sharding": f"{world} contiguous row blocks",
                        "l2": "192 MiB buffer rewritten between timed kernels"},
             "hbuild_ms": build_ms, "hbuild_count_ms": count_ms, "hbuild_fill_ms": fill_ms,
+            "hbuild_setup_ms": float(np.mean(t_setup)), "hbuild_thresh_ms": float(np.mean(t_thresh)),
             "sigma_iter_ms": sigma_ms, "sigma_nnz_per_s": nnz_total / (sigma_ms * 1e-3),
             "roofline": {"kernel": "k_rows<FILL> (H-build fill pass)", "bound": "hbm",
                          "achieved": fill_gbs, "peak": hbm_peak, "unit": "GB/s",

@@ -37,6 +37,9 @@ int b2ci_ctx_destroy(b2ci_ctx* ctx);
 int b2ci_ctx_synchronize(b2ci_ctx* ctx);
 /* number of kernels this context has launched so far (bench.py's gpu_launches claim) */
 int64_t b2ci_ctx_launch_count(const b2ci_ctx* ctx);
+/* Device memory of this library is drawn from the device's stream-ordered pool and kept
+ * there when handles are freed; this returns the cached blocks to the driver. */
+int b2ci_ctx_trim(b2ci_ctx* ctx);
 
 /* ---- multi-GPU (one process per GPU). Replaces MACIS' MPI communicator argument
  * (solvers/selected_ci_diag.hpp:181, solvers/davidson.hpp:391-688). The 128-byte id is

@@ -49,6 +49,7 @@ def lib():
     L.b2ci_ctx_synchronize.argtypes = [vp]
     L.b2ci_ctx_launch_count.restype = i64
     L.b2ci_ctx_launch_count.argtypes = [vp]
+    L.b2ci_ctx_trim.argtypes = [vp]
     L.b2ci_comm_unique_id.argtypes = [vp]
     L.b2ci_comm_init.argtypes = [vp, vp, i32, i32]
     L.b2ci_comm_rank.argtypes = [vp, C.POINTER(i32), C.POINTER(i32)]

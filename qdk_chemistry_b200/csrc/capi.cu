@@ -10,6 +10,10 @@ namespace b2ci {
 
 static thread_local std::string g_last_error;
 void set_error(const std::string& msg) { g_last_error = msg; }
+cudaStream_t& alloc_stream() {
+  static thread_local cudaStream_t s = nullptr;
+  return s;
+}
 
 // implemented in the other translation units
 void integrals_upload(b2ci_ctx* ctx, int norb, const double* T, const double* V);
@@ -44,6 +48,10 @@ __global__ void k_i64_to_i32(const int64_t* __restrict__ in, int64_t n, int32_t*
 using namespace b2ci;
 
 #define B2_TRY try {
+#define B2_TRY_CTX(ctx)                                            \
+  try {                                                            \
+    if (!(ctx)) throw b2ci::Error("null b2ci context");            \
+    b2ci::StreamScope _scope(ctx);
 #define B2_CATCH                                   \
   }                                                \
   catch (const b2ci::Error& e) {                   \
@@ -75,6 +83,11 @@ int b2ci_ctx_create(int device, void* stream, b2ci_ctx** out) {
   if (prop.major < 10)
     throw Error("b2ci_ctx_create: kernels are built for sm_100a only; device is sm_" +
                 std::to_string(prop.major) + std::to_string(prop.minor));
+  // keep freed blocks in the device's stream-ordered pool (see common.cuh)
+  cudaMemPool_t pool;
+  B2_CUDA(cudaDeviceGetDefaultMemPool(&pool, device));
+  uint64_t keep = UINT64_MAX;
+  B2_CUDA(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep));
   b2ci_ctx* c = new b2ci_ctx;
   c->device = device;
   c->stream = (cudaStream_t)stream;
@@ -86,19 +99,32 @@ int b2ci_ctx_create(int device, void* stream, b2ci_ctx** out) {
 int b2ci_ctx_destroy(b2ci_ctx* ctx) {
   B2_TRY
   if (!ctx) return 0;
-  comm_destroy(ctx);
-  if (ctx->ints_dev) cudaFree(ctx->ints_dev);
+  {
+    StreamScope scope(ctx);
+    comm_destroy(ctx);
+    dev_free(ctx->ints_dev);
+    cudaStreamSynchronize(ctx->stream);
+  }
   delete ctx;
   return 0;
   B2_CATCH
 }
 int b2ci_ctx_synchronize(b2ci_ctx* ctx) {
-  B2_TRY
+  B2_TRY_CTX(ctx)
   B2_CUDA(cudaStreamSynchronize(ctx->stream));
   return 0;
   B2_CATCH
 }
 int64_t b2ci_ctx_launch_count(const b2ci_ctx* ctx) { return ctx ? ctx->launches : 0; }
+int b2ci_ctx_trim(b2ci_ctx* ctx) {
+  B2_TRY_CTX(ctx)
+  B2_CUDA(cudaStreamSynchronize(ctx->stream));
+  cudaMemPool_t pool;
+  B2_CUDA(cudaDeviceGetDefaultMemPool(&pool, ctx->device));
+  B2_CUDA(cudaMemPoolTrimTo(pool, 0));
+  return 0;
+  B2_CATCH
+}
 
 int b2ci_comm_unique_id(void* id128) {
   B2_TRY
@@ -107,7 +133,7 @@ int b2ci_comm_unique_id(void* id128) {
   B2_CATCH
 }
 int b2ci_comm_init(b2ci_ctx* ctx, const void* id128, int rank, int nranks) {
-  B2_TRY
+  B2_TRY_CTX(ctx)
   comm_init(ctx, id128, rank, nranks);
   return 0;
   B2_CATCH
@@ -119,14 +145,14 @@ int b2ci_comm_rank(const b2ci_ctx* ctx, int* rank, int* nranks) {
 }
 
 int b2ci_integrals_upload(b2ci_ctx* ctx, int norb, const double* T, const double* V) {
-  B2_TRY
+  B2_TRY_CTX(ctx)
   integrals_upload(ctx, norb, T, V);
   return 0;
   B2_CATCH
 }
 int b2ci_integrals_download(b2ci_ctx* ctx, double* G_red, double* V_red, double* G2_red,
                             double* V2_red) {
-  B2_TRY
+  B2_TRY_CTX(ctx)
   if (!ctx->ints_dev) throw Error("integrals not uploaded");
   const size_t n = ctx->norb, n2 = n * n, n3 = n2 * n;
   const IntsView h = make_view(ctx->norb, ctx->ints_host.data());
@@ -139,7 +165,7 @@ int b2ci_integrals_download(b2ci_ctx* ctx, double* G_red, double* V_red, double*
 }
 
 int b2ci_dets_upload(b2ci_ctx* ctx, const uint64_t* words, int wpd, int64_t n, b2ci_dets** out) {
-  B2_TRY
+  B2_TRY_CTX(ctx)
   if (n < 0 || (n > 0 && !words)) throw Error("b2ci_dets_upload: bad arguments");
   b2ci_dets* d = new b2ci_dets;
   try { dets_from_words(ctx, words, wpd, n, d); } catch (...) { delete d; throw; }
@@ -148,7 +174,7 @@ int b2ci_dets_upload(b2ci_ctx* ctx, const uint64_t* words, int wpd, int64_t n, b
   B2_CATCH
 }
 int b2ci_dets_generate_fci(b2ci_ctx* ctx, int norb, int na, int nb, b2ci_dets** out) {
-  B2_TRY
+  B2_TRY_CTX(ctx)
   b2ci_dets* d = new b2ci_dets;
   try { dets_generate_fci(ctx, norb, na, nb, d); } catch (...) { delete d; throw; }
   *out = d;
@@ -160,23 +186,23 @@ int b2ci_dets_size(const b2ci_dets* d, int64_t* n) {
   return 0;
 }
 int b2ci_dets_download(b2ci_ctx* ctx, const b2ci_dets* d, uint64_t* words, int wpd) {
-  B2_TRY
+  B2_TRY_CTX(ctx)
   dets_to_words(ctx, d, words, wpd);
   return 0;
   B2_CATCH
 }
 int b2ci_dets_free(b2ci_ctx* ctx, b2ci_dets* d) {
-  (void)ctx;
   if (!d) return 0;
-  if (d->alpha) cudaFree(d->alpha);
-  if (d->beta) cudaFree(d->beta);
+  StreamScope scope(ctx);
+  dev_free(d->alpha);
+  dev_free(d->beta);
   delete d;
   return 0;
 }
 
 int b2ci_hbuild_csr(b2ci_ctx* ctx, const b2ci_dets* dets, int64_t row_begin, int64_t row_end,
                     double h_thresh, b2ci_csr** out) {
-  B2_TRY
+  B2_TRY_CTX(ctx)
   b2ci_csr* m = new b2ci_csr;
   try { hbuild_csr(ctx, dets, row_begin, row_end, h_thresh, m); } catch (...) { delete m; throw; }
   *out = m;
@@ -185,7 +211,7 @@ int b2ci_hbuild_csr(b2ci_ctx* ctx, const b2ci_dets* dets, int64_t row_begin, int
 }
 int b2ci_csr_upload(b2ci_ctx* ctx, int64_t n, int64_t nnz, const int64_t* rowptr,
                     const int64_t* colind, const double* nzval, b2ci_csr** out) {
-  B2_TRY
+  B2_TRY_CTX(ctx)
   if (n < 0 || nnz < 0 || !rowptr) throw Error("b2ci_csr_upload: bad arguments");
   if (n >= (int64_t(1) << 31)) throw Error("b2ci_csr_upload: dimension exceeds int32 column indices");
   if (rowptr[0] != 0 || rowptr[n] != nnz) throw Error("b2ci_csr_upload: rowptr must be 0-based and end at nnz");
@@ -219,7 +245,7 @@ int b2ci_csr_info(const b2ci_csr* m, int64_t* nrows, int64_t* ncols, int64_t* nn
 }
 int b2ci_csr_download(b2ci_ctx* ctx, const b2ci_csr* m, int64_t* rowptr, int64_t* colind,
                       double* nzval) {
-  B2_TRY
+  B2_TRY_CTX(ctx)
   cudaStream_t st = ctx->stream;
   if (rowptr) B2_CUDA(cudaMemcpyAsync(rowptr, m->rowptr, size_t(m->nrows + 1) * 8, cudaMemcpyDeviceToHost, st));
   if (m->nnz && colind) {
@@ -248,23 +274,23 @@ int b2ci_csr_device_ptrs(const b2ci_csr* m, const int64_t** rowptr, const int32_
   return 0;
 }
 int b2ci_csr_free(b2ci_ctx* ctx, b2ci_csr* m) {
-  (void)ctx;
   if (!m) return 0;
-  if (m->rowptr) cudaFree(m->rowptr);
-  if (m->colind) cudaFree(m->colind);
-  if (m->nzval) cudaFree(m->nzval);
+  StreamScope scope(ctx);
+  dev_free(m->rowptr);
+  dev_free(m->colind);
+  dev_free(m->nzval);
   delete m;
   return 0;
 }
 
 int b2ci_spmv(b2ci_ctx* ctx, const b2ci_csr* m, const double* x_dev, double* y_dev) {
-  B2_TRY
+  B2_TRY_CTX(ctx)
   spmv_launch(ctx, m, x_dev, y_dev);
   return 0;
   B2_CATCH
 }
 int b2ci_spmv_host(b2ci_ctx* ctx, const b2ci_csr* m, const double* x, double* y) {
-  B2_TRY
+  B2_TRY_CTX(ctx)
   DevBuf<double> dx(m->ncols > 0 ? m->ncols : 1), dy(m->nrows > 0 ? m->nrows : 1);
   cudaStream_t st = ctx->stream;
   B2_CUDA(cudaMemcpyAsync(dx, x, size_t(m->ncols) * 8, cudaMemcpyHostToDevice, st));
@@ -276,7 +302,7 @@ int b2ci_spmv_host(b2ci_ctx* ctx, const b2ci_csr* m, const double* x, double* y)
 }
 int b2ci_sigma_sharded(b2ci_ctx* ctx, const b2ci_csr* m, const double* x_local_dev,
                        double* x_full_dev, double* y_local_dev) {
-  B2_TRY
+  B2_TRY_CTX(ctx)
   if (ctx->nranks == 1) {
     spmv_launch(ctx, m, x_local_dev, y_local_dev);
     return 0;
@@ -296,7 +322,7 @@ int b2ci_sigma_sharded(b2ci_ctx* ctx, const b2ci_csr* m, const double* x_local_d
   B2_CATCH
 }
 int b2ci_csr_diagonal(b2ci_ctx* ctx, const b2ci_csr* m, double* D) {
-  B2_TRY
+  B2_TRY_CTX(ctx)
   DevBuf<double> d(m->nrows > 0 ? m->nrows : 1);
   csr_diagonal_dev(ctx, m, d);
   B2_CUDA(cudaMemcpyAsync(D, d, size_t(m->nrows) * 8, cudaMemcpyDeviceToHost, ctx->stream));
@@ -307,7 +333,7 @@ int b2ci_csr_diagonal(b2ci_ctx* ctx, const b2ci_csr* m, double* D) {
 
 int b2ci_davidson(b2ci_ctx* ctx, const b2ci_csr* m, int64_t max_m, double tol, double* X,
                   int use_guess_policy, int64_t* niter, double* eigval, double* trace) {
-  B2_TRY
+  B2_TRY_CTX(ctx)
   int64_t it = 0;
   double ev = 0.;
   const int rc = davidson(ctx, m, max_m, tol, X, use_guess_policy, &it, &ev, trace);
@@ -325,7 +351,7 @@ double b2ci_timer_ms(const b2ci_ctx* ctx, const char* name) {
 int b2ci_asci_search(b2ci_ctx* ctx, const b2ci_asci_search_opts* opts, const uint64_t* core_words,
                      int wpd, const double* core_coeffs, int64_t ncdets, double E0,
                      uint64_t* out_words, int64_t cap, int64_t* n_out, double* stats) {
-  B2_TRY
+  B2_TRY_CTX(ctx)
   return asci_search(ctx, opts, core_words, wpd, core_coeffs, ncdets, E0, out_words, cap, n_out, stats,
                      nullptr, nullptr, nullptr, nullptr, false);
   B2_CATCH
@@ -333,7 +359,7 @@ int b2ci_asci_search(b2ci_ctx* ctx, const b2ci_asci_search_opts* opts, const uin
 int b2ci_asci_candidates(b2ci_ctx* ctx, const b2ci_asci_search_opts* opts, const uint64_t* core_words,
                          int wpd, const double* core_coeffs, int64_t ncdets, double E0,
                          uint64_t* out_words, double* out_cmatel, double* out_hdiag, int64_t* n_out) {
-  B2_TRY
+  B2_TRY_CTX(ctx)
   return asci_search(ctx, opts, core_words, wpd, core_coeffs, ncdets, E0, nullptr, 0, nullptr, nullptr,
                      out_words, out_cmatel, out_hdiag, n_out, true);
   B2_CATCH

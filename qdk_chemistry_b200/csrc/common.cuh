@@ -102,6 +102,35 @@ struct b2ci_csr {
 
 namespace b2ci {
 
+// Device memory comes from the device's stream-ordered pool (cudaMallocAsync) with the release
+// threshold lifted in b2ci_ctx_create, so the multi-GB CSR / slot buffers of repeated builds are
+// recycled instead of going back to the driver (a cudaMalloc + cudaFree pair of 14 GB costs
+// ~100 ms, ten times the kernels it serves). Every C-ABI entry that takes a context opens a
+// StreamScope; allocations and frees are ordered on that context's stream.
+cudaStream_t& alloc_stream();  // thread-local, set by StreamScope
+inline void* dev_alloc(size_t bytes) {
+  void* p = nullptr;
+  cudaError_t e = cudaMallocAsync(&p, bytes, alloc_stream());
+  if (e != cudaSuccess) {
+    cudaGetLastError();
+    throw Error("device allocation of " + std::to_string(bytes) + " bytes failed: " + cudaGetErrorString(e));
+  }
+  return p;
+}
+inline void dev_free(void* p) {
+  if (p) cudaFreeAsync(p, alloc_stream());
+}
+struct StreamScope {
+  cudaStream_t prev;
+  explicit StreamScope(const b2ci_ctx* ctx) : prev(alloc_stream()) {
+    if (ctx) {
+      cudaSetDevice(ctx->device);
+      alloc_stream() = ctx->stream;
+    }
+  }
+  ~StreamScope() { alloc_stream() = prev; }
+};
+
 // RAII device buffer
 template <typename T>
 struct DevBuf {
@@ -120,17 +149,10 @@ struct DevBuf {
   void alloc(size_t count) {
     release();
     n = count;
-    if (count) {
-      cudaError_t e = cudaMalloc((void**)&p, count * sizeof(T));
-      if (e != cudaSuccess) {
-        p = nullptr;
-        throw Error("cudaMalloc of " + std::to_string(count * sizeof(T)) + " bytes failed: " +
-                    cudaGetErrorString(e));
-      }
-    }
+    if (count) p = static_cast<T*>(dev_alloc(count * sizeof(T)));
   }
   void release() {
-    if (p) cudaFree(p);
+    dev_free(p);
     p = nullptr;
     n = 0;
   }

@@ -200,13 +200,19 @@ __global__ void k_check_rect(const uint64_t* __restrict__ alpha, const uint64_t*
 }
 
 // Per-pair metadata, computed once per (alpha run pair) / (beta template pair) instead of once
-// per matrix element. Same-spin doubles depend on one spin string pair only, so their VALUE is
-// precomputed; for single excitations the (hole, particle, sign) triple is precomputed so an
-// opposite-spin double costs one integral load:  sign_a * sign_b * V(v1,o1,v2,o2)
-// (matrix_elements.hpp:140-151). Orientation: bra = lower determinant index, as the reference.
+// per matrix element. Orientation everywhere: bra = lower determinant index, as the reference
+// (it evaluates the upper triangle and mirrors it).
+//   same-spin double : the VALUE  sign * (V(v1,o1,v2,o2) - V(v1,o2,v2,o1))  (matrix_elements.hpp:113-121)
+//   single           : (hole, particle, sign) and the leading part of the single-excitation sum
+//                      T(v,o) + sum_{p in occ_same(bra), ascending} G_red(p,v,o)   (:176-182);
+//                      the kernel appends the other-spin terms V_red(p,v,o) in ascending p,
+//                      i.e. the additions happen in exactly the reference's order.
+//                      An opposite-spin double through two singles is one integral load:
+//                      sign_a * sign_b * V(v1,o1,v2,o2)  (:140-151).
 //   meta = o | v << 8 | (sign < 0) << 16 | dead << 17
-// dead (h_thresh > 0 only): a same-spin double with |value| <= thr, or an alpha single whose
-// integrals V(v,o,*,*) are all <= thr, i.e. every opposite-spin double through it is dropped.
+// dead (h_thresh > 0 only): a same-spin double with |value| <= thr (dropped outright), or an
+// alpha single whose integrals V(v,o,*,*) are all <= thr, i.e. every opposite-spin double
+// through it would be dropped, so only its k' = k element is enumerated.
 __global__ void k_dead_ov(IntsView I, double thr, unsigned char* __restrict__ dead /* n*n */) {
   const int n = I.n;
   const int t = blockIdx.x * blockDim.x + threadIdx.x;
@@ -216,19 +222,24 @@ __global__ void k_dead_ov(IntsView I, double thr, unsigned char* __restrict__ de
   for (size_t pq = 0; pq < n2 && all_small; ++pq) all_small = fabs(I.V[t + pq * n2]) <= thr;
   dead[t] = all_small ? 1 : 0;
 }
-// one warp per string; IS_ALPHA: entries of the alpha-run adjacency (orientation by run index),
-// else entries of a beta adjacency list (orientation by template index)
-template <bool IS_ALPHA>
+__device__ __forceinline__ double single_lead_sum(const IntsView& I, uint64_t occ_same, unsigned o,
+                                                  unsigned v) {
+  const size_t n = I.n;
+  double h = ldg(I.T + v + o * n);
+  const double* G = I.G + v * n + o * n * n;
+  for (uint64_t s = occ_same; s; s &= s - 1) h += ldg(G + lsb64(s));
+  return h;
+}
+// one warp per string: meta / val of every adjacency entry
 __global__ void __launch_bounds__(256)
 k_pair_meta(IntsView I, const uint64_t* __restrict__ str, int32_t nstr,
             const int64_t* __restrict__ adj_ptr, const uint32_t* __restrict__ adj, double thr,
             const unsigned char* __restrict__ dead_ov, uint32_t* __restrict__ meta,
-            double* __restrict__ val, int32_t* __restrict__ deg4 /* alpha: 4 per run */) {
+            double* __restrict__ val) {
   const int lane = threadIdx.x & 31;
   const int64_t r = (int64_t(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
   if (r >= nstr) return;
   const uint64_t s = str[r];
-  int c0 = 0, c2live = 0, c2dead = 0, c4live = 0;
   for (int64_t e = adj_ptr[r] + lane; e < adj_ptr[r + 1]; e += 32) {
     const uint32_t pk = adj[e];
     const int64_t r2 = pk >> 2;
@@ -239,33 +250,105 @@ k_pair_meta(IntsView I, const uint64_t* __restrict__ str, int32_t nstr,
     double v = 0.;
     if (dc == 2) {
       v = me4(I, bra, ket, bra ^ ket);
-      const bool dd = thr > 0.0 && !(fabs(v) > thr);
-      m = dd ? (1u << 17) : 0u;
-      if (!dd) ++c4live;
+      if (thr > 0.0 && !(fabs(v) > thr)) m = 1u << 17;
     } else if (dc == 1) {
       unsigned o, vv;
       double sg;
       sx_sign_indices(bra, ket, bra ^ ket, o, vv, sg);
-      const bool dd = dead_ov[vv + o * I.n] != 0;
+      const bool dd = dead_ov && dead_ov[vv + o * I.n] != 0;
       m = o | (vv << 8) | (sg < 0 ? (1u << 16) : 0u) | (dd ? (1u << 17) : 0u);
-      if (dd) ++c2dead; else ++c2live;
-    } else {
-      ++c0;
+      v = single_lead_sum(I, bra, o, vv);
     }
     meta[e] = m;
-    if (val) val[e] = v;
+    val[e] = v;
   }
-  if (IS_ALPHA) {
-#pragma unroll
-    for (int d = 16; d > 0; d >>= 1) {
-      c0 += __shfl_down_sync(0xffffffffu, c0, d);
-      c2live += __shfl_down_sync(0xffffffffu, c2live, d);
-      c2dead += __shfl_down_sync(0xffffffffu, c2dead, d);
-      c4live += __shfl_down_sync(0xffffffffu, c4live, d);
+}
+
+// Compacted alpha-run adjacency: entries that enumerate at least one column, in ascending run
+// order, each with the number of live-single and unit-length entries that precede it in its
+// run. With len2(k) / len4(k) the lengths of the beta lists of row (r, k), entry e starts at
+//   (r2 > r ? len4 : 0) + nlive_before * len2 + nunit_before
+// inside the row -- position -> entry needs no search structure per row.
+struct __align__(16) ARec {
+  uint32_t r2t;   // run index << 2 | kind: 0 self, 1 live single, 2 unit (double, or dead single)
+  uint32_t meta;  // o | v << 8 | sign << 16 | is_single << 18   (singles)
+  uint32_t nlive; // live singles before this entry
+  uint32_t nunit; // unit entries before this entry
+};
+template <bool FILL>
+__global__ void __launch_bounds__(256)
+k_adj_compact(const uint64_t* __restrict__ str, int32_t nstr, const int64_t* __restrict__ adj_ptr,
+              const uint32_t* __restrict__ adj, const uint32_t* __restrict__ meta,
+              const double* __restrict__ val, int32_t* __restrict__ cnt /* 4 per run */,
+              const int64_t* __restrict__ cptr, ARec* __restrict__ crec, double* __restrict__ cval) {
+  const int lane = threadIdx.x & 31;
+  const int64_t r = (int64_t(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+  if (r >= nstr) return;
+  const unsigned lt = (1u << lane) - 1u;
+  int64_t out = FILL ? cptr[r] : 0;
+  uint32_t nself = 0, nlive = 0, nunit = 0;
+  const int64_t e0 = adj_ptr[r], e1 = adj_ptr[r + 1];
+  for (int64_t eb = e0; eb < e1; eb += 32) {
+    const int64_t e = eb + lane;
+    const bool ev = e < e1;
+    const uint32_t pk = ev ? adj[e] : 0u;
+    const uint32_t m = ev ? meta[e] : 0u;
+    const int dc = int(pk & 3u);
+    const bool dead = (m >> 17) & 1u;
+    const bool is_self = ev && dc == 0, is_live = ev && dc == 1 && !dead;
+    const bool is_unit = ev && ((dc == 1 && dead) || (dc == 2 && !dead));
+    const unsigned ms = __ballot_sync(0xffffffffu, is_self);
+    const unsigned ml = __ballot_sync(0xffffffffu, is_live);
+    const unsigned mu = __ballot_sync(0xffffffffu, is_unit);
+    if (FILL && (is_self || is_live || is_unit)) {
+      ARec rec;
+      rec.r2t = (pk & ~3u) | (is_self ? 0u : (is_live ? 1u : 2u));
+      rec.meta = (m & 0x1FFFFu) | (dc == 1 ? (1u << 18) : 0u);
+      rec.nlive = nlive + __popc(ml & lt);
+      rec.nunit = nunit + __popc(mu & lt);
+      const int64_t pos = out + __popc((ms | ml | mu) & lt);
+      crec[pos] = rec;
+      cval[pos] = val[e];
     }
-    if (lane == 0) {
-      deg4[4 * r] = c0; deg4[4 * r + 1] = c2live; deg4[4 * r + 2] = c2dead; deg4[4 * r + 3] = c4live;
-    }
+    out += __popc(ms | ml | mu);
+    nself += __popc(ms);
+    nlive += __popc(ml);
+    nunit += __popc(mu);
+  }
+  if (!FILL && lane == 0) {
+    cnt[4 * r] = int32_t(nself + nlive + nunit);
+    cnt[4 * r + 1] = int32_t(nself);
+    cnt[4 * r + 2] = int32_t(nlive);
+    cnt[4 * r + 3] = int32_t(nunit);
+  }
+}
+
+// Beta-side records of the two lists of template string k.
+//   B2 (distance <= 2): k2, V offset of the (particle, hole) pair in both orientations, sign
+//   B4 (distance <= 4): k2 << 2 | distance / 2, meta; value (double) or leading sum (single)
+struct __align__(16) B2Rec {
+  uint32_t k2;
+  uint32_t offa;  // v2 n^2 + o2 n^3 (bra = lower template index) | sign << 31 | is_self << 30
+  uint32_t offb;  // o2 n^2 + v2 n^3 (orientation swapped)        | (k2 > k) << 31
+  uint32_t pad;
+};
+__global__ void __launch_bounds__(256)
+k_beta_rec(int n, int32_t nstr, const int64_t* __restrict__ b2_ptr, const uint32_t* __restrict__ b2,
+           const uint32_t* __restrict__ b2_meta, B2Rec* __restrict__ rec) {
+  const int lane = threadIdx.x & 31;
+  const int64_t k = (int64_t(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+  if (k >= nstr) return;
+  const uint32_t n2 = uint32_t(n) * n, n3 = n2 * n;
+  for (int64_t e = b2_ptr[k] + lane; e < b2_ptr[k + 1]; e += 32) {
+    const uint32_t pk = b2[e], m = b2_meta[e];
+    const uint32_t k2 = pk >> 2;
+    const uint32_t o = m & 0xFFu, v = (m >> 8) & 0xFFu;
+    B2Rec r;
+    r.k2 = k2;
+    r.offa = (v * n2 + o * n3) | (((m >> 16) & 1u) << 31) | ((pk & 3u) == 0 ? (1u << 30) : 0u);
+    r.offb = (o * n2 + v * n3) | (k2 > uint32_t(k) ? (1u << 31) : 0u);
+    r.pad = 0;
+    rec[e] = r;
   }
 }
 
@@ -273,17 +356,16 @@ struct ProdArgs {
   IntsView I;
   const uint64_t* run_alpha;  // R
   const uint64_t* tmpl_beta;  // Nb
-  const int64_t* adj_ptr;     // alpha-run adjacency
-  const uint32_t* adj;
-  const uint32_t* a_meta;     // per alpha adjacency entry
-  const double* a_val;        // same-spin (alpha) double values
-  const int32_t* run_deg;     // 4 per run: d0, d2 live, d2 dead, d4 live
+  const int64_t* cptr;        // compacted alpha-run adjacency
+  const ARec* crec;
+  const double* cval;
+  const int32_t* run_cnt;     // 4 per run: entries, self, live singles, unit
   const int64_t* b2_ptr;      // beta adjacency, distance <= 2
-  const uint32_t* b2;
-  const uint32_t* b2_meta;
+  const B2Rec* b2rec;
   const int64_t* b4_ptr;      // distance <= 4
   const uint32_t* b4;
-  const double* b4_val;       // same-spin (beta) double values
+  const uint32_t* b4_meta;
+  const double* b4_val;
   int64_t nb;
   int64_t row_begin;
   int64_t nrows;
@@ -300,11 +382,19 @@ __global__ void k_prod_struct_count(const ProdArgs A) {
   const int64_t i = A.row_begin + row;
   const int64_t r = i / A.nb, k = i % A.nb;
   const int64_t l2 = A.b2_ptr[k + 1] - A.b2_ptr[k], l4 = A.b4_ptr[k + 1] - A.b4_ptr[k];
-  const int32_t* d = A.run_deg + 4 * r;
-  const int64_t c = int64_t(d[0]) * l4 + int64_t(d[1]) * l2 + int64_t(d[2]) + int64_t(d[3]);
+  const int32_t* d = A.run_cnt + 4 * r;
+  const int64_t c = int64_t(d[1]) * l4 + int64_t(d[2]) * l2 + int64_t(d[3]);
   A.row_cnt[row] = int32_t(c);
 }
 
+__device__ __forceinline__ double flip_sign_if(double v, bool neg) {
+  return __longlong_as_double(__double_as_longlong(v) ^ (neg ? (long long)0x8000000000000000ull : 0ll));
+}
+
+// One warp per row. Output positions are produced 32 at a time; the warp keeps a window of 32
+// consecutive adjacency entries starting at the entry that holds the first position of the
+// batch, every window lane marks the batch-relative start of its entry in a 32-bit mask
+// (one redux.or), and a lane's owner entry is a popcount of that mask below its position.
 template <bool EVAL>
 __global__ void __launch_bounds__(ROW_WARPS * 32)
 k_rows_product(const ProdArgs A) {
@@ -316,99 +406,103 @@ k_rows_product(const ProdArgs A) {
   const uint64_t ai = A.run_alpha[r], bi = A.tmpl_beta[k];
   const int64_t b2s = A.b2_ptr[k], b4s = A.b4_ptr[k];
   const int len2 = int(A.b2_ptr[k + 1] - b2s), len4 = int(A.b4_ptr[k + 1] - b4s);
-  const size_t n = A.I.n, n2 = n * n, n3 = n2 * n;
+  const int n = A.I.n;
+  const size_t n2 = size_t(n) * n;
   int64_t out = A.rowptr[row];
   const int64_t out0 = out;
+  const int total = int(A.rowptr[row + 1] - out0);
   const unsigned lt = (1u << lane) - 1u;
-  if (ai != 0) {
-    const int64_t e0 = A.adj_ptr[r], e1 = A.adj_ptr[r + 1];
-    for (int64_t eb = e0; eb < e1; eb += 32) {
-      const int64_t e = eb + lane;
-      const bool ev = e < e1;
-      const uint32_t pk = ev ? A.adj[e] : 0u;
-      const uint32_t am = ev ? A.a_meta[e] : 0u;
-      const int dc = int(pk & 3u);  // alpha distance / 2
-      const bool adead = (am >> 17) & 1u;
-      const int len = !ev ? 0 : (dc == 2 ? (adead ? 0 : 1) : (dc == 1 ? (adead ? 1 : len2) : len4));
-      int incl = len;
-#pragma unroll
-      for (int d = 1; d < 32; d <<= 1) {
-        const int t = __shfl_up_sync(0xffffffffu, incl, d);
-        if (lane >= d) incl += t;
+  const unsigned le = (2u << lane) - 1u;
+  const int64_t E1 = A.cptr[r + 1];
+  int64_t e0 = A.cptr[r];
+  for (int c0 = 0; c0 < total; c0 += 32) {
+    // ---- window of entries e0 .. e0 + 31
+    const int64_t ej = e0 + lane;
+    const bool ev = ej < E1;
+    ARec rec;
+    if (ev) rec = A.crec[ej]; else { rec.r2t = 0; rec.meta = 0; rec.nlive = 0; rec.nunit = 0; }
+    const int kind_j = int(rec.r2t & 3u);
+    const int start_j = ((int64_t(rec.r2t >> 2) > r) ? len4 : 0) + int(rec.nlive) * len2 + int(rec.nunit);
+    const int end_j = start_j + (kind_j == 0 ? len4 : (kind_j == 1 ? len2 : 1));
+    const int rel = start_j - c0;
+    const unsigned bit = (ev && lane > 0 && rel < 32) ? (1u << rel) : 0u;
+    const unsigned mask = __reduce_or_sync(0xffffffffu, bit);
+    const int wo = __popc(mask & le);  // window lane of the entry that owns position c0 + lane
+    const uint32_t r2t = __shfl_sync(0xffffffffu, rec.r2t, wo);
+    const uint32_t am = __shfl_sync(0xffffffffu, rec.meta, wo);
+    const int st = __shfl_sync(0xffffffffu, start_j, wo);
+    // next window starts at the entry that holds position c0 + 32
+    const int wlast = __shfl_sync(0xffffffffu, wo, 31);
+    const int endlast = __shfl_sync(0xffffffffu, end_j, wlast);
+    const int64_t e_own = e0 + wo;
+    e0 += wlast + (endlast > c0 + 32 ? 0 : 1);
+
+    const int c = c0 + lane;
+    const bool act = c < total;
+    int32_t j = 0;
+    double v = 0.;
+    bool keep = false;
+    if (act) {
+      const int kind = int(r2t & 3u);
+      const int64_t r2 = r2t >> 2;
+      const int t = c - st;
+      if (kind == 1) {
+        const B2Rec br = A.b2rec[b2s + t];
+        j = int32_t(r2 * A.nb + br.k2);
+        const unsigned o1 = am & 0xFFu, v1 = (am >> 8) & 0xFFu;
+        if (br.offa & (1u << 30)) {
+          // alpha single, same beta: leading sum + V_red over the occupied beta orbitals
+          double h = A.cval[e_own];
+          const double* Vr = A.I.Vr + v1 * n + o1 * n2;
+          for (uint64_t s = bi; s; s &= s - 1) h += ldg(Vr + lsb64(s));
+          v = flip_sign_if(h, (am >> 16) & 1u);
+        } else {
+          // opposite-spin double: the bra determinant is the one with the lower index; the
+          // stored beta pair has bra = lower template index
+          const bool swap_b = (r < r2) != bool(br.offb >> 31);
+          const uint32_t off = (swap_b ? br.offb : br.offa) & 0x3FFFFFFFu;
+          const double g = ldg(A.I.V + v1 + o1 * n + off);
+          v = flip_sign_if(g, ((am >> 16) ^ (br.offa >> 31)) & 1u);
+        }
+      } else if (kind == 2) {
+        j = int32_t(r2 * A.nb + k);
+        if (am & (1u << 18)) {
+          // alpha single whose opposite-spin doubles all vanish: the k' = k element only
+          const unsigned o1 = am & 0xFFu, v1 = (am >> 8) & 0xFFu;
+          double h = A.cval[e_own];
+          const double* Vr = A.I.Vr + v1 * n + o1 * n2;
+          for (uint64_t s = bi; s; s &= s - 1) h += ldg(Vr + lsb64(s));
+          v = flip_sign_if(h, (am >> 16) & 1u);
+        } else {
+          v = A.cval[e_own];  // alpha double, value precomputed per run pair
+        }
+      } else {
+        const uint32_t bpk = A.b4[b4s + t];
+        const int64_t k2 = bpk >> 2;
+        const int db = int(bpk & 3u);
+        j = int32_t(r * A.nb + k2);
+        if (db == 2) {
+          v = A.b4_val[b4s + t];  // beta double, value precomputed per template pair
+        } else if (db == 1) {
+          const uint32_t bm = A.b4_meta[b4s + t];
+          const unsigned o2 = bm & 0xFFu, v2 = (bm >> 8) & 0xFFu;
+          double h = A.b4_val[b4s + t];
+          const double* Vr = A.I.Vr + v2 * n + o2 * n2;
+          for (uint64_t s = ai; s; s &= s - 1) h += ldg(Vr + lsb64(s));
+          v = flip_sign_if(h, (bm >> 16) & 1u);
+        } else {
+          v = me_diag(A.I, ai, bi);
+        }
       }
-      const int excl = incl - len;
-      const int total = __shfl_sync(0xffffffffu, incl, 31);
-      for (int c0 = 0; c0 < total; c0 += 32) {
-        const int c = c0 + lane;
-        const bool act = c < total;
-        // owner entry: the last lane whose exclusive offset is <= c
-        int lo = 0;
-#pragma unroll
-        for (int step = 16; step > 0; step >>= 1) {
-          const int mid = lo + step;
-          const int ex_mid = __shfl_sync(0xffffffffu, excl, mid & 31);
-          if (mid < 32 && ex_mid <= c) lo = mid;
-        }
-        const uint32_t pks = __shfl_sync(0xffffffffu, pk, lo);
-        const uint32_t ams = __shfl_sync(0xffffffffu, am, lo);
-        const int exs = __shfl_sync(0xffffffffu, excl, lo);
-        int32_t j = 0;
-        double v = 0.;
-        bool keep = false;
-        if (act) {
-          const int dcs = int(pks & 3u);
-          const int64_t r2 = pks >> 2;
-          const int t = c - exs;
-          const uint64_t aj = A.run_alpha[r2];
-          if (dcs == 2) {
-            // alpha double: value precomputed per run pair
-            j = int32_t(r2 * A.nb + k);
-            v = A.a_val[eb + lo];
-          } else if (dcs == 1) {
-            if ((ams >> 17) & 1u) {
-              // every opposite-spin double through this alpha single vanishes: k' = k only
-              j = int32_t(r2 * A.nb + k);
-              v = (r < r2) ? matel(A.I, ai, bi, aj, bi) : matel(A.I, aj, bi, ai, bi);
-            } else {
-              const uint32_t bpk = A.b2[b2s + t];
-              const int64_t k2 = bpk >> 2;
-              j = int32_t(r2 * A.nb + k2);
-              if ((bpk & 3u) == 0) {
-                v = (r < r2) ? matel(A.I, ai, bi, aj, bi) : matel(A.I, aj, bi, ai, bi);
-              } else {
-                const uint32_t bm = A.b2_meta[b2s + t];
-                const unsigned o1 = ams & 0xFFu, v1 = (ams >> 8) & 0xFFu;
-                unsigned o2 = bm & 0xFFu, v2 = (bm >> 8) & 0xFFu;  // stored with bra = lower template index
-                const bool swap_b = (r < r2) != (k < k2);          // bra determinant holds beta_k2
-                if (swap_b) { const unsigned tmp = o2; o2 = v2; v2 = tmp; }
-                const double sa = ((ams >> 16) & 1u) ? -1. : 1.;
-                const double sb = ((bm >> 16) & 1u) ? -1. : 1.;
-                const double sign = sa * sb;
-                v = sign * ldg(A.I.V + v1 + o1 * n + v2 * n2 + o2 * n3);
-              }
-            }
-          } else {
-            const uint32_t bpk = A.b4[b4s + t];
-            const int64_t k2 = bpk >> 2;
-            j = int32_t(r2 * A.nb + k2);
-            if ((bpk & 3u) == 2) {
-              v = A.b4_val[b4s + t];  // beta double: value precomputed per template pair
-            } else {
-              const uint64_t bj = A.tmpl_beta[k2];
-              v = (i <= int64_t(j)) ? matel(A.I, ai, bi, aj, bj) : matel(A.I, aj, bj, ai, bi);
-            }
-          }
-          keep = EVAL ? (fabs(v) > A.thr) : true;
-        }
-        const unsigned km = __ballot_sync(0xffffffffu, keep);
-        if (keep) {
-          const int64_t pos = out + __popc(km & lt);
-          A.colind[pos] = j;
-          A.nzval[pos] = v;
-        }
-        out += __popc(km);
-      }
+      keep = EVAL ? (fabs(v) > A.thr) : true;
     }
+    const unsigned km = __ballot_sync(0xffffffffu, keep);
+    if (keep) {
+      const int64_t pos = out + __popc(km & lt);
+      A.colind[pos] = j;
+      A.nzval[pos] = v;
+    }
+    out += __popc(km);
   }
   if (lane == 0) A.row_cnt[row] = int32_t(out - out0);
 }
@@ -635,41 +729,59 @@ void hbuild_csr(b2ci_ctx* ctx, const b2ci_dets* dets, int64_t row_begin, int64_t
         B2_CHECK_LAUNCH();
       }
     }
-    // per-pair metadata (values of same-spin doubles, hole/particle/sign of singles)
+    // per-pair metadata (values of same-spin doubles, hole/particle/sign/leading sum of singles)
     int64_t nadj_h = 0, nb2_h = 0, nb4_h = 0;
     B2_CUDA(cudaMemcpyAsync(&nadj_h, adj_ptr.p + nruns, 8, cudaMemcpyDeviceToHost, st));
     B2_CUDA(cudaMemcpyAsync(&nb2_h, b2_ptr.p + nb, 8, cudaMemcpyDeviceToHost, st));
     B2_CUDA(cudaMemcpyAsync(&nb4_h, b4_ptr.p + nb, 8, cudaMemcpyDeviceToHost, st));
     B2_CUDA(cudaStreamSynchronize(st));
-    DevBuf<unsigned char> dead_ov(size_t(ctx->norb) * ctx->norb);
-    DevBuf<uint32_t> a_meta(nadj_h > 0 ? nadj_h : 1), b2_meta(nb2_h > 0 ? nb2_h : 1), b4_meta(nb4_h > 0 ? nb4_h : 1);
-    DevBuf<double> a_val(nadj_h > 0 ? nadj_h : 1), b4_val(nb4_h > 0 ? nb4_h : 1);
-    DevBuf<int32_t> deg4(size_t(nruns) * 4);
+    DevBuf<uint32_t> b4_meta(nb4_h > 0 ? nb4_h : 1);
+    DevBuf<double> b4_val(nb4_h > 0 ? nb4_h : 1);
+    DevBuf<B2Rec> b2rec(nb2_h > 0 ? nb2_h : 1);
+    DevBuf<int32_t> run_cnt(size_t(nruns) * 4);
+    DevBuf<int64_t> cptr(nruns + 1);
+    DevBuf<ARec> crec;
+    DevBuf<double> cval;
     {
       ScopedTimer t(ctx, "h_build.setup", true);
+      DevBuf<unsigned char> dead_ov(size_t(ctx->norb) * ctx->norb);
+      DevBuf<uint32_t> a_meta(nadj_h > 0 ? nadj_h : 1), b2_meta(nb2_h > 0 ? nb2_h : 1);
+      DevBuf<double> a_val(nadj_h > 0 ? nadj_h : 1), b2_val(nb2_h > 0 ? nb2_h : 1);
       const int nn = ctx->norb * ctx->norb;
-      k_dead_ov<<<(nn + 127) / 128, 128, 0, st>>>(ctx->ints, thr, dead_ov);
-      k_pair_meta<true><<<unsigned((int64_t(nruns) * 32 + 255) / 256), 256, 0, st>>>(
-          ctx->ints, run_alpha, nruns, adj_ptr, adj, thr, dead_ov, a_meta, a_val, deg4);
+      const unsigned ga = unsigned((int64_t(nruns) * 32 + 255) / 256);
       const unsigned gb = unsigned((nb * 32 + 255) / 256);
-      k_pair_meta<false><<<gb, 256, 0, st>>>(ctx->ints, dets->beta, int32_t(nb), b2_ptr, b2, thr, dead_ov,
-                                             b2_meta, nullptr, nullptr);
-      k_pair_meta<false><<<gb, 256, 0, st>>>(ctx->ints, dets->beta, int32_t(nb), b4_ptr, b4, thr, dead_ov,
-                                             b4_meta, b4_val, nullptr);
-      ctx->launches += 4;
+      k_dead_ov<<<(nn + 127) / 128, 128, 0, st>>>(ctx->ints, thr, dead_ov);
+      k_pair_meta<<<ga, 256, 0, st>>>(ctx->ints, run_alpha, nruns, adj_ptr, adj, thr, dead_ov, a_meta, a_val);
+      k_pair_meta<<<gb, 256, 0, st>>>(ctx->ints, dets->beta, int32_t(nb), b2_ptr, b2, thr, nullptr, b2_meta, b2_val);
+      k_pair_meta<<<gb, 256, 0, st>>>(ctx->ints, dets->beta, int32_t(nb), b4_ptr, b4, thr, nullptr, b4_meta, b4_val);
+      k_beta_rec<<<gb, 256, 0, st>>>(ctx->norb, int32_t(nb), b2_ptr, b2, b2_meta, b2rec);
+      k_adj_compact<false><<<ga, 256, 0, st>>>(run_alpha, nruns, adj_ptr, adj, a_meta, a_val, run_cnt, nullptr,
+                                              nullptr, nullptr);
+      ctx->launches += 6;
+      B2_CHECK_LAUNCH();
+      // run_cnt is 4 ints per run with the entry count first: scan with stride via a gather
+      DevBuf<int32_t> ecnt(nruns);
+      B2_CUDA(cudaMemcpy2DAsync(ecnt, 4, run_cnt, 16, 4, nruns, cudaMemcpyDeviceToDevice, st));
+      exclusive_scan_i32_to_i64(ctx, ecnt, cptr, nruns);
+      int64_t ncadj = 0;
+      B2_CUDA(cudaMemcpyAsync(&ncadj, cptr.p + nruns, 8, cudaMemcpyDeviceToHost, st));
+      B2_CUDA(cudaStreamSynchronize(st));
+      crec.alloc(ncadj > 0 ? ncadj : 1);
+      cval.alloc(ncadj > 0 ? ncadj : 1);
+      k_adj_compact<true><<<ga, 256, 0, st>>>(run_alpha, nruns, adj_ptr, adj, a_meta, a_val, nullptr, cptr, crec, cval);
+      ctx->launches++;
       B2_CHECK_LAUNCH();
     }
     ProdArgs P;
     P.I = ctx->ints;
     P.run_alpha = run_alpha;
     P.tmpl_beta = dets->beta;
-    P.adj_ptr = adj_ptr;
-    P.adj = adj;
-    P.a_meta = a_meta;
-    P.a_val = a_val;
-    P.run_deg = deg4;
-    P.b2_ptr = b2_ptr; P.b2 = b2; P.b2_meta = b2_meta;
-    P.b4_ptr = b4_ptr; P.b4 = b4; P.b4_val = b4_val;
+    P.cptr = cptr;
+    P.crec = crec;
+    P.cval = cval;
+    P.run_cnt = run_cnt;
+    P.b2_ptr = b2_ptr; P.b2rec = b2rec;
+    P.b4_ptr = b4_ptr; P.b4 = b4; P.b4_meta = b4_meta; P.b4_val = b4_val;
     P.nb = nb;
     P.row_begin = row_begin;
     P.nrows = nrows;

@@ -32,8 +32,8 @@ void integrals_upload(b2ci_ctx* ctx, int norb, const double* T, const double* V)
   if (!T || !V) throw Error("b2ci_integrals_upload: null integrals");
   const size_t n = norb, n2 = n * n, n3 = n2 * n, n4 = n2 * n2;
   const size_t total = ints_total_doubles(norb);
-  if (ctx->ints_dev) { cudaFree(ctx->ints_dev); ctx->ints_dev = nullptr; }
-  B2_CUDA(cudaMalloc((void**)&ctx->ints_dev, total * 8));
+  dev_free(ctx->ints_dev);
+  ctx->ints_dev = static_cast<double*>(dev_alloc(total * 8));
   double* base = ctx->ints_dev;
   cudaStream_t st = ctx->stream;
   B2_CUDA(cudaMemcpyAsync(base, T, n2 * 8, cudaMemcpyHostToDevice, st));

@@ -103,7 +103,7 @@ void scan_impl(b2ci_ctx* ctx, const Tin* in, Tout* out, int64_t n) {
   k_tile_scan<Tin, Tout><<<(unsigned)ntiles, SCAN_THREADS, 0, ctx->stream>>>(in, n, offs, out);
   ctx->launches++;
   B2_CHECK_LAUNCH();
-  B2_CUDA(cudaStreamSynchronize(ctx->stream));  // temporaries die here
+  // temporaries are released in stream order (cudaFreeAsync), no synchronisation needed
 }
 }  // namespace
 

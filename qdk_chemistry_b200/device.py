@@ -52,6 +52,10 @@ class Context:
     def synchronize(self):
         check(lib().b2ci_ctx_synchronize(self.h))
 
+    def trim(self):
+        """Return the library's cached device memory (stream-ordered pool) to the driver."""
+        check(lib().b2ci_ctx_trim(self.h))
+
     @property
     def launch_count(self) -> int:
         return lib().b2ci_ctx_launch_count(self.h)
