@@ -265,28 +265,24 @@ k_pair_meta(IntsView I, const uint64_t* __restrict__ str, int32_t nstr,
 }
 
 // Compacted alpha-run adjacency: entries that enumerate at least one column, in ascending run
-// order, each with the number of live-single and unit-length entries that precede it in its
-// run. With len2(k) / len4(k) the lengths of the beta lists of row (r, k), entry e starts at
-//   (r2 > r ? len4 : 0) + nlive_before * len2 + nunit_before
-// inside the row -- position -> entry needs no search structure per row.
-struct __align__(16) ARec {
+// order, plus the list of the run's single excitations (leading sum + meta) in the same order.
+struct __align__(8) ARec {
   uint32_t r2t;   // run index << 2 | kind: 0 self, 1 live single, 2 unit (double, or dead single)
   uint32_t meta;  // o | v << 8 | sign << 16 | is_single << 18   (singles)
-  uint32_t nlive; // live singles before this entry
-  uint32_t nunit; // unit entries before this entry
 };
 template <bool FILL>
 __global__ void __launch_bounds__(256)
-k_adj_compact(const uint64_t* __restrict__ str, int32_t nstr, const int64_t* __restrict__ adj_ptr,
-              const uint32_t* __restrict__ adj, const uint32_t* __restrict__ meta,
-              const double* __restrict__ val, int32_t* __restrict__ cnt /* 4 per run */,
-              const int64_t* __restrict__ cptr, ARec* __restrict__ crec, double* __restrict__ cval) {
+k_adj_compact(int32_t nstr, const int64_t* __restrict__ adj_ptr, const uint32_t* __restrict__ adj,
+              const uint32_t* __restrict__ meta, const double* __restrict__ val,
+              int32_t* __restrict__ ecnt, int32_t* __restrict__ scnt, int32_t* __restrict__ run_cnt,
+              const int64_t* __restrict__ cptr, ARec* __restrict__ crec, double* __restrict__ cval,
+              const int64_t* __restrict__ sptr, double* __restrict__ slead, uint32_t* __restrict__ smeta) {
   const int lane = threadIdx.x & 31;
   const int64_t r = (int64_t(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
   if (r >= nstr) return;
   const unsigned lt = (1u << lane) - 1u;
-  int64_t out = FILL ? cptr[r] : 0;
-  uint32_t nself = 0, nlive = 0, nunit = 0;
+  int64_t out = FILL ? cptr[r] : 0, sout = FILL ? sptr[r] : 0;
+  uint32_t nself = 0, nlive = 0, nunit = 0, nsing = 0;
   const int64_t e0 = adj_ptr[r], e1 = adj_ptr[r + 1];
   for (int64_t eb = e0; eb < e1; eb += 32) {
     const int64_t e = eb + lane;
@@ -297,35 +293,43 @@ k_adj_compact(const uint64_t* __restrict__ str, int32_t nstr, const int64_t* __r
     const bool dead = (m >> 17) & 1u;
     const bool is_self = ev && dc == 0, is_live = ev && dc == 1 && !dead;
     const bool is_unit = ev && ((dc == 1 && dead) || (dc == 2 && !dead));
+    const bool is_sing = ev && dc == 1;
     const unsigned ms = __ballot_sync(0xffffffffu, is_self);
     const unsigned ml = __ballot_sync(0xffffffffu, is_live);
     const unsigned mu = __ballot_sync(0xffffffffu, is_unit);
+    const unsigned mg = __ballot_sync(0xffffffffu, is_sing);
     if (FILL && (is_self || is_live || is_unit)) {
       ARec rec;
       rec.r2t = (pk & ~3u) | (is_self ? 0u : (is_live ? 1u : 2u));
       rec.meta = (m & 0x1FFFFu) | (dc == 1 ? (1u << 18) : 0u);
-      rec.nlive = nlive + __popc(ml & lt);
-      rec.nunit = nunit + __popc(mu & lt);
       const int64_t pos = out + __popc((ms | ml | mu) & lt);
       crec[pos] = rec;
       cval[pos] = val[e];
     }
+    if (FILL && is_sing) {
+      const int64_t pos = sout + __popc(mg & lt);
+      slead[pos] = val[e];
+      smeta[pos] = m & 0x1FFFFu;
+    }
     out += __popc(ms | ml | mu);
+    sout += __popc(mg);
     nself += __popc(ms);
     nlive += __popc(ml);
     nunit += __popc(mu);
+    nsing += __popc(mg);
   }
   if (!FILL && lane == 0) {
-    cnt[4 * r] = int32_t(nself + nlive + nunit);
-    cnt[4 * r + 1] = int32_t(nself);
-    cnt[4 * r + 2] = int32_t(nlive);
-    cnt[4 * r + 3] = int32_t(nunit);
+    ecnt[r] = int32_t(nself + nlive + nunit);
+    scnt[r] = int32_t(nsing);
+    run_cnt[4 * r] = int32_t(nself);
+    run_cnt[4 * r + 1] = int32_t(nlive);
+    run_cnt[4 * r + 2] = int32_t(nunit);
+    run_cnt[4 * r + 3] = int32_t(nsing);
   }
 }
 
-// Beta-side records of the two lists of template string k.
-//   B2 (distance <= 2): k2, V offset of the (particle, hole) pair in both orientations, sign
-//   B4 (distance <= 4): k2 << 2 | distance / 2, meta; value (double) or leading sum (single)
+// Beta-side record of list B2(k) (distance <= 2): k2, V offset of the (particle, hole) pair in
+// both orientations, sign
 struct __align__(16) B2Rec {
   uint32_t k2;
   uint32_t offa;  // v2 n^2 + o2 n^3 (bra = lower template index) | sign << 31 | is_self << 30
@@ -359,17 +363,24 @@ struct ProdArgs {
   const int64_t* cptr;        // compacted alpha-run adjacency
   const ARec* crec;
   const double* cval;
-  const int32_t* run_cnt;     // 4 per run: entries, self, live singles, unit
+  const int64_t* sptr;        // single excitations of every run, in adjacency order
+  const double* slead;
+  const uint32_t* smeta;
+  const int32_t* run_cnt;     // 4 per run: self, live singles, unit, singles
   const int64_t* b2_ptr;      // beta adjacency, distance <= 2
   const B2Rec* b2rec;
+  const uint32_t* b2_meta;
+  const double* b2_val;
   const int64_t* b4_ptr;      // distance <= 4
   const uint32_t* b4;
-  const uint32_t* b4_meta;
   const double* b4_val;
+  const double* diag;         // <D|H|D> of every row of the block
   int64_t nb;
   int64_t row_begin;
   int64_t nrows;
   double thr;
+  int smem_a;                 // doubles of per-warp scratch for alpha singles
+  int smem_b;                 // ... and beta singles
   int32_t* row_cnt;           // structural count (count kernel) / surviving count (fill kernel)
   const int64_t* rowptr;      // slot offsets of the fill kernel
   int32_t* colind;
@@ -383,26 +394,52 @@ __global__ void k_prod_struct_count(const ProdArgs A) {
   const int64_t r = i / A.nb, k = i % A.nb;
   const int64_t l2 = A.b2_ptr[k + 1] - A.b2_ptr[k], l4 = A.b4_ptr[k + 1] - A.b4_ptr[k];
   const int32_t* d = A.run_cnt + 4 * r;
-  const int64_t c = int64_t(d[1]) * l4 + int64_t(d[2]) * l2 + int64_t(d[3]);
+  const int64_t c = int64_t(d[0]) * l4 + int64_t(d[1]) * l2 + int64_t(d[2]);
   A.row_cnt[row] = int32_t(c);
 }
-
-__device__ __forceinline__ double flip_sign_if(double v, bool neg) {
-  return __longlong_as_double(__double_as_longlong(v) ^ (neg ? (long long)0x8000000000000000ull : 0ll));
+// diagonal elements, one thread per row (matrix_elements.hpp:203-230)
+__global__ void k_row_diag(const ProdArgs A, double* __restrict__ diag) {
+  const int64_t row = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (row >= A.nrows) return;
+  const int64_t i = A.row_begin + row;
+  diag[row] = me_diag(A.I, A.run_alpha[i / A.nb], A.tmpl_beta[i % A.nb]);
 }
 
-// One warp per row. Output positions are produced 32 at a time; the warp keeps a window of 32
-// consecutive adjacency entries starting at the entry that holds the first position of the
-// batch, every window lane marks the batch-relative start of its entry in a 32-bit mask
-// (one redux.or), and a lane's owner entry is a popcount of that mask below its position.
+__device__ __forceinline__ double flip_sign_if(double v, unsigned neg) {
+  return __hiloint2double(__double2hiint(v) ^ int((neg & 1u) << 31), __double2loint(v));
+}
+
+// One warp per row. The warp walks the compacted adjacency of its alpha run 32 entries at a
+// time; inside a window, runs of unit entries are emitted with one lane per entry and every
+// list entry (self: B4(k), live single: B2(k)) with one lane per list element. All control flow
+// is warp-uniform, output positions are ascending, so survivors are written in order with a
+// ballot prefix. Single-excitation elements (leading sum + V_red terms of the other spin, added
+// in ascending orbital order) are evaluated once per row with full lanes into shared memory.
+template <bool EVAL>
+__device__ __forceinline__ void emit(const ProdArgs& A, bool act, int32_t j, double v, unsigned lt,
+                                     int64_t& out) {
+  const bool keep = act && (EVAL ? (fabs(v) > A.thr) : true);
+  const unsigned km = __ballot_sync(0xffffffffu, keep);
+  if (keep) {
+    const int64_t pos = out + __popc(km & lt);
+    A.colind[pos] = j;
+    A.nzval[pos] = v;
+  }
+  out += __popc(km);
+}
+
 template <bool EVAL>
 __global__ void __launch_bounds__(ROW_WARPS * 32)
 k_rows_product(const ProdArgs A) {
+  extern __shared__ double sm_singles[];
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   const int64_t row = int64_t(blockIdx.x) * ROW_WARPS + w;
   if (row >= A.nrows) return;
+  double* sa = sm_singles + size_t(w) * (A.smem_a + A.smem_b);
+  double* sb = sa + A.smem_a;
   const int64_t i = A.row_begin + row;
-  const int64_t r = i / A.nb, k = i % A.nb;
+  const uint32_t r = uint32_t(i / A.nb), k = uint32_t(i % A.nb);
+  const uint32_t nb = uint32_t(A.nb);
   const uint64_t ai = A.run_alpha[r], bi = A.tmpl_beta[k];
   const int64_t b2s = A.b2_ptr[k], b4s = A.b4_ptr[k];
   const int len2 = int(A.b2_ptr[k + 1] - b2s), len4 = int(A.b4_ptr[k + 1] - b4s);
@@ -410,99 +447,104 @@ k_rows_product(const ProdArgs A) {
   const size_t n2 = size_t(n) * n;
   int64_t out = A.rowptr[row];
   const int64_t out0 = out;
-  const int total = int(A.rowptr[row + 1] - out0);
   const unsigned lt = (1u << lane) - 1u;
-  const unsigned le = (2u << lane) - 1u;
-  const int64_t E1 = A.cptr[r + 1];
-  int64_t e0 = A.cptr[r];
-  for (int c0 = 0; c0 < total; c0 += 32) {
-    // ---- window of entries e0 .. e0 + 31
-    const int64_t ej = e0 + lane;
-    const bool ev = ej < E1;
-    ARec rec;
-    if (ev) rec = A.crec[ej]; else { rec.r2t = 0; rec.meta = 0; rec.nlive = 0; rec.nunit = 0; }
-    const int kind_j = int(rec.r2t & 3u);
-    const int start_j = ((int64_t(rec.r2t >> 2) > r) ? len4 : 0) + int(rec.nlive) * len2 + int(rec.nunit);
-    const int end_j = start_j + (kind_j == 0 ? len4 : (kind_j == 1 ? len2 : 1));
-    const int rel = start_j - c0;
-    const unsigned bit = (ev && lane > 0 && rel < 32) ? (1u << rel) : 0u;
-    const unsigned mask = __reduce_or_sync(0xffffffffu, bit);
-    const int wo = __popc(mask & le);  // window lane of the entry that owns position c0 + lane
-    const uint32_t r2t = __shfl_sync(0xffffffffu, rec.r2t, wo);
-    const uint32_t am = __shfl_sync(0xffffffffu, rec.meta, wo);
-    const int st = __shfl_sync(0xffffffffu, start_j, wo);
-    // next window starts at the entry that holds position c0 + 32
-    const int wlast = __shfl_sync(0xffffffffu, wo, 31);
-    const int endlast = __shfl_sync(0xffffffffu, end_j, wlast);
-    const int64_t e_own = e0 + wo;
-    e0 += wlast + (endlast > c0 + 32 ? 0 : 1);
-
-    const int c = c0 + lane;
-    const bool act = c < total;
-    int32_t j = 0;
-    double v = 0.;
-    bool keep = false;
-    if (act) {
-      const int kind = int(r2t & 3u);
-      const int64_t r2 = r2t >> 2;
-      const int t = c - st;
-      if (kind == 1) {
-        const B2Rec br = A.b2rec[b2s + t];
-        j = int32_t(r2 * A.nb + br.k2);
-        const unsigned o1 = am & 0xFFu, v1 = (am >> 8) & 0xFFu;
-        if (br.offa & (1u << 30)) {
-          // alpha single, same beta: leading sum + V_red over the occupied beta orbitals
-          double h = A.cval[e_own];
-          const double* Vr = A.I.Vr + v1 * n + o1 * n2;
-          for (uint64_t s = bi; s; s &= s - 1) h += ldg(Vr + lsb64(s));
-          v = flip_sign_if(h, (am >> 16) & 1u);
-        } else {
-          // opposite-spin double: the bra determinant is the one with the lower index; the
-          // stored beta pair has bra = lower template index
-          const bool swap_b = (r < r2) != bool(br.offb >> 31);
-          const uint32_t off = (swap_b ? br.offb : br.offa) & 0x3FFFFFFFu;
-          const double g = ldg(A.I.V + v1 + o1 * n + off);
-          v = flip_sign_if(g, ((am >> 16) ^ (br.offa >> 31)) & 1u);
-        }
-      } else if (kind == 2) {
-        j = int32_t(r2 * A.nb + k);
-        if (am & (1u << 18)) {
-          // alpha single whose opposite-spin doubles all vanish: the k' = k element only
-          const unsigned o1 = am & 0xFFu, v1 = (am >> 8) & 0xFFu;
-          double h = A.cval[e_own];
-          const double* Vr = A.I.Vr + v1 * n + o1 * n2;
-          for (uint64_t s = bi; s; s &= s - 1) h += ldg(Vr + lsb64(s));
-          v = flip_sign_if(h, (am >> 16) & 1u);
-        } else {
-          v = A.cval[e_own];  // alpha double, value precomputed per run pair
-        }
-      } else {
-        const uint32_t bpk = A.b4[b4s + t];
-        const int64_t k2 = bpk >> 2;
-        const int db = int(bpk & 3u);
-        j = int32_t(r * A.nb + k2);
-        if (db == 2) {
-          v = A.b4_val[b4s + t];  // beta double, value precomputed per template pair
-        } else if (db == 1) {
-          const uint32_t bm = A.b4_meta[b4s + t];
-          const unsigned o2 = bm & 0xFFu, v2 = (bm >> 8) & 0xFFu;
-          double h = A.b4_val[b4s + t];
-          const double* Vr = A.I.Vr + v2 * n + o2 * n2;
-          for (uint64_t s = ai; s; s &= s - 1) h += ldg(Vr + lsb64(s));
-          v = flip_sign_if(h, (bm >> 16) & 1u);
-        } else {
-          v = me_diag(A.I, ai, bi);
-        }
+  if (ai != 0) {
+    // ---- single-excitation elements of this row
+    {
+      const int64_t sp = A.sptr[r];
+      const int ns = int(A.sptr[r + 1] - sp);
+      for (int s = lane; s < ns; s += 32) {
+        const uint32_t m = A.smeta[sp + s];
+        double h = A.slead[sp + s];
+        const double* Vr = A.I.Vr + ((m >> 8) & 0xFFu) * n + (m & 0xFFu) * n2;
+        for (uint64_t q = bi; q; q &= q - 1) h += ldg(Vr + lsb64(q));
+        sa[s] = flip_sign_if(h, m >> 16);
       }
-      keep = EVAL ? (fabs(v) > A.thr) : true;
+      for (int t = lane; t < len2; t += 32) {
+        const uint32_t m = A.b2_meta[b2s + t];
+        double h = A.b2_val[b2s + t];
+        const double* Vr = A.I.Vr + ((m >> 8) & 0xFFu) * n + (m & 0xFFu) * n2;
+        for (uint64_t q = ai; q; q &= q - 1) h += ldg(Vr + lsb64(q));
+        sb[t] = flip_sign_if(h, m >> 16);  // the self slot is never read
+      }
+      __syncwarp();
     }
-    const unsigned km = __ballot_sync(0xffffffffu, keep);
-    if (keep) {
-      const int64_t pos = out + __popc(km & lt);
-      A.colind[pos] = j;
-      A.nzval[pos] = v;
+    const int64_t E0 = A.cptr[r], E1 = A.cptr[r + 1];
+    int sord0 = 0;  // singles before the current window
+    for (int64_t eb = E0; eb < E1; eb += 32) {
+      const int nv = int(min(int64_t(32), E1 - eb));
+      const bool ev = lane < nv;
+      ARec rec;
+      rec.r2t = 0; rec.meta = 0;
+      double cv = 0.;
+      if (ev) { rec = A.crec[eb + lane]; cv = A.cval[eb + lane]; }
+      const int kind_l = int(rec.r2t & 3u);
+      const bool sing_l = ev && ((rec.meta >> 18) & 1u);
+      const unsigned lm = __ballot_sync(0xffffffffu, ev && kind_l != 2);  // list entries
+      const unsigned gm = __ballot_sync(0xffffffffu, sing_l);             // singles
+      const int sord_l = sord0 + __popc(gm & lt);
+      // unit entries: value known per lane
+      const int32_t j_unit = int32_t((rec.r2t >> 2) * nb + k);
+      const double v_unit = sing_l ? sa[sord_l] : cv;
+      int cur = 0;
+      while (cur < nv) {
+        const unsigned rem = lm & ~((1u << cur) - 1u);
+        const int f = rem ? (__ffs(rem) - 1) : nv;
+        if (f > cur) emit<EVAL>(A, lane >= cur && lane < f, j_unit, v_unit, lt, out);
+        if (f >= nv) break;
+        const uint32_t r2t = __shfl_sync(0xffffffffu, rec.r2t, f);
+        const uint32_t r2 = r2t >> 2;
+        if ((r2t & 3u) == 1u) {
+          // live alpha single x B2(k): opposite-spin doubles + the same-beta single
+          const uint32_t am = __shfl_sync(0xffffffffu, rec.meta, f);
+          const int so = __shfl_sync(0xffffffffu, sord_l, f);
+          const double* Va = A.I.V + ((am >> 8) & 0xFFu) + (am & 0xFFu) * n;
+          const double vself = sa[so];
+          const bool lower = r < r2;  // the row determinant is the bra
+          const uint32_t base = r2 * nb;
+          for (int t0 = 0; t0 < len2; t0 += 32) {
+            const int t = t0 + lane;
+            const bool act = t < len2;
+            int32_t j = 0;
+            double v = 0.;
+            if (act) {
+              const B2Rec br = A.b2rec[b2s + t];
+              j = int32_t(base + br.k2);
+              // the stored beta pair has bra = lower template index
+              const bool swap_b = lower != bool(br.offb >> 31);
+              const uint32_t off = (swap_b ? br.offb : br.offa) & 0x3FFFFFFFu;
+              v = flip_sign_if(ldg(Va + off), (am >> 16) ^ (br.offa >> 31));
+              if (br.offa & (1u << 30)) v = vself;
+            }
+            emit<EVAL>(A, act, j, v, lt, out);
+          }
+        } else {
+          // same alpha string x B4(k): diagonal, beta singles, beta doubles
+          const uint32_t base = r * nb;
+          int t2run = 0;  // position in B2(k) of the next entry at distance <= 2
+          for (int t0 = 0; t0 < len4; t0 += 32) {
+            const int t = t0 + lane;
+            const bool act = t < len4;
+            uint32_t bpk = 3u;
+            if (act) bpk = A.b4[b4s + t];
+            const int db = int(bpk & 3u);
+            const unsigned m01 = __ballot_sync(0xffffffffu, act && db <= 1);
+            int32_t j = 0;
+            double v = 0.;
+            if (act) {
+              j = int32_t(base + (bpk >> 2));
+              if (db == 2) v = A.b4_val[b4s + t];
+              else if (db == 1) v = sb[t2run + __popc(m01 & lt)];
+              else v = A.diag[row];
+            }
+            t2run += __popc(m01);
+            emit<EVAL>(A, act, j, v, lt, out);
+          }
+        }
+        cur = f + 1;
+      }
+      sord0 += __popc(gm);
     }
-    out += __popc(km);
   }
   if (lane == 0) A.row_cnt[row] = int32_t(out - out0);
 }
@@ -735,18 +777,20 @@ void hbuild_csr(b2ci_ctx* ctx, const b2ci_dets* dets, int64_t row_begin, int64_t
     B2_CUDA(cudaMemcpyAsync(&nb2_h, b2_ptr.p + nb, 8, cudaMemcpyDeviceToHost, st));
     B2_CUDA(cudaMemcpyAsync(&nb4_h, b4_ptr.p + nb, 8, cudaMemcpyDeviceToHost, st));
     B2_CUDA(cudaStreamSynchronize(st));
-    DevBuf<uint32_t> b4_meta(nb4_h > 0 ? nb4_h : 1);
-    DevBuf<double> b4_val(nb4_h > 0 ? nb4_h : 1);
+    DevBuf<double> b4_val(nb4_h > 0 ? nb4_h : 1), b2_val(nb2_h > 0 ? nb2_h : 1);
+    DevBuf<uint32_t> b2_meta(nb2_h > 0 ? nb2_h : 1);
     DevBuf<B2Rec> b2rec(nb2_h > 0 ? nb2_h : 1);
     DevBuf<int32_t> run_cnt(size_t(nruns) * 4);
-    DevBuf<int64_t> cptr(nruns + 1);
+    DevBuf<int64_t> cptr(nruns + 1), sptr(nruns + 1);
     DevBuf<ARec> crec;
-    DevBuf<double> cval;
+    DevBuf<double> cval, slead, diag(nrows);
+    DevBuf<uint32_t> smeta;
     {
       ScopedTimer t(ctx, "h_build.setup", true);
       DevBuf<unsigned char> dead_ov(size_t(ctx->norb) * ctx->norb);
-      DevBuf<uint32_t> a_meta(nadj_h > 0 ? nadj_h : 1), b2_meta(nb2_h > 0 ? nb2_h : 1);
-      DevBuf<double> a_val(nadj_h > 0 ? nadj_h : 1), b2_val(nb2_h > 0 ? nb2_h : 1);
+      DevBuf<uint32_t> a_meta(nadj_h > 0 ? nadj_h : 1), b4_meta(nb4_h > 0 ? nb4_h : 1);
+      DevBuf<double> a_val(nadj_h > 0 ? nadj_h : 1);
+      DevBuf<int32_t> ecnt(nruns), scnt(nruns);
       const int nn = ctx->norb * ctx->norb;
       const unsigned ga = unsigned((int64_t(nruns) * 32 + 255) / 256);
       const unsigned gb = unsigned((nb * 32 + 255) / 256);
@@ -755,20 +799,22 @@ void hbuild_csr(b2ci_ctx* ctx, const b2ci_dets* dets, int64_t row_begin, int64_t
       k_pair_meta<<<gb, 256, 0, st>>>(ctx->ints, dets->beta, int32_t(nb), b2_ptr, b2, thr, nullptr, b2_meta, b2_val);
       k_pair_meta<<<gb, 256, 0, st>>>(ctx->ints, dets->beta, int32_t(nb), b4_ptr, b4, thr, nullptr, b4_meta, b4_val);
       k_beta_rec<<<gb, 256, 0, st>>>(ctx->norb, int32_t(nb), b2_ptr, b2, b2_meta, b2rec);
-      k_adj_compact<false><<<ga, 256, 0, st>>>(run_alpha, nruns, adj_ptr, adj, a_meta, a_val, run_cnt, nullptr,
-                                              nullptr, nullptr);
+      k_adj_compact<false><<<ga, 256, 0, st>>>(nruns, adj_ptr, adj, a_meta, a_val, ecnt, scnt, run_cnt, nullptr,
+                                              nullptr, nullptr, nullptr, nullptr, nullptr);
       ctx->launches += 6;
       B2_CHECK_LAUNCH();
-      // run_cnt is 4 ints per run with the entry count first: scan with stride via a gather
-      DevBuf<int32_t> ecnt(nruns);
-      B2_CUDA(cudaMemcpy2DAsync(ecnt, 4, run_cnt, 16, 4, nruns, cudaMemcpyDeviceToDevice, st));
       exclusive_scan_i32_to_i64(ctx, ecnt, cptr, nruns);
-      int64_t ncadj = 0;
+      exclusive_scan_i32_to_i64(ctx, scnt, sptr, nruns);
+      int64_t ncadj = 0, nsing = 0;
       B2_CUDA(cudaMemcpyAsync(&ncadj, cptr.p + nruns, 8, cudaMemcpyDeviceToHost, st));
+      B2_CUDA(cudaMemcpyAsync(&nsing, sptr.p + nruns, 8, cudaMemcpyDeviceToHost, st));
       B2_CUDA(cudaStreamSynchronize(st));
       crec.alloc(ncadj > 0 ? ncadj : 1);
       cval.alloc(ncadj > 0 ? ncadj : 1);
-      k_adj_compact<true><<<ga, 256, 0, st>>>(run_alpha, nruns, adj_ptr, adj, a_meta, a_val, nullptr, cptr, crec, cval);
+      slead.alloc(nsing > 0 ? nsing : 1);
+      smeta.alloc(nsing > 0 ? nsing : 1);
+      k_adj_compact<true><<<ga, 256, 0, st>>>(nruns, adj_ptr, adj, a_meta, a_val, nullptr, nullptr, nullptr, cptr,
+                                             crec, cval, sptr, slead, smeta);
       ctx->launches++;
       B2_CHECK_LAUNCH();
     }
@@ -779,13 +825,19 @@ void hbuild_csr(b2ci_ctx* ctx, const b2ci_dets* dets, int64_t row_begin, int64_t
     P.cptr = cptr;
     P.crec = crec;
     P.cval = cval;
+    P.sptr = sptr; P.slead = slead; P.smeta = smeta;
     P.run_cnt = run_cnt;
-    P.b2_ptr = b2_ptr; P.b2rec = b2rec;
-    P.b4_ptr = b4_ptr; P.b4 = b4; P.b4_meta = b4_meta; P.b4_val = b4_val;
+    P.b2_ptr = b2_ptr; P.b2rec = b2rec; P.b2_meta = b2_meta; P.b2_val = b2_val;
+    P.b4_ptr = b4_ptr; P.b4 = b4; P.b4_val = b4_val;
+    P.diag = diag;
     P.nb = nb;
     P.row_begin = row_begin;
     P.nrows = nrows;
     P.thr = thr;
+    // per-warp scratch for the single-excitation elements of a row: at most
+    // nocc * nvirt <= floor(n/2) * ceil(n/2) singles per spin, + 1 for the self slot of B2(k)
+    P.smem_a = (ctx->norb / 2) * (ctx->norb - ctx->norb / 2) + 1;
+    P.smem_b = P.smem_a;
     P.rowptr = nullptr; P.colind = nullptr; P.nzval = nullptr;
     DevBuf<int64_t> slot_ptr(nrows + 1);
     int64_t nslots = 0;
@@ -794,7 +846,8 @@ void hbuild_csr(b2ci_ctx* ctx, const b2ci_dets* dets, int64_t row_begin, int64_t
       DevBuf<int32_t> scnt(nrows);
       P.row_cnt = scnt;
       k_prod_struct_count<<<unsigned((nrows + 255) / 256), 256, 0, st>>>(P);
-      ctx->launches++;
+      k_row_diag<<<unsigned((nrows + 127) / 128), 128, 0, st>>>(P, diag);
+      ctx->launches += 2;
       B2_CHECK_LAUNCH();
       exclusive_scan_i32_to_i64(ctx, scnt, slot_ptr, nrows);
       B2_CUDA(cudaMemcpyAsync(&nslots, slot_ptr.p + nrows, 8, cudaMemcpyDeviceToHost, st));
@@ -809,8 +862,13 @@ void hbuild_csr(b2ci_ctx* ctx, const b2ci_dets* dets, int64_t row_begin, int64_t
       P.colind = ci_s;
       P.nzval = nz_s;
       const unsigned grid = unsigned((nrows + ROW_WARPS - 1) / ROW_WARPS);
-      if (thr > 0.0) k_rows_product<true><<<grid, ROW_WARPS * 32, 0, st>>>(P);
-      else k_rows_product<false><<<grid, ROW_WARPS * 32, 0, st>>>(P);
+      const size_t smem = size_t(ROW_WARPS) * (P.smem_a + P.smem_b) * sizeof(double);
+      if (smem > 48 * 1024) {
+        B2_CUDA(cudaFuncSetAttribute(k_rows_product<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
+        B2_CUDA(cudaFuncSetAttribute(k_rows_product<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
+      }
+      if (thr > 0.0) k_rows_product<true><<<grid, ROW_WARPS * 32, smem, st>>>(P);
+      else k_rows_product<false><<<grid, ROW_WARPS * 32, smem, st>>>(P);
       ctx->launches++;
       B2_CHECK_LAUNCH();
     }
