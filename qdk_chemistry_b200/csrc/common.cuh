@@ -31,9 +31,15 @@ struct Error : std::runtime_error {
 
 // Integral tables on the device, one contiguous allocation so the small ones can be staged
 // into shared memory with a single bulk copy:
-//   [ T n^2 | G2_red n^2 | V2_red n^2 | G_red n^3 | V_red n^3 | V n^4 ]
+//   [ T n^2 | G2_red n^2 | V2_red n^2 | G_red n^3 | V_red n^3 | V n^4 | Vt n^2 * n2p ]
+// Vt is V with the index pairs exchanged, Vt[(r + s n) + (p + q n) n2p] = V(p,q,r,s) (a copy,
+// no arithmetic), n2p = n^2 rounded up to even: the n^2 integrals (pq|..) that one alpha single
+// excitation p<-q needs are then one contiguous, 16-byte aligned slice -- the unit the H-build
+// kernel stages into shared memory with bulk (TMA) copies.
 struct IntsView {
   int n;
+  int n2p;
+  const double* Vt;
   const double* T;
   const double* G2;
   const double* V2;
@@ -46,9 +52,14 @@ inline size_t ints_small_doubles(int n) {  // T, G2, V2, G_red, V_red
   size_t n2 = size_t(n) * n;
   return 3 * n2 + 2 * n2 * n;
 }
+inline size_t ints_n2p(int n) { return (size_t(n) * n + 1) & ~size_t(1); }
+inline size_t ints_vt_offset(int n) {  // even, so Vt is 16-byte aligned
+  size_t n2 = size_t(n) * n;
+  return (ints_small_doubles(n) + n2 * n2 + 1) & ~size_t(1);
+}
 inline size_t ints_total_doubles(int n) {
   size_t n2 = size_t(n) * n;
-  return ints_small_doubles(n) + n2 * n2;
+  return ints_vt_offset(n) + n2 * ints_n2p(n);
 }
 inline IntsView make_view(int n, const double* base) {
   size_t n2 = size_t(n) * n, n3 = n2 * n;
@@ -60,6 +71,8 @@ inline IntsView make_view(int n, const double* base) {
   v.G = base + 3 * n2;
   v.Vr = base + 3 * n2 + n3;
   v.V = base + 3 * n2 + 2 * n3;
+  v.n2p = int(ints_n2p(n));
+  v.Vt = base + ints_vt_offset(n);
   return v;
 }
 

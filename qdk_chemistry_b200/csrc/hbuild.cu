@@ -16,7 +16,9 @@
 //                   per-row sort, no atomics, both triangles computed with the SAME
 //                   (bra = lower index, ket = higher index) roles as the reference so the
 //                   values are bit-identical to its mirrored entries.
+#include <cmath>
 #include <cstdlib>
+#include <type_traits>
 
 #include "common.cuh"
 #include "slater.cuh"
@@ -328,13 +330,13 @@ k_adj_compact(int32_t nstr, const int64_t* __restrict__ adj_ptr, const uint32_t*
   }
 }
 
-// Beta-side record of list B2(k) (distance <= 2): k2, V offset of the (particle, hole) pair in
-// both orientations, sign
-struct __align__(16) B2Rec {
+// Beta-side record of list B2(k) (distance <= 2): column offset k2 and, packed, the position of
+// the (particle, hole) pair inside an integral slice in both orientations, sign and flags
+//   pk = (v2 + o2 n) | (o2 + v2 n) << 12 | sign << 24 | is_self << 25 | (k2 > k) << 26
+// (first offset: bra = lower template index; second: orientation swapped)
+struct __align__(8) B2Rec {
   uint32_t k2;
-  uint32_t offa;  // v2 n^2 + o2 n^3 (bra = lower template index) | sign << 31 | is_self << 30
-  uint32_t offb;  // o2 n^2 + v2 n^3 (orientation swapped)        | (k2 > k) << 31
-  uint32_t pad;
+  uint32_t pk;
 };
 __global__ void __launch_bounds__(256)
 k_beta_rec(int n, int32_t nstr, const int64_t* __restrict__ b2_ptr, const uint32_t* __restrict__ b2,
@@ -342,16 +344,14 @@ k_beta_rec(int n, int32_t nstr, const int64_t* __restrict__ b2_ptr, const uint32
   const int lane = threadIdx.x & 31;
   const int64_t k = (int64_t(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
   if (k >= nstr) return;
-  const uint32_t n2 = uint32_t(n) * n, n3 = n2 * n;
   for (int64_t e = b2_ptr[k] + lane; e < b2_ptr[k + 1]; e += 32) {
     const uint32_t pk = b2[e], m = b2_meta[e];
     const uint32_t k2 = pk >> 2;
     const uint32_t o = m & 0xFFu, v = (m >> 8) & 0xFFu;
     B2Rec r;
     r.k2 = k2;
-    r.offa = (v * n2 + o * n3) | (((m >> 16) & 1u) << 31) | ((pk & 3u) == 0 ? (1u << 30) : 0u);
-    r.offb = (o * n2 + v * n3) | (k2 > uint32_t(k) ? (1u << 31) : 0u);
-    r.pad = 0;
+    r.pk = (v + o * n) | ((o + v * n) << 12) | (((m >> 16) & 1u) << 24) |
+           ((pk & 3u) == 0 ? (1u << 25) : 0u) | (k2 > uint32_t(k) ? (1u << 26) : 0u);
     rec[e] = r;
   }
 }
@@ -380,7 +380,8 @@ struct ProdArgs {
   int64_t nrows;
   double thr;
   int smem_a;                 // doubles of per-warp scratch for alpha singles
-  int smem_b;                 // ... and beta singles
+  int smem_b;                 // ... and beta singles / B2 records
+  int nslice_max;             // integral slices staged per CTA (singles per run, upper bound)
   int32_t* row_cnt;           // structural count (count kernel) / surviving count (fill kernel)
   const int64_t* rowptr;      // slot offsets of the fill kernel
   int32_t* colind;
@@ -409,144 +410,238 @@ __device__ __forceinline__ double flip_sign_if(double v, unsigned neg) {
   return __hiloint2double(__double2hiint(v) ^ int((neg & 1u) << 31), __double2loint(v));
 }
 
-// One warp per row. The warp walks the compacted adjacency of its alpha run 32 entries at a
-// time; inside a window, runs of unit entries are emitted with one lane per entry and every
-// list entry (self: B4(k), live single: B2(k)) with one lane per list element. All control flow
-// is warp-uniform, output positions are ascending, so survivors are written in order with a
-// ballot prefix. Single-excitation elements (leading sum + V_red terms of the other spin, added
-// in ascending orbital order) are evaluated once per row with full lanes into shared memory.
-template <bool EVAL>
-__device__ __forceinline__ void emit(const ProdArgs& A, bool act, int32_t j, double v, unsigned lt,
-                                     int64_t& out) {
-  const bool keep = act && (EVAL ? (fabs(v) > A.thr) : true);
-  const unsigned km = __ballot_sync(0xffffffffu, keep);
-  if (keep) {
-    const int64_t pos = out + __popc(km & lt);
-    A.colind[pos] = j;
-    A.nzval[pos] = v;
-  }
-  out += __popc(km);
+// ---- bulk (TMA) copy + mbarrier primitives (PTX ISA 8.0+, sm_90+; SASS: UBLKCP / SYNCS)
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return uint32_t(__cvta_generic_to_shared(p)); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "WAIT_%=:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra DONE_%=;\n\t"
+      "bra WAIT_%=;\n\t"
+      "DONE_%=:\n\t}"
+      ::"r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(smem_u32(dst_smem)), "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
 }
 
-template <bool EVAL>
-__global__ void __launch_bounds__(ROW_WARPS * 32)
+// One CTA per (alpha run, chunk of template strings); G lanes per row, 32 / G rows per warp.
+// The CTA first stages, with bulk (TMA) copies signalled on an mbarrier, the integral slice
+// Vt(v1 o1 | . .) of every single excitation of its run -- the only integrals the opposite-spin
+// doubles of these rows read (SLICES; for large n they stay in global memory / L2). Every warp
+// then walks the compacted adjacency of the run 32 entries at a time; inside a window, runs of
+// unit entries are emitted with one lane per entry and every list entry (self: B4(k), live
+// single: B2(k)) with one lane per list element, each lane group doing so for its own row. All
+// rows of a run share the adjacency, so control flow is warp-uniform; output positions are
+// ascending, so survivors are written in order with a ballot prefix. Narrow groups keep the
+// lanes busy when the lists are short (CAS(12,12): |B2| = 37, unit runs of ~6).
+// Single-excitation elements (leading sum + V_red terms of the other spin, added in ascending
+// orbital order) are evaluated once per row with full lanes into shared memory, next to the
+// row's B2 records.
+constexpr int PW = 16;  // warps per CTA of the product kernel
+template <int G>
+struct GroupOut {
+  int32_t* ci;   // colind of this row (slot base)
+  double* nz;    // nzval of this row
+  int rel;       // elements written so far
+  unsigned ltg;  // lanes of the group below this lane
+  int gshift;    // first lane of the group
+};
+template <int G>
+__device__ __forceinline__ unsigned group_bits(unsigned m, int gshift) {
+  if (G == 32) return m;
+  return (m >> gshift) & ((1u << (G & 31)) - 1u);
+}
+template <bool EVAL, int G>
+__device__ __forceinline__ void emit(GroupOut<G>& O, double thr, bool act, int32_t j, double v) {
+  const bool keep = act && (EVAL ? (fabs(v) > thr) : true);
+  const unsigned gm = group_bits<G>(__ballot_sync(0xffffffffu, keep), O.gshift);
+  if (keep) {
+    const int pos = O.rel + __popc(gm & O.ltg);
+    O.ci[pos] = j;
+    O.nz[pos] = v;
+  }
+  O.rel += __popc(gm);
+}
+
+template <bool EVAL, int G, bool SLICES>
+__global__ void __launch_bounds__(PW * 32)
 k_rows_product(const ProdArgs A) {
-  extern __shared__ double sm_singles[];
+  constexpr int RPW = 32 / G, RPC = PW * RPW;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  // layout: [mbarrier, 16 B][slices][per row: singles alpha | singles beta][per row: B2 records]
+  uint64_t* bar = reinterpret_cast<uint64_t*>(smem_raw);
+  double* slices = reinterpret_cast<double*>(smem_raw + 16);
+  double* rows_d = slices + (SLICES ? size_t(A.nslice_max) * A.I.n2p : 0);
+  B2Rec* rows_b = reinterpret_cast<B2Rec*>(rows_d + size_t(RPC) * (A.smem_a + A.smem_b));
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-  const int64_t row = int64_t(blockIdx.x) * ROW_WARPS + w;
-  if (row >= A.nrows) return;
-  double* sa = sm_singles + size_t(w) * (A.smem_a + A.smem_b);
-  double* sb = sa + A.smem_a;
-  const int64_t i = A.row_begin + row;
-  const uint32_t r = uint32_t(i / A.nb), k = uint32_t(i % A.nb);
-  const uint32_t nb = uint32_t(A.nb);
-  const uint64_t ai = A.run_alpha[r], bi = A.tmpl_beta[k];
-  const int64_t b2s = A.b2_ptr[k], b4s = A.b4_ptr[k];
-  const int len2 = int(A.b2_ptr[k + 1] - b2s), len4 = int(A.b4_ptr[k + 1] - b4s);
+  const int gid = lane / G, l = lane % G;
+  const int64_t cpr = (A.nb + RPC - 1) / RPC;  // chunks per run
+  const uint32_t r = uint32_t(A.row_begin / A.nb + blockIdx.x / cpr);
+  const int64_t kk = (blockIdx.x % cpr) * RPC + w * RPW + gid;
+  const int64_t i = int64_t(r) * A.nb + kk;
+  const bool rowvalid = kk < A.nb && i >= A.row_begin && i < A.row_begin + A.nrows;
+  const int64_t row = rowvalid ? i - A.row_begin : 0;
+  const uint64_t ai = A.run_alpha[r];
+  if (ai == 0) {  // alpha-empty determinants are skipped (uniform over the CTA)
+    if (rowvalid && l == 0) A.row_cnt[row] = 0;
+    return;
+  }
   const int n = A.I.n;
   const size_t n2 = size_t(n) * n;
-  int64_t out = A.rowptr[row];
-  const int64_t out0 = out;
-  const unsigned lt = (1u << lane) - 1u;
-  if (ai != 0) {
-    // ---- single-excitation elements of this row
-    {
-      const int64_t sp = A.sptr[r];
-      const int ns = int(A.sptr[r + 1] - sp);
+  const int64_t sp = A.sptr[r];
+  const int ns = int(A.sptr[r + 1] - sp);
+  if (SLICES) {
+    if (threadIdx.x == 0) mbar_init(bar, 1);
+    __syncthreads();
+    if (w == 0) {
+      const uint32_t bytes = uint32_t(A.I.n2p) * 8u;
+      int mine = 0;
+      for (int s = lane; s < ns; s += 32) mine += ((A.smeta[sp + s] >> 17) & 1u) ? 0 : 1;
+      const int total = __reduce_add_sync(0xffffffffu, mine);
+      if (lane == 0) mbar_arrive_expect_tx(bar, uint32_t(total) * bytes);
+      __syncwarp();
       for (int s = lane; s < ns; s += 32) {
         const uint32_t m = A.smeta[sp + s];
-        double h = A.slead[sp + s];
-        const double* Vr = A.I.Vr + ((m >> 8) & 0xFFu) * n + (m & 0xFFu) * n2;
-        for (uint64_t q = bi; q; q &= q - 1) h += ldg(Vr + lsb64(q));
-        sa[s] = flip_sign_if(h, m >> 16);
+        if ((m >> 17) & 1u) continue;  // no opposite-spin double through this single survives
+        const size_t pq = ((m >> 8) & 0xFFu) + size_t(m & 0xFFu) * n;
+        bulk_g2s(slices + size_t(s) * A.I.n2p, A.I.Vt + pq * A.I.n2p, bytes, bar);
       }
-      for (int t = lane; t < len2; t += 32) {
-        const uint32_t m = A.b2_meta[b2s + t];
-        double h = A.b2_val[b2s + t];
-        const double* Vr = A.I.Vr + ((m >> 8) & 0xFFu) * n + (m & 0xFFu) * n2;
-        for (uint64_t q = ai; q; q &= q - 1) h += ldg(Vr + lsb64(q));
-        sb[t] = flip_sign_if(h, m >> 16);  // the self slot is never read
-      }
-      __syncwarp();
-    }
-    const int64_t E0 = A.cptr[r], E1 = A.cptr[r + 1];
-    int sord0 = 0;  // singles before the current window
-    for (int64_t eb = E0; eb < E1; eb += 32) {
-      const int nv = int(min(int64_t(32), E1 - eb));
-      const bool ev = lane < nv;
-      ARec rec;
-      rec.r2t = 0; rec.meta = 0;
-      double cv = 0.;
-      if (ev) { rec = A.crec[eb + lane]; cv = A.cval[eb + lane]; }
-      const int kind_l = int(rec.r2t & 3u);
-      const bool sing_l = ev && ((rec.meta >> 18) & 1u);
-      const unsigned lm = __ballot_sync(0xffffffffu, ev && kind_l != 2);  // list entries
-      const unsigned gm = __ballot_sync(0xffffffffu, sing_l);             // singles
-      const int sord_l = sord0 + __popc(gm & lt);
-      // unit entries: value known per lane
-      const int32_t j_unit = int32_t((rec.r2t >> 2) * nb + k);
-      const double v_unit = sing_l ? sa[sord_l] : cv;
-      int cur = 0;
-      while (cur < nv) {
-        const unsigned rem = lm & ~((1u << cur) - 1u);
-        const int f = rem ? (__ffs(rem) - 1) : nv;
-        if (f > cur) emit<EVAL>(A, lane >= cur && lane < f, j_unit, v_unit, lt, out);
-        if (f >= nv) break;
-        const uint32_t r2t = __shfl_sync(0xffffffffu, rec.r2t, f);
-        const uint32_t r2 = r2t >> 2;
-        if ((r2t & 3u) == 1u) {
-          // live alpha single x B2(k): opposite-spin doubles + the same-beta single
-          const uint32_t am = __shfl_sync(0xffffffffu, rec.meta, f);
-          const int so = __shfl_sync(0xffffffffu, sord_l, f);
-          const double* Va = A.I.V + ((am >> 8) & 0xFFu) + (am & 0xFFu) * n;
-          const double vself = sa[so];
-          const bool lower = r < r2;  // the row determinant is the bra
-          const uint32_t base = r2 * nb;
-          for (int t0 = 0; t0 < len2; t0 += 32) {
-            const int t = t0 + lane;
-            const bool act = t < len2;
-            int32_t j = 0;
-            double v = 0.;
-            if (act) {
-              const B2Rec br = A.b2rec[b2s + t];
-              j = int32_t(base + br.k2);
-              // the stored beta pair has bra = lower template index
-              const bool swap_b = lower != bool(br.offb >> 31);
-              const uint32_t off = (swap_b ? br.offb : br.offa) & 0x3FFFFFFFu;
-              v = flip_sign_if(ldg(Va + off), (am >> 16) ^ (br.offa >> 31));
-              if (br.offa & (1u << 30)) v = vself;
-            }
-            emit<EVAL>(A, act, j, v, lt, out);
-          }
-        } else {
-          // same alpha string x B4(k): diagonal, beta singles, beta doubles
-          const uint32_t base = r * nb;
-          int t2run = 0;  // position in B2(k) of the next entry at distance <= 2
-          for (int t0 = 0; t0 < len4; t0 += 32) {
-            const int t = t0 + lane;
-            const bool act = t < len4;
-            uint32_t bpk = 3u;
-            if (act) bpk = A.b4[b4s + t];
-            const int db = int(bpk & 3u);
-            const unsigned m01 = __ballot_sync(0xffffffffu, act && db <= 1);
-            int32_t j = 0;
-            double v = 0.;
-            if (act) {
-              j = int32_t(base + (bpk >> 2));
-              if (db == 2) v = A.b4_val[b4s + t];
-              else if (db == 1) v = sb[t2run + __popc(m01 & lt)];
-              else v = A.diag[row];
-            }
-            t2run += __popc(m01);
-            emit<EVAL>(A, act, j, v, lt, out);
-          }
-        }
-        cur = f + 1;
-      }
-      sord0 += __popc(gm);
     }
   }
-  if (lane == 0) A.row_cnt[row] = int32_t(out - out0);
+  const bool warp_active = __any_sync(0xffffffffu, rowvalid);
+  const uint32_t k = rowvalid ? uint32_t(kk) : 0u;
+  const uint32_t nb = uint32_t(A.nb);
+  double* sa = rows_d + size_t(w * RPW + gid) * (A.smem_a + A.smem_b);
+  double* sb = sa + A.smem_a;
+  B2Rec* sb2 = rows_b + size_t(w * RPW + gid) * A.smem_b;
+  const uint64_t bi = A.tmpl_beta[k];
+  const int64_t b2s = A.b2_ptr[k], b4s = A.b4_ptr[k];
+  const int len2 = int(A.b2_ptr[k + 1] - b2s), len4 = int(A.b4_ptr[k + 1] - b4s);
+  const int len2max = G == 32 ? len2 : __reduce_max_sync(0xffffffffu, rowvalid ? len2 : 0);
+  const int len4max = G == 32 ? len4 : __reduce_max_sync(0xffffffffu, rowvalid ? len4 : 0);
+  const int64_t out0 = A.rowptr[row];
+  GroupOut<G> O;
+  O.ci = A.colind + out0;
+  O.nz = A.nzval + out0;
+  O.rel = 0;
+  O.ltg = (1u << l) - 1u;
+  O.gshift = gid * G;
+  const unsigned lt = (1u << lane) - 1u;
+  if (warp_active) {
+    // ---- single-excitation elements and B2 records of this row
+    for (int s = l; s < ns; s += G) {
+      const uint32_t m = A.smeta[sp + s];
+      double h = A.slead[sp + s];
+      const double* Vr = A.I.Vr + ((m >> 8) & 0xFFu) * n + (m & 0xFFu) * n2;
+      for (uint64_t q = bi; q; q &= q - 1) h += ldg(Vr + lsb64(q));
+      sa[s] = flip_sign_if(h, m >> 16);
+    }
+    for (int t = l; t < len2; t += G) {
+      const uint32_t m = A.b2_meta[b2s + t];
+      double h = A.b2_val[b2s + t];
+      const double* Vr = A.I.Vr + ((m >> 8) & 0xFFu) * n + (m & 0xFFu) * n2;
+      for (uint64_t q = ai; q; q &= q - 1) h += ldg(Vr + lsb64(q));
+      sb[t] = flip_sign_if(h, m >> 16);  // the self slot is never read
+      sb2[t] = A.b2rec[b2s + t];
+    }
+    __syncwarp();
+  }
+  if (SLICES) mbar_wait(bar, 0);
+  if (!warp_active) return;
+  const int64_t E0 = A.cptr[r], E1 = A.cptr[r + 1];
+  int sord0 = 0;  // singles before the current window
+  for (int64_t eb = E0; eb < E1; eb += 32) {
+    const int nv = int(min(int64_t(32), E1 - eb));
+    const bool ev = lane < nv;
+    ARec rec;
+    rec.r2t = 0; rec.meta = 0;
+    double cv = 0.;
+    if (ev) { rec = A.crec[eb + lane]; cv = A.cval[eb + lane]; }
+    const bool sing_l = ev && ((rec.meta >> 18) & 1u);
+    const unsigned lm = __ballot_sync(0xffffffffu, ev && (rec.r2t & 3u) != 2u);  // list entries
+    const unsigned gm = __ballot_sync(0xffffffffu, sing_l);                      // singles
+    const int sord_l = sord0 + __popc(gm & lt);
+    int cur = 0;
+    while (cur < nv) {
+      const unsigned rem = lm & ~((1u << cur) - 1u);
+      const int f = rem ? (__ffs(rem) - 1) : nv;
+      if (f > cur) {
+        // unit entries cur .. f-1: one element each, column (r2, k)
+        const unsigned runmask = (f - cur >= 32 ? 0xffffffffu : ((1u << (f - cur)) - 1u)) << cur;
+        const bool any_sing = (gm & runmask) != 0u;
+        for (int u0 = cur; u0 < f; u0 += G) {
+          const int src = u0 + l;
+          const bool act = rowvalid && src < f;
+          const uint32_t r2t = __shfl_sync(0xffffffffu, rec.r2t, src & 31);
+          double v = __shfl_sync(0xffffffffu, cv, src & 31);
+          if (any_sing) {
+            const int so = __shfl_sync(0xffffffffu, sing_l ? sord_l : -1, src & 31);
+            if (so >= 0) v = sa[so];
+          }
+          emit<EVAL, G>(O, A.thr, act, int32_t((r2t >> 2) * nb + k), v);
+        }
+      }
+      if (f >= nv) break;
+      const uint32_t r2t = __shfl_sync(0xffffffffu, rec.r2t, f);
+      const uint32_t r2 = r2t >> 2;
+      if ((r2t & 3u) == 1u) {
+        // live alpha single x B2(k): opposite-spin doubles + the same-beta single
+        const uint32_t am = __shfl_sync(0xffffffffu, rec.meta, f);
+        const int so = __shfl_sync(0xffffffffu, sord_l, f);
+        const double* Va = SLICES ? slices + size_t(so) * A.I.n2p
+                                  : A.I.Vt + (((am >> 8) & 0xFFu) + size_t(am & 0xFFu) * n) * A.I.n2p;
+        const double vself = sa[so];
+        // the row determinant is the bra iff r < r2; the stored beta pair has bra = lower
+        // template index, so its orientation is swapped when the two orders disagree
+        const uint32_t lower = r < r2 ? 1u : 0u;
+        const uint32_t base = r2 * nb;
+        for (int t0 = 0; t0 < len2max; t0 += G) {
+          const int t = t0 + l;
+          const bool act = rowvalid && t < len2;
+          const B2Rec br = sb2[min(t, len2 - 1)];
+          const bool swap_b = lower != ((br.pk >> 26) & 1u);
+          const uint32_t off = (swap_b ? (br.pk >> 12) : br.pk) & 0xFFFu;
+          double v = flip_sign_if(SLICES ? Va[off] : ldg(Va + off), (am >> 16) ^ (br.pk >> 24));
+          if (br.pk & (1u << 25)) v = vself;
+          emit<EVAL, G>(O, A.thr, act, int32_t(base + br.k2), v);
+        }
+      } else {
+        // same alpha string x B4(k): diagonal, beta singles, beta doubles
+        const uint32_t base = r * nb;
+        int t2run = 0;  // position in B2(k) of the next entry at distance <= 2
+        for (int t0 = 0; t0 < len4max; t0 += G) {
+          const int t = t0 + l;
+          const bool act = rowvalid && t < len4;
+          const int64_t e4 = b4s + min(t, len4 - 1);
+          const uint32_t bpk = A.b4[e4];
+          const int db = int(bpk & 3u);
+          const unsigned g01 = group_bits<G>(__ballot_sync(0xffffffffu, act && db <= 1), O.gshift);
+          double v;
+          if (db == 2) v = A.b4_val[e4];
+          else if (db == 1) v = act ? sb[t2run + __popc(g01 & O.ltg)] : 0.;
+          else v = A.diag[row];
+          t2run += __popc(g01);
+          emit<EVAL, G>(O, A.thr, act, int32_t(base + (bpk >> 2)), v);
+        }
+      }
+      cur = f + 1;
+    }
+    sord0 += __popc(gm);
+  }
+  if (rowvalid && l == 0) A.row_cnt[row] = O.rel;
 }
 
 // move the surviving prefix of every structural row slot to its final position
@@ -861,14 +956,64 @@ void hbuild_csr(b2ci_ctx* ctx, const b2ci_dets* dets, int64_t row_begin, int64_t
       P.rowptr = slot_ptr;
       P.colind = ci_s;
       P.nzval = nz_s;
-      const unsigned grid = unsigned((nrows + ROW_WARPS - 1) / ROW_WARPS);
-      const size_t smem = size_t(ROW_WARPS) * (P.smem_a + P.smem_b) * sizeof(double);
-      if (smem > 48 * 1024) {
-        B2_CUDA(cudaFuncSetAttribute(k_rows_product<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
-        B2_CUDA(cudaFuncSetAttribute(k_rows_product<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
+      // lanes per row: the group width that wastes the fewest lane slots on this list shape
+      int G = 32;
+      {
+        int32_t rc[4] = {0, 0, 0, 0};
+        int64_t bp[2] = {0, 0}, bq[2] = {0, 0};
+        B2_CUDA(cudaMemcpyAsync(rc, run_cnt.p, 16, cudaMemcpyDeviceToHost, st));
+        B2_CUDA(cudaMemcpyAsync(bp, b2_ptr.p, 16, cudaMemcpyDeviceToHost, st));
+        B2_CUDA(cudaMemcpyAsync(bq, b4_ptr.p, 16, cudaMemcpyDeviceToHost, st));
+        B2_CUDA(cudaStreamSynchronize(st));
+        const double l2 = double(bp[1] - bp[0]), l4 = double(bq[1] - bq[0]);
+        const double nunit_runs = std::min<double>(rc[2], rc[0] + rc[1] + 1);
+        const double unit_len = nunit_runs > 0 ? rc[2] / nunit_runs : 0.;
+        double best = 0.;
+        for (int g : {32, 16, 8}) {
+          const double slots = g * (rc[1] * std::ceil(l2 / g) + rc[0] * std::ceil(l4 / g) +
+                                    nunit_runs * std::ceil(std::max(1., unit_len) / g));
+          // per-iteration cost is shared by the 32 / g rows of the warp
+          const double cost = slots * (1.0 + 0.02 * (32 / g));
+          if (best == 0. || cost < best) { best = cost; G = g; }
+        }
+        if (const char* env = getenv("B2CI_HBUILD_GROUP")) {
+          const int g = atoi(env);
+          if (g == 8 || g == 16 || g == 32) G = g;
+        }
       }
-      if (thr > 0.0) k_rows_product<true><<<grid, ROW_WARPS * 32, smem, st>>>(P);
-      else k_rows_product<false><<<grid, ROW_WARPS * 32, smem, st>>>(P);
+      ctx->timers["h_build.group_width"] = G;
+      const int rpc = PW * (32 / G);
+      const int64_t cpr = (nb + rpc - 1) / rpc;
+      const int64_t nruns_blk = (row_end - 1) / nb - row_begin / nb + 1;
+      const unsigned grid = unsigned(nruns_blk * cpr);
+      // shared memory: mbarrier + integral slices + per-row singles and B2 records
+      P.nslice_max = P.smem_a - 1;
+      const size_t rows_bytes = size_t(rpc) * ((P.smem_a + P.smem_b) * sizeof(double) + P.smem_b * sizeof(B2Rec));
+      const size_t slice_bytes = size_t(P.nslice_max) * ctx->ints.n2p * sizeof(double);
+      // stage the slices when two CTAs per SM still fit (227 KB per SM)
+      bool slices = 16 + slice_bytes + rows_bytes <= 110 * 1024;
+      if (const char* env = getenv("B2CI_HBUILD_SLICES")) slices = atoi(env) != 0 && 16 + slice_bytes + rows_bytes <= 220 * 1024;
+      ctx->timers["h_build.smem_slices"] = slices ? 1. : 0.;
+      const size_t smem = 16 + (slices ? slice_bytes : 0) + rows_bytes;
+      if (smem > 220 * 1024) throw Error("b2ci_hbuild_csr: product path needs " + std::to_string(smem) + " bytes of shared memory per CTA");
+      auto launch = [&](auto kern) {
+        if (smem > 48 * 1024)
+          B2_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
+        kern<<<grid, PW * 32, smem, st>>>(P);
+      };
+      auto launch_g = [&](auto ev, auto sl) {
+        constexpr bool EV = decltype(ev)::value, SL = decltype(sl)::value;
+        if (G == 8) launch(k_rows_product<EV, 8, SL>);
+        else if (G == 16) launch(k_rows_product<EV, 16, SL>);
+        else launch(k_rows_product<EV, 32, SL>);
+      };
+      if (thr > 0.0) {
+        if (slices) launch_g(std::true_type{}, std::true_type{});
+        else launch_g(std::true_type{}, std::false_type{});
+      } else {
+        if (slices) launch_g(std::false_type{}, std::true_type{});
+        else launch_g(std::false_type{}, std::false_type{});
+      }
       ctx->launches++;
       B2_CHECK_LAUNCH();
     }

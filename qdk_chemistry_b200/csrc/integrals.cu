@@ -25,6 +25,13 @@ __global__ void k_intermediates(int n, const double* __restrict__ V, double* __r
     V2[t] = viijj;
   }
 }
+__global__ void k_transpose_pairs(int n, int n2p, const double* __restrict__ V, double* __restrict__ Vt) {
+  const size_t n2 = size_t(n) * n;
+  const size_t t = size_t(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (t >= n2 * n2p) return;
+  const size_t rs = t % n2p, pq = t / n2p;
+  Vt[t] = rs < n2 ? V[pq + rs * n2] : 0.0;
+}
 }  // namespace
 
 void integrals_upload(b2ci_ctx* ctx, int norb, const double* T, const double* V) {
@@ -43,7 +50,9 @@ void integrals_upload(b2ci_ctx* ctx, int norb, const double* T, const double* V)
   k_intermediates<<<unsigned((n3 + 255) / 256), 256, 0, st>>>(
       norb, ctx->ints.V, const_cast<double*>(ctx->ints.G), const_cast<double*>(ctx->ints.Vr),
       const_cast<double*>(ctx->ints.G2), const_cast<double*>(ctx->ints.V2));
-  ctx->launches++;
+  k_transpose_pairs<<<unsigned((n2 * ctx->ints.n2p + 255) / 256), 256, 0, st>>>(
+      norb, ctx->ints.n2p, ctx->ints.V, const_cast<double*>(ctx->ints.Vt));
+  ctx->launches += 2;
   B2_CHECK_LAUNCH();
   ctx->ints_host.resize(total);
   B2_CUDA(cudaMemcpyAsync(ctx->ints_host.data(), base, total * 8, cudaMemcpyDeviceToHost, st));
