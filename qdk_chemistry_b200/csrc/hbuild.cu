@@ -972,8 +972,9 @@ void hbuild_csr(b2ci_ctx* ctx, const b2ci_dets* dets, int64_t row_begin, int64_t
         for (int g : {32, 16, 8}) {
           const double slots = g * (rc[1] * std::ceil(l2 / g) + rc[0] * std::ceil(l4 / g) +
                                     nunit_runs * std::ceil(std::max(1., unit_len) / g));
-          // per-iteration cost is shared by the 32 / g rows of the warp
-          const double cost = slots * (1.0 + 0.02 * (32 / g));
+          // measured cost per lane slot on B200 (Cr2 CAS(12,12)): 8-lane groups write 64-byte
+          // pieces and pay ~1.6x per slot, 16 and 32 lanes are level
+          const double cost = slots * (g == 8 ? 1.58 : (g == 16 ? 1.0 : 0.96));
           if (best == 0. || cost < best) { best = cost; G = g; }
         }
         if (const char* env = getenv("B2CI_HBUILD_GROUP")) {
