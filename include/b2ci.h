@@ -111,6 +111,11 @@ int b2ci_csr_diagonal(b2ci_ctx* ctx, const b2ci_csr* m, double* D);
 int b2ci_davidson(b2ci_ctx* ctx, const b2ci_csr* m, int64_t max_m, double tol, double* X,
                   int use_guess_policy, int64_t* niter, double* eigval, double* trace);
 
+/* ---- dense branch of the adapters for small spaces (n <= iterative_solver_dimension_cutoff):
+ * sparsexx::convert_to_dense + lapack::syev, lowest eigenpair (macis_cas.cpp:89-101,
+ * macis_pmc.cpp:98-112). eigvec: HOST, nrows entries. Full square matrices only. */
+int b2ci_dense_ground_state(b2ci_ctx* ctx, const b2ci_csr* m, double* eigval, double* eigvec);
+
 /* per-phase device timings of the last b2ci_davidson / b2ci_hbuild_csr / b2ci_asci_search
  * call on this context, in milliseconds (CUDA events on the context stream). Names follow
  * the reference's loggers (h_build: setup/count/fill; davidson: OP_DUR, RR_DUR, RES_DUR,

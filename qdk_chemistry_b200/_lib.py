@@ -71,6 +71,7 @@ def lib():
     L.b2ci_sigma_sharded.argtypes = [vp, vp, vp, vp, vp]
     L.b2ci_csr_diagonal.argtypes = [vp, vp, vp]
     L.b2ci_davidson.argtypes = [vp, vp, i64, dbl, vp, i32, pi64, C.POINTER(dbl), vp]
+    L.b2ci_dense_ground_state.argtypes = [vp, vp, C.POINTER(dbl), vp]
     L.b2ci_timer_ms.restype = dbl
     L.b2ci_timer_ms.argtypes = [vp, C.c_char_p]
     L.b2ci_asci_search.argtypes = [vp, vp, vp, i32, vp, i64, dbl, vp, i64, pi64, vp]

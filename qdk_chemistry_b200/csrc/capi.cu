@@ -25,6 +25,7 @@ void hbuild_csr(b2ci_ctx* ctx, const b2ci_dets* dets, int64_t row_begin, int64_t
 void csr_diagonal_dev(b2ci_ctx* ctx, const b2ci_csr* m, double* D_dev);
 int davidson(b2ci_ctx* ctx, const b2ci_csr* m, int64_t max_m, double tol, double* X_host,
              int use_guess_policy, int64_t* niter_out, double* eig_out, double* trace);
+void dense_ground_state(b2ci_ctx* ctx, const b2ci_csr* m, double* eigval, double* eigvec_host);
 void comm_unique_id(void* id128);
 void comm_init(b2ci_ctx* ctx, const void* id128, int rank, int nranks);
 void comm_destroy(b2ci_ctx* ctx);
@@ -340,6 +341,14 @@ int b2ci_davidson(b2ci_ctx* ctx, const b2ci_csr* m, int64_t max_m, double tol, d
   if (niter) *niter = it;
   if (eigval) *eigval = ev;
   return rc;
+  B2_CATCH
+}
+
+int b2ci_dense_ground_state(b2ci_ctx* ctx, const b2ci_csr* m, double* eigval, double* eigvec) {
+  B2_TRY_CTX(ctx)
+  if (!m || !eigval || !eigvec) throw Error("b2ci_dense_ground_state: null argument");
+  dense_ground_state(ctx, m, eigval, eigvec);
+  return 0;
   B2_CATCH
 }
 

@@ -264,6 +264,13 @@ class CsrMatrix:
                                   C.byref(niter), C.byref(eig), _p(trace)))
         return eig.value, X, niter.value, trace.reshape(-1, 2)
 
+    def dense_ground_state(self):
+        """Lowest eigenpair by dense diagonalisation (the adapters' small-space branch)."""
+        e = C.c_double(0.0)
+        x = np.empty(self.nrows, dtype=np.float64)
+        check(lib().b2ci_dense_ground_state(self.ctx.h, self.h, C.byref(e), _p(x)))
+        return e.value, x
+
     def free(self):
         if self.h and self.ctx.h:
             lib().b2ci_csr_free(self.ctx.h, self.h)

@@ -1,0 +1,707 @@
+// Host side of the B200 CI path: the MultiConfigurationCalculator plugins and the orchestration
+// that MACIS keeps on the host (guess policies, the ASCI grow / refine loops), driving the CUDA
+// library through the C ABI of include/b2ci.h and nothing else. No arithmetic of the hot path
+// happens here: Hamiltonian build, sigma, Davidson, dense diagonalisation and the ASCI search
+// are b2ci_* calls; this file sorts determinant lists, picks core sets and keeps settings.
+//
+// Reference call stacks mirrored:
+//   B200Cas::_run_impl   cas_helper::impl      macis_cas.cpp:35-148, mcscf/cas.hpp:33-64
+//   B200Asci::_run_impl  asci_helper::impl     macis_asci.cpp:44-234
+//   asci_iter/grow/refine                      asci/iteration.hpp:50-226, grow.hpp:45-268, refine.hpp:44-237
+//   B200Pmc::_run_impl   pmc_helper::impl      macis_pmc.cpp:36-174
+//   selected_ci_diag                           solvers/selected_ci_diag.hpp:111-311
+#include <algorithm>
+#include <chrono>
+#include <cmath>
+#include <cstring>
+#include <limits>
+#include <numeric>
+#include <unordered_map>
+
+#include "b2ci.h"
+#include "qdk_b200/mc.hpp"
+
+namespace qdk_b200::algorithms {
+
+namespace {
+
+struct Det {
+  uint64_t a, b;  // word 0 = alpha, word 1 = beta: the wfn_t<128> layout of the C ABI
+  bool operator==(const Det& o) const { return a == o.a && b == o.b; }
+};
+static_assert(sizeof(Det) == 16, "Det must be two packed words");
+struct DetHash {
+  size_t operator()(const Det& d) const { return std::hash<uint64_t>()(d.a * 0x9e3779b97f4a7c15ull ^ (d.b + (d.a << 7))); }
+};
+// spin_comparator: alpha-major, then beta (raw_bitset.hpp:119-141)
+inline bool spin_less(const Det& x, const Det& y) { return x.a != y.a ? x.a < y.a : x.b < y.b; }
+
+struct CommConfig {
+  bool set = false;
+  std::string id;
+  int rank = 0, nranks = 1;
+  int device = 0;
+};
+CommConfig& comm_config() {
+  static CommConfig c;
+  return c;
+}
+thread_local std::map<std::string, double> g_stats;
+
+[[noreturn]] void fail(const std::string& what) {
+  throw std::runtime_error(what + ": " + b2ci_last_error());
+}
+#define B2(call)                    \
+  do {                              \
+    if ((call) != 0) fail(#call);   \
+  } while (0)
+
+struct McscfSettings {  // macis::MCSCFSettings fields that reach the path
+  double ci_res_tol, ci_matel_tol;
+  int64_t ci_max_subspace;
+};
+McscfSettings get_mcscf_settings(const data::Settings& s) {  // macis_base.cpp:35-45
+  McscfSettings m;
+  m.ci_res_tol = s.get<double>("ci_residual_tolerance");
+  m.ci_max_subspace = s.get<int64_t>("max_solver_iterations");
+  m.ci_matel_tol = s.get<double>("ci_matel_tol");
+  return m;
+}
+struct AsciSettings {  // macis::ASCISettings fields that reach the path
+  int64_t ntdets_max, ntdets_min, ncdets_max, max_refine_iter;
+  double h_el_tol, rv_prune_tol, grow_factor, min_grow_factor, growth_backoff_rate, growth_recovery_rate,
+      refine_energy_tol, core_selection_threshold, min_warm_start_overlap, grow_ci_residual_tolerance,
+      taper_grow_factor;
+  bool just_singles, warm_start_davidson, fixed_core;
+};
+AsciSettings get_asci_settings(const data::Settings& s) {  // macis_base.cpp:47-134
+  AsciSettings a;
+  a.ntdets_max = s.get<int64_t>("ntdets_max");
+  a.ntdets_min = s.get<int64_t>("ntdets_min");
+  a.ncdets_max = s.get<int64_t>("ncdets_max");
+  a.h_el_tol = s.get<double>("search_matel_tol");
+  a.rv_prune_tol = s.get<double>("rv_prune_tol");
+  a.just_singles = s.get<bool>("just_singles");
+  a.grow_factor = s.get<double>("grow_factor");
+  a.min_grow_factor = s.get<double>("min_grow_factor");
+  a.growth_backoff_rate = s.get<double>("growth_backoff_rate");
+  a.growth_recovery_rate = s.get<double>("growth_recovery_rate");
+  a.max_refine_iter = s.get<int64_t>("max_refine_iter");
+  a.refine_energy_tol = s.get<double>("refine_energy_tol");
+  const std::string strat = s.get<std::string>("core_selection_strategy");
+  if (strat == "fixed") a.fixed_core = true;
+  else if (strat == "percentage") a.fixed_core = false;
+  else
+    throw std::invalid_argument("Invalid core_selection_strategy: '" + strat +
+                                "'. Valid options are 'fixed' or 'percentage'.");
+  a.core_selection_threshold = s.get<double>("core_selection_threshold");
+  a.warm_start_davidson = s.get<bool>("warm_start_davidson");
+  a.min_warm_start_overlap = s.get<double>("min_warm_start_overlap");
+  a.grow_ci_residual_tolerance = s.get<double>("grow_ci_residual_tolerance");
+  a.taper_grow_factor = s.get<double>("taper_grow_factor");
+  if (a.grow_factor <= 1.0) throw std::runtime_error("grow_factor must be > 1.0, got " + std::to_string(a.grow_factor));
+  if (a.min_grow_factor <= 1.0)
+    throw std::runtime_error("min_grow_factor must be > 1.0, got " + std::to_string(a.min_grow_factor));
+  if (a.min_grow_factor > a.grow_factor) throw std::runtime_error("min_grow_factor must be <= grow_factor");
+  if (a.growth_backoff_rate <= 0.0 || a.growth_backoff_rate >= 1.0)
+    throw std::runtime_error("growth_backoff_rate must be in (0, 1), got " + std::to_string(a.growth_backoff_rate));
+  if (a.growth_recovery_rate <= 1.0)
+    throw std::runtime_error("growth_recovery_rate must be > 1.0, got " + std::to_string(a.growth_recovery_rate));
+  if (!a.fixed_core && (a.core_selection_threshold < std::numeric_limits<double>::epsilon() ||
+                        a.core_selection_threshold > 1.0))
+    throw std::invalid_argument("core_selection_threshold must be in [epsilon, 1.0], got " +
+                                std::to_string(a.core_selection_threshold));
+  const std::string algo = s.get<std::string>("hamiltonian_build_algorithm");
+  if (!(algo.empty() || algo == "sorted_double_loop"))
+    throw std::invalid_argument("hamiltonian_build_algorithm '" + algo +
+                                "' is not available in this build; the B200 path implements the "
+                                "sorted_double_loop pattern and threshold semantics");
+  return a;
+}
+
+void reject_unsupported_outputs(const data::Settings& s) {
+  for (const char* k : {"calculate_one_rdm", "calculate_two_rdm", "calculate_single_orbital_entropies",
+                        "calculate_two_orbital_entropies", "calculate_mutual_information"})
+    if (s.get<bool>(k))
+      throw std::runtime_error(std::string("setting '") + k +
+                               "' is not available: RDM / entropy builders are outside the hot path "
+                               "this build covers (DESIGN.md, scope)");
+}
+
+int64_t binomial(int64_t n, int64_t k) {
+  if (k < 0 || k > n) return 0;
+  k = std::min(k, n - k);
+  __int128 r = 1;
+  for (int64_t i = 1; i <= k; ++i) {
+    r = r * (n - k + i) / i;
+    if (r > (__int128)std::numeric_limits<int64_t>::max()) return std::numeric_limits<int64_t>::max();
+  }
+  return (int64_t)r;
+}
+
+// ---------------------------------------------------------------------------------------------
+class CiSession {
+ public:
+  explicit CiSession(const data::Hamiltonian& h) : norb_(int(h.num_active_orbitals())), ham_(h) {
+    const CommConfig& cc = comm_config();
+    if (norb_ > 64) throw std::runtime_error("active spaces with more than 64 orbitals are not built");
+    B2(b2ci_ctx_create(cc.device, nullptr, &ctx_));
+    try {
+      if (cc.set && cc.nranks > 1) B2(b2ci_comm_init(ctx_, cc.id.data(), cc.rank, cc.nranks));
+      rank_ = cc.set ? cc.rank : 0;
+      nranks_ = cc.set ? cc.nranks : 1;
+      // T is symmetric; the two-body array is handed over as MACIS reinterprets it
+      // (macis_cas.cpp:76-82): element (pq|rs) of the QDK layout p n^3 + q n^2 + r n + s is
+      // read as column-major V(s,r,q,p) = (sr|qp), equal by symmetry.
+      B2(b2ci_integrals_upload(ctx_, norb_, h.get_one_body_integrals().data(), h.get_two_body_integrals().data()));
+    } catch (...) {
+      b2ci_ctx_destroy(ctx_);
+      throw;
+    }
+  }
+  ~CiSession() { b2ci_ctx_destroy(ctx_); }
+  CiSession(const CiSession&) = delete;
+
+  int norb() const { return norb_; }
+  b2ci_ctx* ctx() const { return ctx_; }
+
+  double diagonal_element(const Det& d) const {  // ham_gen.matrix_element(d, d)
+    return b2ci_host_matrix_element(norb_, ham_.get_one_body_integrals().data(),
+                                    ham_.get_two_body_integrals().data(), d.a, d.b, d.a, d.b);
+  }
+
+  std::pair<int64_t, int64_t> my_rows(int64_t n) const {  // contiguous row blocks in rank order
+    const int64_t base = n / nranks_, rem = n % nranks_;
+    const int64_t r0 = rank_ * base + std::min<int64_t>(rank_, rem);
+    return {r0, r0 + base + (rank_ < rem ? 1 : 0)};
+  }
+
+  // selected_ci_diag on a device-resident list: H build of this rank's rows + Davidson with
+  // the guess policy of serial_selected_ci_diag. X: empty or a guess; returns the full vector.
+  double selected_ci_diag(const b2ci_dets* dets, int64_t n, double matel_tol, int64_t max_m, double res_tol,
+                          std::vector<double>& X) {
+    if (n == 0) throw std::runtime_error("selected_ci_diag: empty determinant list");
+    X.resize(size_t(n), 0.0);
+    const auto rows = my_rows(n);
+    b2ci_csr* H = nullptr;
+    B2(b2ci_hbuild_csr(ctx_, dets, rows.first, rows.second, matel_tol, &H));
+    add_timer("h_build_ms", {"h_build.setup", "h_build.count", "h_build.fill", "h_build.thresh"});
+    int64_t nnz = 0;
+    b2ci_csr_info(H, nullptr, nullptr, &nnz, nullptr);
+    g_stats["nnz_local"] = double(nnz);
+    int64_t niter = 0;
+    double E = 0.;
+    const int rc = b2ci_davidson(ctx_, H, max_m, res_tol, X.data(), 1, &niter, &E, nullptr);
+    const std::string err = rc ? b2ci_last_error() : "";
+    add_timer("davidson_sigma_ms", {"davidson.OP_DUR"});
+    add_timer("davidson_other_ms", {"davidson.RR_DUR", "davidson.RES_DUR", "davidson.GS_DUR"});
+    g_stats["davidson_iterations"] += double(niter);
+    g_stats["davidson_calls"] += 1.0;
+    b2ci_csr_free(ctx_, H);
+    if (rc != 0) throw std::runtime_error(err);
+    return E;
+  }
+  double selected_ci_diag(const std::vector<Det>& dets, double matel_tol, int64_t max_m, double res_tol,
+                          std::vector<double>& X) {
+    b2ci_dets* d = nullptr;
+    B2(b2ci_dets_upload(ctx_, reinterpret_cast<const uint64_t*>(dets.data()), 2, int64_t(dets.size()), &d));
+    try {
+      const double E = selected_ci_diag(d, int64_t(dets.size()), matel_tol, max_m, res_tol, X);
+      b2ci_dets_free(ctx_, d);
+      return E;
+    } catch (...) {
+      b2ci_dets_free(ctx_, d);
+      throw;
+    }
+  }
+  // dense branch: full CSR (index pattern as the reference's int32 build) -> lowest eigenpair
+  double dense_diag(const b2ci_dets* dets, int64_t n, double matel_tol, std::vector<double>& X) {
+    X.assign(size_t(n), 0.0);
+    b2ci_csr* H = nullptr;
+    B2(b2ci_hbuild_csr(ctx_, dets, 0, n, matel_tol, &H));
+    double E = 0.;
+    const int rc = b2ci_dense_ground_state(ctx_, H, &E, X.data());
+    const std::string err = rc ? b2ci_last_error() : "";
+    b2ci_csr_free(ctx_, H);
+    if (rc != 0) throw std::runtime_error(err);
+    return E;
+  }
+  double dense_diag(const std::vector<Det>& dets, double matel_tol, std::vector<double>& X) {
+    b2ci_dets* d = nullptr;
+    B2(b2ci_dets_upload(ctx_, reinterpret_cast<const uint64_t*>(dets.data()), 2, int64_t(dets.size()), &d));
+    try {
+      const double E = dense_diag(d, int64_t(dets.size()), matel_tol, X);
+      b2ci_dets_free(ctx_, d);
+      return E;
+    } catch (...) {
+      b2ci_dets_free(ctx_, d);
+      throw;
+    }
+  }
+
+  std::vector<Det> asci_search(const Det* core, const double* coeffs, int64_t ncore, double E0, int64_t ndets_max,
+                               const AsciSettings& a) {
+    b2ci_asci_search_opts o;
+    o.ndets_max = ndets_max;
+    o.h_el_tol = a.h_el_tol;
+    o.rv_prune_tol = a.rv_prune_tol;
+    o.just_singles = a.just_singles ? 1 : 0;
+    o.reserved = 0;
+    int64_t cap = ndets_max + ncore + 4096, n_out = 0;
+    std::vector<Det> out;
+    for (;;) {
+      out.resize(size_t(cap));
+      const int rc = b2ci_asci_search(ctx_, &o, reinterpret_cast<const uint64_t*>(core), 2, coeffs, ncore, E0,
+                                      reinterpret_cast<uint64_t*>(out.data()), cap, &n_out, nullptr);
+      if (rc == 4 && n_out > cap) {  // ties at the cut exceed the capacity: retry with the exact size
+        cap = n_out;
+        continue;
+      }
+      if (rc != 0) fail("b2ci_asci_search");
+      break;
+    }
+    add_timer("asci_search_ms", {"asci_search.PAIR_DUR", "asci_search.SORT_ACC_DUR", "asci_search.TOPK_DUR"});
+    g_stats["asci_search_calls"] += 1.0;
+    out.resize(size_t(n_out));
+    return out;
+  }
+
+ private:
+  void add_timer(const char* key, std::initializer_list<const char*> names) {
+    double t = 0.;
+    for (const char* nm : names) {
+      const double v = b2ci_timer_ms(ctx_, nm);
+      if (v > 0) t += v;
+    }
+    g_stats[key] += t;
+  }
+  int norb_;
+  const data::Hamiltonian& ham_;
+  b2ci_ctx* ctx_ = nullptr;
+  int rank_ = 0, nranks_ = 1;
+};
+
+std::shared_ptr<data::Wavefunction> make_wavefunction(const std::vector<Det>& dets, std::vector<double> C,
+                                                      size_t norb) {
+  std::vector<data::Configuration> cfg;
+  cfg.reserve(dets.size());
+  for (const Det& d : dets) cfg.emplace_back(d.a, d.b, norb);
+  return std::make_shared<data::Wavefunction>(std::move(C), std::move(cfg), norb);
+}
+
+void check_hamiltonian(const data::Hamiltonian& h, const char* who, unsigned na, unsigned nb) {
+  if (h.is_unrestricted())
+    throw std::runtime_error(std::string(who) + " does not support unrestricted orbitals. "
+                                                "Only restricted orbitals are supported.");
+  if (na > h.num_active_orbitals() || nb > h.num_active_orbitals())
+    throw std::invalid_argument(std::string(who) + ": more electrons of one spin than active orbitals");
+}
+
+// CASCI on the device-generated Hilbert space (cas_helper::impl / compute_casci_rdms)
+double casci(CiSession& S, const data::Settings& st, unsigned na, unsigned nb, std::vector<Det>& dets,
+             std::vector<double>& C) {
+  const McscfSettings m = get_mcscf_settings(st);
+  const int64_t cutoff = st.get<int64_t>("iterative_solver_dimension_cutoff");
+  b2ci_dets* d = nullptr;
+  B2(b2ci_dets_generate_fci(S.ctx(), S.norb(), int(na), int(nb), &d));
+  int64_t n = 0;
+  b2ci_dets_size(d, &n);
+  double E = 0.;
+  try {
+    dets.resize(size_t(n));
+    B2(b2ci_dets_download(S.ctx(), d, reinterpret_cast<uint64_t*>(dets.data()), 2));
+    if (n == 1) {
+      E = S.diagonal_element(dets[0]);
+      C = {1.0};
+    } else if (n <= cutoff) {
+      E = S.dense_diag(d, n, m.ci_matel_tol, C);
+    } else {
+      C.clear();
+      E = S.selected_ci_diag(d, n, m.ci_matel_tol, m.ci_max_subspace, m.ci_res_tol, C);
+    }
+  } catch (...) {
+    b2ci_dets_free(S.ctx(), d);
+    throw;
+  }
+  b2ci_dets_free(S.ctx(), d);
+  g_stats["ndets"] = double(n);
+  return E;
+}
+
+// ---- ASCI outer loop -------------------------------------------------------------------------
+// reorder_ci_on_coeff (determinant_sort.hpp:45-64): |c| descending. The reference's std::sort
+// leaves the order of equal |c| unspecified; ties keep their current (spin-sorted) order here,
+// the same rule as oracle/port.py, so the core set is reproducible.
+void reorder_ci_on_coeff(std::vector<Det>& wfn, std::vector<double>& X) {
+  std::vector<int64_t> idx(X.size());
+  std::iota(idx.begin(), idx.end(), 0);
+  std::stable_sort(idx.begin(), idx.end(), [&](int64_t i, int64_t j) { return std::abs(X[i]) > std::abs(X[j]); });
+  std::vector<Det> w2(wfn.size());
+  std::vector<double> x2(X.size());
+  for (size_t i = 0; i < idx.size(); ++i) { w2[i] = wfn[idx[i]]; x2[i] = X[idx[i]]; }
+  wfn.swap(w2);
+  X.swap(x2);
+}
+void reorder_ci_on_alpha(std::vector<Det>& wfn, std::vector<double>& X, size_t nkeep) {  // :78-101
+  std::vector<int64_t> idx(nkeep);
+  std::iota(idx.begin(), idx.end(), 0);
+  std::stable_sort(idx.begin(), idx.end(), [&](int64_t i, int64_t j) { return spin_less(wfn[i], wfn[j]); });
+  std::vector<Det> w2(nkeep);
+  std::vector<double> x2(nkeep);
+  for (size_t i = 0; i < nkeep; ++i) { w2[i] = wfn[idx[i]]; x2[i] = X[idx[i]]; }
+  std::copy(w2.begin(), w2.end(), wfn.begin());
+  std::copy(x2.begin(), x2.end(), X.begin());
+}
+
+double asci_iter(CiSession& S, const AsciSettings& a, const McscfSettings& m, int64_t ndets_max, double E0,
+                 std::vector<Det>& wfn, std::vector<double>& X) {  // iteration.hpp:50-226
+  if (wfn.size() > 1) reorder_ci_on_coeff(wfn, X);
+  size_t nkeep = 0;
+  if (a.fixed_core) {
+    nkeep = std::min<size_t>(size_t(a.ncdets_max), wfn.size());
+  } else {
+    double w = 0.0;
+    for (size_t i = 0; i < wfn.size(); ++i) {
+      w += X[i] * X[i];
+      nkeep++;
+      if (w >= a.core_selection_threshold) break;
+    }
+  }
+  if (wfn.size() > 1) reorder_ci_on_alpha(wfn, X, nkeep);
+  std::unordered_map<Det, double, DetHash> old;
+  if (a.warm_start_davidson) {
+    old.reserve(wfn.size());
+    for (size_t i = 0; i < wfn.size(); ++i) old.emplace(wfn[i], X[i]);
+  }
+  wfn = S.asci_search(wfn.data(), X.data(), int64_t(nkeep), E0, ndets_max, a);
+  std::sort(wfn.begin(), wfn.end(), spin_less);
+  std::vector<double> X_local;
+  if (a.warm_start_davidson && !old.empty()) {
+    X_local.assign(wfn.size(), 0.0);
+    for (size_t i = 0; i < wfn.size(); ++i) {
+      auto it = old.find(wfn[i]);
+      if (it != old.end()) X_local[i] = it->second;
+    }
+    double nrm = 0.;
+    for (double x : X_local) nrm += x * x;
+    nrm = std::sqrt(nrm);
+    if (nrm < std::max(a.min_warm_start_overlap, std::numeric_limits<double>::epsilon())) {
+      X_local.clear();  // diagonal guess
+    } else {
+      const double inv = 1.0 / nrm;
+      for (double& x : X_local) x *= inv;
+    }
+  }
+  const double E = S.selected_ci_diag(wfn, m.ci_matel_tol, m.ci_max_subspace, m.ci_res_tol, X_local);
+  X = std::move(X_local);
+  g_stats["asci_iterations"] += 1.0;
+  return E;
+}
+
+double asci_grow(CiSession& S, const AsciSettings& a, const McscfSettings& m, double E0, std::vector<Det>& wfn,
+                 std::vector<double>& X) {  // grow.hpp:45-268 (grow_with_rot is rejected up front)
+  McscfSettings gm = m;
+  if (a.grow_ci_residual_tolerance > 0) gm.ci_res_tol = a.grow_ci_residual_tolerance;
+  size_t prev = wfn.size();
+  double gf = a.grow_factor;
+  const size_t ntmax = size_t(a.ntdets_max);
+  while (wfn.size() < ntmax) {
+    double eff = gf;
+    if (a.taper_grow_factor > 0 && size_t(std::ceil(wfn.size() * gf)) > ntmax)
+      eff = std::max(a.min_grow_factor, a.taper_grow_factor);
+    size_t ndets_new = std::min(std::max(size_t(a.ntdets_min), size_t(std::ceil(wfn.size() * eff))), ntmax);
+    if (ndets_new <= wfn.size()) {
+      ndets_new = std::min(wfn.size() + 1, ntmax);
+      if (ndets_new <= wfn.size()) break;
+    }
+    const double E = asci_iter(S, a, gm, int64_t(ndets_new), E0, wfn, X);
+    if (wfn.size() < ndets_new) {
+      gf = std::max(a.min_grow_factor, gf * a.growth_backoff_rate);
+      if (wfn.size() <= prev) break;  // (the reference leaves E0 at its previous value here)
+    } else {
+      gf = std::min(a.grow_factor, gf * a.growth_recovery_rate);
+    }
+    prev = wfn.size();
+    E0 = E;
+  }
+  return E0;
+}
+
+double asci_refine(CiSession& S, const AsciSettings& a, const McscfSettings& m, double E0, std::vector<Det>& wfn,
+                   std::vector<double>& X) {  // refine.hpp:44-237
+  size_t ndets = wfn.size();
+  bool converged = false;
+  double prev_dE = 0.0;
+  int oscillation = 0;
+  size_t max_iter = size_t(a.max_refine_iter), total_ext = 0;
+  const size_t max_ext = size_t(a.max_refine_iter);
+  std::vector<Det> prev_wfn;
+  for (size_t iter = 0; iter < max_iter; ++iter) {
+    const double E = asci_iter(S, a, m, int64_t(ndets), E0, wfn, X);
+    if (wfn.size() != ndets) {
+      ndets = wfn.size();
+      if (wfn.size() < size_t(a.ntdets_min)) break;
+    }
+    const double dE = E - E0;
+    if (std::abs(dE) < a.refine_energy_tol) {
+      E0 = E;
+      converged = true;
+      break;
+    }
+    if (iter > 0 && prev_dE * dE < 0 && std::abs(prev_dE + dE) < a.refine_energy_tol) {
+      oscillation++;
+      if (oscillation >= 2 && !prev_wfn.empty()) {
+        // stabilise by diagonalising in the union of the last two determinant sets
+        std::vector<Det> uni;
+        uni.reserve(wfn.size() + prev_wfn.size());
+        std::set_union(prev_wfn.begin(), prev_wfn.end(), wfn.begin(), wfn.end(), std::back_inserter(uni), spin_less);
+        std::vector<double> Xu(uni.size(), 0.0);
+        for (size_t i = 0; i < wfn.size(); ++i) {
+          auto it = std::lower_bound(uni.begin(), uni.end(), wfn[i], spin_less);
+          if (it != uni.end() && *it == wfn[i]) Xu[size_t(it - uni.begin())] = X[i];
+        }
+        const double Eu = S.selected_ci_diag(uni, m.ci_matel_tol, m.ci_max_subspace, m.ci_res_tol, Xu);
+        const size_t ext = std::min(size_t(oscillation), max_ext - total_ext);
+        if (ext > 0) { max_iter += ext; total_ext += ext; }
+        wfn = std::move(uni);
+        X = std::move(Xu);
+        ndets = wfn.size();
+        E0 = Eu;
+        prev_wfn.clear();
+        oscillation = 0;
+        prev_dE = 0.0;
+        continue;
+      }
+    } else {
+      oscillation = 0;
+    }
+    prev_dE = dE;
+    prev_wfn = wfn;
+    E0 = E;
+  }
+  if (!converged) {
+    std::string msg = "ASCI Refine did not converge";
+    if (total_ext > 0)
+      msg += " (oscillation detected, " + std::to_string(total_ext) +
+             " extra iterations granted). Consider using percentage core_selection_strategy, increasing "
+             "ncdets_max, or loosening refine_energy_tol.";
+    throw std::runtime_error(msg);
+  }
+  return E0;
+}
+
+}  // namespace
+
+// ---------------------------------------------------------------------------------------------
+MultiConfigurationSettings::MultiConfigurationSettings() {  // mc.hpp:26-61
+  set_default<bool>("calculate_one_rdm", false);
+  set_default<bool>("calculate_two_rdm", false);
+  set_default<bool>("calculate_single_orbital_entropies", false);
+  set_default<bool>("calculate_two_orbital_entropies", false);
+  set_default<bool>("calculate_mutual_information", false);
+  set_default<double>("ci_residual_tolerance", 1.0e-6, "CI residual convergence tolerance",
+                      data::BoundConstraint<double>{0.0, 1.0});
+  set_default<int64_t>("max_solver_iterations", 200, "Maximum number of Davidson iterations",
+                       data::BoundConstraint<int64_t>{1, std::numeric_limits<int64_t>::max()});
+  set_default<int64_t>("iterative_solver_dimension_cutoff", 2000,
+                       "Matrix size cutoff for using iterative eigensolver",
+                       data::BoundConstraint<int64_t>{1, std::numeric_limits<int64_t>::max()});
+}
+B200CiSettings::B200CiSettings() {  // MacisSettings, macis_base.hpp:27-37
+  set_default<double>("ci_matel_tol", std::numeric_limits<double>::epsilon(),
+                      "Hamiltonian matrix element sparsification threshold", data::BoundConstraint<double>{0.0, 1.0});
+}
+B200AsciSettings::B200AsciSettings() {  // MacisAsciSettings, macis_asci.hpp:34-183
+  const int64_t imax = std::numeric_limits<int64_t>::max();
+  const double dmax = std::numeric_limits<double>::max();
+  using BI = data::BoundConstraint<int64_t>;
+  using BD = data::BoundConstraint<double>;
+  set_default<int64_t>("ntdets_max", 100000, "Maximum number of trial determinants in the variational space", BI{1, imax});
+  set_default<int64_t>("ntdets_min", 100, "Minimum number of trial determinants required", BI{1, imax});
+  set_default<int64_t>("ncdets_max", 100, "Maximum number of core determinants", BI{1, imax});
+  set_default<double>("search_matel_tol", 1e-8, "Hamiltonian matrix element magnitude threshold", BD{0.0, 1.0});
+  set_default<double>("rv_prune_tol", 1e-8, "Ratio value pruning threshold", BD{0.0, 1.0});
+  set_default<double>("pt2_tol", 1e-16, "PT2 correction tolerance", BD{0.0, 1.0});
+  set_default<double>("refine_energy_tol", 1e-6, "Energy convergence tolerance for refinement", BD{0.0, 1.0});
+  set_default<int64_t>("pt2_reserve_count", 70000000, "Reserve count for PT2 calculations", BI{0, imax});
+  set_default<bool>("pt2_prune", false);
+  set_default<bool>("pt2_precompute_eps", false);
+  set_default<bool>("pt2_precompute_idx", false);
+  set_default<bool>("pt2_print_progress", false);
+  set_default<int64_t>("pt2_bigcon_thresh", 250, "Threshold for using bigcon PT2 algorithm", BI{0, imax});
+  set_default<int64_t>("pair_size_max", 500000000, "Maximum number of ASCI contribution pairs to store in memory", BI{1, imax});
+  set_default<int64_t>("nxtval_bcount_thresh", 1000, "Threshold for next value batch count", BI{1, imax});
+  set_default<int64_t>("nxtval_bcount_inc", 10, "Increment for next value batch count", BI{1, imax});
+  set_default<bool>("just_singles", false);
+  set_default<double>("grow_factor", 8.0, "Factor by which to grow the variational space", BD{1.0, dmax});
+  set_default<double>("min_grow_factor", 1.01, "Minimum allowed growth factor", BD{1.0, dmax});
+  set_default<double>("growth_backoff_rate", 0.5, "Rate to reduce grow_factor on failure", BD{0.0, 1.0});
+  set_default<double>("growth_recovery_rate", 1.1, "Rate to restore grow_factor on success", BD{1.0, dmax});
+  set_default<int64_t>("max_refine_iter", 6, "Maximum number of refinement iterations", BI{0, imax});
+  set_default<bool>("grow_with_rot", false);
+  set_default<int64_t>("rot_size_start", 1000, "Starting size for rotations", BI{1, imax});
+  set_default<int64_t>("constraint_level", 2, "Constraint level for excitation generation", BI{0, imax});
+  set_default<int64_t>("pt2_max_constraint_level", 5, "Maximum constraint level for PT2 calculations", BI{0, imax});
+  set_default<int64_t>("pt2_min_constraint_level", 0, "Minimum constraint level for PT2 calculations", BI{0, imax});
+  set_default<int64_t>("pt2_constraint_refine_force", 0, "Force constraint refinement for PT2 calculations", BI{0, imax});
+  set_default("core_selection_strategy", std::string("percentage"),
+              "Core determinant selection strategy: 'percentage' uses cumulative weight threshold, 'fixed' "
+              "uses a fixed number of determinants",
+              data::ListConstraint<std::string>{{"percentage", "fixed"}});
+  set_default<double>("core_selection_threshold", 0.95, "Cumulative weight threshold for core selection",
+                      BD{std::numeric_limits<double>::epsilon(), 1.0});
+  set_default<bool>("warm_start_davidson", true, "Warm-start Davidson from previous eigenvector");
+  set_default<double>("min_warm_start_overlap", 0.5, "Minimum projected vector norm for warm-start Davidson", BD{0.0, 1.0});
+  set_default<double>("min_patch_overlap", 0.3, "Minimum determinant overlap for incremental H build", BD{0.0, 1.0});
+  set_default<double>("grow_ci_residual_tolerance", 0.0, "CI residual tolerance during grow phase (0 = use refine tolerance)");
+  set_default<double>("taper_grow_factor", 0.0, "Growth factor for final expansion near ntdets_max (0 = disabled)");
+  set_default<std::string>("hamiltonian_build_algorithm", std::string(""),
+                           "Algorithm for diagonal Hamiltonian construction: '' or 'sorted_double_loop'");
+  set_default<int64_t>("dynamic_bit_masking_num_masks", 0);
+}
+
+std::string MultiConfigurationCalculator::hash(std::shared_ptr<data::Hamiltonian> h, unsigned na, unsigned nb) const {
+  return hash_hex(type_name() + "|" + name() + "|" + settings().content_hash() + "|" +
+                  (h ? h->content_hash() : std::string("null")) + "|" + std::to_string(na) + "|" + std::to_string(nb));
+}
+
+void MultiConfigurationCalculatorFactory::register_default_instances() {  // mc.cpp:26-31
+  register_instance([]() { return std::make_unique<B200Cas>(); });
+  register_instance([]() { return std::make_unique<B200Asci>(); });
+}
+void ProjectedMultiConfigurationCalculatorFactory::register_default_instances() {
+  register_instance([]() { return std::make_unique<B200Pmc>(); });
+}
+
+McResult B200Cas::_run_impl(std::shared_ptr<data::Hamiltonian> h, unsigned na, unsigned nb) const {
+  if (!h) throw std::invalid_argument("B200Cas: null Hamiltonian");
+  check_hamiltonian(*h, "B200Cas", na, nb);
+  reject_unsupported_outputs(*_settings);
+  g_stats.clear();
+  const auto t0 = std::chrono::steady_clock::now();
+  CiSession S(*h);
+  std::vector<Det> dets;
+  std::vector<double> C;
+  const double E = casci(S, *_settings, na, nb, dets, C);
+  g_stats["wall_ms"] = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+  return {E + h->get_core_energy(), make_wavefunction(dets, std::move(C), h->num_active_orbitals())};
+}
+
+McResult B200Asci::_run_impl(std::shared_ptr<data::Hamiltonian> h, unsigned na, unsigned nb) const {
+  if (!h) throw std::invalid_argument("B200Asci: null Hamiltonian");
+  check_hamiltonian(*h, "B200Asci", na, nb);
+  reject_unsupported_outputs(*_settings);
+  if (_settings->get<bool>("grow_with_rot"))
+    throw std::runtime_error("grow_with_rot (natural-orbital rotation during growth) needs the RDM builders, "
+                             "which are outside the hot path this build covers");
+  const McscfSettings m = get_mcscf_settings(*_settings);
+  const AsciSettings a = get_asci_settings(*_settings);
+  g_stats.clear();
+  const auto t0 = std::chrono::steady_clock::now();
+  CiSession S(*h);
+  const int norb = S.norb();
+  std::vector<Det> dets;
+  std::vector<double> C;
+  double E = 0.;
+  const int64_t fci_dim_a = binomial(norb, na), fci_dim_b = binomial(norb, nb);
+  const bool fits = fci_dim_a != std::numeric_limits<int64_t>::max() && fci_dim_b != std::numeric_limits<int64_t>::max() &&
+                    (fci_dim_b == 0 || fci_dim_a <= std::numeric_limits<int64_t>::max() / std::max<int64_t>(1, fci_dim_b));
+  if (fits && a.ntdets_max > fci_dim_a * fci_dim_b) {
+    // more determinants requested than the space holds: CASCI (macis_asci.cpp:125-157)
+    E = casci(S, *_settings, na, nb, dets, C);
+  } else {
+    // canonical HF determinant (wavefunction_traits::canonical_hf_determinant)
+    Det hf{na >= 64 ? ~uint64_t(0) : ((uint64_t(1) << na) - 1), nb >= 64 ? ~uint64_t(0) : ((uint64_t(1) << nb) - 1)};
+    dets = {hf};
+    C = {1.0};
+    E = S.diagonal_element(hf);
+    E = asci_grow(S, a, m, E, dets, C);
+    g_stats["ndets_after_grow"] = double(dets.size());
+    if (a.max_refine_iter) E = asci_refine(S, a, m, E, dets, C);
+    g_stats["ndets"] = double(dets.size());
+  }
+  g_stats["wall_ms"] = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+  return {E + h->get_core_energy(), make_wavefunction(dets, std::move(C), h->num_active_orbitals())};
+}
+
+McResult B200Pmc::_run_impl(std::shared_ptr<data::Hamiltonian> h,
+                            const std::vector<data::Configuration>& configurations) const {
+  if (!h) throw std::invalid_argument("B200Pmc: null Hamiltonian");
+  if (h->is_unrestricted())
+    throw std::runtime_error("B200Pmc does not support unrestricted orbitals. Only restricted orbitals are supported.");
+  reject_unsupported_outputs(*_settings);
+  const McscfSettings m = get_mcscf_settings(*_settings);
+  const int64_t cutoff = _settings->get<int64_t>("iterative_solver_dimension_cutoff");
+  const size_t norb = h->num_active_orbitals();
+  if (!configurations.empty() && configurations[0].get_orbital_capacity() < norb)
+    throw std::runtime_error("Configuration orbital capacity does not match Hamiltonian active space.");
+  if (configurations.empty()) throw std::runtime_error("Configuration basis cannot be empty");
+  std::vector<Det> dets;
+  dets.reserve(configurations.size());
+  for (const auto& c : configurations) dets.push_back(Det{c.alpha_word(), c.beta_word()});
+  g_stats.clear();
+  const auto t0 = std::chrono::steady_clock::now();
+  CiSession S(*h);
+  std::vector<double> C;
+  double E = 0.;
+  const int64_t n = int64_t(dets.size());
+  if (n == 1) {
+    E = S.diagonal_element(dets[0]);
+    C = {1.0};
+  } else if (n <= cutoff) {
+    E = S.dense_diag(dets, m.ci_matel_tol, C);
+  } else {
+    E = S.selected_ci_diag(dets, m.ci_matel_tol, m.ci_max_subspace, m.ci_res_tol, C);
+  }
+  g_stats["ndets"] = double(n);
+  g_stats["wall_ms"] = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+  return {E + h->get_core_energy(), make_wavefunction(dets, std::move(C), norb)};
+}
+
+void set_device(int device) { comm_config().device = device; }
+void set_communicator(const std::string& id, int rank, int nranks) {
+  if (id.size() != 128) throw std::invalid_argument("set_communicator: the NCCL unique id has 128 bytes");
+  if (nranks < 1 || rank < 0 || rank >= nranks) throw std::invalid_argument("set_communicator: bad rank / nranks");
+  CommConfig& c = comm_config();
+  c.set = true;
+  c.id = id;
+  c.rank = rank;
+  c.nranks = nranks;
+}
+void clear_communicator() {
+  CommConfig& c = comm_config();
+  c.set = false;
+  c.id.clear();
+  c.rank = 0;
+  c.nranks = 1;
+}
+std::map<std::string, double> last_run_stats() { return g_stats; }
+
+std::pair<double, std::vector<double>> davidson_solver(int64_t n, const int64_t* rowptr, const int64_t* colind,
+                                                       const double* nzval, double tol, int64_t max_m) {
+  if (n < 1) throw std::invalid_argument("davidson_solver: empty matrix");
+  b2ci_ctx* ctx = nullptr;
+  B2(b2ci_ctx_create(comm_config().device, nullptr, &ctx));
+  b2ci_csr* H = nullptr;
+  std::vector<double> X(size_t(n), 0.0);
+  double E = 0.;
+  int64_t niter = 0;
+  try {
+    B2(b2ci_csr_upload(ctx, n, rowptr[n] - rowptr[0], rowptr, colind, nzval, &H));
+    // diagonal_guess: unit vector at the smallest diagonal element (davidson.hpp:106-113)
+    std::vector<double> D(static_cast<size_t>(n), 0.0);
+    B2(b2ci_csr_diagonal(ctx, H, D.data()));
+    X[size_t(std::min_element(D.begin(), D.end()) - D.begin())] = 1.0;
+    const int rc = b2ci_davidson(ctx, H, max_m, tol, X.data(), 0, &niter, &E, nullptr);
+    if (rc != 0) throw std::runtime_error(b2ci_last_error());
+  } catch (...) {
+    if (H) b2ci_csr_free(ctx, H);
+    b2ci_ctx_destroy(ctx);
+    throw;
+  }
+  b2ci_csr_free(ctx, H);
+  b2ci_ctx_destroy(ctx);
+  return {E, std::move(X)};
+}
+
+}  // namespace qdk_b200::algorithms

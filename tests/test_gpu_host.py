@@ -1,0 +1,145 @@
+"""GPU tests of the plugin layer: the calculators are created through the factory and run like
+their MACIS counterparts; energies are checked against the reference's own known answers
+(external/macis/tests/{asci,davidson}.cxx, external/macis/python/tests/test_pymacis.py) and the
+fixtures generated from the compiled reference (tests/golden/make_golden.py)."""
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from oracle import port
+from qdk_chemistry_b200 import algorithms as alg
+from qdk_chemistry_b200 import data
+from qdk_chemistry_b200 import workloads as W
+from helpers import cisd_space, sha
+
+pytestmark = pytest.mark.gpu
+MC = "multi_configuration_calculator"
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _ham(sp):
+    return data.Hamiltonian(sp.T, sp.V, sp.core_energy)
+
+
+def _words(wfn):
+    w = wfn.determinant_words()
+    return w[:, 0], w[:, 1]
+
+
+def test_cpp_consumer_of_the_plugin_api():
+    exe = os.path.join(ROOT, "qdk_chemistry_b200", "host", "build", "host_smoke")
+    out = subprocess.run([exe], capture_output=True, text=True, timeout=120)
+    assert out.returncode == 0, out.stdout + out.stderr
+    assert "b200_cas" in out.stdout and "b200_asci" in out.stdout
+
+
+def test_casci_n2_6e6o_dense_and_iterative(n2_6, golden_meta):
+    # test_pymacis.py:114-126; dense branch (n = 400 <= 2000) and forced iterative branch
+    # (cpp/tests/test_mc.cpp:415-437 uses iterative_solver_dimension_cutoff = 10 the same way)
+    Ed, wd = alg.create(MC, "macis_cas").run(_ham(n2_6), 3, 3)
+    Ei, wi = alg.create(MC, "macis_cas", iterative_solver_dimension_cutoff=10,
+                        ci_residual_tolerance=1e-9).run(_ham(n2_6), 3, 3)
+    ref = golden_meta["n2_6e6o_casci_ref"]["E"]
+    assert wd.size() == wi.size() == 400
+    assert abs(Ed - n2_6.core_energy - ref) < 1e-9          # dense: eigenvalue to rounding
+    assert abs(Ei - n2_6.core_energy - ref) < 1e-8          # north_star: 1e-8 Eh
+    assert np.isclose(Ed - n2_6.core_energy, golden_meta["known_answers"]["n2_6e6o_casci"])
+    assert abs(wd.norm() - 1) < 1e-12 and abs(wi.norm() - 1) < 1e-12
+    assert abs(abs(wd.overlap(wi)) - 1) < 1e-8
+    # determinant order of the wavefunction = generate_hilbert_space order
+    a, b = port.generate_hilbert_space(6, 3, 3)
+    wa, wb = _words(wd)
+    assert np.array_equal(wa, a) and np.array_equal(wb, b)
+    assert wd.get_active_determinants()[0].to_string() == "222000"
+    st = alg.last_run_stats()
+    assert st["ndets"] == 400 and st["davidson_calls"] == 1 and st["h_build_ms"] > 0
+
+
+def test_casci_single_determinant_and_errors(n2_6):
+    E, w = alg.create(MC, "b200_cas").run(_ham(n2_6), 6, 6)   # one determinant: <D|H|D>
+    h = port.Ham(n2_6.norb, n2_6.T, n2_6.V)
+    assert w.size() == 1 and abs(E - n2_6.core_energy - h.matrix_element(63, 63, 63, 63)) < 1e-12
+    with pytest.raises(RuntimeError, match="Davidson Did Not Converge"):
+        alg.create(MC, "b200_cas", iterative_solver_dimension_cutoff=10, max_solver_iterations=2,
+                   ci_residual_tolerance=1e-12).run(_ham(n2_6), 3, 3)
+    with pytest.raises(ValueError):
+        alg.create(MC, "b200_cas").run(_ham(n2_6), 7, 3)
+
+
+def test_asci_water_grow_and_refine_known_answers(water, golden_meta):
+    # external/macis/tests/asci.cxx:541-558 (fixed core of 100 determinants, 10,000 determinants)
+    ka = golden_meta["known_answers"]
+    kw = dict(ntdets_max=10000, core_selection_strategy="fixed", ci_residual_tolerance=1e-8)
+    Eg, wg = alg.create(MC, "macis_asci", max_refine_iter=0, **kw).run(_ham(water), 5, 5)
+    assert wg.size() == 10000 and abs(wg.norm() - 1) < 1e-12
+    assert abs(Eg - water.core_energy - ka["water_asci_grow"]) < 1e-8
+    Er, wr = alg.create(MC, "macis_asci", **kw).run(_ham(water), 5, 5)
+    assert abs(Er - water.core_energy - ka["water_asci_refine"]) < 1e-8
+    a, b = _words(wr)
+    assert sha(np.sort(port.pack(a, b))) == golden_meta["water_asci_refine_ref"]["dets_sha"]
+    # wavefunction comes back in solver (spin_comparator) order
+    assert np.array_equal(port.spin_sort_order(a, b), np.arange(len(a)))
+    st = alg.last_run_stats()
+    assert st["asci_search_calls"] >= 4 and st["asci_search_ms"] > 0
+
+
+def test_asci_n2_14e18o_2000_determinants(n2_18, golden_meta, golden_arrays):
+    # external/macis/python/tests/test_pymacis.py:158-188
+    E, w = alg.create(MC, "macis_asci", ntdets_max=2000, grow_factor=2.0, max_refine_iter=15,
+                      max_solver_iterations=1000, ci_residual_tolerance=1e-8).run(_ham(n2_18), 7, 7)
+    assert np.isclose(E - n2_18.core_energy, golden_meta["known_answers"]["n2_14e18o_asci2000"])
+    assert abs(E - n2_18.core_energy - golden_meta["n2_14e18o_asci2000_ref"]["E"]) < 1e-8
+    a, b = _words(w)
+    got = set(port.pack(a, b).tolist())
+    want = set(golden_arrays["n2_14e18o_asci2000.dets"].tolist())
+    flip = lambda k: ((k & 0xFFFFFFFF) << 32) | (k >> 32)
+    # see tests/test_oracle.py::test_n2_14e18o_asci_2000 for the spin-flip-partner rule
+    assert len(got) == len(want) == 2000
+    assert all(flip(k) in (want - got) for k in (got - want)) and len(got - want) <= 40
+    # and against the oracle's outer loop: same energy; the selection again modulo spin-flip
+    # partners (their |c| are equal in exact arithmetic, the last bits of two Davidson
+    # implementations are not)
+    Eo, ao, bo, Xo = port.asci_run(port.Ham(n2_18.norb, n2_18.T, n2_18.V), 7, 7, refine=True,
+                                   ntdets_max=2000, grow_factor=2.0, max_refine_iter=15,
+                                   ci_max_subspace=1000)
+    wo = set(port.pack(ao, bo).tolist())
+    assert abs(E - n2_18.core_energy - Eo) < 1e-8
+    assert all(flip(k) in (wo - got) for k in (got - wo)) and len(got - wo) <= 40
+
+
+def test_asci_falls_through_to_casci_when_the_space_is_small(n2_6, golden_meta):
+    # macis_asci.cpp:125-157: ntdets_max (1e5) > FCI dimension (400)
+    E, w = alg.create(MC, "macis_asci").run(_ham(n2_6), 3, 3)
+    assert w.size() == 400 and abs(E - n2_6.core_energy - golden_meta["n2_6e6o_casci_ref"]["E"]) < 1e-8
+
+
+def test_pmc_water_cisd(water, golden_meta):
+    # projected CI on a user-supplied list (macis_pmc.cpp:36-174) = davidson.cxx:20-75 energy
+    a, b = cisd_space(24, 5, 5)
+    cfgs = [data.Configuration(int(x), int(y), 24) for x, y in zip(a, b)]
+    pmc = alg.create("projected_multi_configuration_calculator", "macis_pmc", ci_matel_tol=1e-16,
+                     ci_residual_tolerance=1e-8)
+    E, w = pmc.run(_ham(water), cfgs)
+    assert w.size() == 12636
+    assert abs(E - golden_meta["known_answers"]["water_cisd_davidson_total"]) < 1e-8
+    wa, wb = _words(w)
+    assert np.array_equal(wa, a) and np.array_equal(wb, b)   # order of the input list is kept
+    with pytest.raises(RuntimeError, match="cannot be empty"):
+        pmc2 = alg.create("projected_multi_configuration_calculator", "macis_pmc")
+        pmc2.run(_ham(water), [])
+
+
+def test_davidson_solver_on_scipy_csr():
+    # python/tests/test_davidson_solver.py: tridiagonal matrix with an analytic ground state
+    import scipy.sparse as sp
+    n = 50
+    A = sp.diags([-np.ones(n - 1), 2 * np.ones(n), -np.ones(n - 1)], [-1, 0, 1], format="csr")
+    E, x = alg.davidson_solver(A, 1e-10, 60)
+    assert abs(E - (2 - 2 * np.cos(np.pi / (n + 1)))) < 1e-9
+    assert abs(np.linalg.norm(x) - 1) < 1e-10 and np.allclose(A @ x, E * x, atol=1e-8)
+    E2, x2 = alg.davidson_solver(sp.csr_matrix(np.array([[-3.5]])))
+    assert E2 == -3.5 and x2[0] == 1.0
+    with pytest.raises(RuntimeError, match="Davidson Did Not Converge"):
+        alg.davidson_solver(A, 1e-13, 3)

@@ -1,0 +1,142 @@
+"""Host plugin layer without a GPU: factory / registration / settings behaviour of the
+MultiConfigurationCalculator API (reference: cpp/tests/test_mc.cpp factory + metadata cases,
+cpp/tests/test_macis.cpp settings round trips, algorithm.hpp:262-372)."""
+import numpy as np
+import pytest
+
+from qdk_chemistry_b200 import algorithms as alg
+from qdk_chemistry_b200 import data
+
+MC = "multi_configuration_calculator"
+PMC = "projected_multi_configuration_calculator"
+
+
+def test_factory_contents_and_defaults():
+    assert alg.available(MC) == ["b200_asci", "b200_cas"]
+    assert alg.available(PMC) == ["b200_pmc"]
+    assert alg.show_default(MC) == "b200_cas"
+    F = alg.MultiConfigurationCalculatorFactory
+    assert F.algorithm_type_name() == MC and F.has("b200_cas") and not F.has("macis_cas")
+    c = F.create("")  # empty name -> default algorithm (algorithm.hpp:262-266)
+    assert c.name() == "b200_cas" and c.type_name() == MC and c.aliases() == ["b200_cas"]
+    with pytest.raises(RuntimeError, match="not found in registry, available options are"):
+        F.create("nope")
+    with pytest.raises(KeyError):
+        alg.create("scf_solver")
+
+
+def test_reference_names_resolve_to_drop_ins():
+    assert alg.create(MC, "macis_cas").name() == "b200_cas"
+    assert alg.create(MC, "macis_asci").name() == "b200_asci"
+    assert alg.create(PMC, "macis_pmc").name() == "b200_pmc"
+
+
+def test_settings_defaults_match_the_reference():
+    s = alg.create(MC, "b200_cas").settings()
+    assert s.get("ci_residual_tolerance") == 1e-6          # mc.hpp:47-49
+    assert s.get("max_solver_iterations") == 200
+    assert s.get("iterative_solver_dimension_cutoff") == 2000
+    assert s.get("ci_matel_tol") == np.finfo(np.float64).eps  # mcscf.hpp:51
+    assert s.get("calculate_one_rdm") is False
+    a = alg.create(MC, "b200_asci").settings()
+    want = dict(ntdets_max=100000, ntdets_min=100, ncdets_max=100, search_matel_tol=1e-8,
+                rv_prune_tol=1e-8, pair_size_max=500000000, grow_factor=8.0, min_grow_factor=1.01,
+                growth_backoff_rate=0.5, growth_recovery_rate=1.1, max_refine_iter=6,
+                refine_energy_tol=1e-6, warm_start_davidson=True, min_warm_start_overlap=0.5,
+                min_patch_overlap=0.3, grow_ci_residual_tolerance=0.0, taper_grow_factor=0.0,
+                constraint_level=2, hamiltonian_build_algorithm="", just_singles=False,
+                core_selection_strategy="percentage", core_selection_threshold=0.95)
+    for k, v in want.items():                               # determinant_search.hpp:95-199
+        assert a.get(k) == v, k
+    assert a.has_description("ntdets_max") and a.get_type_name("grow_factor") == "double"
+
+
+def test_settings_errors():
+    s = alg.create(MC, "b200_asci").settings()
+    with pytest.raises(data.SettingNotFound):
+        s.set("no_such_key", 1)
+    with pytest.raises(data.SettingNotFound):
+        s.get("no_such_key")
+    with pytest.raises(data.SettingTypeMismatch):
+        s.set("ntdets_max", "many")
+    with pytest.raises(ValueError):
+        s.set("ntdets_max", 0)                      # BoundConstraint{1, max}
+    with pytest.raises(ValueError):
+        s.set("core_selection_strategy", "random")  # ListConstraint
+    s.set("grow_factor", 2)                         # int accepted for a double setting
+    assert s.get("grow_factor") == 2.0
+    s.update({"ntdets_max": 2000, "core_selection_strategy": "fixed"})
+    assert s["ntdets_max"] == 2000 and "ntdets_max" in s
+    s.lock()
+    with pytest.raises(data.SettingsAreLocked):
+        s.set("ntdets_max", 10)
+
+
+def test_create_forwards_kwargs_and_hash_changes_with_settings():
+    h = data.Hamiltonian(np.eye(2), np.zeros(16), 0.25)
+    c1 = alg.create(MC, "b200_cas")
+    c2 = alg.create(MC, "b200_cas", ci_residual_tolerance=1e-9)
+    assert c2.settings().get("ci_residual_tolerance") == 1e-9
+    assert c1.hash(h, 1, 1) != c2.hash(h, 1, 1)
+    assert c1.hash(h, 1, 1) == alg.create(MC, "b200_cas").hash(h, 1, 1)
+    assert c1.hash(h, 1, 1) != c1.hash(h, 1, 0)
+
+
+def test_python_subclass_registration_through_the_trampoline():
+    class Fixed(alg.MultiConfigurationCalculator):
+        def __init__(self):
+            super().__init__()
+
+        def name(self):
+            return "fixed_energy"
+
+        def _run_impl(self, hamiltonian, na, nb):
+            wfn = alg.create(MC, "b200_cas")  # any object; the energy is what is checked
+            return -1.25 + hamiltonian.get_core_energy(), None
+
+    alg.register(lambda: Fixed())
+    try:
+        assert "fixed_energy" in alg.available(MC)
+        with pytest.raises(alg.DuplicateRegistrationError):
+            alg.register(lambda: Fixed())
+        c = alg.create(MC, "fixed_energy")
+        E, w = c.run(data.Hamiltonian(np.eye(2), np.zeros(16), 0.25), 1, 1)
+        assert E == -1.0 and w is None
+    finally:
+        alg.unregister(MC, "fixed_energy")
+    assert "fixed_energy" not in alg.available(MC)
+    with pytest.raises(KeyError):
+        alg.unregister(MC, "fixed_energy")
+
+
+def test_data_stand_ins():
+    c = data.Configuration("2ud0")
+    assert (c.alpha_word(), c.beta_word()) == (0b0011, 0b0101) and c.to_string() == "2ud0"
+    assert c.get_n_electrons() == (2, 2) and c == data.Configuration(3, 5, 4)
+    with pytest.raises(ValueError):
+        data.Configuration("2x")
+    with pytest.raises(ValueError):
+        data.Hamiltonian(np.eye(3), np.zeros(16), 0.0)
+    h = data.Hamiltonian(np.arange(4.0).reshape(2, 2), np.arange(16.0), -2.0)
+    assert h.num_active_orbitals() == 2 and h.get_core_energy() == -2.0
+    assert np.array_equal(h.get_two_body_integrals(), np.arange(16.0))
+
+
+def test_run_without_a_gpu_fails_loudly_and_locks_settings():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    c = alg.create(MC, "b200_cas")
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        c.run(data.Hamiltonian(np.eye(2), np.zeros(16), 0.0), 1, 1)
+    with pytest.raises(data.SettingsAreLocked):   # run() locks before _run_impl (algorithm.hpp:67-70)
+        c.settings().set("ci_residual_tolerance", 1e-9)
+    unres = data.Hamiltonian(np.eye(2), np.zeros(16), 0.0, True)
+    with pytest.raises(RuntimeError, match="does not support unrestricted orbitals"):
+        alg.create(MC, "b200_asci").run(unres, 1, 1)
+    with pytest.raises(RuntimeError, match="not available"):
+        alg.create(MC, "b200_cas", calculate_one_rdm=True).run(
+            data.Hamiltonian(np.eye(2), np.zeros(16), 0.0), 1, 1)
+    with pytest.raises(RuntimeError, match="grow_factor must be > 1.0"):
+        alg.create(MC, "b200_asci", grow_factor=1.0).run(
+            data.Hamiltonian(np.eye(2), np.zeros(16), 0.0), 1, 1)
