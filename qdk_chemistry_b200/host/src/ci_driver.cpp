@@ -15,6 +15,7 @@
 #include <cmath>
 #include <cstring>
 #include <limits>
+#include <mutex>
 #include <numeric>
 #include <unordered_map>
 
@@ -36,15 +37,23 @@ struct DetHash {
 // spin_comparator: alpha-major, then beta (raw_bitset.hpp:119-141)
 inline bool spin_less(const Det& x, const Det& y) { return x.a != y.a ? x.a < y.a : x.b < y.b; }
 
-struct CommConfig {
-  bool set = false;
-  std::string id;
-  int rank = 0, nranks = 1;
+// One CUDA context (device + stream + optional NCCL communicator) per process, shared by all
+// calculator runs: an NCCL unique id can initialise a communicator only once, so the
+// communicator is created in set_communicator() and lives until clear_communicator().
+struct Runtime {
+  std::mutex mutex;  // run() is single-caller in the reference; concurrent runs serialise here
+  b2ci_ctx* ctx = nullptr;
   int device = 0;
+  int rank = 0, nranks = 1;
+  void drop() {
+    if (ctx) b2ci_ctx_destroy(ctx);
+    ctx = nullptr;
+  }
+  ~Runtime() { drop(); }
 };
-CommConfig& comm_config() {
-  static CommConfig c;
-  return c;
+Runtime& runtime() {
+  static Runtime r;
+  return r;
 }
 thread_local std::map<std::string, double> g_stats;
 
@@ -142,24 +151,19 @@ int64_t binomial(int64_t n, int64_t k) {
 // ---------------------------------------------------------------------------------------------
 class CiSession {
  public:
-  explicit CiSession(const data::Hamiltonian& h) : norb_(int(h.num_active_orbitals())), ham_(h) {
-    const CommConfig& cc = comm_config();
+  explicit CiSession(const data::Hamiltonian& h)
+      : norb_(int(h.num_active_orbitals())), ham_(h), lock_(runtime().mutex) {
+    Runtime& rt = runtime();
     if (norb_ > 64) throw std::runtime_error("active spaces with more than 64 orbitals are not built");
-    B2(b2ci_ctx_create(cc.device, nullptr, &ctx_));
-    try {
-      if (cc.set && cc.nranks > 1) B2(b2ci_comm_init(ctx_, cc.id.data(), cc.rank, cc.nranks));
-      rank_ = cc.set ? cc.rank : 0;
-      nranks_ = cc.set ? cc.nranks : 1;
-      // T is symmetric; the two-body array is handed over as MACIS reinterprets it
-      // (macis_cas.cpp:76-82): element (pq|rs) of the QDK layout p n^3 + q n^2 + r n + s is
-      // read as column-major V(s,r,q,p) = (sr|qp), equal by symmetry.
-      B2(b2ci_integrals_upload(ctx_, norb_, h.get_one_body_integrals().data(), h.get_two_body_integrals().data()));
-    } catch (...) {
-      b2ci_ctx_destroy(ctx_);
-      throw;
-    }
+    if (!rt.ctx) B2(b2ci_ctx_create(rt.device, nullptr, &rt.ctx));
+    ctx_ = rt.ctx;
+    rank_ = rt.rank;
+    nranks_ = rt.nranks;
+    // T is symmetric; the two-body array is handed over as MACIS reinterprets it
+    // (macis_cas.cpp:76-82): element (pq|rs) of the QDK layout p n^3 + q n^2 + r n + s is
+    // read as column-major V(s,r,q,p) = (sr|qp), equal by symmetry.
+    B2(b2ci_integrals_upload(ctx_, norb_, h.get_one_body_integrals().data(), h.get_two_body_integrals().data()));
   }
-  ~CiSession() { b2ci_ctx_destroy(ctx_); }
   CiSession(const CiSession&) = delete;
 
   int norb() const { return norb_; }
@@ -277,7 +281,8 @@ class CiSession {
   }
   int norb_;
   const data::Hamiltonian& ham_;
-  b2ci_ctx* ctx_ = nullptr;
+  std::unique_lock<std::mutex> lock_;
+  b2ci_ctx* ctx_ = nullptr;  // borrowed from the process runtime
   int rank_ = 0, nranks_ = 1;
 };
 
@@ -658,22 +663,40 @@ McResult B200Pmc::_run_impl(std::shared_ptr<data::Hamiltonian> h,
   return {E + h->get_core_energy(), make_wavefunction(dets, std::move(C), norb)};
 }
 
-void set_device(int device) { comm_config().device = device; }
+void set_device(int device) {
+  Runtime& rt = runtime();
+  std::lock_guard<std::mutex> g(rt.mutex);
+  if (device != rt.device) {
+    if (rt.nranks > 1) throw std::runtime_error("set_device: clear_communicator() first");
+    rt.drop();
+    rt.device = device;
+  }
+}
 void set_communicator(const std::string& id, int rank, int nranks) {
   if (id.size() != 128) throw std::invalid_argument("set_communicator: the NCCL unique id has 128 bytes");
   if (nranks < 1 || rank < 0 || rank >= nranks) throw std::invalid_argument("set_communicator: bad rank / nranks");
-  CommConfig& c = comm_config();
-  c.set = true;
-  c.id = id;
-  c.rank = rank;
-  c.nranks = nranks;
+  Runtime& rt = runtime();
+  std::lock_guard<std::mutex> g(rt.mutex);
+  rt.drop();
+  rt.rank = 0;
+  rt.nranks = 1;
+  B2(b2ci_ctx_create(rt.device, nullptr, &rt.ctx));
+  if (nranks > 1) {
+    if (b2ci_comm_init(rt.ctx, id.data(), rank, nranks) != 0) {
+      const std::string err = b2ci_last_error();
+      rt.drop();
+      throw std::runtime_error("b2ci_comm_init: " + err);
+    }
+  }
+  rt.rank = rank;
+  rt.nranks = nranks;
 }
 void clear_communicator() {
-  CommConfig& c = comm_config();
-  c.set = false;
-  c.id.clear();
-  c.rank = 0;
-  c.nranks = 1;
+  Runtime& rt = runtime();
+  std::lock_guard<std::mutex> g(rt.mutex);
+  rt.drop();
+  rt.rank = 0;
+  rt.nranks = 1;
 }
 std::map<std::string, double> last_run_stats() { return g_stats; }
 
@@ -681,7 +704,7 @@ std::pair<double, std::vector<double>> davidson_solver(int64_t n, const int64_t*
                                                        const double* nzval, double tol, int64_t max_m) {
   if (n < 1) throw std::invalid_argument("davidson_solver: empty matrix");
   b2ci_ctx* ctx = nullptr;
-  B2(b2ci_ctx_create(comm_config().device, nullptr, &ctx));
+  B2(b2ci_ctx_create(runtime().device, nullptr, &ctx));
   b2ci_csr* H = nullptr;
   std::vector<double> X(size_t(n), 0.0);
   double E = 0.;

@@ -1,0 +1,89 @@
+"""Worker of the multi-GPU tests (one process per GPU, launched by torchrun): row-sharded H
+build, sigma (NCCL all-gather + SpMV) and Davidson through the C ABI and through the plugin
+layer, checked against the single-GPU result computed by every rank. Prints one JSON line."""
+import json
+import os
+import sys
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from qdk_chemistry_b200 import algorithms as alg  # noqa: E402
+from qdk_chemistry_b200 import data, device  # noqa: E402
+from qdk_chemistry_b200 import workloads as W  # noqa: E402
+
+EPS = float(np.finfo(np.float64).eps)
+
+
+def main():
+    rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
+    local = int(os.environ.get("LOCAL_RANK", rank))
+    torch.cuda.set_device(local)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    out = {"world": world}
+    sp = W.config("small_cas8")
+    # ---- C ABI level
+    ctx = device.Context(local, torch.cuda.current_stream().cuda_stream)
+    idt = torch.zeros(128, dtype=torch.uint8, device="cuda")
+    if rank == 0:
+        idt.copy_(torch.frombuffer(bytearray(device.Context.comm_unique_id()), dtype=torch.uint8))
+    dist.broadcast(idt, 0)
+    ctx.comm_init(bytes(idt.cpu().numpy().tobytes()), rank, world)
+    ctx.upload_integrals(sp.norb, sp.T, sp.V)
+    dets = ctx.generate_fci(sp.norb, sp.nalpha, sp.nbeta)
+    n = len(dets)
+    # deliberately unequal blocks: exercises the grouped-broadcast all-gather
+    cuts = [0] + [int(n * (r + 1) / world) - (7 if r % 2 == 0 and r + 1 < world else 0) for r in range(world)]
+    cuts[-1] = n
+    r0, r1 = cuts[rank], cuts[rank + 1]
+    Hloc = ctx.hbuild(dets, EPS, (r0, r1))
+    # single-GPU reference on a second, communicator-free context
+    ctx1 = device.Context(local, torch.cuda.current_stream().cuda_stream)
+    ctx1.upload_integrals(sp.norb, sp.T, sp.V)
+    d1 = ctx1.generate_fci(sp.norb, sp.nalpha, sp.nbeta)
+    Hfull = ctx1.hbuild(d1, EPS)
+    rp, ci, nz = Hfull.download()
+    rpl, cil, nzl = Hloc.download()
+    out["block_bit_exact"] = bool(np.array_equal(rpl, rp[r0:r1 + 1] - rp[r0]) and
+                                  np.array_equal(cil, ci[rp[r0]:rp[r1]]) and
+                                  np.array_equal(nzl, nz[rp[r0]:rp[r1]]))
+    x = np.random.default_rng(0).normal(size=n)
+    xl = torch.from_numpy(x[r0:r1].copy()).cuda()
+    xf = torch.empty(n, dtype=torch.float64, device="cuda")
+    yl = torch.empty(r1 - r0, dtype=torch.float64, device="cuda")
+    Hloc.sigma_sharded(xl.data_ptr(), xf.data_ptr(), yl.data_ptr())
+    torch.cuda.synchronize()
+    yref = Hfull.spmv(x)
+    out["gather_exact"] = bool(np.array_equal(xf.cpu().numpy(), x))
+    out["sigma_bit_exact"] = bool(np.array_equal(yl.cpu().numpy(), yref[r0:r1]))
+    E1, X1, it1, _ = Hfull.davidson(200, 1e-8)
+    Ed, Xd, itd, _ = Hloc.davidson(200, 1e-8)
+    out.update(E_single=E1, E_sharded=Ed, niter_single=it1, niter_sharded=itd,
+               overlap=float(abs(X1 @ Xd)), norm=float(Xd @ Xd))
+    ctx.close()
+    ctx1.close()
+    # ---- plugin level
+    alg.init_distributed_from_torch(local)
+    ham = data.Hamiltonian(sp.T, sp.V, sp.core_energy)
+    Ep, wp = alg.create("multi_configuration_calculator", "macis_cas", ci_residual_tolerance=1e-8).run(
+        ham, sp.nalpha, sp.nbeta)
+    out.update(E_plugin=Ep - sp.core_energy, plugin_norm=wp.norm(), plugin_ndets=wp.size())
+    Ea, wa = alg.create("multi_configuration_calculator", "macis_asci", ntdets_max=600,
+                        ci_residual_tolerance=1e-8).run(ham, sp.nalpha, sp.nbeta)
+    alg.clear_communicator()
+    Ea1, wa1 = alg.create("multi_configuration_calculator", "macis_asci", ntdets_max=600,
+                          ci_residual_tolerance=1e-8).run(ham, sp.nalpha, sp.nbeta)
+    out.update(E_asci_sharded=Ea, E_asci_single=Ea1, asci_ndets=wa.size(),
+               asci_same_dets=bool(np.array_equal(wa.determinant_words(), wa1.determinant_words())))
+    gathered = [None] * world
+    dist.all_gather_object(gathered, out)
+    if rank == 0:
+        print("DIST_RESULT " + json.dumps(gathered))
+    dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()
