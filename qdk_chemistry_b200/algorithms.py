@@ -23,6 +23,7 @@ from ._core.algorithms import (  # noqa: F401  (re-exported)
     clear_communicator,
     davidson_solver,
     last_run_stats,
+    row_block,
     set_communicator,
     set_device,
 )
@@ -102,8 +103,19 @@ def init_distributed_from_torch(device: int | None = None) -> None:
     if world == 1:
         clear_communicator()
         return
-    idt = torch.zeros(128, dtype=torch.uint8, device=f"cuda:{device}")
-    if rank == 0:
-        idt.copy_(torch.frombuffer(bytearray(_dev.Context.comm_unique_id()), dtype=torch.uint8))
+    uid = broadcast_unique_id(_dev.Context.comm_unique_id() if rank == 0 else None,
+                              f"cuda:{device}" if dist.get_backend() == "nccl" else "cpu")
+    set_communicator(uid, rank, world)
+
+
+def broadcast_unique_id(unique_id: bytes | None, tensor_device: str = "cpu") -> bytes:
+    """Rank 0 passes the 128-byte NCCL unique id, the others None; returns it on every rank."""
+    import torch
+    import torch.distributed as dist
+    idt = torch.zeros(128, dtype=torch.uint8, device=tensor_device)
+    if dist.get_rank() == 0:
+        if unique_id is None or len(unique_id) != 128:
+            raise ValueError("rank 0 must pass the 128-byte unique id")
+        idt.copy_(torch.frombuffer(bytearray(unique_id), dtype=torch.uint8))
     dist.broadcast(idt, 0)
-    set_communicator(bytes(idt.cpu().numpy().tobytes()), rank, world)
+    return bytes(idt.cpu().numpy().tobytes())

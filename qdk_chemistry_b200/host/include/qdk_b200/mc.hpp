@@ -92,6 +92,9 @@ void set_device(int device);
 void set_communicator(const std::string& unique_id128, int rank, int nranks);
 void clear_communicator();
 
+// contiguous row block [r0, r1) of a rank: equal blocks, the remainder spread over the first ranks
+std::pair<int64_t, int64_t> row_block(int64_t n, int rank, int nranks);
+
 // last-run statistics of the calling thread (phase timings in ms, sizes, Davidson iterations)
 std::map<std::string, double> last_run_stats();
 

@@ -24,6 +24,8 @@
 
 namespace qdk_b200::algorithms {
 
+std::pair<int64_t, int64_t> row_block(int64_t n, int rank, int nranks);
+
 namespace {
 
 struct Det {
@@ -174,11 +176,7 @@ class CiSession {
                                     ham_.get_two_body_integrals().data(), d.a, d.b, d.a, d.b);
   }
 
-  std::pair<int64_t, int64_t> my_rows(int64_t n) const {  // contiguous row blocks in rank order
-    const int64_t base = n / nranks_, rem = n % nranks_;
-    const int64_t r0 = rank_ * base + std::min<int64_t>(rank_, rem);
-    return {r0, r0 + base + (rank_ < rem ? 1 : 0)};
-  }
+  std::pair<int64_t, int64_t> my_rows(int64_t n) const { return row_block(n, rank_, nranks_); }
 
   // selected_ci_diag on a device-resident list: H build of this rank's rows + Davidson with
   // the guess policy of serial_selected_ci_diag. X: empty or a guess; returns the full vector.
@@ -663,6 +661,12 @@ McResult B200Pmc::_run_impl(std::shared_ptr<data::Hamiltonian> h,
   return {E + h->get_core_energy(), make_wavefunction(dets, std::move(C), norb)};
 }
 
+std::pair<int64_t, int64_t> row_block(int64_t n, int rank, int nranks) {
+  if (n < 0 || nranks < 1 || rank < 0 || rank >= nranks) throw std::invalid_argument("row_block: bad arguments");
+  const int64_t base = n / nranks, rem = n % nranks;
+  const int64_t r0 = rank * base + std::min<int64_t>(rank, rem);
+  return {r0, r0 + base + (rank < rem ? 1 : 0)};
+}
 void set_device(int device) {
   Runtime& rt = runtime();
   std::lock_guard<std::mutex> g(rt.mutex);

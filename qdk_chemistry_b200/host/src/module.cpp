@@ -250,4 +250,6 @@ PYBIND11_MODULE(_core, m) {
            py::arg("unique_id"), py::arg("rank"), py::arg("nranks"));
   amod.def("clear_communicator", &clear_communicator);
   amod.def("last_run_stats", &last_run_stats);
+  amod.def("row_block", &row_block, py::arg("n"), py::arg("rank"), py::arg("nranks"),
+           "contiguous row block [r0, r1) of rank `rank` (the partition every sharded run uses)");
 }
