@@ -24,6 +24,11 @@
 #include "slater.cuh"
 
 namespace b2ci {
+
+void radix_sort_pairs(b2ci_ctx* ctx, uint64_t* keys, uint64_t* keys_alt, uint32_t* vals,
+                      uint32_t* vals_alt, int64_t n, const std::vector<int>& shifts);
+void iota_u32(b2ci_ctx* ctx, uint32_t* v, int64_t n);
+
 namespace {
 
 constexpr int ROW_WARPS = 8;  // warps (rows) per CTA
@@ -98,8 +103,11 @@ struct RowArgs {
   const uint64_t* beta;
   const int32_t* run_of;
   const int64_t* run_start;
-  const int64_t* adj_ptr;
+  const int64_t* adj_ptr;   // alpha-run adjacency, distance <= 2 (self included), ascending
   const uint32_t* adj;
+  const int32_t* bgrp_of;   // beta group of every determinant
+  const int64_t* bgrp_start;
+  const uint32_t* bgrp_mem; // determinant indices grouped by beta string, ascending inside a group
   int64_t row_begin;
   int64_t nrows;
   double thr;
@@ -137,6 +145,15 @@ __device__ __forceinline__ void process_batch(const RowArgs& A, int64_t i, uint6
   cnt += __popc(km);
 }
 
+// Row i = (alpha_i, beta_i) of an arbitrary list connects to
+//   (a) the determinants of its own alpha run with beta distance <= 4,
+//   (b) the determinants of runs one alpha single excitation away with beta distance <= 2,
+//   (c) the determinants with the SAME beta string whose alpha string is a double excitation.
+// (a) and (b) are found by scanning the beta strings of the <= 1 + n_occ n_virt adjacent runs;
+// (c) comes from the list of determinants grouped by beta string -- no scan of the (thousands
+// of) runs two alpha excitations away. Runs are contiguous index ranges and group members are
+// stored in ascending index, so the two streams are merged on the fly: before run r' is
+// scanned, the group members below its first index are emitted. Columns come out ascending.
 template <bool FILL, bool EVAL>
 __global__ void __launch_bounds__(ROW_WARPS * 32)
 k_rows(const RowArgs A) {
@@ -152,36 +169,84 @@ k_rows(const RowArgs A) {
   int32_t cnt = 0;
   int64_t out = FILL ? A.rowptr[row] : 0;
   const unsigned lt = (1u << lane) - 1u;
+  // enqueue the hits of one ballot; evaluate / count / write 32 at a time with full lanes
+  auto push = [&](bool hit, int64_t j) {
+    const unsigned m = __ballot_sync(0xffffffffu, hit);
+    if (!m) return;
+    if (hit) q[qn + __popc(m & lt)] = int32_t(j);
+    qn += __popc(m);
+    __syncwarp();
+    if (qn >= 32) {
+      process_batch<FILL, EVAL>(A, i, ai, bi, q, 32, lane, out, cnt);
+      const int rest = qn - 32;
+      const int32_t t = (lane < rest) ? q[32 + lane] : 0;
+      __syncwarp();
+      if (lane < rest) q[lane] = t;
+      qn = rest;
+      __syncwarp();
+    }
+  };
   if (ai != 0) {
+    const int32_t g = A.bgrp_of[i];
+    int64_t bpos = A.bgrp_start[g];
+    const int64_t bend = A.bgrp_start[g + 1];
+    int64_t nextj = bpos < bend ? int64_t(A.bgrp_mem[bpos]) : INT64_MAX;
+    // (c): members of the beta group with index < bound
+    auto flush_group = [&](int64_t bound) {
+      while (nextj < bound) {
+        const int64_t p = bpos + lane;
+        const int64_t j = p < bend ? int64_t(A.bgrp_mem[p]) : INT64_MAX;
+        const bool in = j < bound;
+        bool hit = false;
+        if (in) {
+          const uint64_t aj = A.alpha[j];
+          hit = aj != 0 && __popcll(ai ^ aj) == 4;
+        }
+        const int nin = __popc(__ballot_sync(0xffffffffu, in));  // a prefix: members ascend
+        push(hit, j);
+        bpos += nin;
+        nextj = bpos < bend ? int64_t(A.bgrp_mem[bpos]) : INT64_MAX;
+        if (nin < 32) break;
+      }
+    };
     const int64_t e0 = A.adj_ptr[r], e1 = A.adj_ptr[r + 1];
     for (int64_t e = e0; e < e1; ++e) {
       const uint32_t pk = A.adj[e];
       const int da = int(pk & 3u) * 2;
       const int64_t ks = A.run_start[pk >> 2], ke = A.run_start[(pk >> 2) + 1];
+      flush_group(ks);
       for (int64_t j0 = ks; j0 < ke; j0 += 32) {
         const int64_t j = j0 + lane;
         bool hit = false;
         if (j < ke) hit = (da + __popcll(bi ^ A.beta[j])) <= 4;
-        const unsigned m = __ballot_sync(0xffffffffu, hit);
-        if (m) {
-          if (hit) q[qn + __popc(m & lt)] = int32_t(j);
-          qn += __popc(m);
-          __syncwarp();
-          if (qn >= 32) {
-            process_batch<FILL, EVAL>(A, i, ai, bi, q, 32, lane, out, cnt);
-            const int rest = qn - 32;
-            const int32_t t = (lane < rest) ? q[32 + lane] : 0;
-            __syncwarp();
-            if (lane < rest) q[lane] = t;
-            qn = rest;
-            __syncwarp();
-          }
-        }
+        push(hit, j);
+      }
+      // group members inside this run are at alpha distance <= 2: already covered by the scan
+      while (nextj < ke) {
+        const int64_t p = bpos + lane;
+        const int64_t j = p < bend ? int64_t(A.bgrp_mem[p]) : INT64_MAX;
+        const int nin = __popc(__ballot_sync(0xffffffffu, j < ke));
+        bpos += nin;
+        nextj = bpos < bend ? int64_t(A.bgrp_mem[bpos]) : INT64_MAX;
+        if (nin < 32) break;
       }
     }
+    flush_group(INT64_MAX);
     if (qn > 0) process_batch<FILL, EVAL>(A, i, ai, bi, q, qn, lane, out, cnt);
   }
   if (!FILL && lane == 0) A.row_cnt[row] = cnt;
+}
+
+// beta groups: determinant indices sorted by beta string (stable), group boundaries
+__global__ void k_group_scatter(const uint64_t* __restrict__ key_sorted, const uint32_t* __restrict__ idx_sorted,
+                                int64_t n, const int32_t* __restrict__ flag, const int32_t* __restrict__ excl,
+                                int32_t* __restrict__ grp_of, int64_t* __restrict__ grp_start, int32_t ngroups) {
+  const int64_t p = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (p >= n) return;
+  const int32_t g = excl[p] + flag[p] - 1;
+  grp_of[idx_sorted[p]] = g;
+  if (flag[p]) grp_start[g] = p;
+  if (p == n - 1) grp_start[ngroups] = n;
 }
 
 // ------------------------------------------------------------------ rectangular lists
@@ -806,12 +871,14 @@ void hbuild_csr(b2ci_ctx* ctx, const b2ci_dets* dets, int64_t row_begin, int64_t
     k_run_scatter<<<gb, 256, 0, st>>>(dets->alpha, n, flag, excl, run_of, run_start, run_alpha, nruns);
     ctx->launches++;
     B2_CHECK_LAUNCH();
-    // run adjacency (count, scan, fill)
+  }
+  // run adjacency (count, scan, fill): distance <= 4 for the product path, <= 2 for the scan path
+  auto build_adjacency = [&](int maxd) {
+    ScopedTimer t(ctx, "h_build.setup", true);
     DevBuf<int32_t> acnt(nruns);
-    run_deg.alloc(size_t(nruns) * 3);
     adj_ptr.alloc(nruns + 1);
     const unsigned ga = unsigned((int64_t(nruns) * 32 + 255) / 256);
-    k_string_adjacency<false><<<ga, 256, 0, st>>>(run_alpha, nruns, 4, 1, acnt, run_deg, nullptr, nullptr);
+    k_string_adjacency<false><<<ga, 256, 0, st>>>(run_alpha, nruns, maxd, 1, acnt, nullptr, nullptr, nullptr);
     ctx->launches++;
     B2_CHECK_LAUNCH();
     exclusive_scan_i32_to_i64(ctx, acnt, adj_ptr, nruns);
@@ -819,10 +886,10 @@ void hbuild_csr(b2ci_ctx* ctx, const b2ci_dets* dets, int64_t row_begin, int64_t
     B2_CUDA(cudaMemcpyAsync(&nadj, adj_ptr.p + nruns, 8, cudaMemcpyDeviceToHost, st));
     B2_CUDA(cudaStreamSynchronize(st));
     adj.alloc(nadj > 0 ? nadj : 1);
-    k_string_adjacency<true><<<ga, 256, 0, st>>>(run_alpha, nruns, 4, 1, nullptr, nullptr, adj_ptr, adj);
+    k_string_adjacency<true><<<ga, 256, 0, st>>>(run_alpha, nruns, maxd, 1, nullptr, nullptr, adj_ptr, adj);
     ctx->launches++;
     B2_CHECK_LAUNCH();
-  }
+  };
 
   // ---- rectangular (FCI-shaped) lists: product enumeration, no beta scan
   int64_t nb = 0;
@@ -842,6 +909,7 @@ void hbuild_csr(b2ci_ctx* ctx, const b2ci_dets* dets, int64_t row_begin, int64_t
     }
   }
   ctx->timers["h_build.rectangular"] = rect ? 1. : 0.;
+  build_adjacency(rect ? 4 : 2);
   if (rect) {
     DevBuf<int64_t> b2_ptr(nb + 1), b4_ptr(nb + 1);
     DevBuf<uint32_t> b2, b4;
@@ -1048,6 +1116,32 @@ void hbuild_csr(b2ci_ctx* ctx, const b2ci_dets* dets, int64_t row_begin, int64_t
     return;
   }
 
+  // ---- general lists: determinants grouped by beta string (stable radix sort of the indices)
+  DevBuf<int32_t> bgrp_of(n);
+  DevBuf<int64_t> bgrp_start;
+  DevBuf<uint32_t> bgrp_mem(n), idx_alt(n);
+  {
+    ScopedTimer t(ctx, "h_build.setup", true);
+    DevBuf<uint64_t> key(n), key_alt(n);
+    B2_CUDA(cudaMemcpyAsync(key, dets->beta, size_t(n) * 8, cudaMemcpyDeviceToDevice, st));
+    iota_u32(ctx, bgrp_mem, n);
+    std::vector<int> shifts;
+    for (int d = 0; d < (ctx->norb + 7) / 8; ++d) shifts.push_back(8 * d);
+    radix_sort_pairs(ctx, key, key_alt, bgrp_mem, idx_alt, n, shifts);
+    DevBuf<int32_t> flag(n), excl(n + 1);
+    const unsigned gb = unsigned((n + 255) / 256);
+    k_run_flags<<<gb, 256, 0, st>>>(key, n, flag);
+    ctx->launches++;
+    B2_CHECK_LAUNCH();
+    exclusive_scan_i32(ctx, flag, excl, n);
+    int32_t ngroups = 0;
+    B2_CUDA(cudaMemcpyAsync(&ngroups, excl.p + n, 4, cudaMemcpyDeviceToHost, st));
+    B2_CUDA(cudaStreamSynchronize(st));
+    bgrp_start.alloc(size_t(ngroups) + 1);
+    k_group_scatter<<<gb, 256, 0, st>>>(key, bgrp_mem, n, flag, excl, bgrp_of, bgrp_start, ngroups);
+    ctx->launches++;
+    B2_CHECK_LAUNCH();
+  }
   RowArgs A;
   A.I = ctx->ints;
   A.alpha = dets->alpha;
@@ -1056,6 +1150,9 @@ void hbuild_csr(b2ci_ctx* ctx, const b2ci_dets* dets, int64_t row_begin, int64_t
   A.run_start = run_start;
   A.adj_ptr = adj_ptr;
   A.adj = adj;
+  A.bgrp_of = bgrp_of;
+  A.bgrp_start = bgrp_start;
+  A.bgrp_mem = bgrp_mem;
   A.row_begin = row_begin;
   A.nrows = nrows;
   A.thr = thr;

@@ -51,11 +51,12 @@ struct Runtime {
     if (ctx) b2ci_ctx_destroy(ctx);
     ctx = nullptr;
   }
-  ~Runtime() { drop(); }
 };
 Runtime& runtime() {
-  static Runtime r;
-  return r;
+  // never destroyed: at process exit the CUDA runtime may already be gone, and tearing a
+  // context down then can block
+  static Runtime* r = new Runtime;
+  return *r;
 }
 thread_local std::map<std::string, double> g_stats;
 
@@ -188,6 +189,11 @@ class CiSession {
     b2ci_csr* H = nullptr;
     B2(b2ci_hbuild_csr(ctx_, dets, rows.first, rows.second, matel_tol, &H));
     add_timer("h_build_ms", {"h_build.setup", "h_build.count", "h_build.fill", "h_build.thresh"});
+    add_timer("h_build_setup_ms", {"h_build.setup"});
+    add_timer("h_build_count_ms", {"h_build.count"});
+    add_timer("h_build_fill_ms", {"h_build.fill"});
+    g_stats["h_build_last_ms"] = b2ci_timer_ms(ctx_, "h_build.setup") + b2ci_timer_ms(ctx_, "h_build.count") +
+                                 b2ci_timer_ms(ctx_, "h_build.fill") + b2ci_timer_ms(ctx_, "h_build.thresh");
     int64_t nnz = 0;
     b2ci_csr_info(H, nullptr, nullptr, &nnz, nullptr);
     g_stats["nnz_local"] = double(nnz);
@@ -263,6 +269,10 @@ class CiSession {
       break;
     }
     add_timer("asci_search_ms", {"asci_search.PAIR_DUR", "asci_search.SORT_ACC_DUR", "asci_search.TOPK_DUR"});
+    add_timer("asci_pair_ms", {"asci_search.PAIR_DUR"});
+    add_timer("asci_sort_acc_ms", {"asci_search.SORT_ACC_DUR"});
+    add_timer("asci_topk_ms", {"asci_search.TOPK_DUR"});
+    g_stats["asci_last_ncore"] = double(ncore);
     g_stats["asci_search_calls"] += 1.0;
     out.resize(size_t(n_out));
     return out;
