@@ -6,8 +6,11 @@
 A *step* is one pass of the hot path over one synthetic workload: the Hamiltonian build of
 this rank's row block (b2ci_hbuild_csr) followed by one sigma = H c application
 (b2ci_sigma_sharded: NCCL all-gather of the trial vector + SpMV). The default workload is
-BASELINE.json configs[1] (2D extended Hubbard 4x3, 6a6b, 853,776 determinants); the other FCI
-configs are selectable with --workload.
+BASELINE.json configs[2] (Cr2-like CAS(12e,12o), dense synthetic integrals, 853,776 determinants,
+1.55e9 non-zeros = 18.6 GB of CSR: the largest full-CI configuration that fits one GPU and the
+one SURVEY.md section 8(d) sizes the sigma roofline on); configs[1] (2D extended Hubbard 4x3,
+same dimension, 1.7e7 non-zeros after thresholding) is measured in the same run and reported
+under "also". Other workloads are selectable with --workload.
 
 Metric (BASELINE.json: "H-build nnz/s and Davidson sigma-iter time (ms)"): `value` is the
 whole-job H-build throughput in nnz/s with the determinant list and integrals resident in
@@ -222,11 +225,151 @@ def run_reference(args):
 # ---------------------------------------------------------------------------------------
 # GPU arm
 # ---------------------------------------------------------------------------------------
+def load_traffic(kernel_key):
+    """DRAM traffic per launch (dram__bytes_read.sum + dram__bytes_write.sum) of the dominant
+    kernels, from the committed `ncu --set full` capture (profiles/r01_traffic.json)."""
+    p = os.path.join(ROOT, "profiles", "r01_traffic.json")
+    try:
+        with open(p) as fh:
+            return json.load(fh).get(kernel_key)
+    except OSError:
+        return None
+
+
+def measure(ctx, sp, name, args, world, rank, local_rank, dist, torch, steps, warmup, full):
+    """One workload: `warmup` untimed + `steps` timed passes of (H build of this rank's rows,
+    one sigma), CUDA events on the library's stream, max over ranks. `full` adds the e2e leg
+    (host buffers through the C ABI), Davidson to 1e-8 Eh and the clock samples."""
+    from qdk_chemistry_b200 import device
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def reduce(x, op):
+        if world == 1:
+            return float(x)
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=op)
+        return float(t.item())
+
+    mx = lambda x: reduce(x, dist.ReduceOp.MAX) if world > 1 else float(x)
+    sm = lambda x: reduce(x, dist.ReduceOp.SUM) if world > 1 else float(x)
+
+    n = sp.fci_dimension
+    offs = split_rows(n, world)
+    r0, r1 = offs[rank], offs[rank + 1]
+    hbm_peak, peak_src = measured_peaks()
+
+    ctx.upload_integrals(sp.norb, sp.T, sp.V)
+    dets = ctx.generate_fci(sp.norb, sp.nalpha, sp.nbeta)
+    x_local = torch.randn(r1 - r0, dtype=torch.float64, device="cuda")
+    x_full = torch.empty(n, dtype=torch.float64, device="cuda")
+    y_local = torch.empty(r1 - r0, dtype=torch.float64, device="cuda")
+    flush = torch.empty(192 * 1024 * 1024 // 4, dtype=torch.float32, device="cuda")  # > L2 (126 MB)
+
+    ev = lambda: torch.cuda.Event(enable_timing=True)
+    T = {k: [] for k in ("build", "fill", "count", "setup", "thresh", "sigma")}
+    H = None
+    sampler = ClockSampler(local_rank)
+    launches0 = wall0 = 0
+    for it in range(warmup + steps):
+        timed = it >= warmup
+        if it == warmup:
+            barrier()
+            launches0 = ctx.launch_count
+            if rank == 0 and full:
+                sampler.start()
+            wall0 = time.perf_counter()
+        if H is not None:
+            H.free()
+        flush.zero_()  # evict L2 between iterations (outside the timed events)
+        e0, e1, e2, e3 = ev(), ev(), ev(), ev()
+        e0.record()
+        H = ctx.hbuild(dets, EPS, (r0, r1))
+        e1.record()
+        flush.zero_()
+        e2.record()
+        H.sigma_sharded(x_local.data_ptr(), x_full.data_ptr(), y_local.data_ptr())
+        e3.record()
+        torch.cuda.synchronize()
+        if timed:
+            T["build"].append(e0.elapsed_time(e1))
+            T["sigma"].append(e2.elapsed_time(e3))
+            for k in ("count", "fill", "setup", "thresh"):
+                T[k].append(ctx.timer_ms("h_build." + k))
+    barrier()
+    wall1 = time.perf_counter()
+    clocks = sampler.stop() if (rank == 0 and full) else None
+    launches = ctx.launch_count - launches0
+    nnz_local = H.nnz
+    group = ctx.timer_ms("h_build.group_width")
+    slices = ctx.timer_ms("h_build.smem_slices")
+
+    res = {"workload": name}
+    # ---- e2e leg: same H build through the C ABI with HOST buffers (pinned determinant words,
+    # integrals), row pointer (= per-row nnz, the step's result) read back, per step
+    if full:
+        words_host = dets.download(1)
+        words_pinned = torch.from_numpy(words_host.view(np.int64)).pin_memory()
+        t_e2e = []
+        ne_w, ne_s = max(1, warmup // 2), max(2, steps)
+        for it in range(ne_w + ne_s):
+            H.free()
+            H = None
+            flush.zero_()
+            barrier()
+            t0 = time.perf_counter()
+            ctx.upload_integrals(sp.norb, sp.T, sp.V)
+            d2 = ctx.upload_dets(words_pinned.numpy().view(np.uint64), 1)
+            H = ctx.hbuild(d2, EPS, (r0, r1))
+            H.download_rowptr()
+            torch.cuda.synchronize()
+            t1 = time.perf_counter()
+            d2.free()
+            if it >= ne_w:
+                t_e2e.append((t1 - t0) * 1e3)
+        res["e2e_ms"] = mx(float(np.mean(t_e2e)))
+        res["h2d"] = int(sp.T.nbytes + sp.V.nbytes + words_host.nbytes)
+        res["d2h"] = int((r1 - r0 + 1) * 8)
+
+    nrows = r1 - r0
+    res.update(
+        n=n, nnz_total=sm(nnz_local), nnz_local=int(nnz_local),
+        build_ms=mx(float(np.mean(T["build"]))), sigma_ms=mx(float(np.mean(T["sigma"]))),
+        fill_ms=mx(float(np.mean(T["fill"]))), count_ms=mx(float(np.mean(T["count"]))),
+        setup_ms=mx(float(np.mean(T["setup"]))), thresh_ms=mx(float(np.mean(T["thresh"]))),
+        launches=int(launches), clocks=clocks, wall=wall1 - wall0, group=int(group), slices=bool(slices),
+        # algorithmic bytes per launch on THIS rank (DESIGN.md section 3)
+        B_sigma=int(nnz_local * 12 + (nrows + 1) * 8 + n * 8 + nrows * 8),
+        B_fill=int(n * 16 + nnz_local * 12 + (nrows + 1) * 8),
+        fill_ms_local=float(np.mean(T["fill"])), sigma_ms_local=float(np.mean(T["sigma"])),
+        hbm_peak=hbm_peak, peak_src=peak_src)
+
+    if full and args.davidson:
+        try:
+            E, X, niter, _ = H.davidson(args.max_m, 1e-8)
+            ncalls = max(1.0, ctx.timer_ms("davidson.OP_CALLS"))
+            other = sum(ctx.timer_ms("davidson." + k) for k in ("RR_DUR", "RES_DUR", "GS_DUR"))
+            res["davidson"] = {"niter": int(niter), "E0_electronic": E, "E0_total": E + sp.core_energy,
+                               "sigma_ms_mean": ctx.timer_ms("davidson.OP_DUR") / ncalls,
+                               "other_ms_per_iter": other / max(1, niter),
+                               "rr_ms_total": ctx.timer_ms("davidson.RR_DUR"),
+                               "res_ms_total": ctx.timer_ms("davidson.RES_DUR"),
+                               "gs_ms_total": ctx.timer_ms("davidson.GS_DUR")}
+        except device.B2ciError as e:
+            res["davidson"] = {"error": str(e)}
+    H.free()
+    dets.free()
+    del flush, x_full
+    return res
+
+
 def run_b200(args):
     import torch
     import torch.distributed as dist
     from qdk_chemistry_b200 import device
-    from oracle import port  # only for the cpu_baseline leg and the packed determinant order
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -245,132 +388,21 @@ def run_b200(args):
         dist.broadcast(idt, 0)
         ctx.comm_init(bytes(idt.cpu().numpy().tobytes()), rank, world)
 
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    def max_over_ranks(x):
-        if world == 1:
-            return float(x)
-        t = torch.tensor([x], dtype=torch.float64, device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return float(t.item())
-
-    def sum_over_ranks(x):
-        if world == 1:
-            return float(x)
-        t = torch.tensor([x], dtype=torch.float64, device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.SUM)
-        return float(t.item())
-
     sp = fci_workload(args.workload)
-    n = sp.fci_dimension
-    offs = split_rows(n, world)
-    r0, r1 = offs[rank], offs[rank + 1]
-    hbm_peak, peak_src = measured_peaks()
-
-    # resident inputs
-    ctx.upload_integrals(sp.norb, sp.T, sp.V)
-    dets = ctx.generate_fci(sp.norb, sp.nalpha, sp.nbeta)
-    words_host = dets.download(1)  # host copy for the e2e leg (pageable -> pinned below)
-    words_pinned = torch.from_numpy(words_host.view(np.int64)).pin_memory()
-    x_local = torch.randn(r1 - r0, dtype=torch.float64, device="cuda")
-    x_full = torch.empty(n, dtype=torch.float64, device="cuda")
-    y_local = torch.empty(r1 - r0, dtype=torch.float64, device="cuda")
-    flush = torch.empty(192 * 1024 * 1024 // 4, dtype=torch.float32, device="cuda")  # > L2 (126 MB)
-
-    ev = lambda: torch.cuda.Event(enable_timing=True)
-    t_build, t_fill, t_count, t_sigma, t_step, t_e2e = [], [], [], [], [], []
-    t_setup, t_thresh = [], []
-    launches0 = None
-    nnz_local = 0
-    H = None
-    sampler = ClockSampler(local_rank)
-    for it in range(args.warmup + args.steps):
-        timed = it >= args.warmup
-        if it == args.warmup:
-            barrier()
-            launches0 = ctx.launch_count
-            if rank == 0:
-                sampler.start()
-            wall0 = time.perf_counter()
-        if H is not None:
-            H.free()
-        flush.zero_()  # evict L2 between iterations (outside the timed events)
-        e0, e1, e2, e3 = ev(), ev(), ev(), ev()
-        e0.record()
-        H = ctx.hbuild(dets, EPS, (r0, r1))
-        e1.record()
-        flush.zero_()
-        e2.record()
-        H.sigma_sharded(x_local.data_ptr(), x_full.data_ptr(), y_local.data_ptr())
-        e3.record()
-        torch.cuda.synchronize()
-        if timed:
-            t_build.append(e0.elapsed_time(e1))
-            t_sigma.append(e2.elapsed_time(e3))
-            t_step.append(e0.elapsed_time(e1) + e2.elapsed_time(e3))
-            t_count.append(ctx.timer_ms("h_build.count"))
-            t_fill.append(ctx.timer_ms("h_build.fill"))
-            t_setup.append(ctx.timer_ms("h_build.setup"))
-            t_thresh.append(ctx.timer_ms("h_build.thresh"))
-        nnz_local = H.nnz
-    barrier()
-    wall1 = time.perf_counter()
-    clocks = sampler.stop() if rank == 0 else None
-    launches = ctx.launch_count - launches0
-
-    # e2e leg: same H build through the C ABI with HOST buffers (pinned), result read back
-    for it in range(max(1, args.warmup // 2) + max(1, args.steps // 2)):
-        timed = it >= max(1, args.warmup // 2)
-        H.free()
-        H = None
-        flush.zero_()
-        torch.cuda.synchronize()
-        t0 = time.perf_counter()
-        ctx.upload_integrals(sp.norb, sp.T, sp.V)
-        d2 = ctx.upload_dets(words_pinned.numpy().view(np.uint64), 1)
-        H = ctx.hbuild(d2, EPS, (r0, r1))
-        rp = H.download_rowptr()
-        torch.cuda.synchronize()
-        t1 = time.perf_counter()
-        d2.free()
-        if timed:
-            t_e2e.append((t1 - t0) * 1e3)
-    h2d = sp.T.nbytes + sp.V.nbytes + words_host.nbytes
-    d2h = (r1 - r0 + 1) * 8
-
-    nnz_total = sum_over_ranks(nnz_local)
-    build_ms = max_over_ranks(float(np.mean(t_build)))
-    fill_ms = max_over_ranks(float(np.mean(t_fill)))
-    count_ms = max_over_ranks(float(np.mean(t_count)))
-    sigma_ms = max_over_ranks(float(np.mean(t_sigma)))
-    step_ms = max_over_ranks(float(np.mean(t_step)))
-    e2e_ms = max_over_ranks(float(np.mean(t_e2e)))
-
-    # algorithmic bytes: per GPU launch
-    nrows = r1 - r0
-    B_sigma = nnz_local * 12 + (nrows + 1) * 8 + n * 8 + nrows * 8
-    B_fill = n * 16 + nnz_local * 12 + (nrows + 1) * 8
-    sig_gbs = B_sigma / (float(np.mean(t_sigma)) * 1e-3) / 1e9
-    fill_gbs = B_fill / (float(np.mean(t_fill)) * 1e-3) / 1e9
-
-    # ground-state energy of the workload (Davidson to 1e-8 Eh) -- outside the timed region
-    energy = None
-    dav = None
-    if args.davidson:
-        try:
-            E, X, niter, _ = H.davidson(args.max_m, 1e-8)
-            energy = E + sp.core_energy
-            ncalls = max(1.0, ctx.timer_ms("davidson.OP_CALLS"))
-            dav = {"niter": int(niter), "E0_electronic": E, "E0_total": energy,
-                   "sigma_ms_mean": ctx.timer_ms("davidson.OP_DUR") / ncalls,
-                   "rr_ms_total": ctx.timer_ms("davidson.RR_DUR"),
-                   "res_ms_total": ctx.timer_ms("davidson.RES_DUR"),
-                   "gs_ms_total": ctx.timer_ms("davidson.GS_DUR")}
-        except device.B2ciError as e:
-            dav = {"error": str(e)}
+    m = measure(ctx, sp, args.workload, args, world, rank, local_rank, dist, torch, args.steps, args.warmup, True)
+    also = None
+    if args.also and args.workload != "hubbard_4x3":
+        sp2 = fci_workload("hubbard_4x3")
+        a = measure(ctx, sp2, "hubbard_4x3", args, world, rank, local_rank, dist, torch, max(3, args.steps),
+                    args.warmup, True)
+        also = {"hubbard_4x3": {
+            "config": "BASELINE configs[1], 853,776 dets; structurally connected entries are evaluated "
+                      "and |h| <= eps ones dropped (nnz is the surviving count)",
+            "hbuild_nnz_per_s": a["nnz_total"] / (a["build_ms"] * 1e-3), "nnz": int(a["nnz_total"]),
+            "hbuild_ms": a["build_ms"], "hbuild_fill_ms": a["fill_ms"], "sigma_iter_ms": a["sigma_ms"],
+            "sigma_frac_of_hbm": a["B_sigma"] / (a["sigma_ms_local"] * 1e-3) / 1e9 / a["hbm_peak"],
+            "e2e_nnz_per_s": a["nnz_total"] / (a["e2e_ms"] * 1e-3), "e2e_ms": a["e2e_ms"],
+            "davidson": a.get("davidson")}}
 
     cpu = None
     if rank == 0 and world == 1 and args.cpu_seconds > 0:
@@ -380,30 +412,41 @@ def run_b200(args):
             cpu = {"error": repr(e)}
 
     if rank == 0:
+        fill_gbs = m["B_fill"] / (m["fill_ms_local"] * 1e-3) / 1e9
+        sig_gbs = m["B_sigma"] / (m["sigma_ms_local"] * 1e-3) / 1e9
+        rect = "k_rows_product<EVAL,G=%d,SLICES=%d> (H-build fill: evaluates and writes the CSR)" % (
+            m["group"], int(m["slices"]))
         line = {
-            "metric": "hbuild_nnz_per_s", "value": nnz_total / (build_ms * 1e-3), "unit": "nnz/s",
-            "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": step_ms,
+            "metric": "hbuild_nnz_per_s", "value": m["nnz_total"] / (m["build_ms"] * 1e-3), "unit": "nnz/s",
+            "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": m["build_ms"] + m["sigma_ms"],
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
             "data": "synthetic",
             "config": {"workload": args.workload, "norb": sp.norb, "nalpha": sp.nalpha,
-                       "nbeta": sp.nbeta, "ndets": n, "nnz": int(nnz_total), "h_thresh": EPS,
+                       "nbeta": sp.nbeta, "ndets": m["n"], "nnz": int(m["nnz_total"]), "h_thresh": EPS,
                        "row_sharding": f"{world} contiguous row blocks",
                        "l2": "192 MiB buffer rewritten between timed kernels"},
-            "hbuild_ms": build_ms, "hbuild_count_ms": count_ms, "hbuild_fill_ms": fill_ms,
-            "hbuild_setup_ms": float(np.mean(t_setup)), "hbuild_thresh_ms": float(np.mean(t_thresh)),
-            "sigma_iter_ms": sigma_ms, "sigma_nnz_per_s": nnz_total / (sigma_ms * 1e-3),
-            "roofline": {"kernel": "k_rows<FILL> (H-build fill pass)", "bound": "hbm",
-                         "achieved": fill_gbs, "peak": hbm_peak, "unit": "GB/s",
-                         "frac": fill_gbs / hbm_peak, "traffic": None, "peak_source": peak_src,
-                         "note": "integer/latency bound (XOR/popcount scan); bytes = dets + CSR written"},
-            "roofline_sigma": {"kernel": "k_spmv", "bound": "hbm", "achieved": sig_gbs,
-                               "peak": hbm_peak, "unit": "GB/s", "frac": sig_gbs / hbm_peak,
-                               "traffic": None, "bytes_per_launch": int(B_sigma)},
-            "e2e": {"value": nnz_total / (e2e_ms * 1e-3), "unit": "nnz/s", "ms": e2e_ms,
-                    "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h)},
-            "gpu_launches": int(launches), "clocks": clocks, "davidson": dav,
-            "energy_total": energy, "wall_s_timed_region": wall1 - wall0,
+            "hbuild_ms": m["build_ms"], "hbuild_setup_ms": m["setup_ms"], "hbuild_count_ms": m["count_ms"],
+            "hbuild_fill_ms": m["fill_ms"], "hbuild_thresh_ms": m["thresh_ms"],
+            "sigma_iter_ms": m["sigma_ms"], "sigma_nnz_per_s": m["nnz_total"] / (m["sigma_ms"] * 1e-3),
+            "roofline": {"kernel": rect, "bound": "hbm", "achieved": fill_gbs, "peak": m["hbm_peak"],
+                         "unit": "GB/s", "frac": fill_gbs / m["hbm_peak"],
+                         "traffic": load_traffic("k_rows_product") if args.workload == "cr2_cas12" else None,
+                         "bytes_per_launch": m["B_fill"], "peak_source": m["peak_src"],
+                         "note": "algorithmic bytes = determinants read + CSR (12 B/nnz) + rowptr written by "
+                                 "rank 0's launch; duration = CUDA events around the launch on the library stream"},
+            "roofline_sigma": {"kernel": "k_spmv", "bound": "hbm", "achieved": sig_gbs, "peak": m["hbm_peak"],
+                               "unit": "GB/s", "frac": sig_gbs / m["hbm_peak"],
+                               "traffic": load_traffic("k_spmv") if args.workload == "cr2_cas12" else None,
+                               "bytes_per_launch": m["B_sigma"]},
+            "e2e": {"value": m["nnz_total"] / (m["e2e_ms"] * 1e-3), "unit": "nnz/s", "ms": m["e2e_ms"],
+                    "h2d_bytes_per_step": m["h2d"], "d2h_bytes_per_step": m["d2h"]},
+            "gpu_launches": m["launches"], "clocks": m["clocks"], "davidson": m.get("davidson"),
+            "energy_total": (m.get("davidson") or {}).get("E0_total"),
+            "wall_s_timed_region": m["wall"],
         }
+        if also is not None:
+            line["also"] = also
         if cpu is not None:
             if "error" in cpu:
                 line["cpu_baseline"] = cpu
@@ -414,8 +457,6 @@ def run_b200(args):
                                         "sigma_ms_full_est": cpu.get("sigma_ms_full_est"),
                                         "sigma_nnz_per_s": cpu.get("sigma_nnz_per_s")}
         print(json.dumps(line))
-    if H is not None:
-        H.free()
     ctx.close()
     if world > 1:
         dist.destroy_process_group()
@@ -427,10 +468,12 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--workload", default="hubbard_4x3",
+    ap.add_argument("--workload", default="cr2_cas12",
                     choices=["hubbard_4x3", "cr2_cas12", "n2_cas10", "small_cas8", "hubbard_4x2"])
     ap.add_argument("--max-m", type=int, default=100, dest="max_m")
     ap.add_argument("--no-davidson", action="store_false", dest="davidson")
+    ap.add_argument("--no-also", action="store_false", dest="also",
+                    help="skip the secondary hubbard_4x3 measurement")
     ap.add_argument("--cpu-seconds", type=float, default=12.0, dest="cpu_seconds",
                     help="CPU work budget of the cpu_baseline sample (0 disables)")
     args = ap.parse_args()

@@ -5,8 +5,8 @@
 mkdir -p gpurun_out
 (timeout 900 python -m pytest tests -m gpu -x -q 2>&1 | tail -25) > gpurun_out/pytest_gpu.log
 tail -4 gpurun_out/pytest_gpu.log
-timeout 300 python bench.py --steps 3 --warmup 3 --cpu-seconds ${CPU_SECONDS:-0} > gpurun_out/bench_hubbard.json 2> gpurun_out/bench_hubbard.err
-timeout 300 python bench.py --workload cr2_cas12 --steps 3 --warmup 3 --cpu-seconds ${CPU_SECONDS:-0} > gpurun_out/bench_cr2.json 2> gpurun_out/bench_cr2.err
+timeout 300 python bench.py --workload hubbard_4x3 --steps 3 --warmup 3 --cpu-seconds ${CPU_SECONDS:-0} > gpurun_out/bench_hubbard.json 2> gpurun_out/bench_hubbard.err
+timeout 300 python bench.py --workload cr2_cas12 --no-also --steps 3 --warmup 3 --cpu-seconds ${CPU_SECONDS:-0} > gpurun_out/bench_cr2.json 2> gpurun_out/bench_cr2.err
 cat gpurun_out/bench_hubbard.json gpurun_out/bench_cr2.json | python -c "
 import sys, json
 for l in sys.stdin:
@@ -17,6 +17,6 @@ for l in sys.stdin:
 tail -n 3 gpurun_out/bench_hubbard.err gpurun_out/bench_cr2.err
 if [ -n "$1" ]; then
   timeout 600 ncu --set full --clock-control none --import-source on -k "regex:$1" -s ${NCU_SKIP:-6} -c ${NCU_COUNT:-2} -o gpurun_out/prof_cr2 -f \
-    python bench.py --workload cr2_cas12 --steps 1 --warmup 3 --no-davidson --cpu-seconds 0 > gpurun_out/ncu_full.log 2>&1
+    python bench.py --workload cr2_cas12 --no-also --steps 1 --warmup 3 --no-davidson --cpu-seconds 0 > gpurun_out/ncu_full.log 2>&1
   tail -n 2 gpurun_out/ncu_full.log | cut -c1-200
 fi
