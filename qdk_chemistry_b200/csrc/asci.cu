@@ -60,6 +60,7 @@ struct GenArgs {
   double E0, tol;
   int just_singles;
   int packed;              // 1: key = beta << 32 | alpha (norb <= 32); 0: key = alpha, key2 = beta
+  uint32_t nparts, part;   // key partition handled by this launch (nparts == 1: everything)
   int32_t* count;          // count pass
   const int64_t* base;     // fill pass
   uint64_t* key;
@@ -68,6 +69,16 @@ struct GenArgs {
   double* hd;
 };
 
+// partition of the excited space by a hash of the determinant key: every contribution to one
+// determinant lands in the same part, in parent order, so per-part sort + accumulate gives the
+// same sums as one global pass (the device analogue of the reference's alpha-string constraints,
+// asci/mask_constraints.hpp: each Q determinant belongs to exactly one constraint)
+__host__ __device__ __forceinline__ uint32_t key_part(uint64_t key, uint32_t nparts) {
+  uint64_t x = key * 0x9E3779B97F4A7C15ull;
+  x ^= x >> 29;
+  x *= 0xBF58476D1CE4E5B9ull;
+  return uint32_t((x >> 33) % nparts);
+}
 __device__ __forceinline__ void pair_from_index(int p, int m, int& ii, int& jj) {
   // p-th pair (ii < jj) of m items in the order of the reference's nested loops
   int i = 0, rem = p;
@@ -210,6 +221,7 @@ k_generate(const GenArgs A) {
       hdv = 1.0;
       emit = true;
     }
+    if (emit && A.nparts > 1) emit = key_part((eb << 32) | ea, A.nparts) == A.part;
     if (emit) {
       if (FILL) {
         const int64_t pos = base + atomicAdd(&s_cnt, 1);
@@ -309,6 +321,10 @@ __global__ void k_max_below(const double* __restrict__ score, int64_t n, double 
   atomicMax(out, best);
 }
 
+__global__ void k_fill_u64(uint64_t* p, int64_t n, uint64_t v) {
+  const int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i < n) p[i] = v;
+}
 unsigned grid1d(int64_t n, int threads = 256) { return unsigned((n + threads - 1) / threads); }
 
 }  // namespace
@@ -347,164 +363,285 @@ int asci_search(b2ci_ctx* ctx, const b2ci_asci_search_opts* o, const uint64_t* c
   // Two-word keys (32 < norb <= 64, wfn_t<128>) need a second sort phase that is not part of
   // this build; the H build and Davidson paths have no such limit.
   if (n > 32) throw Error("b2ci_asci_search: norb > 32 (wfn_t<128> keys) is not supported by this build");
-  const bool packed = true;
-  int64_t M = 0;
-  DevBuf<uint64_t> key, key2;
-  DevBuf<double> cm, hd;
+
+  GenArgs A;
+  A.I = ctx->ints;
+  A.ca = core.alpha; A.cb = core.beta; A.coeff = dcoeff;
+  A.eps_a = eps_a; A.eps_b = eps_b; A.root = root;
+  A.E0 = E0; A.tol = o->h_el_tol; A.just_singles = o->just_singles;
+  A.packed = 1;
+  DevBuf<int32_t> count(nc);
+  DevBuf<int64_t> base(nc + 1);
+
+  // ---- how many key partitions: the unfiltered contribution count against the memory budget
+  int64_t M_total = 0;
   {
-    ScopedTimer t(ctx, "asci_search.PAIR_DUR");
+    ScopedTimer t(ctx, "asci_search.PAIR_DUR", true);
     k_core_pre<<<grid1d(nc * n), 256, 0, st>>>(ctx->ints, core.alpha, core.beta, nc, eps_a, eps_b, root);
-    ctx->launches++;
-    B2_CHECK_LAUNCH();
-    GenArgs A;
-    A.I = ctx->ints;
-    A.ca = core.alpha; A.cb = core.beta; A.coeff = dcoeff;
-    A.eps_a = eps_a; A.eps_b = eps_b; A.root = root;
-    A.E0 = E0; A.tol = o->h_el_tol; A.just_singles = o->just_singles;
-    A.packed = packed ? 1 : 0;
-    DevBuf<int32_t> count(nc);
-    DevBuf<int64_t> base(nc + 1);
+    A.nparts = 1; A.part = 0;
     A.count = count; A.base = nullptr; A.key = nullptr; A.key2 = nullptr; A.cm = nullptr; A.hd = nullptr;
     k_generate<false><<<unsigned(nc), GEN_THREADS, 0, st>>>(A);
-    ctx->launches++;
+    ctx->launches += 2;
     B2_CHECK_LAUNCH();
     exclusive_scan_i32_to_i64(ctx, count, base, nc);
-    B2_CUDA(cudaMemcpyAsync(&M, base.p + nc, 8, cudaMemcpyDeviceToHost, st));
-    B2_CUDA(cudaStreamSynchronize(st));
-    if (M >= (int64_t(1) << 32)) throw Error("b2ci_asci_search: more than 2^32 contributions in one batch");
-    size_t free_b = 0, total_b = 0;
-    B2_CUDA(cudaMemGetInfo(&free_b, &total_b));
-    const size_t need = size_t(M) * (packed ? 56 : 80);
-    if (need > free_b)
-      throw Error("b2ci_asci_search: " + std::to_string(M) + " contributions need " +
-                  std::to_string(need >> 20) + " MiB of device memory, " + std::to_string(free_b >> 20) + " MiB free");
-    key.alloc(M);
-    if (!packed) key2.alloc(M);
-    cm.alloc(M);
-    hd.alloc(M);
-    A.count = nullptr; A.base = base; A.key = key; A.key2 = packed ? nullptr : key2.p; A.cm = cm; A.hd = hd;
-    k_generate<true><<<unsigned(nc), GEN_THREADS, 0, st>>>(A);
-    ctx->launches++;
-    B2_CHECK_LAUNCH();
+    B2_CUDA(cudaMemcpyAsync(&M_total, base.p + nc, 8, cudaMemcpyDeviceToHost, st));
     B2_CUDA(cudaStreamSynchronize(st));
   }
+  size_t free_b = 0, total_b = 0;
+  B2_CUDA(cudaMemGetInfo(&free_b, &total_b));
+  const int64_t bytes_per = 64;  // key, c*h, h_diag, sort double buffers, flags, segment ids
+  int64_t budget = std::min<int64_t>(int64_t(double(free_b) * 0.5) / bytes_per, (int64_t(1) << 31) - 1);
+  if (const char* env = getenv("B2CI_ASCI_BUDGET")) budget = std::max<int64_t>(1024, atoll(env));
+  // hash partitions are even to a few percent; 1.25 covers the imbalance
+  int64_t nparts = std::max<int64_t>(1, (int64_t(double(M_total) * 1.25) + budget - 1) / budget);
+  if (M_total <= budget) nparts = 1;
+  if (const char* env = getenv("B2CI_ASCI_PARTS")) nparts = std::max<int64_t>(1, atoll(env));
+  const int nranks = ctx->nranks, rank = ctx->rank;
+  if (nranks > 1) nparts = ((std::max<int64_t>(nparts, nranks) + nranks - 1) / nranks) * nranks;
+  if (candidates_only && (nparts > 1 || nranks > 1))
+    throw Error("b2ci_asci_candidates: the candidate table is only available for single-part searches");
+  T["asci_search.nparts"] = double(nparts);
 
-  // ---- sort + accumulate
-  int64_t nseg = 0;
-  DevBuf<uint64_t> sk1, sk2;
-  DevBuf<double> scm, shd;
-  {
-    ScopedTimer t(ctx, "asci_search.SORT_ACC_DUR");
-    DevBuf<uint64_t> kalt(M);
-    DevBuf<uint32_t> idx(M), idx_alt(M);
-    iota_u32(ctx, idx, M);
-    const int ndig = (n + 7) / 8;
-    std::vector<int> shifts;
-    if (packed) {
-      for (int d = 0; d < ndig; ++d) shifts.push_back(8 * d);        // alpha bits
-      for (int d = 0; d < ndig; ++d) shifts.push_back(32 + 8 * d);   // beta bits (high half)
-      radix_sort_pairs(ctx, key, kalt, idx, idx_alt, M, shifts);
+  // candidates of this rank that survive pruning: (key, |rv|), appended part by part
+  DevBuf<uint64_t> cand_key;
+  DevBuf<double> cand_score;
+  int64_t ncand = 0, cand_cap = 0;
+  int64_t M_sum = 0, nseg_sum = 0;
+  auto append_candidates = [&](const uint64_t* k, const double* sc, int64_t m) {
+    if (ncand + m > cand_cap) {
+      const int64_t ncap = std::max<int64_t>(ncand + m, cand_cap * 2);
+      DevBuf<uint64_t> nk(ncap);
+      DevBuf<double> ns(ncap);
+      if (ncand) {
+        B2_CUDA(cudaMemcpyAsync(nk, cand_key, size_t(ncand) * 8, cudaMemcpyDeviceToDevice, st));
+        B2_CUDA(cudaMemcpyAsync(ns, cand_score, size_t(ncand) * 8, cudaMemcpyDeviceToDevice, st));
+      }
+      cand_key = std::move(nk);
+      cand_score = std::move(ns);
+      cand_cap = ncap;
     }
-    DevBuf<int32_t> flag(M);
-    DevBuf<int64_t> seg_of(M + 1);
-    k_seg_flags<<<grid1d(M), 256, 0, st>>>(key, nullptr, M, flag);
-    ctx->launches++;
-    B2_CHECK_LAUNCH();
-    exclusive_scan_i32_to_i64(ctx, flag, seg_of, M);
-    B2_CUDA(cudaMemcpyAsync(&nseg, seg_of.p + M, 8, cudaMemcpyDeviceToHost, st));
-    B2_CUDA(cudaStreamSynchronize(st));
-    sk1.alloc(nseg);
-    scm.alloc(nseg);
-    shd.alloc(nseg);
-    // seg_of[i] (exclusive scan) is the segment id of a head at i
-    k_seg_accumulate<<<grid1d(M), 256, 0, st>>>(key, nullptr, idx, flag, seg_of, M, cm, hd, sk1, nullptr, scm, shd);
-    ctx->launches++;
-    B2_CHECK_LAUNCH();
-    B2_CUDA(cudaStreamSynchronize(st));
-  }
-  key.release(); cm.release(); hd.release();
-
-  auto unpack_keys_to_words = [&](const uint64_t* dk1, int64_t cnt, uint64_t* host_words) {
-    // packed key == wfn_t<64> word; for words_per_det == 2 split into (alpha, beta)
-    std::vector<uint64_t> tmp(cnt);
-    B2_CUDA(cudaMemcpyAsync(tmp.data(), dk1, size_t(cnt) * 8, cudaMemcpyDeviceToHost, st));
-    B2_CUDA(cudaStreamSynchronize(st));
-    if (wpd == 1) memcpy(host_words, tmp.data(), size_t(cnt) * 8);
-    else
-      for (int64_t i = 0; i < cnt; ++i) { host_words[2 * i] = tmp[i] & 0xFFFFFFFFull; host_words[2 * i + 1] = tmp[i] >> 32; }
+    if (m) {
+      B2_CUDA(cudaMemcpyAsync(cand_key.p + ncand, k, size_t(m) * 8, cudaMemcpyDeviceToDevice, st));
+      B2_CUDA(cudaMemcpyAsync(cand_score.p + ncand, sc, size_t(m) * 8, cudaMemcpyDeviceToDevice, st));
+    }
+    ncand += m;
   };
 
-  if (candidates_only) {
-    if (cand_n) *cand_n = nseg;
-    if (cand_words) {
-      unpack_keys_to_words(sk1, nseg, cand_words);
-      B2_CUDA(cudaMemcpyAsync(cand_cm, scm, size_t(nseg) * 8, cudaMemcpyDeviceToHost, st));
-      B2_CUDA(cudaMemcpyAsync(cand_hd, shd, size_t(nseg) * 8, cudaMemcpyDeviceToHost, st));
+  for (int64_t part = rank; part < nparts; part += nranks) {
+    int64_t M = 0;
+    DevBuf<uint64_t> key;
+    DevBuf<double> cm, hd;
+    {
+      ScopedTimer t(ctx, "asci_search.PAIR_DUR", true);
+      A.nparts = uint32_t(nparts); A.part = uint32_t(part);
+      if (nparts > 1) {
+        A.count = count; A.base = nullptr; A.key = nullptr; A.cm = nullptr; A.hd = nullptr;
+        k_generate<false><<<unsigned(nc), GEN_THREADS, 0, st>>>(A);
+        ctx->launches++;
+        B2_CHECK_LAUNCH();
+        exclusive_scan_i32_to_i64(ctx, count, base, nc);
+      }
+      B2_CUDA(cudaMemcpyAsync(&M, base.p + nc, 8, cudaMemcpyDeviceToHost, st));
       B2_CUDA(cudaStreamSynchronize(st));
-    }
-    return 0;
-  }
-
-  // ---- prune, top-k, output
-  int64_t m = 0, nkeep = 0;
-  double kth = 0., below = 0.;
-  DevBuf<uint64_t> sel;
-  {
-    ScopedTimer t(ctx, "asci_search.TOPK_DUR");
-    DevBuf<int32_t> keep(nseg);
-    DevBuf<double> score(nseg);
-    DevBuf<int64_t> pos(nseg + 1);
-    k_score<<<grid1d(nseg), 256, 0, st>>>(scm, shd, nseg, o->rv_prune_tol, keep, score);
-    ctx->launches++;
-    B2_CHECK_LAUNCH();
-    exclusive_scan_i32_to_i64(ctx, keep, pos, nseg);
-    B2_CUDA(cudaMemcpyAsync(&m, pos.p + nseg, 8, cudaMemcpyDeviceToHost, st));
-    B2_CUDA(cudaStreamSynchronize(st));
-    DevBuf<uint64_t> ck(m > 0 ? m : 1);
-    DevBuf<double> cs(m > 0 ? m : 1);
-    if (m) {
-      k_compact<<<grid1d(nseg), 256, 0, st>>>(keep, pos, nseg, sk1, nullptr, score, ck, nullptr, cs);
+      if (M >= (int64_t(1) << 32)) throw Error("b2ci_asci_search: more than 2^32 contributions in one part");
+      B2_CUDA(cudaMemGetInfo(&free_b, &total_b));
+      const size_t need = size_t(M) * 56;
+      if (need > free_b)
+        throw Error("b2ci_asci_search: " + std::to_string(M) + " contributions need " +
+                    std::to_string(need >> 20) + " MiB of device memory, " + std::to_string(free_b >> 20) + " MiB free");
+      key.alloc(M > 0 ? M : 1);
+      cm.alloc(M > 0 ? M : 1);
+      hd.alloc(M > 0 ? M : 1);
+      A.count = nullptr; A.base = base; A.key = key; A.key2 = nullptr; A.cm = cm; A.hd = hd;
+      k_generate<true><<<unsigned(nc), GEN_THREADS, 0, st>>>(A);
       ctx->launches++;
       B2_CHECK_LAUNCH();
     }
-    const int64_t top_k = o->ndets_max - nc;
-    nkeep = m;
-    if (o->ndets_max >= nc && m > top_k) {
-      // top_k == 0: the reference's max_element over an empty range lands on element 0 after
-      // nth_element, i.e. the largest score (determinant_search.hpp:1056-1062)
-      kth = select_kth_largest(ctx, cs, m, top_k > 0 ? top_k : 1);
-      DevBuf<int32_t> keep2(m);
-      DevBuf<int64_t> pos2(m + 1);
-      k_keep_ge<<<grid1d(m), 256, 0, st>>>(cs, m, kth, keep2);
+    M_sum += M;
+    if (M == 0) continue;
+
+    // ---- sort + accumulate
+    int64_t nseg = 0;
+    DevBuf<uint64_t> sk1;
+    DevBuf<double> scm, shd;
+    {
+      ScopedTimer t(ctx, "asci_search.SORT_ACC_DUR", true);
+      DevBuf<uint64_t> kalt(M);
+      DevBuf<uint32_t> idx(M), idx_alt(M);
+      iota_u32(ctx, idx, M);
+      const int ndig = (n + 7) / 8;
+      std::vector<int> shifts;
+      for (int d = 0; d < ndig; ++d) shifts.push_back(8 * d);        // alpha bits
+      for (int d = 0; d < ndig; ++d) shifts.push_back(32 + 8 * d);   // beta bits (high half)
+      radix_sort_pairs(ctx, key, kalt, idx, idx_alt, M, shifts);
+      DevBuf<int32_t> flag(M);
+      DevBuf<int64_t> seg_of(M + 1);
+      k_seg_flags<<<grid1d(M), 256, 0, st>>>(key, nullptr, M, flag);
       ctx->launches++;
-      exclusive_scan_i32_to_i64(ctx, keep2, pos2, m);
-      B2_CUDA(cudaMemcpyAsync(&nkeep, pos2.p + m, 8, cudaMemcpyDeviceToHost, st));
-      DevBuf<unsigned long long> mb(1);
-      B2_CUDA(cudaMemsetAsync(mb, 0, 8, st));
-      k_max_below<<<(unsigned)std::max<int64_t>(1, std::min<int64_t>(ctx->sm_count * 4, (m + 255) / 256)), 256, 0, st>>>(cs, m, kth, mb);
-      ctx->launches++;
-      unsigned long long mbh = 0;
-      B2_CUDA(cudaMemcpyAsync(&mbh, mb, 8, cudaMemcpyDeviceToHost, st));
+      B2_CHECK_LAUNCH();
+      exclusive_scan_i32_to_i64(ctx, flag, seg_of, M);
+      B2_CUDA(cudaMemcpyAsync(&nseg, seg_of.p + M, 8, cudaMemcpyDeviceToHost, st));
       B2_CUDA(cudaStreamSynchronize(st));
-      memcpy(&below, &mbh, 8);
-      sel.alloc(nkeep > 0 ? nkeep : 1);
-      if (nkeep) {
-        k_compact<<<grid1d(m), 256, 0, st>>>(keep2, pos2, m, ck, nullptr, nullptr, sel, nullptr, nullptr);
+      sk1.alloc(nseg);
+      scm.alloc(nseg);
+      shd.alloc(nseg);
+      // seg_of[i] (exclusive scan) is the segment id of a head at i
+      k_seg_accumulate<<<grid1d(M), 256, 0, st>>>(key, nullptr, idx, flag, seg_of, M, cm, hd, sk1, nullptr, scm, shd);
+      ctx->launches++;
+      B2_CHECK_LAUNCH();
+    }
+    key.release(); cm.release(); hd.release();
+    nseg_sum += nseg;
+
+    if (candidates_only) {
+      if (cand_n) *cand_n = nseg;
+      if (cand_words) {
+        std::vector<uint64_t> tmp(nseg);
+        B2_CUDA(cudaMemcpyAsync(tmp.data(), sk1, size_t(nseg) * 8, cudaMemcpyDeviceToHost, st));
+        B2_CUDA(cudaMemcpyAsync(cand_cm, scm, size_t(nseg) * 8, cudaMemcpyDeviceToHost, st));
+        B2_CUDA(cudaMemcpyAsync(cand_hd, shd, size_t(nseg) * 8, cudaMemcpyDeviceToHost, st));
+        B2_CUDA(cudaStreamSynchronize(st));
+        if (wpd == 1) memcpy(cand_words, tmp.data(), size_t(nseg) * 8);
+        else
+          for (int64_t i = 0; i < nseg; ++i) { cand_words[2 * i] = tmp[i] & 0xFFFFFFFFull; cand_words[2 * i + 1] = tmp[i] >> 32; }
+      }
+      return 0;
+    }
+
+    // ---- prune: finite rv (core determinants carry inf) and |rv| > rv_prune_tol
+    {
+      ScopedTimer t(ctx, "asci_search.TOPK_DUR", true);
+      DevBuf<int32_t> keep(nseg);
+      DevBuf<double> score(nseg);
+      DevBuf<int64_t> pos(nseg + 1);
+      int64_t m = 0;
+      k_score<<<grid1d(nseg), 256, 0, st>>>(scm, shd, nseg, o->rv_prune_tol, keep, score);
+      ctx->launches++;
+      B2_CHECK_LAUNCH();
+      exclusive_scan_i32_to_i64(ctx, keep, pos, nseg);
+      B2_CUDA(cudaMemcpyAsync(&m, pos.p + nseg, 8, cudaMemcpyDeviceToHost, st));
+      B2_CUDA(cudaStreamSynchronize(st));
+      if (m) {
+        DevBuf<uint64_t> ck(m);
+        DevBuf<double> cs(m);
+        k_compact<<<grid1d(nseg), 256, 0, st>>>(keep, pos, nseg, sk1, nullptr, score, ck, nullptr, cs);
         ctx->launches++;
         B2_CHECK_LAUNCH();
+        if (nparts == 1 && nranks == 1) {
+          cand_key = std::move(ck);
+          cand_score = std::move(cs);
+          ncand = cand_cap = m;
+        } else {
+          append_candidates(ck, cs, m);
+          B2_CUDA(cudaStreamSynchronize(st));
+        }
       }
+    }
+  }
+
+  // ---- top-k over the surviving candidates (determinant_search.hpp:966-1114)
+  const int64_t top_k = o->ndets_max - nc;
+  // keep every candidate with score >= the k-th largest of `cs` (ties retained); returns count
+  auto keep_top = [&](DevBuf<uint64_t>& ck, DevBuf<double>& cs, int64_t m, int64_t k, double& kth, double& below,
+                      bool want_scores) -> int64_t {
+    kth = select_kth_largest(ctx, cs, m, k);
+    DevBuf<int32_t> keep2(m);
+    DevBuf<int64_t> pos2(m + 1);
+    int64_t nk = 0;
+    k_keep_ge<<<grid1d(m), 256, 0, st>>>(cs, m, kth, keep2);
+    ctx->launches++;
+    exclusive_scan_i32_to_i64(ctx, keep2, pos2, m);
+    B2_CUDA(cudaMemcpyAsync(&nk, pos2.p + m, 8, cudaMemcpyDeviceToHost, st));
+    DevBuf<unsigned long long> mb(1);
+    B2_CUDA(cudaMemsetAsync(mb, 0, 8, st));
+    k_max_below<<<(unsigned)std::max<int64_t>(1, std::min<int64_t>(ctx->sm_count * 4, (m + 255) / 256)), 256, 0, st>>>(cs, m, kth, mb);
+    ctx->launches++;
+    unsigned long long mbh = 0;
+    B2_CUDA(cudaMemcpyAsync(&mbh, mb, 8, cudaMemcpyDeviceToHost, st));
+    B2_CUDA(cudaStreamSynchronize(st));
+    memcpy(&below, &mbh, 8);
+    DevBuf<uint64_t> sk(nk > 0 ? nk : 1);
+    DevBuf<double> ss(want_scores && nk > 0 ? nk : 1);
+    if (nk) {
+      k_compact<<<grid1d(m), 256, 0, st>>>(keep2, pos2, m, ck, nullptr, want_scores ? cs.p : nullptr, sk, nullptr,
+                                          want_scores ? ss.p : nullptr);
+      ctx->launches++;
+      B2_CHECK_LAUNCH();
+    }
+    B2_CUDA(cudaStreamSynchronize(st));
+    ck = std::move(sk);
+    if (want_scores) cs = std::move(ss);
+    return nk;
+  };
+
+  int64_t nkeep = ncand;
+  double kth = 0., below = 0.;
+  {
+    ScopedTimer t(ctx, "asci_search.TOPK_DUR", true);
+    const int64_t k_eff = top_k > 0 ? top_k : 1;  // top_k == 0: max_element over an empty range
+                                                   // lands on the largest score (:1056-1062)
+    if (nranks == 1) {
+      if (o->ndets_max >= nc && ncand > top_k) nkeep = keep_top(cand_key, cand_score, ncand, k_eff, kth, below, false);
     } else {
-      sel = std::move(ck);
+      // local top-k (with ties), all-gather of fixed-size slabs, final select on every rank:
+      // the counterpart of the distributed quickselect + Allgatherv (:1000-1053)
+      if (o->ndets_max >= nc && ncand > top_k) nkeep = keep_top(cand_key, cand_score, ncand, k_eff, kth, below, true);
+      std::vector<int64_t> counts;
+      comm_allgather_i64_host(ctx, nkeep, counts);
+      int64_t slab = 0, total = 0;
+      for (int64_t c : counts) { slab = std::max(slab, c); total += c; }
+      if (total > 0) {
+        DevBuf<uint64_t> sk(slab), gk(size_t(slab) * nranks);
+        DevBuf<double> ss(slab), gs(size_t(slab) * nranks);
+        // padding: score 0 (never selected ahead of a real candidate, dropped below)
+        k_fill_u64<<<grid1d(slab), 256, 0, st>>>(sk, slab, ~uint64_t(0));
+        B2_CUDA(cudaMemsetAsync(ss, 0, size_t(slab) * 8, st));
+        if (nkeep) {
+          B2_CUDA(cudaMemcpyAsync(sk, cand_key, size_t(nkeep) * 8, cudaMemcpyDeviceToDevice, st));
+          B2_CUDA(cudaMemcpyAsync(ss, cand_score, size_t(nkeep) * 8, cudaMemcpyDeviceToDevice, st));
+        }
+        comm_allgather_bytes(ctx, sk, gk, size_t(slab) * 8);
+        comm_allgather_bytes(ctx, ss, gs, size_t(slab) * 8);
+        const int64_t mg = slab * nranks;
+        if (o->ndets_max >= nc && total > top_k) {
+          nkeep = keep_top(gk, gs, mg, k_eff, kth, below, false);
+        } else {
+          // everything survives: drop the padding (score 0 < any pruned-in score)
+          DevBuf<int32_t> keep2(mg);
+          DevBuf<int64_t> pos2(mg + 1);
+          k_keep_ge<<<grid1d(mg), 256, 0, st>>>(gs, mg, 1e-300, keep2);
+          exclusive_scan_i32_to_i64(ctx, keep2, pos2, mg);
+          B2_CUDA(cudaMemcpyAsync(&nkeep, pos2.p + mg, 8, cudaMemcpyDeviceToHost, st));
+          B2_CUDA(cudaStreamSynchronize(st));
+          DevBuf<uint64_t> sel2(nkeep > 0 ? nkeep : 1);
+          if (nkeep) k_compact<<<grid1d(mg), 256, 0, st>>>(keep2, pos2, mg, gk, nullptr, nullptr, sel2, nullptr, nullptr);
+          ctx->launches += 2;
+          B2_CHECK_LAUNCH();
+          B2_CUDA(cudaStreamSynchronize(st));
+          gk = std::move(sel2);
+        }
+        cand_key = std::move(gk);
+      } else {
+        nkeep = 0;
+      }
     }
     B2_CUDA(cudaStreamSynchronize(st));
   }
   if (stats) {
-    stats[0] = double(M); stats[1] = double(nseg); stats[2] = kth; stats[3] = below; stats[4] = double(nkeep);
+    stats[0] = double(M_sum); stats[1] = double(nseg_sum); stats[2] = kth; stats[3] = below; stats[4] = double(nkeep);
+    stats[5] = double(nparts);
   }
   const int64_t total = nkeep + nc;
   if (n_out) *n_out = total;
   if (total > cap) throw Error("b2ci_asci_search: output capacity " + std::to_string(cap) + " < " + std::to_string(total), 4);
-  if (nkeep) unpack_keys_to_words(sel, nkeep, out_words);
+  if (nkeep) {
+    std::vector<uint64_t> tmp(nkeep);
+    B2_CUDA(cudaMemcpyAsync(tmp.data(), cand_key, size_t(nkeep) * 8, cudaMemcpyDeviceToHost, st));
+    B2_CUDA(cudaStreamSynchronize(st));
+    if (wpd == 1) memcpy(out_words, tmp.data(), size_t(nkeep) * 8);
+    else
+      for (int64_t i = 0; i < nkeep; ++i) { out_words[2 * i] = tmp[i] & 0xFFFFFFFFull; out_words[2 * i + 1] = tmp[i] >> 32; }
+  }
   memcpy(out_words + size_t(nkeep) * wpd, core_words, size_t(nc) * wpd * 8);
   return 0;
 }

@@ -132,6 +132,14 @@ void comm_allgather_i64_host(b2ci_ctx* ctx, int64_t local, std::vector<int64_t>&
   B2_CUDA(cudaStreamSynchronize(ctx->stream));
 }
 
+void comm_allgather_bytes(b2ci_ctx* ctx, const void* send, void* recv, size_t bytes_per_rank) {
+  if (ctx->nranks == 1) {
+    if (send != recv) B2_CUDA(cudaMemcpyAsync(recv, send, bytes_per_rank, cudaMemcpyDeviceToDevice, ctx->stream));
+    return;
+  }
+  B2_NCCL(api().AllGather(send, recv, bytes_per_rank, ncclChar, (ncclComm_t)ctx->nccl_comm, ctx->stream));
+}
+
 void comm_allreduce_sum_i64_host(b2ci_ctx* ctx, int64_t* vals, int n) {
   if (ctx->nranks == 1 || n == 0) return;
   DevBuf<int64_t> d(n);

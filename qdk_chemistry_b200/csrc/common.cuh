@@ -210,5 +210,6 @@ void comm_allgather_rows(b2ci_ctx* ctx, const double* local, double* full,
 void comm_allreduce_sum(b2ci_ctx* ctx, double* dev_buf, int64_t n);
 void comm_allreduce_sum_i64_host(b2ci_ctx* ctx, int64_t* host_vals, int n);
 void comm_allgather_i64_host(b2ci_ctx* ctx, int64_t local, std::vector<int64_t>& all);
+void comm_allgather_bytes(b2ci_ctx* ctx, const void* send, void* recv, size_t bytes_per_rank);
 
 }  // namespace b2ci

@@ -88,3 +88,28 @@ def test_unsorted_core_is_rejected(ctx):
     with pytest.raises(device.B2ciError) as e:
         ctx.asci_search(port.pack(ca[::-1], cb[::-1]), c, -2.0, 100)
     assert "Sorted" in str(e.value)
+
+
+@pytest.mark.parametrize("parts", [2, 3, 7])
+def test_key_partitioned_search_is_identical(ctx, water, golden_meta, golden_arrays, parts, monkeypatch):
+    """Large searches are split into key partitions (hash of the determinant word); every
+    determinant's contributions stay together and in parent order, so selection, pivot and
+    counts are those of the single-pass search."""
+    m = golden_meta["water_search"]
+    ca, cb = golden_arrays["water_search.core_alpha"], golden_arrays["water_search.core_beta"]
+    cc = golden_arrays["water_search.core_C"]
+    ctx.upload_integrals(water.norb, water.T, water.V)
+    out1, st1 = ctx.asci_search(port.pack(ca, cb), cc, m["E0"], m["ndets_max"])
+    assert st1[5] == 1
+    monkeypatch.setenv("B2CI_ASCI_PARTS", str(parts))
+    outp, stp = ctx.asci_search(port.pack(ca, cb), cc, m["E0"], m["ndets_max"])
+    assert stp[5] == parts
+    assert np.array_equal(np.sort(outp), np.sort(out1))
+    assert np.array_equal(np.sort(outp), golden_arrays["water_search.selected"])
+    assert np.array_equal(stp[:5], st1[:5])        # contributions, unique candidates, pivot, gap, kept
+    assert np.array_equal(outp[-len(ca):], port.pack(ca, cb))
+    # a tiny memory budget picks the partition count by itself
+    monkeypatch.delenv("B2CI_ASCI_PARTS")
+    monkeypatch.setenv("B2CI_ASCI_BUDGET", str(int(st1[0] // 5)))
+    outb, stb = ctx.asci_search(port.pack(ca, cb), cc, m["E0"], m["ndets_max"])
+    assert stb[5] >= 6 and np.array_equal(np.sort(outb), np.sort(out1))
