@@ -155,6 +155,9 @@ double b2ci_host_matrix_element(int norb, const double* T, const double* V, uint
  * eigenvalues ascending, eigenvectors in the columns of A); stands where the reference calls
  * lapack::syev (external/macis/src/lobpcgxx/include/lobpcgxx/rayleigh_ritz.hpp:75) */
 int b2ci_host_sym_eig_lower(int n, double* A, int lda, double* W);
+/* lowest eigenpair only (what the single-root Davidson uses every iteration): Householder
+ * tridiagonalisation + Sturm bisection + inverse iteration; A is read (lower triangle) */
+int b2ci_host_sym_eig_lowest(int n, const double* A, int lda, double* lambda, double* vec);
 
 #ifdef __cplusplus
 }

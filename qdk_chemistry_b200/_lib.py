@@ -79,6 +79,7 @@ def lib():
     L.b2ci_host_matrix_element.restype = dbl
     L.b2ci_host_matrix_element.argtypes = [i32, vp, vp, u64, u64, u64, u64]
     L.b2ci_host_sym_eig_lower.argtypes = [i32, vp, i32, vp]
+    L.b2ci_host_sym_eig_lowest.argtypes = [i32, vp, i32, C.POINTER(dbl), vp]
     _lib = L
     return L
 

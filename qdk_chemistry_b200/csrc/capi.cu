@@ -400,6 +400,14 @@ double b2ci_host_matrix_element(int norb, const double* T, const double* V, uint
   return matel(I, bra_alpha, bra_beta, ket_alpha, ket_beta);
 }
 
+int b2ci_host_sym_eig_lowest(int n, const double* A, int lda, double* lambda, double* vec) {
+  B2_TRY
+  if (n < 1 || !A || !lambda || !vec || lda < n) throw Error("b2ci_host_sym_eig_lowest: bad arguments");
+  sym_eig_lowest(n, A, lda, lambda, vec);
+  return 0;
+  B2_CATCH
+}
+
 int b2ci_host_sym_eig_lower(int n, double* A, int lda, double* W) {
   B2_TRY
   sym_eig_lower(n, A, lda, W);

@@ -194,6 +194,42 @@ struct ScopedTimer {  // CUDA-event timing of a phase on the context stream
   }
 };
 
+// Phase timing without synchronising inside the phase loop: event pairs are recorded on the
+// context stream and resolved once, after the caller's final synchronisation.
+struct DeferredTimers {
+  b2ci_ctx* ctx;
+  struct Rec { std::string name; cudaEvent_t a, b; };
+  std::vector<Rec> recs;
+  explicit DeferredTimers(b2ci_ctx* c) : ctx(c) {}
+  size_t start(const char* name) {
+    Rec r;
+    r.name = name;
+    cudaEventCreate(&r.a);
+    cudaEventCreate(&r.b);
+    cudaEventRecord(r.a, ctx->stream);
+    recs.push_back(r);
+    return recs.size() - 1;
+  }
+  void stop(size_t id) { cudaEventRecord(recs[id].b, ctx->stream); }
+  void resolve() {  // after a stream synchronisation
+    for (auto& r : recs) {
+      float ms = 0.f;
+      if (cudaEventSynchronize(r.b) == cudaSuccess && cudaEventElapsedTime(&ms, r.a, r.b) == cudaSuccess)
+        ctx->timers[r.name] += ms;
+      cudaEventDestroy(r.a);
+      cudaEventDestroy(r.b);
+    }
+    recs.clear();
+  }
+  ~DeferredTimers() { resolve(); }
+};
+struct DeferredScope {
+  DeferredTimers& t;
+  size_t id;
+  DeferredScope(DeferredTimers& tt, const char* name) : t(tt), id(tt.start(name)) {}
+  ~DeferredScope() { t.stop(id); }
+};
+
 // scan.cu : out has n + 1 entries, out[n] = total
 void exclusive_scan_i32_to_i64(b2ci_ctx* ctx, const int32_t* in, int64_t* out, int64_t n);
 void exclusive_scan_i32(b2ci_ctx* ctx, const int32_t* in, int32_t* out, int64_t n);
@@ -203,6 +239,7 @@ void spmv_launch(b2ci_ctx* ctx, const b2ci_csr* m, const double* x, double* y);
 
 // eig.cpp-ish (davidson.cu): symmetric eigensolver, lower triangle, ascending
 void sym_eig_lower(int n, double* A, int lda, double* W);
+void sym_eig_lowest(int n, const double* A, int lda, double* lambda, double* vec);
 
 // comm.cu
 void comm_allgather_rows(b2ci_ctx* ctx, const double* local, double* full,

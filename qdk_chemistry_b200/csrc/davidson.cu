@@ -159,6 +159,148 @@ void sym_eig_lower(int n, double* A, int lda, double* W) {
   }
 }
 
+// Lowest eigenpair only -- what single-root Davidson needs from the Rayleigh-Ritz step. Householder
+// reduction to tridiagonal form keeping the reflectors (no accumulation of Q), Sturm bisection for
+// the lowest eigenvalue, inverse iteration on the tridiagonal matrix, back-transformation of that
+// one vector: ~(4/3) n^3 flops instead of the ~10 n^3 of the full decomposition, which at
+// n = max_m = 200 would otherwise cost more than a sigma application of a 10^6-determinant matrix.
+void sym_eig_lowest(int n, const double* A, int lda, double* lambda, double* vec) {
+  if (n <= 0) return;
+  if (n == 1) { *lambda = A[0]; vec[0] = 1.0; return; }
+  std::vector<double> a(size_t(n) * n), d(n), e(n, 0.0), tau(n, 0.0), p(n), w(n);
+  auto M = [&](int i, int j) -> double& { return a[size_t(j) * n + i]; };  // column-major, lower used
+  for (int j = 0; j < n; ++j)
+    for (int i = j; i < n; ++i) M(i, j) = A[i + size_t(j) * lda];
+  for (int i = 0; i < n - 1; ++i) {
+    const int m = n - i - 1;  // reflector acts on rows i+1 .. n-1
+    double* x = &M(i + 1, i);
+    const double alpha = x[0];
+    double xnorm = 0.0;
+    for (int k = 1; k < m; ++k) xnorm = std::hypot(xnorm, x[k]);
+    d[i] = M(i, i);
+    if (xnorm == 0.0) {
+      tau[i] = 0.0;
+      e[i] = alpha;
+      x[0] = 1.0;
+      continue;
+    }
+    const double beta = -std::copysign(std::hypot(alpha, xnorm), alpha);
+    tau[i] = (beta - alpha) / beta;
+    const double sc = 1.0 / (alpha - beta);
+    for (int k = 1; k < m; ++k) x[k] *= sc;
+    x[0] = 1.0;
+    e[i] = beta;
+    // p = tau * A22 v (A22 symmetric, lower part stored), columnwise for unit stride
+    for (int r = 0; r < m; ++r) p[r] = 0.0;
+    for (int c = 0; c < m; ++c) {
+      const double* col = &M(i + 1, i + 1 + c);  // entries (i+1.., i+1+c); rows >= c valid
+      const double vc = x[c];
+      double acc = col[c] * vc;
+      for (int r = c + 1; r < m; ++r) {
+        p[r] += col[r] * vc;
+        acc += col[r] * x[r];
+      }
+      p[c] += acc;
+    }
+    double pv = 0.0;
+    for (int r = 0; r < m; ++r) { p[r] *= tau[i]; pv += p[r] * x[r]; }
+    const double K = -0.5 * tau[i] * pv;
+    for (int r = 0; r < m; ++r) w[r] = p[r] + K * x[r];
+    for (int c = 0; c < m; ++c) {
+      double* col = &M(i + 1, i + 1 + c);
+      const double vc = x[c], wc = w[c];
+      for (int r = c; r < m; ++r) col[r] -= x[r] * wc + w[r] * vc;
+    }
+  }
+  d[n - 1] = M(n - 1, n - 1);
+  // ---- lowest eigenvalue of tridiag(d, e) by bisection on the Sturm count
+  double lo = d[0], hi = d[0], tnorm = 0.0;
+  for (int i = 0; i < n; ++i) {
+    const double r = (i > 0 ? std::fabs(e[i - 1]) : 0.0) + (i < n - 1 ? std::fabs(e[i]) : 0.0);
+    lo = std::min(lo, d[i] - r);
+    hi = std::max(hi, d[i] + r);
+    tnorm = std::max(tnorm, std::fabs(d[i]) + r);
+  }
+  const double eps = std::ldexp(1.0, -52);
+  const double tiny = std::max(tnorm, 1.0) * eps * eps;
+  auto count_below = [&](double x) {  // number of eigenvalues < x
+    int c = 0;
+    double q = d[0] - x;
+    if (q < 0) ++c;
+    for (int i = 1; i < n; ++i) {
+      if (std::fabs(q) < tiny) q = q < 0 ? -tiny : tiny;
+      q = d[i] - x - e[i - 1] * e[i - 1] / q;
+      if (q < 0) ++c;
+    }
+    return c;
+  };
+  double a0 = lo, b0 = hi;
+  for (int it = 0; it < 200; ++it) {
+    const double mid = 0.5 * (a0 + b0);
+    if (mid <= a0 || mid >= b0) break;
+    if (count_below(mid) >= 1) b0 = mid; else a0 = mid;
+  }
+  const double lam = 0.5 * (a0 + b0);
+  // ---- inverse iteration: (T - lam I) y = y_prev, tridiagonal LU with partial pivoting
+  std::vector<double> dl(n), dd(n), du(n), du2(n), y(n);
+  std::vector<int> piv(n);
+  for (int i = 0; i < n; ++i) { dd[i] = d[i] - lam; dl[i] = i < n - 1 ? e[i] : 0.0; du[i] = i < n - 1 ? e[i] : 0.0; du2[i] = 0.0; }
+  const double pert = std::max(tnorm, 1.0) * eps;
+  for (int i = 0; i < n - 1; ++i) {
+    if (std::fabs(dd[i]) >= std::fabs(dl[i])) {
+      piv[i] = 0;
+      if (std::fabs(dd[i]) < pert) dd[i] = dd[i] < 0 ? -pert : pert;
+      const double f = dl[i] / dd[i];
+      dl[i] = f;
+      dd[i + 1] -= f * du[i];
+    } else {
+      piv[i] = 1;  // swap rows i and i+1
+      const double f = dd[i] / dl[i];
+      dd[i] = dl[i];
+      dl[i] = f;
+      const double t = du[i];
+      du[i] = dd[i + 1];
+      dd[i + 1] = t - f * dd[i + 1];
+      if (i < n - 2) { du2[i] = du[i + 1]; du[i + 1] = -f * du[i + 1]; }
+    }
+  }
+  if (std::fabs(dd[n - 1]) < pert) dd[n - 1] = dd[n - 1] < 0 ? -pert : pert;
+  for (int i = 0; i < n; ++i) y[i] = 1.0 / std::sqrt(double(n)) * (1.0 + 0.01 * ((i * 7919) % 13));
+  for (int iter = 0; iter < 4; ++iter) {
+    for (int i = 0; i < n - 1; ++i) {  // forward: L^-1 P y
+      if (piv[i]) std::swap(y[i], y[i + 1]);
+      y[i + 1] -= dl[i] * y[i];
+    }
+    y[n - 1] /= dd[n - 1];  // backward: U^-1
+    if (n > 1) y[n - 2] = (y[n - 2] - du[n - 2] * y[n - 1]) / dd[n - 2];
+    for (int i = n - 3; i >= 0; --i) y[i] = (y[i] - du[i] * y[i + 1] - du2[i] * y[i + 2]) / dd[i];
+    double nrm = 0.0;
+    for (int i = 0; i < n; ++i) nrm = std::hypot(nrm, y[i]);
+    for (int i = 0; i < n; ++i) y[i] /= nrm;
+  }
+  // ---- back-transformation x = H_0 H_1 ... H_{n-2} y
+  for (int i = n - 2; i >= 0; --i) {
+    if (tau[i] == 0.0) continue;
+    const int m = n - i - 1;
+    const double* v = &M(i + 1, i);
+    double s = 0.0;
+    for (int k = 0; k < m; ++k) s += v[k] * y[i + 1 + k];
+    s *= tau[i];
+    for (int k = 0; k < m; ++k) y[i + 1 + k] -= s * v[k];
+  }
+  double nrm = 0.0;
+  for (int i = 0; i < n; ++i) nrm = std::hypot(nrm, y[i]);
+  for (int i = 0; i < n; ++i) vec[i] = y[i] / nrm;
+  // Rayleigh quotient of the back-transformed vector: second-order accurate in the vector error
+  double num = 0.0;
+  for (int j = 0; j < n; ++j) {
+    double t = 0.0;
+    for (int i = 0; i < n; ++i) t += (i >= j ? A[i + size_t(j) * lda] : A[j + size_t(i) * lda]) * vec[i];
+    num += t * vec[j];
+  }
+  *lambda = num;
+}
+
 namespace {
 
 constexpr int DOT_THREADS = 256;
@@ -171,7 +313,8 @@ k_multi_dot(int64_t N, int k, const double* __restrict__ A, int64_t ld,
   __shared__ double red[DOT_CG][DOT_THREADS / 32];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int64_t stride = int64_t(gridDim.x) * DOT_THREADS;
-  for (int j0 = 0; j0 < k; j0 += DOT_CG) {
+  // column groups are spread over blockIdx.y so that all of them stream concurrently
+  for (int j0 = blockIdx.y * DOT_CG; j0 < k; j0 += gridDim.y * DOT_CG) {
     double acc[DOT_CG];
 #pragma unroll
     for (int c = 0; c < DOT_CG; ++c) acc[c] = 0.;
@@ -280,14 +423,16 @@ __global__ void k_diag(int64_t nrows, int64_t row_begin, const int64_t* __restri
 struct Work {
   b2ci_ctx* ctx;
   int64_t N, ld;
-  int nblocks;
+  int nblocks;   // CTAs of the reductions (one partial per CTA)
+  int nstream;   // CTAs of the streaming updates
   DevBuf<double> partial, small;  // small: k-sized device scratch
   std::vector<double> host_small;
 };
 
 void dots(Work& W, int k, const double* A, const double* w, double* host_out) {
   b2ci_ctx* ctx = W.ctx;
-  k_multi_dot<<<W.nblocks, DOT_THREADS, 0, ctx->stream>>>(W.N, k, A, W.ld, w, W.partial);
+  const dim3 grid(W.nblocks, unsigned(std::min(8, (k + DOT_CG - 1) / DOT_CG)));
+  k_multi_dot<<<grid, DOT_THREADS, 0, ctx->stream>>>(W.N, k, A, W.ld, w, W.partial);
   ctx->launches++;
   k_reduce_partials<<<(k + 127) / 128, 128, 0, ctx->stream>>>(W.nblocks, k, W.partial, W.small);
   ctx->launches++;
@@ -306,12 +451,12 @@ double norm2(Work& W, const double* w) {
 void project(Work& W, int k, const double* V, double* w) {
   b2ci_ctx* ctx = W.ctx;
   dots(W, k, V, w, nullptr);  // h stays on the device (W.small)
-  k_project_out<<<W.nblocks, 256, size_t(k) * 8, ctx->stream>>>(W.N, k, V, W.ld, W.small, w);
+  k_project_out<<<W.nstream, 256, size_t(k) * 8, ctx->stream>>>(W.N, k, V, W.ld, W.small, w);
   ctx->launches++;
   B2_CHECK_LAUNCH();
 }
 void scale(Work& W, double a, double* w) {
-  k_scale<<<W.nblocks, 256, 0, W.ctx->stream>>>(W.N, a, w);
+  k_scale<<<W.nstream, 256, 0, W.ctx->stream>>>(W.N, a, w);
   W.ctx->launches++;
   B2_CHECK_LAUNCH();
 }
@@ -423,7 +568,8 @@ int davidson(b2ci_ctx* ctx, const b2ci_csr* m, int64_t max_m, double tol, double
   W.N = Nloc;
   W.ld = Nloc > 0 ? Nloc : 1;
   W.nblocks = (int)std::max<int64_t>(1, std::min<int64_t>(int64_t(ctx->sm_count) * 2, (Nloc + 255) / 256));
-  W.partial.alloc(size_t(W.nblocks) * (max_m + 2));
+  W.nstream = (int)std::max<int64_t>(1, std::min<int64_t>(int64_t(ctx->sm_count) * 16, (Nloc + 255) / 256));
+  W.partial.alloc(std::max(size_t(W.nblocks) * (max_m + 2), size_t(W.nstream)));
   W.small.alloc(max_m + 2);
   const int64_t ld = W.ld;
 
@@ -438,8 +584,9 @@ int davidson(b2ci_ctx* ctx, const b2ci_csr* m, int64_t max_m, double tol, double
   DevBuf<double> cdev(max_m + 2);
   std::vector<double> C(size_t(max_m + 1) * (max_m + 1), 0.), Cw, LAM(max_m + 1, 0.), crow(max_m + 2);
 
+  DeferredTimers timers(ctx);
   auto sigma = [&](const double* v_local, double* av_local) {
-    ScopedTimer t(ctx, "davidson.OP_DUR", true);
+    DeferredScope t(timers, "davidson.OP_DUR");
     const double* xin = v_local;
     if (ctx->nranks > 1) {
       comm_allgather_rows(ctx, v_local, xfull, row_offsets);
@@ -465,25 +612,26 @@ int davidson(b2ci_ctx* ctx, const b2ci_csr* m, int64_t max_m, double tol, double
     const int k = int(i + 1);
     sigma(V + i * ld, AV + i * ld);
     {
-      ScopedTimer t(ctx, "davidson.RR_DUR", true);
+      DeferredScope t(timers, "davidson.RR_DUR");
       // new row of the lower triangle: C(i, j) = V_i^T (A V_j), j = 0..i
       dots(W, k, AV, V + i * ld, crow.data());
       for (int j = 0; j < k; ++j) C[i + size_t(j) * (max_m + 1)] = crow[j];
-      Cw.assign(size_t(k) * k, 0.);
+      Cw.assign(size_t(k) * k + k, 0.);
       for (int b = 0; b < k; ++b)
         for (int a = b; a < k; ++a) Cw[a + size_t(b) * k] = C[a + size_t(b) * (max_m + 1)];
-      sym_eig_lower(k, Cw.data(), k, LAM.data());
+      sym_eig_lowest(k, Cw.data(), k, &LAM[0], Cw.data() + size_t(k) * k);
+      std::copy(Cw.begin() + size_t(k) * k, Cw.begin() + size_t(k) * k + k, Cw.begin());
       lam = LAM[0];
       B2_CUDA(cudaMemcpyAsync(cdev, Cw.data(), size_t(k) * 8, cudaMemcpyHostToDevice, st));
     }
     double res_nrm;
     {
-      ScopedTimer t(ctx, "davidson.RES_DUR", true);
+      DeferredScope t(timers, "davidson.RES_DUR");
       double* R = V + (i + 1) * ld;
-      k_residual<<<W.nblocks, 256, size_t(k) * 8, st>>>(Nloc, k, V, AV, ld, cdev, lam, D,
+      k_residual<<<W.nstream, 256, size_t(k) * 8, st>>>(Nloc, k, V, AV, ld, cdev, lam, D,
                                                         xfull + row0, R, W.partial);
       ctx->launches++;
-      k_reduce_partials<<<1, 128, 0, st>>>(W.nblocks, 1, W.partial, W.small);
+      k_reduce_partials<<<1, 128, 0, st>>>(W.nstream, 1, W.partial, W.small);
       ctx->launches++;
       B2_CHECK_LAUNCH();
       if (ctx->nranks > 1) comm_allreduce_sum(ctx, W.small, 1);
@@ -495,7 +643,7 @@ int davidson(b2ci_ctx* ctx, const b2ci_csr* m, int64_t max_m, double tol, double
     if (trace) { trace[2 * (i - 1)] = lam; trace[2 * (i - 1) + 1] = res_nrm; }
     if (res_nrm < tol) { converged = true; break; }
     {
-      ScopedTimer t(ctx, "davidson.GS_DUR", true);
+      DeferredScope t(timers, "davidson.GS_DUR");
       gram_schmidt(W, k, V, V + (i + 1) * ld, row0, N);
     }
   }
@@ -507,6 +655,7 @@ int davidson(b2ci_ctx* ctx, const b2ci_csr* m, int64_t max_m, double tol, double
   }
   B2_CUDA(cudaMemcpyAsync(X_host, xfull, size_t(N) * 8, cudaMemcpyDeviceToHost, st));
   B2_CUDA(cudaStreamSynchronize(st));
+  timers.resolve();
   *niter_out = iter;
   *eig_out = lam;
   if (!converged) {

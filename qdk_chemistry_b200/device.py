@@ -296,3 +296,12 @@ def host_sym_eig_lower(A: np.ndarray):
     W = np.empty(n)
     check(lib().b2ci_host_sym_eig_lower(n, _p(M), n, _p(W)))
     return W, M
+
+
+def host_sym_eig_lowest(A: np.ndarray):
+    n = A.shape[0]
+    M = np.array(A, dtype=np.float64, order="F", copy=True)
+    lam = C.c_double(0.0)
+    v = np.empty(n)
+    check(lib().b2ci_host_sym_eig_lowest(n, _p(M), n, C.byref(lam), _p(v)))
+    return lam.value, v

@@ -366,8 +366,16 @@ void reorder_ci_on_alpha(std::vector<Det>& wfn, std::vector<double>& X, size_t n
   std::copy(x2.begin(), x2.end(), X.begin());
 }
 
+struct WallTimer {  // host wall clock of one phase, accumulated into the run statistics
+  const char* key;
+  std::chrono::steady_clock::time_point t0 = std::chrono::steady_clock::now();
+  explicit WallTimer(const char* k) : key(k) {}
+  ~WallTimer() { g_stats[key] += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count(); }
+};
+
 double asci_iter(CiSession& S, const AsciSettings& a, const McscfSettings& m, int64_t ndets_max, double E0,
                  std::vector<Det>& wfn, std::vector<double>& X) {  // iteration.hpp:50-226
+  std::unique_ptr<WallTimer> wt(new WallTimer("wall_core_selection_ms"));
   if (wfn.size() > 1) reorder_ci_on_coeff(wfn, X);
   size_t nkeep = 0;
   if (a.fixed_core) {
@@ -386,7 +394,9 @@ double asci_iter(CiSession& S, const AsciSettings& a, const McscfSettings& m, in
     old.reserve(wfn.size());
     for (size_t i = 0; i < wfn.size(); ++i) old.emplace(wfn[i], X[i]);
   }
+  wt.reset(new WallTimer("wall_search_ms"));
   wfn = S.asci_search(wfn.data(), X.data(), int64_t(nkeep), E0, ndets_max, a);
+  wt.reset(new WallTimer("wall_sort_warmstart_ms"));
   std::sort(wfn.begin(), wfn.end(), spin_less);
   std::vector<double> X_local;
   if (a.warm_start_davidson && !old.empty()) {
@@ -405,7 +415,9 @@ double asci_iter(CiSession& S, const AsciSettings& a, const McscfSettings& m, in
       for (double& x : X_local) x *= inv;
     }
   }
+  wt.reset(new WallTimer("wall_selected_ci_diag_ms"));
   const double E = S.selected_ci_diag(wfn, m.ci_matel_tol, m.ci_max_subspace, m.ci_res_tol, X_local);
+  wt.reset();
   X = std::move(X_local);
   g_stats["asci_iterations"] += 1.0;
   return E;

@@ -81,3 +81,24 @@ def test_host_sym_eig_degenerate_and_graded():
     B = np.diag([1e-12, 1.0, 1e6]) + 1e-3
     Wv, Q = device.host_sym_eig_lower(B)
     assert np.allclose(Wv, np.linalg.eigvalsh(B), rtol=1e-10)
+
+
+def test_host_lowest_eigenpair_solver():
+    """Rayleigh-Ritz helper (host side, no GPU needed): lowest eigenpair of the projected matrix."""
+    import numpy as np
+    from qdk_chemistry_b200 import device
+    rng = np.random.default_rng(7)
+    for k in (1, 2, 3, 7, 33, 64, 150):
+        for kind in range(3):
+            A = rng.normal(size=(k, k))
+            A = A + A.T
+            if kind == 1:    # Davidson-shaped: dominant diagonal, weak coupling
+                A = np.diag(np.arange(k) * 0.3 - 5.0) + 0.05 * A
+            elif kind == 2:  # (nearly) diagonal, including exactly zero off-diagonals for small k
+                A = np.diag(np.sort(rng.normal(size=k))) + (1e-9 * A if k > 3 else 0.0)
+            lam, v = device.host_sym_eig_lowest(A)
+            w = np.linalg.eigvalsh(A)
+            scale = max(1.0, np.abs(w).max())
+            assert abs(lam - w[0]) <= 1e-13 * scale
+            assert np.linalg.norm(A @ v - lam * v) <= 1e-12 * scale
+            assert abs(np.linalg.norm(v) - 1.0) < 1e-14
