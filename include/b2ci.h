@@ -146,6 +146,16 @@ int b2ci_asci_candidates(b2ci_ctx* ctx, const b2ci_asci_search_opts* opts,
                          uint64_t* out_words, double* out_cmatel, double* out_hdiag,
                          int64_t* n_out);
 
+/* ---- ASCI-PT2: macis::asci_pt2_constraint (external/macis/include/macis/asci/pt2.hpp:61-565).
+ * Second-order energy of the determinants outside the (spin-sorted) wavefunction: every single
+ * and double excitation with |c*h| >= pt2_tol is generated, contributions to the same
+ * determinant are summed, and EPT2 = sum (sum c*h)^2 / (E_asci - <Q|H|Q>). The reference's
+ * alpha-constraint partition is replaced by hash partitions of the determinant key; with a
+ * communicator the partitions are dealt to the ranks and the partial sums all-reduced.
+ * npt2 (may be NULL): number of external determinants that contributed. */
+int b2ci_asci_pt2(b2ci_ctx* ctx, const uint64_t* det_words, int words_per_det, const double* coeffs,
+                  int64_t ndets, double E_asci, double pt2_tol, double* ept2, int64_t* npt2);
+
 /* ---- host-side evaluation of the SAME device functions (they are __host__ __device__):
  * lets CPU-only tests check the Slater-Condon code against the oracle without a GPU. */
 double b2ci_host_matrix_element(int norb, const double* T, const double* V, uint64_t bra_alpha,

@@ -161,6 +161,17 @@ class Ham:
                                  _p(oa), _p(ob), _p(cm), _p(hd))
         return oa, ob, cm, hd
 
+    def asci_pt2(self, alpha, beta, coeff, E_asci, pt2_tol=1e-16):
+        """asci_pt2_constraint (asci/pt2.hpp:61-565) without the constraint partition (which only
+        distributes the work: every external determinant belongs to exactly one constraint, so
+        the per-determinant sums are the same): contributions with |c*h| >= pt2_tol summed per
+        determinant (accumulate_asci_pairs), wavefunction members dropped (inf sentinel,
+        :310-311,399-404), EPT2 = sum rv * c_times_matel (determinant_contributions.hpp:49-55).
+        Returns (EPT2, NPT2)."""
+        _, _, cm, hd = self.asci_candidates(alpha, beta, coeff, E_asci, h_el_tol=pt2_tol)
+        fin = np.isfinite(cm)
+        return float(np.sum((cm[fin] / hd[fin]) * cm[fin])), int(np.count_nonzero(fin))
+
     def asci_search(self, calpha, cbeta, coeff, E0, ndets_max, h_el_tol=1e-8,
                     rv_prune_tol=1e-8, just_singles=False):
         """Returns (alpha, beta, stats): selected determinants followed by the core ones."""

@@ -321,6 +321,28 @@ __global__ void k_max_below(const double* __restrict__ score, int64_t n, double 
   atomicMax(out, best);
 }
 
+// ASCI-PT2 (asci/pt2.hpp:399-410): sum of rv * c_times_matel = (sum c*h)^2 / (E0 - <Q|H|Q>) over the
+// accumulated candidates whose c*h is finite (the core determinants carry the inf sentinel).
+// Fixed grid, fixed tree: the partial sums are combined on the host in block order.
+constexpr int PT2_BLOCKS = 592, PT2_THREADS = 256;
+__global__ void __launch_bounds__(PT2_THREADS)
+k_pt2_partial(const double* __restrict__ scm, const double* __restrict__ shd, int64_t n,
+              double* __restrict__ part_sum, double* __restrict__ part_cnt) {
+  __shared__ double ssum[PT2_THREADS], scnt[PT2_THREADS];
+  double acc = 0., cnt = 0.;
+  for (int64_t i = int64_t(blockIdx.x) * PT2_THREADS + threadIdx.x; i < n; i += int64_t(PT2_BLOCKS) * PT2_THREADS) {
+    const double c = scm[i];
+    if (!isinf(c)) { acc += (c / shd[i]) * c; cnt += 1.; }
+  }
+  ssum[threadIdx.x] = acc; scnt[threadIdx.x] = cnt;
+  __syncthreads();
+  for (int s = PT2_THREADS / 2; s > 0; s >>= 1) {
+    if (threadIdx.x < s) { ssum[threadIdx.x] += ssum[threadIdx.x + s]; scnt[threadIdx.x] += scnt[threadIdx.x + s]; }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) { part_sum[blockIdx.x] = ssum[0]; part_cnt[blockIdx.x] = scnt[0]; }
+}
+
 __global__ void k_fill_u64(uint64_t* p, int64_t n, uint64_t v) {
   const int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
   if (i < n) p[i] = v;
@@ -332,7 +354,7 @@ unsigned grid1d(int64_t n, int threads = 256) { return unsigned((n + threads - 1
 int asci_search(b2ci_ctx* ctx, const b2ci_asci_search_opts* o, const uint64_t* core_words, int wpd,
                 const double* coeffs, int64_t nc, double E0, uint64_t* out_words, int64_t cap,
                 int64_t* n_out, double* stats, uint64_t* cand_words, double* cand_cm,
-                double* cand_hd, int64_t* cand_n, bool candidates_only) {
+                double* cand_hd, int64_t* cand_n, bool candidates_only, double* pt2_out) {
   if (!ctx->ints_dev) throw Error("b2ci_asci_search: integrals not uploaded");
   if (!o || !core_words || !coeffs || nc < 1) throw Error("b2ci_asci_search: bad arguments");
   if (wpd != 1 && wpd != 2) throw Error("b2ci_asci_search: words_per_det must be 1 or 2");
@@ -407,6 +429,7 @@ int asci_search(b2ci_ctx* ctx, const b2ci_asci_search_opts* o, const uint64_t* c
   DevBuf<double> cand_score;
   int64_t ncand = 0, cand_cap = 0;
   int64_t M_sum = 0, nseg_sum = 0;
+  if (pt2_out) pt2_out[0] = pt2_out[1] = 0.;
   auto append_candidates = [&](const uint64_t* k, const double* sc, int64_t m) {
     if (ncand + m > cand_cap) {
       const int64_t ncap = std::max<int64_t>(ncand + m, cand_cap * 2);
@@ -493,6 +516,19 @@ int asci_search(b2ci_ctx* ctx, const b2ci_asci_search_opts* o, const uint64_t* c
     key.release(); cm.release(); hd.release();
     nseg_sum += nseg;
 
+    if (pt2_out) {
+      ScopedTimer t(ctx, "asci_search.TOPK_DUR", true);
+      DevBuf<double> ps(PT2_BLOCKS), pc(PT2_BLOCKS);
+      k_pt2_partial<<<PT2_BLOCKS, PT2_THREADS, 0, st>>>(scm, shd, nseg, ps, pc);
+      ctx->launches++;
+      B2_CHECK_LAUNCH();
+      std::vector<double> hs(PT2_BLOCKS), hc(PT2_BLOCKS);
+      B2_CUDA(cudaMemcpyAsync(hs.data(), ps, PT2_BLOCKS * 8, cudaMemcpyDeviceToHost, st));
+      B2_CUDA(cudaMemcpyAsync(hc.data(), pc, PT2_BLOCKS * 8, cudaMemcpyDeviceToHost, st));
+      B2_CUDA(cudaStreamSynchronize(st));
+      for (int b = 0; b < PT2_BLOCKS; ++b) { pt2_out[0] += hs[b]; pt2_out[1] += hc[b]; }
+      continue;
+    }
     if (candidates_only) {
       if (cand_n) *cand_n = nseg;
       if (cand_words) {
@@ -537,6 +573,18 @@ int asci_search(b2ci_ctx* ctx, const b2ci_asci_search_opts* o, const uint64_t* c
         }
       }
     }
+  }
+
+  if (pt2_out) {
+    if (nranks > 1) {  // every rank summed its own key partitions
+      DevBuf<double> d(2);
+      B2_CUDA(cudaMemcpyAsync(d, pt2_out, 16, cudaMemcpyHostToDevice, st));
+      comm_allreduce_sum(ctx, d, 2);
+      B2_CUDA(cudaMemcpyAsync(pt2_out, d, 16, cudaMemcpyDeviceToHost, st));
+      B2_CUDA(cudaStreamSynchronize(st));
+    }
+    if (stats) { stats[0] = double(M_sum); stats[1] = double(nseg_sum); stats[5] = double(nparts); }
+    return 0;
   }
 
   // ---- top-k over the surviving candidates (determinant_search.hpp:966-1114)

@@ -32,7 +32,7 @@ void comm_destroy(b2ci_ctx* ctx);
 int asci_search(b2ci_ctx* ctx, const b2ci_asci_search_opts* o, const uint64_t* core_words, int wpd,
                 const double* coeffs, int64_t ncdets, double E0, uint64_t* out_words, int64_t cap,
                 int64_t* n_out, double* stats, uint64_t* cand_words, double* cand_cm, double* cand_hd,
-                int64_t* cand_n, bool candidates_only);
+                int64_t* cand_n, bool candidates_only, double* pt2_out = nullptr);
 
 namespace {
 __global__ void k_i32_to_i64(const int32_t* __restrict__ in, int64_t n, int64_t* __restrict__ out) {
@@ -371,6 +371,21 @@ int b2ci_asci_candidates(b2ci_ctx* ctx, const b2ci_asci_search_opts* opts, const
   B2_TRY_CTX(ctx)
   return asci_search(ctx, opts, core_words, wpd, core_coeffs, ncdets, E0, nullptr, 0, nullptr, nullptr,
                      out_words, out_cmatel, out_hdiag, n_out, true);
+  B2_CATCH
+}
+
+int b2ci_asci_pt2(b2ci_ctx* ctx, const uint64_t* det_words, int wpd, const double* coeffs,
+                  int64_t ndets, double E_asci, double pt2_tol, double* ept2, int64_t* npt2) {
+  B2_TRY_CTX(ctx)
+  if (!ept2) throw Error("b2ci_asci_pt2: ept2 is NULL");
+  b2ci_asci_search_opts o;
+  o.ndets_max = ndets; o.h_el_tol = pt2_tol; o.rv_prune_tol = 0.; o.just_singles = 0; o.reserved = 0;
+  double acc[2] = {0., 0.};
+  asci_search(ctx, &o, det_words, wpd, coeffs, ndets, E_asci, nullptr, 0, nullptr, nullptr, nullptr, nullptr,
+              nullptr, nullptr, false, acc);
+  *ept2 = acc[0];
+  if (npt2) *npt2 = int64_t(acc[1]);
+  return 0;
   B2_CATCH
 }
 

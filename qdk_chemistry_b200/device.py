@@ -157,6 +157,18 @@ class Context:
         return words, cm, hd
 
 
+    def asci_pt2(self, det_words, coeffs, E_asci: float, pt2_tol: float = 1e-16,
+                 words_per_det: int = 1):
+        """macis::asci_pt2_constraint (asci/pt2.hpp): (EPT2, number of external determinants).
+        `det_words` must be spin-sorted, `coeffs` in the same order."""
+        dw = np.ascontiguousarray(det_words, dtype=np.uint64)
+        cc = np.ascontiguousarray(coeffs, dtype=np.float64)
+        e, npt2 = C.c_double(0.0), C.c_int64(0)
+        check(lib().b2ci_asci_pt2(self.h, _p(dw), words_per_det, _p(cc), dw.size // words_per_det,
+                                  E_asci, pt2_tol, C.byref(e), C.byref(npt2)))
+        return e.value, npt2.value
+
+
 class DetList:
     def __init__(self, ctx: Context, handle):
         self.ctx, self.h = ctx, handle

@@ -113,3 +113,39 @@ def test_key_partitioned_search_is_identical(ctx, water, golden_meta, golden_arr
     monkeypatch.setenv("B2CI_ASCI_BUDGET", str(int(st1[0] // 5)))
     outb, stb = ctx.asci_search(port.pack(ca, cb), cc, m["E0"], m["ndets_max"])
     assert stb[5] >= 6 and np.array_equal(np.sort(outb), np.sort(out1))
+
+
+# ---- ASCI-PT2 (asci/pt2.hpp; known answer asci.cxx:562-570) -----------------------------------
+@pytest.fixture(scope="module")
+def water_refined():
+    import json, os
+    g = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+    z = np.load(os.path.join(g, "water_refined_wfn.npz"))
+    with open(os.path.join(g, "pt2_meta.json")) as fh:
+        return z["alpha"], z["beta"], z["C"], json.load(fh)
+
+
+def test_pt2_water_known_answer(ctx, water, water_refined):
+    a, b, C, m = water_refined
+    ctx.upload_integrals(water.norb, water.T, water.V)
+    e, npt2 = ctx.asci_pt2(port.pack(a, b), C, m["E_asci"], m["pt2_tol"])
+    assert abs(e - m["known_answer"]) < 1e-8            # the reference's own tolerance (asci.cxx:569)
+    assert abs(e - m["port_full"]) < 1e-12 * abs(m["port_full"]) * 1e2   # summation order only
+    assert npt2 == m["port_full_npt2"]                   # same external determinants, exactly
+
+
+@pytest.mark.parametrize("parts", [1, 3])
+def test_pt2_matches_oracle_small(ctx, water, water_refined, parts, monkeypatch):
+    a, b, C, m = water_refined
+    top = np.sort(np.argsort(-np.abs(C), kind="stable")[: m["small_n"]])
+    cs = C[top] / np.linalg.norm(C[top])
+    eo, no = port.Ham(water.norb, water.T, water.V).asci_pt2(a[top], b[top], cs, m["E_asci"], 1e-16)
+    ctx.upload_integrals(water.norb, water.T, water.V)
+    monkeypatch.setenv("B2CI_ASCI_PARTS", str(parts))
+    e, npt2 = ctx.asci_pt2(port.pack(a[top], b[top]), cs, m["E_asci"], 1e-16)
+    assert npt2 == no
+    assert abs(e - eo) <= 1e-13 * abs(eo)
+    # a looser generation tolerance drops contributions on both sides alike
+    e3, n3 = ctx.asci_pt2(port.pack(a[top], b[top]), cs, m["E_asci"], 1e-5)
+    eo3, no3 = port.Ham(water.norb, water.T, water.V).asci_pt2(a[top], b[top], cs, m["E_asci"], 1e-5)
+    assert n3 == no3 and n3 < no and abs(e3 - eo3) <= 1e-13 * abs(eo3)
