@@ -288,6 +288,8 @@ def measure(ctx, sp, name, args, world, rank, local_rank, dist, torch, steps, wa
         e0, e1, e2, e3 = ev(), ev(), ev(), ev()
         e0.record()
         H = ctx.hbuild(dets, EPS, (r0, r1))
+        if world > 1:
+            H.set_row_partition(offs)
         e1.record()
         flush.zero_()
         e2.record()

@@ -98,6 +98,12 @@ int b2ci_spmv_host(b2ci_ctx* ctx, const b2ci_csr* m, const double* x, double* y)
  * is b2ci_spmv(x_local_dev). DEVICE pointers. */
 int b2ci_sigma_sharded(b2ci_ctx* ctx, const b2ci_csr* m, const double* x_local_dev,
                        double* x_full_dev, double* y_local_dev);
+/* Optional: tell a row block how the rows are split over the ranks (row_offsets has nranks + 1
+ * entries, block r = [row_offsets[r], row_offsets[r+1])), the information MACIS keeps in
+ * dist_sparse_matrix::row_tiling (sparsexx/matrix_types/dist_sparse_matrix.hpp:83-97). Without
+ * it the first b2ci_sigma_sharded / b2ci_davidson call on the block exchanges the block sizes
+ * (a host-synchronising all-gather). HOST pointer. */
+int b2ci_csr_set_row_partition(b2ci_ctx* ctx, b2ci_csr* m, const int64_t* row_offsets, int nranks);
 /* extract_diagonal_elements (sparsexx/util/submatrix.hpp:354-383); host output, nrows */
 int b2ci_csr_diagonal(b2ci_ctx* ctx, const b2ci_csr* m, double* D);
 

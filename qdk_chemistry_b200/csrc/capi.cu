@@ -322,6 +322,18 @@ int b2ci_sigma_sharded(b2ci_ctx* ctx, const b2ci_csr* m, const double* x_local_d
   return 0;
   B2_CATCH
 }
+int b2ci_csr_set_row_partition(b2ci_ctx* ctx, b2ci_csr* m, const int64_t* row_offsets, int nranks) {
+  B2_TRY_CTX(ctx)
+  if (!m || !row_offsets || nranks != ctx->nranks) throw Error("b2ci_csr_set_row_partition: bad arguments");
+  for (int r = 0; r < nranks; ++r)
+    if (row_offsets[r + 1] < row_offsets[r]) throw Error("b2ci_csr_set_row_partition: offsets must ascend");
+  if (row_offsets[0] != 0 || row_offsets[nranks] != m->ncols || row_offsets[ctx->rank] != m->row_begin ||
+      row_offsets[ctx->rank + 1] != m->row_begin + m->nrows)
+    throw Error("b2ci_csr_set_row_partition: offsets do not match this rank's row block");
+  m->row_offsets.assign(row_offsets, row_offsets + nranks + 1);
+  return 0;
+  B2_CATCH
+}
 int b2ci_csr_diagonal(b2ci_ctx* ctx, const b2ci_csr* m, double* D) {
   B2_TRY_CTX(ctx)
   DevBuf<double> d(m->nrows > 0 ? m->nrows : 1);

@@ -510,7 +510,9 @@ int davidson(b2ci_ctx* ctx, const b2ci_csr* m, int64_t max_m, double tol, double
 
   // row offsets of every rank (rank order tiles [0, N))
   std::vector<int64_t> row_offsets;
-  if (ctx->nranks > 1) {
+  if (ctx->nranks > 1 && int(m->row_offsets.size()) == ctx->nranks + 1) {
+    row_offsets = m->row_offsets;  // b2ci_csr_set_row_partition / an earlier sigma
+  } else if (ctx->nranks > 1) {
     std::vector<int64_t> counts;
     comm_allgather_i64_host(ctx, Nloc, counts);
     row_offsets.assign(ctx->nranks + 1, 0);

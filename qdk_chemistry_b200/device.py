@@ -256,6 +256,12 @@ class CsrMatrix:
         check(lib().b2ci_sigma_sharded(self.ctx.h, self.h, C.c_void_p(x_local_ptr),
                                        C.c_void_p(x_full_ptr), C.c_void_p(y_local_ptr)))
 
+    def set_row_partition(self, row_offsets):
+        """Row offsets of all ranks (nranks + 1 entries): spares the first sharded sigma /
+        Davidson call on this block its host-synchronising exchange of block sizes."""
+        off = np.ascontiguousarray(row_offsets, dtype=np.int64)
+        check(lib().b2ci_csr_set_row_partition(self.ctx.h, self.h, _p(off), off.size - 1))
+
     def diagonal(self) -> np.ndarray:
         d = np.empty(self.nrows, dtype=np.float64)
         check(lib().b2ci_csr_diagonal(self.ctx.h, self.h, _p(d)))

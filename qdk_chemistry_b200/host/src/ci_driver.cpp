@@ -188,6 +188,11 @@ class CiSession {
     const auto rows = my_rows(n);
     b2ci_csr* H = nullptr;
     B2(b2ci_hbuild_csr(ctx_, dets, rows.first, rows.second, matel_tol, &H));
+    if (nranks_ > 1) {  // every rank knows the split (row_block): no exchange of block sizes
+      std::vector<int64_t> off(size_t(nranks_) + 1, 0);
+      for (int r = 0; r < nranks_; ++r) off[size_t(r) + 1] = row_block(n, r, nranks_).second;
+      B2(b2ci_csr_set_row_partition(ctx_, H, off.data(), nranks_));
+    }
     add_timer("h_build_ms", {"h_build.setup", "h_build.count", "h_build.fill", "h_build.thresh"});
     add_timer("h_build_setup_ms", {"h_build.setup"});
     add_timer("h_build_count_ms", {"h_build.count"});

@@ -59,6 +59,18 @@ def main():
     yref = Hfull.spmv(x)
     out["gather_exact"] = bool(np.array_equal(xf.cpu().numpy(), x))
     out["sigma_bit_exact"] = bool(np.array_equal(yl.cpu().numpy(), yref[r0:r1]))
+    # the same with the split supplied by the caller (no exchange of block sizes)
+    Hloc2 = ctx.hbuild(dets, EPS, (r0, r1))
+    Hloc2.set_row_partition(cuts)
+    xf.zero_(); yl.zero_()
+    Hloc2.sigma_sharded(xl.data_ptr(), xf.data_ptr(), yl.data_ptr())
+    torch.cuda.synchronize()
+    out["sigma_bit_exact"] = bool(out["sigma_bit_exact"] and np.array_equal(yl.cpu().numpy(), yref[r0:r1]))
+    try:
+        Hloc2.set_row_partition([0] + [c + 1 for c in cuts[1:-1]] + [n])
+        out["bad_partition_rejected"] = world == 1
+    except device.B2ciError:
+        out["bad_partition_rejected"] = True
     E1, X1, it1, _ = Hfull.davidson(200, 1e-8)
     Ed, Xd, itd, _ = Hloc.davidson(200, 1e-8)
     out.update(E_single=E1, E_sharded=Ed, niter_single=it1, niter_sharded=itd,
