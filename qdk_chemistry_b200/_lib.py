@@ -11,7 +11,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libb2ci.so")
+LIB_PATH = os.environ.get("B2CI_LIB_PATH") or os.path.join(_HERE, "libb2ci.so")
 HEADER_PATH = os.path.join(os.path.dirname(_HERE), "include", "b2ci.h")
 
 _lib = None

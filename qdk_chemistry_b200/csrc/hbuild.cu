@@ -445,7 +445,8 @@ struct ProdArgs {
   int64_t nrows;
   double thr;
   int smem_a;                 // doubles of per-warp scratch for alpha singles
-  int smem_b;                 // ... and beta singles / B2 records
+  int smem_b;                 // ... and beta singles
+  int smem_r;                 // opposite-spin records per row (smem_b rounded up to the group width)
   int nslice_max;             // integral slices staged per CTA (singles per run, upper bound)
   int32_t* row_cnt;           // structural count (count kernel) / surviving count (fill kernel)
   const int64_t* rowptr;      // slot offsets of the fill kernel
@@ -516,33 +517,45 @@ __device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, u
 // orbital order) are evaluated once per row with full lanes into shared memory, next to the
 // row's B2 records.
 constexpr int PW = 16;  // warps per CTA of the product kernel
+#ifndef B2CI_PROD_MINB
+#define B2CI_PROD_MINB 2    // resident CTAs per SM the register allocation must allow
+#endif
 template <int G>
 struct GroupOut {
-  int32_t* ci;   // colind of this row (slot base)
-  double* nz;    // nzval of this row
-  int rel;       // elements written so far
-  unsigned ltg;  // lanes of the group below this lane
-  int gshift;    // first lane of the group
+  int32_t* ci;      // colind of this row (slot base), kept as an opaque 64-bit register pair
+  double* nz;       // nzval of this row
+  int rel;          // elements written so far
+  unsigned ltmask;  // lanes of this group below this lane (warp-wide bit positions)
+  unsigned gmask;   // lanes of this group
+  int lig;          // lane index inside the group
 };
-template <int G>
-__device__ __forceinline__ unsigned group_bits(unsigned m, int gshift) {
-  if (G == 32) return m;
-  return (m >> gshift) & ((1u << (G & 31)) - 1u);
-}
 template <bool EVAL, int G>
 __device__ __forceinline__ void emit(GroupOut<G>& O, double thr, bool act, int32_t j, double v) {
   const bool keep = act && (EVAL ? (fabs(v) > thr) : true);
-  const unsigned gm = group_bits<G>(__ballot_sync(0xffffffffu, keep), O.gshift);
+  const unsigned m = __ballot_sync(0xffffffffu, keep);
+  if (m == 0xffffffffu) {  // every lane of the warp survives (the common case): no prefix count
+    const int pos = O.rel + O.lig;
+    O.ci[pos] = j;
+    O.nz[pos] = v;
+    O.rel += G;
+    return;
+  }
   if (keep) {
-    const int pos = O.rel + __popc(gm & O.ltg);
+    const int pos = O.rel + __popc(m & O.ltmask);
     O.ci[pos] = j;
     O.nz[pos] = v;
   }
-  O.rel += __popc(gm);
+  O.rel += __popc(m & O.gmask);
 }
+// opposite-spin record of one (row, B2 entry), resolved for both bra/ket orientations:
+//   w = off(r < r2) | off(r > r2) << 12 | is_self << 30 | sign << 31; k2 = ~0 marks padding
+struct __align__(8) OsRec {
+  uint32_t k2;
+  uint32_t w;
+};
 
 template <bool EVAL, int G, bool SLICES>
-__global__ void __launch_bounds__(PW * 32)
+__global__ void __launch_bounds__(PW * 32, B2CI_PROD_MINB)
 k_rows_product(const ProdArgs A) {
   constexpr int RPW = 32 / G, RPC = PW * RPW;
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -550,7 +563,7 @@ k_rows_product(const ProdArgs A) {
   uint64_t* bar = reinterpret_cast<uint64_t*>(smem_raw);
   double* slices = reinterpret_cast<double*>(smem_raw + 16);
   double* rows_d = slices + (SLICES ? size_t(A.nslice_max) * A.I.n2p : 0);
-  B2Rec* rows_b = reinterpret_cast<B2Rec*>(rows_d + size_t(RPC) * (A.smem_a + A.smem_b));
+  OsRec* rows_b = reinterpret_cast<OsRec*>(rows_d + size_t(RPC) * (A.smem_a + A.smem_b));
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   const int gid = lane / G, l = lane % G;
   const int64_t cpr = (A.nb + RPC - 1) / RPC;  // chunks per run
@@ -591,20 +604,29 @@ k_rows_product(const ProdArgs A) {
   const uint32_t nb = uint32_t(A.nb);
   double* sa = rows_d + size_t(w * RPW + gid) * (A.smem_a + A.smem_b);
   double* sb = sa + A.smem_a;
-  B2Rec* sb2 = rows_b + size_t(w * RPW + gid) * A.smem_b;
+  OsRec* sb2 = rows_b + size_t(w * RPW + gid) * A.smem_r;
   const uint64_t bi = A.tmpl_beta[k];
   const int64_t b2s = A.b2_ptr[k], b4s = A.b4_ptr[k];
   const int len2 = int(A.b2_ptr[k + 1] - b2s), len4 = int(A.b4_ptr[k + 1] - b4s);
   const int len2max = G == 32 ? len2 : __reduce_max_sync(0xffffffffu, rowvalid ? len2 : 0);
   const int len4max = G == 32 ? len4 : __reduce_max_sync(0xffffffffu, rowvalid ? len4 : 0);
   const int64_t out0 = A.rowptr[row];
+  const double dgv = A.diag[row];  // fetched early: its latency hides behind the staging phase
   GroupOut<G> O;
   O.ci = A.colind + out0;
   O.nz = A.nzval + out0;
+  // keep the two row pointers as plain registers: stores become one IMAD.WIDE + STG each
+  asm volatile("" : "+l"(O.ci), "+l"(O.nz));
+  __builtin_assume(__isGlobal(O.ci));
+  __builtin_assume(__isGlobal(O.nz));
   O.rel = 0;
-  O.ltg = (1u << l) - 1u;
-  O.gshift = gid * G;
+  const unsigned ltg = (1u << l) - 1u;   // lanes of the group below this lane (group-relative)
+  const int gshift = gid * G;
+  O.ltmask = ltg << gshift;
+  O.lig = l;
+  O.gmask = (G == 32 ? 0xffffffffu : ((1u << (G & 31)) - 1u)) << gshift;
   const unsigned lt = (1u << lane) - 1u;
+  const int len2pad = (len2max + G - 1) / G * G;  // records per row incl. padding (<= smem_r)
   if (warp_active) {
     // ---- single-excitation elements and B2 records of this row
     for (int s = l; s < ns; s += G) {
@@ -614,13 +636,25 @@ k_rows_product(const ProdArgs A) {
       for (uint64_t q = bi; q; q &= q - 1) h += ldg(Vr + lsb64(q));
       sa[s] = flip_sign_if(h, m >> 16);
     }
-    for (int t = l; t < len2; t += G) {
+    for (int t = l; t < (rowvalid ? len2 : 0); t += G) {
       const uint32_t m = A.b2_meta[b2s + t];
       double h = A.b2_val[b2s + t];
       const double* Vr = A.I.Vr + ((m >> 8) & 0xFFu) * n + (m & 0xFFu) * n2;
       for (uint64_t q = ai; q; q &= q - 1) h += ldg(Vr + lsb64(q));
       sb[t] = flip_sign_if(h, m >> 16);  // the self slot is never read
-      sb2[t] = A.b2rec[b2s + t];
+      const B2Rec br = A.b2rec[b2s + t];
+      const uint32_t o0 = br.pk & 0xFFFu, o1 = (br.pk >> 12) & 0xFFFu;
+      const bool up = (br.pk >> 26) & 1u;  // k2 > k
+      OsRec orec;
+      orec.k2 = br.k2;
+      // row is the bra iff r < r2; the stored pair has bra = lower template index
+      orec.w = (up ? o0 : o1) | ((up ? o1 : o0) << 12) | (((br.pk >> 25) & 1u) << 30) | (((br.pk >> 24) & 1u) << 31);
+      sb2[t] = orec;
+    }
+    for (int t = (rowvalid ? len2 : 0) + l; t < len2pad; t += G) {
+      OsRec orec;
+      orec.k2 = 0xFFFFFFFFu; orec.w = 0u;
+      sb2[t] = orec;
     }
     __syncwarp();
   }
@@ -628,13 +662,19 @@ k_rows_product(const ProdArgs A) {
   if (!warp_active) return;
   const int64_t E0 = A.cptr[r], E1 = A.cptr[r + 1];
   int sord0 = 0;  // singles before the current window
+  // adjacency windows are fetched one window ahead of their use
+  ARec rec_n;
+  rec_n.r2t = 0; rec_n.meta = 0;
+  double cv_n = 0.;
+  if (E0 + lane < E1) { rec_n = A.crec[E0 + lane]; cv_n = A.cval[E0 + lane]; }
   for (int64_t eb = E0; eb < E1; eb += 32) {
     const int nv = int(min(int64_t(32), E1 - eb));
     const bool ev = lane < nv;
-    ARec rec;
-    rec.r2t = 0; rec.meta = 0;
-    double cv = 0.;
-    if (ev) { rec = A.crec[eb + lane]; cv = A.cval[eb + lane]; }
+    const ARec rec = rec_n;
+    const double cv = cv_n;
+    rec_n.r2t = 0; rec_n.meta = 0;
+    cv_n = 0.;
+    if (eb + 32 + lane < E1) { rec_n = A.crec[eb + 32 + lane]; cv_n = A.cval[eb + 32 + lane]; }
     const bool sing_l = ev && ((rec.meta >> 18) & 1u);
     const unsigned lm = __ballot_sync(0xffffffffu, ev && (rec.r2t & 3u) != 2u);  // list entries
     const unsigned gm = __ballot_sync(0xffffffffu, sing_l);                      // singles
@@ -669,37 +709,51 @@ k_rows_product(const ProdArgs A) {
         const double* Va = SLICES ? slices + size_t(so) * A.I.n2p
                                   : A.I.Vt + (((am >> 8) & 0xFFu) + size_t(am & 0xFFu) * n) * A.I.n2p;
         const double vself = sa[so];
-        // the row determinant is the bra iff r < r2; the stored beta pair has bra = lower
-        // template index, so its orientation is swapped when the two orders disagree
-        const uint32_t lower = r < r2 ? 1u : 0u;
+        // the row determinant is the bra iff r < r2 (orientation resolved when the records were staged)
+        const uint32_t sh = r < r2 ? 0u : 12u;
+        const uint32_t asign = ((am >> 16) & 1u) << 31;
         const uint32_t base = r2 * nb;
-        for (int t0 = 0; t0 < len2max; t0 += G) {
-          const int t = t0 + l;
-          const bool act = rowvalid && t < len2;
-          const B2Rec br = sb2[min(t, len2 - 1)];
-          const bool swap_b = lower != ((br.pk >> 26) & 1u);
-          const uint32_t off = (swap_b ? (br.pk >> 12) : br.pk) & 0xFFFu;
-          double v = flip_sign_if(SLICES ? Va[off] : ldg(Va + off), (am >> 16) ^ (br.pk >> 24));
-          if (br.pk & (1u << 25)) v = vself;
+        for (int t0 = 0; t0 < len2pad; t0 += G) {
+          const OsRec br = sb2[t0 + l];
+          const bool act = br.k2 != 0xFFFFFFFFu;
+          const uint32_t off = (br.w >> sh) & 0xFFFu;
+          const double vr = SLICES ? Va[off] : ldg(Va + off);
+          double v = __hiloint2double(__double2hiint(vr) ^ int((br.w & 0x80000000u) ^ asign), __double2loint(vr));
+          if (br.w & (1u << 30)) v = vself;
           emit<EVAL, G>(O, A.thr, act, int32_t(base + br.k2), v);
         }
       } else {
         // same alpha string x B4(k): diagonal, beta singles, beta doubles
         const uint32_t base = r * nb;
         int t2run = 0;  // position in B2(k) of the next entry at distance <= 2
-        for (int t0 = 0; t0 < len4max; t0 += G) {
-          const int t = t0 + l;
-          const bool act = rowvalid && t < len4;
-          const int64_t e4 = b4s + min(t, len4 - 1);
-          const uint32_t bpk = A.b4[e4];
-          const int db = int(bpk & 3u);
-          const unsigned g01 = group_bits<G>(__ballot_sync(0xffffffffu, act && db <= 1), O.gshift);
-          double v;
-          if (db == 2) v = A.b4_val[e4];
-          else if (db == 1) v = act ? sb[t2run + __popc(g01 & O.ltg)] : 0.;
-          else v = A.diag[row];
-          t2run += __popc(g01);
-          emit<EVAL, G>(O, A.thr, act, int32_t(base + (bpk >> 2)), v);
+        // the list lives in global memory (L2): issue the loads of U iterations together, value
+        // and descriptor side by side, so one latency is paid per U * G elements
+        constexpr int U = 4;
+        for (int c0 = 0; c0 < len4max; c0 += U * G) {
+          uint32_t bpk_u[U];
+          double bv_u[U];
+#pragma unroll
+          for (int u = 0; u < U; ++u) {
+            const int64_t e4 = b4s + min(c0 + u * G + l, len4 - 1);
+            bpk_u[u] = __ldg(A.b4 + e4);
+            bv_u[u] = ldg(A.b4_val + e4);
+          }
+#pragma unroll
+          for (int u = 0; u < U; ++u) {
+            const int t = c0 + u * G + l;
+            if (c0 + u * G < len4max) {  // warp-uniform
+              const bool act = rowvalid && t < len4;
+              const uint32_t bpk = bpk_u[u];
+              const int db = int(bpk & 3u);
+              const unsigned g01 = __ballot_sync(0xffffffffu, act && db <= 1) & O.gmask;
+              double v;
+              if (db == 2) v = bv_u[u];
+              else if (db == 1) v = act ? sb[t2run + __popc(g01 & O.ltmask)] : 0.;
+              else v = dgv;
+              t2run += __popc(g01);
+              emit<EVAL, G>(O, A.thr, act, int32_t(base + (bpk >> 2)), v);
+            }
+          }
         }
       }
       cur = f + 1;
@@ -1057,7 +1111,8 @@ void hbuild_csr(b2ci_ctx* ctx, const b2ci_dets* dets, int64_t row_begin, int64_t
       const unsigned grid = unsigned(nruns_blk * cpr);
       // shared memory: mbarrier + integral slices + per-row singles and B2 records
       P.nslice_max = P.smem_a - 1;
-      const size_t rows_bytes = size_t(rpc) * ((P.smem_a + P.smem_b) * sizeof(double) + P.smem_b * sizeof(B2Rec));
+      P.smem_r = (P.smem_b + G - 1) / G * G;
+      const size_t rows_bytes = size_t(rpc) * ((P.smem_a + P.smem_b) * sizeof(double) + P.smem_r * sizeof(OsRec));
       const size_t slice_bytes = size_t(P.nslice_max) * ctx->ints.n2p * sizeof(double);
       // stage the slices when two CTAs per SM still fit (227 KB per SM)
       bool slices = 16 + slice_bytes + rows_bytes <= 110 * 1024;
