@@ -517,6 +517,12 @@ __device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, u
 // orbital order) are evaluated once per row with full lanes into shared memory, next to the
 // row's B2 records.
 constexpr int PW = 16;  // warps per CTA of the product kernel
+#ifndef B2CI_PROD_UH
+#define B2CI_PROD_UH 1      // opposite-spin iterations whose shared-memory loads are grouped
+#endif
+#ifndef B2CI_PROD_U4
+#define B2CI_PROD_U4 4      // B4-list iterations whose global loads are grouped
+#endif
 #ifndef B2CI_PROD_MINB
 #define B2CI_PROD_MINB 2    // resident CTAs per SM the register allocation must allow
 #endif
@@ -658,6 +664,26 @@ k_rows_product(const ProdArgs A) {
     }
     __syncwarp();
   }
+  // Short lists (the usual full-CI shapes): every lane keeps the NR records it will ever touch
+  // in registers, one packed word each --
+  //   off(r < r2) | off(r > r2) << 8 | is_self << 16 | sign << 17 | k2 << 18, ~0 = padding
+  // -- so the inner loop reads shared memory only for the integral itself.
+  constexpr int NR = 3;
+  const bool regrec = SLICES && len2pad <= NR * G && A.I.n2p <= 256 && A.nb < 16383;
+  uint32_t rr[NR];
+#pragma unroll
+  for (int u = 0; u < NR; ++u) rr[u] = 0xFFFFFFFFu;
+  if (warp_active && regrec) {
+#pragma unroll
+    for (int u = 0; u < NR; ++u) {
+      if (u * G < len2pad) {
+        const OsRec o = sb2[u * G + l];
+        if (o.k2 != 0xFFFFFFFFu)
+          rr[u] = (o.w & 0xFFu) | (((o.w >> 12) & 0xFFu) << 8) | (((o.w >> 30) & 1u) << 16) |
+                  ((o.w >> 31) << 17) | (o.k2 << 18);
+      }
+    }
+  }
   if (SLICES) mbar_wait(bar, 0);
   if (!warp_active) return;
   const int64_t E0 = A.cptr[r], E1 = A.cptr[r + 1];
@@ -713,14 +739,29 @@ k_rows_product(const ProdArgs A) {
         const uint32_t sh = r < r2 ? 0u : 12u;
         const uint32_t asign = ((am >> 16) & 1u) << 31;
         const uint32_t base = r2 * nb;
-        for (int t0 = 0; t0 < len2pad; t0 += G) {
-          const OsRec br = sb2[t0 + l];
-          const bool act = br.k2 != 0xFFFFFFFFu;
-          const uint32_t off = (br.w >> sh) & 0xFFFu;
-          const double vr = SLICES ? Va[off] : ldg(Va + off);
-          double v = __hiloint2double(__double2hiint(vr) ^ int((br.w & 0x80000000u) ^ asign), __double2loint(vr));
-          if (br.w & (1u << 30)) v = vself;
-          emit<EVAL, G>(O, A.thr, act, int32_t(base + br.k2), v);
+        if (regrec) {
+          const uint32_t sh8 = r < r2 ? 0u : 8u;
+#pragma unroll
+          for (int u = 0; u < NR; ++u) {
+            if (u * G < len2pad) {  // warp-uniform
+              const uint32_t w = rr[u];
+              const double vr = Va[(w >> sh8) & 0xFFu];
+              double v = __hiloint2double(__double2hiint(vr) ^ int(((w << 14) & 0x80000000u) ^ asign),
+                                          __double2loint(vr));
+              if (w & (1u << 16)) v = vself;
+              emit<EVAL, G>(O, A.thr, w != 0xFFFFFFFFu, int32_t(base + (w >> 18)), v);
+            }
+          }
+        } else {
+          for (int t0 = 0; t0 < len2pad; t0 += G) {
+            const OsRec br = sb2[t0 + l];
+            const bool act = br.k2 != 0xFFFFFFFFu;
+            const uint32_t off = (br.w >> sh) & 0xFFFu;
+            const double vr = SLICES ? Va[off] : ldg(Va + off);
+            double v = __hiloint2double(__double2hiint(vr) ^ int((br.w & 0x80000000u) ^ asign), __double2loint(vr));
+            if (br.w & (1u << 30)) v = vself;
+            emit<EVAL, G>(O, A.thr, act, int32_t(base + br.k2), v);
+          }
         }
       } else {
         // same alpha string x B4(k): diagonal, beta singles, beta doubles
@@ -728,7 +769,7 @@ k_rows_product(const ProdArgs A) {
         int t2run = 0;  // position in B2(k) of the next entry at distance <= 2
         // the list lives in global memory (L2): issue the loads of U iterations together, value
         // and descriptor side by side, so one latency is paid per U * G elements
-        constexpr int U = 4;
+        constexpr int U = B2CI_PROD_U4;
         for (int c0 = 0; c0 < len4max; c0 += U * G) {
           uint32_t bpk_u[U];
           double bv_u[U];
@@ -1123,6 +1164,8 @@ void hbuild_csr(b2ci_ctx* ctx, const b2ci_dets* dets, int64_t row_begin, int64_t
       auto launch = [&](auto kern) {
         if (smem > 48 * 1024)
           B2_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
+        // the largest carve-out: resident CTAs are then limited by registers, not by the split
+        B2_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
         kern<<<grid, PW * 32, smem, st>>>(P);
       };
       auto launch_g = [&](auto ev, auto sl) {

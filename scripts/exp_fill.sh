@@ -1,5 +1,5 @@
 mkdir -p gpurun_out
-(timeout 600 python -m pytest tests/test_gpu_parity.py -x -q 2>&1 | tail -4)
+(timeout 600 python -m pytest tests/test_gpu_parity.py -x -q -k "cr2 or cas or hubbard or product or path" 2>&1 | tail -4)
 run() { # name, env...
   name=$1; shift
   env "$@" timeout 200 python bench.py --workload ${WL:-cr2_cas12} --no-also --no-davidson --steps 5 --warmup 3 --cpu-seconds 0 > gpurun_out/exp_$name.json 2> gpurun_out/exp_$name.err
