@@ -56,6 +56,7 @@ class ClockSampler:
     def __init__(self, index: int):
         self.index = index
         self.samples = []
+        self.first = 0
         self.proc = None
 
     def start(self):
@@ -65,7 +66,7 @@ class ClockSampler:
         try:
             self.proc = subprocess.Popen(
                 ["nvidia-smi", f"--id={self.index}", f"--query-gpu={q}", "--format=csv,noheader,nounits",
-                 "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+                 "-lms", "50"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._read, daemon=True)
             self.thread.start()
         except OSError:
@@ -74,6 +75,15 @@ class ClockSampler:
     def _read(self):
         for line in self.proc.stdout:
             self.samples.append(line.strip())
+
+    def wait_first(self, timeout_s):
+        t0 = time.time()
+        while self.proc and not self.samples and time.time() - t0 < timeout_s:
+            time.sleep(0.01)
+
+    def mark(self):
+        """samples from here on belong to the timed region"""
+        self.first = len(self.samples)
 
     def stop(self):
         if not self.proc:
@@ -86,7 +96,7 @@ class ClockSampler:
             self.proc.kill()
         sm, mx, reasons = [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for s in self.samples:
+        for s in self.samples[max(0, self.first - 1):]:
             f = [x.strip() for x in s.split(",")]
             if len(f) < 7:
                 continue
@@ -276,11 +286,16 @@ def measure(ctx, sp, name, args, world, rank, local_rank, dist, torch, steps, wa
     launches0 = wall0 = 0
     for it in range(warmup + steps):
         timed = it >= warmup
+        if it == 0 and rank == 0 and full:
+            # nvidia-smi is started during the warm-up: its start-up (NVML initialisation takes the
+            # driver lock for tens of ms and stalls the host-synchronising steps of a build) must
+            # not land in the timed region; the 100 ms samples keep coming throughout it
+            sampler.start()
+            sampler.wait_first(3.0)
         if it == warmup:
             barrier()
             launches0 = ctx.launch_count
-            if rank == 0 and full:
-                sampler.start()
+            sampler.mark()
             wall0 = time.perf_counter()
         if H is not None:
             H.free()
@@ -303,6 +318,8 @@ def measure(ctx, sp, name, args, world, rank, local_rank, dist, torch, steps, wa
                 T[k].append(ctx.timer_ms("h_build." + k))
     barrier()
     wall1 = time.perf_counter()
+    if os.environ.get("B2CI_BENCH_VERBOSE") and rank == 0:
+        print(name, {k: [round(x, 3) for x in v] for k, v in T.items()}, file=sys.stderr)
     clocks = sampler.stop() if (rank == 0 and full) else None
     launches = ctx.launch_count - launches0
     nnz_local = H.nnz

@@ -104,6 +104,8 @@ int b2ci_ctx_destroy(b2ci_ctx* ctx) {
     StreamScope scope(ctx);
     comm_destroy(ctx);
     dev_free(ctx->ints_dev);
+    for (int i = 0; i < 2; ++i) dev_free(ctx->slot_cache[i]);
+    if (ctx->pinned) cudaFreeHost(ctx->pinned);
     cudaStreamSynchronize(ctx->stream);
   }
   delete ctx;
@@ -119,6 +121,11 @@ int b2ci_ctx_synchronize(b2ci_ctx* ctx) {
 int64_t b2ci_ctx_launch_count(const b2ci_ctx* ctx) { return ctx ? ctx->launches : 0; }
 int b2ci_ctx_trim(b2ci_ctx* ctx) {
   B2_TRY_CTX(ctx)
+  for (int i = 0; i < 2; ++i) {
+    dev_free(ctx->slot_cache[i]);
+    ctx->slot_cache[i] = nullptr;
+    ctx->slot_cache_bytes[i] = 0;
+  }
   B2_CUDA(cudaStreamSynchronize(ctx->stream));
   cudaMemPool_t pool;
   B2_CUDA(cudaDeviceGetDefaultMemPool(&pool, ctx->device));
@@ -278,8 +285,8 @@ int b2ci_csr_free(b2ci_ctx* ctx, b2ci_csr* m) {
   if (!m) return 0;
   StreamScope scope(ctx);
   dev_free(m->rowptr);
-  dev_free(m->colind);
-  dev_free(m->nzval);
+  if (ctx && m->colind_cap) big_release(ctx, 0, m->colind, m->colind_cap); else dev_free(m->colind);
+  if (ctx && m->nzval_cap) big_release(ctx, 1, m->nzval, m->nzval_cap); else dev_free(m->nzval);
   delete m;
   return 0;
 }

@@ -97,6 +97,13 @@ struct b2ci_ctx {
   // multi-GPU
   void* nccl_comm = nullptr;
   int rank = 0, nranks = 1;
+  // structural slot arrays of the last thresholded H build (kept when rows had to be packed:
+  // handing multi-GB blocks back to the pool between builds fragments it and makes it grow)
+  void* slot_cache[2] = {nullptr, nullptr};
+  size_t slot_cache_bytes[2] = {0, 0};
+  // pinned staging for the scalars a build reads back (pageable targets would make every
+  // cudaMemcpyAsync a synchronisation of its own)
+  int64_t* pinned = nullptr;
 };
 
 struct b2ci_dets {
@@ -111,6 +118,7 @@ struct b2ci_csr {
   int32_t* colind = nullptr;  // device, global column indices
   double* nzval = nullptr;    // device
   std::vector<int64_t> row_offsets;  // multi-GPU: row offsets of all ranks (lazy)
+  size_t colind_cap = 0, nzval_cap = 0;  // allocated bytes when known (recycled through the context)
 };
 
 namespace b2ci {
@@ -172,6 +180,43 @@ struct DevBuf {
   T* take() { T* q = p; p = nullptr; n = 0; return q; }
   operator T*() const { return p; }
 };
+
+// [0] colind-like (4 B / entry), [1] nzval-like (8 B / entry): take a cached block or allocate
+inline void* big_alloc(b2ci_ctx* ctx, int which, size_t bytes, size_t* cap) {
+  void* q = nullptr;
+  if (ctx->slot_cache[which] && ctx->slot_cache_bytes[which] >= bytes) {
+    q = ctx->slot_cache[which];
+    *cap = ctx->slot_cache_bytes[which];
+  } else {
+    dev_free(ctx->slot_cache[which]);
+    q = dev_alloc(bytes);
+    *cap = bytes;
+  }
+  ctx->slot_cache[which] = nullptr;
+  ctx->slot_cache_bytes[which] = 0;
+  return q;
+}
+// give a block back: the context keeps the larger one, the other returns to the pool
+inline void big_release(b2ci_ctx* ctx, int which, void* p, size_t cap) {
+  if (!p) return;
+  if (cap > ctx->slot_cache_bytes[which]) {
+    dev_free(ctx->slot_cache[which]);
+    ctx->slot_cache[which] = p;
+    ctx->slot_cache_bytes[which] = cap;
+  } else {
+    dev_free(p);
+  }
+}
+constexpr int PINNED_WORDS = 64;
+inline int64_t* pinned_words(b2ci_ctx* ctx) {
+  if (!ctx->pinned) {
+    if (cudaHostAlloc(reinterpret_cast<void**>(&ctx->pinned), PINNED_WORDS * 8, cudaHostAllocDefault) != cudaSuccess) {
+      cudaGetLastError();
+      throw Error("pinned staging allocation failed");
+    }
+  }
+  return ctx->pinned;
+}
 
 struct ScopedTimer {  // CUDA-event timing of a phase on the context stream
   b2ci_ctx* ctx;

@@ -16,6 +16,7 @@
 //                   per-row sort, no atomics, both triangles computed with the SAME
 //                   (bra = lower index, ket = higher index) roles as the reference so the
 //                   values are bit-identical to its mirrored entries.
+#include <chrono>
 #include <cmath>
 #include <cstdlib>
 #include <type_traits>
@@ -41,8 +42,7 @@ __global__ void k_run_flags(const uint64_t* __restrict__ alpha, int64_t n,
 __global__ void k_run_scatter(const uint64_t* __restrict__ alpha, int64_t n,
                               const int32_t* __restrict__ flag,
                               const int32_t* __restrict__ excl, int32_t* __restrict__ run_of,
-                              int64_t* __restrict__ run_start, uint64_t* __restrict__ run_alpha,
-                              int32_t nruns) {
+                              int64_t* __restrict__ run_start, uint64_t* __restrict__ run_alpha) {
   const int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
   if (i >= n) return;
   const int32_t r = excl[i] + flag[i] - 1;
@@ -51,7 +51,7 @@ __global__ void k_run_scatter(const uint64_t* __restrict__ alpha, int64_t n,
     run_start[r] = i;
     run_alpha[r] = alpha[i];
   }
-  if (i == n - 1) run_start[nruns] = n;
+  if (i == n - 1) run_start[r + 1] = n;  // r + 1 == number of runs
 }
 
 // adjacency between bit strings (alpha runs, or the beta template of a rectangular list):
@@ -257,9 +257,15 @@ __global__ void k_group_scatter(const uint64_t* __restrict__ key_sorted, const u
 //   { (r', k') : r' in A(r), k' in B_{4 - d_alpha(r, r')}(k) },
 // already in ascending column order. Every lane evaluates a real matrix element.
 __global__ void k_check_rect(const uint64_t* __restrict__ alpha, const uint64_t* __restrict__ beta,
-                             int64_t n, int64_t nb, int* __restrict__ bad) {
+                             int64_t n, const int32_t* __restrict__ nruns_dev, int* __restrict__ bad) {
   const int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
   if (i >= n) return;
+  const int64_t nruns = *nruns_dev;
+  if (nruns <= 0 || n % nruns != 0 || n / nruns >= (int64_t(1) << 29)) {
+    if (i == 0) atomicOr(bad, 1);
+    return;
+  }
+  const int64_t nb = n / nruns;
   const int64_t r = i / nb, k = i % nb;
   bool ok = beta[i] == beta[k] && alpha[i] == alpha[r * nb];
   if (k == 0 && r > 0) ok = ok && alpha[i] != alpha[i - 1];
@@ -951,25 +957,48 @@ void hbuild_csr(b2ci_ctx* ctx, const b2ci_dets* dets, int64_t row_begin, int64_t
     out->rowptr = rowptr.take();
     return;
   }
+  DeferredTimers DT(ctx);  // phase events are resolved at the (few) host synchronisations
+  // host wall-clock trace of the orchestration (B2CI_HBUILD_TRACE=1): where the time between
+  // kernels goes (allocations, synchronisations, launch gaps)
+  const bool trace = getenv("B2CI_HBUILD_TRACE") != nullptr;
+  auto t_host0 = std::chrono::steady_clock::now();
+  auto mark = [&](const char* what) {
+    if (!trace) return;
+    auto t = std::chrono::steady_clock::now();
+    fprintf(stderr, "[hbuild] %-28s +%8.1f us\n", what, std::chrono::duration<double, std::micro>(t - t_host0).count());
+    t_host0 = t;
+  };
+  bool rect = false;
   {
-    ScopedTimer t(ctx, "h_build.setup");
+    DeferredScope t(DT, "h_build.setup");
     DevBuf<int32_t> flag(n), excl(n + 1);
+    DevBuf<int> bad(1);
     const unsigned gb = unsigned((n + 255) / 256);
     k_run_flags<<<gb, 256, 0, st>>>(dets->alpha, n, flag);
     ctx->launches++;
     B2_CHECK_LAUNCH();
     exclusive_scan_i32(ctx, flag, excl, n);
-    B2_CUDA(cudaMemcpyAsync(&nruns, excl.p + n, 4, cudaMemcpyDeviceToHost, st));
-    B2_CUDA(cudaStreamSynchronize(st));
-    run_start.alloc(nruns + 1);
-    run_alpha.alloc(nruns);
-    k_run_scatter<<<gb, 256, 0, st>>>(dets->alpha, n, flag, excl, run_of, run_start, run_alpha, nruns);
-    ctx->launches++;
+    // run tables are sized for the worst case (every determinant its own run): the run count
+    // and the shape test come back in one synchronisation
+    run_start.alloc(n + 1);
+    run_alpha.alloc(n);
+    k_run_scatter<<<gb, 256, 0, st>>>(dets->alpha, n, flag, excl, run_of, run_start, run_alpha);
+    B2_CUDA(cudaMemsetAsync(bad, 0, sizeof(int), st));
+    k_check_rect<<<gb, 256, 0, st>>>(dets->alpha, dets->beta, n, excl.p + n, bad);
+    ctx->launches += 2;
     B2_CHECK_LAUNCH();
+    int64_t* pin = pinned_words(ctx);
+    B2_CUDA(cudaMemcpyAsync(pin, excl.p + n, 4, cudaMemcpyDeviceToHost, st));
+    B2_CUDA(cudaMemcpyAsync(pin + 1, bad, sizeof(int), cudaMemcpyDeviceToHost, st));
+    B2_CUDA(cudaStreamSynchronize(st));
+    nruns = *reinterpret_cast<const int32_t*>(pin);
+    const int hbad = *reinterpret_cast<const int*>(pin + 1);
+    rect = hbad == 0 && nruns > 0 && !getenv("B2CI_HBUILD_FORCE_SCAN");
+    mark("runs + shape test (sync A)");
   }
-  // run adjacency (count, scan, fill): distance <= 4 for the product path, <= 2 for the scan path
+  // run adjacency (count, scan, fill): distance <= 2 for the scan path
   auto build_adjacency = [&](int maxd) {
-    ScopedTimer t(ctx, "h_build.setup", true);
+    DeferredScope t(DT, "h_build.setup");
     DevBuf<int32_t> acnt(nruns);
     adj_ptr.alloc(nruns + 1);
     const unsigned ga = unsigned((int64_t(nruns) * 32 + 255) / 256);
@@ -987,54 +1016,45 @@ void hbuild_csr(b2ci_ctx* ctx, const b2ci_dets* dets, int64_t row_begin, int64_t
   };
 
   // ---- rectangular (FCI-shaped) lists: product enumeration, no beta scan
-  int64_t nb = 0;
-  bool rect = false;
-  if (nruns > 0 && n % nruns == 0 && !getenv("B2CI_HBUILD_FORCE_SCAN")) {
-    nb = n / nruns;
-    if (nb < (int64_t(1) << 29)) {
-      DevBuf<int> bad(1);
-      B2_CUDA(cudaMemsetAsync(bad, 0, sizeof(int), st));
-      k_check_rect<<<unsigned((n + 255) / 256), 256, 0, st>>>(dets->alpha, dets->beta, n, nb, bad);
-      ctx->launches++;
-      B2_CHECK_LAUNCH();
-      int hbad = 1;
-      B2_CUDA(cudaMemcpyAsync(&hbad, bad, sizeof(int), cudaMemcpyDeviceToHost, st));
-      B2_CUDA(cudaStreamSynchronize(st));
-      rect = hbad == 0;
-    }
-  }
+  const int64_t nb = rect ? n / nruns : 0;
   ctx->timers["h_build.rectangular"] = rect ? 1. : 0.;
-  build_adjacency(rect ? 4 : 2);
   if (rect) {
     DevBuf<int64_t> b2_ptr(nb + 1), b4_ptr(nb + 1);
     DevBuf<uint32_t> b2, b4;
+    const unsigned ga = unsigned((int64_t(nruns) * 32 + 255) / 256);
+    const unsigned gb = unsigned((nb * 32 + 255) / 256);
+    int64_t nadj_h = 0, nb2_h = 0, nb4_h = 0;
     {
-      ScopedTimer t(ctx, "h_build.setup", true);
-      const unsigned gb = unsigned((nb * 32 + 255) / 256);
-      DevBuf<int32_t> bc(nb);
-      for (int pass = 0; pass < 2; ++pass) {
-        const int maxd = pass == 0 ? 2 : 4;
-        DevBuf<int64_t>& ptr = pass == 0 ? b2_ptr : b4_ptr;
-        DevBuf<uint32_t>& lst = pass == 0 ? b2 : b4;
-        k_string_adjacency<false><<<gb, 256, 0, st>>>(dets->beta, int32_t(nb), maxd, 0, bc, nullptr, nullptr, nullptr);
-        ctx->launches++;
-        B2_CHECK_LAUNCH();
-        exclusive_scan_i32_to_i64(ctx, bc, ptr, nb);
-        int64_t tot = 0;
-        B2_CUDA(cudaMemcpyAsync(&tot, ptr.p + nb, 8, cudaMemcpyDeviceToHost, st));
-        B2_CUDA(cudaStreamSynchronize(st));
-        lst.alloc(tot > 0 ? tot : 1);
-        k_string_adjacency<true><<<gb, 256, 0, st>>>(dets->beta, int32_t(nb), maxd, 0, nullptr, nullptr, ptr, lst);
-        ctx->launches++;
-        B2_CHECK_LAUNCH();
-      }
+      // the three adjacency counts (alpha runs at distance <= 4, beta strings at <= 2 and <= 4)
+      // go out together and their totals come back in one synchronisation
+      DeferredScope t(DT, "h_build.setup");
+      DevBuf<int32_t> acnt(nruns), bc2(nb), bc4(nb);
+      adj_ptr.alloc(nruns + 1);
+      k_string_adjacency<false><<<ga, 256, 0, st>>>(run_alpha, nruns, 4, 1, acnt, nullptr, nullptr, nullptr);
+      k_string_adjacency<false><<<gb, 256, 0, st>>>(dets->beta, int32_t(nb), 2, 0, bc2, nullptr, nullptr, nullptr);
+      k_string_adjacency<false><<<gb, 256, 0, st>>>(dets->beta, int32_t(nb), 4, 0, bc4, nullptr, nullptr, nullptr);
+      ctx->launches += 3;
+      B2_CHECK_LAUNCH();
+      exclusive_scan_i32_to_i64(ctx, acnt, adj_ptr, nruns);
+      exclusive_scan_i32_to_i64(ctx, bc2, b2_ptr, nb);
+      exclusive_scan_i32_to_i64(ctx, bc4, b4_ptr, nb);
+      int64_t* pin = pinned_words(ctx);
+      B2_CUDA(cudaMemcpyAsync(pin, adj_ptr.p + nruns, 8, cudaMemcpyDeviceToHost, st));
+      B2_CUDA(cudaMemcpyAsync(pin + 1, b2_ptr.p + nb, 8, cudaMemcpyDeviceToHost, st));
+      B2_CUDA(cudaMemcpyAsync(pin + 2, b4_ptr.p + nb, 8, cudaMemcpyDeviceToHost, st));
+      B2_CUDA(cudaStreamSynchronize(st));
+      nadj_h = pin[0]; nb2_h = pin[1]; nb4_h = pin[2];
+      mark("adjacency counts (sync B)");
+      adj.alloc(nadj_h > 0 ? nadj_h : 1);
+      b2.alloc(nb2_h > 0 ? nb2_h : 1);
+      b4.alloc(nb4_h > 0 ? nb4_h : 1);
+      k_string_adjacency<true><<<ga, 256, 0, st>>>(run_alpha, nruns, 4, 1, nullptr, nullptr, adj_ptr, adj);
+      k_string_adjacency<true><<<gb, 256, 0, st>>>(dets->beta, int32_t(nb), 2, 0, nullptr, nullptr, b2_ptr, b2);
+      k_string_adjacency<true><<<gb, 256, 0, st>>>(dets->beta, int32_t(nb), 4, 0, nullptr, nullptr, b4_ptr, b4);
+      ctx->launches += 3;
+      B2_CHECK_LAUNCH();
     }
     // per-pair metadata (values of same-spin doubles, hole/particle/sign/leading sum of singles)
-    int64_t nadj_h = 0, nb2_h = 0, nb4_h = 0;
-    B2_CUDA(cudaMemcpyAsync(&nadj_h, adj_ptr.p + nruns, 8, cudaMemcpyDeviceToHost, st));
-    B2_CUDA(cudaMemcpyAsync(&nb2_h, b2_ptr.p + nb, 8, cudaMemcpyDeviceToHost, st));
-    B2_CUDA(cudaMemcpyAsync(&nb4_h, b4_ptr.p + nb, 8, cudaMemcpyDeviceToHost, st));
-    B2_CUDA(cudaStreamSynchronize(st));
     DevBuf<double> b4_val(nb4_h > 0 ? nb4_h : 1), b2_val(nb2_h > 0 ? nb2_h : 1);
     DevBuf<uint32_t> b2_meta(nb2_h > 0 ? nb2_h : 1);
     DevBuf<B2Rec> b2rec(nb2_h > 0 ? nb2_h : 1);
@@ -1043,15 +1063,13 @@ void hbuild_csr(b2ci_ctx* ctx, const b2ci_dets* dets, int64_t row_begin, int64_t
     DevBuf<ARec> crec;
     DevBuf<double> cval, slead, diag(nrows);
     DevBuf<uint32_t> smeta;
+    DevBuf<uint32_t> a_meta(nadj_h > 0 ? nadj_h : 1), b4_meta(nb4_h > 0 ? nb4_h : 1);
+    DevBuf<double> a_val(nadj_h > 0 ? nadj_h : 1);
+    DevBuf<int32_t> ecnt(nruns), scnt(nruns);
     {
-      ScopedTimer t(ctx, "h_build.setup", true);
+      DeferredScope t(DT, "h_build.setup");
       DevBuf<unsigned char> dead_ov(size_t(ctx->norb) * ctx->norb);
-      DevBuf<uint32_t> a_meta(nadj_h > 0 ? nadj_h : 1), b4_meta(nb4_h > 0 ? nb4_h : 1);
-      DevBuf<double> a_val(nadj_h > 0 ? nadj_h : 1);
-      DevBuf<int32_t> ecnt(nruns), scnt(nruns);
       const int nn = ctx->norb * ctx->norb;
-      const unsigned ga = unsigned((int64_t(nruns) * 32 + 255) / 256);
-      const unsigned gb = unsigned((nb * 32 + 255) / 256);
       k_dead_ov<<<(nn + 127) / 128, 128, 0, st>>>(ctx->ints, thr, dead_ov);
       k_pair_meta<<<ga, 256, 0, st>>>(ctx->ints, run_alpha, nruns, adj_ptr, adj, thr, dead_ov, a_meta, a_val);
       k_pair_meta<<<gb, 256, 0, st>>>(ctx->ints, dets->beta, int32_t(nb), b2_ptr, b2, thr, nullptr, b2_meta, b2_val);
@@ -1063,27 +1081,13 @@ void hbuild_csr(b2ci_ctx* ctx, const b2ci_dets* dets, int64_t row_begin, int64_t
       B2_CHECK_LAUNCH();
       exclusive_scan_i32_to_i64(ctx, ecnt, cptr, nruns);
       exclusive_scan_i32_to_i64(ctx, scnt, sptr, nruns);
-      int64_t ncadj = 0, nsing = 0;
-      B2_CUDA(cudaMemcpyAsync(&ncadj, cptr.p + nruns, 8, cudaMemcpyDeviceToHost, st));
-      B2_CUDA(cudaMemcpyAsync(&nsing, sptr.p + nruns, 8, cudaMemcpyDeviceToHost, st));
-      B2_CUDA(cudaStreamSynchronize(st));
-      crec.alloc(ncadj > 0 ? ncadj : 1);
-      cval.alloc(ncadj > 0 ? ncadj : 1);
-      slead.alloc(nsing > 0 ? nsing : 1);
-      smeta.alloc(nsing > 0 ? nsing : 1);
-      k_adj_compact<true><<<ga, 256, 0, st>>>(nruns, adj_ptr, adj, a_meta, a_val, nullptr, nullptr, nullptr, cptr,
-                                             crec, cval, sptr, slead, smeta);
-      ctx->launches++;
-      B2_CHECK_LAUNCH();
     }
     ProdArgs P;
     P.I = ctx->ints;
     P.run_alpha = run_alpha;
     P.tmpl_beta = dets->beta;
     P.cptr = cptr;
-    P.crec = crec;
-    P.cval = cval;
-    P.sptr = sptr; P.slead = slead; P.smeta = smeta;
+    P.sptr = sptr;
     P.run_cnt = run_cnt;
     P.b2_ptr = b2_ptr; P.b2rec = b2rec; P.b2_meta = b2_meta; P.b2_val = b2_val;
     P.b4_ptr = b4_ptr; P.b4 = b4; P.b4_val = b4_val;
@@ -1097,24 +1101,59 @@ void hbuild_csr(b2ci_ctx* ctx, const b2ci_dets* dets, int64_t row_begin, int64_t
     P.smem_a = (ctx->norb / 2) * (ctx->norb - ctx->norb / 2) + 1;
     P.smem_b = P.smem_a;
     P.rowptr = nullptr; P.colind = nullptr; P.nzval = nullptr;
+    P.crec = nullptr; P.cval = nullptr; P.slead = nullptr; P.smeta = nullptr;
     DevBuf<int64_t> slot_ptr(nrows + 1);
-    int64_t nslots = 0;
+    DevBuf<int32_t> struct_cnt(nrows);
+    int64_t nslots = 0, ncadj = 0, nsing = 0;
+    int32_t rc[4] = {0, 0, 0, 0};
+    int64_t bp[2] = {0, 0}, bq[2] = {0, 0};
     {
-      ScopedTimer t(ctx, "h_build.count");
-      DevBuf<int32_t> scnt(nrows);
-      P.row_cnt = scnt;
+      // structural row lengths and diagonal elements need only the run counts: they are queued
+      // behind the metadata kernels and everything the host must know comes back together
+      DeferredScope t(DT, "h_build.count");
+      P.row_cnt = struct_cnt;
       k_prod_struct_count<<<unsigned((nrows + 255) / 256), 256, 0, st>>>(P);
       k_row_diag<<<unsigned((nrows + 127) / 128), 128, 0, st>>>(P, diag);
       ctx->launches += 2;
       B2_CHECK_LAUNCH();
-      exclusive_scan_i32_to_i64(ctx, scnt, slot_ptr, nrows);
-      B2_CUDA(cudaMemcpyAsync(&nslots, slot_ptr.p + nrows, 8, cudaMemcpyDeviceToHost, st));
+      exclusive_scan_i32_to_i64(ctx, struct_cnt, slot_ptr, nrows);
+      int64_t* pin = pinned_words(ctx);
+      B2_CUDA(cudaMemcpyAsync(pin, slot_ptr.p + nrows, 8, cudaMemcpyDeviceToHost, st));
+      B2_CUDA(cudaMemcpyAsync(pin + 1, cptr.p + nruns, 8, cudaMemcpyDeviceToHost, st));
+      B2_CUDA(cudaMemcpyAsync(pin + 2, sptr.p + nruns, 8, cudaMemcpyDeviceToHost, st));
+      B2_CUDA(cudaMemcpyAsync(pin + 4, run_cnt.p, 16, cudaMemcpyDeviceToHost, st));
+      B2_CUDA(cudaMemcpyAsync(pin + 6, b2_ptr.p, 16, cudaMemcpyDeviceToHost, st));
+      B2_CUDA(cudaMemcpyAsync(pin + 8, b4_ptr.p, 16, cudaMemcpyDeviceToHost, st));
+      mark("metadata + count queued");
       B2_CUDA(cudaStreamSynchronize(st));
+      nslots = pin[0]; ncadj = pin[1]; nsing = pin[2];
+      memcpy(rc, pin + 4, 16); memcpy(bp, pin + 6, 16); memcpy(bq, pin + 8, 16);
+      mark("metadata + count (sync C)");
     }
-    DevBuf<int32_t> ci_s(nslots > 0 ? nslots : 1), kept(nrows);
-    DevBuf<double> nz_s(nslots > 0 ? nslots : 1);
+    crec.alloc(ncadj > 0 ? ncadj : 1);
+    cval.alloc(ncadj > 0 ? ncadj : 1);
+    slead.alloc(nsing > 0 ? nsing : 1);
+    smeta.alloc(nsing > 0 ? nsing : 1);
     {
-      ScopedTimer t(ctx, "h_build.fill");
+      DeferredScope t(DT, "h_build.setup");
+      k_adj_compact<true><<<ga, 256, 0, st>>>(nruns, adj_ptr, adj, a_meta, a_val, nullptr, nullptr, nullptr, cptr,
+                                             crec, cval, sptr, slead, smeta);
+      ctx->launches++;
+      B2_CHECK_LAUNCH();
+    }
+    P.crec = crec; P.cval = cval; P.slead = slead; P.smeta = smeta;
+    // structural slots: recycled through the context (a freed matrix or the slots of a previous
+    // thresholded build); a pool allocation of this size costs ~0.3 ms of host time
+    DevBuf<int32_t> ci_s, kept(nrows);
+    DevBuf<double> nz_s;
+    size_t ci_cap = 0, nz_cap = 0;
+    ci_s.p = static_cast<int32_t*>(big_alloc(ctx, 0, size_t(nslots > 0 ? nslots : 1) * sizeof(int32_t), &ci_cap));
+    ci_s.n = ci_cap / sizeof(int32_t);
+    nz_s.p = static_cast<double*>(big_alloc(ctx, 1, size_t(nslots > 0 ? nslots : 1) * sizeof(double), &nz_cap));
+    nz_s.n = nz_cap / sizeof(double);
+    mark("slot allocation");
+    {
+      DeferredScope t(DT, "h_build.fill");
       P.row_cnt = kept;
       P.rowptr = slot_ptr;
       P.colind = ci_s;
@@ -1122,12 +1161,6 @@ void hbuild_csr(b2ci_ctx* ctx, const b2ci_dets* dets, int64_t row_begin, int64_t
       // lanes per row: the group width that wastes the fewest lane slots on this list shape
       int G = 32;
       {
-        int32_t rc[4] = {0, 0, 0, 0};
-        int64_t bp[2] = {0, 0}, bq[2] = {0, 0};
-        B2_CUDA(cudaMemcpyAsync(rc, run_cnt.p, 16, cudaMemcpyDeviceToHost, st));
-        B2_CUDA(cudaMemcpyAsync(bp, b2_ptr.p, 16, cudaMemcpyDeviceToHost, st));
-        B2_CUDA(cudaMemcpyAsync(bq, b4_ptr.p, 16, cudaMemcpyDeviceToHost, st));
-        B2_CUDA(cudaStreamSynchronize(st));
         const double l2 = double(bp[1] - bp[0]), l4 = double(bq[1] - bq[0]);
         const double nunit_runs = std::min<double>(rc[2], rc[0] + rc[1] + 1);
         const double unit_len = nunit_runs > 0 ? rc[2] / nunit_runs : 0.;
@@ -1184,15 +1217,21 @@ void hbuild_csr(b2ci_ctx* ctx, const b2ci_dets* dets, int64_t row_begin, int64_t
       ctx->launches++;
       B2_CHECK_LAUNCH();
     }
+    mark("fill queued");
     int64_t nnz = nslots;
     if (thr > 0.0) {
       // threshold_parallel equivalent: rows were written compacted inside their structural
       // slots; when something was dropped, pack the rows (csr_matrix.hpp:317-370)
-      ScopedTimer t(ctx, "h_build.thresh");
+      size_t tt = DT.start("h_build.thresh");
       exclusive_scan_i32_to_i64(ctx, kept, rowptr, nrows);
-      B2_CUDA(cudaMemcpyAsync(&nnz, rowptr.p + nrows, 8, cudaMemcpyDeviceToHost, st));
+      int64_t* pin = pinned_words(ctx);
+      B2_CUDA(cudaMemcpyAsync(pin, rowptr.p + nrows, 8, cudaMemcpyDeviceToHost, st));
+      DT.stop(tt);
       B2_CUDA(cudaStreamSynchronize(st));
+      nnz = pin[0];
+      mark("fill + nnz (sync E)");
       if (nnz != nslots) {
+        DeferredScope t(DT, "h_build.thresh");
         DevBuf<int32_t> ci_f(nnz > 0 ? nnz : 1);
         DevBuf<double> nz_f(nnz > 0 ? nnz : 1);
         k_compact_rows<<<unsigned((nrows * 32 + ROW_WARPS * 32 - 1) / (ROW_WARPS * 32)), ROW_WARPS * 32, 0, st>>>(
@@ -1200,19 +1239,28 @@ void hbuild_csr(b2ci_ctx* ctx, const b2ci_dets* dets, int64_t row_begin, int64_t
         ctx->launches++;
         B2_CHECK_LAUNCH();
         B2_CUDA(cudaStreamSynchronize(st));
+        // the structural arrays stay with the context for the next build
+        big_release(ctx, 0, ci_s.take(), ci_cap);
+        big_release(ctx, 1, nz_s.take(), nz_cap);
+        ci_cap = nz_cap = 0;  // the packed arrays are ordinary pool allocations
         ci_s = std::move(ci_f);
         nz_s = std::move(nz_f);
       }
     } else {
       rowptr = std::move(slot_ptr);
+      B2_CUDA(cudaStreamSynchronize(st));
     }
-    B2_CUDA(cudaStreamSynchronize(st));
+    DT.resolve();
+    mark("compaction + timers");
     out->nnz = nnz;
     out->rowptr = rowptr.take();
     out->colind = ci_s.take();
     out->nzval = nz_s.take();
+    out->colind_cap = ci_cap;
+    out->nzval_cap = nz_cap;
     return;
   }
+  build_adjacency(2);
 
   // ---- general lists: determinants grouped by beta string (stable radix sort of the indices)
   DevBuf<int32_t> bgrp_of(n);
