@@ -162,6 +162,19 @@ int b2ci_asci_candidates(b2ci_ctx* ctx, const b2ci_asci_search_opts* opts,
 int b2ci_asci_pt2(b2ci_ctx* ctx, const uint64_t* det_words, int words_per_det, const double* coeffs,
                   int64_t ndets, double E_asci, double pt2_tol, double* ept2, int64_t* npt2);
 
+/* ---- reduced density matrices of sum_i C_i |D_i>:
+ * HamiltonianGenerator::form_rdms / form_rdms_spin_dep with bra == ket, as the adapters call them
+ * (cpp/src/qdk/chemistry/algorithms/microsoft/macis_base.hpp:166-197, macis_pmc.cpp:128-148;
+ * external/macis/include/macis/hamiltonian_generator/sorted_double_loop.hpp:512-760; rules of
+ * external/macis/include/macis/util/rdms.hpp). C: HOST, one coefficient per determinant of
+ * `dets`. Outputs: HOST, column-major n*n and n^4 ((p,q,r,s) at p + q n + r n^2 + s n^3), any
+ * may be NULL, ACCUMULATED INTO as the reference does (zero them first). The orbital count is
+ * that of the uploaded integrals. With a communicator the pairs are sharded by rows and the
+ * matrices all-reduced (every rank gets the result). */
+int b2ci_form_rdms(b2ci_ctx* ctx, const b2ci_dets* dets, const double* C, double* ordm, double* trdm);
+int b2ci_form_rdms_spin_dep(b2ci_ctx* ctx, const b2ci_dets* dets, const double* C, double* ordm_aa,
+                            double* ordm_bb, double* trdm_aaaa, double* trdm_bbbb, double* trdm_aabb);
+
 /* ---- host-side evaluation of the SAME device functions (they are __host__ __device__):
  * lets CPU-only tests check the Slater-Condon code against the oracle without a GPU. */
 double b2ci_host_matrix_element(int norb, const double* T, const double* V, uint64_t bra_alpha,

@@ -68,6 +68,8 @@ def lib():
         L.op_asci_search.argtypes = [vp, vp, vp, vp, vp, i64, dbl, vp, vp, i64, vp]
         L.op_asci_candidates.restype = i64
         L.op_asci_candidates.argtypes = [vp, vp, vp, vp, vp, i64, dbl, vp, vp, vp, vp]
+        L.op_form_rdms.argtypes = [i32, vp, vp, i64, vp, vp, vp]
+        L.op_form_rdms_spin_dep.argtypes = [i32, vp, vp, i64, vp, vp, vp, vp, vp, vp]
         L.op_num_threads.restype = i32
         _lib = L
     return _lib
@@ -188,6 +190,25 @@ class Ham:
                 cap = -r
                 continue
             return oa[:r].copy(), ob[:r].copy(), stats
+
+
+def form_rdms(norb, alpha, beta, C, spin_dep=False, one=True, two=True):
+    """SortedDoubleLoopHamiltonianGenerator::form_rdms / form_rdms_spin_dep for bra == ket
+    (sorted_double_loop.hpp:512-760; contribution rules util/rdms.hpp). Returns Fortran-ordered
+    (n, n) / (n, n, n, n) arrays: (ordm, trdm) or (aa, bb, aaaa, bbbb, aabb)."""
+    a, b = _u64(alpha), _u64(beta)
+    c = np.ascontiguousarray(C, dtype=np.float64)
+    n = int(norb)
+    mk1 = lambda: np.zeros(n * n) if one else None
+    mk2 = lambda: np.zeros(n ** 4) if two else None
+    sh = lambda x, k: None if x is None else x.reshape((n,) * k, order="F")
+    if spin_dep:
+        o1, o2, t1, t2, t3 = mk1(), mk1(), mk2(), mk2(), mk2()
+        lib().op_form_rdms_spin_dep(n, _p(a), _p(b), a.size, _p(c), _p(o1), _p(o2), _p(t1), _p(t2), _p(t3))
+        return sh(o1, 2), sh(o2, 2), sh(t1, 4), sh(t2, 4), sh(t3, 4)
+    o1, t1 = mk1(), mk2()
+    lib().op_form_rdms(n, _p(a), _p(b), a.size, _p(c), _p(o1), _p(t1))
+    return sh(o1, 2), sh(t1, 4)
 
 
 def spmv(rowptr, colind, nzval, x):

@@ -716,3 +716,224 @@ int64_t op_asci_search(const op_ham* h, const op_asci_search_opts* o, const uint
   free(score); free(v.p);
   return w;
 }
+
+
+/* ---------------------------------------------------------------------------------------
+ * Reduced density matrices (util/rdms.hpp, symm = true everywhere: the generators call the
+ * contribution routines once per unordered pair, bra = the lower index). */
+#define T4(t, n, p, q, r, s_) (t)[(size_t)(p) + (size_t)(q) * (n) + (size_t)(r) * (n) * (n) + (size_t)(s_) * (n) * (n) * (n)]
+
+/* rdm_contributions_4<true> (rdms.hpp:36-65) */
+static void rdm4(int n, uint64_t bra, uint64_t ket, uint64_t ex, double val, double* trdm) {
+  if (!trdm) return;
+  unsigned o1, v1, o2, v2;
+  double sign;
+  dx_sign_indices(bra, ket, ex, &o1, &v1, &o2, &v2, &sign);
+  val *= sign * 0.5;
+  T4(trdm, n, v1, o1, v2, o2) += val;
+  T4(trdm, n, v2, o1, v1, o2) -= val;
+  T4(trdm, n, v1, o2, v2, o1) -= val;
+  T4(trdm, n, v2, o2, v1, o1) += val;
+  T4(trdm, n, o2, v2, o1, v1) += val;
+  T4(trdm, n, o2, v1, o1, v2) -= val;
+  T4(trdm, n, o1, v2, o2, v1) -= val;
+  T4(trdm, n, o1, v1, o2, v2) += val;
+}
+/* rdm_contributions_22<true> (rdms.hpp:85-113) */
+static void rdm22(int n, uint64_t bra_a, uint64_t ket_a, uint64_t ex_a, uint64_t bra_b,
+                  uint64_t ket_b, uint64_t ex_b, double val, double* trdm) {
+  if (!trdm) return;
+  unsigned o1, v1, o2, v2;
+  double sa, sb;
+  sx_sign_indices(bra_a, ket_a, ex_a, &o1, &v1, &sa);
+  sx_sign_indices(bra_b, ket_b, ex_b, &o2, &v2, &sb);
+  val *= sa * sb * 0.5;
+  T4(trdm, n, v1, o1, v2, o2) += val;
+  T4(trdm, n, v2, o2, v1, o1) += val;
+  T4(trdm, n, o2, v2, o1, v1) += val;
+  T4(trdm, n, o1, v1, o2, v2) += val;
+}
+/* rdm_contributions_22_spin_dep<true> (rdms.hpp:134-157): NB the roles -- (o2,v2) from the
+ * alpha strings, (o1,v1) from the beta strings */
+static void rdm22_sd(int n, uint64_t bra_a, uint64_t ket_a, uint64_t ex_a, uint64_t bra_b,
+                     uint64_t ket_b, uint64_t ex_b, double val, double* aabb) {
+  if (!aabb) return;
+  unsigned o1, v1, o2, v2;
+  double sa, sb;
+  sx_sign_indices(bra_a, ket_a, ex_a, &o2, &v2, &sb);
+  sx_sign_indices(bra_b, ket_b, ex_b, &o1, &v1, &sa);
+  val *= sa * sb * 0.5;
+  T4(aabb, n, v1, o1, v2, o2) += val;
+  T4(aabb, n, o1, v1, o2, v2) += val;
+}
+/* rdm_contributions_2<true> (rdms.hpp:177-244): occ_same = bra occupation of the excited spin */
+static void rdm2(int n, uint64_t bra, uint64_t ket, uint64_t ex, const unsigned* occ_same, int ns,
+                 const unsigned* occ_othr, int no, double val, double* ordm, double* trdm) {
+  unsigned o1, v1;
+  double sign;
+  sx_sign_indices(bra, ket, ex, &o1, &v1, &sign);
+  if (ordm) {
+    ordm[v1 + (size_t)o1 * n] += sign * val;
+    ordm[o1 + (size_t)v1 * n] += sign * val;
+  }
+  if (!trdm) return;
+  val *= sign * 0.5;
+  for (int i = 0; i < ns; ++i) {
+    const unsigned p = occ_same[i];
+    T4(trdm, n, v1, o1, p, p) += val;
+    T4(trdm, n, p, p, v1, o1) += val;
+    T4(trdm, n, v1, p, p, o1) -= val;
+    T4(trdm, n, p, o1, v1, p) -= val;
+  }
+  for (int i = 0; i < ns; ++i) {
+    const unsigned p = occ_same[i];
+    T4(trdm, n, p, p, o1, v1) += val;
+    T4(trdm, n, o1, v1, p, p) += val;
+    T4(trdm, n, o1, p, p, v1) -= val;
+    T4(trdm, n, p, v1, o1, p) -= val;
+  }
+  for (int i = 0; i < no; ++i) {
+    const unsigned p = occ_othr[i];
+    T4(trdm, n, v1, o1, p, p) += val;
+    T4(trdm, n, p, p, v1, o1) += val;
+  }
+  for (int i = 0; i < no; ++i) {
+    const unsigned p = occ_othr[i];
+    T4(trdm, n, o1, v1, p, p) += val;
+    T4(trdm, n, p, p, o1, v1) += val;
+  }
+}
+/* rdm_contributions_2_spin_dep<true, transpose> (rdms.hpp:267-335) */
+static void rdm2_sd(int n, int transpose, uint64_t bra, uint64_t ket, uint64_t ex,
+                    const unsigned* occ_ss, int ns, const unsigned* occ_os, int no, double val,
+                    double* ordm_ss, double* trdm_ss, double* trdm_os) {
+  unsigned o1, v1;
+  double sign;
+  sx_sign_indices(bra, ket, ex, &o1, &v1, &sign);
+  if (ordm_ss) {
+    ordm_ss[v1 + (size_t)o1 * n] += sign * val;
+    ordm_ss[o1 + (size_t)v1 * n] += sign * val;
+  }
+  val *= sign * 0.5;
+  if (trdm_ss) {
+    for (int i = 0; i < ns; ++i) {
+      const unsigned p = occ_ss[i];
+      T4(trdm_ss, n, v1, o1, p, p) += val;
+      T4(trdm_ss, n, p, p, v1, o1) += val;
+      T4(trdm_ss, n, v1, p, p, o1) -= val;
+      T4(trdm_ss, n, p, o1, v1, p) -= val;
+    }
+    for (int i = 0; i < ns; ++i) {
+      const unsigned p = occ_ss[i];
+      T4(trdm_ss, n, p, p, o1, v1) += val;
+      T4(trdm_ss, n, o1, v1, p, p) += val;
+      T4(trdm_ss, n, o1, p, p, v1) -= val;
+      T4(trdm_ss, n, p, v1, o1, p) -= val;
+    }
+  }
+  if (trdm_os) {
+    for (int i = 0; i < no; ++i) {
+      const unsigned p = occ_os[i];
+      if (transpose) T4(trdm_os, n, v1, o1, p, p) += val;
+      else T4(trdm_os, n, p, p, v1, o1) += val;
+    }
+    for (int i = 0; i < no; ++i) {
+      const unsigned p = occ_os[i];
+      if (transpose) T4(trdm_os, n, o1, v1, p, p) += val;
+      else T4(trdm_os, n, p, p, o1, v1) += val;
+    }
+  }
+}
+/* rdm_contributions_diag (rdms.hpp:352-394) */
+static void rdm_diag(int n, const unsigned* oa, int na, const unsigned* ob, int nb, double val,
+                     double* ordm, double* trdm) {
+  if (ordm) {
+    for (int i = 0; i < na; ++i) ordm[oa[i] + (size_t)oa[i] * n] += val;
+    for (int i = 0; i < nb; ++i) ordm[ob[i] + (size_t)ob[i] * n] += val;
+  }
+  if (!trdm) return;
+  val *= 0.5;
+  for (int j = 0; j < na; ++j)
+    for (int i = 0; i < na; ++i) {
+      T4(trdm, n, oa[i], oa[i], oa[j], oa[j]) += val;
+      T4(trdm, n, oa[i], oa[j], oa[j], oa[i]) -= val;
+    }
+  for (int j = 0; j < nb; ++j)
+    for (int i = 0; i < nb; ++i) {
+      T4(trdm, n, ob[i], ob[i], ob[j], ob[j]) += val;
+      T4(trdm, n, ob[i], ob[j], ob[j], ob[i]) -= val;
+    }
+  for (int j = 0; j < nb; ++j)
+    for (int i = 0; i < na; ++i) {
+      T4(trdm, n, oa[i], oa[i], ob[j], ob[j]) += val;
+      T4(trdm, n, ob[j], ob[j], oa[i], oa[i]) += val;
+    }
+}
+/* rdm_contributions_diag_spin_dep (rdms.hpp:415-460) */
+static void rdm_diag_sd(int n, const unsigned* oa, int na, const unsigned* ob, int nb, double val,
+                        double* ordm_aa, double* ordm_bb, double* aaaa, double* bbbb, double* aabb) {
+  if (ordm_aa) for (int i = 0; i < na; ++i) ordm_aa[oa[i] + (size_t)oa[i] * n] += val;
+  if (ordm_bb) for (int i = 0; i < nb; ++i) ordm_bb[ob[i] + (size_t)ob[i] * n] += val;
+  val *= 0.5;
+  if (aaaa)
+    for (int j = 0; j < na; ++j)
+      for (int i = 0; i < na; ++i) {
+        T4(aaaa, n, oa[i], oa[i], oa[j], oa[j]) += val;
+        T4(aaaa, n, oa[i], oa[j], oa[j], oa[i]) -= val;
+      }
+  if (bbbb)
+    for (int j = 0; j < nb; ++j)
+      for (int i = 0; i < nb; ++i) {
+        T4(bbbb, n, ob[i], ob[i], ob[j], ob[j]) += val;
+        T4(bbbb, n, ob[i], ob[j], ob[j], ob[i]) -= val;
+      }
+  if (aabb)
+    for (int j = 0; j < nb; ++j)
+      for (int i = 0; i < na; ++i) T4(aabb, n, ob[j], ob[j], oa[i], oa[i]) += val;
+}
+
+/* the pair loop of form_rdms(_spin_dep) for bra == ket (sorted_double_loop.hpp:560-620,
+ * 682-744): pairs i <= j, alpha-empty determinants skipped, popcount filter, |C_i C_j| > 1e-16 */
+static void rdm_pairs(int norb, const uint64_t* alpha, const uint64_t* beta, int64_t n,
+                      const double* C, int spin_dep, double* o1, double* o2, double* t1,
+                      double* t2, double* t3) {
+  unsigned oa[64], ob[64];
+  for (int64_t i = 0; i < n; ++i) {
+    const uint64_t ba = alpha[i], bb = beta[i];
+    if (!ba) continue;
+    const int na = occ_list(ba, oa), nb = occ_list(bb, ob);
+    for (int64_t j = i; j < n; ++j) {
+      const uint64_t ka = alpha[j], kb = beta[j];
+      if (!ka) continue;
+      const uint64_t exa = ba ^ ka, exb = bb ^ kb;
+      const int ca = popc(exa), cb = popc(exb);
+      if (ca + cb > 4) continue;
+      const double val = C[i] * C[j];
+      if (!(fabs(val) > 1e-16)) continue;
+      if (!spin_dep) {
+        if (ca == 4) rdm4(norb, ba, ka, exa, val, t1);
+        else if (cb == 4) rdm4(norb, bb, kb, exb, val, t1);
+        else if (ca == 2 && cb == 2) rdm22(norb, ba, ka, exa, bb, kb, exb, val, t1);
+        else if (ca == 2) rdm2(norb, ba, ka, exa, oa, na, ob, nb, val, o1, t1);
+        else if (cb == 2) rdm2(norb, bb, kb, exb, ob, nb, oa, na, val, o1, t1);
+        else rdm_diag(norb, oa, na, ob, nb, val, o1, t1);
+      } else {
+        if (ca == 4) rdm4(norb, ba, ka, exa, val, t1);
+        else if (cb == 4) rdm4(norb, bb, kb, exb, val, t2);
+        else if (ca == 2 && cb == 2) rdm22_sd(norb, ba, ka, exa, bb, kb, exb, val, t3);
+        else if (ca == 2) rdm2_sd(norb, 0, ba, ka, exa, oa, na, ob, nb, val, o1, t1, t3);
+        else if (cb == 2) rdm2_sd(norb, 1, bb, kb, exb, ob, nb, oa, na, val, o2, t2, t3);
+        else rdm_diag_sd(norb, oa, na, ob, nb, val, o1, o2, t1, t2, t3);
+      }
+    }
+  }
+}
+void op_form_rdms(int norb, const uint64_t* alpha, const uint64_t* beta, int64_t n,
+                  const double* C, double* ordm, double* trdm) {
+  rdm_pairs(norb, alpha, beta, n, C, 0, ordm, NULL, trdm, NULL, NULL);
+}
+void op_form_rdms_spin_dep(int norb, const uint64_t* alpha, const uint64_t* beta, int64_t n,
+                           const double* C, double* ordm_aa, double* ordm_bb,
+                           double* trdm_aaaa, double* trdm_bbbb, double* trdm_aabb) {
+  rdm_pairs(norb, alpha, beta, n, C, 1, ordm_aa, ordm_bb, trdm_aaaa, trdm_bbbb, trdm_aabb);
+}

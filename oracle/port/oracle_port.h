@@ -84,6 +84,18 @@ int64_t op_asci_candidates(const op_ham* h, const op_asci_search_opts* o,
                            uint64_t* out_alpha, uint64_t* out_beta, double* out_cmatel,
                            double* out_hdiag);
 
+/* Reduced density matrices of sum_i C_i |D_i> (SortedDoubleLoopHamiltonianGenerator::
+ * form_rdms / form_rdms_spin_dep, sorted_double_loop.hpp:512-760, with the symmetric
+ * bra == ket case; contribution rules of util/rdms.hpp). Pairs (i <= j) with
+ * |C_i C_j| > 1e-16 contribute. ordm: n*n column-major; trdm: n^4 with
+ * (p,q,r,s) at p + q n + r n^2 + s n^3. Outputs are ACCUMULATED INTO (caller zeroes);
+ * any output may be NULL. */
+void op_form_rdms(int norb, const uint64_t* alpha, const uint64_t* beta, int64_t n,
+                  const double* C, double* ordm, double* trdm);
+void op_form_rdms_spin_dep(int norb, const uint64_t* alpha, const uint64_t* beta, int64_t n,
+                           const double* C, double* ordm_aa, double* ordm_bb,
+                           double* trdm_aaaa, double* trdm_bbbb, double* trdm_aabb);
+
 int op_num_threads(void);
 
 #ifdef __cplusplus

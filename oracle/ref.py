@@ -42,6 +42,7 @@ def lib():
         L.ref_hamgen_intermediates.argtypes = [vp, vp, vp]
         L.ref_matrix_element.restype = dbl
         L.ref_matrix_element.argtypes = [vp, vp, vp]
+        L.ref_form_rdms.argtypes = [vp, i32, vp, i64, vp, i32, vp, vp, vp, vp, vp]
         L.ref_hbuild.restype = vp
         L.ref_hbuild.argtypes = [vp, i32, vp, i64, vp, i64, dbl, vp]
         L.ref_csr_from_arrays.restype = vp
@@ -236,6 +237,28 @@ class HamGen:
         if not h:
             raise RuntimeError(lib().ref_last_error().decode())
         return Csr(h), sec.value
+
+    def form_rdms(self, dets: np.ndarray, C: np.ndarray, spin_dep: bool = False,
+                  generator: str = "sdl", one: bool = True, two: bool = True):
+        """form_rdms -> (ordm, trdm); form_rdms_spin_dep -> (aa, bb, aaaa, bbbb, aabb).
+        Matrices are (n, n) / (n, n, n, n) Fortran-ordered views of the reference's buffers."""
+        d = np.ascontiguousarray(dets, dtype=np.uint64)
+        c = np.ascontiguousarray(C, dtype=np.float64)
+        n = self.norb
+        mk1 = lambda: np.zeros(n * n) if one else None
+        mk2 = lambda: np.zeros(n ** 4) if two else None
+        if spin_dep:
+            o1, o2, t1, t2, t3 = mk1(), mk1(), mk2(), mk2(), mk2()
+        else:
+            o1, o2, t1, t2, t3 = mk1(), None, mk2(), None, None
+        rc = lib().ref_form_rdms(self.h, 1 if generator == "double_loop" else 0, _p(d), c.size, _p(c),
+                                 1 if spin_dep else 0, _p(o1), _p(o2), _p(t1), _p(t2), _p(t3))
+        if rc:
+            raise RuntimeError(lib().ref_last_error().decode())
+        sh = lambda a, k: None if a is None else a.reshape((n,) * k, order="F")
+        if spin_dep:
+            return sh(o1, 2), sh(o2, 2), sh(t1, 4), sh(t2, 4), sh(t3, 4)
+        return sh(o1, 2), sh(t1, 4)
 
     def selected_ci_diag(self, dets: np.ndarray, h_el_tol: float, max_m: int,
                          res_tol: float, c0: Optional[np.ndarray] = None):

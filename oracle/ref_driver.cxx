@@ -193,6 +193,24 @@ csr_t* hbuild_impl(HamGenBase* b, int which, const uint64_t* bra, int64_t nbra,
       bd.begin(), bd.end(), kd.begin(), kd.end(), hg->gen(which), thresh));
 }
 
+// form_rdms / form_rdms_spin_dep of the chosen generator, bra == ket
+// (sorted_double_loop.hpp:512-760, double_loop.hpp); NULL outputs are skipped
+template <size_t N>
+void rdm_impl(HamGenBase* b, int which, const uint64_t* dets, int64_t n, const double* C, int spin_dep,
+              double* o1, double* o2, double* t1, double* t2, double* t3) {
+  auto* hg = static_cast<HamGen<N>*>(b);
+  auto d = dets_in<N>(dets, n);
+  std::vector<double> c(C, C + n);
+  const size_t no = b->norb;
+  auto ms = [&](double* p) { return macis::matrix_span<double>(p, no, no); };
+  auto rs = [&](double* p) { return macis::rank4_span<double>(p, no, no, no, no); };
+  if (spin_dep)
+    hg->gen(which).form_rdms_spin_dep(d.begin(), d.end(), d.begin(), d.end(), c.data(), ms(o1), ms(o2),
+                                      rs(t1), rs(t2), rs(t3));
+  else
+    hg->gen(which).form_rdms(d.begin(), d.end(), d.begin(), d.end(), c.data(), ms(o1), rs(t1));
+}
+
 template <size_t N>
 double sci_diag_impl(HamGenBase* b, const uint64_t* dets, int64_t n, double h_el_tol,
                      int64_t max_m, double res_tol, double* C) {
@@ -335,6 +353,16 @@ void* ref_hbuild(void* h, int which, const uint64_t* bra, int64_t nbra,
   if (seconds) *seconds = std::chrono::duration<double>(t1 - t0).count();
   return (void*)m;
   CATCH(nullptr)
+}
+int ref_form_rdms(void* h, int which, const uint64_t* dets, int64_t n, const double* C, int spin_dep,
+                  double* o1, double* o2, double* t1, double* t2, double* t3) {
+  auto* b = static_cast<HamGenBase*>(h);
+  quiet_loggers(0);
+  TRY
+  if (b->nbits == 64) rdm_impl<64>(b, which, dets, n, C, spin_dep, o1, o2, t1, t2, t3);
+  else rdm_impl<128>(b, which, dets, n, C, spin_dep, o1, o2, t1, t2, t3);
+  return 0;
+  CATCH(1)
 }
 // wrap caller arrays as a reference csr_matrix
 // (python/src/pybind11/algorithms/davidson_solver.cpp:60-80)

@@ -78,6 +78,8 @@ def lib():
     L.b2ci_asci_search.argtypes = [vp, vp, vp, i32, vp, i64, dbl, vp, i64, pi64, vp]
     L.b2ci_asci_candidates.argtypes = [vp, vp, vp, i32, vp, i64, dbl, vp, vp, vp, pi64]
     L.b2ci_asci_pt2.argtypes = [vp, vp, i32, vp, i64, dbl, dbl, C.POINTER(dbl), pi64]
+    L.b2ci_form_rdms.argtypes = [vp, vp, vp, vp, vp]
+    L.b2ci_form_rdms_spin_dep.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp]
     L.b2ci_host_matrix_element.restype = dbl
     L.b2ci_host_matrix_element.argtypes = [i32, vp, vp, u64, u64, u64, u64]
     L.b2ci_host_sym_eig_lower.argtypes = [i32, vp, i32, vp]

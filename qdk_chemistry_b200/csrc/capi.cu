@@ -34,6 +34,9 @@ int asci_search(b2ci_ctx* ctx, const b2ci_asci_search_opts* o, const uint64_t* c
                 int64_t* n_out, double* stats, uint64_t* cand_words, double* cand_cm, double* cand_hd,
                 int64_t* cand_n, bool candidates_only, double* pt2_out = nullptr);
 
+void form_rdms(b2ci_ctx* ctx, const b2ci_dets* dets, const double* C_host, bool spin_dep, double* o1,
+               double* o2, double* t1, double* t2, double* t3);
+
 namespace {
 __global__ void k_i32_to_i64(const int32_t* __restrict__ in, int64_t n, int64_t* __restrict__ out) {
   const int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
@@ -404,6 +407,20 @@ int b2ci_asci_pt2(b2ci_ctx* ctx, const uint64_t* det_words, int wpd, const doubl
               nullptr, nullptr, false, acc);
   *ept2 = acc[0];
   if (npt2) *npt2 = int64_t(acc[1]);
+  return 0;
+  B2_CATCH
+}
+
+int b2ci_form_rdms(b2ci_ctx* ctx, const b2ci_dets* dets, const double* C, double* ordm, double* trdm) {
+  B2_TRY_CTX(ctx)
+  form_rdms(ctx, dets, C, false, ordm, nullptr, trdm, nullptr, nullptr);
+  return 0;
+  B2_CATCH
+}
+int b2ci_form_rdms_spin_dep(b2ci_ctx* ctx, const b2ci_dets* dets, const double* C, double* ordm_aa,
+                            double* ordm_bb, double* trdm_aaaa, double* trdm_bbbb, double* trdm_aabb) {
+  B2_TRY_CTX(ctx)
+  form_rdms(ctx, dets, C, true, ordm_aa, ordm_bb, trdm_aaaa, trdm_bbbb, trdm_aabb);
   return 0;
   B2_CATCH
 }

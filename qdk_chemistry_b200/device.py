@@ -157,6 +157,25 @@ class Context:
         return words, cm, hd
 
 
+    def form_rdms(self, dets: "DetList", C: np.ndarray, spin_dep: bool = False, one: bool = True,
+                  two: bool = True):
+        """form_rdms -> (ordm, trdm); form_rdms_spin_dep -> (aa, bb, aaaa, bbbb, aabb); Fortran-ordered
+        (n, n) / (n, n, n, n) arrays, None where not requested. n = orbitals of the uploaded integrals."""
+        c = np.ascontiguousarray(C, dtype=np.float64)
+        if c.size != len(dets):
+            raise ValueError("one coefficient per determinant")
+        n = self.norb
+        mk1 = lambda: np.zeros(n * n) if one else None
+        mk2 = lambda: np.zeros(n ** 4) if two else None
+        sh = lambda x, k: None if x is None else x.reshape((n,) * k, order="F")
+        if spin_dep:
+            o1, o2, t1, t2, t3 = mk1(), mk1(), mk2(), mk2(), mk2()
+            check(lib().b2ci_form_rdms_spin_dep(self.h, dets.h, _p(c), _p(o1), _p(o2), _p(t1), _p(t2), _p(t3)))
+            return sh(o1, 2), sh(o2, 2), sh(t1, 4), sh(t2, 4), sh(t3, 4)
+        o1, t1 = mk1(), mk2()
+        check(lib().b2ci_form_rdms(self.h, dets.h, _p(c), _p(o1), _p(t1)))
+        return sh(o1, 2), sh(t1, 4)
+
     def asci_pt2(self, det_words, coeffs, E_asci: float, pt2_tol: float = 1e-16,
                  words_per_det: int = 1):
         """macis::asci_pt2_constraint (asci/pt2.hpp): (EPT2, number of external determinants).

@@ -18,6 +18,7 @@
 #include <stdexcept>
 #include <string>
 #include <variant>
+#include <tuple>
 #include <vector>
 
 namespace qdk_b200::data {
@@ -196,10 +197,31 @@ class Wavefunction {
   // <this|other> over the determinants both hold
   double overlap(const Wavefunction& other) const;
 
+  // ---- reduced density matrices over the active orbitals, as the reference's containers hold
+  // them (cpp/include/qdk/chemistry/data/wavefunction.hpp:338-370,556-577): matrices n*n
+  // column-major, two-body tensors n^4 with (p,q,r,s) at p + q n + r n^2 + s n^3.
+  // Spin-dependent set (macis_base.hpp:199-215; the two-body blocks carry the adapter's factor 2).
+  void set_rdms_spin_dependent(std::vector<double> one_aa, std::vector<double> one_bb, std::vector<double> two_aaaa,
+                               std::vector<double> two_aabb, std::vector<double> two_bbbb);
+  // Spin-traced set (macis_pmc.cpp:128-160)
+  void set_rdms_spin_traced(std::vector<double> one, std::vector<double> two);
+  bool has_one_rdm_spin_dependent() const { return !one_aa_.empty(); }
+  bool has_two_rdm_spin_dependent() const { return !two_aaaa_.empty(); }
+  bool has_one_rdm_spin_traced() const { return !one_st_.empty() || has_one_rdm_spin_dependent(); }
+  bool has_two_rdm_spin_traced() const { return !two_st_.empty() || has_two_rdm_spin_dependent(); }
+  // (aa, bb)
+  std::pair<std::vector<double>, std::vector<double>> get_active_one_rdm_spin_dependent() const;
+  // (aaaa, aabb, bbbb)
+  std::tuple<std::vector<double>, std::vector<double>, std::vector<double>> get_active_two_rdm_spin_dependent() const;
+  // stored, or derived: aa + bb;  aaaa + bbbb + aabb + aabb^T(pq<->rs)  (wavefunction.cpp:255-340)
+  std::vector<double> get_active_one_rdm_spin_traced() const;
+  std::vector<double> get_active_two_rdm_spin_traced() const;
+
  private:
   std::vector<double> coeffs_;
   std::vector<Configuration> dets_;
   size_t norb_;
+  std::vector<double> one_aa_, one_bb_, two_aaaa_, two_aabb_, two_bbbb_, one_st_, two_st_;
 };
 
 }  // namespace qdk_b200::data

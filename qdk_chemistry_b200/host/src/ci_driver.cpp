@@ -132,11 +132,11 @@ AsciSettings get_asci_settings(const data::Settings& s) {  // macis_base.cpp:47-
 }
 
 void reject_unsupported_outputs(const data::Settings& s) {
-  for (const char* k : {"calculate_one_rdm", "calculate_two_rdm", "calculate_single_orbital_entropies",
-                        "calculate_two_orbital_entropies", "calculate_mutual_information"})
+  for (const char* k : {"calculate_single_orbital_entropies", "calculate_two_orbital_entropies",
+                        "calculate_mutual_information"})
     if (s.get<bool>(k))
       throw std::runtime_error(std::string("setting '") + k +
-                               "' is not available: RDM / entropy builders are outside the hot path "
+                               "' is not available: the orbital-entropy builders are outside the hot path "
                                "this build covers (DESIGN.md, scope)");
 }
 
@@ -283,6 +283,21 @@ class CiSession {
     return out;
   }
 
+  // HamiltonianGenerator::form_rdms_spin_dep / form_rdms on the solver-ordered list
+  // (macis_base.hpp:166-215, macis_pmc.cpp:128-160); outputs sized by the caller, empty = skip
+  void form_rdms(const std::vector<Det>& dets, const std::vector<double>& C, bool spin_dep, std::vector<double>& o1,
+                 std::vector<double>& o2, std::vector<double>& t1, std::vector<double>& t2, std::vector<double>& t3) {
+    b2ci_dets* d = nullptr;
+    B2(b2ci_dets_upload(ctx_, reinterpret_cast<const uint64_t*>(dets.data()), 2, int64_t(dets.size()), &d));
+    auto p = [](std::vector<double>& v) { return v.empty() ? nullptr : v.data(); };
+    const int rc = spin_dep ? b2ci_form_rdms_spin_dep(ctx_, d, C.data(), p(o1), p(o2), p(t1), p(t2), p(t3))
+                            : b2ci_form_rdms(ctx_, d, C.data(), p(o1), p(t1));
+    b2ci_dets_free(ctx_, d);
+    if (rc != 0) throw std::runtime_error(b2ci_last_error());
+    g_stats["rdm_pattern_ms"] = b2ci_timer_ms(ctx_, "rdm.pattern");
+    g_stats["rdm_scatter_ms"] = b2ci_timer_ms(ctx_, "rdm.scatter");
+  }
+
  private:
   void add_timer(const char* key, std::initializer_list<const char*> names) {
     double t = 0.;
@@ -305,6 +320,21 @@ std::shared_ptr<data::Wavefunction> make_wavefunction(const std::vector<Det>& de
   cfg.reserve(dets.size());
   for (const Det& d : dets) cfg.emplace_back(d.a, d.b, norb);
   return std::make_shared<data::Wavefunction>(std::move(C), std::move(cfg), norb);
+}
+
+// build_wavefunction's RDM step (macis_base.hpp:155-215): spin-dependent blocks, two-body ones
+// scaled by 2 as the adapter stores them
+void attach_rdms_spin_dependent(CiSession& S, const data::Settings& st, const std::vector<Det>& dets,
+                                const std::vector<double>& C, data::Wavefunction& w) {
+  const bool one = st.get<bool>("calculate_one_rdm"), two = st.get<bool>("calculate_two_rdm");
+  if (!one && !two) return;
+  const size_t n = w.num_active_orbitals(), n2 = n * n, n4 = n2 * n2;
+  std::vector<double> aa(one ? n2 : 0, 0.0), bb(one ? n2 : 0, 0.0), aaaa(two ? n4 : 0, 0.0), bbbb(two ? n4 : 0, 0.0),
+      aabb(two ? n4 : 0, 0.0);
+  S.form_rdms(dets, C, true, aa, bb, aaaa, bbbb, aabb);
+  for (auto* v : {&aaaa, &bbbb, &aabb})
+    for (double& x : *v) x *= 2.0;
+  w.set_rdms_spin_dependent(std::move(aa), std::move(bb), std::move(aaaa), std::move(aabb), std::move(bbbb));
 }
 
 void check_hamiltonian(const data::Hamiltonian& h, const char* who, unsigned na, unsigned nb) {
@@ -613,8 +643,10 @@ McResult B200Cas::_run_impl(std::shared_ptr<data::Hamiltonian> h, unsigned na, u
   std::vector<Det> dets;
   std::vector<double> C;
   const double E = casci(S, *_settings, na, nb, dets, C);
+  auto w = make_wavefunction(dets, C, h->num_active_orbitals());
+  attach_rdms_spin_dependent(S, *_settings, dets, C, *w);
   g_stats["wall_ms"] = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
-  return {E + h->get_core_energy(), make_wavefunction(dets, std::move(C), h->num_active_orbitals())};
+  return {E + h->get_core_energy(), w};
 }
 
 McResult B200Asci::_run_impl(std::shared_ptr<data::Hamiltonian> h, unsigned na, unsigned nb) const {
@@ -622,8 +654,8 @@ McResult B200Asci::_run_impl(std::shared_ptr<data::Hamiltonian> h, unsigned na, 
   check_hamiltonian(*h, "B200Asci", na, nb);
   reject_unsupported_outputs(*_settings);
   if (_settings->get<bool>("grow_with_rot"))
-    throw std::runtime_error("grow_with_rot (natural-orbital rotation during growth) needs the RDM builders, "
-                             "which are outside the hot path this build covers");
+    throw std::runtime_error("grow_with_rot (natural-orbital rotation of the integrals during growth) is outside "
+                             "the hot path this build covers");
   const McscfSettings m = get_mcscf_settings(*_settings);
   const AsciSettings a = get_asci_settings(*_settings);
   g_stats.clear();
@@ -650,8 +682,10 @@ McResult B200Asci::_run_impl(std::shared_ptr<data::Hamiltonian> h, unsigned na, 
     if (a.max_refine_iter) E = asci_refine(S, a, m, E, dets, C);
     g_stats["ndets"] = double(dets.size());
   }
+  auto w = make_wavefunction(dets, C, h->num_active_orbitals());
+  attach_rdms_spin_dependent(S, *_settings, dets, C, *w);
   g_stats["wall_ms"] = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
-  return {E + h->get_core_energy(), make_wavefunction(dets, std::move(C), h->num_active_orbitals())};
+  return {E + h->get_core_energy(), w};
 }
 
 McResult B200Pmc::_run_impl(std::shared_ptr<data::Hamiltonian> h,
@@ -684,8 +718,16 @@ McResult B200Pmc::_run_impl(std::shared_ptr<data::Hamiltonian> h,
     E = S.selected_ci_diag(dets, m.ci_matel_tol, m.ci_max_subspace, m.ci_res_tol, C);
   }
   g_stats["ndets"] = double(n);
+  auto w = make_wavefunction(dets, C, norb);
+  if (_settings->get<bool>("calculate_one_rdm") || _settings->get<bool>("calculate_two_rdm")) {
+    // the PMC adapter always forms both spin-traced matrices (macis_pmc.cpp:128-160)
+    const size_t n2 = norb * norb;
+    std::vector<double> one(n2, 0.0), two(n2 * n2, 0.0), none;
+    S.form_rdms(dets, C, false, one, none, two, none, none);
+    w->set_rdms_spin_traced(std::move(one), std::move(two));
+  }
   g_stats["wall_ms"] = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
-  return {E + h->get_core_energy(), make_wavefunction(dets, std::move(C), norb)};
+  return {E + h->get_core_energy(), w};
 }
 
 std::pair<int64_t, int64_t> row_block(int64_t n, int rank, int nranks) {

@@ -1,4 +1,5 @@
 // Settings / Hamiltonian / Configuration / Wavefunction stand-ins (see include/qdk_b200/data.hpp).
+#include <stdexcept>
 #include "qdk_b200/data.hpp"
 
 #include <cmath>
@@ -156,6 +157,43 @@ double Wavefunction::overlap(const Wavefunction& other) const {
     if (it != m.end()) s += it->second * other.coeffs_[i];
   }
   return s;
+}
+
+void Wavefunction::set_rdms_spin_dependent(std::vector<double> one_aa, std::vector<double> one_bb,
+                                           std::vector<double> two_aaaa, std::vector<double> two_aabb,
+                                           std::vector<double> two_bbbb) {
+  one_aa_ = std::move(one_aa); one_bb_ = std::move(one_bb);
+  two_aaaa_ = std::move(two_aaaa); two_aabb_ = std::move(two_aabb); two_bbbb_ = std::move(two_bbbb);
+}
+void Wavefunction::set_rdms_spin_traced(std::vector<double> one, std::vector<double> two) {
+  one_st_ = std::move(one);
+  two_st_ = std::move(two);
+}
+std::pair<std::vector<double>, std::vector<double>> Wavefunction::get_active_one_rdm_spin_dependent() const {
+  if (!has_one_rdm_spin_dependent()) throw std::runtime_error("Spin-dependent one-body RDM not set");
+  return {one_aa_, one_bb_};
+}
+std::tuple<std::vector<double>, std::vector<double>, std::vector<double>>
+Wavefunction::get_active_two_rdm_spin_dependent() const {
+  if (!has_two_rdm_spin_dependent()) throw std::runtime_error("Spin-dependent two-body RDM not set");
+  return {two_aaaa_, two_aabb_, two_bbbb_};
+}
+std::vector<double> Wavefunction::get_active_one_rdm_spin_traced() const {
+  if (!one_st_.empty()) return one_st_;
+  if (!has_one_rdm_spin_dependent()) throw std::runtime_error("Spin-traced one-body RDM not set");
+  std::vector<double> r(one_aa_);
+  for (size_t i = 0; i < r.size(); ++i) r[i] += one_bb_[i];
+  return r;
+}
+std::vector<double> Wavefunction::get_active_two_rdm_spin_traced() const {
+  if (!two_st_.empty()) return two_st_;
+  if (!has_two_rdm_spin_dependent()) throw std::runtime_error("Spin-traced two-body RDM not set");
+  const size_t n = norb_, n2 = n * n;
+  std::vector<double> r(two_aaaa_);
+  for (size_t pq = 0; pq < n2; ++pq)
+    for (size_t rs = 0; rs < n2; ++rs)
+      r[pq + rs * n2] += two_bbbb_[pq + rs * n2] + two_aabb_[pq + rs * n2] + two_aabb_[rs + pq * n2];
+  return r;
 }
 
 }  // namespace qdk_b200::data

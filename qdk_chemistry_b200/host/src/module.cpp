@@ -157,6 +157,46 @@ PYBIND11_MODULE(_core, m) {
              std::memcpy(a.mutable_data(), c.data(), c.size() * 8);
              return a;
            })
+      .def("has_one_rdm_spin_dependent", &data::Wavefunction::has_one_rdm_spin_dependent)
+      .def("has_two_rdm_spin_dependent", &data::Wavefunction::has_two_rdm_spin_dependent)
+      .def("has_one_rdm_spin_traced", &data::Wavefunction::has_one_rdm_spin_traced)
+      .def("has_two_rdm_spin_traced", &data::Wavefunction::has_two_rdm_spin_traced)
+      .def("get_active_one_rdm_spin_dependent",
+           [](const data::Wavefunction& w) {
+             auto r = w.get_active_one_rdm_spin_dependent();
+             const py::ssize_t n = py::ssize_t(w.num_active_orbitals());
+             auto mk = [n](const std::vector<double>& v) {  // column-major n x n
+               py::array_t<double, py::array::f_style> a({n, n});
+               std::memcpy(a.mutable_data(), v.data(), v.size() * 8);
+               return a;
+             };
+             return py::make_tuple(mk(r.first), mk(r.second));
+           })
+      .def("get_active_two_rdm_spin_dependent",
+           [](const data::Wavefunction& w) {  // (aaaa, aabb, bbbb), flat n^4 like the reference's VectorXd
+             auto r = w.get_active_two_rdm_spin_dependent();
+             auto mk = [](const std::vector<double>& v) {
+               py::array_t<double> a{py::ssize_t(v.size())};
+               std::memcpy(a.mutable_data(), v.data(), v.size() * 8);
+               return a;
+             };
+             return py::make_tuple(mk(std::get<0>(r)), mk(std::get<1>(r)), mk(std::get<2>(r)));
+           })
+      .def("get_active_one_rdm_spin_traced",
+           [](const data::Wavefunction& w) {
+             auto v = w.get_active_one_rdm_spin_traced();
+             const py::ssize_t n = py::ssize_t(w.num_active_orbitals());
+             py::array_t<double, py::array::f_style> a({n, n});
+             std::memcpy(a.mutable_data(), v.data(), v.size() * 8);
+             return a;
+           })
+      .def("get_active_two_rdm_spin_traced",
+           [](const data::Wavefunction& w) {
+             auto v = w.get_active_two_rdm_spin_traced();
+             py::array_t<double> a{py::ssize_t(v.size())};
+             std::memcpy(a.mutable_data(), v.data(), v.size() * 8);
+             return a;
+           })
       .def("get_active_determinants", &data::Wavefunction::get_active_determinants)
       .def("determinant_words", [](const data::Wavefunction& w) {
         // (alpha, beta) occupation words, shape (n, 2)

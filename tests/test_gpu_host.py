@@ -143,3 +143,53 @@ def test_davidson_solver_on_scipy_csr():
     assert E2 == -3.5 and x2[0] == 1.0
     with pytest.raises(RuntimeError, match="Davidson Did Not Converge"):
         alg.davidson_solver(A, 1e-13, 3)
+
+
+def test_cas_plugin_rdms_spin_dependent(golden_meta):
+    """calculate_one_rdm / calculate_two_rdm on the CAS plugin: the container holds (aa, bb) and
+    (aaaa, aabb, bbbb) with the adapter's factor 2 on the two-body blocks (macis_base.hpp:199-215);
+    checked against the oracle port on the plugin's own wavefunction."""
+    sp = W.config("small_cas8")
+    n = sp.norb
+    E, w = alg.create(MC, "macis_cas", calculate_one_rdm=True, calculate_two_rdm=True,
+                      ci_residual_tolerance=1e-10).run(_ham(sp), sp.nalpha, sp.nbeta)
+    assert w.has_one_rdm_spin_dependent() and w.has_two_rdm_spin_dependent()
+    assert w.has_one_rdm_spin_traced() and w.has_two_rdm_spin_traced()
+    words = w.determinant_words()
+    C = w.get_coefficients()
+    p_aa, p_bb, p_aaaa, p_bbbb, p_aabb = port.form_rdms(n, words[:, 0], words[:, 1], C, spin_dep=True)
+    aa, bb = w.get_active_one_rdm_spin_dependent()
+    aaaa, aabb, bbbb = w.get_active_two_rdm_spin_dependent()
+    sh4 = lambda v: v.reshape((n,) * 4, order="F")
+    assert np.abs(aa - p_aa).max() < 1e-12 and np.abs(bb - p_bb).max() < 1e-12
+    assert np.abs(sh4(aaaa) - 2 * p_aaaa).max() < 1e-12
+    assert np.abs(sh4(aabb) - 2 * p_aabb).max() < 1e-12
+    assert np.abs(sh4(bbbb) - 2 * p_bbbb).max() < 1e-12
+    one = w.get_active_one_rdm_spin_traced()
+    assert abs(np.trace(one) - (sp.nalpha + sp.nbeta)) < 1e-10
+    # E_active = <one, T> + 1/2 <two_spin_traced, V> with the adapter's normalisation
+    two = sh4(w.get_active_two_rdm_spin_traced())
+    Er = np.sum(one * sp.T.reshape(n, n, order="F")) + 0.5 * np.sum(two * sp.V.reshape((n,) * 4, order="F"))
+    assert abs(Er + sp.core_energy - E) < 1e-8
+    # without the settings nothing is attached
+    _, w0 = alg.create(MC, "macis_cas").run(_ham(sp), sp.nalpha, sp.nbeta)
+    assert not w0.has_one_rdm_spin_dependent() and not w0.has_two_rdm_spin_traced()
+    with pytest.raises(RuntimeError):
+        w0.get_active_one_rdm_spin_traced()
+
+
+def test_pmc_plugin_rdms_spin_traced(water, golden_meta):
+    """PMC stores the spin-traced pair from form_rdms (macis_pmc.cpp:128-160)."""
+    a, b = cisd_space(24, 5, 5)
+    sel = np.arange(0, len(a), 7)
+    cfgs = [data.Configuration(int(x), int(y), water.norb) for x, y in zip(a[sel], b[sel])]
+    pmc = alg.create("projected_multi_configuration_calculator", "macis_pmc", calculate_one_rdm=True)
+    E, w = pmc.run(_ham(water), cfgs)
+    one = w.get_active_one_rdm_spin_traced()
+    two = w.get_active_two_rdm_spin_traced().reshape((water.norb,) * 4, order="F")
+    po, pt = port.form_rdms(water.norb, a[sel], b[sel], w.get_coefficients())
+    assert np.abs(one - po).max() < 1e-12 and np.abs(two - pt).max() < 1e-12
+    assert not w.has_one_rdm_spin_dependent()
+    n = water.norb
+    Er = np.sum(one * water.T.reshape(n, n, order="F")) + np.sum(two * water.V.reshape((n,) * 4, order="F"))
+    assert abs(Er + water.core_energy - E) < 1e-8

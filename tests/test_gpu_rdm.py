@@ -1,0 +1,90 @@
+"""GPU parity of the reduced density matrices (b2ci_form_rdms / b2ci_form_rdms_spin_dep) against
+the oracle port, which tests/test_oracle.py pins to the compiled reference. Summation order on
+the device differs (fp64 reductions in L2), so the bar is rounding: 1e-12 absolute on entries of
+magnitude <= 2."""
+import numpy as np
+import pytest
+
+from oracle import port
+from qdk_chemistry_b200 import device
+from qdk_chemistry_b200 import workloads as W
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-12
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    c = device.Context(0)
+    yield c
+    c.close()
+
+
+def _subset(sp, m, seed):
+    a, b = port.generate_hilbert_space(sp.norb, sp.nalpha, sp.nbeta)
+    rng = np.random.default_rng(seed)
+    if m < len(a):
+        idx = np.sort(rng.choice(len(a), m, replace=False))
+        a, b = a[idx], b[idx]
+    C = rng.normal(size=len(a)) * np.exp(-rng.uniform(0, 6, size=len(a)))
+    return a, b, C / np.linalg.norm(C)
+
+
+@pytest.mark.parametrize("name,m,seed", [("tiny_cas6", 400, 0), ("small_cas8", 700, 1), ("hubbard_4x2", 4900, 2),
+                                         ("small_cas8", 3920, 3)])
+def test_rdms_match_oracle(ctx, name, m, seed):
+    sp = W.config(name)
+    a, b, C = _subset(sp, m, seed)
+    ctx.upload_integrals(sp.norb, sp.T, sp.V)
+    dets = ctx.upload_dets(port.pack(a, b), 1)
+    o, t = ctx.form_rdms(dets, C)
+    po, pt = port.form_rdms(sp.norb, a, b, C)
+    assert np.abs(o - po).max() < TOL and np.abs(t - pt).max() < TOL
+    g5 = ctx.form_rdms(dets, C, spin_dep=True)
+    p5 = port.form_rdms(sp.norb, a, b, C, spin_dep=True)
+    for x, y in zip(g5, p5):
+        assert np.abs(x - y).max() < TOL
+    # relations the reference's own test checks (double_loop.cxx:330-375)
+    aa, bb, aaaa, bbbb, aabb = g5
+    assert np.abs(o - (aa + bb)).max() < TOL
+    assert np.abs(t - (aaaa + bbbb + aabb + aabb.transpose(2, 3, 0, 1))).max() < TOL
+    assert abs(np.trace(o) - (sp.nalpha + sp.nbeta)) < 1e-11
+    assert np.abs(o - o.T).max() < TOL
+    dets.free()
+
+
+def test_rdm_energy_equals_rayleigh_quotient_full_ci(ctx):
+    """E = sum ordm*T + sum trdm*V (double_loop.cxx:198-237) at the converged CASCI vector."""
+    sp = W.config("small_cas8")
+    ctx.upload_integrals(sp.norb, sp.T, sp.V)
+    dets = ctx.generate_fci(sp.norb, sp.nalpha, sp.nbeta)
+    H = ctx.hbuild(dets, 0.0)
+    E, X, _, _ = H.davidson(200, 1e-10)
+    o, t = ctx.form_rdms(dets, X)
+    n = sp.norb
+    Er = np.sum(o * sp.T.reshape(n, n, order="F")) + np.sum(t * sp.V.reshape((n,) * 4, order="F"))
+    assert abs(Er - E) < 1e-9
+    # requesting only one of the two leaves the other untouched
+    o1, t1 = ctx.form_rdms(dets, X, two=False)
+    assert t1 is None and np.abs(o1 - o).max() < TOL
+    o2, t2 = ctx.form_rdms(dets, X, one=False)
+    assert o2 is None and np.abs(t2 - t).max() < TOL
+    H.free()
+    dets.free()
+
+
+def test_rdm_hf_determinant(ctx):
+    """single determinant: ordm(i,i) = 2, trdm(i,i,j,j) = 2, trdm(i,j,j,i) = -1, trdm(i,i,i,i) = 1
+    (double_loop.cxx:266-300)"""
+    sp = W.config("tiny_cas6")
+    ctx.upload_integrals(sp.norb, sp.T, sp.V)
+    hf = np.array([(1 << sp.nalpha) - 1], dtype=np.uint64)
+    dets = ctx.upload_dets(port.pack(hf, hf), 1)
+    o, t = ctx.form_rdms(dets, np.array([1.0]))
+    for i in range(sp.nalpha):
+        assert o[i, i] == 2.0 and t[i, i, i, i] == 1.0
+        for j in range(sp.nalpha):
+            if i != j:
+                assert t[i, i, j, j] == 2.0 and t[i, j, j, i] == -1.0
+    assert np.count_nonzero(o) == sp.nalpha
+    dets.free()

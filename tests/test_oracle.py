@@ -171,3 +171,45 @@ def test_port_pt2_pinned_to_reference_known_answer(water):
     cs = C[top] / np.linalg.norm(C[top])
     e, n = port.Ham(water.norb, water.T, water.V).asci_pt2(a[top], b[top], cs, m["E_asci"], m["pt2_tol"])
     assert n == m["port_small_npt2"] and abs(e - m["port_small"]) < 1e-14
+
+
+@pytest.mark.parametrize("spin_dep", [False, True])
+def test_port_rdms_match_compiled_reference(spin_dep):
+    """op_form_rdms(_spin_dep) against SortedDoubleLoop / DoubleLoop form_rdms of oracle/_ref."""
+    ref = pytest.importorskip("oracle.ref")
+    if not ref.available():
+        pytest.skip("oracle/_ref not built (needs /root/reference)")
+    sp = W.config("small_cas8")
+    a, b = port.generate_hilbert_space(sp.norb, sp.nalpha, sp.nbeta)
+    rng = np.random.default_rng(11)
+    idx = np.sort(rng.choice(len(a), 500, replace=False))
+    a, b = a[idx], b[idx]
+    C = rng.normal(size=len(a))
+    C /= np.linalg.norm(C)
+    hg = ref.HamGen(sp.norb, sp.T, sp.V)
+    for gen in ("sdl", "double_loop"):
+        r = hg.form_rdms(port.pack(a, b), C, spin_dep=spin_dep, generator=gen)
+        p = port.form_rdms(sp.norb, a, b, C, spin_dep=spin_dep)
+        for x, y in zip(r, p):
+            assert np.abs(x - y).max() < 1e-14   # the reference's omp-atomic order is not fixed
+
+
+def test_port_rdm_properties():
+    """Properties the reference's tests assert (double_loop.cxx:198-237, 266-375): HF values,
+    trace, symmetry, spin-traced = sum of spin blocks, E = <ordm,T> + <trdm,V>."""
+    sp = W.config("tiny_cas6")
+    n = sp.norb
+    hf = np.array([(1 << sp.nalpha) - 1], dtype=np.uint64)
+    o, t = port.form_rdms(n, hf, hf, np.array([1.0]))
+    for i in range(sp.nalpha):
+        assert o[i, i] == 2.0 and t[i, i, i, i] == 1.0
+    a, b = port.generate_hilbert_space(n, sp.nalpha, sp.nbeta)
+    rp, ci, nz = port.Ham(n, sp.T, sp.V).hbuild(a, b, 0.0)
+    E, X, _, _ = port.davidson(rp, ci, nz, 100, 1e-10)
+    o, t = port.form_rdms(n, a, b, X)
+    aa, bb, aaaa, bbbb, aabb = port.form_rdms(n, a, b, X, spin_dep=True)
+    assert abs(np.trace(o) - (sp.nalpha + sp.nbeta)) < 1e-12 and np.abs(o - o.T).max() < 1e-14
+    assert np.abs(o - aa - bb).max() < 1e-14
+    assert np.abs(t - (aaaa + bbbb + aabb + aabb.transpose(2, 3, 0, 1))).max() < 1e-14
+    Er = np.sum(o * sp.T.reshape(n, n, order="F")) + np.sum(t * sp.V.reshape((n,) * 4, order="F"))
+    assert abs(Er - E) < 1e-9
