@@ -16,6 +16,7 @@
 //   5. drop core determinants (rv = inf sentinel, determinant_search.hpp:659-660,970-974)
 //      and |rv| <= rv_prune_tol (:676-681); radix-select the k-th largest |rv| and keep
 //      every candidate >= it (ties retained, :994-1080); append the core determinants.
+#include <chrono>
 #include <cmath>
 #include <cstring>
 
@@ -361,6 +362,16 @@ int asci_search(b2ci_ctx* ctx, const b2ci_asci_search_opts* o, const uint64_t* c
   const int n = ctx->norb;
   if (wpd == 1 && n > 32) throw Error("b2ci_asci_search: wfn_t<64> holds at most 32 orbitals per spin");
   cudaStream_t st = ctx->stream;
+  // host wall-clock trace (B2CI_ASCI_TRACE=1): time between marks includes allocations and waits
+  const bool trace = getenv("B2CI_ASCI_TRACE") != nullptr;
+  auto t_host0 = std::chrono::steady_clock::now();
+  auto mark = [&](const char* what) {
+    if (!trace) return;
+    cudaStreamSynchronize(st);
+    auto t = std::chrono::steady_clock::now();
+    fprintf(stderr, "[asci] %-28s +%9.1f us\n", what, std::chrono::duration<double, std::micro>(t - t_host0).count());
+    t_host0 = t;
+  };
   auto& T = ctx->timers;
   T["asci_search.PAIR_DUR"] = T["asci_search.SORT_ACC_DUR"] = T["asci_search.TOPK_DUR"] = 0.;
 
@@ -409,9 +420,10 @@ int asci_search(b2ci_ctx* ctx, const b2ci_asci_search_opts* o, const uint64_t* c
     B2_CUDA(cudaMemcpyAsync(&M_total, base.p + nc, 8, cudaMemcpyDeviceToHost, st));
     B2_CUDA(cudaStreamSynchronize(st));
   }
+  mark("core upload + count pass");
   size_t free_b = 0, total_b = 0;
   B2_CUDA(cudaMemGetInfo(&free_b, &total_b));
-  const int64_t bytes_per = 64;  // key, c*h, h_diag, sort double buffers, flags, segment ids
+  const int64_t bytes_per = 80;  // workspace per contribution (records, sort buffers, flags, segments)
   int64_t budget = std::min<int64_t>(int64_t(double(free_b) * 0.5) / bytes_per, (int64_t(1) << 31) - 1);
   if (const char* env = getenv("B2CI_ASCI_BUDGET")) budget = std::max<int64_t>(1024, atoll(env));
   // hash partitions are even to a few percent; 1.25 covers the imbalance
@@ -452,8 +464,8 @@ int asci_search(b2ci_ctx* ctx, const b2ci_asci_search_opts* o, const uint64_t* c
 
   for (int64_t part = rank; part < nparts; part += nranks) {
     int64_t M = 0;
-    DevBuf<uint64_t> key;
-    DevBuf<double> cm, hd;
+    uint64_t* key = nullptr;
+    double *cm = nullptr, *hd = nullptr;
     {
       ScopedTimer t(ctx, "asci_search.PAIR_DUR", true);
       A.nparts = uint32_t(nparts); A.part = uint32_t(part);
@@ -467,53 +479,68 @@ int asci_search(b2ci_ctx* ctx, const b2ci_asci_search_opts* o, const uint64_t* c
       B2_CUDA(cudaMemcpyAsync(&M, base.p + nc, 8, cudaMemcpyDeviceToHost, st));
       B2_CUDA(cudaStreamSynchronize(st));
       if (M >= (int64_t(1) << 32)) throw Error("b2ci_asci_search: more than 2^32 contributions in one part");
-      B2_CUDA(cudaMemGetInfo(&free_b, &total_b));
-      const size_t need = size_t(M) * 56;
-      if (need > free_b)
-        throw Error("b2ci_asci_search: " + std::to_string(M) + " contributions need " +
-                    std::to_string(need >> 20) + " MiB of device memory, " + std::to_string(free_b >> 20) + " MiB free");
-      key.alloc(M > 0 ? M : 1);
-      cm.alloc(M > 0 ? M : 1);
-      hd.alloc(M > 0 ? M : 1);
+      mark("part count");
+      // workspace of this part: records (24 B), sort double buffers and indices (16 B), segment
+      // flags and ids (12 B), accumulated segments (<= 24 B), 256-byte alignment slack
+      const size_t Mz = size_t(M > 0 ? M : 1);
+      const size_t need = Mz * 76 + 16 * 1024;
+      if (need > ctx->arena_cap) {
+        B2_CUDA(cudaMemGetInfo(&free_b, &total_b));
+        if (need > free_b + ctx->arena_cap)
+          throw Error("b2ci_asci_search: " + std::to_string(M) + " contributions need " +
+                      std::to_string(need >> 20) + " MiB of device memory, " +
+                      std::to_string((free_b + ctx->arena_cap) >> 20) + " MiB free");
+      }
+      arena_reserve(ctx, need);
+      arena_reset(ctx);
+      key = arena_take<uint64_t>(ctx, Mz);
+      cm = arena_take<double>(ctx, Mz);
+      hd = arena_take<double>(ctx, Mz);
+      mark("alloc key/cm/hd");
       A.count = nullptr; A.base = base; A.key = key; A.key2 = nullptr; A.cm = cm; A.hd = hd;
       k_generate<true><<<unsigned(nc), GEN_THREADS, 0, st>>>(A);
       ctx->launches++;
       B2_CHECK_LAUNCH();
+      mark("generate");
     }
     M_sum += M;
     if (M == 0) continue;
 
     // ---- sort + accumulate
     int64_t nseg = 0;
-    DevBuf<uint64_t> sk1;
-    DevBuf<double> scm, shd;
+    uint64_t* sk1 = nullptr;
+    double *scm = nullptr, *shd = nullptr;
     {
       ScopedTimer t(ctx, "asci_search.SORT_ACC_DUR", true);
-      DevBuf<uint64_t> kalt(M);
-      DevBuf<uint32_t> idx(M), idx_alt(M);
+      uint64_t* kalt = arena_take<uint64_t>(ctx, M);
+      uint32_t* idx = arena_take<uint32_t>(ctx, M);
+      uint32_t* idx_alt = arena_take<uint32_t>(ctx, M);
+      mark("alloc sort buffers");
       iota_u32(ctx, idx, M);
       const int ndig = (n + 7) / 8;
       std::vector<int> shifts;
       for (int d = 0; d < ndig; ++d) shifts.push_back(8 * d);        // alpha bits
       for (int d = 0; d < ndig; ++d) shifts.push_back(32 + 8 * d);   // beta bits (high half)
       radix_sort_pairs(ctx, key, kalt, idx, idx_alt, M, shifts);
-      DevBuf<int32_t> flag(M);
-      DevBuf<int64_t> seg_of(M + 1);
+      mark("radix sort");
+      int32_t* flag = arena_take<int32_t>(ctx, M);
+      int64_t* seg_of = arena_take<int64_t>(ctx, M + 1);
       k_seg_flags<<<grid1d(M), 256, 0, st>>>(key, nullptr, M, flag);
       ctx->launches++;
       B2_CHECK_LAUNCH();
       exclusive_scan_i32_to_i64(ctx, flag, seg_of, M);
-      B2_CUDA(cudaMemcpyAsync(&nseg, seg_of.p + M, 8, cudaMemcpyDeviceToHost, st));
+      B2_CUDA(cudaMemcpyAsync(&nseg, seg_of + M, 8, cudaMemcpyDeviceToHost, st));
       B2_CUDA(cudaStreamSynchronize(st));
-      sk1.alloc(nseg);
-      scm.alloc(nseg);
-      shd.alloc(nseg);
+      mark("segment flags + scan");
+      sk1 = arena_take<uint64_t>(ctx, nseg);
+      scm = arena_take<double>(ctx, nseg);
+      shd = arena_take<double>(ctx, nseg);
       // seg_of[i] (exclusive scan) is the segment id of a head at i
       k_seg_accumulate<<<grid1d(M), 256, 0, st>>>(key, nullptr, idx, flag, seg_of, M, cm, hd, sk1, nullptr, scm, shd);
       ctx->launches++;
       B2_CHECK_LAUNCH();
     }
-    key.release(); cm.release(); hd.release();
+    mark("accumulate");
     nseg_sum += nseg;
 
     if (pt2_out) {
@@ -547,30 +574,27 @@ int asci_search(b2ci_ctx* ctx, const b2ci_asci_search_opts* o, const uint64_t* c
     // ---- prune: finite rv (core determinants carry inf) and |rv| > rv_prune_tol
     {
       ScopedTimer t(ctx, "asci_search.TOPK_DUR", true);
-      DevBuf<int32_t> keep(nseg);
-      DevBuf<double> score(nseg);
-      DevBuf<int64_t> pos(nseg + 1);
+      // records, sort buffers and flags are dead now: their workspace (52 B per contribution,
+      // below the accumulated segments) is reused for the 36 B per segment of this phase
+      arena_reset(ctx);
+      int32_t* keep = arena_take<int32_t>(ctx, nseg);
+      double* score = arena_take<double>(ctx, nseg);
+      int64_t* pos = arena_take<int64_t>(ctx, nseg + 1);
       int64_t m = 0;
       k_score<<<grid1d(nseg), 256, 0, st>>>(scm, shd, nseg, o->rv_prune_tol, keep, score);
       ctx->launches++;
       B2_CHECK_LAUNCH();
       exclusive_scan_i32_to_i64(ctx, keep, pos, nseg);
-      B2_CUDA(cudaMemcpyAsync(&m, pos.p + nseg, 8, cudaMemcpyDeviceToHost, st));
+      B2_CUDA(cudaMemcpyAsync(&m, pos + nseg, 8, cudaMemcpyDeviceToHost, st));
       B2_CUDA(cudaStreamSynchronize(st));
       if (m) {
-        DevBuf<uint64_t> ck(m);
-        DevBuf<double> cs(m);
+        uint64_t* ck = arena_take<uint64_t>(ctx, m);
+        double* cs = arena_take<double>(ctx, m);
         k_compact<<<grid1d(nseg), 256, 0, st>>>(keep, pos, nseg, sk1, nullptr, score, ck, nullptr, cs);
         ctx->launches++;
         B2_CHECK_LAUNCH();
-        if (nparts == 1 && nranks == 1) {
-          cand_key = std::move(ck);
-          cand_score = std::move(cs);
-          ncand = cand_cap = m;
-        } else {
-          append_candidates(ck, cs, m);
-          B2_CUDA(cudaStreamSynchronize(st));
-        }
+        append_candidates(ck, cs, m);  // survivors leave the workspace
+        B2_CUDA(cudaStreamSynchronize(st));
       }
     }
   }

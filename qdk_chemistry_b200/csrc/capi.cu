@@ -1,6 +1,8 @@
 // extern "C" surface declared in include/b2ci.h. Every entry catches C++ exceptions,
 // records the message for b2ci_last_error() and returns a non-zero status -- there is no
 // CPU fallback behind any of them.
+#include <unordered_map>
+#include <mutex>
 #include <cstring>
 
 #include "common.cuh"
@@ -10,6 +12,75 @@ namespace b2ci {
 
 static thread_local std::string g_last_error;
 void set_error(const std::string& msg) { g_last_error = msg; }
+namespace {
+struct BigBlock { void* p; size_t bytes; int device; cudaStream_t stream; };
+struct BigCache {
+  std::mutex mu;
+  std::vector<BigBlock> idle;
+  std::unordered_map<void*, BigBlock> live;
+};
+BigCache& big_cache() {
+  static BigCache* c = new BigCache;  // never destroyed: frees at exit would race the driver
+  return *c;
+}
+}  // namespace
+void* big_cache_alloc(size_t bytes, cudaStream_t st) {
+  BigCache& C = big_cache();
+  int dev = 0;
+  cudaGetDevice(&dev);
+  std::lock_guard<std::mutex> g(C.mu);
+  // best fit among idle blocks of this device and stream that are not wastefully large
+  int best = -1;
+  for (int i = 0; i < int(C.idle.size()); ++i) {
+    const BigBlock& b = C.idle[i];
+    if (b.device != dev || b.stream != st || b.bytes < bytes || b.bytes > bytes + bytes / 2 + (size_t(64) << 20)) continue;
+    if (best < 0 || b.bytes < C.idle[best].bytes) best = i;
+  }
+  if (best >= 0) {
+    BigBlock b = C.idle[best];
+    C.idle.erase(C.idle.begin() + best);
+    C.live[b.p] = b;
+    return b.p;
+  }
+  void* p = nullptr;
+  cudaError_t e = cudaMalloc(&p, bytes);
+  if (e != cudaSuccess) {  // give the idle blocks back and retry once
+    cudaGetLastError();
+    cudaDeviceSynchronize();
+    for (auto it = C.idle.begin(); it != C.idle.end();) {
+      if (it->device == dev) { cudaFree(it->p); it = C.idle.erase(it); } else ++it;
+    }
+    e = cudaMalloc(&p, bytes);
+  }
+  if (e != cudaSuccess) {
+    cudaGetLastError();
+    throw Error("device allocation of " + std::to_string(bytes >> 20) + " MiB failed: " + cudaGetErrorString(e));
+  }
+  C.live[p] = BigBlock{p, bytes, dev, st};
+  return p;
+}
+bool big_cache_free(void* p, cudaStream_t st) {
+  BigCache& C = big_cache();
+  std::lock_guard<std::mutex> g(C.mu);
+  auto it = C.live.find(p);
+  if (it == C.live.end()) return false;
+  BigBlock b = it->second;
+  C.live.erase(it);
+  b.stream = st;  // later work on this stream is ordered behind whatever still reads the block
+  C.idle.push_back(b);
+  return true;
+}
+void big_cache_trim() {
+  BigCache& C = big_cache();
+  int dev = 0;
+  cudaGetDevice(&dev);
+  std::lock_guard<std::mutex> g(C.mu);
+  cudaDeviceSynchronize();
+  for (auto it = C.idle.begin(); it != C.idle.end();) {
+    if (it->device == dev) { cudaFree(it->p); it = C.idle.erase(it); } else ++it;
+  }
+}
+
 cudaStream_t& alloc_stream() {
   static thread_local cudaStream_t s = nullptr;
   return s;
@@ -109,6 +180,7 @@ int b2ci_ctx_destroy(b2ci_ctx* ctx) {
     dev_free(ctx->ints_dev);
     for (int i = 0; i < 2; ++i) dev_free(ctx->slot_cache[i]);
     if (ctx->pinned) cudaFreeHost(ctx->pinned);
+    if (ctx->arena) cudaFree(ctx->arena);
     cudaStreamSynchronize(ctx->stream);
   }
   delete ctx;
@@ -130,6 +202,10 @@ int b2ci_ctx_trim(b2ci_ctx* ctx) {
     ctx->slot_cache_bytes[i] = 0;
   }
   B2_CUDA(cudaStreamSynchronize(ctx->stream));
+  if (ctx->arena) cudaFree(ctx->arena);
+  ctx->arena = nullptr;
+  ctx->arena_cap = ctx->arena_off = 0;
+  big_cache_trim();
   cudaMemPool_t pool;
   B2_CUDA(cudaDeviceGetDefaultMemPool(&pool, ctx->device));
   B2_CUDA(cudaMemPoolTrimTo(pool, 0));

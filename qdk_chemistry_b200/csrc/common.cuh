@@ -104,6 +104,10 @@ struct b2ci_ctx {
   // pinned staging for the scalars a build reads back (pageable targets would make every
   // cudaMemcpyAsync a synchronisation of its own)
   int64_t* pinned = nullptr;
+  // grow-only workspace of the ASCI search (plain cudaMalloc): the candidate tables grow 8x per
+  // ASCI iteration, and growing the stream-ordered pool by tens of GB costs ~1 s per step
+  char* arena = nullptr;
+  size_t arena_cap = 0, arena_off = 0;
 };
 
 struct b2ci_dets {
@@ -129,7 +133,16 @@ namespace b2ci {
 // ~100 ms, ten times the kernels it serves). Every C-ABI entry that takes a context opens a
 // StreamScope; allocations and frees are ordered on that context's stream.
 cudaStream_t& alloc_stream();  // thread-local, set by StreamScope
+// Large blocks (>= 32 MiB) bypass the stream-ordered pool: growing that pool costs ~50 ms per GB
+// (mapping granule by granule), a plain cudaMalloc ~7 ms per GB. They are cached per (device,
+// stream) in a process-wide free list and handed out again to requests of similar size; reuse on
+// the same stream is ordered by the stream itself. capi.cu.
+void* big_cache_alloc(size_t bytes, cudaStream_t st);
+bool big_cache_free(void* p, cudaStream_t st);   // false: not a cached block
+void big_cache_trim();                            // cudaFree every idle block of the current device
+constexpr size_t BIG_BLOCK_MIN = size_t(32) << 20;
 inline void* dev_alloc(size_t bytes) {
+  if (bytes >= BIG_BLOCK_MIN) return big_cache_alloc(bytes, alloc_stream());
   void* p = nullptr;
   cudaError_t e = cudaMallocAsync(&p, bytes, alloc_stream());
   if (e != cudaSuccess) {
@@ -139,7 +152,9 @@ inline void* dev_alloc(size_t bytes) {
   return p;
 }
 inline void dev_free(void* p) {
-  if (p) cudaFreeAsync(p, alloc_stream());
+  if (!p) return;
+  if (big_cache_free(p, alloc_stream())) return;
+  cudaFreeAsync(p, alloc_stream());
 }
 struct StreamScope {
   cudaStream_t prev;
@@ -206,6 +221,36 @@ inline void big_release(b2ci_ctx* ctx, int which, void* p, size_t cap) {
   } else {
     dev_free(p);
   }
+}
+// bump allocation from the context's workspace; arena_reset() at the start of a phase
+inline void arena_reserve(b2ci_ctx* ctx, size_t bytes) {
+  if (bytes <= ctx->arena_cap) return;
+  cudaStreamSynchronize(ctx->stream);
+  if (ctx->arena) cudaFree(ctx->arena);
+  ctx->arena = nullptr;
+  ctx->arena_cap = 0;
+  const size_t want = bytes + bytes / 8;
+  void* p = nullptr;
+  if (cudaMalloc(&p, want) != cudaSuccess) {
+    cudaGetLastError();
+    if (cudaMalloc(&p, bytes) != cudaSuccess) {
+      cudaGetLastError();
+      throw Error("workspace allocation of " + std::to_string(bytes >> 20) + " MiB failed");
+    }
+    ctx->arena_cap = bytes;
+  } else {
+    ctx->arena_cap = want;
+  }
+  ctx->arena = static_cast<char*>(p);
+}
+inline void arena_reset(b2ci_ctx* ctx) { ctx->arena_off = 0; }
+template <typename T>
+inline T* arena_take(b2ci_ctx* ctx, size_t count) {
+  const size_t bytes = (count * sizeof(T) + 255) & ~size_t(255);
+  if (ctx->arena_off + bytes > ctx->arena_cap) throw Error("workspace overflow (internal sizing error)");
+  T* p = reinterpret_cast<T*>(ctx->arena + ctx->arena_off);
+  ctx->arena_off += bytes;
+  return p;
 }
 constexpr int PINNED_WORDS = 64;
 inline int64_t* pinned_words(b2ci_ctx* ctx) {
