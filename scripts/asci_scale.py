@@ -1,6 +1,8 @@
 #!/usr/bin/env python
 """Run the b200_asci plugin on a named synthetic workload and print per-phase statistics.
-    python scripts/asci_scale.py n2_asci26 100000 [key=value ...]"""
+    python scripts/asci_scale.py n2_asci26 100000 [key=value ...]
+Under torchrun (one process per GPU) the rows of H and the key partitions of the search are
+sharded over the ranks; rank 0 prints."""
 import json
 import os
 import sys
@@ -20,6 +22,14 @@ for a in sys.argv[3:]:
             kw[k] = float(v)
         except ValueError:
             kw[k] = v
+rank, world = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
+if world > 1:
+    import torch
+    import torch.distributed as dist
+    local = int(os.environ.get("LOCAL_RANK", rank))
+    torch.cuda.set_device(local)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    alg.init_distributed_from_torch(local)
 sp = W.config(name)
 ham = data.Hamiltonian(sp.T, sp.V, sp.core_energy)
 c = alg.create("multi_configuration_calculator", "b200_asci", ntdets_max=nt, ci_residual_tolerance=1e-8, **kw)
@@ -31,4 +41,9 @@ except Exception as e:  # report what failed and the statistics so far
     out = {"error": str(e)[:300]}
 out["wall_s"] = time.perf_counter() - t0
 out.update(alg.last_run_stats())
-print(json.dumps(out))
+out["world"] = world
+if rank == 0:
+    print(json.dumps(out))
+if world > 1:
+    dist.barrier()
+    dist.destroy_process_group()
