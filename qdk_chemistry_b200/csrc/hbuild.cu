@@ -234,7 +234,7 @@ k_rows(const RowArgs A) {
     flush_group(INT64_MAX);
     if (qn > 0) process_batch<FILL, EVAL>(A, i, ai, bi, q, qn, lane, out, cnt);
   }
-  if (!FILL && lane == 0) A.row_cnt[row] = cnt;
+  if (lane == 0 && A.row_cnt) A.row_cnt[row] = cnt;
 }
 
 // beta groups: determinant indices sorted by beta string (stable), group boundaries
@@ -1307,25 +1307,37 @@ void hbuild_csr(b2ci_ctx* ctx, const b2ci_dets* dets, int64_t row_begin, int64_t
   A.colind = nullptr;
   A.nzval = nullptr;
   const unsigned grid = unsigned((nrows + ROW_WARPS - 1) / ROW_WARPS);
-  int64_t nnz = 0;
+  // Count pass = the scan alone (structural connections, no matrix element); the fill pass
+  // evaluates every element ONCE, writes the survivors compacted inside the row's structural
+  // slot and records how many there were; rows are packed afterwards only if something was
+  // dropped (threshold_parallel, csr_matrix.hpp:317-370). Evaluating in both passes doubled
+  // the cost of the ASCI builds.
+  int64_t nslots = 0;
+  DevBuf<int64_t> slot_ptr(nrows + 1);
   {
     ScopedTimer t(ctx, "h_build.count");
     DevBuf<int32_t> row_cnt(nrows);
     A.row_cnt = row_cnt;
-    if (thr > 0.0) k_rows<false, true><<<grid, ROW_WARPS * 32, 0, st>>>(A);
-    else k_rows<false, false><<<grid, ROW_WARPS * 32, 0, st>>>(A);
+    k_rows<false, false><<<grid, ROW_WARPS * 32, 0, st>>>(A);
     ctx->launches++;
     B2_CHECK_LAUNCH();
-    exclusive_scan_i32_to_i64(ctx, row_cnt, rowptr, nrows);
-    B2_CUDA(cudaMemcpyAsync(&nnz, rowptr.p + nrows, 8, cudaMemcpyDeviceToHost, st));
+    exclusive_scan_i32_to_i64(ctx, row_cnt, slot_ptr, nrows);
+    int64_t* pin = pinned_words(ctx);
+    B2_CUDA(cudaMemcpyAsync(pin, slot_ptr.p + nrows, 8, cudaMemcpyDeviceToHost, st));
     B2_CUDA(cudaStreamSynchronize(st));
+    nslots = pin[0];
   }
-  DevBuf<int32_t> colind(nnz > 0 ? nnz : 1);
-  DevBuf<double> nzval(nnz > 0 ? nnz : 1);
+  DevBuf<int32_t> colind, kept(nrows);
+  DevBuf<double> nzval;
+  size_t ci_cap = 0, nz_cap = 0;
+  colind.p = static_cast<int32_t*>(big_alloc(ctx, 0, size_t(nslots > 0 ? nslots : 1) * sizeof(int32_t), &ci_cap));
+  colind.n = ci_cap / sizeof(int32_t);
+  nzval.p = static_cast<double*>(big_alloc(ctx, 1, size_t(nslots > 0 ? nslots : 1) * sizeof(double), &nz_cap));
+  nzval.n = nz_cap / sizeof(double);
   {
     ScopedTimer t(ctx, "h_build.fill");
-    A.row_cnt = nullptr;
-    A.rowptr = rowptr;
+    A.row_cnt = kept;
+    A.rowptr = slot_ptr;
     A.colind = colind;
     A.nzval = nzval;
     if (thr > 0.0) k_rows<true, true><<<grid, ROW_WARPS * 32, 0, st>>>(A);
@@ -1333,7 +1345,34 @@ void hbuild_csr(b2ci_ctx* ctx, const b2ci_dets* dets, int64_t row_begin, int64_t
     ctx->launches++;
     B2_CHECK_LAUNCH();
   }
+  int64_t nnz = nslots;
+  if (thr > 0.0) {
+    ScopedTimer t(ctx, "h_build.thresh");
+    exclusive_scan_i32_to_i64(ctx, kept, rowptr, nrows);
+    int64_t* pin = pinned_words(ctx);
+    B2_CUDA(cudaMemcpyAsync(pin, rowptr.p + nrows, 8, cudaMemcpyDeviceToHost, st));
+    B2_CUDA(cudaStreamSynchronize(st));
+    nnz = pin[0];
+    if (nnz != nslots) {
+      DevBuf<int32_t> ci_f(nnz > 0 ? nnz : 1);
+      DevBuf<double> nz_f(nnz > 0 ? nnz : 1);
+      k_compact_rows<<<unsigned((nrows * 32 + ROW_WARPS * 32 - 1) / (ROW_WARPS * 32)), ROW_WARPS * 32, 0, st>>>(
+          nrows, slot_ptr, rowptr, colind, nzval, ci_f, nz_f);
+      ctx->launches++;
+      B2_CHECK_LAUNCH();
+      B2_CUDA(cudaStreamSynchronize(st));
+      big_release(ctx, 0, colind.take(), ci_cap);
+      big_release(ctx, 1, nzval.take(), nz_cap);
+      ci_cap = nz_cap = 0;
+      colind = std::move(ci_f);
+      nzval = std::move(nz_f);
+    }
+  } else {
+    rowptr = std::move(slot_ptr);
+  }
   B2_CUDA(cudaStreamSynchronize(st));
+  out->colind_cap = ci_cap;
+  out->nzval_cap = nz_cap;
   out->nnz = nnz;
   out->rowptr = rowptr.take();
   out->colind = colind.take();
