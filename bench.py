@@ -308,7 +308,8 @@ def measure(ctx, sp, name, args, world, rank, local_rank, dist, torch, steps, wa
         e1.record()
         flush.zero_()
         e2.record()
-        H.sigma_sharded(x_local.data_ptr(), x_full.data_ptr(), y_local.data_ptr())
+        # x_full = NULL: the library's own exchange buffers are used (peer-to-peer stores over NVLink)
+        H.sigma_sharded(x_local.data_ptr(), 0 if world > 1 else x_full.data_ptr(), y_local.data_ptr())
         e3.record()
         torch.cuda.synchronize()
         if timed:
@@ -359,7 +360,7 @@ def measure(ctx, sp, name, args, world, rank, local_rank, dist, torch, steps, wa
         build_ms=mx(float(np.mean(T["build"]))), sigma_ms=mx(float(np.mean(T["sigma"]))),
         fill_ms=mx(float(np.mean(T["fill"]))), count_ms=mx(float(np.mean(T["count"]))),
         setup_ms=mx(float(np.mean(T["setup"]))), thresh_ms=mx(float(np.mean(T["thresh"]))),
-        launches=int(launches), clocks=clocks, wall=wall1 - wall0, group=int(group), slices=bool(slices),
+        launches=int(launches), clocks=clocks, p2p=ctx.timer_ms("comm.p2p"), wall=wall1 - wall0, group=int(group), slices=bool(slices),
         # algorithmic bytes per launch on THIS rank
         B_sigma=int(nnz_local * 12 + (nrows + 1) * 8 + n * 8 + nrows * 8),
         B_fill=int(n * 16 + nnz_local * 12 + (nrows + 1) * 8),
@@ -460,7 +461,10 @@ def run_b200(args):
                                "bytes_per_launch": m["B_sigma"]},
             "e2e": {"value": m["nnz_total"] / (m["e2e_ms"] * 1e-3), "unit": "nnz/s", "ms": m["e2e_ms"],
                     "h2d_bytes_per_step": m["h2d"], "d2h_bytes_per_step": m["d2h"]},
-            "gpu_launches": m["launches"], "clocks": m["clocks"], "davidson": m.get("davidson"),
+            "gpu_launches": m["launches"], "clocks": m["clocks"],
+            "sigma_exchange": ("single GPU" if world == 1 else
+                               ("peer-to-peer stores over NVLink (k_push + flag wait)" if m["p2p"] == 1.0
+                                else "ncclAllGather")), "davidson": m.get("davidson"),
             "energy_total": (m.get("davidson") or {}).get("E0_total"),
             "wall_s_timed_region": m["wall"],
         }

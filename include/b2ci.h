@@ -92,10 +92,12 @@ int b2ci_csr_free(b2ci_ctx* ctx, b2ci_csr* m);
 int b2ci_spmv(b2ci_ctx* ctx, const b2ci_csr* m, const double* x_dev, double* y_dev);
 /* same with HOST buffers (copies inside) */
 int b2ci_spmv_host(b2ci_ctx* ctx, const b2ci_csr* m, const double* x, double* y);
-/* Row-sharded sigma: all-gather of the local trial-vector blocks into x_full_dev (ncols
- * entries, scratch owned by the caller) followed by the local SpMV -- the NCCL counterpart of
- * sparsexx::spblas::pgespmv (sparsexx/spblas/pspmbv.hpp:316-405). Without a communicator it
- * is b2ci_spmv(x_local_dev). DEVICE pointers. */
+/* Row-sharded sigma: exchange of the local trial-vector blocks followed by the local SpMV -- the
+ * counterpart of sparsexx::spblas::pgespmv (sparsexx/spblas/pspmbv.hpp:316-405). With peer access
+ * between the GPUs every rank stores its block directly into the other ranks' exchange buffers
+ * over NVLink (one push kernel + a flag wait, no NCCL launch); otherwise ncclAllGather. x_full_dev
+ * (ncols entries) may be NULL; when given it also receives the gathered vector. Without a
+ * communicator it is b2ci_spmv(x_local_dev). DEVICE pointers. */
 int b2ci_sigma_sharded(b2ci_ctx* ctx, const b2ci_csr* m, const double* x_local_dev,
                        double* x_full_dev, double* y_local_dev);
 /* Optional: tell a row block how the rows are split over the ranks (row_offsets has nranks + 1

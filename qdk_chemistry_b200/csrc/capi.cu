@@ -403,8 +403,10 @@ int b2ci_sigma_sharded(b2ci_ctx* ctx, const b2ci_csr* m, const double* x_local_d
     if (mm->row_offsets[ctx->rank] != m->row_begin || mm->row_offsets[ctx->nranks] != m->ncols)
       throw Error("b2ci_sigma_sharded: row blocks of the ranks do not tile [0, ncols) in rank order");
   }
-  comm_allgather_rows(ctx, x_local_dev, x_full_dev, mm->row_offsets);
-  spmv_launch(ctx, m, x_full_dev, y_local_dev);
+  const double* xg = comm_exchange_rows(ctx, x_local_dev, mm->row_offsets, x_full_dev);
+  if (x_full_dev && xg != x_full_dev)  // the caller asked for the gathered vector as well
+    B2_CUDA(cudaMemcpyAsync(x_full_dev, xg, size_t(m->ncols) * 8, cudaMemcpyDeviceToDevice, ctx->stream));
+  spmv_launch(ctx, m, xg, y_local_dev);
   return 0;
   B2_CATCH
 }

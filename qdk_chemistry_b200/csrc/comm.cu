@@ -82,7 +82,206 @@ void comm_init(b2ci_ctx* ctx, const void* id128, int rank, int nranks) {
   ctx->nccl_comm = comm;
 }
 
+// ---------------------------------------------------------------------------------------------
+// Peer-to-peer exchange of the trial vector (the sigma step's only communication).
+//
+// Every rank owns two exchange buffers of N doubles (plain cudaMalloc, exported with CUDA IPC)
+// and a flag word per peer. One sigma = epoch e:
+//   k_push : copies this rank's block into buffer e&1 of EVERY rank (coalesced stores over
+//            NVLink / NVSwitch), fences, and the last CTA publishes flag[rank] = e on every peer
+//   k_wait : one warp spins until all peers' flags reached e
+//   k_spmv : unchanged, reads the local buffer
+// No NCCL launch, no staging. Two buffers make the write-after-read hazard impossible: a peer can
+// only push epoch e+2 (same buffer as e) after it saw my flag e+1, which I publish after my SpMV
+// of epoch e on the same stream. If IPC or peer access is unavailable on any rank, all ranks
+// fall back to ncclAllGather together.
+namespace {
+struct P2P {
+  bool tried = false, ok = false;
+  size_t cap = 0;  // doubles per buffer
+  double* xbuf[2] = {nullptr, nullptr};
+  unsigned long long* flags = nullptr;  // [nranks], written by the peers
+  unsigned int* done = nullptr;         // CTA counter of k_push
+  double** d_peer_x[2] = {nullptr, nullptr};
+  unsigned long long** d_peer_flag = nullptr;
+  std::vector<void*> opened;
+  unsigned long long epoch = 0;
+  double* fallback = nullptr;  // library-owned gather buffer of the NCCL path
+  size_t fallback_cap = 0;
+};
+struct IpcPack { cudaIpcMemHandle_t h[3]; };
+
+constexpr int PUSH_THREADS = 256;
+__global__ void __launch_bounds__(PUSH_THREADS)
+k_push(const double* __restrict__ local, int64_t nloc, int64_t row0, double* const* __restrict__ peer_x,
+       unsigned long long* const* __restrict__ peer_flag, int nranks, int rank, unsigned long long epoch,
+       unsigned int* __restrict__ done) {
+  const int64_t stride = int64_t(gridDim.x) * blockDim.x;
+  for (int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < nloc; i += stride) {
+    const double v = local[i];
+    for (int p = 0; p < nranks; ++p) peer_x[p][row0 + i] = v;
+  }
+  __threadfence_system();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const unsigned int prev = atomicAdd(done, 1u);
+    if (prev == gridDim.x - 1) {  // every CTA's stores are fenced: publish
+      *done = 0;
+      __threadfence_system();
+      for (int p = 0; p < nranks; ++p)
+        asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(peer_flag[p] + rank), "l"(epoch) : "memory");
+    }
+  }
+}
+__global__ void k_wait(const unsigned long long* __restrict__ flags, int nranks, unsigned long long epoch) {
+  const int r = threadIdx.x;
+  if (r >= nranks) return;
+  const long long t0 = clock64();
+  for (;;) {
+    unsigned long long f;
+    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(f) : "l"(flags + r) : "memory");
+    if (f >= epoch) break;
+    if (clock64() - t0 > 20000000000ll) __trap();  // ~10 s: a peer is gone; fail instead of hanging
+    __nanosleep(64);
+  }
+}
+
+P2P* p2p_state(b2ci_ctx* ctx) {
+  if (!ctx->p2p) ctx->p2p = new P2P;
+  return static_cast<P2P*>(ctx->p2p);
+}
+void p2p_release(b2ci_ctx* ctx, P2P* s) {
+  cudaStreamSynchronize(ctx->stream);
+  for (void* q : s->opened) cudaIpcCloseMemHandle(q);
+  s->opened.clear();
+  for (int b = 0; b < 2; ++b) {
+    if (s->xbuf[b]) cudaFree(s->xbuf[b]);
+    if (s->d_peer_x[b]) cudaFree(s->d_peer_x[b]);
+    s->xbuf[b] = nullptr;
+    s->d_peer_x[b] = nullptr;
+  }
+  if (s->flags) cudaFree(s->flags);
+  if (s->done) cudaFree(s->done);
+  if (s->d_peer_flag) cudaFree(s->d_peer_flag);
+  s->flags = nullptr; s->done = nullptr; s->d_peer_flag = nullptr;
+  s->cap = 0;
+  s->ok = false;
+  cudaGetLastError();
+}
+// collective: (re)create the exchange buffers for vectors of n doubles
+void p2p_setup(b2ci_ctx* ctx, P2P* s, size_t n) {
+  const int nr = ctx->nranks, me = ctx->rank;
+  cudaStream_t st = ctx->stream;
+  p2p_release(ctx, s);
+  s->tried = true;
+  s->epoch = 0;
+  int64_t good = 1;
+  const size_t cap = (n + 1023) & ~size_t(1023);
+  IpcPack mine;
+  memset(&mine, 0, sizeof(mine));
+  if (getenv("B2CI_NO_P2P")) good = 0;
+  if (good) {
+    bool a = cudaMalloc(&s->xbuf[0], cap * 8) == cudaSuccess && cudaMalloc(&s->xbuf[1], cap * 8) == cudaSuccess &&
+             cudaMalloc(&s->flags, size_t(nr) * 8) == cudaSuccess && cudaMalloc(&s->done, 4) == cudaSuccess;
+    a = a && cudaMemset(s->flags, 0, size_t(nr) * 8) == cudaSuccess && cudaMemset(s->done, 0, 4) == cudaSuccess;
+    a = a && cudaIpcGetMemHandle(&mine.h[0], s->xbuf[0]) == cudaSuccess &&
+        cudaIpcGetMemHandle(&mine.h[1], s->xbuf[1]) == cudaSuccess &&
+        cudaIpcGetMemHandle(&mine.h[2], s->flags) == cudaSuccess;
+    if (!a) { cudaGetLastError(); good = 0; }
+  }
+  // exchange the handles (every rank takes part whatever its own outcome)
+  std::vector<IpcPack> all(nr);
+  {
+    DevBuf<char> send(sizeof(IpcPack)), recv(sizeof(IpcPack) * size_t(nr));
+    B2_CUDA(cudaMemcpyAsync(send, &mine, sizeof(IpcPack), cudaMemcpyHostToDevice, st));
+    comm_allgather_bytes(ctx, send, recv, sizeof(IpcPack));
+    B2_CUDA(cudaMemcpyAsync(all.data(), recv, sizeof(IpcPack) * size_t(nr), cudaMemcpyDeviceToHost, st));
+    B2_CUDA(cudaStreamSynchronize(st));
+  }
+  comm_allreduce_sum_i64_host(ctx, &good, 1);
+  good = good == nr ? 1 : 0;
+  std::vector<double*> px0(nr, nullptr), px1(nr, nullptr);
+  std::vector<unsigned long long*> pf(nr, nullptr);
+  if (good) {
+    for (int r = 0; r < nr && good; ++r) {
+      if (r == me) { px0[r] = s->xbuf[0]; px1[r] = s->xbuf[1]; pf[r] = s->flags; continue; }
+      void* q[3] = {nullptr, nullptr, nullptr};
+      for (int k = 0; k < 3; ++k) {
+        if (cudaIpcOpenMemHandle(&q[k], all[r].h[k], cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) {
+          cudaGetLastError();
+          good = 0;
+          break;
+        }
+        s->opened.push_back(q[k]);
+      }
+      px0[r] = static_cast<double*>(q[0]);
+      px1[r] = static_cast<double*>(q[1]);
+      pf[r] = static_cast<unsigned long long*>(q[2]);
+    }
+  }
+  if (good) {
+    bool a = cudaMalloc(&s->d_peer_x[0], size_t(nr) * 8) == cudaSuccess &&
+             cudaMalloc(&s->d_peer_x[1], size_t(nr) * 8) == cudaSuccess &&
+             cudaMalloc(&s->d_peer_flag, size_t(nr) * 8) == cudaSuccess;
+    a = a && cudaMemcpy(s->d_peer_x[0], px0.data(), size_t(nr) * 8, cudaMemcpyHostToDevice) == cudaSuccess &&
+        cudaMemcpy(s->d_peer_x[1], px1.data(), size_t(nr) * 8, cudaMemcpyHostToDevice) == cudaSuccess &&
+        cudaMemcpy(s->d_peer_flag, pf.data(), size_t(nr) * 8, cudaMemcpyHostToDevice) == cudaSuccess;
+    if (!a) { cudaGetLastError(); good = 0; }
+  }
+  // all or nothing: one rank without peer access sends everybody to the NCCL path
+  int64_t agree = good;
+  comm_allreduce_sum_i64_host(ctx, &agree, 1);
+  if (agree == nr) {
+    s->ok = true;
+    s->cap = cap;
+  } else {
+    p2p_release(ctx, s);
+  }
+  ctx->timers["comm.p2p"] = s->ok ? 1. : 0.;
+}
+}  // namespace
+
+const double* comm_exchange_rows(b2ci_ctx* ctx, const double* local, const std::vector<int64_t>& off,
+                                 double* fallback_full) {
+  const int nr = ctx->nranks, me = ctx->rank;
+  if (nr == 1) return local;
+  const size_t n = size_t(off[nr]);
+  P2P* s = p2p_state(ctx);
+  if (!s->tried || (s->ok && s->cap < n)) p2p_setup(ctx, s, n);  // collective: n is the same everywhere
+  if (s->ok) {
+    const unsigned long long e = ++s->epoch;
+    const int b = int(e & 1ull);
+    const int64_t nloc = off[me + 1] - off[me];
+    const int grid = int(std::max<int64_t>(1, std::min<int64_t>(ctx->sm_count, (nloc + PUSH_THREADS - 1) / PUSH_THREADS)));
+    k_push<<<grid, PUSH_THREADS, 0, ctx->stream>>>(local, nloc, off[me], s->d_peer_x[b], s->d_peer_flag, nr, me, e, s->done);
+    k_wait<<<1, 32, 0, ctx->stream>>>(s->flags, nr, e);
+    ctx->launches += 2;
+    B2_CHECK_LAUNCH();
+    return s->xbuf[b];
+  }
+  double* full = fallback_full;
+  if (!full) {
+    if (s->fallback_cap < n) {
+      if (s->fallback) cudaFree(s->fallback);
+      s->fallback = nullptr;
+      s->fallback_cap = 0;
+      B2_CUDA(cudaMalloc(&s->fallback, n * 8));
+      s->fallback_cap = n;
+    }
+    full = s->fallback;
+  }
+  comm_allgather_rows(ctx, local, full, off);
+  return full;
+}
+
 void comm_destroy(b2ci_ctx* ctx) {
+  if (ctx->p2p) {
+    P2P* s = static_cast<P2P*>(ctx->p2p);
+    p2p_release(ctx, s);
+    if (s->fallback) cudaFree(s->fallback);
+    delete s;
+    ctx->p2p = nullptr;
+  }
   if (ctx->nccl_comm) {
     api().CommDestroy((ncclComm_t)ctx->nccl_comm);
     ctx->nccl_comm = nullptr;

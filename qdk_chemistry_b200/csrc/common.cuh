@@ -108,6 +108,8 @@ struct b2ci_ctx {
   // ASCI iteration, and growing the stream-ordered pool by tens of GB costs ~1 s per step
   char* arena = nullptr;
   size_t arena_cap = 0, arena_off = 0;
+  // peer-to-peer exchange state of the sharded sigma (comm.cu), NULL until first use
+  void* p2p = nullptr;
 };
 
 struct b2ci_dets {
@@ -335,6 +337,11 @@ void sym_eig_lowest(int n, const double* A, int lda, double* lambda, double* vec
 void comm_allgather_rows(b2ci_ctx* ctx, const double* local, double* full,
                          const std::vector<int64_t>& row_offsets);
 void comm_allreduce_sum(b2ci_ctx* ctx, double* dev_buf, int64_t n);
+// Gather the row blocks of all ranks: returns a device pointer to the full vector. With peer
+// access every rank writes its block straight into the others' buffers over NVLink (one small
+// kernel + a flag wait); otherwise NCCL gathers into `fallback_full` (or a library buffer).
+const double* comm_exchange_rows(b2ci_ctx* ctx, const double* local, const std::vector<int64_t>& off,
+                                 double* fallback_full);
 void comm_allreduce_sum_i64_host(b2ci_ctx* ctx, int64_t* host_vals, int n);
 void comm_allgather_i64_host(b2ci_ctx* ctx, int64_t local, std::vector<int64_t>& all);
 void comm_allgather_bytes(b2ci_ctx* ctx, const void* send, void* recv, size_t bytes_per_rank);

@@ -590,10 +590,7 @@ int davidson(b2ci_ctx* ctx, const b2ci_csr* m, int64_t max_m, double tol, double
   auto sigma = [&](const double* v_local, double* av_local) {
     DeferredScope t(timers, "davidson.OP_DUR");
     const double* xin = v_local;
-    if (ctx->nranks > 1) {
-      comm_allgather_rows(ctx, v_local, xfull, row_offsets);
-      xin = xfull;
-    }
+    if (ctx->nranks > 1) xin = comm_exchange_rows(ctx, v_local, row_offsets, xfull);
     spmv_launch(ctx, m, xin, av_local);
     T["davidson.OP_CALLS"] += 1.;
   };

@@ -59,6 +59,16 @@ def main():
     yref = Hfull.spmv(x)
     out["gather_exact"] = bool(np.array_equal(xf.cpu().numpy(), x))
     out["sigma_bit_exact"] = bool(np.array_equal(yl.cpu().numpy(), yref[r0:r1]))
+    out["p2p"] = ctx.timer_ms("comm.p2p")
+    # repeated sigmas with changing vectors (exchange-buffer parity, epochs) and x_full = NULL
+    ok = True
+    for rep in range(5):
+        xr = np.random.default_rng(100 + rep).normal(size=n)
+        xl2 = torch.from_numpy(xr[r0:r1].copy()).cuda()
+        Hloc.sigma_sharded(xl2.data_ptr(), 0, yl.data_ptr())
+        torch.cuda.synchronize()
+        ok = ok and np.array_equal(yl.cpu().numpy(), Hfull.spmv(xr)[r0:r1])
+    out["sigma_repeat_exact"] = bool(ok)
     # the same with the split supplied by the caller (no exchange of block sizes)
     Hloc2 = ctx.hbuild(dets, EPS, (r0, r1))
     Hloc2.set_row_partition(cuts)

@@ -30,7 +30,7 @@ def test_row_sharded_path_matches_single_gpu(world):
     assert len(res) == world
     for r in res:
         assert r["block_bit_exact"] and r["gather_exact"] and r["sigma_bit_exact"]
-        assert r["bad_partition_rejected"]
+        assert r["bad_partition_rejected"] and r["sigma_repeat_exact"]
         assert abs(r["E_sharded"] - r["E_single"]) < 1e-9          # north_star: 1e-8 Eh
         assert abs(r["niter_sharded"] - r["niter_single"]) <= 1   # serial davidson semantics kept
         assert abs(r["overlap"] - 1) < 1e-7 and abs(r["norm"] - 1) < 1e-12
