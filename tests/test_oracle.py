@@ -213,3 +213,22 @@ def test_port_rdm_properties():
     assert np.abs(t - (aaaa + bbbb + aabb + aabb.transpose(2, 3, 0, 1))).max() < 1e-14
     Er = np.sum(o * sp.T.reshape(n, n, order="F")) + np.sum(t * sp.V.reshape((n,) * 4, order="F"))
     assert abs(Er - E) < 1e-9
+
+
+def test_wavefunction_text_io_round_trip(tmp_path):
+    """MACIS text wavefunctions (wavefunction_io.hpp): the reference's own o2.wfn.dat fixture is
+    read, written back and re-read without loss; canonical strings follow sd_operations.hpp:478-525."""
+    from qdk_chemistry_b200 import wavefunction_io as wio
+    a, b, c, meta = wio.read_wavefunction(os.path.join(GOLDEN, "o2.wfn.dat"))
+    assert meta == (120, 6, 5, 3) and len(c) == 120
+    assert all(bin(int(x)).count("1") == 5 for x in a) and all(bin(int(x)).count("1") == 3 for x in b)
+    assert abs(c @ c - 1.0) < 1e-10
+    assert wio.to_canonical_string(0b000111, 0b001011, 6) == "22ud00"
+    assert wio.from_canonical_string("222uu0") == (0b011111, 0b000111)
+    assert c[0] == -6.8728389771404168e-09 and wio.to_canonical_string(int(a[0]), int(b[0]), 6) == "222uu0"
+    out = tmp_path / "w.dat"
+    wio.write_wavefunction(str(out), 6, a, b, c)
+    a2, b2, c2, meta2 = wio.read_wavefunction(str(out))
+    assert meta2 == meta and np.array_equal(a2, a) and np.array_equal(b2, b) and np.array_equal(c2, c)
+    lines = out.read_text().splitlines()
+    assert lines[0] == "120 6 5 3" and lines[1] == "       -6.8728389771404168e-09 222uu0 "
