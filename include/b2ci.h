@@ -177,6 +177,20 @@ int b2ci_form_rdms(b2ci_ctx* ctx, const b2ci_dets* dets, const double* C, double
 int b2ci_form_rdms_spin_dep(b2ci_ctx* ctx, const b2ci_dets* dets, const double* C, double* ordm_aa,
                             double* ordm_bb, double* trdm_aaaa, double* trdm_bbbb, double* trdm_aabb);
 
+/* ---- orbital entropies: HamiltonianGenerator::form_entropies with bra == ket
+ * (sorted_double_loop.hpp:760-905, util/entropies.hpp; called from macis_base.hpp:219-245 for
+ * calculate_single_orbital_entropies / _two_orbital_entropies / _mutual_information).
+ * s1: norb single-orbital entropies (required); s2, mi: norb x norb column-major, either may be
+ * NULL (both NULL: only the diagonal pairs are visited, as the reference does). HOST pointers. */
+int b2ci_form_entropies(b2ci_ctx* ctx, const b2ci_dets* dets, const double* C, double* s1, double* s2, double* mi);
+/* the two halves of it, for parity tests: the OrbitalRDMIntermediates (entropies.hpp:62-205;
+ * 3 vectors of norb then 18 norb x norb matrices, order of csrc/entropy.cu) accumulated on the
+ * device, and the host assembly of the entropies from them (no GPU needed) */
+int64_t b2ci_entropy_intermediate_count(int norb, int need_s2);
+int b2ci_entropy_intermediates(b2ci_ctx* ctx, const b2ci_dets* dets, const double* C, int need_s2, double* out);
+int b2ci_host_entropies_from_intermediates(int norb, int need_s2, const double* intermediates, double* s1,
+                                           double* s2, double* mi);
+
 /* ---- host-side evaluation of the SAME device functions (they are __host__ __device__):
  * lets CPU-only tests check the Slater-Condon code against the oracle without a GPU. */
 double b2ci_host_matrix_element(int norb, const double* T, const double* V, uint64_t bra_alpha,

@@ -379,3 +379,188 @@ def asci_run(ham: Ham, na: int, nb: int, refine: bool = True, **settings):
     if refine and s["max_refine_iter"]:
         E, a, b, X = asci_refine(ham, s, E, a, b, X)
     return E, a, b, X
+
+
+# ---------------------------------------------------------------------------------------
+# Orbital entropies (util/entropies.hpp; SortedDoubleLoopHamiltonianGenerator::form_entropies,
+# sorted_double_loop.hpp:760-905). Python loops: small cases only.
+# ---------------------------------------------------------------------------------------
+ENT_VECS = ("a_ii", "b_ii", "ab_iiii")
+ENT_MATS = ("a_ij", "b_ij", "aa_iijj", "bb_iijj", "ab_iijj", "ab_ijjj", "ab_jijj", "ab_jjij", "ab_jjji",
+            "ab_ijij", "ab_ijji", "aab_iijjjj", "abb_jjiijj", "aab_iijjii", "abb_iiiijj", "abb_ijiijj",
+            "aab_iijjij", "aabb_iijjiijj")
+
+
+def _occ(x):
+    x = int(x)
+    return [i for i in range(64) if (x >> i) & 1]
+
+
+def _sx(bra, ket, ex):
+    """single_excitation_sign_indices (sd_operations.hpp:394-402)"""
+    bra, ket, ex = int(bra), int(ket), int(ex)
+    o1 = ((ket & ex) & -(ket & ex)).bit_length() - 1
+    v1 = ((bra & ex) & -(bra & ex)).bit_length() - 1
+    lo, hi = min(o1, v1), max(o1, v1)
+    between = ket & ((1 << hi) - 1) & ~((1 << (lo + 1)) - 1)
+    return o1, v1, -1.0 if bin(between).count("1") & 1 else 1.0
+
+
+def entropy_intermediates(norb, alpha, beta, C, need_s2=True):
+    """OrbitalRDMIntermediates accumulated over the pairs i <= j with |C_i C_j| > 1e-16
+    (eval_ordm_intermediates, entropies.hpp:906-962; contributions :212-475). Returns a dict of
+    vectors (n) and Fortran-indexed matrices M[i, j]."""
+    n = int(norb)
+    I = {k: np.zeros(n) for k in ENT_VECS}
+    I.update({k: np.zeros((n, n)) for k in ENT_MATS})
+    alpha = [int(x) for x in alpha]
+    beta = [int(x) for x in beta]
+    for i in range(len(alpha)):
+        ba, bb = alpha[i], beta[i]
+        if ba == 0:
+            continue
+        oa, ob = _occ(ba), _occ(bb)
+        for j in range(i, len(alpha)):
+            ka, kb = alpha[j], beta[j]
+            if ka == 0:
+                continue
+            exa, exb = ba ^ ka, bb ^ kb
+            ca, cb = bin(exa).count("1"), bin(exb).count("1")
+            if ca > (2 if need_s2 else 0) or cb > (2 if need_s2 else 0):
+                continue
+            val = C[i] * C[j]
+            if not abs(val) > 1e-16:
+                continue
+            if ca == 0 and cb == 0:
+                for p in oa:
+                    I["a_ii"][p] += val
+                for p in ob:
+                    I["b_ii"][p] += val
+                for q in ob:
+                    if q in oa:
+                        I["ab_iiii"][q] += val
+                if not need_s2:
+                    continue
+                for q in oa:
+                    for p in oa:
+                        if p == q:
+                            continue
+                        I["aa_iijj"][p, q] += val
+                        if p in ob:
+                            I["aab_iijjii"][p, q] += val
+                            if q in ob:
+                                I["aabb_iijjiijj"][p, q] += val
+                        if q in ob:
+                            I["aab_iijjjj"][p, q] += val
+                for q in ob:
+                    for p in ob:
+                        if p == q:
+                            continue
+                        I["bb_iijj"][p, q] += val
+                        if p in oa:
+                            I["abb_jjiijj"][q, p] += val
+                        if q in oa:
+                            I["abb_iiiijj"][q, p] += val
+                for q in ob:
+                    for p in oa:
+                        I["ab_iijj"][p, q] += val
+            elif (ca, cb) in ((2, 0), (0, 2)):
+                transpose = cb == 2
+                bra, ket, ex = (bb, kb, exb) if transpose else (ba, ka, exa)
+                occ_os = oa if transpose else ob
+                o1, v1, sign = _sx(bra, ket, ex)
+                sv = sign * val
+                x = I["b_ij"] if transpose else I["a_ij"]
+                x[v1, o1] += sv
+                x[o1, v1] += sv
+                m1, m2 = ("ab_jjij", "ab_jjji") if transpose else ("ab_ijjj", "ab_jijj")
+                if o1 in occ_os:
+                    I[m1][v1, o1] += sv
+                    I[m2][v1, o1] += sv
+                if v1 in occ_os:
+                    I[m1][o1, v1] += sv
+                    I[m2][o1, v1] += sv
+                if o1 in occ_os and v1 in occ_os:
+                    if transpose:
+                        I["aab_iijjij"][o1, v1] += sv
+                        I["aab_iijjij"][v1, o1] += sv
+                    else:
+                        I["abb_ijiijj"][v1, o1] += sv
+                        I["abb_ijiijj"][o1, v1] += sv
+            elif ca == 2 and cb == 2:
+                o2, v2, sb = _sx(ba, ka, exa)
+                o1, v1, sa = _sx(bb, kb, exb)
+                sv = sa * sb * val
+                if o1 == o2 and v1 == v2:
+                    I["ab_ijij"][v1, o1] += sv
+                    I["ab_ijij"][o1, v1] += sv
+                elif o1 == v2 and v1 == o2:
+                    I["ab_ijji"][v1, o1] += sv
+                    I["ab_ijji"][o1, v1] += sv
+    return I
+
+
+def _eig2(a, b, d):
+    hs, hd = 0.5 * (a + d), 0.5 * (a - d)
+    w = math.sqrt(hd * hd + b * b)
+    return hs - w, hs + w
+
+
+def entropies_from_intermediates(I, need_s2=True):
+    """build_s1_entropy / build_s2_entropy / build_mutual_information (entropies.hpp:476-510,
+    552-724, 875-886). The 4x4 block is diagonalised with numpy instead of the reference's Jacobi
+    sweeps (same eigenvalues to rounding)."""
+    eps = float(np.finfo(np.float64).eps)
+    n = len(I["a_ii"])
+    a, b, d = I["a_ii"], I["b_ii"], I["ab_iiii"]
+
+    def h(v):
+        return -v * math.log(v) if v > eps else 0.0
+
+    s1 = np.array([h(1 - a[i] - b[i] + d[i]) + h(a[i] - d[i]) + h(b[i] - d[i]) + h(d[i]) for i in range(n)])
+    if not need_s2:
+        return s1, None, None
+    g = lambda k: I[k]
+    s2 = np.zeros((n, n))
+    for i in range(n):
+        for j in range(i + 1, n):
+            AA, BB, AB = g("aa_iijj")[i, j], g("bb_iijj")[i, j], g("ab_iijj")
+            x1, x2, x3, x4, x5 = (g("aab_iijjjj")[i, j], g("abb_jjiijj")[i, j], g("aab_iijjii")[i, j],
+                                  g("abb_iiiijj")[i, j], g("aabb_iijjiijj")[i, j])
+            e = 0.0
+            e += h(1 - a[i] - b[i] - a[j] - b[j] + d[i] + d[j] + AA + AB[i, j] + AB[j, i] + BB - x1 - x2 - x3 - x4 + x5)
+            v = a[j] - AB[j, i] - AA - AB[j, j] + x1 + x3 + x2 - x5
+            v1 = g("a_ij")[i, j] - g("ab_jijj")[j, i] - g("ab_ijjj")[i, j] + g("abb_ijiijj")[i, j]
+            v2 = a[i] - AB[i, j] - AA - AB[i, i] + x1 + x3 + x4 - x5
+            e += sum(h(t) for t in _eig2(v, v1, v2))
+            v = b[j] - AB[i, j] - BB - AB[j, j] + x4 + x1 + x2 - x5
+            v1 = g("b_ij")[i, j] - g("ab_jjij")[j, i] - g("ab_jjji")[i, j] + g("aab_iijjij")[i, j]
+            v2 = b[i] - AB[j, i] - BB - AB[i, i] + x2 + x3 + x4 - x5
+            e += sum(h(t) for t in _eig2(v, v1, v2))
+            e += h(AA - x3 - x1 + x5)
+            e += h(BB - x4 - x2 + x5)
+            B4 = np.zeros((4, 4))
+            B4[0, 0] = AB[j, j] - x1 - x2 + x5
+            B4[0, 1] = B4[1, 0] = g("ab_ijjj")[i, j] - g("abb_ijiijj")[i, j]
+            B4[0, 2] = B4[2, 0] = -g("ab_jjij")[i, j] + g("aab_iijjij")[i, j]
+            B4[0, 3] = B4[3, 0] = g("ab_ijij")[i, j]
+            B4[1, 1] = AB[i, j] - x4 - x1 + x5
+            B4[1, 2] = B4[2, 1] = -g("ab_ijji")[j, i]
+            B4[1, 3] = B4[3, 1] = g("ab_jjji")[j, i] - g("aab_iijjij")[i, j]
+            B4[2, 2] = AB[j, i] - x3 - x2 + x5
+            B4[2, 3] = B4[3, 2] = -g("ab_jijj")[j, i] + g("abb_ijiijj")[i, j]
+            B4[3, 3] = d[i] - x3 - x4 + x5
+            e += sum(h(float(t)) for t in np.linalg.eigvalsh(B4))
+            e += sum(h(t) for t in _eig2(x1 - x5, -g("aab_iijjij")[i, j], x3 - x5))
+            e += sum(h(t) for t in _eig2(x2 - x5, -g("abb_ijiijj")[i, j], x4 - x5))
+            e += h(x5)
+            s2[i, j] = s2[j, i] = e
+    mi = np.zeros((n, n))
+    for i in range(n):
+        for j in range(i + 1, n):
+            mi[i, j] = mi[j, i] = s1[i] + s1[j] - s2[i, j]
+    return s1, s2, mi
+
+
+def form_entropies(norb, alpha, beta, C, need_s2=True):
+    return entropies_from_intermediates(entropy_intermediates(norb, alpha, beta, C, need_s2), need_s2)

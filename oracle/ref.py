@@ -43,6 +43,7 @@ def lib():
         L.ref_matrix_element.restype = dbl
         L.ref_matrix_element.argtypes = [vp, vp, vp]
         L.ref_form_rdms.argtypes = [vp, i32, vp, i64, vp, i32, vp, vp, vp, vp, vp]
+        L.ref_form_entropies.argtypes = [vp, i32, vp, i64, vp, vp, vp, vp]
         L.ref_hbuild.restype = vp
         L.ref_hbuild.argtypes = [vp, i32, vp, i64, vp, i64, dbl, vp]
         L.ref_csr_from_arrays.restype = vp
@@ -259,6 +260,22 @@ class HamGen:
         if spin_dep:
             return sh(o1, 2), sh(o2, 2), sh(t1, 4), sh(t2, 4), sh(t3, 4)
         return sh(o1, 2), sh(t1, 4)
+
+    def form_entropies(self, dets: np.ndarray, C: np.ndarray, s2: bool = True, mi: bool = True,
+                       generator: str = "sdl"):
+        """form_entropies -> (s1[n], s2[n, n] or None, mutual_information[n, n] or None)"""
+        d = np.ascontiguousarray(dets, dtype=np.uint64)
+        c = np.ascontiguousarray(C, dtype=np.float64)
+        n = self.norb
+        s1 = np.zeros(n)
+        S2 = np.zeros(n * n) if s2 else None
+        MI = np.zeros(n * n) if mi else None
+        rc = lib().ref_form_entropies(self.h, 1 if generator == "double_loop" else 0, _p(d), c.size, _p(c),
+                                      _p(s1), _p(S2), _p(MI))
+        if rc:
+            raise RuntimeError(lib().ref_last_error().decode())
+        sh = lambda a: None if a is None else a.reshape(n, n, order="F")
+        return s1, sh(S2), sh(MI)
 
     def selected_ci_diag(self, dets: np.ndarray, h_el_tol: float, max_m: int,
                          res_tol: float, c0: Optional[np.ndarray] = None):

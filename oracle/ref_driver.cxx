@@ -211,6 +211,20 @@ void rdm_impl(HamGenBase* b, int which, const uint64_t* dets, int64_t n, const d
     hg->gen(which).form_rdms(d.begin(), d.end(), d.begin(), d.end(), c.data(), ms(o1), rs(t1));
 }
 
+// form_entropies of the chosen generator, bra == ket (sorted_double_loop.hpp:760-905)
+template <size_t N>
+void entropy_impl(HamGenBase* b, int which, const uint64_t* dets, int64_t n, const double* C, double* s1,
+                  double* s2, double* mi) {
+  auto* hg = static_cast<HamGen<N>*>(b);
+  auto d = dets_in<N>(dets, n);
+  std::vector<double> c(C, C + n);
+  const size_t no = b->norb;
+  std::vector<double> s1v(no, 0.0);
+  hg->gen(which).form_entropies(d.begin(), d.end(), d.begin(), d.end(), c.data(), s1v,
+                                macis::matrix_span<double>(s2, no, no), macis::matrix_span<double>(mi, no, no));
+  std::copy(s1v.begin(), s1v.end(), s1);
+}
+
 template <size_t N>
 double sci_diag_impl(HamGenBase* b, const uint64_t* dets, int64_t n, double h_el_tol,
                      int64_t max_m, double res_tol, double* C) {
@@ -361,6 +375,16 @@ int ref_form_rdms(void* h, int which, const uint64_t* dets, int64_t n, const dou
   TRY
   if (b->nbits == 64) rdm_impl<64>(b, which, dets, n, C, spin_dep, o1, o2, t1, t2, t3);
   else rdm_impl<128>(b, which, dets, n, C, spin_dep, o1, o2, t1, t2, t3);
+  return 0;
+  CATCH(1)
+}
+int ref_form_entropies(void* h, int which, const uint64_t* dets, int64_t n, const double* C, double* s1,
+                       double* s2, double* mi) {
+  auto* b = static_cast<HamGenBase*>(h);
+  quiet_loggers(0);
+  TRY
+  if (b->nbits == 64) entropy_impl<64>(b, which, dets, n, C, s1, s2, mi);
+  else entropy_impl<128>(b, which, dets, n, C, s1, s2, mi);
   return 0;
   CATCH(1)
 }

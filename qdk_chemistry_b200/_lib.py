@@ -80,6 +80,11 @@ def lib():
     L.b2ci_asci_pt2.argtypes = [vp, vp, i32, vp, i64, dbl, dbl, C.POINTER(dbl), pi64]
     L.b2ci_form_rdms.argtypes = [vp, vp, vp, vp, vp]
     L.b2ci_form_rdms_spin_dep.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp]
+    L.b2ci_form_entropies.argtypes = [vp, vp, vp, vp, vp, vp]
+    L.b2ci_entropy_intermediate_count.restype = i64
+    L.b2ci_entropy_intermediate_count.argtypes = [i32, i32]
+    L.b2ci_entropy_intermediates.argtypes = [vp, vp, vp, i32, vp]
+    L.b2ci_host_entropies_from_intermediates.argtypes = [i32, i32, vp, vp, vp, vp]
     L.b2ci_host_matrix_element.restype = dbl
     L.b2ci_host_matrix_element.argtypes = [i32, vp, vp, u64, u64, u64, u64]
     L.b2ci_host_sym_eig_lower.argtypes = [i32, vp, i32, vp]

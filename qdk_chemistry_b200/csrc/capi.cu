@@ -108,6 +108,10 @@ int asci_search(b2ci_ctx* ctx, const b2ci_asci_search_opts* o, const uint64_t* c
 void form_rdms(b2ci_ctx* ctx, const b2ci_dets* dets, const double* C_host, bool spin_dep, double* o1,
                double* o2, double* t1, double* t2, double* t3);
 
+size_t entropy_intermediate_doubles(int n, bool need_s2);
+void entropy_intermediates(b2ci_ctx* ctx, const b2ci_dets* dets, const double* C_host, bool need_s2, double* out_host);
+void host_entropies_from_intermediates(int n, bool need_s2, const double* I, double* s1, double* s2, double* mi);
+
 namespace {
 __global__ void k_i32_to_i64(const int32_t* __restrict__ in, int64_t n, int64_t* __restrict__ out) {
   const int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
@@ -499,6 +503,34 @@ int b2ci_form_rdms_spin_dep(b2ci_ctx* ctx, const b2ci_dets* dets, const double* 
                             double* ordm_bb, double* trdm_aaaa, double* trdm_bbbb, double* trdm_aabb) {
   B2_TRY_CTX(ctx)
   form_rdms(ctx, dets, C, true, ordm_aa, ordm_bb, trdm_aaaa, trdm_bbbb, trdm_aabb);
+  return 0;
+  B2_CATCH
+}
+
+int b2ci_form_entropies(b2ci_ctx* ctx, const b2ci_dets* dets, const double* C, double* s1, double* s2, double* mi) {
+  B2_TRY_CTX(ctx)
+  if (!s1) throw Error("b2ci_form_entropies: single_orbital_entropies output is NULL");
+  const bool need_s2 = s2 || mi;
+  std::vector<double> I(entropy_intermediate_doubles(ctx->norb, need_s2));
+  entropy_intermediates(ctx, dets, C, need_s2, I.data());
+  host_entropies_from_intermediates(ctx->norb, need_s2, I.data(), s1, s2, mi);
+  return 0;
+  B2_CATCH
+}
+int64_t b2ci_entropy_intermediate_count(int norb, int need_s2) {
+  return int64_t(entropy_intermediate_doubles(norb, need_s2 != 0));
+}
+int b2ci_entropy_intermediates(b2ci_ctx* ctx, const b2ci_dets* dets, const double* C, int need_s2, double* out) {
+  B2_TRY_CTX(ctx)
+  entropy_intermediates(ctx, dets, C, need_s2 != 0, out);
+  return 0;
+  B2_CATCH
+}
+int b2ci_host_entropies_from_intermediates(int norb, int need_s2, const double* intermediates, double* s1,
+                                           double* s2, double* mi) {
+  B2_TRY
+  if (norb < 1 || !intermediates || !s1) throw Error("b2ci_host_entropies_from_intermediates: bad arguments");
+  host_entropies_from_intermediates(norb, need_s2 != 0, intermediates, s1, s2, mi);
   return 0;
   B2_CATCH
 }

@@ -176,6 +176,26 @@ class Context:
         check(lib().b2ci_form_rdms(self.h, dets.h, _p(c), _p(o1), _p(t1)))
         return sh(o1, 2), sh(t1, 4)
 
+    def form_entropies(self, dets: "DetList", C: np.ndarray, two_orbital: bool = True,
+                       mutual_information: bool = True):
+        """form_entropies -> (s1[n], s2[n, n] or None, mutual information [n, n] or None)"""
+        c = np.ascontiguousarray(C, dtype=np.float64)
+        if c.size != len(dets):
+            raise ValueError("one coefficient per determinant")
+        n = self.norb
+        s1 = np.zeros(n)
+        s2 = np.zeros(n * n) if two_orbital else None
+        mi = np.zeros(n * n) if mutual_information else None
+        check(lib().b2ci_form_entropies(self.h, dets.h, _p(c), _p(s1), _p(s2), _p(mi)))
+        sh = lambda a: None if a is None else a.reshape(n, n, order="F")
+        return s1, sh(s2), sh(mi)
+
+    def entropy_intermediates(self, dets: "DetList", C: np.ndarray, need_s2: bool = True) -> np.ndarray:
+        c = np.ascontiguousarray(C, dtype=np.float64)
+        out = np.zeros(lib().b2ci_entropy_intermediate_count(self.norb, int(need_s2)))
+        check(lib().b2ci_entropy_intermediates(self.h, dets.h, _p(c), int(need_s2), _p(out)))
+        return out
+
     def asci_pt2(self, det_words, coeffs, E_asci: float, pt2_tol: float = 1e-16,
                  words_per_det: int = 1):
         """macis::asci_pt2_constraint (asci/pt2.hpp): (EPT2, number of external determinants).
@@ -186,6 +206,16 @@ class Context:
         check(lib().b2ci_asci_pt2(self.h, _p(dw), words_per_det, _p(cc), dw.size // words_per_det,
                                   E_asci, pt2_tol, C.byref(e), C.byref(npt2)))
         return e.value, npt2.value
+
+
+def host_entropies_from_intermediates(norb: int, intermediates: np.ndarray, need_s2: bool = True):
+    """Host assembly of (s1, s2, mutual information) from the flat intermediates (no GPU)."""
+    I = np.ascontiguousarray(intermediates, dtype=np.float64)
+    n = int(norb)
+    s1, s2, mi = np.zeros(n), (np.zeros(n * n) if need_s2 else None), (np.zeros(n * n) if need_s2 else None)
+    check(lib().b2ci_host_entropies_from_intermediates(n, int(need_s2), _p(I), _p(s1), _p(s2), _p(mi)))
+    sh = lambda a: None if a is None else a.reshape(n, n, order="F")
+    return s1, sh(s2), sh(mi)
 
 
 class DetList:

@@ -217,11 +217,23 @@ class Wavefunction {
   std::vector<double> get_active_one_rdm_spin_traced() const;
   std::vector<double> get_active_two_rdm_spin_traced() const;
 
+  // ---- orbital entropies (OrbitalEntropies, wavefunction.hpp:165-180,380-423): vector of n,
+  // matrices n x n column-major; empty = not computed
+  void set_entropies(std::vector<double> single_orbital, std::vector<double> two_orbital,
+                     std::vector<double> mutual_information);
+  bool has_single_orbital_entropies() const { return !s1_.empty(); }
+  bool has_two_orbital_entropies() const { return !s2_.empty(); }
+  bool has_mutual_information() const { return !mi_.empty(); }
+  const std::vector<double>& get_single_orbital_entropies() const;
+  const std::vector<double>& get_two_orbital_entropies() const;
+  const std::vector<double>& get_mutual_information() const;
+
  private:
   std::vector<double> coeffs_;
   std::vector<Configuration> dets_;
   size_t norb_;
   std::vector<double> one_aa_, one_bb_, two_aaaa_, two_aabb_, two_bbbb_, one_st_, two_st_;
+  std::vector<double> s1_, s2_, mi_;
 };
 
 }  // namespace qdk_b200::data

@@ -131,15 +131,6 @@ AsciSettings get_asci_settings(const data::Settings& s) {  // macis_base.cpp:47-
   return a;
 }
 
-void reject_unsupported_outputs(const data::Settings& s) {
-  for (const char* k : {"calculate_single_orbital_entropies", "calculate_two_orbital_entropies",
-                        "calculate_mutual_information"})
-    if (s.get<bool>(k))
-      throw std::runtime_error(std::string("setting '") + k +
-                               "' is not available: the orbital-entropy builders are outside the hot path "
-                               "this build covers (DESIGN.md, scope)");
-}
-
 int64_t binomial(int64_t n, int64_t k) {
   if (k < 0 || k > n) return 0;
   k = std::min(k, n - k);
@@ -283,6 +274,18 @@ class CiSession {
     return out;
   }
 
+  // HamiltonianGenerator::form_entropies on the solver-ordered list (macis_base.hpp:219-245)
+  void form_entropies(const std::vector<Det>& dets, const std::vector<double>& C, std::vector<double>& s1,
+                      std::vector<double>& s2, std::vector<double>& mi) {
+    b2ci_dets* d = nullptr;
+    B2(b2ci_dets_upload(ctx_, reinterpret_cast<const uint64_t*>(dets.data()), 2, int64_t(dets.size()), &d));
+    const int rc = b2ci_form_entropies(ctx_, d, C.data(), s1.data(), s2.empty() ? nullptr : s2.data(),
+                                       mi.empty() ? nullptr : mi.data());
+    b2ci_dets_free(ctx_, d);
+    if (rc != 0) throw std::runtime_error(b2ci_last_error());
+    g_stats["entropy_pattern_ms"] = b2ci_timer_ms(ctx_, "entropy.pattern");
+    g_stats["entropy_scatter_ms"] = b2ci_timer_ms(ctx_, "entropy.scatter");
+  }
   // HamiltonianGenerator::form_rdms_spin_dep / form_rdms on the solver-ordered list
   // (macis_base.hpp:166-215, macis_pmc.cpp:128-160); outputs sized by the caller, empty = skip
   void form_rdms(const std::vector<Det>& dets, const std::vector<double>& C, bool spin_dep, std::vector<double>& o1,
@@ -335,6 +338,21 @@ void attach_rdms_spin_dependent(CiSession& S, const data::Settings& st, const st
   for (auto* v : {&aaaa, &bbbb, &aabb})
     for (double& x : *v) x *= 2.0;
   w.set_rdms_spin_dependent(std::move(aa), std::move(bb), std::move(aaaa), std::move(aabb), std::move(bbbb));
+}
+
+// build_wavefunction's entropy step (macis_base.hpp:219-260): s1 whenever any of the three is
+// asked for, the two-orbital matrix / mutual information only where requested
+void attach_entropies(CiSession& S, const data::Settings& st, const std::vector<Det>& dets,
+                      const std::vector<double>& C, data::Wavefunction& w) {
+  const bool e1 = st.get<bool>("calculate_single_orbital_entropies");
+  const bool e2 = st.get<bool>("calculate_two_orbital_entropies");
+  const bool emi = st.get<bool>("calculate_mutual_information");
+  if (!e1 && !e2 && !emi) return;
+  const size_t n = w.num_active_orbitals();
+  std::vector<double> s1(n, 0.0), s2(e2 ? n * n : 0, 0.0), mi(emi ? n * n : 0, 0.0);
+  S.form_entropies(dets, C, s1, s2, mi);
+  if (!e1) s1.clear();
+  w.set_entropies(std::move(s1), std::move(s2), std::move(mi));
 }
 
 void check_hamiltonian(const data::Hamiltonian& h, const char* who, unsigned na, unsigned nb) {
@@ -411,6 +429,16 @@ struct WallTimer {  // host wall clock of one phase, accumulated into the run st
 double asci_iter(CiSession& S, const AsciSettings& a, const McscfSettings& m, int64_t ndets_max, double E0,
                  std::vector<Det>& wfn, std::vector<double>& X) {  // iteration.hpp:50-226
   std::unique_ptr<WallTimer> wt(new WallTimer("wall_core_selection_ms"));
+  // warm start (iteration.hpp:132-180) needs old determinant -> old coefficient. The list arrives
+  // spin-sorted from the previous iteration, so a copy taken here turns the lookup into a merge
+  // of two sorted lists; only an unsorted input (first call of a user-supplied list) is hashed.
+  std::vector<Det> old_dets;
+  std::vector<double> old_X;
+  bool old_sorted = false;
+  if (a.warm_start_davidson) {
+    old_sorted = std::is_sorted(wfn.begin(), wfn.end(), spin_less);
+    if (old_sorted) { old_dets = wfn; old_X = X; }
+  }
   if (wfn.size() > 1) reorder_ci_on_coeff(wfn, X);
   size_t nkeep = 0;
   if (a.fixed_core) {
@@ -425,7 +453,7 @@ double asci_iter(CiSession& S, const AsciSettings& a, const McscfSettings& m, in
   }
   if (wfn.size() > 1) reorder_ci_on_alpha(wfn, X, nkeep);
   std::unordered_map<Det, double, DetHash> old;
-  if (a.warm_start_davidson) {
+  if (a.warm_start_davidson && !old_sorted) {
     old.reserve(wfn.size());
     for (size_t i = 0; i < wfn.size(); ++i) old.emplace(wfn[i], X[i]);
   }
@@ -434,11 +462,19 @@ double asci_iter(CiSession& S, const AsciSettings& a, const McscfSettings& m, in
   wt.reset(new WallTimer("wall_sort_warmstart_ms"));
   std::sort(wfn.begin(), wfn.end(), spin_less);
   std::vector<double> X_local;
-  if (a.warm_start_davidson && !old.empty()) {
+  if (a.warm_start_davidson && (!old.empty() || !old_dets.empty())) {
     X_local.assign(wfn.size(), 0.0);
-    for (size_t i = 0; i < wfn.size(); ++i) {
-      auto it = old.find(wfn[i]);
-      if (it != old.end()) X_local[i] = it->second;
+    if (old_sorted) {
+      size_t j = 0;
+      for (size_t i = 0; i < wfn.size() && j < old_dets.size(); ++i) {
+        while (j < old_dets.size() && spin_less(old_dets[j], wfn[i])) ++j;
+        if (j < old_dets.size() && old_dets[j] == wfn[i]) X_local[i] = old_X[j];
+      }
+    } else {
+      for (size_t i = 0; i < wfn.size(); ++i) {
+        auto it = old.find(wfn[i]);
+        if (it != old.end()) X_local[i] = it->second;
+      }
     }
     double nrm = 0.;
     for (double x : X_local) nrm += x * x;
@@ -636,7 +672,6 @@ void ProjectedMultiConfigurationCalculatorFactory::register_default_instances() 
 McResult B200Cas::_run_impl(std::shared_ptr<data::Hamiltonian> h, unsigned na, unsigned nb) const {
   if (!h) throw std::invalid_argument("B200Cas: null Hamiltonian");
   check_hamiltonian(*h, "B200Cas", na, nb);
-  reject_unsupported_outputs(*_settings);
   g_stats.clear();
   const auto t0 = std::chrono::steady_clock::now();
   CiSession S(*h);
@@ -645,6 +680,7 @@ McResult B200Cas::_run_impl(std::shared_ptr<data::Hamiltonian> h, unsigned na, u
   const double E = casci(S, *_settings, na, nb, dets, C);
   auto w = make_wavefunction(dets, C, h->num_active_orbitals());
   attach_rdms_spin_dependent(S, *_settings, dets, C, *w);
+  attach_entropies(S, *_settings, dets, C, *w);
   g_stats["wall_ms"] = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
   return {E + h->get_core_energy(), w};
 }
@@ -652,7 +688,6 @@ McResult B200Cas::_run_impl(std::shared_ptr<data::Hamiltonian> h, unsigned na, u
 McResult B200Asci::_run_impl(std::shared_ptr<data::Hamiltonian> h, unsigned na, unsigned nb) const {
   if (!h) throw std::invalid_argument("B200Asci: null Hamiltonian");
   check_hamiltonian(*h, "B200Asci", na, nb);
-  reject_unsupported_outputs(*_settings);
   if (_settings->get<bool>("grow_with_rot"))
     throw std::runtime_error("grow_with_rot (natural-orbital rotation of the integrals during growth) is outside "
                              "the hot path this build covers");
@@ -684,6 +719,7 @@ McResult B200Asci::_run_impl(std::shared_ptr<data::Hamiltonian> h, unsigned na, 
   }
   auto w = make_wavefunction(dets, C, h->num_active_orbitals());
   attach_rdms_spin_dependent(S, *_settings, dets, C, *w);
+  attach_entropies(S, *_settings, dets, C, *w);
   g_stats["wall_ms"] = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
   return {E + h->get_core_energy(), w};
 }
@@ -693,7 +729,6 @@ McResult B200Pmc::_run_impl(std::shared_ptr<data::Hamiltonian> h,
   if (!h) throw std::invalid_argument("B200Pmc: null Hamiltonian");
   if (h->is_unrestricted())
     throw std::runtime_error("B200Pmc does not support unrestricted orbitals. Only restricted orbitals are supported.");
-  reject_unsupported_outputs(*_settings);
   const McscfSettings m = get_mcscf_settings(*_settings);
   const int64_t cutoff = _settings->get<int64_t>("iterative_solver_dimension_cutoff");
   const size_t norb = h->num_active_orbitals();

@@ -196,4 +196,23 @@ std::vector<double> Wavefunction::get_active_two_rdm_spin_traced() const {
   return r;
 }
 
+void Wavefunction::set_entropies(std::vector<double> single_orbital, std::vector<double> two_orbital,
+                                 std::vector<double> mutual_information) {
+  s1_ = std::move(single_orbital);
+  s2_ = std::move(two_orbital);
+  mi_ = std::move(mutual_information);
+}
+const std::vector<double>& Wavefunction::get_single_orbital_entropies() const {
+  if (s1_.empty()) throw std::runtime_error("Single orbital entropies not available");
+  return s1_;
+}
+const std::vector<double>& Wavefunction::get_two_orbital_entropies() const {
+  if (s2_.empty()) throw std::runtime_error("Two orbital entropies not available");
+  return s2_;
+}
+const std::vector<double>& Wavefunction::get_mutual_information() const {
+  if (mi_.empty()) throw std::runtime_error("Mutual information not available");
+  return mi_;
+}
+
 }  // namespace qdk_b200::data

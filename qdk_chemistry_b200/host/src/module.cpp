@@ -197,6 +197,32 @@ PYBIND11_MODULE(_core, m) {
              std::memcpy(a.mutable_data(), v.data(), v.size() * 8);
              return a;
            })
+      .def("has_single_orbital_entropies", &data::Wavefunction::has_single_orbital_entropies)
+      .def("has_two_orbital_entropies", &data::Wavefunction::has_two_orbital_entropies)
+      .def("has_mutual_information", &data::Wavefunction::has_mutual_information)
+      .def("get_single_orbital_entropies",
+           [](const data::Wavefunction& w) {
+             const auto& v = w.get_single_orbital_entropies();
+             py::array_t<double> a{py::ssize_t(v.size())};
+             std::memcpy(a.mutable_data(), v.data(), v.size() * 8);
+             return a;
+           })
+      .def("get_two_orbital_entropies",
+           [](const data::Wavefunction& w) {
+             const auto& v = w.get_two_orbital_entropies();
+             const py::ssize_t n = py::ssize_t(w.num_active_orbitals());
+             py::array_t<double, py::array::f_style> a({n, n});
+             std::memcpy(a.mutable_data(), v.data(), v.size() * 8);
+             return a;
+           })
+      .def("get_mutual_information",
+           [](const data::Wavefunction& w) {
+             const auto& v = w.get_mutual_information();
+             const py::ssize_t n = py::ssize_t(w.num_active_orbitals());
+             py::array_t<double, py::array::f_style> a({n, n});
+             std::memcpy(a.mutable_data(), v.data(), v.size() * 8);
+             return a;
+           })
       .def("get_active_determinants", &data::Wavefunction::get_active_determinants)
       .def("determinant_words", [](const data::Wavefunction& w) {
         // (alpha, beta) occupation words, shape (n, 2)

@@ -193,3 +193,21 @@ def test_pmc_plugin_rdms_spin_traced(water, golden_meta):
     n = water.norb
     Er = np.sum(one * water.T.reshape(n, n, order="F")) + np.sum(two * water.V.reshape((n,) * 4, order="F"))
     assert abs(Er + water.core_energy - E) < 1e-8
+
+
+def test_cas_plugin_entropies():
+    """calculate_single_orbital_entropies / _two_orbital_entropies / _mutual_information on the CAS
+    plugin (macis_base.hpp:219-260), against the python oracle on the plugin's own wavefunction."""
+    sp = W.config("tiny_cas6")
+    E, w = alg.create(MC, "macis_cas", calculate_single_orbital_entropies=True, calculate_mutual_information=True,
+                      ci_residual_tolerance=1e-10).run(_ham(sp), sp.nalpha, sp.nbeta)
+    assert w.has_single_orbital_entropies() and w.has_mutual_information() and not w.has_two_orbital_entropies()
+    words = w.determinant_words()
+    p1, p2, pmi = port.form_entropies(sp.norb, words[:, 0], words[:, 1], w.get_coefficients())
+    assert np.abs(w.get_single_orbital_entropies() - p1).max() < 1e-12
+    assert np.abs(w.get_mutual_information() - pmi).max() < 1e-11
+    with pytest.raises(RuntimeError):
+        w.get_two_orbital_entropies()
+    _, w2 = alg.create(MC, "macis_cas", calculate_two_orbital_entropies=True).run(_ham(sp), sp.nalpha, sp.nbeta)
+    assert w2.has_two_orbital_entropies() and not w2.has_single_orbital_entropies()
+    assert np.abs(w2.get_two_orbital_entropies() - p2).max() < 1e-7   # looser CI tolerance of this run

@@ -88,3 +88,55 @@ def test_rdm_hf_determinant(ctx):
                 assert t[i, i, j, j] == 2.0 and t[i, j, j, i] == -1.0
     assert np.count_nonzero(o) == sp.nalpha
     dets.free()
+
+
+# ---- orbital entropies (form_entropies) ---------------------------------------------------------
+def _flat(I, need_s2=True):
+    parts = [I[k] for k in port.ENT_VECS]
+    if need_s2:
+        parts += [I[k].reshape(-1, order="F") for k in port.ENT_MATS]
+    return np.concatenate(parts)
+
+
+@pytest.mark.parametrize("name", ["tiny_cas6", "small_cas8", "hubbard_4x2"])
+def test_entropies_match_reference_golden(ctx, name):
+    """s1 / s2 / mutual information against the compiled reference's form_entropies
+    (tests/golden/entropy_golden.npz) and the device intermediates against the python oracle."""
+    import os
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "entropy_golden.npz"))
+    sp = W.config(name)
+    a, b, C = g[f"{name}.alpha"], g[f"{name}.beta"], g[f"{name}.C"]
+    ctx.upload_integrals(sp.norb, sp.T, sp.V)
+    dets = ctx.upload_dets(port.pack(a, b), 1)
+    s1, s2, mi = ctx.form_entropies(dets, C)
+    assert np.abs(s1 - g[f"{name}.s1"]).max() < 1e-12
+    assert np.abs(s2 - g[f"{name}.s2"]).max() < 1e-11 and np.abs(mi - g[f"{name}.mi"]).max() < 1e-11
+    I = ctx.entropy_intermediates(dets, C)
+    assert np.abs(I - _flat(port.entropy_intermediates(sp.norb, a, b, C))).max() < 1e-13
+    # single-orbital entropies alone: diagonal pairs only, no pattern build
+    o1, n2, nmi = ctx.form_entropies(dets, C, two_orbital=False, mutual_information=False)
+    assert n2 is None and nmi is None and np.abs(o1 - g[f"{name}.s1"]).max() < 1e-12
+    I1 = ctx.entropy_intermediates(dets, C, need_s2=False)
+    assert np.abs(I1 - _flat(port.entropy_intermediates(sp.norb, a, b, C, need_s2=False), False)).max() < 1e-13
+    # mutual information without the two-orbital matrix (the reference builds s2 internally)
+    m1, m2, mmi = ctx.form_entropies(dets, C, two_orbital=False, mutual_information=True)
+    assert m2 is None and np.abs(mmi - g[f"{name}.mi"]).max() < 1e-11
+    dets.free()
+
+
+def test_entropies_full_ci_vector_properties(ctx):
+    """On the converged CASCI vector of small_cas8 (3,920 determinants): s2 symmetric with zero
+    diagonal, mutual information = s1_i + s1_j - s2_ij >= -1e-12, s1 <= ln 4."""
+    sp = W.config("small_cas8")
+    ctx.upload_integrals(sp.norb, sp.T, sp.V)
+    dets = ctx.generate_fci(sp.norb, sp.nalpha, sp.nbeta)
+    H = ctx.hbuild(dets, 0.0)
+    _, X, _, _ = H.davidson(200, 1e-10)
+    s1, s2, mi = ctx.form_entropies(dets, X)
+    a, b = port.unpack(dets.download(1))
+    p1, p2, pmi = port.form_entropies(sp.norb, a, b, X)
+    assert np.abs(s1 - p1).max() < 1e-12 and np.abs(s2 - p2).max() < 1e-11 and np.abs(mi - pmi).max() < 1e-11
+    assert np.all(s1 <= np.log(4) + 1e-12) and np.all(s1 >= 0)
+    assert np.abs(s2 - s2.T).max() == 0 and np.all(np.diag(s2) == 0) and mi.min() > -1e-12
+    H.free()
+    dets.free()

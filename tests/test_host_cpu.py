@@ -134,8 +134,8 @@ def test_run_without_a_gpu_fails_loudly_and_locks_settings():
     unres = data.Hamiltonian(np.eye(2), np.zeros(16), 0.0, True)
     with pytest.raises(RuntimeError, match="does not support unrestricted orbitals"):
         alg.create(MC, "b200_asci").run(unres, 1, 1)
-    with pytest.raises(RuntimeError, match="not available"):
-        alg.create(MC, "b200_cas", calculate_single_orbital_entropies=True).run(
+    with pytest.raises(RuntimeError, match="grow_with_rot"):
+        alg.create(MC, "b200_asci", grow_with_rot=True).run(
             data.Hamiltonian(np.eye(2), np.zeros(16), 0.0), 1, 1)
     with pytest.raises(RuntimeError, match="grow_factor must be > 1.0"):
         alg.create(MC, "b200_asci", grow_factor=1.0).run(

@@ -232,3 +232,39 @@ def test_wavefunction_text_io_round_trip(tmp_path):
     assert meta2 == meta and np.array_equal(a2, a) and np.array_equal(b2, b) and np.array_equal(c2, c)
     lines = out.read_text().splitlines()
     assert lines[0] == "120 6 5 3" and lines[1] == "       -6.8728389771404168e-09 222uu0 "
+
+
+ENT_CASES = ["tiny_cas6", "small_cas8", "hubbard_4x2"]
+
+
+def _flatten_intermediates(I, need_s2=True):
+    """dict of the python oracle -> the flat layout of csrc/entropy.cu (vectors, then matrices
+    column-major in ENT_MATS order)"""
+    parts = [I[k] for k in port.ENT_VECS]
+    if need_s2:
+        parts += [I[k].reshape(-1, order="F") for k in port.ENT_MATS]
+    return np.concatenate(parts)
+
+
+@pytest.mark.parametrize("name", ENT_CASES)
+def test_entropy_oracle_and_host_assembly_match_reference_golden(name):
+    """Golden s1 / s2 / mutual information come from the compiled reference
+    (tests/golden/make_golden_entropy.py). Checked here without a GPU: the python oracle
+    end to end, and the product's host assembly (b2ci_host_entropies_from_intermediates) fed
+    with the oracle's intermediates."""
+    from qdk_chemistry_b200 import device
+    g = np.load(os.path.join(GOLDEN, "entropy_golden.npz"))
+    sp = W.config(name)
+    a, b, C = g[f"{name}.alpha"], g[f"{name}.beta"], g[f"{name}.C"]
+    I = port.entropy_intermediates(sp.norb, a, b, C)
+    s1, s2, mi = port.entropies_from_intermediates(I)
+    assert np.abs(s1 - g[f"{name}.s1"]).max() < 1e-13
+    assert np.abs(s2 - g[f"{name}.s2"]).max() < 1e-12 and np.abs(mi - g[f"{name}.mi"]).max() < 1e-12
+    h1, h2, hmi = device.host_entropies_from_intermediates(sp.norb, _flatten_intermediates(I))
+    assert np.abs(h1 - g[f"{name}.s1"]).max() < 1e-13
+    assert np.abs(h2 - g[f"{name}.s2"]).max() < 1e-12 and np.abs(hmi - g[f"{name}.mi"]).max() < 1e-12
+    assert np.abs(h2 - h2.T).max() == 0 and np.all(np.diag(hmi) == 0)
+    # single-orbital entropies alone: only the diagonal pairs contribute (entropies.hpp:917-924)
+    I1 = port.entropy_intermediates(sp.norb, a, b, C, need_s2=False)
+    o1, _, _ = device.host_entropies_from_intermediates(sp.norb, _flatten_intermediates(I1, False), need_s2=False)
+    assert np.abs(o1 - g[f"{name}.s1"]).max() < 1e-13
