@@ -222,7 +222,8 @@ k_generate(const GenArgs A) {
       hdv = 1.0;
       emit = true;
     }
-    if (emit && A.nparts > 1) emit = key_part((eb << 32) | ea, A.nparts) == A.part;
+    if (emit && A.nparts > 1)
+      emit = key_part(A.packed ? ((eb << 32) | ea) : (ea ^ (eb * 0xD6E8FEB86659FD93ull)), A.nparts) == A.part;
     if (emit) {
       if (FILL) {
         const int64_t pos = base + atomicAdd(&s_cnt, 1);
@@ -392,17 +393,19 @@ int asci_search(b2ci_ctx* ctx, const b2ci_asci_search_opts* o, const uint64_t* c
   DevBuf<double> dcoeff(nc), eps_a(size_t(nc) * n), eps_b(size_t(nc) * n), root(nc);
   B2_CUDA(cudaMemcpyAsync(dcoeff, coeffs, size_t(nc) * 8, cudaMemcpyHostToDevice, st));
 
-  // Keys are the wfn_t<64> word itself (beta << 32 | alpha): numeric order == bitset_less.
-  // Two-word keys (32 < norb <= 64, wfn_t<128>) need a second sort phase that is not part of
-  // this build; the H build and Davidson paths have no such limit.
-  if (n > 32) throw Error("b2ci_asci_search: norb > 32 (wfn_t<128> keys) is not supported by this build");
+  // norb <= 32: the key is the wfn_t<64> word itself (beta << 32 | alpha), numeric order ==
+  // bitset_less. 32 < norb <= 64 (wfn_t<128>): 128-bit keys held as two words (alpha = low word,
+  // beta = high word, raw_bitset.hpp:94-106), sorted by two stable LSD phases (alpha digits, then
+  // beta digits), which is the numeric order of the 128-bit word (bitset_less, raw_bitset.hpp:143-160).
+  if (n > 64) throw Error("b2ci_asci_search: norb > 64 (wfn_t<256>) is not supported");
+  const bool two = n > 32;
 
   GenArgs A;
   A.I = ctx->ints;
   A.ca = core.alpha; A.cb = core.beta; A.coeff = dcoeff;
   A.eps_a = eps_a; A.eps_b = eps_b; A.root = root;
   A.E0 = E0; A.tol = o->h_el_tol; A.just_singles = o->just_singles;
-  A.packed = 1;
+  A.packed = two ? 0 : 1;
   DevBuf<int32_t> count(nc);
   DevBuf<int64_t> base(nc + 1);
 
@@ -423,7 +426,7 @@ int asci_search(b2ci_ctx* ctx, const b2ci_asci_search_opts* o, const uint64_t* c
   mark("core upload + count pass");
   size_t free_b = 0, total_b = 0;
   B2_CUDA(cudaMemGetInfo(&free_b, &total_b));
-  const int64_t bytes_per = 80;  // workspace per contribution (records, sort buffers, flags, segments)
+  const int64_t bytes_per = two ? 108 : 80;  // workspace per contribution (records, sort buffers, flags, segments)
   int64_t budget = std::min<int64_t>(int64_t(double(free_b) * 0.5) / bytes_per, (int64_t(1) << 31) - 1);
   if (const char* env = getenv("B2CI_ASCI_BUDGET")) budget = std::max<int64_t>(1024, atoll(env));
   // hash partitions are even to a few percent; 1.25 covers the imbalance
@@ -437,26 +440,29 @@ int asci_search(b2ci_ctx* ctx, const b2ci_asci_search_opts* o, const uint64_t* c
   T["asci_search.nparts"] = double(nparts);
 
   // candidates of this rank that survive pruning: (key, |rv|), appended part by part
-  DevBuf<uint64_t> cand_key;
+  DevBuf<uint64_t> cand_key, cand_key2;  // cand_key2: beta words of two-word keys
   DevBuf<double> cand_score;
   int64_t ncand = 0, cand_cap = 0;
   int64_t M_sum = 0, nseg_sum = 0;
   if (pt2_out) pt2_out[0] = pt2_out[1] = 0.;
-  auto append_candidates = [&](const uint64_t* k, const double* sc, int64_t m) {
+  auto append_candidates = [&](const uint64_t* k, const uint64_t* k2, const double* sc, int64_t m) {
     if (ncand + m > cand_cap) {
       const int64_t ncap = std::max<int64_t>(ncand + m, cand_cap * 2);
-      DevBuf<uint64_t> nk(ncap);
+      DevBuf<uint64_t> nk(ncap), nk2(two ? ncap : 1);
       DevBuf<double> ns(ncap);
       if (ncand) {
         B2_CUDA(cudaMemcpyAsync(nk, cand_key, size_t(ncand) * 8, cudaMemcpyDeviceToDevice, st));
+        if (two) B2_CUDA(cudaMemcpyAsync(nk2, cand_key2, size_t(ncand) * 8, cudaMemcpyDeviceToDevice, st));
         B2_CUDA(cudaMemcpyAsync(ns, cand_score, size_t(ncand) * 8, cudaMemcpyDeviceToDevice, st));
       }
       cand_key = std::move(nk);
+      cand_key2 = std::move(nk2);
       cand_score = std::move(ns);
       cand_cap = ncap;
     }
     if (m) {
       B2_CUDA(cudaMemcpyAsync(cand_key.p + ncand, k, size_t(m) * 8, cudaMemcpyDeviceToDevice, st));
+      if (two) B2_CUDA(cudaMemcpyAsync(cand_key2.p + ncand, k2, size_t(m) * 8, cudaMemcpyDeviceToDevice, st));
       B2_CUDA(cudaMemcpyAsync(cand_score.p + ncand, sc, size_t(m) * 8, cudaMemcpyDeviceToDevice, st));
     }
     ncand += m;
@@ -464,7 +470,7 @@ int asci_search(b2ci_ctx* ctx, const b2ci_asci_search_opts* o, const uint64_t* c
 
   for (int64_t part = rank; part < nparts; part += nranks) {
     int64_t M = 0;
-    uint64_t* key = nullptr;
+    uint64_t *key = nullptr, *key2 = nullptr;
     double *cm = nullptr, *hd = nullptr;
     {
       ScopedTimer t(ctx, "asci_search.PAIR_DUR", true);
@@ -481,9 +487,10 @@ int asci_search(b2ci_ctx* ctx, const b2ci_asci_search_opts* o, const uint64_t* c
       if (M >= (int64_t(1) << 32)) throw Error("b2ci_asci_search: more than 2^32 contributions in one part");
       mark("part count");
       // workspace of this part: records (24 B), sort double buffers and indices (16 B), segment
-      // flags and ids (12 B), accumulated segments (<= 24 B), 256-byte alignment slack
+      // flags and ids (12 B), accumulated segments (<= 24 B), 256-byte alignment slack; two-word
+      // keys add the beta word of the records (8 B), a sort copy (8 B) and of the segments (8 B)
       const size_t Mz = size_t(M > 0 ? M : 1);
-      const size_t need = Mz * 76 + 16 * 1024;
+      const size_t need = Mz * (two ? 100 : 76) + 16 * 1024;
       if (need > ctx->arena_cap) {
         B2_CUDA(cudaMemGetInfo(&free_b, &total_b));
         if (need > free_b + ctx->arena_cap)
@@ -494,10 +501,11 @@ int asci_search(b2ci_ctx* ctx, const b2ci_asci_search_opts* o, const uint64_t* c
       arena_reserve(ctx, need);
       arena_reset(ctx);
       key = arena_take<uint64_t>(ctx, Mz);
+      if (two) key2 = arena_take<uint64_t>(ctx, Mz);
       cm = arena_take<double>(ctx, Mz);
       hd = arena_take<double>(ctx, Mz);
       mark("alloc key/cm/hd");
-      A.count = nullptr; A.base = base; A.key = key; A.key2 = nullptr; A.cm = cm; A.hd = hd;
+      A.count = nullptr; A.base = base; A.key = key; A.key2 = key2; A.cm = cm; A.hd = hd;
       k_generate<true><<<unsigned(nc), GEN_THREADS, 0, st>>>(A);
       ctx->launches++;
       B2_CHECK_LAUNCH();
@@ -508,24 +516,43 @@ int asci_search(b2ci_ctx* ctx, const b2ci_asci_search_opts* o, const uint64_t* c
 
     // ---- sort + accumulate
     int64_t nseg = 0;
-    uint64_t* sk1 = nullptr;
+    uint64_t *sk1 = nullptr, *sk2 = nullptr;
     double *scm = nullptr, *shd = nullptr;
     {
       ScopedTimer t(ctx, "asci_search.SORT_ACC_DUR", true);
       uint64_t* kalt = arena_take<uint64_t>(ctx, M);
+      uint64_t* kwork = two ? arena_take<uint64_t>(ctx, M) : nullptr;
       uint32_t* idx = arena_take<uint32_t>(ctx, M);
       uint32_t* idx_alt = arena_take<uint32_t>(ctx, M);
       mark("alloc sort buffers");
       iota_u32(ctx, idx, M);
       const int ndig = (n + 7) / 8;
       std::vector<int> shifts;
-      for (int d = 0; d < ndig; ++d) shifts.push_back(8 * d);        // alpha bits
-      for (int d = 0; d < ndig; ++d) shifts.push_back(32 + 8 * d);   // beta bits (high half)
-      radix_sort_pairs(ctx, key, kalt, idx, idx_alt, M, shifts);
+      const uint64_t *k1s = key, *k2s = nullptr;  // the sorted key words
+      if (!two) {
+        for (int d = 0; d < ndig; ++d) shifts.push_back(8 * d);        // alpha bits
+        for (int d = 0; d < ndig; ++d) shifts.push_back(32 + 8 * d);   // beta bits (high half)
+        radix_sort_pairs(ctx, key, kalt, idx, idx_alt, M, shifts);
+      } else {
+        for (int d = 0; d < ndig; ++d) shifts.push_back(8 * d);
+        // phase 1: by the alpha word (a copy: the records keep their order for the final gather)
+        B2_CUDA(cudaMemcpyAsync(kwork, key, size_t(M) * 8, cudaMemcpyDeviceToDevice, st));
+        radix_sort_pairs(ctx, kwork, kalt, idx, idx_alt, M, shifts);
+        // phase 2: by the beta word, stable on top of phase 1
+        k_gather_u64<<<grid1d(M), 256, 0, st>>>(key2, idx, M, kwork);
+        ctx->launches++;
+        B2_CHECK_LAUNCH();
+        radix_sort_pairs(ctx, kwork, kalt, idx, idx_alt, M, shifts);
+        k_gather_u64<<<grid1d(M), 256, 0, st>>>(key, idx, M, kalt);
+        ctx->launches++;
+        B2_CHECK_LAUNCH();
+        k1s = kalt;
+        k2s = kwork;
+      }
       mark("radix sort");
       int32_t* flag = arena_take<int32_t>(ctx, M);
       int64_t* seg_of = arena_take<int64_t>(ctx, M + 1);
-      k_seg_flags<<<grid1d(M), 256, 0, st>>>(key, nullptr, M, flag);
+      k_seg_flags<<<grid1d(M), 256, 0, st>>>(k1s, k2s, M, flag);
       ctx->launches++;
       B2_CHECK_LAUNCH();
       exclusive_scan_i32_to_i64(ctx, flag, seg_of, M);
@@ -533,10 +560,11 @@ int asci_search(b2ci_ctx* ctx, const b2ci_asci_search_opts* o, const uint64_t* c
       B2_CUDA(cudaStreamSynchronize(st));
       mark("segment flags + scan");
       sk1 = arena_take<uint64_t>(ctx, nseg);
+      if (two) sk2 = arena_take<uint64_t>(ctx, nseg);
       scm = arena_take<double>(ctx, nseg);
       shd = arena_take<double>(ctx, nseg);
       // seg_of[i] (exclusive scan) is the segment id of a head at i
-      k_seg_accumulate<<<grid1d(M), 256, 0, st>>>(key, nullptr, idx, flag, seg_of, M, cm, hd, sk1, nullptr, scm, shd);
+      k_seg_accumulate<<<grid1d(M), 256, 0, st>>>(k1s, k2s, idx, flag, seg_of, M, cm, hd, sk1, sk2, scm, shd);
       ctx->launches++;
       B2_CHECK_LAUNCH();
     }
@@ -559,12 +587,15 @@ int asci_search(b2ci_ctx* ctx, const b2ci_asci_search_opts* o, const uint64_t* c
     if (candidates_only) {
       if (cand_n) *cand_n = nseg;
       if (cand_words) {
-        std::vector<uint64_t> tmp(nseg);
+        std::vector<uint64_t> tmp(nseg), tmp2(two ? nseg : 0);
         B2_CUDA(cudaMemcpyAsync(tmp.data(), sk1, size_t(nseg) * 8, cudaMemcpyDeviceToHost, st));
+        if (two) B2_CUDA(cudaMemcpyAsync(tmp2.data(), sk2, size_t(nseg) * 8, cudaMemcpyDeviceToHost, st));
         B2_CUDA(cudaMemcpyAsync(cand_cm, scm, size_t(nseg) * 8, cudaMemcpyDeviceToHost, st));
         B2_CUDA(cudaMemcpyAsync(cand_hd, shd, size_t(nseg) * 8, cudaMemcpyDeviceToHost, st));
         B2_CUDA(cudaStreamSynchronize(st));
-        if (wpd == 1) memcpy(cand_words, tmp.data(), size_t(nseg) * 8);
+        if (two)
+          for (int64_t i = 0; i < nseg; ++i) { cand_words[2 * i] = tmp[i]; cand_words[2 * i + 1] = tmp2[i]; }
+        else if (wpd == 1) memcpy(cand_words, tmp.data(), size_t(nseg) * 8);
         else
           for (int64_t i = 0; i < nseg; ++i) { cand_words[2 * i] = tmp[i] & 0xFFFFFFFFull; cand_words[2 * i + 1] = tmp[i] >> 32; }
       }
@@ -589,11 +620,12 @@ int asci_search(b2ci_ctx* ctx, const b2ci_asci_search_opts* o, const uint64_t* c
       B2_CUDA(cudaStreamSynchronize(st));
       if (m) {
         uint64_t* ck = arena_take<uint64_t>(ctx, m);
+        uint64_t* ck2 = two ? arena_take<uint64_t>(ctx, m) : nullptr;
         double* cs = arena_take<double>(ctx, m);
-        k_compact<<<grid1d(nseg), 256, 0, st>>>(keep, pos, nseg, sk1, nullptr, score, ck, nullptr, cs);
+        k_compact<<<grid1d(nseg), 256, 0, st>>>(keep, pos, nseg, sk1, sk2, score, ck, ck2, cs);
         ctx->launches++;
         B2_CHECK_LAUNCH();
-        append_candidates(ck, cs, m);  // survivors leave the workspace
+        append_candidates(ck, ck2, cs, m);  // survivors leave the workspace
         B2_CUDA(cudaStreamSynchronize(st));
       }
     }
@@ -614,8 +646,8 @@ int asci_search(b2ci_ctx* ctx, const b2ci_asci_search_opts* o, const uint64_t* c
   // ---- top-k over the surviving candidates (determinant_search.hpp:966-1114)
   const int64_t top_k = o->ndets_max - nc;
   // keep every candidate with score >= the k-th largest of `cs` (ties retained); returns count
-  auto keep_top = [&](DevBuf<uint64_t>& ck, DevBuf<double>& cs, int64_t m, int64_t k, double& kth, double& below,
-                      bool want_scores) -> int64_t {
+  auto keep_top = [&](DevBuf<uint64_t>& ck, DevBuf<uint64_t>& ck2, DevBuf<double>& cs, int64_t m, int64_t k,
+                      double& kth, double& below, bool want_scores) -> int64_t {
     kth = select_kth_largest(ctx, cs, m, k);
     DevBuf<int32_t> keep2(m);
     DevBuf<int64_t> pos2(m + 1);
@@ -632,16 +664,17 @@ int asci_search(b2ci_ctx* ctx, const b2ci_asci_search_opts* o, const uint64_t* c
     B2_CUDA(cudaMemcpyAsync(&mbh, mb, 8, cudaMemcpyDeviceToHost, st));
     B2_CUDA(cudaStreamSynchronize(st));
     memcpy(&below, &mbh, 8);
-    DevBuf<uint64_t> sk(nk > 0 ? nk : 1);
+    DevBuf<uint64_t> sk(nk > 0 ? nk : 1), sk2(two && nk > 0 ? nk : 1);
     DevBuf<double> ss(want_scores && nk > 0 ? nk : 1);
     if (nk) {
-      k_compact<<<grid1d(m), 256, 0, st>>>(keep2, pos2, m, ck, nullptr, want_scores ? cs.p : nullptr, sk, nullptr,
-                                          want_scores ? ss.p : nullptr);
+      k_compact<<<grid1d(m), 256, 0, st>>>(keep2, pos2, m, ck, two ? ck2.p : nullptr, want_scores ? cs.p : nullptr,
+                                          sk, two ? sk2.p : nullptr, want_scores ? ss.p : nullptr);
       ctx->launches++;
       B2_CHECK_LAUNCH();
     }
     B2_CUDA(cudaStreamSynchronize(st));
     ck = std::move(sk);
+    ck2 = std::move(sk2);
     if (want_scores) cs = std::move(ss);
     return nk;
   };
@@ -653,30 +686,34 @@ int asci_search(b2ci_ctx* ctx, const b2ci_asci_search_opts* o, const uint64_t* c
     const int64_t k_eff = top_k > 0 ? top_k : 1;  // top_k == 0: max_element over an empty range
                                                    // lands on the largest score (:1056-1062)
     if (nranks == 1) {
-      if (o->ndets_max >= nc && ncand > top_k) nkeep = keep_top(cand_key, cand_score, ncand, k_eff, kth, below, false);
+      if (o->ndets_max >= nc && ncand > top_k) nkeep = keep_top(cand_key, cand_key2, cand_score, ncand, k_eff, kth, below, false);
     } else {
       // local top-k (with ties), all-gather of fixed-size slabs, final select on every rank:
       // the counterpart of the distributed quickselect + Allgatherv (:1000-1053)
-      if (o->ndets_max >= nc && ncand > top_k) nkeep = keep_top(cand_key, cand_score, ncand, k_eff, kth, below, true);
+      if (o->ndets_max >= nc && ncand > top_k) nkeep = keep_top(cand_key, cand_key2, cand_score, ncand, k_eff, kth, below, true);
       std::vector<int64_t> counts;
       comm_allgather_i64_host(ctx, nkeep, counts);
       int64_t slab = 0, total = 0;
       for (int64_t c : counts) { slab = std::max(slab, c); total += c; }
       if (total > 0) {
         DevBuf<uint64_t> sk(slab), gk(size_t(slab) * nranks);
+        DevBuf<uint64_t> sk2(two ? slab : 1), gk2(two ? size_t(slab) * nranks : 1);
         DevBuf<double> ss(slab), gs(size_t(slab) * nranks);
         // padding: score 0 (never selected ahead of a real candidate, dropped below)
         k_fill_u64<<<grid1d(slab), 256, 0, st>>>(sk, slab, ~uint64_t(0));
         B2_CUDA(cudaMemsetAsync(ss, 0, size_t(slab) * 8, st));
+        if (two) k_fill_u64<<<grid1d(slab), 256, 0, st>>>(sk2, slab, ~uint64_t(0));
         if (nkeep) {
           B2_CUDA(cudaMemcpyAsync(sk, cand_key, size_t(nkeep) * 8, cudaMemcpyDeviceToDevice, st));
+          if (two) B2_CUDA(cudaMemcpyAsync(sk2, cand_key2, size_t(nkeep) * 8, cudaMemcpyDeviceToDevice, st));
           B2_CUDA(cudaMemcpyAsync(ss, cand_score, size_t(nkeep) * 8, cudaMemcpyDeviceToDevice, st));
         }
         comm_allgather_bytes(ctx, sk, gk, size_t(slab) * 8);
+        if (two) comm_allgather_bytes(ctx, sk2, gk2, size_t(slab) * 8);
         comm_allgather_bytes(ctx, ss, gs, size_t(slab) * 8);
         const int64_t mg = slab * nranks;
         if (o->ndets_max >= nc && total > top_k) {
-          nkeep = keep_top(gk, gs, mg, k_eff, kth, below, false);
+          nkeep = keep_top(gk, gk2, gs, mg, k_eff, kth, below, false);
         } else {
           // everything survives: drop the padding (score 0 < any pruned-in score)
           DevBuf<int32_t> keep2(mg);
@@ -685,14 +722,18 @@ int asci_search(b2ci_ctx* ctx, const b2ci_asci_search_opts* o, const uint64_t* c
           exclusive_scan_i32_to_i64(ctx, keep2, pos2, mg);
           B2_CUDA(cudaMemcpyAsync(&nkeep, pos2.p + mg, 8, cudaMemcpyDeviceToHost, st));
           B2_CUDA(cudaStreamSynchronize(st));
-          DevBuf<uint64_t> sel2(nkeep > 0 ? nkeep : 1);
-          if (nkeep) k_compact<<<grid1d(mg), 256, 0, st>>>(keep2, pos2, mg, gk, nullptr, nullptr, sel2, nullptr, nullptr);
+          DevBuf<uint64_t> sel2(nkeep > 0 ? nkeep : 1), sel22(two && nkeep > 0 ? nkeep : 1);
+          if (nkeep)
+            k_compact<<<grid1d(mg), 256, 0, st>>>(keep2, pos2, mg, gk, two ? gk2.p : nullptr, nullptr, sel2,
+                                                 two ? sel22.p : nullptr, nullptr);
           ctx->launches += 2;
           B2_CHECK_LAUNCH();
           B2_CUDA(cudaStreamSynchronize(st));
           gk = std::move(sel2);
+          gk2 = std::move(sel22);
         }
         cand_key = std::move(gk);
+        cand_key2 = std::move(gk2);
       } else {
         nkeep = 0;
       }
@@ -707,10 +748,13 @@ int asci_search(b2ci_ctx* ctx, const b2ci_asci_search_opts* o, const uint64_t* c
   if (n_out) *n_out = total;
   if (total > cap) throw Error("b2ci_asci_search: output capacity " + std::to_string(cap) + " < " + std::to_string(total), 4);
   if (nkeep) {
-    std::vector<uint64_t> tmp(nkeep);
+    std::vector<uint64_t> tmp(nkeep), tmp2(two ? nkeep : 0);
     B2_CUDA(cudaMemcpyAsync(tmp.data(), cand_key, size_t(nkeep) * 8, cudaMemcpyDeviceToHost, st));
+    if (two) B2_CUDA(cudaMemcpyAsync(tmp2.data(), cand_key2, size_t(nkeep) * 8, cudaMemcpyDeviceToHost, st));
     B2_CUDA(cudaStreamSynchronize(st));
-    if (wpd == 1) memcpy(out_words, tmp.data(), size_t(nkeep) * 8);
+    if (two)
+      for (int64_t i = 0; i < nkeep; ++i) { out_words[2 * i] = tmp[i]; out_words[2 * i + 1] = tmp2[i]; }
+    else if (wpd == 1) memcpy(out_words, tmp.data(), size_t(nkeep) * 8);
     else
       for (int64_t i = 0; i < nkeep; ++i) { out_words[2 * i] = tmp[i] & 0xFFFFFFFFull; out_words[2 * i + 1] = tmp[i] >> 32; }
   }

@@ -243,6 +243,8 @@ def config(name: str) -> ActiveSpace:
         return synthetic_molecular(name, 6, 3, 3, 11, 12)
     if name == "small_cas8":
         return synthetic_molecular(name, 8, 4, 3, 21, 22)
+    if name == "wide36":  # 32 < norb < 64: wfn_t<128> determinants, 128-bit ASCI keys
+        return synthetic_molecular(name, 36, 3, 3, 6001, 6002, deps=0.05)
     if name == "hubbard_3x2":
         return hubbard_2d(3, 2, 3, 3, name=name)
     if name == "hubbard_4x2":

@@ -149,3 +149,48 @@ def test_pt2_matches_oracle_small(ctx, water, water_refined, parts, monkeypatch)
     e3, n3 = ctx.asci_pt2(port.pack(a[top], b[top]), cs, m["E_asci"], 1e-5)
     eo3, no3 = port.Ham(water.norb, water.T, water.V).asci_pt2(a[top], b[top], cs, m["E_asci"], 1e-5)
     assert n3 == no3 and n3 < no and abs(e3 - eo3) <= 1e-13 * abs(eo3)
+
+
+# ---- 32 < norb < 64: wfn_t<128> determinants, 128-bit keys (two-phase radix sort) -------------
+@pytest.fixture(scope="module")
+def wide():
+    import json, os
+    g = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+    with open(os.path.join(g, "wide36_meta.json")) as fh:
+        return W.config("wide36"), np.load(os.path.join(g, "wide36_golden.npz")), json.load(fh)
+
+
+def test_wide_keys_candidate_table_bit_exact(ctx, wide):
+    sp, z, m = wide
+    ca, cb, cc = z["core_alpha"], z["core_beta"], z["core_C"]
+    ctx.upload_integrals(sp.norb, sp.T, sp.V)
+    words, cm, hd = ctx.asci_candidates(port.pack(ca, cb, 128), cc, m["E0"], h_el_tol=1e-8, words_per_det=2)
+    oa, ob, ocm, ohd = port.Ham(sp.norb, sp.T, sp.V).asci_candidates(ca, cb, cc, m["E0"], 1e-8)
+    assert np.array_equal(words, port.pack(oa, ob, 128))   # 128-bit numeric order: beta word, then alpha
+    assert np.array_equal(hd, ohd)
+    fin = np.isfinite(ocm)
+    assert np.array_equal(np.isfinite(cm), fin) and np.array_equal(cm[fin], ocm[fin])
+
+
+@pytest.mark.parametrize("parts", [1, 3])
+def test_wide_keys_search_matches_reference(ctx, wide, parts, monkeypatch):
+    sp, z, m = wide
+    ca, cb, cc = z["core_alpha"], z["core_beta"], z["core_C"]
+    ctx.upload_integrals(sp.norb, sp.T, sp.V)
+    monkeypatch.setenv("B2CI_ASCI_PARTS", str(parts))
+    out, stats = ctx.asci_search(port.pack(ca, cb, 128), cc, m["E0"], m["ndets_max"], words_per_det=2)
+    out = out.reshape(-1, 2)
+    assert stats[5] == parts and len(out) == m["n_selected"]
+    assert sorted(map(tuple, out.tolist())) == sorted(map(tuple, z["selected"].tolist()))
+    assert np.array_equal(out[-len(ca):, 0], ca) and np.array_equal(out[-len(ca):, 1], cb)
+    _, _, ostats = port.Ham(sp.norb, sp.T, sp.V).asci_search(ca, cb, cc, m["E0"], m["ndets_max"])
+    assert np.array_equal(stats[:5], ostats[:5])
+
+
+def test_wide_keys_pt2_matches_oracle(ctx, wide):
+    sp, z, m = wide
+    ca, cb, cc = z["core_alpha"], z["core_beta"], z["core_C"]
+    ctx.upload_integrals(sp.norb, sp.T, sp.V)
+    e, npt2 = ctx.asci_pt2(port.pack(ca, cb, 128), cc, m["E0"], 1e-16, words_per_det=2)
+    eo, no = port.Ham(sp.norb, sp.T, sp.V).asci_pt2(ca, cb, cc, m["E0"], 1e-16)
+    assert npt2 == no and abs(e - eo) <= 1e-13 * abs(eo)

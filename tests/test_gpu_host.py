@@ -211,3 +211,26 @@ def test_cas_plugin_entropies():
     _, w2 = alg.create(MC, "macis_cas", calculate_two_orbital_entropies=True).run(_ham(sp), sp.nalpha, sp.nbeta)
     assert w2.has_two_orbital_entropies() and not w2.has_single_orbital_entropies()
     assert np.abs(w2.get_two_orbital_entropies() - p2).max() < 1e-7   # looser CI tolerance of this run
+
+
+def test_asci_plugin_on_36_orbitals_matches_reference_run():
+    # 32 <= norb < 64 dispatches to wfn_t<128> in the reference (macis_base.hpp:80-100); golden
+    # energy and determinant set made with the compiled reference (tests/golden/make_golden_wide.py)
+    import json
+    g = os.path.join(ROOT, "tests", "golden")
+    z = np.load(os.path.join(g, "wide36_golden.npz"))
+    with open(os.path.join(g, "wide36_meta.json")) as fh:
+        m = json.load(fh)
+    sp = W.config("wide36")
+    o = m["run_opts"]
+    E, w = alg.create(MC, "macis_asci", ntdets_max=o["ntdets_max"], ntdets_min=o["ntdets_min"],
+                      max_refine_iter=o["max_refine_iter"], ci_residual_tolerance=1e-8).run(_ham(sp), 3, 3)
+    assert w.size() == m["run_n"] and abs(E - sp.core_energy - m["run_E"]) < 1e-8
+    a, b = _words(w)
+    got = set(zip(a.tolist(), b.tolist()))
+    want = set(map(tuple, z["run_dets"].tolist()))
+    # H is symmetric under alpha <-> beta; with 3 + 3 electrons the first cuts split spin-flip
+    # partners of equal |rv| and the truncated wavefunction the reference lands on is one of two
+    # mirror images (its unstable sort decides which): the sets are compared modulo that flip
+    canon = lambda s: sorted((min(x, y), max(x, y)) for x, y in s)
+    assert canon(got) == canon(want)

@@ -268,3 +268,23 @@ def test_entropy_oracle_and_host_assembly_match_reference_golden(name):
     I1 = port.entropy_intermediates(sp.norb, a, b, C, need_s2=False)
     o1, _, _ = device.host_entropies_from_intermediates(sp.norb, _flatten_intermediates(I1, False), need_s2=False)
     assert np.abs(o1 - g[f"{name}.s1"]).max() < 1e-13
+
+
+# ---- 32 < norb < 64: wfn_t<128> determinants, 128-bit ASCI keys (tests/golden/make_golden_wide.py)
+def _wide_golden():
+    import json, os
+    g = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+    with open(os.path.join(g, "wide36_meta.json")) as fh:
+        return np.load(os.path.join(g, "wide36_golden.npz")), json.load(fh)
+
+
+def test_wide_keys_search_and_run_match_compiled_reference():
+    z, m = _wide_golden()
+    sp = W.config("wide36")
+    h = port.Ham(sp.norb, sp.T, sp.V)
+    sa, sb, _ = h.asci_search(z["core_alpha"], z["core_beta"], z["core_C"], m["E0"], m["ndets_max"])
+    got = sorted(zip(sa.tolist(), sb.tolist()))
+    assert got == sorted(map(tuple, z["selected"].tolist()))
+    assert (sa >> np.uint64(32)).any() and (sb >> np.uint64(32)).any()   # both words are in play
+    E, a, b, X = port.asci_run(h, sp.nalpha, sp.nbeta, refine=True, **m["run_opts"])
+    assert len(a) == m["run_n"] and abs(E - m["run_E"]) < 1e-8
