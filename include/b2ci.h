@@ -72,6 +72,19 @@ int b2ci_dets_free(b2ci_ctx* ctx, b2ci_dets* d);
  * h_thresh > 0, everything structurally connected kept when h_thresh == 0. */
 int b2ci_hbuild_csr(b2ci_ctx* ctx, const b2ci_dets* dets, int64_t row_begin, int64_t row_end,
                     double h_thresh, b2ci_csr** out);
+/* Incremental build between ASCI iterations: CachedHamiltonianState + build_patched_operator
+ * (external/macis/include/macis/solvers/incremental_h_build.hpp:192-356), called from
+ * selected_ci_diag (solvers/selected_ci_diag.hpp:217-256). old_H must be the full square matrix
+ * of old_dets built with the same integrals and h_thresh; both lists spin_comparator-sorted
+ * (alpha-major, then beta). The kept x kept block is taken from old_H (columns renumbered), only
+ * kept x added and added x all are evaluated, and the blocks are merged into one CSR of new_dets
+ * that is bit-identical to b2ci_hbuild_csr(new_dets, 0, n, h_thresh). When n_kept / n_new <
+ * min_overlap nothing is built and *out is NULL (the reference falls back to the full build the
+ * same way, :266-283). n_kept may be NULL. Not available with a communicator, like the
+ * reference's MPI builds (selected_ci_diag.hpp:196-202). */
+int b2ci_hbuild_csr_patched(b2ci_ctx* ctx, const b2ci_dets* old_dets, const b2ci_csr* old_H,
+                            const b2ci_dets* new_dets, double h_thresh, double min_overlap,
+                            b2ci_csr** out, int64_t* n_kept);
 /* sparsexx::csr_matrix from caller arrays (python/src/pybind11/algorithms/
  * davidson_solver.cpp:60-80); host pointers, int64 indices, square n x n */
 int b2ci_csr_upload(b2ci_ctx* ctx, int64_t n, int64_t nnz, const int64_t* rowptr,

@@ -93,6 +93,8 @@ void dets_to_words(b2ci_ctx* ctx, const b2ci_dets* d, uint64_t* words_host, int 
 void dets_generate_fci(b2ci_ctx* ctx, int norb, int na, int nb, b2ci_dets* d);
 void hbuild_csr(b2ci_ctx* ctx, const b2ci_dets* dets, int64_t row_begin, int64_t row_end, double thr,
                 b2ci_csr* out);
+bool hbuild_csr_patched(b2ci_ctx* ctx, const b2ci_dets* od, const b2ci_csr* oH, const b2ci_dets* nd, double thr,
+                        double min_overlap, b2ci_csr* out, int64_t* n_kept_out);
 void csr_diagonal_dev(b2ci_ctx* ctx, const b2ci_csr* m, double* D_dev);
 int davidson(b2ci_ctx* ctx, const b2ci_csr* m, int64_t max_m, double tol, double* X_host,
              int use_guess_policy, int64_t* niter_out, double* eig_out, double* trace);
@@ -297,6 +299,20 @@ int b2ci_hbuild_csr(b2ci_ctx* ctx, const b2ci_dets* dets, int64_t row_begin, int
   b2ci_csr* m = new b2ci_csr;
   try { hbuild_csr(ctx, dets, row_begin, row_end, h_thresh, m); } catch (...) { delete m; throw; }
   *out = m;
+  return 0;
+  B2_CATCH
+}
+int b2ci_hbuild_csr_patched(b2ci_ctx* ctx, const b2ci_dets* old_dets, const b2ci_csr* old_H,
+                            const b2ci_dets* new_dets, double h_thresh, double min_overlap,
+                            b2ci_csr** out, int64_t* n_kept) {
+  B2_TRY_CTX(ctx)
+  if (!out) throw Error("b2ci_hbuild_csr_patched: out is NULL");
+  *out = nullptr;
+  b2ci_csr* m = new b2ci_csr;
+  bool built = false;
+  try { built = hbuild_csr_patched(ctx, old_dets, old_H, new_dets, h_thresh, min_overlap, m, n_kept); }
+  catch (...) { delete m; throw; }
+  if (built) *out = m; else delete m;
   return 0;
   B2_CATCH
 }

@@ -115,10 +115,18 @@ struct RowArgs {
   const int64_t* rowptr;  // fill pass input
   int32_t* colind;
   double* nzval;
+  // rectangular blocks (BLK): the rows come from a second (bra) list; alpha / beta / run_start /
+  // bgrp_* above describe the ket list. Used by the patched (incremental) build.
+  const uint64_t* bra_alpha = nullptr;
+  const uint64_t* bra_beta = nullptr;
+  const int32_t* bra_run = nullptr;  // row of the bra-run x ket-run adjacency of every bra determinant
+  const int32_t* bra_grp = nullptr;  // beta group of the ket list holding the bra's beta string, or -1
+  const int32_t* rowmap = nullptr;   // index of a bra / ket determinant in the common (global) list:
+  const int32_t* colmap = nullptr;   //   decides the (bra, ket) roles and is the column written
 };
 
 // Evaluate up to 32 queued column indices (one per lane) and count / emit the survivors.
-template <bool FILL, bool EVAL>
+template <bool FILL, bool EVAL, bool BLK>
 __device__ __forceinline__ void process_batch(const RowArgs& A, int64_t i, uint64_t ai,
                                               uint64_t bi, const int32_t* q, int nvalid, int lane,
                                               int64_t& out, int32_t& cnt) {
@@ -130,6 +138,7 @@ __device__ __forceinline__ void process_batch(const RowArgs& A, int64_t i, uint6
     j = q[lane];
     if (FILL || EVAL) {
       const uint64_t aj = A.alpha[j], bj = A.beta[j];
+      if (BLK && A.colmap) j = A.colmap[j];
       // the reference computes the upper triangle with bra = lower index and mirrors it
       v = (i <= int64_t(j)) ? matel(A.I, ai, bi, aj, bj) : matel(A.I, aj, bj, ai, bi);
       if (EVAL) keep = fabs(v) > A.thr;
@@ -154,16 +163,17 @@ __device__ __forceinline__ void process_batch(const RowArgs& A, int64_t i, uint6
 // of) runs two alpha excitations away. Runs are contiguous index ranges and group members are
 // stored in ascending index, so the two streams are merged on the fly: before run r' is
 // scanned, the group members below its first index are emitted. Columns come out ascending.
-template <bool FILL, bool EVAL>
+template <bool FILL, bool EVAL, bool BLK = false>
 __global__ void __launch_bounds__(ROW_WARPS * 32)
 k_rows(const RowArgs A) {
   __shared__ int32_t queue[ROW_WARPS][64];
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   const int64_t row = int64_t(blockIdx.x) * ROW_WARPS + w;
   if (row >= A.nrows) return;
-  const int64_t i = A.row_begin + row;
-  const uint64_t ai = A.alpha[i], bi = A.beta[i];
-  const int32_t r = A.run_of[i];
+  const int64_t il = A.row_begin + row;  // index in the bra list
+  const uint64_t ai = BLK ? A.bra_alpha[il] : A.alpha[il], bi = BLK ? A.bra_beta[il] : A.beta[il];
+  const int32_t r = BLK ? A.bra_run[il] : A.run_of[il];
+  const int64_t i = (BLK && A.rowmap) ? int64_t(A.rowmap[il]) : il;  // index in the common list
   int32_t* q = queue[w];
   int qn = 0;
   int32_t cnt = 0;
@@ -177,7 +187,7 @@ k_rows(const RowArgs A) {
     qn += __popc(m);
     __syncwarp();
     if (qn >= 32) {
-      process_batch<FILL, EVAL>(A, i, ai, bi, q, 32, lane, out, cnt);
+      process_batch<FILL, EVAL, BLK>(A, i, ai, bi, q, 32, lane, out, cnt);
       const int rest = qn - 32;
       const int32_t t = (lane < rest) ? q[32 + lane] : 0;
       __syncwarp();
@@ -187,9 +197,9 @@ k_rows(const RowArgs A) {
     }
   };
   if (ai != 0) {
-    const int32_t g = A.bgrp_of[i];
-    int64_t bpos = A.bgrp_start[g];
-    const int64_t bend = A.bgrp_start[g + 1];
+    const int32_t g = BLK ? A.bra_grp[il] : A.bgrp_of[il];
+    int64_t bpos = g >= 0 ? A.bgrp_start[g] : 0;
+    const int64_t bend = g >= 0 ? A.bgrp_start[g + 1] : 0;
     int64_t nextj = bpos < bend ? int64_t(A.bgrp_mem[bpos]) : INT64_MAX;
     // (c): members of the beta group with index < bound
     auto flush_group = [&](int64_t bound) {
@@ -232,7 +242,7 @@ k_rows(const RowArgs A) {
       }
     }
     flush_group(INT64_MAX);
-    if (qn > 0) process_batch<FILL, EVAL>(A, i, ai, bi, q, qn, lane, out, cnt);
+    if (qn > 0) process_batch<FILL, EVAL, BLK>(A, i, ai, bi, q, qn, lane, out, cnt);
   }
   if (lane == 0 && A.row_cnt) A.row_cnt[row] = cnt;
 }
@@ -874,6 +884,180 @@ __global__ void k_generate_fci(int norb, int na, int nb, int64_t nalpha_str, int
   beta[i] = unrank_comb(norb, nb, i % nbeta_str, binom);
 }
 
+// ------------------------------------------------------------------ patched (incremental) build
+// adjacency between two string tables (bra runs x ket runs), entries as k_string_adjacency
+template <bool FILL>
+__global__ void __launch_bounds__(256)
+k_string_adjacency2(const uint64_t* __restrict__ sa, int32_t na, const uint64_t* __restrict__ sb, int32_t nb,
+                    int maxd, int32_t* __restrict__ cnt, const int64_t* __restrict__ adj_ptr,
+                    uint32_t* __restrict__ adj) {
+  const int lane = threadIdx.x & 31;
+  const int64_t r = (int64_t(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+  if (r >= na) return;
+  const uint64_t a = sa[r];
+  int64_t out = FILL ? adj_ptr[r] : 0;
+  int32_t c = 0;
+  if (a != 0) {
+    for (int32_t r0 = 0; r0 < nb; r0 += 32) {
+      const int32_t r2 = r0 + lane;
+      bool ok = false;
+      int d = 0;
+      if (r2 < nb) {
+        const uint64_t a2 = sb[r2];
+        d = __popcll(a ^ a2);
+        ok = a2 != 0 && d <= maxd;
+      }
+      const unsigned m = __ballot_sync(0xffffffffu, ok);
+      if (FILL && ok) adj[out + __popc(m & ((1u << lane) - 1u))] = (uint32_t(r2) << 2) | uint32_t(d >> 1);
+      out += __popc(m);
+      c += __popc(m);
+    }
+  }
+  if (!FILL && lane == 0) cnt[r] = c;
+}
+// beta group of the ket list that holds each bra determinant's beta string (-1: none)
+__global__ void k_lookup_group(const uint64_t* __restrict__ bra_beta, int64_t n,
+                               const uint64_t* __restrict__ key_sorted, const int64_t* __restrict__ grp_start,
+                               int32_t ngroups, int32_t* __restrict__ grp) {
+  const int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const uint64_t b = bra_beta[i];
+  int32_t lo = 0, hi = ngroups;
+  while (lo < hi) {
+    const int32_t mid = (lo + hi) >> 1;
+    if (key_sorted[grp_start[mid]] < b) lo = mid + 1; else hi = mid;
+  }
+  grp[i] = (lo < ngroups && key_sorted[grp_start[lo]] == b) ? lo : -1;
+}
+// position of every new determinant in the old list (both spin_comparator-sorted: alpha-major,
+// then beta -- raw_bitset.hpp:119-141), -1 if it is new; the merge scan of
+// build_patched_operator (incremental_h_build.hpp:237-262) as one binary search per determinant
+__global__ void k_classify(const uint64_t* __restrict__ na, const uint64_t* __restrict__ nb, int64_t n_new,
+                           const uint64_t* __restrict__ oa, const uint64_t* __restrict__ ob, int64_t n_old,
+                           int32_t* __restrict__ new_to_old, int32_t* __restrict__ old_to_new,
+                           int32_t* __restrict__ kept_flag, int32_t* __restrict__ added_flag) {
+  const int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= n_new) return;
+  const uint64_t a = na[i], b = nb[i];
+  int64_t lo = 0, hi = n_old;
+  while (lo < hi) {
+    const int64_t mid = (lo + hi) >> 1;
+    const uint64_t ma = oa[mid], mb = ob[mid];
+    if (ma < a || (ma == a && mb < b)) lo = mid + 1; else hi = mid;
+  }
+  const bool found = lo < n_old && oa[lo] == a && ob[lo] == b;
+  new_to_old[i] = found ? int32_t(lo) : -1;
+  if (found) old_to_new[lo] = int32_t(i);
+  kept_flag[i] = found ? 1 : 0;
+  added_flag[i] = found ? 0 : 1;
+}
+// index lists and sub-lists of the kept / added determinants
+__global__ void k_split_lists(const uint64_t* __restrict__ na, const uint64_t* __restrict__ nb, int64_t n_new,
+                              const int32_t* __restrict__ kept_flag, const int32_t* __restrict__ kept_excl,
+                              const int32_t* __restrict__ added_excl, int32_t* __restrict__ kept_new,
+                              int32_t* __restrict__ added_new, uint64_t* __restrict__ ka, uint64_t* __restrict__ kb,
+                              uint64_t* __restrict__ aa, uint64_t* __restrict__ ab) {
+  const int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= n_new) return;
+  if (kept_flag[i]) {
+    const int32_t k = kept_excl[i];
+    kept_new[k] = int32_t(i); ka[k] = na[i]; kb[k] = nb[i];
+  } else {
+    const int32_t k = added_excl[i];
+    added_new[k] = int32_t(i); aa[k] = na[i]; ab[k] = nb[i];
+  }
+}
+// kept x kept block: the old rows of the kept determinants, dropped columns removed, columns
+// renumbered (old_to_new is monotone on the kept determinants, so rows stay ascending)
+template <bool FILL>
+__global__ void __launch_bounds__(ROW_WARPS * 32)
+k_kept_rows(int64_t n_kept, const int32_t* __restrict__ kept_new, const int32_t* __restrict__ new_to_old,
+            const int32_t* __restrict__ old_to_new, const int64_t* __restrict__ orp,
+            const int32_t* __restrict__ oci, const double* __restrict__ onz, int32_t* __restrict__ cnt,
+            const int64_t* __restrict__ kptr, int32_t* __restrict__ kci, double* __restrict__ knz) {
+  const int lane = threadIdx.x & 31;
+  const int64_t kr = (int64_t(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+  if (kr >= n_kept) return;
+  const int32_t io = new_to_old[kept_new[kr]];
+  const int64_t e0 = orp[io], e1 = orp[io + 1];
+  int64_t out = FILL ? kptr[kr] : 0;
+  int32_t c = 0;
+  for (int64_t e = e0; e < e1; e += 32) {
+    const int64_t p = e + lane;
+    int32_t cn = -1;
+    if (p < e1) cn = old_to_new[oci[p]];
+    const unsigned m = __ballot_sync(0xffffffffu, cn >= 0);
+    if (FILL && cn >= 0) {
+      const int64_t pos = out + __popc(m & ((1u << lane) - 1u));
+      kci[pos] = cn;
+      knz[pos] = onz[p];
+    }
+    out += __popc(m);
+    c += __popc(m);
+  }
+  if (!FILL && lane == 0) cnt[kr] = c;
+}
+// row lengths of the patched matrix: added rows = their freshly built row, kept rows = kept x kept
+// part + kept x added part
+__global__ void k_patch_count(int64_t n_new, const int32_t* __restrict__ kept_flag,
+                              const int32_t* __restrict__ kept_excl, const int32_t* __restrict__ added_excl,
+                              const int64_t* __restrict__ kptr, const int64_t* __restrict__ dkptr,
+                              const int64_t* __restrict__ daptr, int32_t* __restrict__ cnt) {
+  const int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= n_new) return;
+  if (kept_flag[i]) {
+    const int32_t k = kept_excl[i];
+    cnt[i] = int32_t((kptr[k + 1] - kptr[k]) + (dkptr ? dkptr[k + 1] - dkptr[k] : 0));
+  } else {
+    const int32_t k = added_excl[i];
+    cnt[i] = int32_t(daptr[k + 1] - daptr[k]);
+  }
+}
+__device__ __forceinline__ int64_t lower_bound_i32(const int32_t* __restrict__ v, int64_t n, int32_t x) {
+  int64_t lo = 0, hi = n;
+  while (lo < hi) {
+    const int64_t mid = (lo + hi) >> 1;
+    if (v[mid] < x) lo = mid + 1; else hi = mid;
+  }
+  return lo;
+}
+// merge by column: the two parts of a kept row have disjoint, ascending column sets, so every
+// element's final position is its own rank plus its lower bound in the other part
+__global__ void __launch_bounds__(ROW_WARPS * 32)
+k_patch_fill(int64_t n_new, const int32_t* __restrict__ kept_flag, const int32_t* __restrict__ kept_excl,
+             const int32_t* __restrict__ added_excl, const int64_t* __restrict__ kptr,
+             const int32_t* __restrict__ kci, const double* __restrict__ knz,
+             const int64_t* __restrict__ dkptr, const int32_t* __restrict__ dkci,
+             const double* __restrict__ dknz, const int64_t* __restrict__ daptr,
+             const int32_t* __restrict__ daci, const double* __restrict__ danz,
+             const int64_t* __restrict__ rowptr, int32_t* __restrict__ ci, double* __restrict__ nz) {
+  const int lane = threadIdx.x & 31;
+  const int64_t i = (int64_t(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+  if (i >= n_new) return;
+  const int64_t dst = rowptr[i];
+  if (!kept_flag[i]) {
+    const int32_t k = added_excl[i];
+    const int64_t src = daptr[k], len = daptr[k + 1] - src;
+    for (int64_t t = lane; t < len; t += 32) { ci[dst + t] = daci[src + t]; nz[dst + t] = danz[src + t]; }
+    return;
+  }
+  const int32_t k = kept_excl[i];
+  const int64_t ks = kptr[k], kl = kptr[k + 1] - ks;
+  const int64_t ds = dkptr ? dkptr[k] : 0, dl = dkptr ? dkptr[k + 1] - ds : 0;
+  for (int64_t t = lane; t < kl; t += 32) {
+    const int32_t c = kci[ks + t];
+    const int64_t pos = dst + t + (dl ? lower_bound_i32(dkci + ds, dl, c) : 0);
+    ci[pos] = c;
+    nz[pos] = knz[ks + t];
+  }
+  for (int64_t t = lane; t < dl; t += 32) {
+    const int32_t c = dkci[ds + t];
+    const int64_t pos = dst + t + lower_bound_i32(kci + ks, kl, c);
+    ci[pos] = c;
+    nz[pos] = dknz[ds + t];
+  }
+}
+
 }  // namespace
 
 // ------------------------------------------------------------------------------------
@@ -1380,6 +1564,308 @@ void hbuild_csr(b2ci_ctx* ctx, const b2ci_dets* dets, int64_t row_begin, int64_t
   out->rowptr = rowptr.take();
   out->colind = colind.take();
   out->nzval = nzval.take();
+}
+
+// ------------------------------------------------------------------------------------
+// Rectangular block over two alpha-grouped lists (make_csr_hamiltonian_block with bra != ket,
+// csr_hamiltonian.hpp:41-72), rows = bra determinants, columns = ket determinants renumbered by
+// gmap (their index in a common list, which also decides the bra/ket roles of every element).
+namespace {
+struct DetView {
+  const uint64_t* alpha;
+  const uint64_t* beta;
+  int64_t n;
+  const int32_t* gmap;  // may be NULL: the list is the common list
+};
+struct BlockOut {
+  DevBuf<int64_t> rowptr;
+  DevBuf<int32_t> colind;
+  DevBuf<double> nzval;
+  int64_t nnz = 0;
+};
+int32_t run_tables(b2ci_ctx* ctx, const DetView& L, DevBuf<int32_t>& run_of, DevBuf<int64_t>& run_start,
+                   DevBuf<uint64_t>& run_alpha) {
+  cudaStream_t st = ctx->stream;
+  DevBuf<int32_t> flag(L.n), excl(L.n + 1);
+  const unsigned gb = unsigned((L.n + 255) / 256);
+  k_run_flags<<<gb, 256, 0, st>>>(L.alpha, L.n, flag);
+  ctx->launches++;
+  B2_CHECK_LAUNCH();
+  exclusive_scan_i32(ctx, flag, excl, L.n);
+  run_of.alloc(L.n);
+  run_start.alloc(L.n + 1);
+  run_alpha.alloc(L.n);
+  k_run_scatter<<<gb, 256, 0, st>>>(L.alpha, L.n, flag, excl, run_of, run_start, run_alpha);
+  ctx->launches++;
+  B2_CHECK_LAUNCH();
+  int32_t nruns = 0;
+  B2_CUDA(cudaMemcpyAsync(&nruns, excl.p + L.n, 4, cudaMemcpyDeviceToHost, st));
+  B2_CUDA(cudaStreamSynchronize(st));
+  return nruns;
+}
+void build_block_general(b2ci_ctx* ctx, const DetView& bra, const DetView& ket, double thr, BlockOut& out) {
+  cudaStream_t st = ctx->stream;
+  const int64_t nrows = bra.n, nk = ket.n;
+  out.rowptr.alloc(nrows + 1);
+  out.nnz = 0;
+  if (nrows == 0 || nk == 0) {
+    B2_CUDA(cudaMemsetAsync(out.rowptr, 0, size_t(nrows + 1) * 8, st));
+    out.colind.alloc(1);
+    out.nzval.alloc(1);
+    return;
+  }
+  DevBuf<int32_t> bra_run, ket_run_of;
+  DevBuf<int64_t> bra_run_start, ket_run_start, adj_ptr;
+  DevBuf<uint64_t> bra_run_alpha, ket_run_alpha;
+  const int32_t nrb = run_tables(ctx, bra, bra_run, bra_run_start, bra_run_alpha);
+  const int32_t nrk = run_tables(ctx, ket, ket_run_of, ket_run_start, ket_run_alpha);
+  // bra-run x ket-run adjacency, alpha distance <= 2
+  DevBuf<uint32_t> adj;
+  {
+    DevBuf<int32_t> acnt(nrb);
+    adj_ptr.alloc(size_t(nrb) + 1);
+    const unsigned ga = unsigned((int64_t(nrb) * 32 + 255) / 256);
+    k_string_adjacency2<false><<<ga, 256, 0, st>>>(bra_run_alpha, nrb, ket_run_alpha, nrk, 2, acnt, nullptr, nullptr);
+    ctx->launches++;
+    B2_CHECK_LAUNCH();
+    exclusive_scan_i32_to_i64(ctx, acnt, adj_ptr, nrb);
+    int64_t nadj = 0;
+    B2_CUDA(cudaMemcpyAsync(&nadj, adj_ptr.p + nrb, 8, cudaMemcpyDeviceToHost, st));
+    B2_CUDA(cudaStreamSynchronize(st));
+    adj.alloc(nadj > 0 ? nadj : 1);
+    k_string_adjacency2<true><<<ga, 256, 0, st>>>(bra_run_alpha, nrb, ket_run_alpha, nrk, 2, nullptr, adj_ptr, adj);
+    ctx->launches++;
+    B2_CHECK_LAUNCH();
+  }
+  // ket determinants grouped by beta string; the group of every bra determinant's beta string
+  DevBuf<int32_t> bgrp_of(nk), bra_grp(nrows);
+  DevBuf<int64_t> bgrp_start;
+  DevBuf<uint32_t> bgrp_mem(nk), idx_alt(nk);
+  DevBuf<uint64_t> key(nk), key_alt(nk);
+  {
+    B2_CUDA(cudaMemcpyAsync(key, ket.beta, size_t(nk) * 8, cudaMemcpyDeviceToDevice, st));
+    iota_u32(ctx, bgrp_mem, nk);
+    std::vector<int> shifts;
+    for (int d = 0; d < (ctx->norb + 7) / 8; ++d) shifts.push_back(8 * d);
+    radix_sort_pairs(ctx, key, key_alt, bgrp_mem, idx_alt, nk, shifts);
+    DevBuf<int32_t> flag(nk), excl(nk + 1);
+    const unsigned gb = unsigned((nk + 255) / 256);
+    k_run_flags<<<gb, 256, 0, st>>>(key, nk, flag);
+    ctx->launches++;
+    B2_CHECK_LAUNCH();
+    exclusive_scan_i32(ctx, flag, excl, nk);
+    int32_t ngroups = 0;
+    B2_CUDA(cudaMemcpyAsync(&ngroups, excl.p + nk, 4, cudaMemcpyDeviceToHost, st));
+    B2_CUDA(cudaStreamSynchronize(st));
+    bgrp_start.alloc(size_t(ngroups) + 1);
+    k_group_scatter<<<gb, 256, 0, st>>>(key, bgrp_mem, nk, flag, excl, bgrp_of, bgrp_start, ngroups);
+    k_lookup_group<<<unsigned((nrows + 255) / 256), 256, 0, st>>>(bra.beta, nrows, key, bgrp_start, ngroups, bra_grp);
+    ctx->launches += 2;
+    B2_CHECK_LAUNCH();
+  }
+  RowArgs A;
+  A.I = ctx->ints;
+  A.alpha = ket.alpha;
+  A.beta = ket.beta;
+  A.run_of = ket_run_of;
+  A.run_start = ket_run_start;
+  A.adj_ptr = adj_ptr;
+  A.adj = adj;
+  A.bgrp_of = bgrp_of;
+  A.bgrp_start = bgrp_start;
+  A.bgrp_mem = bgrp_mem;
+  A.row_begin = 0;
+  A.nrows = nrows;
+  A.thr = thr;
+  A.row_cnt = nullptr; A.rowptr = nullptr; A.colind = nullptr; A.nzval = nullptr;
+  A.bra_alpha = bra.alpha;
+  A.bra_beta = bra.beta;
+  A.bra_run = bra_run;
+  A.bra_grp = bra_grp;
+  A.rowmap = bra.gmap;
+  A.colmap = ket.gmap;
+  const unsigned grid = unsigned((nrows + ROW_WARPS - 1) / ROW_WARPS);
+  int64_t nslots = 0;
+  DevBuf<int64_t> slot_ptr(nrows + 1);
+  {
+    DevBuf<int32_t> row_cnt(nrows);
+    A.row_cnt = row_cnt;
+    k_rows<false, false, true><<<grid, ROW_WARPS * 32, 0, st>>>(A);
+    ctx->launches++;
+    B2_CHECK_LAUNCH();
+    exclusive_scan_i32_to_i64(ctx, row_cnt, slot_ptr, nrows);
+    B2_CUDA(cudaMemcpyAsync(&nslots, slot_ptr.p + nrows, 8, cudaMemcpyDeviceToHost, st));
+    B2_CUDA(cudaStreamSynchronize(st));
+  }
+  DevBuf<int32_t> colind(nslots > 0 ? nslots : 1), kept(nrows);
+  DevBuf<double> nzval(nslots > 0 ? nslots : 1);
+  A.row_cnt = kept;
+  A.rowptr = slot_ptr;
+  A.colind = colind;
+  A.nzval = nzval;
+  if (thr > 0.0) k_rows<true, true, true><<<grid, ROW_WARPS * 32, 0, st>>>(A);
+  else k_rows<true, false, true><<<grid, ROW_WARPS * 32, 0, st>>>(A);
+  ctx->launches++;
+  B2_CHECK_LAUNCH();
+  int64_t nnz = nslots;
+  if (thr > 0.0) {
+    exclusive_scan_i32_to_i64(ctx, kept, out.rowptr, nrows);
+    B2_CUDA(cudaMemcpyAsync(&nnz, out.rowptr.p + nrows, 8, cudaMemcpyDeviceToHost, st));
+    B2_CUDA(cudaStreamSynchronize(st));
+    if (nnz != nslots) {
+      DevBuf<int32_t> ci_f(nnz > 0 ? nnz : 1);
+      DevBuf<double> nz_f(nnz > 0 ? nnz : 1);
+      k_compact_rows<<<unsigned((nrows * 32 + ROW_WARPS * 32 - 1) / (ROW_WARPS * 32)), ROW_WARPS * 32, 0, st>>>(
+          nrows, slot_ptr, out.rowptr, colind, nzval, ci_f, nz_f);
+      ctx->launches++;
+      B2_CHECK_LAUNCH();
+      B2_CUDA(cudaStreamSynchronize(st));
+      colind = std::move(ci_f);
+      nzval = std::move(nz_f);
+    }
+  } else {
+    out.rowptr = std::move(slot_ptr);
+  }
+  B2_CUDA(cudaStreamSynchronize(st));
+  out.nnz = nnz;
+  out.colind = std::move(colind);
+  out.nzval = std::move(nzval);
+}
+}  // namespace
+
+// Patched (incremental) build: the CSR of `nd` from the CSR of an overlapping list `od`
+// (CachedHamiltonianState / build_patched_operator, solvers/incremental_h_build.hpp:192-356).
+// The reference keeps the old matrix and applies three blocks (old-old with an index remap,
+// added x added, kept x added and its transpose) inside the Davidson operator; on the device the
+// blocks are merged into ONE ordinary CSR of the new list -- bit-identical to a full build,
+// because every element is the same function of its determinant pair and the old-to-new map is
+// monotone -- so sigma stays a single streaming SpMV and the result can seed the next patch.
+//   kept x kept  : old rows, dropped columns removed, columns renumbered
+//   kept x added : block build, bra = kept determinants, ket = added determinants
+//   added x all  : block build, bra = added determinants, ket = the whole new list
+// Returns false (nothing built) when n_kept / n_new < min_overlap (:266-283).
+bool hbuild_csr_patched(b2ci_ctx* ctx, const b2ci_dets* od, const b2ci_csr* oH, const b2ci_dets* nd, double thr,
+                        double min_overlap, b2ci_csr* out, int64_t* n_kept_out) {
+  if (!ctx->ints_dev) throw Error("b2ci_hbuild_csr_patched: integrals not uploaded");
+  if (ctx->nranks > 1) throw Error("b2ci_hbuild_csr_patched: not available with a communicator (row-sharded builds are full builds)");
+  if (!od || !oH || !nd) throw Error("b2ci_hbuild_csr_patched: null argument");
+  const int64_t n_old = od->n, n_new = nd->n;
+  if (oH->row_begin != 0 || oH->nrows != n_old || oH->ncols != n_old)
+    throw Error("b2ci_hbuild_csr_patched: the cached matrix must be the full square matrix of the old list");
+  if (n_new >= (int64_t(1) << 30)) throw Error("b2ci_hbuild_csr_patched: more than 2^30 determinants per list");
+  if (!(thr >= 0.0)) throw Error("b2ci_hbuild_csr_patched: h_thresh must be >= 0");
+  cudaStream_t st = ctx->stream;
+  auto& T = ctx->timers;
+  T["h_build.setup"] = T["h_build.count"] = T["h_build.fill"] = T["h_build.thresh"] = 0.;
+  T["h_build.patch_kept"] = T["h_build.patch_added"] = 0.;
+  if (n_kept_out) *n_kept_out = 0;
+  if (n_new == 0 || n_old == 0) return false;
+  // ---- classify (both lists spin-sorted)
+  DevBuf<int32_t> new_to_old(n_new), old_to_new(n_old), kflag(n_new), aflag(n_new), kexcl(n_new + 1), aexcl(n_new + 1);
+  int32_t n_kept = 0;
+  {
+    ScopedTimer t(ctx, "h_build.setup", true);
+    B2_CUDA(cudaMemsetAsync(old_to_new, 0xFF, size_t(n_old) * 4, st));
+    k_classify<<<unsigned((n_new + 255) / 256), 256, 0, st>>>(nd->alpha, nd->beta, n_new, od->alpha, od->beta, n_old,
+                                                              new_to_old, old_to_new, kflag, aflag);
+    ctx->launches++;
+    B2_CHECK_LAUNCH();
+    exclusive_scan_i32(ctx, kflag, kexcl, n_new);
+    exclusive_scan_i32(ctx, aflag, aexcl, n_new);
+    B2_CUDA(cudaMemcpyAsync(&n_kept, kexcl.p + n_new, 4, cudaMemcpyDeviceToHost, st));
+    B2_CUDA(cudaStreamSynchronize(st));
+  }
+  if (n_kept_out) *n_kept_out = n_kept;
+  const int64_t n_added = n_new - n_kept;
+  T["h_build.patch_kept"] = double(n_kept);
+  T["h_build.patch_added"] = double(n_added);
+  if (double(n_kept) / double(n_new) < min_overlap) return false;
+  DevBuf<int32_t> kept_new(n_kept > 0 ? n_kept : 1), added_new(n_added > 0 ? n_added : 1);
+  DevBuf<uint64_t> ka(n_kept > 0 ? n_kept : 1), kb(n_kept > 0 ? n_kept : 1), aa(n_added > 0 ? n_added : 1),
+      ab(n_added > 0 ? n_added : 1);
+  DevBuf<int64_t> kptr(size_t(n_kept) + 1);
+  DevBuf<int32_t> kci;
+  DevBuf<double> knz;
+  {
+    ScopedTimer t(ctx, "h_build.setup", true);
+    k_split_lists<<<unsigned((n_new + 255) / 256), 256, 0, st>>>(nd->alpha, nd->beta, n_new, kflag, kexcl, aexcl,
+                                                                 kept_new, added_new, ka, kb, aa, ab);
+    ctx->launches++;
+    B2_CHECK_LAUNCH();
+  }
+  // ---- kept x kept from the cached matrix
+  {
+    ScopedTimer t(ctx, "h_build.count", true);
+    DevBuf<int32_t> kcnt(n_kept > 0 ? n_kept : 1);
+    const unsigned gk = unsigned((int64_t(n_kept) * 32 + ROW_WARPS * 32 - 1) / (ROW_WARPS * 32));
+    int64_t nkk = 0;
+    if (n_kept) {
+      k_kept_rows<false><<<gk, ROW_WARPS * 32, 0, st>>>(n_kept, kept_new, new_to_old, old_to_new, oH->rowptr, oH->colind,
+                                                       oH->nzval, kcnt, nullptr, nullptr, nullptr);
+      ctx->launches++;
+      B2_CHECK_LAUNCH();
+    }
+    exclusive_scan_i32_to_i64(ctx, kcnt, kptr, n_kept);
+    B2_CUDA(cudaMemcpyAsync(&nkk, kptr.p + n_kept, 8, cudaMemcpyDeviceToHost, st));
+    B2_CUDA(cudaStreamSynchronize(st));
+    kci.alloc(nkk > 0 ? nkk : 1);
+    knz.alloc(nkk > 0 ? nkk : 1);
+    if (n_kept) {
+      k_kept_rows<true><<<gk, ROW_WARPS * 32, 0, st>>>(n_kept, kept_new, new_to_old, old_to_new, oH->rowptr, oH->colind,
+                                                      oH->nzval, nullptr, kptr, kci, knz);
+      ctx->launches++;
+      B2_CHECK_LAUNCH();
+    }
+  }
+  // ---- the two freshly evaluated blocks
+  BlockOut DK, DA;
+  if (n_added) {
+    ScopedTimer t(ctx, "h_build.fill", true);
+    const DetView kept_v{ka, kb, n_kept, kept_new}, added_v{aa, ab, n_added, added_new}, all_v{nd->alpha, nd->beta, n_new, nullptr};
+    if (n_kept) build_block_general(ctx, kept_v, added_v, thr, DK);
+    build_block_general(ctx, added_v, all_v, thr, DA);
+  }
+  // ---- merge
+  out->nrows = n_new;
+  out->ncols = n_new;
+  out->row_begin = 0;
+  DevBuf<int64_t> rowptr(n_new + 1);
+  DevBuf<int32_t> ci;
+  DevBuf<double> nz;
+  int64_t nnz = 0;
+  {
+    ScopedTimer t(ctx, "h_build.thresh", true);
+    DevBuf<int32_t> cnt(n_new);
+    const int64_t* dkp = (n_added && n_kept) ? DK.rowptr.p : nullptr;
+    DevBuf<int64_t> zero_ptr;
+    const int64_t* dap = DA.rowptr.p;
+    if (!n_added) {  // nothing was added: every row is a kept row
+      zero_ptr.alloc(1);
+      B2_CUDA(cudaMemsetAsync(zero_ptr, 0, 8, st));
+      dap = zero_ptr;
+    }
+    k_patch_count<<<unsigned((n_new + 255) / 256), 256, 0, st>>>(n_new, kflag, kexcl, aexcl, kptr, dkp, dap, cnt);
+    ctx->launches++;
+    B2_CHECK_LAUNCH();
+    exclusive_scan_i32_to_i64(ctx, cnt, rowptr, n_new);
+    B2_CUDA(cudaMemcpyAsync(&nnz, rowptr.p + n_new, 8, cudaMemcpyDeviceToHost, st));
+    B2_CUDA(cudaStreamSynchronize(st));
+    ci.alloc(nnz > 0 ? nnz : 1);
+    nz.alloc(nnz > 0 ? nnz : 1);
+    k_patch_fill<<<unsigned((n_new * 32 + ROW_WARPS * 32 - 1) / (ROW_WARPS * 32)), ROW_WARPS * 32, 0, st>>>(
+        n_new, kflag, kexcl, aexcl, kptr, kci, knz, dkp, DK.colind.p, DK.nzval.p, dap, DA.colind.p, DA.nzval.p, rowptr,
+        ci, nz);
+    ctx->launches++;
+    B2_CHECK_LAUNCH();
+    B2_CUDA(cudaStreamSynchronize(st));
+  }
+  out->nnz = nnz;
+  out->rowptr = rowptr.take();
+  out->colind = ci.take();
+  out->nzval = nz.take();
+  out->colind_cap = 0;
+  out->nzval_cap = 0;
+  return true;
 }
 
 }  // namespace b2ci

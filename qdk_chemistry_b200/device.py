@@ -110,6 +110,16 @@ class Context:
         check(lib().b2ci_hbuild_csr(self.h, dets.h, r0, r1, h_thresh, C.byref(h)))
         return CsrMatrix(self, h)
 
+    def hbuild_patched(self, old_dets: "DetList", old_H: "CsrMatrix", new_dets: "DetList", h_thresh: float,
+                       min_overlap: float = 0.3):
+        """build_patched_operator (incremental_h_build.hpp:219-356) merged into one CSR of
+        ``new_dets``. Returns (matrix or None when the overlap is below ``min_overlap``, n_kept)."""
+        h = C.c_void_p()
+        nk = C.c_int64(0)
+        check(lib().b2ci_hbuild_csr_patched(self.h, old_dets.h, old_H.h, new_dets.h, h_thresh, min_overlap,
+                                            C.byref(h), C.byref(nk)))
+        return (CsrMatrix(self, h) if h.value else None), nk.value
+
     def upload_csr(self, rowptr, colind, nzval) -> "CsrMatrix":
         rp = np.ascontiguousarray(rowptr, dtype=np.int64)
         ci = np.ascontiguousarray(colind, dtype=np.int64)

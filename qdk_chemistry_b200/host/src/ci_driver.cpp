@@ -83,7 +83,7 @@ struct AsciSettings {  // macis::ASCISettings fields that reach the path
   int64_t ntdets_max, ntdets_min, ncdets_max, max_refine_iter;
   double h_el_tol, rv_prune_tol, grow_factor, min_grow_factor, growth_backoff_rate, growth_recovery_rate,
       refine_energy_tol, core_selection_threshold, min_warm_start_overlap, grow_ci_residual_tolerance,
-      taper_grow_factor;
+      taper_grow_factor, min_patch_overlap;
   bool just_singles, warm_start_davidson, fixed_core;
 };
 AsciSettings get_asci_settings(const data::Settings& s) {  // macis_base.cpp:47-134
@@ -111,6 +111,7 @@ AsciSettings get_asci_settings(const data::Settings& s) {  // macis_base.cpp:47-
   a.min_warm_start_overlap = s.get<double>("min_warm_start_overlap");
   a.grow_ci_residual_tolerance = s.get<double>("grow_ci_residual_tolerance");
   a.taper_grow_factor = s.get<double>("taper_grow_factor");
+  a.min_patch_overlap = s.get<double>("min_patch_overlap");
   if (a.grow_factor <= 1.0) throw std::runtime_error("grow_factor must be > 1.0, got " + std::to_string(a.grow_factor));
   if (a.min_grow_factor <= 1.0)
     throw std::runtime_error("min_grow_factor must be > 1.0, got " + std::to_string(a.min_grow_factor));
@@ -172,13 +173,31 @@ class CiSession {
 
   // selected_ci_diag on a device-resident list: H build of this rank's rows + Davidson with
   // the guess policy of serial_selected_ci_diag. X: empty or a guess; returns the full vector.
-  double selected_ci_diag(const b2ci_dets* dets, int64_t n, double matel_tol, int64_t max_m, double res_tol,
-                          std::vector<double>& X) {
+  //
+  // cache (ASCI iterations, single rank): CachedHamiltonianState of incremental_h_build.hpp. When
+  // the previous list overlaps the new one by min_patch_overlap or more, only the blocks that touch
+  // added determinants are evaluated (b2ci_hbuild_csr_patched); the matrix and the device list of
+  // this call are then kept for the next one. take_dets: the session owns `dets` afterwards.
+  double selected_ci_diag(b2ci_dets* dets, int64_t n, double matel_tol, int64_t max_m, double res_tol,
+                          std::vector<double>& X, bool use_cache = false, double min_patch_overlap = 0.3,
+                          bool take_dets = false) {
     if (n == 0) throw std::runtime_error("selected_ci_diag: empty determinant list");
     X.resize(size_t(n), 0.0);
     const auto rows = my_rows(n);
     b2ci_csr* H = nullptr;
-    B2(b2ci_hbuild_csr(ctx_, dets, rows.first, rows.second, matel_tol, &H));
+    struct DetsGuard {  // frees a taken-over list unless the cache adopts it
+      b2ci_ctx* c;
+      b2ci_dets* d;
+      ~DetsGuard() { if (d) b2ci_dets_free(c, d); }
+    } guard{ctx_, take_dets ? dets : nullptr};
+    use_cache = use_cache && nranks_ == 1 && take_dets && !getenv("B2CI_NO_INCREMENTAL");
+    if (use_cache && cache_H_ && cache_tol_ == matel_tol) {
+      int64_t n_kept = 0;
+      B2(b2ci_hbuild_csr_patched(ctx_, cache_dets_, cache_H_, dets, matel_tol, min_patch_overlap, &H, &n_kept));
+      g_stats["h_build_patch_last_overlap"] = double(n_kept) / double(n);
+      if (H) g_stats["h_build_patched"] += 1.0;
+    }
+    if (!H) B2(b2ci_hbuild_csr(ctx_, dets, rows.first, rows.second, matel_tol, &H));
     if (nranks_ > 1) {  // every rank knows the split (row_block): no exchange of block sizes
       std::vector<int64_t> off(size_t(nranks_) + 1, 0);
       for (int r = 0; r < nranks_; ++r) off[size_t(r) + 1] = row_block(n, r, nranks_).second;
@@ -201,23 +220,32 @@ class CiSession {
     add_timer("davidson_other_ms", {"davidson.RR_DUR", "davidson.RES_DUR", "davidson.GS_DUR"});
     g_stats["davidson_iterations"] += double(niter);
     g_stats["davidson_calls"] += 1.0;
-    b2ci_csr_free(ctx_, H);
+    if (use_cache) {
+      drop_cache();
+      cache_H_ = H;
+      cache_dets_ = dets;
+      cache_tol_ = matel_tol;
+      guard.d = nullptr;
+    } else {
+      b2ci_csr_free(ctx_, H);
+    }
     if (rc != 0) throw std::runtime_error(err);
     return E;
   }
   double selected_ci_diag(const std::vector<Det>& dets, double matel_tol, int64_t max_m, double res_tol,
-                          std::vector<double>& X) {
+                          std::vector<double>& X, bool use_cache = false, double min_patch_overlap = 0.3) {
     b2ci_dets* d = nullptr;
     B2(b2ci_dets_upload(ctx_, reinterpret_cast<const uint64_t*>(dets.data()), 2, int64_t(dets.size()), &d));
-    try {
-      const double E = selected_ci_diag(d, int64_t(dets.size()), matel_tol, max_m, res_tol, X);
-      b2ci_dets_free(ctx_, d);
-      return E;
-    } catch (...) {
-      b2ci_dets_free(ctx_, d);
-      throw;
-    }
+    // the list is handed over: freed there, or adopted by the cache
+    return selected_ci_diag(d, int64_t(dets.size()), matel_tol, max_m, res_tol, X, use_cache, min_patch_overlap, true);
   }
+  void drop_cache() {  // CachedHamiltonianState::clear
+    if (cache_H_) b2ci_csr_free(ctx_, cache_H_);
+    if (cache_dets_) b2ci_dets_free(ctx_, cache_dets_);
+    cache_H_ = nullptr;
+    cache_dets_ = nullptr;
+  }
+  ~CiSession() { drop_cache(); }
   // dense branch: full CSR (index pattern as the reference's int32 build) -> lowest eigenpair
   double dense_diag(const b2ci_dets* dets, int64_t n, double matel_tol, std::vector<double>& X) {
     X.assign(size_t(n), 0.0);
@@ -315,6 +343,9 @@ class CiSession {
   std::unique_lock<std::mutex> lock_;
   b2ci_ctx* ctx_ = nullptr;  // borrowed from the process runtime
   int rank_ = 0, nranks_ = 1;
+  b2ci_csr* cache_H_ = nullptr;  // matrix and list of the last cached selected_ci_diag
+  b2ci_dets* cache_dets_ = nullptr;
+  double cache_tol_ = 0.;
 };
 
 std::shared_ptr<data::Wavefunction> make_wavefunction(const std::vector<Det>& dets, std::vector<double> C,
@@ -487,7 +518,8 @@ double asci_iter(CiSession& S, const AsciSettings& a, const McscfSettings& m, in
     }
   }
   wt.reset(new WallTimer("wall_selected_ci_diag_ms"));
-  const double E = S.selected_ci_diag(wfn, m.ci_matel_tol, m.ci_max_subspace, m.ci_res_tol, X_local);
+  const double E = S.selected_ci_diag(wfn, m.ci_matel_tol, m.ci_max_subspace, m.ci_res_tol, X_local, true,
+                                      a.min_patch_overlap);
   wt.reset();
   X = std::move(X_local);
   g_stats["asci_iterations"] += 1.0;
@@ -556,7 +588,8 @@ double asci_refine(CiSession& S, const AsciSettings& a, const McscfSettings& m, 
           auto it = std::lower_bound(uni.begin(), uni.end(), wfn[i], spin_less);
           if (it != uni.end() && *it == wfn[i]) Xu[size_t(it - uni.begin())] = X[i];
         }
-        const double Eu = S.selected_ci_diag(uni, m.ci_matel_tol, m.ci_max_subspace, m.ci_res_tol, Xu);
+        const double Eu = S.selected_ci_diag(uni, m.ci_matel_tol, m.ci_max_subspace, m.ci_res_tol, Xu, true,
+                                             a.min_patch_overlap);
         const size_t ext = std::min(size_t(oscillation), max_ext - total_ext);
         if (ext > 0) { max_iter += ext; total_ext += ext; }
         wfn = std::move(uni);

@@ -234,3 +234,35 @@ def test_asci_plugin_on_36_orbitals_matches_reference_run():
     # mirror images (its unstable sort decides which): the sets are compared modulo that flip
     canon = lambda s: sorted((min(x, y), max(x, y)) for x, y in s)
     assert canon(got) == canon(want)
+
+
+def test_asci_refine_uses_patched_builds_with_identical_results(water, monkeypatch):
+    # incremental H build between ASCI iterations (asci/refine.hpp:84-90, selected_ci_diag.hpp:217-256):
+    # refine iterations overlap their predecessor by far more than min_patch_overlap
+    kw = dict(ntdets_max=3000, core_selection_strategy="fixed", ci_residual_tolerance=1e-8, max_refine_iter=4,
+              refine_energy_tol=1e-12)
+    try:
+        E1, w1 = alg.create(MC, "macis_asci", **kw).run(_ham(water), 5, 5)
+    except RuntimeError as e:      # "ASCI Refine did not converge" still ran the iterations
+        assert "Refine" in str(e)
+        E1, w1 = None, None
+    st = alg.last_run_stats()
+    assert st["h_build_patched"] >= 3 and st["h_build_patch_last_overlap"] > 0.3
+    monkeypatch.setenv("B2CI_NO_INCREMENTAL", "1")
+    try:
+        E2, w2 = alg.create(MC, "macis_asci", **kw).run(_ham(water), 5, 5)
+    except RuntimeError:
+        E2, w2 = None, None
+    assert alg.last_run_stats().get("h_build_patched", 0.0) == 0.0
+    assert (E1 is None) == (E2 is None)
+    if E1 is not None:
+        assert E1 == E2                      # the patched matrix is bit-identical, so is everything after it
+        a1, b1 = _words(w1)
+        a2, b2 = _words(w2)
+        assert np.array_equal(a1, a2) and np.array_equal(b1, b2)
+        assert np.array_equal(w1.get_coefficients(), w2.get_coefficients())
+    # a lower gate is a setting like in the reference
+    monkeypatch.delenv("B2CI_NO_INCREMENTAL")
+    E3, _ = alg.create(MC, "macis_asci", ntdets_max=3000, core_selection_strategy="fixed", max_refine_iter=2,
+                       refine_energy_tol=1e-3, min_patch_overlap=0.05).run(_ham(water), 5, 5)
+    assert alg.last_run_stats()["h_build_patched"] >= 1

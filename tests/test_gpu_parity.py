@@ -314,3 +314,78 @@ def test_dense_ground_state_matches_davidson(ctx):
     import scipy.sparse as sps
     M = sps.csr_matrix((nz, ci, rp), shape=(len(a), len(a))).toarray()
     assert abs(Ed - np.linalg.eigvalsh(M)[0]) < 1e-11
+
+
+# ---- patched (incremental) build: CachedHamiltonianState / build_patched_operator ---------------
+def _spin_sorted_subset(a, b, pick):
+    sa, sb = a[pick], b[pick]
+    o = port.spin_sort_order(sa, sb)
+    return sa[o], sb[o]
+
+
+@pytest.mark.parametrize("name,n_old,n_new,n_common,seed", [
+    ("small_cas8", 600, 700, 500, 1),     # ordinary refine step: most determinants kept
+    ("small_cas8", 300, 900, 300, 2),     # pure growth: old list is a subset
+    ("small_cas8", 800, 500, 500, 3),     # pure shrink: nothing added, rows and columns dropped
+    ("hubbard_4x2", 1500, 1600, 1200, 4),  # exact zeros at the threshold
+    ("n2_cas10", 3000, 3300, 2500, 5),
+    ("wide36", 400, 450, 300, 6),         # two-word determinants
+])
+@pytest.mark.parametrize("thr", [EPS, 0.0])
+def test_patched_build_is_bit_identical_to_full_build(ctx, name, n_old, n_new, n_common, seed, thr):
+    """The merged patch (kept x kept from the cached matrix, kept x added and added x all freshly
+    evaluated) equals the full build of the new list bit for bit, and equals the oracle's CSR."""
+    sp = W.config(name)
+    rng = np.random.default_rng(seed)
+    if name == "wide36":
+        pool = set()
+        while len(pool) < n_old + n_new:
+            pool.add((sum(1 << int(i) for i in rng.choice(sp.norb, sp.nalpha, replace=False)),
+                      sum(1 << int(i) for i in rng.choice(sp.norb, sp.nbeta, replace=False))))
+        pool = sorted(pool)
+        a = np.array([p[0] for p in pool], dtype=np.uint64)
+        b = np.array([p[1] for p in pool], dtype=np.uint64)
+        nbits = 128
+    else:
+        a, b = port.generate_hilbert_space(sp.norb, sp.nalpha, sp.nbeta)
+        nbits = 64
+    perm = rng.permutation(len(a))
+    common, only_old, only_new = perm[:n_common], perm[n_common:n_old], perm[n_old:n_old + n_new - n_common]
+    oa, ob = _spin_sorted_subset(a, b, np.concatenate([common, only_old]))
+    na, nb = _spin_sorted_subset(a, b, np.concatenate([common, only_new]))
+    wpd = nbits // 64
+    ctx.upload_integrals(sp.norb, sp.T, sp.V)
+    d_old = ctx.upload_dets(port.pack(oa, ob, nbits), wpd)
+    d_new = ctx.upload_dets(port.pack(na, nb, nbits), wpd)
+    H_old = ctx.hbuild(d_old, thr)
+    H_pat, n_kept = ctx.hbuild_patched(d_old, H_old, d_new, thr, min_overlap=0.3)
+    assert n_kept == n_common and H_pat is not None
+    rp, ci, nz = H_pat.download()
+    frp, fci, fnz = ctx.hbuild(d_new, thr).download()
+    assert np.array_equal(rp, frp) and np.array_equal(ci, fci) and np.array_equal(nz, fnz)
+    orp, oci, onz = port.Ham(sp.norb, sp.T, sp.V).hbuild(na, nb, thr)
+    assert np.array_equal(rp, orp) and np.array_equal(ci, oci) and np.array_equal(nz, onz)
+    # a patched matrix can seed the next patch (here: back to the old list)
+    H_back, _ = ctx.hbuild_patched(d_new, H_pat, d_old, thr, min_overlap=0.0)
+    brp, bci, bnz = H_back.download()
+    o2 = H_old.download()
+    assert np.array_equal(brp, o2[0]) and np.array_equal(bci, o2[1]) and np.array_equal(bnz, o2[2])
+
+
+def test_patched_build_overlap_gate_and_errors(ctx):
+    sp = W.config("small_cas8")
+    a, b = port.generate_hilbert_space(sp.norb, sp.nalpha, sp.nbeta)
+    o = port.spin_sort_order(a, b)      # both lists must be spin_comparator-sorted
+    a, b = a[o], b[o]
+    ctx.upload_integrals(sp.norb, sp.T, sp.V)
+    d_old = ctx.upload_dets(port.pack(a[:100], b[:100]), 1)
+    d_new = ctx.upload_dets(port.pack(a[50:1000], b[50:1000]), 1)
+    H_old = ctx.hbuild(d_old, EPS)
+    H, n_kept = ctx.hbuild_patched(d_old, H_old, d_new, EPS, min_overlap=0.3)   # 50 / 950 kept
+    assert H is None and n_kept == 50
+    H, _ = ctx.hbuild_patched(d_old, H_old, d_new, EPS, min_overlap=0.05)
+    frp, fci, fnz = ctx.hbuild(d_new, EPS).download()
+    rp, ci, nz = H.download()
+    assert np.array_equal(rp, frp) and np.array_equal(ci, fci) and np.array_equal(nz, fnz)
+    with pytest.raises(device.B2ciError, match="full square"):
+        ctx.hbuild_patched(d_old, ctx.hbuild(d_old, EPS, (10, 60)), d_new, EPS)
