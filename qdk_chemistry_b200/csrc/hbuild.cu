@@ -1760,6 +1760,15 @@ bool hbuild_csr_patched(b2ci_ctx* ctx, const b2ci_dets* od, const b2ci_csr* oH, 
   T["h_build.patch_kept"] = T["h_build.patch_added"] = 0.;
   if (n_kept_out) *n_kept_out = 0;
   if (n_new == 0 || n_old == 0) return false;
+  const bool trace = getenv("B2CI_HBUILD_TRACE") != nullptr;
+  auto t_host0 = std::chrono::steady_clock::now();
+  auto mark = [&](const char* what) {
+    if (!trace) return;
+    cudaStreamSynchronize(st);
+    auto t = std::chrono::steady_clock::now();
+    fprintf(stderr, "[hbuild patched] %-24s +%9.1f us\n", what, std::chrono::duration<double, std::micro>(t - t_host0).count());
+    t_host0 = t;
+  };
   // ---- classify (both lists spin-sorted)
   DevBuf<int32_t> new_to_old(n_new), old_to_new(n_old), kflag(n_new), aflag(n_new), kexcl(n_new + 1), aexcl(n_new + 1);
   int32_t n_kept = 0;
@@ -1779,6 +1788,7 @@ bool hbuild_csr_patched(b2ci_ctx* ctx, const b2ci_dets* od, const b2ci_csr* oH, 
   const int64_t n_added = n_new - n_kept;
   T["h_build.patch_kept"] = double(n_kept);
   T["h_build.patch_added"] = double(n_added);
+  mark("classify");
   if (double(n_kept) / double(n_new) < min_overlap) return false;
   DevBuf<int32_t> kept_new(n_kept > 0 ? n_kept : 1), added_new(n_added > 0 ? n_added : 1);
   DevBuf<uint64_t> ka(n_kept > 0 ? n_kept : 1), kb(n_kept > 0 ? n_kept : 1), aa(n_added > 0 ? n_added : 1),
@@ -1817,13 +1827,16 @@ bool hbuild_csr_patched(b2ci_ctx* ctx, const b2ci_dets* od, const b2ci_csr* oH, 
       B2_CHECK_LAUNCH();
     }
   }
+  mark("kept x kept");
   // ---- the two freshly evaluated blocks
   BlockOut DK, DA;
   if (n_added) {
     ScopedTimer t(ctx, "h_build.fill", true);
     const DetView kept_v{ka, kb, n_kept, kept_new}, added_v{aa, ab, n_added, added_new}, all_v{nd->alpha, nd->beta, n_new, nullptr};
     if (n_kept) build_block_general(ctx, kept_v, added_v, thr, DK);
+    mark("kept x added");
     build_block_general(ctx, added_v, all_v, thr, DA);
+    mark("added x all");
   }
   // ---- merge
   out->nrows = n_new;
@@ -1850,14 +1863,17 @@ bool hbuild_csr_patched(b2ci_ctx* ctx, const b2ci_dets* od, const b2ci_csr* oH, 
     exclusive_scan_i32_to_i64(ctx, cnt, rowptr, n_new);
     B2_CUDA(cudaMemcpyAsync(&nnz, rowptr.p + n_new, 8, cudaMemcpyDeviceToHost, st));
     B2_CUDA(cudaStreamSynchronize(st));
+    mark("merge count");
     ci.alloc(nnz > 0 ? nnz : 1);
     nz.alloc(nnz > 0 ? nnz : 1);
+    mark("merge alloc");
     k_patch_fill<<<unsigned((n_new * 32 + ROW_WARPS * 32 - 1) / (ROW_WARPS * 32)), ROW_WARPS * 32, 0, st>>>(
         n_new, kflag, kexcl, aexcl, kptr, kci, knz, dkp, DK.colind.p, DK.nzval.p, dap, DA.colind.p, DA.nzval.p, rowptr,
         ci, nz);
     ctx->launches++;
     B2_CHECK_LAUNCH();
     B2_CUDA(cudaStreamSynchronize(st));
+    mark("merge fill");
   }
   out->nnz = nnz;
   out->rowptr = rowptr.take();

@@ -193,11 +193,19 @@ class CiSession {
     use_cache = use_cache && nranks_ == 1 && take_dets && !getenv("B2CI_NO_INCREMENTAL");
     if (use_cache && cache_H_ && cache_tol_ == matel_tol) {
       int64_t n_kept = 0;
-      B2(b2ci_hbuild_csr_patched(ctx_, cache_dets_, cache_H_, dets, matel_tol, min_patch_overlap, &H, &n_kept));
+      // a patch that cannot be built (three matrices do not fit the device) is not an error:
+      // the cache is dropped and the full build runs with the memory it held
+      if (b2ci_hbuild_csr_patched(ctx_, cache_dets_, cache_H_, dets, matel_tol, min_patch_overlap, &H, &n_kept) != 0) {
+        H = nullptr;
+        g_stats["h_build_patch_failed"] += 1.0;
+      }
       g_stats["h_build_patch_last_overlap"] = double(n_kept) / double(n);
       if (H) g_stats["h_build_patched"] += 1.0;
     }
-    if (!H) B2(b2ci_hbuild_csr(ctx_, dets, rows.first, rows.second, matel_tol, &H));
+    if (!H) {
+      drop_cache();
+      B2(b2ci_hbuild_csr(ctx_, dets, rows.first, rows.second, matel_tol, &H));
+    }
     if (nranks_ > 1) {  // every rank knows the split (row_block): no exchange of block sizes
       std::vector<int64_t> off(size_t(nranks_) + 1, 0);
       for (int r = 0; r < nranks_; ++r) off[size_t(r) + 1] = row_block(n, r, nranks_).second;
