@@ -72,6 +72,21 @@ int b2ci_dets_free(b2ci_ctx* ctx, b2ci_dets* d);
  * h_thresh > 0, everything structurally connected kept when h_thresh == 0. */
 int b2ci_hbuild_csr(b2ci_ctx* ctx, const b2ci_dets* dets, int64_t row_begin, int64_t row_end,
                     double h_thresh, b2ci_csr** out);
+/* Which generator's pattern rules b2ci_hbuild_csr / b2ci_hbuild_csr_patched follow: QDK's
+ * hamiltonian_build_algorithm setting (macis_asci.hpp:174-179, macis_asci.cpp:92-118).
+ *   SORTED_DOUBLE_LOOP : sorted_double_loop.hpp:86-451 -- |h| > h_thresh kept (diagonal included),
+ *                        alpha-empty determinants skipped
+ *   RESIDUE_ARRAYS, DYNAMIC_BIT_MASKING : both end in build_csr_from_pairs
+ *                        (connection_build_utils.hpp:125-249) -- the diagonal is always stored,
+ *                        an off-diagonal element is dropped only when |h| < h_thresh, alpha-empty
+ *                        determinants are ordinary determinants. The reference's two generators
+ *                        differ only in how the CPU enumerates the connected pairs; on the device
+ *                        both take the same row scan. Matrix elements are identical in all three.
+ * The selection stays with the context until changed. */
+#define B2CI_GEN_SORTED_DOUBLE_LOOP 0
+#define B2CI_GEN_RESIDUE_ARRAYS 1
+#define B2CI_GEN_DYNAMIC_BIT_MASKING 2
+int b2ci_set_hamiltonian_generator(b2ci_ctx* ctx, int generator);
 /* Incremental build between ASCI iterations: CachedHamiltonianState + build_patched_operator
  * (external/macis/include/macis/solvers/incremental_h_build.hpp:192-356), called from
  * selected_ci_diag (solvers/selected_ci_diag.hpp:217-256). old_H must be the full square matrix

@@ -57,6 +57,8 @@ def lib():
         L.op_matrix_element.argtypes = [vp, C.c_uint64, C.c_uint64, C.c_uint64, C.c_uint64]
         L.op_hbuild_rows.restype = i64
         L.op_hbuild_rows.argtypes = [vp, vp, vp, i64, i64, i64, dbl, vp, vp, vp]
+        L.op_hbuild_rows_gen.restype = i64
+        L.op_hbuild_rows_gen.argtypes = [vp, vp, vp, i64, i64, i64, dbl, i32, vp, vp, vp]
         L.op_spmv.argtypes = [i64, vp, vp, vp, vp, vp]
         L.op_extract_diagonal.argtypes = [i64, vp, vp, vp, vp]
         L.op_davidson.restype = i32
@@ -140,15 +142,17 @@ class Ham:
     def matrix_element(self, bra_a, bra_b, ket_a, ket_b) -> float:
         return lib().op_matrix_element(self.h, int(bra_a), int(bra_b), int(ket_a), int(ket_b))
 
-    def hbuild(self, alpha, beta, thresh: float, rows: Optional[Tuple[int, int]] = None):
+    def hbuild(self, alpha, beta, thresh: float, rows: Optional[Tuple[int, int]] = None,
+               generator: str = "sorted_double_loop"):
         a, b = _u64(alpha), _u64(beta)
         n = a.size
         r0, r1 = rows if rows is not None else (0, n)
+        rule = 0 if generator in ("", "sdl", "sorted_double_loop") else 1   # residue_arrays, dynamic_bit_masking
         rp = np.zeros(r1 - r0 + 1, dtype=np.int64)
-        nnz = lib().op_hbuild_rows(self.h, _p(a), _p(b), n, r0, r1, thresh, _p(rp), None, None)
+        nnz = lib().op_hbuild_rows_gen(self.h, _p(a), _p(b), n, r0, r1, thresh, rule, _p(rp), None, None)
         ci = np.empty(nnz, dtype=np.int64)
         nz = np.empty(nnz, dtype=np.float64)
-        lib().op_hbuild_rows(self.h, _p(a), _p(b), n, r0, r1, thresh, _p(rp), _p(ci), _p(nz))
+        lib().op_hbuild_rows_gen(self.h, _p(a), _p(b), n, r0, r1, thresh, rule, _p(rp), _p(ci), _p(nz))
         return rp, ci, nz
 
     def asci_candidates(self, calpha, cbeta, coeff, E0, h_el_tol=1e-8, just_singles=False):

@@ -231,6 +231,16 @@ double op_matrix_element(const op_ham* h, uint64_t bra_a, uint64_t bra_b, uint64
 int64_t op_hbuild_rows(const op_ham* h, const uint64_t* alpha, const uint64_t* beta,
                        int64_t n, int64_t r0, int64_t r1, double thresh, int64_t* rowptr,
                        int64_t* colind, double* nzval) {
+  return op_hbuild_rows_gen(h, alpha, beta, n, r0, r1, thresh, 0, rowptr, colind, nzval);
+}
+/* pair_rule != 0: the CSR the pair-based generators produce (residue_arrays.hpp,
+ * dynamic_bit_masking.hpp -> build_csr_from_pairs, connection_build_utils.hpp:125-249): same
+ * connected pairs and matrix elements, but the diagonal is always stored (:181-192), an
+ * off-diagonal element is dropped only when |h| < thresh (:166,199) and determinants with an
+ * empty alpha string are not skipped. */
+int64_t op_hbuild_rows_gen(const op_ham* h, const uint64_t* alpha, const uint64_t* beta,
+                           int64_t n, int64_t r0, int64_t r1, double thresh, int pair_rule,
+                           int64_t* rowptr, int64_t* colind, double* nzval) {
   /* run-length encode alpha strings (sd_operations.hpp:449-468) */
   int64_t nrun = 0;
   int64_t* run_st = (int64_t*)malloc((n + 1) * 8);
@@ -245,10 +255,10 @@ int64_t op_hbuild_rows(const op_ham* h, const uint64_t* alpha, const uint64_t* b
     const uint64_t ai = alpha[i], bi = beta[i];
     int64_t c = 0;
     int64_t w = fill ? rowptr[i - r0] : 0;
-    if (ai) {
+    if (ai || pair_rule) {
       for (int64_t r = 0; r < nrun; ++r) {
         const uint64_t ar = alpha[run_st[r]];
-        if (!ar) continue;
+        if (!ar && !pair_rule) continue;
         const int ca = popc(ai ^ ar);
         if (ca > 4) continue;
         for (int64_t j = run_st[r]; j < run_st[r + 1]; ++j) {
@@ -257,7 +267,9 @@ int64_t op_hbuild_rows(const op_ham* h, const uint64_t* alpha, const uint64_t* b
           double v;
           if (i <= j) v = matel(h, ai, bi, alpha[j], beta[j]);
           else v = matel(h, alpha[j], beta[j], ai, bi);
-          if (thresh > 0.0) {
+          if (pair_rule) {
+            if (i != j && fabs(v) < thresh) continue;
+          } else if (thresh > 0.0) {
             if (!(fabs(v) > thresh)) continue;
           }
           if (fill) { colind[w] = j; nzval[w] = v; ++w; }

@@ -42,6 +42,10 @@ int64_t op_hbuild(const op_ham* h, const uint64_t* alpha, const uint64_t* beta, 
 int64_t op_hbuild_rows(const op_ham* h, const uint64_t* alpha, const uint64_t* beta,
                        int64_t n, int64_t r0, int64_t r1, double thresh, int64_t* rowptr,
                        int64_t* colind, double* nzval);
+/* the same under the pair-based generators' rules (residue_arrays / dynamic_bit_masking) */
+int64_t op_hbuild_rows_gen(const op_ham* h, const uint64_t* alpha, const uint64_t* beta,
+                           int64_t n, int64_t r0, int64_t r1, double thresh, int pair_rule,
+                           int64_t* rowptr, int64_t* colind, double* nzval);
 
 void op_spmv(int64_t n, const int64_t* rowptr, const int64_t* colind, const double* nzval,
              const double* x, double* y);

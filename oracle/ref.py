@@ -112,6 +112,10 @@ class AsciOpts(C.Structure):
         super().__init__(**d)
 
 
+# generator selector of oracle/ref_driver.cxx (HamGen::gen)
+_GEN = {"sdl": 0, "sorted_double_loop": 0, "double_loop": 1, "residue_arrays": 2, "dynamic_bit_masking": 3}
+
+
 def words_per_det(nbits: int) -> int:
     return nbits // 64
 
@@ -232,7 +236,7 @@ class HamGen:
         d = np.ascontiguousarray(dets, dtype=np.uint64)
         k = None if kets is None else np.ascontiguousarray(kets, dtype=np.uint64)
         sec = C.c_double(0.0)
-        h = lib().ref_hbuild(self.h, 1 if generator == "double_loop" else 0, _p(d),
+        h = lib().ref_hbuild(self.h, _GEN[generator], _p(d),
                              d.size // w, _p(k), 0 if k is None else k.size // w,
                              thresh, C.byref(sec))
         if not h:
@@ -252,7 +256,7 @@ class HamGen:
             o1, o2, t1, t2, t3 = mk1(), mk1(), mk2(), mk2(), mk2()
         else:
             o1, o2, t1, t2, t3 = mk1(), None, mk2(), None, None
-        rc = lib().ref_form_rdms(self.h, 1 if generator == "double_loop" else 0, _p(d), c.size, _p(c),
+        rc = lib().ref_form_rdms(self.h, _GEN[generator], _p(d), c.size, _p(c),
                                  1 if spin_dep else 0, _p(o1), _p(o2), _p(t1), _p(t2), _p(t3))
         if rc:
             raise RuntimeError(lib().ref_last_error().decode())
@@ -270,7 +274,7 @@ class HamGen:
         s1 = np.zeros(n)
         S2 = np.zeros(n * n) if s2 else None
         MI = np.zeros(n * n) if mi else None
-        rc = lib().ref_form_entropies(self.h, 1 if generator == "double_loop" else 0, _p(d), c.size, _p(c),
+        rc = lib().ref_form_entropies(self.h, _GEN[generator], _p(d), c.size, _p(c),
                                       _p(s1), _p(S2), _p(MI))
         if rc:
             raise RuntimeError(lib().ref_last_error().decode())

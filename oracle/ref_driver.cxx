@@ -23,6 +23,8 @@
 #include <macis/asci/refine.hpp>
 #include <macis/csr_hamiltonian.hpp>
 #include <macis/hamiltonian_generator/double_loop.hpp>
+#include <macis/hamiltonian_generator/dynamic_bit_masking.hpp>
+#include <macis/hamiltonian_generator/residue_arrays.hpp>
 #include <macis/hamiltonian_generator/sorted_double_loop.hpp>
 #include <macis/mcscf/cas.hpp>
 #include <macis/sd_operations.hpp>
@@ -93,6 +95,8 @@ struct HamGen : HamGenBase {
   using wfn = macis::wfn_t<N>;
   std::unique_ptr<macis::SortedDoubleLoopHamiltonianGenerator<wfn>> sdl;
   std::unique_ptr<macis::DoubleLoopHamiltonianGenerator<wfn>> dl;
+  std::unique_ptr<macis::ResidueArrayHamiltonianGenerator<wfn>> ra;
+  std::unique_ptr<macis::DynamicBitMaskHamiltonianGenerator<wfn>> dbm;
   HamGen(int n, const double* t, const double* v) {
     nbits = N;
     norb = n;
@@ -102,9 +106,13 @@ struct HamGen : HamGenBase {
     macis::rank4_span<double> Vs(V.data(), n, n, n, n);
     sdl = std::make_unique<macis::SortedDoubleLoopHamiltonianGenerator<wfn>>(Ts, Vs);
     dl = std::make_unique<macis::DoubleLoopHamiltonianGenerator<wfn>>(Ts, Vs);
+    ra = std::make_unique<macis::ResidueArrayHamiltonianGenerator<wfn>>(Ts, Vs);
+    dbm = std::make_unique<macis::DynamicBitMaskHamiltonianGenerator<wfn>>(Ts, Vs);
   }
   macis::HamiltonianGenerator<wfn>& gen(int which) {
     if (which == 1) return *dl;
+    if (which == 2) return *ra;   // hamiltonian_build_algorithm = "residue_arrays"
+    if (which == 3) return *dbm;  // hamiltonian_build_algorithm = "dynamic_bit_masking"
     return *sdl;
   }
 };

@@ -61,6 +61,7 @@ def lib():
     L.b2ci_dets_download.argtypes = [vp, vp, vp, i32]
     L.b2ci_dets_free.argtypes = [vp, vp]
     L.b2ci_hbuild_csr.argtypes = [vp, vp, i64, i64, dbl, pp]
+    L.b2ci_set_hamiltonian_generator.argtypes = [vp, i32]
     L.b2ci_hbuild_csr_patched.argtypes = [vp, vp, vp, vp, dbl, dbl, pp, pi64]
     L.b2ci_csr_upload.argtypes = [vp, i64, i64, vp, vp, vp, pp]
     L.b2ci_csr_info.argtypes = [vp, pi64, pi64, pi64, pi64]

@@ -302,6 +302,13 @@ int b2ci_hbuild_csr(b2ci_ctx* ctx, const b2ci_dets* dets, int64_t row_begin, int
   return 0;
   B2_CATCH
 }
+int b2ci_set_hamiltonian_generator(b2ci_ctx* ctx, int generator) {
+  B2_TRY_CTX(ctx)
+  if (generator < 0 || generator > 2) throw Error("b2ci_set_hamiltonian_generator: unknown generator");
+  ctx->generator = generator;
+  return 0;
+  B2_CATCH
+}
 int b2ci_hbuild_csr_patched(b2ci_ctx* ctx, const b2ci_dets* old_dets, const b2ci_csr* old_H,
                             const b2ci_dets* new_dets, double h_thresh, double min_overlap,
                             b2ci_csr** out, int64_t* n_kept) {

@@ -93,6 +93,7 @@ struct b2ci_ctx {
   b2ci::IntsView ints{};
   std::vector<double> ints_host;  // same layout, host copy (host-side evaluation / ASCI driver)
   int64_t launches = 0;
+  int generator = 0;  // B2CI_GEN_*: pattern / threshold rules of the H build (b2ci_set_hamiltonian_generator)
   std::map<std::string, double> timers;
   // multi-GPU
   void* nccl_comm = nullptr;

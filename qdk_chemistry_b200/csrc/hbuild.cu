@@ -123,6 +123,10 @@ struct RowArgs {
   const int32_t* bra_grp = nullptr;  // beta group of the ket list holding the bra's beta string, or -1
   const int32_t* rowmap = nullptr;   // index of a bra / ket determinant in the common (global) list:
   const int32_t* colmap = nullptr;   //   decides the (bra, ket) roles and is the column written
+  // threshold rule of the pair-based generators (residue_arrays, dynamic_bit_masking:
+  // connection_build_utils.hpp:163-199): the diagonal is always kept, an off-diagonal element is
+  // dropped only when |h| < thr, and alpha-empty determinants are ordinary determinants
+  int pair_rule = 0;
 };
 
 // Evaluate up to 32 queued column indices (one per lane) and count / emit the survivors.
@@ -141,7 +145,7 @@ __device__ __forceinline__ void process_batch(const RowArgs& A, int64_t i, uint6
       if (BLK && A.colmap) j = A.colmap[j];
       // the reference computes the upper triangle with bra = lower index and mirrors it
       v = (i <= int64_t(j)) ? matel(A.I, ai, bi, aj, bj) : matel(A.I, aj, bj, ai, bi);
-      if (EVAL) keep = fabs(v) > A.thr;
+      if (EVAL) keep = A.pair_rule ? (i == int64_t(j) || !(fabs(v) < A.thr)) : fabs(v) > A.thr;
     }
   }
   const unsigned km = __ballot_sync(0xffffffffu, keep);
@@ -196,7 +200,7 @@ k_rows(const RowArgs A) {
       __syncwarp();
     }
   };
-  if (ai != 0) {
+  if (ai != 0 || A.pair_rule) {
     const int32_t g = BLK ? A.bra_grp[il] : A.bgrp_of[il];
     int64_t bpos = g >= 0 ? A.bgrp_start[g] : 0;
     const int64_t bend = g >= 0 ? A.bgrp_start[g + 1] : 0;
@@ -210,7 +214,7 @@ k_rows(const RowArgs A) {
         bool hit = false;
         if (in) {
           const uint64_t aj = A.alpha[j];
-          hit = aj != 0 && __popcll(ai ^ aj) == 4;
+          hit = (aj != 0 || A.pair_rule) && __popcll(ai ^ aj) == 4;
         }
         const int nin = __popc(__ballot_sync(0xffffffffu, in));  // a prefix: members ascend
         push(hit, j);
@@ -889,7 +893,7 @@ __global__ void k_generate_fci(int norb, int na, int nb, int64_t nalpha_str, int
 template <bool FILL>
 __global__ void __launch_bounds__(256)
 k_string_adjacency2(const uint64_t* __restrict__ sa, int32_t na, const uint64_t* __restrict__ sb, int32_t nb,
-                    int maxd, int32_t* __restrict__ cnt, const int64_t* __restrict__ adj_ptr,
+                    int maxd, int skip_zero, int32_t* __restrict__ cnt, const int64_t* __restrict__ adj_ptr,
                     uint32_t* __restrict__ adj) {
   const int lane = threadIdx.x & 31;
   const int64_t r = (int64_t(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
@@ -897,7 +901,7 @@ k_string_adjacency2(const uint64_t* __restrict__ sa, int32_t na, const uint64_t*
   const uint64_t a = sa[r];
   int64_t out = FILL ? adj_ptr[r] : 0;
   int32_t c = 0;
-  if (a != 0) {
+  if (!(skip_zero && a == 0)) {
     for (int32_t r0 = 0; r0 < nb; r0 += 32) {
       const int32_t r2 = r0 + lane;
       bool ok = false;
@@ -905,7 +909,7 @@ k_string_adjacency2(const uint64_t* __restrict__ sa, int32_t na, const uint64_t*
       if (r2 < nb) {
         const uint64_t a2 = sb[r2];
         d = __popcll(a ^ a2);
-        ok = a2 != 0 && d <= maxd;
+        ok = !(skip_zero && a2 == 0) && d <= maxd;
       }
       const unsigned m = __ballot_sync(0xffffffffu, ok);
       if (FILL && ok) adj[out + __popc(m & ((1u << lane) - 1u))] = (uint32_t(r2) << 2) | uint32_t(d >> 1);
@@ -1180,7 +1184,9 @@ void hbuild_csr(b2ci_ctx* ctx, const b2ci_dets* dets, int64_t row_begin, int64_t
     B2_CUDA(cudaStreamSynchronize(st));
     nruns = *reinterpret_cast<const int32_t*>(pin);
     const int hbad = *reinterpret_cast<const int*>(pin + 1);
-    rect = hbad == 0 && nruns > 0 && !getenv("B2CI_HBUILD_FORCE_SCAN");
+    // the product enumeration implements the sorted_double_loop rules; lists built under the
+    // pair-based generators' rules take the row scan
+    rect = hbad == 0 && nruns > 0 && !getenv("B2CI_HBUILD_FORCE_SCAN") && ctx->generator == 0;
     mark("runs + shape test (sync A)");
   }
   // run adjacency (count, scan, fill): distance <= 2 for the scan path
@@ -1189,7 +1195,8 @@ void hbuild_csr(b2ci_ctx* ctx, const b2ci_dets* dets, int64_t row_begin, int64_t
     DevBuf<int32_t> acnt(nruns);
     adj_ptr.alloc(nruns + 1);
     const unsigned ga = unsigned((int64_t(nruns) * 32 + 255) / 256);
-    k_string_adjacency<false><<<ga, 256, 0, st>>>(run_alpha, nruns, maxd, 1, acnt, nullptr, nullptr, nullptr);
+    const int skipz = ctx->generator == 0 ? 1 : 0;
+    k_string_adjacency<false><<<ga, 256, 0, st>>>(run_alpha, nruns, maxd, skipz, acnt, nullptr, nullptr, nullptr);
     ctx->launches++;
     B2_CHECK_LAUNCH();
     exclusive_scan_i32_to_i64(ctx, acnt, adj_ptr, nruns);
@@ -1197,7 +1204,7 @@ void hbuild_csr(b2ci_ctx* ctx, const b2ci_dets* dets, int64_t row_begin, int64_t
     B2_CUDA(cudaMemcpyAsync(&nadj, adj_ptr.p + nruns, 8, cudaMemcpyDeviceToHost, st));
     B2_CUDA(cudaStreamSynchronize(st));
     adj.alloc(nadj > 0 ? nadj : 1);
-    k_string_adjacency<true><<<ga, 256, 0, st>>>(run_alpha, nruns, maxd, 1, nullptr, nullptr, adj_ptr, adj);
+    k_string_adjacency<true><<<ga, 256, 0, st>>>(run_alpha, nruns, maxd, skipz, nullptr, nullptr, adj_ptr, adj);
     ctx->launches++;
     B2_CHECK_LAUNCH();
   };
@@ -1493,6 +1500,7 @@ void hbuild_csr(b2ci_ctx* ctx, const b2ci_dets* dets, int64_t row_begin, int64_t
   A.rowptr = nullptr;
   A.colind = nullptr;
   A.nzval = nullptr;
+  A.pair_rule = ctx->generator != 0;
   const unsigned grid = unsigned((nrows + ROW_WARPS - 1) / ROW_WARPS);
   // Count pass = the scan alone (structural connections, no matrix element); the fill pass
   // evaluates every element ONCE, writes the survivors compacted inside the row's structural
@@ -1621,11 +1629,12 @@ void build_block_general(b2ci_ctx* ctx, const DetView& bra, const DetView& ket, 
   const int32_t nrk = run_tables(ctx, ket, ket_run_of, ket_run_start, ket_run_alpha);
   // bra-run x ket-run adjacency, alpha distance <= 2
   DevBuf<uint32_t> adj;
+  const int skipz = ctx->generator == 0 ? 1 : 0;
   {
     DevBuf<int32_t> acnt(nrb);
     adj_ptr.alloc(size_t(nrb) + 1);
     const unsigned ga = unsigned((int64_t(nrb) * 32 + 255) / 256);
-    k_string_adjacency2<false><<<ga, 256, 0, st>>>(bra_run_alpha, nrb, ket_run_alpha, nrk, 2, acnt, nullptr, nullptr);
+    k_string_adjacency2<false><<<ga, 256, 0, st>>>(bra_run_alpha, nrb, ket_run_alpha, nrk, 2, skipz, acnt, nullptr, nullptr);
     ctx->launches++;
     B2_CHECK_LAUNCH();
     exclusive_scan_i32_to_i64(ctx, acnt, adj_ptr, nrb);
@@ -1633,7 +1642,7 @@ void build_block_general(b2ci_ctx* ctx, const DetView& bra, const DetView& ket, 
     B2_CUDA(cudaMemcpyAsync(&nadj, adj_ptr.p + nrb, 8, cudaMemcpyDeviceToHost, st));
     B2_CUDA(cudaStreamSynchronize(st));
     adj.alloc(nadj > 0 ? nadj : 1);
-    k_string_adjacency2<true><<<ga, 256, 0, st>>>(bra_run_alpha, nrb, ket_run_alpha, nrk, 2, nullptr, adj_ptr, adj);
+    k_string_adjacency2<true><<<ga, 256, 0, st>>>(bra_run_alpha, nrb, ket_run_alpha, nrk, 2, skipz, nullptr, adj_ptr, adj);
     ctx->launches++;
     B2_CHECK_LAUNCH();
   }
@@ -1684,6 +1693,7 @@ void build_block_general(b2ci_ctx* ctx, const DetView& bra, const DetView& ket, 
   A.bra_grp = bra_grp;
   A.rowmap = bra.gmap;
   A.colmap = ket.gmap;
+  A.pair_rule = ctx->generator != 0;
   const unsigned grid = unsigned((nrows + ROW_WARPS - 1) / ROW_WARPS);
   int64_t nslots = 0;
   DevBuf<int64_t> slot_ptr(nrows + 1);

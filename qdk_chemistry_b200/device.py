@@ -110,6 +110,12 @@ class Context:
         check(lib().b2ci_hbuild_csr(self.h, dets.h, r0, r1, h_thresh, C.byref(h)))
         return CsrMatrix(self, h)
 
+    GENERATORS = {"": 0, "sorted_double_loop": 0, "residue_arrays": 1, "dynamic_bit_masking": 2}
+
+    def set_hamiltonian_generator(self, name: str) -> None:
+        """QDK's hamiltonian_build_algorithm (macis_asci.hpp:174-179): pattern / threshold rules."""
+        check(lib().b2ci_set_hamiltonian_generator(self.h, self.GENERATORS[name]))
+
     def hbuild_patched(self, old_dets: "DetList", old_H: "CsrMatrix", new_dets: "DetList", h_thresh: float,
                        min_overlap: float = 0.3):
         """build_patched_operator (incremental_h_build.hpp:219-356) merged into one CSR of

@@ -85,6 +85,7 @@ struct AsciSettings {  // macis::ASCISettings fields that reach the path
       refine_energy_tol, core_selection_threshold, min_warm_start_overlap, grow_ci_residual_tolerance,
       taper_grow_factor, min_patch_overlap;
   bool just_singles, warm_start_davidson, fixed_core;
+  int generator;  // B2CI_GEN_*: hamiltonian_build_algorithm
 };
 AsciSettings get_asci_settings(const data::Settings& s) {  // macis_base.cpp:47-134
   AsciSettings a;
@@ -124,11 +125,12 @@ AsciSettings get_asci_settings(const data::Settings& s) {  // macis_base.cpp:47-
                         a.core_selection_threshold > 1.0))
     throw std::invalid_argument("core_selection_threshold must be in [epsilon, 1.0], got " +
                                 std::to_string(a.core_selection_threshold));
+  // macis_asci.cpp:92-118: anything that is not one of the two pair-based generators is the
+  // sorted double loop. On the device the three share one enumeration; what the choice selects is
+  // the generator's pattern rules (b2ci_set_hamiltonian_generator).
   const std::string algo = s.get<std::string>("hamiltonian_build_algorithm");
-  if (!(algo.empty() || algo == "sorted_double_loop"))
-    throw std::invalid_argument("hamiltonian_build_algorithm '" + algo +
-                                "' is not available in this build; the B200 path implements the "
-                                "sorted_double_loop pattern and threshold semantics");
+  a.generator = algo == "residue_arrays" ? B2CI_GEN_RESIDUE_ARRAYS
+                : algo == "dynamic_bit_masking" ? B2CI_GEN_DYNAMIC_BIT_MASKING : B2CI_GEN_SORTED_DOUBLE_LOOP;
   return a;
 }
 
@@ -247,13 +249,17 @@ class CiSession {
     // the list is handed over: freed there, or adopted by the cache
     return selected_ci_diag(d, int64_t(dets.size()), matel_tol, max_m, res_tol, X, use_cache, min_patch_overlap, true);
   }
+  void set_generator(int g) { B2(b2ci_set_hamiltonian_generator(ctx_, g)); }
   void drop_cache() {  // CachedHamiltonianState::clear
     if (cache_H_) b2ci_csr_free(ctx_, cache_H_);
     if (cache_dets_) b2ci_dets_free(ctx_, cache_dets_);
     cache_H_ = nullptr;
     cache_dets_ = nullptr;
   }
-  ~CiSession() { drop_cache(); }
+  ~CiSession() {
+    drop_cache();
+    b2ci_set_hamiltonian_generator(ctx_, B2CI_GEN_SORTED_DOUBLE_LOOP);  // the context is shared by all runs
+  }
   // dense branch: full CSR (index pattern as the reference's int32 build) -> lowest eigenpair
   double dense_diag(const b2ci_dets* dets, int64_t n, double matel_tol, std::vector<double>& X) {
     X.assign(size_t(n), 0.0);
@@ -693,8 +699,11 @@ B200AsciSettings::B200AsciSettings() {  // MacisAsciSettings, macis_asci.hpp:34-
   set_default<double>("grow_ci_residual_tolerance", 0.0, "CI residual tolerance during grow phase (0 = use refine tolerance)");
   set_default<double>("taper_grow_factor", 0.0, "Growth factor for final expansion near ntdets_max (0 = disabled)");
   set_default<std::string>("hamiltonian_build_algorithm", std::string(""),
-                           "Algorithm for diagonal Hamiltonian construction: '' or 'sorted_double_loop'");
-  set_default<int64_t>("dynamic_bit_masking_num_masks", 0);
+                           "Algorithm for diagonal Hamiltonian construction: '' or 'sorted_double_loop' (default), "
+                           "'residue_arrays', 'dynamic_bit_masking'");
+  // a tuning knob of the reference's CPU pair enumeration: accepted, no effect on the device enumeration
+  set_default<int64_t>("dynamic_bit_masking_num_masks", 0,
+                       "Number of bit masks for dynamic_bit_masking generator (0 = use generator default)");
 }
 
 std::string MultiConfigurationCalculator::hash(std::shared_ptr<data::Hamiltonian> h, unsigned na, unsigned nb) const {
@@ -738,6 +747,12 @@ McResult B200Asci::_run_impl(std::shared_ptr<data::Hamiltonian> h, unsigned na, 
   const auto t0 = std::chrono::steady_clock::now();
   CiSession S(*h);
   const int norb = S.norb();
+  // residue arrays hold O(n_e^2) residues per determinant: beyond 60 electrons the reference falls
+  // back to the sorted double loop (macis_asci.cpp:32,96-108) and so do its pattern rules
+  int generator = a.generator;
+  if (generator == B2CI_GEN_RESIDUE_ARRAYS && na + nb > 60) generator = B2CI_GEN_SORTED_DOUBLE_LOOP;
+  S.set_generator(generator);
+  g_stats["hamiltonian_generator"] = double(generator);
   std::vector<Det> dets;
   std::vector<double> C;
   double E = 0.;

@@ -49,3 +49,27 @@ def check_csr_against_golden(meta, arrays, key, rp, ci, nz, bit_exact_values=Tru
         got = np.asarray(nz)[::step]
         assert np.allclose(got, ref, rtol=rtol, atol=0.0)
         assert abs(float(np.sum(nz)) - rec["nzval_sum"]) <= 1e-9 * max(1.0, rec["nzval_abs_sum"])
+
+
+def generator_case(tag):
+    """(ActiveSpace, alpha, beta) of a tests/golden/generators_meta.json case (make_golden_generators.py)."""
+    from oracle import port
+    from qdk_chemistry_b200 import workloads as W
+    if tag == "alpha_empty_8o":
+        sp = W.config("small_cas8")
+        bs = np.array([sum(1 << i for i in c) for c in itertools.combinations(range(8), 3)], dtype=np.uint64)
+        return sp, np.zeros(len(bs), dtype=np.uint64), bs
+    name, n, seed = {"hubbard_4x2_s600": ("hubbard_4x2", 600, 5), "small_cas8_s900": ("small_cas8", 900, 6),
+                     "n2_cas10_s2500": ("n2_cas10", 2500, 7)}[tag]
+    sp = W.config(name)
+    a, b = port.generate_hilbert_space(sp.norb, sp.nalpha, sp.nbeta)
+    pick = np.sort(np.random.default_rng(seed).choice(len(a), size=n, replace=False))
+    o = port.spin_sort_order(a[pick], b[pick])
+    return sp, a[pick][o], b[pick][o]
+
+
+def check_generator_golden(rec, rp, ci, nz):
+    assert int(rp[-1]) == rec["nnz"]
+    assert sha(np.asarray(rp, dtype=np.int64)) == rec["rowptr_sha"]
+    assert sha(np.asarray(ci, dtype=np.int64)) == rec["colind_sha"]
+    assert sha(np.asarray(nz, dtype=np.float64)) == rec["nzval_sha"]

@@ -266,3 +266,17 @@ def test_asci_refine_uses_patched_builds_with_identical_results(water, monkeypat
     E3, _ = alg.create(MC, "macis_asci", ntdets_max=3000, core_selection_strategy="fixed", max_refine_iter=2,
                        refine_energy_tol=1e-3, min_patch_overlap=0.05).run(_ham(water), 5, 5)
     assert alg.last_run_stats()["h_build_patched"] >= 1
+
+
+@pytest.mark.parametrize("algo", ["residue_arrays", "dynamic_bit_masking"])
+def test_asci_hamiltonian_build_algorithm_setting(water, golden_meta, algo):
+    # macis_asci.cpp:92-118: the pair-based generators give the same matrix elements; on water their
+    # pattern differs from the sorted double loop at most by stored zeros, so the known answers hold
+    ka = golden_meta["known_answers"]
+    E, w = alg.create(MC, "macis_asci", ntdets_max=10000, core_selection_strategy="fixed", max_refine_iter=0,
+                      ci_residual_tolerance=1e-8, hamiltonian_build_algorithm=algo).run(_ham(water), 5, 5)
+    assert w.size() == 10000 and abs(E - water.core_energy - ka["water_asci_grow"]) < 1e-8
+    assert alg.last_run_stats()["hamiltonian_generator"] == {"residue_arrays": 1, "dynamic_bit_masking": 2}[algo]
+    # the selection does not leak into the next run on the shared context
+    alg.create(MC, "macis_asci", ntdets_max=500, max_refine_iter=0).run(_ham(water), 5, 5)
+    assert alg.last_run_stats()["hamiltonian_generator"] == 0

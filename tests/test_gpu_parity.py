@@ -389,3 +389,62 @@ def test_patched_build_overlap_gate_and_errors(ctx):
     assert np.array_equal(rp, frp) and np.array_equal(ci, fci) and np.array_equal(nz, fnz)
     with pytest.raises(device.B2ciError, match="full square"):
         ctx.hbuild_patched(d_old, ctx.hbuild(d_old, EPS, (10, 60)), d_new, EPS)
+
+
+# ---- hamiltonian_build_algorithm: the pair-based generators' pattern rules ---------------------------
+@pytest.mark.parametrize("tag", ["hubbard_4x2_s600", "small_cas8_s900", "n2_cas10_s2500", "alpha_empty_8o"])
+@pytest.mark.parametrize("gen", ["residue_arrays", "dynamic_bit_masking", "sorted_double_loop"])
+def test_generator_rules_match_reference_golden(ctx, tag, gen):
+    """build_csr_from_pairs semantics (diagonal always stored, |h| < thr dropped, alpha-empty
+    determinants kept) against fingerprints of the compiled reference's generators."""
+    import json
+    from helpers import check_generator_golden, generator_case
+    with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "generators_meta.json")) as fh:
+        meta = json.load(fh)
+    sp, a, b = generator_case(tag)
+    ctx.upload_integrals(sp.norb, sp.T, sp.V)
+    ctx.set_hamiltonian_generator(gen)
+    try:
+        d = ctx.upload_dets(port.pack(a, b), 1)
+        for thr_tag in ("eps", "zero", "1e-2"):
+            m = meta[f"{tag}.{thr_tag}"]
+            H = ctx.hbuild(d, m["thr"])
+            check_generator_golden(m[gen], *H.download())
+            # row block and patched build follow the same rules
+            n = len(a)
+            r0, r1 = n // 3, min(n, n // 3 + 40)
+            rpb, cib, nzb = ctx.hbuild(d, m["thr"], (r0, r1)).download()
+            rp, ci, nz = H.download()
+            assert np.array_equal(rpb, rp[r0:r1 + 1] - rp[r0]) and np.array_equal(cib, ci[rp[r0]:rp[r1]])
+            # (the patch needs spin-sorted lists; the alpha-empty fixture is in combination order)
+            o = port.spin_sort_order(a, b)
+            sa, sb = a[o], b[o]
+            keep = np.sort(np.random.default_rng(1).choice(n, size=(3 * n) // 4, replace=False))
+            d_old = ctx.upload_dets(port.pack(sa[keep], sb[keep]), 1)
+            d_new = ctx.upload_dets(port.pack(sa, sb), 1)
+            Hp, nk = ctx.hbuild_patched(d_old, ctx.hbuild(d_old, m["thr"]), d_new, m["thr"], 0.3)
+            assert nk == len(keep)
+            prp, pci, pnz = Hp.download()
+            if np.array_equal(o, np.arange(n)):
+                check_generator_golden(m[gen], prp, pci, pnz)
+            orp, oci, onz = port.Ham(sp.norb, sp.T, sp.V).hbuild(sa, sb, m["thr"], generator=gen)
+            assert np.array_equal(prp, orp) and np.array_equal(pci, oci) and np.array_equal(pnz, onz)
+    finally:
+        ctx.set_hamiltonian_generator("")
+
+
+def test_fci_list_under_pair_rules_takes_the_scan_path(ctx):
+    sp = W.config("hubbard_3x2")
+    a, b = port.generate_hilbert_space(sp.norb, sp.nalpha, sp.nbeta)
+    ctx.upload_integrals(sp.norb, sp.T, sp.V)
+    ctx.set_hamiltonian_generator("residue_arrays")
+    try:
+        H = ctx.hbuild(ctx.upload_dets(port.pack(a, b), 1), EPS)
+        assert ctx.timer_ms("h_build.rectangular") == 0.0
+        rp, ci, nz = H.download()
+    finally:
+        ctx.set_hamiltonian_generator("")
+    orp, oci, onz = port.Ham(sp.norb, sp.T, sp.V).hbuild(a, b, EPS, generator="residue_arrays")
+    assert np.array_equal(rp, orp) and np.array_equal(ci, oci) and np.array_equal(nz, onz)
+    srp, _, _ = port.Ham(sp.norb, sp.T, sp.V).hbuild(a, b, EPS)
+    assert rp[-1] >= srp[-1]

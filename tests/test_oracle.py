@@ -288,3 +288,22 @@ def test_wide_keys_search_and_run_match_compiled_reference():
     assert (sa >> np.uint64(32)).any() and (sb >> np.uint64(32)).any()   # both words are in play
     E, a, b, X = port.asci_run(h, sp.nalpha, sp.nbeta, refine=True, **m["run_opts"])
     assert len(a) == m["run_n"] and abs(E - m["run_E"]) < 1e-8
+
+
+# ---- hamiltonian_build_algorithm = residue_arrays / dynamic_bit_masking (pair-based generators)
+def _generators_meta():
+    import json
+    with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "generators_meta.json")) as fh:
+        return json.load(fh)
+
+
+@pytest.mark.parametrize("tag", ["hubbard_4x2_s600", "small_cas8_s900", "alpha_empty_8o"])
+def test_port_follows_each_generators_rules(tag):
+    from helpers import check_generator_golden, generator_case
+    meta = _generators_meta()
+    sp, a, b = generator_case(tag)
+    h = port.Ham(sp.norb, sp.T, sp.V)
+    for thr_tag in ("eps", "zero", "1e-2"):
+        m = meta[f"{tag}.{thr_tag}"]
+        for g in ("sorted_double_loop", "residue_arrays", "dynamic_bit_masking"):
+            check_generator_golden(m[g], *h.hbuild(a, b, m["thr"], generator=g))
