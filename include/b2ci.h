@@ -51,6 +51,12 @@ int b2ci_comm_rank(const b2ci_ctx* ctx, int* rank, int* nranks);
 /* ---- integrals: HamiltonianGeneratorBase ctor + generate_integral_intermediates_
  * (external/macis/src/macis/hamiltonian_generator/base.ipp:27-77). Host pointers. */
 int b2ci_integrals_upload(b2ci_ctx* ctx, int norb, const double* T, const double* V);
+/* Orbital rotation of the uploaded integrals, T <- C^T T C and the four-index analogue for V, followed
+ * by the intermediates again: two_index_transform / four_index_transform
+ * (external/macis/src/macis/transform.cxx:22-96) + generate_integral_intermediates as asci_grow's
+ * natural-orbital step uses them (external/macis/include/macis/asci/grow.hpp:163-215). C: HOST, n x n
+ * column-major, columns = new orbitals. T_out (n^2) / V_out (n^4): HOST, may be NULL. */
+int b2ci_integrals_rotate(b2ci_ctx* ctx, const double* C, double* T_out, double* V_out);
 /* debug/parity: copy G_red, V_red (n^3), G2_red, V2_red (n^2) back to the host */
 int b2ci_integrals_download(b2ci_ctx* ctx, double* G_red, double* V_red, double* G2_red,
                             double* V2_red);

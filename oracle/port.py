@@ -133,6 +133,24 @@ class Ham:
             _lib.op_ham_destroy(self.h)
             self.h = None
 
+    def rotate(self, Cm: np.ndarray) -> None:
+        """two_index_transform + four_index_transform + generate_integral_intermediates
+        (src/macis/transform.cxx:22-96; asci/grow.hpp:196-215): T <- C^T T C, V likewise on all four
+        indices, in place like the reference (which rotates the generator's own integrals)."""
+        n = self.norb
+        Cm = np.asarray(Cm, dtype=np.float64).reshape(n, n, order="F")
+        T = self.T.reshape(n, n, order="F")
+        V = self.V.reshape(n, n, n, n, order="F")
+        T = Cm.T @ T @ Cm
+        V = np.einsum("ip,ijkl->pjkl", Cm, V, optimize=True)
+        V = np.einsum("jq,pjkl->pqkl", Cm, V, optimize=True)
+        V = np.einsum("kr,pqkl->pqrl", Cm, V, optimize=True)
+        V = np.einsum("ls,pqrl->pqrs", Cm, V, optimize=True)
+        lib().op_ham_destroy(self.h)
+        self.T = np.ascontiguousarray(T.reshape(-1, order="F"))
+        self.V = np.ascontiguousarray(V.reshape(-1, order="F"))
+        self.h = lib().op_ham_create(n, _p(self.T), _p(self.V))
+
     def intermediates(self):
         n = self.norb
         G, Vr, G2, V2 = np.empty(n ** 3), np.empty(n ** 3), np.empty(n * n), np.empty(n * n)
@@ -281,7 +299,8 @@ ASCI_DEFAULTS = dict(
     grow_factor=8.0, min_grow_factor=1.01, growth_backoff_rate=0.5, growth_recovery_rate=1.1,
     max_refine_iter=6, refine_energy_tol=1e-6, warm_start_davidson=True,
     min_warm_start_overlap=0.5, grow_ci_residual_tolerance=0.0, taper_grow_factor=0.0,
-    ci_res_tol=1e-8, ci_max_subspace=200, ci_matel_tol=float(np.finfo(np.float64).eps))
+    ci_res_tol=1e-8, ci_max_subspace=200, ci_matel_tol=float(np.finfo(np.float64).eps),
+    grow_with_rot=False, rot_size_start=1000)
 
 
 def _selected_ci_diag(ham: Ham, a, b, s, c0, res_tol=None):
@@ -329,7 +348,8 @@ def asci_iter(ham: Ham, s: dict, ndets_max: int, E0: float, a, b, X, res_tol=Non
 
 
 def asci_grow(ham: Ham, s: dict, E0: float, a, b, X):
-    """include/macis/asci/grow.hpp:45-268 (no orbital rotation)."""
+    """include/macis/asci/grow.hpp:45-268. With grow_with_rot the integrals of ``ham`` are rotated
+    in place to natural orbitals after every iteration at or above rot_size_start (:163-258)."""
     a, b, X = _u64(a), _u64(b), np.asarray(X, dtype=np.float64)
     res_tol = s["grow_ci_residual_tolerance"] if s["grow_ci_residual_tolerance"] > 0 else None
     prev = a.size
@@ -351,6 +371,11 @@ def asci_grow(ham: Ham, s: dict, E0: float, a, b, X):
         else:
             gf = min(s["grow_factor"], gf * s["growth_recovery_rate"])
         prev = a.size
+        if s["grow_with_rot"] and a.size >= s["rot_size_start"]:
+            ordm, _ = form_rdms(ham.norb, a, b, X, spin_dep=False, one=True, two=False)
+            _, vec = np.linalg.eigh(-np.asarray(ordm))      # lapack::syev on -ordm: occupations descending
+            ham.rotate(vec)
+            _, X = _selected_ci_diag(ham, a, b, s, None)      # diagonal guess, final tolerances
         E0 = E
     return E0, a, b, X
 

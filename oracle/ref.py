@@ -96,6 +96,7 @@ class AsciOpts(C.Structure):
         ("grow_ci_residual_tolerance", C.c_double), ("taper_grow_factor", C.c_double),
         ("ci_res_tol", C.c_double), ("ci_max_subspace", C.c_int64),
         ("ci_matel_tol", C.c_double),
+        ("grow_with_rot", C.c_int64), ("rot_size_start", C.c_int64),
     ]
 
     def __init__(self, **kw):
@@ -107,7 +108,7 @@ class AsciOpts(C.Structure):
                  warm_start_davidson=1, constraint_level=2, min_warm_start_overlap=0.5,
                  min_patch_overlap=0.3, grow_ci_residual_tolerance=0.0,
                  taper_grow_factor=0.0, ci_res_tol=1e-8, ci_max_subspace=200,
-                 ci_matel_tol=float(np.finfo(np.float64).eps))
+                 ci_matel_tol=float(np.finfo(np.float64).eps), grow_with_rot=0, rot_size_start=1000)
         d.update(kw)
         super().__init__(**d)
 

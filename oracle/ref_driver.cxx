@@ -135,6 +135,8 @@ struct AsciOpts {  // mirrors macis::ASCISettings (determinant_search.hpp:95-199
   double ci_res_tol;
   int64_t ci_max_subspace;
   double ci_matel_tol;
+  // natural-orbital rotation during growth (grow.hpp:163-215); rotates the generator's integrals
+  int64_t grow_with_rot, rot_size_start;
 };
 
 macis::ASCISettings to_asci(const AsciOpts& o) {
@@ -162,6 +164,8 @@ macis::ASCISettings to_asci(const AsciOpts& o) {
   s.min_patch_overlap = o.min_patch_overlap;
   s.grow_ci_residual_tolerance = o.grow_ci_residual_tolerance;
   s.taper_grow_factor = o.taper_grow_factor;
+  s.grow_with_rot = o.grow_with_rot != 0;
+  s.rot_size_start = size_t(o.rot_size_start);
   return s;
 }
 macis::MCSCFSettings to_mcscf(const AsciOpts& o) {

@@ -54,6 +54,7 @@ def lib():
     L.b2ci_comm_init.argtypes = [vp, vp, i32, i32]
     L.b2ci_comm_rank.argtypes = [vp, C.POINTER(i32), C.POINTER(i32)]
     L.b2ci_integrals_upload.argtypes = [vp, i32, vp, vp]
+    L.b2ci_integrals_rotate.argtypes = [vp, vp, vp, vp]
     L.b2ci_integrals_download.argtypes = [vp, vp, vp, vp, vp]
     L.b2ci_dets_upload.argtypes = [vp, vp, i32, i64, pp]
     L.b2ci_dets_generate_fci.argtypes = [vp, i32, i32, i32, pp]

@@ -88,6 +88,7 @@ cudaStream_t& alloc_stream() {
 
 // implemented in the other translation units
 void integrals_upload(b2ci_ctx* ctx, int norb, const double* T, const double* V);
+void integrals_rotate(b2ci_ctx* ctx, const double* C, double* T_out, double* V_out);
 void dets_from_words(b2ci_ctx* ctx, const uint64_t* words_host, int wpd, int64_t n, b2ci_dets* d);
 void dets_to_words(b2ci_ctx* ctx, const b2ci_dets* d, uint64_t* words_host, int wpd);
 void dets_generate_fci(b2ci_ctx* ctx, int norb, int na, int nb, b2ci_dets* d);
@@ -237,6 +238,12 @@ int b2ci_comm_rank(const b2ci_ctx* ctx, int* rank, int* nranks) {
   return 0;
 }
 
+int b2ci_integrals_rotate(b2ci_ctx* ctx, const double* C, double* T_out, double* V_out) {
+  B2_TRY_CTX(ctx)
+  integrals_rotate(ctx, C, T_out, V_out);
+  return 0;
+  B2_CATCH
+}
 int b2ci_integrals_upload(b2ci_ctx* ctx, int norb, const double* T, const double* V) {
   B2_TRY_CTX(ctx)
   integrals_upload(ctx, norb, T, V);

@@ -32,7 +32,53 @@ __global__ void k_transpose_pairs(int n, int n2p, const double* __restrict__ V, 
   const size_t rs = t % n2p, pq = t / n2p;
   Vt[t] = rs < n2 ? V[pq + rs * n2] : 0.0;
 }
+// one quarter of an index transformation: out(.., p, ..) = sum_i C(i, p) in(.., i, ..) on the index of
+// stride `stride` of a column-major tensor with `total` elements and extent n in every index
+// (two_index_transform / four_index_transform, src/macis/transform.cxx:22-96, as n-long dot products)
+__global__ void k_transform_mode(int n, size_t stride, size_t total, const double* __restrict__ Cm,
+                                 const double* __restrict__ in, double* __restrict__ out) {
+  const size_t o = size_t(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (o >= total) return;
+  const size_t lo = o % stride, p = (o / stride) % n, hi = o / (stride * n);
+  const double* src = in + lo + hi * stride * n;
+  double acc = 0.;
+  for (int i = 0; i < n; ++i) acc += Cm[i + p * size_t(n)] * src[size_t(i) * stride];
+  out[o] = acc;
+}
 }  // namespace
+
+// Orbital rotation of the resident integrals: T <- C^T T C, V(pqrs) <- sum C(ip) C(jq) C(kr) C(ls) V(ijkl),
+// then the reduced intermediates again -- the natural-orbital step of asci_grow (asci/grow.hpp:163-215:
+// two_index_transform, four_index_transform, generate_integral_intermediates). C: HOST, n x n column-major
+// (columns = new orbitals). T_out / V_out (HOST, may be NULL) receive the rotated integrals.
+void integrals_rotate(b2ci_ctx* ctx, const double* C, double* T_out, double* V_out) {
+  if (!ctx->ints_dev) throw Error("b2ci_integrals_rotate: integrals not uploaded");
+  if (!C) throw Error("b2ci_integrals_rotate: null rotation");
+  const int norb = ctx->norb;
+  const size_t n = norb, n2 = n * n, n4 = n2 * n2;
+  cudaStream_t st = ctx->stream;
+  DevBuf<double> dC(n2), a(n4), b(n4);
+  B2_CUDA(cudaMemcpyAsync(dC, C, n2 * 8, cudaMemcpyHostToDevice, st));
+  // T: TMP(i,q) = T(i,j) C(j,q); T'(p,q) = C(i,p) TMP(i,q)
+  k_transform_mode<<<unsigned((n2 + 255) / 256), 256, 0, st>>>(norb, n, n2, dC, ctx->ints.T, a);
+  k_transform_mode<<<unsigned((n2 + 255) / 256), 256, 0, st>>>(norb, 1, n2, dC, a, b);
+  std::vector<double> T(n2), V(n4);
+  B2_CUDA(cudaMemcpyAsync(T.data(), b, n2 * 8, cudaMemcpyDeviceToHost, st));
+  // V: the four quarters in the reference's order (first index first)
+  const unsigned g4 = unsigned((n4 + 255) / 256);
+  k_transform_mode<<<g4, 256, 0, st>>>(norb, 1, n4, dC, ctx->ints.V, a);
+  k_transform_mode<<<g4, 256, 0, st>>>(norb, n, n4, dC, a, b);
+  k_transform_mode<<<g4, 256, 0, st>>>(norb, n2, n4, dC, b, a);
+  k_transform_mode<<<g4, 256, 0, st>>>(norb, n2 * n, n4, dC, a, b);
+  ctx->launches += 6;
+  B2_CHECK_LAUNCH();
+  B2_CUDA(cudaMemcpyAsync(V.data(), b, n4 * 8, cudaMemcpyDeviceToHost, st));
+  B2_CUDA(cudaStreamSynchronize(st));
+  void integrals_upload(b2ci_ctx*, int, const double*, const double*);
+  integrals_upload(ctx, norb, T.data(), V.data());
+  if (T_out) memcpy(T_out, T.data(), n2 * 8);
+  if (V_out) memcpy(V_out, V.data(), n4 * 8);
+}
 
 void integrals_upload(b2ci_ctx* ctx, int norb, const double* T, const double* V) {
   if (norb < 1 || norb > 64) throw Error("b2ci_integrals_upload: norb must be in [1, 64]");

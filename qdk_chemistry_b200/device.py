@@ -83,6 +83,15 @@ class Context:
         check(lib().b2ci_integrals_upload(self.h, norb, _p(T), _p(V)))
         self.norb = norb
 
+    def rotate_integrals(self, Cm: np.ndarray):
+        """T <- C^T T C and the four-index analogue for V on the device (transform.cxx:22-96), then
+        the intermediates again. Returns the rotated (T, V) as flat column-major arrays."""
+        n = self.norb
+        Cf = np.ascontiguousarray(np.asarray(Cm, dtype=np.float64).reshape(n, n).T).reshape(-1)  # column-major
+        T, V = np.empty(n * n), np.empty(n ** 4)
+        check(lib().b2ci_integrals_rotate(self.h, _p(Cf), _p(T), _p(V)))
+        return T, V
+
     def download_intermediates(self):
         n = self.norb
         G, Vr, G2, V2 = np.empty(n ** 3), np.empty(n ** 3), np.empty(n * n), np.empty(n * n)

@@ -84,7 +84,8 @@ struct AsciSettings {  // macis::ASCISettings fields that reach the path
   double h_el_tol, rv_prune_tol, grow_factor, min_grow_factor, growth_backoff_rate, growth_recovery_rate,
       refine_energy_tol, core_selection_threshold, min_warm_start_overlap, grow_ci_residual_tolerance,
       taper_grow_factor, min_patch_overlap;
-  bool just_singles, warm_start_davidson, fixed_core;
+  bool just_singles, warm_start_davidson, fixed_core, grow_with_rot;
+  int64_t rot_size_start;
   int generator;  // B2CI_GEN_*: hamiltonian_build_algorithm
 };
 AsciSettings get_asci_settings(const data::Settings& s) {  // macis_base.cpp:47-134
@@ -113,6 +114,8 @@ AsciSettings get_asci_settings(const data::Settings& s) {  // macis_base.cpp:47-
   a.grow_ci_residual_tolerance = s.get<double>("grow_ci_residual_tolerance");
   a.taper_grow_factor = s.get<double>("taper_grow_factor");
   a.min_patch_overlap = s.get<double>("min_patch_overlap");
+  a.grow_with_rot = s.get<bool>("grow_with_rot");
+  a.rot_size_start = s.get<int64_t>("rot_size_start");
   if (a.grow_factor <= 1.0) throw std::runtime_error("grow_factor must be > 1.0, got " + std::to_string(a.grow_factor));
   if (a.min_grow_factor <= 1.0)
     throw std::runtime_error("min_grow_factor must be > 1.0, got " + std::to_string(a.min_grow_factor));
@@ -248,6 +251,21 @@ class CiSession {
     B2(b2ci_dets_upload(ctx_, reinterpret_cast<const uint64_t*>(dets.data()), 2, int64_t(dets.size()), &d));
     // the list is handed over: freed there, or adopted by the cache
     return selected_ci_diag(d, int64_t(dets.size()), matel_tol, max_m, res_tol, X, use_cache, min_patch_overlap, true);
+  }
+  // natural-orbital step of asci_grow (grow.hpp:163-215): spin-traced 1-RDM of the current
+  // wavefunction, eigenvectors of -ordm (occupations descending), integrals rotated on the device
+  void rotate_to_natural_orbitals(const std::vector<Det>& wfn, const std::vector<double>& X) {
+    const size_t n = size_t(norb_);
+    std::vector<double> ordm(n * n, 0.0), none, occ(n);
+    form_rdms(wfn, X, false, ordm, none, none, none, none);
+    for (double& x : ordm) x *= -1.0;
+    if (b2ci_host_sym_eig_lower(int(n), ordm.data(), int(n), occ.data()) != 0) fail("b2ci_host_sym_eig_lower");
+    double on_sum = 0.;
+    for (double o : occ) on_sum -= o;
+    B2(b2ci_integrals_rotate(ctx_, ordm.data(), nullptr, nullptr));
+    drop_cache();  // the rotation invalidates the cached matrix (grow.hpp:218-219)
+    g_stats["natural_orbital_rotations"] += 1.0;
+    g_stats["natural_occupation_sum"] = on_sum;
   }
   void set_generator(int g) { B2(b2ci_set_hamiltonian_generator(ctx_, g)); }
   void drop_cache() {  // CachedHamiltonianState::clear
@@ -541,7 +559,7 @@ double asci_iter(CiSession& S, const AsciSettings& a, const McscfSettings& m, in
 }
 
 double asci_grow(CiSession& S, const AsciSettings& a, const McscfSettings& m, double E0, std::vector<Det>& wfn,
-                 std::vector<double>& X) {  // grow.hpp:45-268 (grow_with_rot is rejected up front)
+                 std::vector<double>& X) {  // grow.hpp:45-268
   McscfSettings gm = m;
   if (a.grow_ci_residual_tolerance > 0) gm.ci_res_tol = a.grow_ci_residual_tolerance;
   size_t prev = wfn.size();
@@ -564,6 +582,15 @@ double asci_grow(CiSession& S, const AsciSettings& a, const McscfSettings& m, do
       gf = std::min(a.grow_factor, gf * a.growth_recovery_rate);
     }
     prev = wfn.size();
+    if (a.grow_with_rot && wfn.size() >= size_t(a.rot_size_start)) {
+      // rotate to natural orbitals and rediagonalise in the rotated basis with a diagonal guess and
+      // the final (not the grow) tolerances (grow.hpp:163-258); the energy carried on is the one
+      // from before the rotation, as in the reference
+      S.rotate_to_natural_orbitals(wfn, X);
+      std::vector<double> X_local;
+      S.selected_ci_diag(wfn, m.ci_matel_tol, m.ci_max_subspace, m.ci_res_tol, X_local);
+      X = std::move(X_local);
+    }
     E0 = E;
   }
   return E0;
@@ -738,9 +765,8 @@ McResult B200Cas::_run_impl(std::shared_ptr<data::Hamiltonian> h, unsigned na, u
 McResult B200Asci::_run_impl(std::shared_ptr<data::Hamiltonian> h, unsigned na, unsigned nb) const {
   if (!h) throw std::invalid_argument("B200Asci: null Hamiltonian");
   check_hamiltonian(*h, "B200Asci", na, nb);
-  if (_settings->get<bool>("grow_with_rot"))
-    throw std::runtime_error("grow_with_rot (natural-orbital rotation of the integrals during growth) is outside "
-                             "the hot path this build covers");
+  if (_settings->get<bool>("grow_with_rot") && runtime().nranks > 1)
+    throw std::runtime_error("grow_with_rot is not available with a communicator in this build");
   const McscfSettings m = get_mcscf_settings(*_settings);
   const AsciSettings a = get_asci_settings(*_settings);
   g_stats.clear();

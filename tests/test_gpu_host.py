@@ -280,3 +280,39 @@ def test_asci_hamiltonian_build_algorithm_setting(water, golden_meta, algo):
     # the selection does not leak into the next run on the shared context
     alg.create(MC, "macis_asci", ntdets_max=500, max_refine_iter=0).run(_ham(water), 5, 5)
     assert alg.last_run_stats()["hamiltonian_generator"] == 0
+
+
+def test_asci_grow_with_rot_matches_reference(water):
+    # natural-orbital rotation during growth (asci/grow.hpp:163-258); golden energies from the
+    # compiled reference (tests/golden/make_golden_rot.py)
+    import json
+    with open(os.path.join(ROOT, "tests", "golden", "rot_meta.json")) as fh:
+        meta = json.load(fh)
+    for tag in ("grow", "refine"):
+        m = meta[tag]
+        E, w = alg.create(MC, "macis_asci", ntdets_max=m["ntdets_max"], core_selection_strategy="fixed",
+                          grow_with_rot=True, rot_size_start=m["rot_size_start"],
+                          max_refine_iter=m["max_refine_iter"], ci_residual_tolerance=1e-8).run(_ham(water), 5, 5)
+        assert w.size() == m["n"] and abs(E - water.core_energy - m["E"]) < 1e-8
+        st = alg.last_run_stats()
+        assert st["natural_orbital_rotations"] >= 1 and abs(st["natural_occupation_sum"] - 10.0) < 1e-9
+
+
+def test_integrals_rotate_matches_numpy():
+    from qdk_chemistry_b200 import device
+    sp = W.config("small_cas8")
+    n = sp.norb
+    rng = np.random.default_rng(3)
+    Q, _ = np.linalg.qr(rng.normal(size=(n, n)))
+    ctx = device.Context(0)
+    try:
+        ctx.upload_integrals(n, sp.T, sp.V)
+        T2, V2 = ctx.rotate_integrals(Q)
+        h = port.Ham(n, sp.T, sp.V)
+        h.rotate(Q)
+        assert np.allclose(T2, h.T, rtol=0, atol=1e-12) and np.allclose(V2, h.V, rtol=0, atol=1e-12)
+        G, Vr, G2, V2r = ctx.download_intermediates()
+        oG, oVr, oG2, oV2 = port.Ham(n, T2, V2).intermediates()      # intermediates of the rotated integrals
+        assert np.array_equal(G, oG) and np.array_equal(Vr, oVr) and np.array_equal(G2, oG2)
+    finally:
+        ctx.close()

@@ -307,3 +307,19 @@ def test_port_follows_each_generators_rules(tag):
         m = meta[f"{tag}.{thr_tag}"]
         for g in ("sorted_double_loop", "residue_arrays", "dynamic_bit_masking"):
             check_generator_golden(m[g], *h.hbuild(a, b, m["thr"], generator=g))
+
+
+def test_port_grow_with_rot_matches_compiled_reference(water):
+    import json
+    with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "rot_meta.json")) as fh:
+        meta = json.load(fh)
+    for tag in ("grow", "refine"):
+        m = meta[tag]
+        h = port.Ham(water.norb, water.T, water.V)
+        E, a, b, X = port.asci_run(h, 5, 5, refine=m["max_refine_iter"] > 0, core_selection_strategy="fixed",
+                                   grow_with_rot=True, ntdets_max=m["ntdets_max"], rot_size_start=m["rot_size_start"],
+                                   max_refine_iter=m["max_refine_iter"])
+        assert len(a) == m["n"] and abs(E - m["E"]) < 1e-8
+        # the integrals were rotated: trace of T changes, the Frobenius norm of V does not
+        assert not np.allclose(h.T, np.ravel(water.T))
+        assert abs(np.linalg.norm(h.V) - np.linalg.norm(np.ravel(water.V))) < 1e-9
