@@ -3,6 +3,7 @@
 // that stand where the reference registers MacisCas / MacisAsci / MacisPmc (mc.cpp:26-31,
 // macis_cas.hpp:24-66, macis_asci.hpp:34-235, macis_pmc.hpp).
 #pragma once
+#include <limits>
 #include <utility>
 
 #include "algorithm.hpp"
@@ -84,6 +85,25 @@ class B200Pmc : public ProjectedMultiConfigurationCalculator {
  protected:
   McResult _run_impl(std::shared_ptr<data::Hamiltonian> hamiltonian,
                      const std::vector<data::Configuration>& configurations) const override;
+};
+
+// ---- the CASCI functor MCSCF drivers call every macro-iteration: macis::compute_casci_rdms and its
+// CASRDMFunctor wrapper (external/macis/include/macis/mcscf/cas.hpp:33-88). T (n x n) and V (n^4)
+// are column-major and only read; full-CI space in generate_hilbert_space order, always the
+// iterative solver (selected_ci_diag), C in/out (a non-trivial C is the Davidson guess). When both
+// ORDM and TRDM are given they receive (accumulate, like the reference) the spin-traced RDMs.
+struct MCSCFSettings {  // macis::MCSCFSettings fields the functor reads (mcscf.hpp:22-52)
+  double ci_res_tol = 1e-8;
+  size_t ci_max_subspace = 20;
+  double ci_matel_tol = std::numeric_limits<double>::epsilon();
+};
+double compute_casci_rdms(const MCSCFSettings& settings, size_t norb, size_t nalpha, size_t nbeta, const double* T,
+                          const double* V, double* ORDM, double* TRDM, std::vector<double>& C);
+struct CASRDMFunctor {
+  template <typename... Args>
+  static auto rdms(Args&&... args) {
+    return compute_casci_rdms(std::forward<Args>(args)...);
+  }
 };
 
 // ---- multi-GPU: one process per GPU. Call once per process before run(); the 128-byte id comes

@@ -847,6 +847,37 @@ McResult B200Pmc::_run_impl(std::shared_ptr<data::Hamiltonian> h,
   return {E + h->get_core_energy(), w};
 }
 
+double compute_casci_rdms(const MCSCFSettings& st, size_t norb, size_t nalpha, size_t nbeta, const double* T,
+                          const double* V, double* ORDM, double* TRDM, std::vector<double>& C) {  // mcscf/cas.hpp:33-64
+  if (!T || !V) throw std::invalid_argument("compute_casci_rdms: null integrals");
+  const size_t n2 = norb * norb;
+  data::Hamiltonian ham(norb, std::vector<double>(T, T + n2), std::vector<double>(V, V + n2 * n2), 0.0);
+  check_hamiltonian(ham, "compute_casci_rdms", unsigned(nalpha), unsigned(nbeta));
+  CiSession S(ham);
+  b2ci_dets* d = nullptr;
+  B2(b2ci_dets_generate_fci(S.ctx(), int(norb), int(nalpha), int(nbeta), &d));
+  int64_t n = 0;
+  b2ci_dets_size(d, &n);
+  std::vector<Det> dets;
+  if (ORDM && TRDM) {
+    dets.resize(size_t(n));
+    if (b2ci_dets_download(S.ctx(), d, reinterpret_cast<uint64_t*>(dets.data()), 2) != 0) {
+      b2ci_dets_free(S.ctx(), d);
+      fail("b2ci_dets_download");
+    }
+  }
+  // (the session frees the list: take_dets)
+  const double E0 = S.selected_ci_diag(d, n, st.ci_matel_tol, int64_t(st.ci_max_subspace), st.ci_res_tol, C, false, 0.3,
+                                       true);
+  if (ORDM && TRDM) {
+    std::vector<double> o1(n2, 0.0), t1(n2 * n2, 0.0), none;
+    S.form_rdms(dets, C, false, o1, none, t1, none, none);
+    for (size_t i = 0; i < n2; ++i) ORDM[i] += o1[i];
+    for (size_t i = 0; i < n2 * n2; ++i) TRDM[i] += t1[i];
+  }
+  return E0;
+}
+
 std::pair<int64_t, int64_t> row_block(int64_t n, int rank, int nranks) {
   if (n < 0 || nranks < 1 || rank < 0 || rank >= nranks) throw std::invalid_argument("row_block: bad arguments");
   const int64_t base = n / nranks, rem = n % nranks;

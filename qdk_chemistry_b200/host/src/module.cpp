@@ -10,6 +10,7 @@
 #include <pybind11/pybind11.h>
 #include <pybind11/stl.h>
 
+#include "qdk_b200/fcidump.hpp"
 #include "qdk_b200/mc.hpp"
 
 namespace py = pybind11;
@@ -310,6 +311,96 @@ PYBIND11_MODULE(_core, m) {
         return py::make_tuple(r.first, x);
       },
       py::arg("csr_matrix"), py::arg("tol") = 1e-8, py::arg("max_m") = 20);
+
+  // ---- compute_casci_rdms (mcscf/cas.hpp:33-64): (E0, C, ordm | None, trdm | None)
+  amod.def(
+      "compute_casci_rdms",
+      [](size_t norb, size_t nalpha, size_t nbeta, py::array_t<double, py::array::f_style | py::array::forcecast> T,
+         py::array_t<double, py::array::f_style | py::array::forcecast> V, bool rdms, double ci_res_tol,
+         size_t ci_max_subspace, double ci_matel_tol) {
+        if (size_t(T.size()) != norb * norb || size_t(V.size()) != norb * norb * norb * norb)
+          throw std::invalid_argument("compute_casci_rdms: T must hold norb^2 and V norb^4 elements");
+        MCSCFSettings st;
+        st.ci_res_tol = ci_res_tol;
+        st.ci_max_subspace = ci_max_subspace;
+        st.ci_matel_tol = ci_matel_tol;
+        std::vector<double> C, o1, t1;
+        if (rdms) { o1.assign(norb * norb, 0.0); t1.assign(norb * norb * norb * norb, 0.0); }
+        double E0;
+        {
+          py::gil_scoped_release nogil;
+          E0 = CASRDMFunctor::rdms(st, norb, nalpha, nbeta, T.data(), V.data(), rdms ? o1.data() : nullptr,
+                                   rdms ? t1.data() : nullptr, C);
+        }
+        auto arr = [](const std::vector<double>& v) {
+          py::array_t<double> a{py::ssize_t(v.size())};
+          std::memcpy(a.mutable_data(), v.data(), v.size() * 8);
+          return a;
+        };
+        return py::make_tuple(E0, arr(C), rdms ? py::object(arr(o1)) : py::object(py::none()),
+                              rdms ? py::object(arr(t1)) : py::object(py::none()));
+      },
+      py::arg("norb"), py::arg("nalpha"), py::arg("nbeta"), py::arg("T"), py::arg("V"), py::arg("rdms") = true,
+      py::arg("ci_res_tol") = 1e-8, py::arg("ci_max_subspace") = 20,
+      py::arg("ci_matel_tol") = std::numeric_limits<double>::epsilon());
+
+  // ---- FCIDUMP / binary RDM files (macis/util/fcidump.hpp)
+  py::module_ io = m.def_submodule("io", "FCIDUMP and RDM file formats shared with MACIS");
+  io.def("fcidump_read_header", [](const std::string& f) {
+    const io::FCIDumpHeader h = io::fcidump_read_header(f);
+    py::dict d;
+    d["norb"] = h.norb; d["nelec"] = h.nelec; d["ms2"] = h.ms2; d["isym"] = h.isym; d["orbsym"] = h.orbsym;
+    return d;
+  });
+  io.def("read_fcidump_norb", &io::read_fcidump_norb);
+  io.def("read_fcidump_core", &io::read_fcidump_core);
+  io.def("read_fcidump_all", [](const std::string& f) {
+    const size_t n = io::read_fcidump_norb(f);
+    py::array_t<double> T{py::ssize_t(n * n)}, V{py::ssize_t(n * n * n * n)};
+    double core = 0.;
+    io::read_fcidump_all(f, T.mutable_data(), n, V.mutable_data(), n, core);
+    return py::make_tuple(T, V, core);   // flat, column-major
+  });
+  io.def("read_fcidump_1body", [](const std::string& f) {
+    const size_t n = io::read_fcidump_norb(f);
+    py::array_t<double> T{py::ssize_t(n * n)};
+    std::fill(T.mutable_data(), T.mutable_data() + n * n, 0.0);
+    io::read_fcidump_1body(f, T.mutable_data(), n);
+    return T;
+  });
+  io.def("read_fcidump_2body", [](const std::string& f) {
+    const size_t n = io::read_fcidump_norb(f);
+    py::array_t<double> V{py::ssize_t(n * n * n * n)};
+    std::fill(V.mutable_data(), V.mutable_data() + n * n * n * n, 0.0);
+    io::read_fcidump_2body(f, V.mutable_data(), n);
+    return V;
+  });
+  io.def(
+      "write_fcidump",
+      [](const std::string& f, uint32_t norb, uint32_t nelec, int32_t ms2,
+         py::array_t<double, py::array::f_style | py::array::forcecast> T,
+         py::array_t<double, py::array::f_style | py::array::forcecast> V, double core, double threshold) {
+        if (size_t(T.size()) != size_t(norb) * norb || size_t(V.size()) != size_t(norb) * norb * norb * norb)
+          throw std::invalid_argument("write_fcidump: T must hold norb^2 and V norb^4 elements");
+        io::FCIDumpHeader h;
+        h.norb = norb; h.nelec = nelec; h.ms2 = ms2; h.isym = 1;
+        h.orbsym.assign(norb, 1);
+        io::write_fcidump(f, h, T.data(), norb, V.data(), norb, core, threshold);
+      },
+      py::arg("fname"), py::arg("norb"), py::arg("nelec"), py::arg("ms2"), py::arg("T"), py::arg("V"),
+      py::arg("core_energy"), py::arg("threshold") = 1e-15);
+  io.def("read_rdms_binary", [](const std::string& f, size_t norb) {
+    py::array_t<double> o{py::ssize_t(norb * norb)}, t{py::ssize_t(norb * norb * norb * norb)};
+    io::read_rdms_binary(f, norb, o.mutable_data(), norb, t.mutable_data(), norb);
+    return py::make_tuple(o, t);
+  });
+  io.def("write_rdms_binary", [](const std::string& f, size_t norb,
+                                 py::array_t<double, py::array::f_style | py::array::forcecast> o,
+                                 py::array_t<double, py::array::f_style | py::array::forcecast> t) {
+    if (size_t(o.size()) != norb * norb || size_t(t.size()) != norb * norb * norb * norb)
+      throw std::invalid_argument("write_rdms_binary: bad array sizes");
+    io::write_rdms_binary(f, norb, o.data(), norb, t.data(), norb);
+  });
 
   amod.def("set_device", &set_device, py::arg("device"));
   amod.def("set_communicator", [](const py::bytes& id, int rank, int nranks) { set_communicator(std::string(id), rank, nranks); },

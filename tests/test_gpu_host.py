@@ -12,7 +12,7 @@ from oracle import port
 from qdk_chemistry_b200 import algorithms as alg
 from qdk_chemistry_b200 import data
 from qdk_chemistry_b200 import workloads as W
-from helpers import cisd_space, sha
+from helpers import EPS, cisd_space, sha
 
 pytestmark = pytest.mark.gpu
 MC = "multi_configuration_calculator"
@@ -316,3 +316,25 @@ def test_integrals_rotate_matches_numpy():
         assert np.array_equal(G, oG) and np.array_equal(Vr, oVr) and np.array_equal(G2, oG2)
     finally:
         ctx.close()
+
+
+def test_compute_casci_rdms_functor():
+    """macis::compute_casci_rdms / CASRDMFunctor (mcscf/cas.hpp:33-88), the CASCI step MCSCF drivers
+    call: energy of the iterative solver on the full-CI space, spin-traced RDMs of form_rdms."""
+    from qdk_chemistry_b200 import _core
+    sp = W.config("small_cas8")
+    n = sp.norb
+    E0, C, o1, t1 = _core.algorithms.compute_casci_rdms(n, sp.nalpha, sp.nbeta, sp.T, sp.V, True, 1e-10, 200)
+    a, b = port.generate_hilbert_space(n, sp.nalpha, sp.nbeta)
+    h = port.Ham(n, sp.T, sp.V)
+    rp, ci, nz = h.hbuild(a, b, EPS)
+    Eo, Xo, _, _ = port.davidson(rp, ci, nz, 200, 1e-10)
+    assert abs(E0 - Eo) < 1e-9 and abs(abs(C @ Xo) - 1) < 1e-8
+    po, pt = port.form_rdms(n, a, b, C, spin_dep=False)
+    assert np.abs(o1.reshape(n, n, order="F") - po).max() < 1e-12
+    assert np.abs(t1.reshape((n,) * 4, order="F") - pt).max() < 1e-12
+    # E = <ordm, T> + <trdm, V> (external/macis/tests/double_loop.cxx:198-375 normalisation)
+    Er = np.sum(o1 * np.ravel(sp.T)) + np.sum(t1 * np.ravel(sp.V))
+    assert abs(Er - E0) < 1e-8
+    E1, C1, none1, none2 = _core.algorithms.compute_casci_rdms(n, sp.nalpha, sp.nbeta, sp.T, sp.V, False, 1e-10, 200)
+    assert none1 is None and none2 is None and abs(E1 - E0) < 1e-9

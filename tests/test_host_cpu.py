@@ -1,6 +1,8 @@
 """Host plugin layer without a GPU: factory / registration / settings behaviour of the
 MultiConfigurationCalculator API (reference: cpp/tests/test_mc.cpp factory + metadata cases,
 cpp/tests/test_macis.cpp settings round trips, algorithm.hpp:262-372)."""
+import os
+
 import numpy as np
 import pytest
 
@@ -134,9 +136,97 @@ def test_run_without_a_gpu_fails_loudly_and_locks_settings():
     unres = data.Hamiltonian(np.eye(2), np.zeros(16), 0.0, True)
     with pytest.raises(RuntimeError, match="does not support unrestricted orbitals"):
         alg.create(MC, "b200_asci").run(unres, 1, 1)
-    with pytest.raises(RuntimeError, match="grow_with_rot"):
-        alg.create(MC, "b200_asci", grow_with_rot=True).run(
-            data.Hamiltonian(np.eye(2), np.zeros(16), 0.0), 1, 1)
+    # every hamiltonian_build_algorithm of the reference is accepted (macis_asci.hpp:174-179)
+    for algo in ("", "sorted_double_loop", "residue_arrays", "dynamic_bit_masking"):
+        with pytest.raises(RuntimeError, match="no CPU fallback"):
+            alg.create(MC, "b200_asci", hamiltonian_build_algorithm=algo, grow_with_rot=True).run(
+                data.Hamiltonian(np.eye(2), np.zeros(16), 0.0), 1, 1)
     with pytest.raises(RuntimeError, match="grow_factor must be > 1.0"):
         alg.create(MC, "b200_asci", grow_factor=1.0).run(
             data.Hamiltonian(np.eye(2), np.zeros(16), 0.0), 1, 1)
+
+
+# ---- FCIDUMP / RDM file formats in the C++ host layer (macis/util/fcidump.hpp) -------------------
+def _core_io():
+    from qdk_chemistry_b200 import _core
+    return _core.io
+
+
+def test_fcidump_cpp_round_trip_and_reference_known_answers(tmp_path):
+    # external/macis/tests/fcidump.cxx:26-61: header fields, core energy and the integral sums of
+    # the water / cc-pVDZ file; here the file is rewritten from the committed integrals
+    import os
+    from qdk_chemistry_b200 import workloads as W
+    io = _core_io()
+    water = W.load_sparse_npz(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "h2o_ccpvdz.ints.npz"))
+    n = water.norb
+    f = str(tmp_path / "water.fcidump")
+    io.write_fcidump(f, n, 10, 0, np.asarray(water.T).reshape(n, n), np.asarray(water.V).reshape(-1), water.core_energy)
+    h = io.fcidump_read_header(f)
+    assert (h["norb"], h["nelec"], h["ms2"], h["isym"]) == (24, 10, 0, 1) and h["orbsym"] == [1] * 24
+    assert io.read_fcidump_norb(f) == 24
+    T, V, core = io.read_fcidump_all(f)
+    assert abs(core - 9.191200742618042) < 1e-10 and abs(io.read_fcidump_core(f) - core) == 0
+    assert abs(T.sum() - (-1.095432762653e+02)) < 1e-9
+    assert abs(V.sum() - 2.701609068389e+02) < 1e-9
+    # %25.14e keeps 15 significant digits
+    assert np.allclose(T, np.ravel(water.T), rtol=1e-14, atol=1e-15)
+    assert np.allclose(V, np.ravel(water.V), rtol=1e-14, atol=1e-15)
+    assert np.array_equal(io.read_fcidump_1body(f), T) and np.array_equal(io.read_fcidump_2body(f), V)
+    # the Python reader of the workload module and the C++ reader agree
+    sp = W.read_fcidump(f)
+    assert sp.norb == 24 and sp.nalpha == 5 and sp.nbeta == 5
+    assert np.array_equal(np.ravel(sp.T), T) and np.array_equal(np.ravel(sp.V), V)
+
+
+def test_fcidump_cpp_both_layouts_and_errors(tmp_path):
+    io = _core_io()
+    body_first = ["0.5 1 1 1 1", "0.25 2 1 1 1", "-1.5 1 1 0 0", "0.125 2 1 0 0", "3.0 0 0 0 0"]
+    idx_first = ["1 1 1 1 0.5", "2 1 1 1 0.25", "1 1 0 0 -1.5", "2 1 0 0 0.125", "0 0 0 0 3.0"]
+    out = []
+    for name, lines in (("a", body_first), ("b", idx_first)):
+        f = str(tmp_path / name)
+        with open(f, "w") as fh:
+            fh.write("&FCI NORB = 2; NELEC = 2; MS2 = 0,\n  ORBSYM=1,1,\n  ISYM=1,\n&END\n\n" + "\n".join(lines) + "\n")
+        out.append(io.read_fcidump_all(f))
+    (T1, V1, c1), (T2, V2, c2) = out
+    assert np.array_equal(T1, T2) and np.array_equal(V1, V2) and c1 == c2 == 3.0
+    assert T1.tolist() == [-1.5, 0.125, 0.125, 0.0]
+    V = V1.reshape(2, 2, 2, 2, order="F")
+    assert V[0, 0, 0, 0] == 0.5
+    # (21|11) under its eight permutations
+    for idx in ((1, 0, 0, 0), (0, 1, 0, 0), (0, 0, 1, 0), (0, 0, 0, 1)):
+        assert V[idx] == 0.25
+    with pytest.raises(RuntimeError, match="No FCIDUMP header"):
+        f = str(tmp_path / "c")
+        open(f, "w").write("1 1 1 1 0.5\n")
+        io.fcidump_read_header(f)
+    with pytest.raises(RuntimeError, match="Could not open"):
+        io.read_fcidump_core(str(tmp_path / "missing"))
+
+
+def test_rdm_binary_round_trip(tmp_path):
+    io = _core_io()
+    rng = np.random.default_rng(0)
+    o, t = rng.normal(size=9), rng.normal(size=81)
+    f = str(tmp_path / "rdm.bin")
+    io.write_rdms_binary(f, 3, o, t)
+    o2, t2 = io.read_rdms_binary(f, 3)
+    assert np.array_equal(o, o2) and np.array_equal(t, t2)
+    with pytest.raises(RuntimeError, match="doesn't match"):
+        io.read_rdms_binary(f, 4)
+
+
+@pytest.mark.skipif(not os.path.exists("/root/reference/external/macis/tests/ref_data/h2o.ccpvdz.fci.dat"),
+                    reason="reference tree not present (build container only)")
+def test_fcidump_cpp_reads_the_reference_fixture():
+    from qdk_chemistry_b200 import workloads as W
+    io = _core_io()
+    f = "/root/reference/external/macis/tests/ref_data/h2o.ccpvdz.fci.dat"
+    h = io.fcidump_read_header(f)
+    assert (h["norb"], h["nelec"], h["ms2"], h["isym"]) == (24, 10, 0, 1) and h["orbsym"] == [1] * 24
+    T, V, core = io.read_fcidump_all(f)
+    assert abs(core - 9.191200742618042) < 1e-10
+    assert abs(T.sum() - (-1.095432762653e+02)) < 1e-9 and abs(V.sum() - 2.701609068389e+02) < 1e-9
+    water = W.load_sparse_npz(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "h2o_ccpvdz.ints.npz"))
+    assert np.array_equal(T, np.ravel(water.T)) and np.array_equal(V, np.ravel(water.V))
