@@ -172,7 +172,9 @@ typedef struct {
   double h_el_tol;      /* ASCISettings::h_el_tol      (QDK key search_matel_tol) */
   double rv_prune_tol;  /* ASCISettings::rv_prune_tol                              */
   int32_t just_singles; /* ASCISettings::just_singles                              */
-  int32_t reserved;
+  int32_t sort_output;  /* 0: selected determinants then the core ones (the reference's order,
+                         * determinant_search.hpp:1107-1114); 1: the whole list in spin_comparator
+                         * order, i.e. what asci_iter sorts it into next (asci/iteration.hpp:117-119) */
 } b2ci_asci_search_opts;
 /* stats (may be NULL, 8 doubles): [0] contributions generated, [1] unique candidates,
  * [2] kth |rv| pivot, [3] largest |rv| below the pivot, [4] number selected */

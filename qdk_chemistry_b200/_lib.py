@@ -25,7 +25,7 @@ class B2ciError(RuntimeError):
 
 class AsciSearchOpts(C.Structure):
     _fields_ = [("ndets_max", C.c_int64), ("h_el_tol", C.c_double), ("rv_prune_tol", C.c_double),
-                ("just_singles", C.c_int32), ("reserved", C.c_int32)]
+                ("just_singles", C.c_int32), ("sort_output", C.c_int32)]
 
 
 NOT_CONVERGED = 3

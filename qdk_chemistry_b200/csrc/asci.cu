@@ -345,6 +345,14 @@ k_pt2_partial(const double* __restrict__ scm, const double* __restrict__ shd, in
   if (threadIdx.x == 0) { part_sum[blockIdx.x] = ssum[0]; part_cnt[blockIdx.x] = scnt[0]; }
 }
 
+// keys of the core determinants behind the selected ones (packed: beta << 32 | alpha)
+__global__ void k_append_core_keys(const uint64_t* __restrict__ ca, const uint64_t* __restrict__ cb, int64_t nc,
+                                   int packed, uint64_t* __restrict__ k1, uint64_t* __restrict__ k2) {
+  const int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= nc) return;
+  if (packed) k1[i] = (cb[i] << 32) | ca[i];
+  else { k1[i] = ca[i]; k2[i] = cb[i]; }
+}
 __global__ void k_fill_u64(uint64_t* p, int64_t n, uint64_t v) {
   const int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
   if (i < n) p[i] = v;
@@ -747,6 +755,51 @@ int asci_search(b2ci_ctx* ctx, const b2ci_asci_search_opts* o, const uint64_t* c
   const int64_t total = nkeep + nc;
   if (n_out) *n_out = total;
   if (total > cap) throw Error("b2ci_asci_search: output capacity " + std::to_string(cap) + " < " + std::to_string(total), 4);
+  if (o->sort_output) {
+    // spin_comparator order (alpha-major, then beta) of the whole new list, made on the device: what
+    // asci_iter does next with a host std::sort (asci/iteration.hpp:117-119). Stable LSD radix: the
+    // minor key (beta) first, then the major key (alpha).
+    ScopedTimer t(ctx, "asci_search.TOPK_DUR", true);
+    DevBuf<uint64_t> k1(total), k1alt(total), k2(two ? total : 1), kw(two ? total : 1);
+    DevBuf<uint32_t> idx(total), idx_alt(total);
+    if (nkeep) {
+      B2_CUDA(cudaMemcpyAsync(k1, cand_key, size_t(nkeep) * 8, cudaMemcpyDeviceToDevice, st));
+      if (two) B2_CUDA(cudaMemcpyAsync(k2, cand_key2, size_t(nkeep) * 8, cudaMemcpyDeviceToDevice, st));
+    }
+    k_append_core_keys<<<grid1d(nc), 256, 0, st>>>(core.alpha, core.beta, nc, two ? 0 : 1, k1.p + nkeep, k2.p + (two ? nkeep : 0));
+    ctx->launches++;
+    B2_CHECK_LAUNCH();
+    iota_u32(ctx, idx, total);
+    const int ndig = (n + 7) / 8;
+    std::vector<int> shifts;
+    std::vector<uint64_t> h1(total), h2(two ? total : 0);
+    if (!two) {
+      for (int d = 0; d < ndig; ++d) shifts.push_back(32 + 8 * d);  // beta: minor
+      for (int d = 0; d < ndig; ++d) shifts.push_back(8 * d);       // alpha: major
+      radix_sort_pairs(ctx, k1, k1alt, idx, idx_alt, total, shifts);
+      B2_CUDA(cudaMemcpyAsync(h1.data(), k1, size_t(total) * 8, cudaMemcpyDeviceToHost, st));
+    } else {
+      for (int d = 0; d < ndig; ++d) shifts.push_back(8 * d);
+      B2_CUDA(cudaMemcpyAsync(kw, k2, size_t(total) * 8, cudaMemcpyDeviceToDevice, st));
+      radix_sort_pairs(ctx, kw, k1alt, idx, idx_alt, total, shifts);            // by beta
+      k_gather_u64<<<grid1d(total), 256, 0, st>>>(k1, idx, total, kw);
+      ctx->launches++;
+      B2_CHECK_LAUNCH();
+      radix_sort_pairs(ctx, kw, k1alt, idx, idx_alt, total, shifts);            // by alpha, stable
+      k_gather_u64<<<grid1d(total), 256, 0, st>>>(k2, idx, total, k1alt);
+      ctx->launches++;
+      B2_CHECK_LAUNCH();
+      B2_CUDA(cudaMemcpyAsync(h1.data(), kw, size_t(total) * 8, cudaMemcpyDeviceToHost, st));
+      B2_CUDA(cudaMemcpyAsync(h2.data(), k1alt, size_t(total) * 8, cudaMemcpyDeviceToHost, st));
+    }
+    B2_CUDA(cudaStreamSynchronize(st));
+    if (two)
+      for (int64_t i = 0; i < total; ++i) { out_words[2 * i] = h1[i]; out_words[2 * i + 1] = h2[i]; }
+    else if (wpd == 1) memcpy(out_words, h1.data(), size_t(total) * 8);
+    else
+      for (int64_t i = 0; i < total; ++i) { out_words[2 * i] = h1[i] & 0xFFFFFFFFull; out_words[2 * i + 1] = h1[i] >> 32; }
+    return 0;
+  }
   if (nkeep) {
     std::vector<uint64_t> tmp(nkeep), tmp2(two ? nkeep : 0);
     B2_CUDA(cudaMemcpyAsync(tmp.data(), cand_key, size_t(nkeep) * 8, cudaMemcpyDeviceToHost, st));

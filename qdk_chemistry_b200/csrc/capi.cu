@@ -513,7 +513,7 @@ int b2ci_asci_pt2(b2ci_ctx* ctx, const uint64_t* det_words, int wpd, const doubl
   B2_TRY_CTX(ctx)
   if (!ept2) throw Error("b2ci_asci_pt2: ept2 is NULL");
   b2ci_asci_search_opts o;
-  o.ndets_max = ndets; o.h_el_tol = pt2_tol; o.rv_prune_tol = 0.; o.just_singles = 0; o.reserved = 0;
+  o.ndets_max = ndets; o.h_el_tol = pt2_tol; o.rv_prune_tol = 0.; o.just_singles = 0; o.sort_output = 0;
   double acc[2] = {0., 0.};
   asci_search(ctx, &o, det_words, wpd, coeffs, ndets, E_asci, nullptr, 0, nullptr, nullptr, nullptr, nullptr,
               nullptr, nullptr, false, acc);

@@ -147,11 +147,11 @@ class Context:
     # -- ASCI search
     def asci_search(self, core_words: np.ndarray, core_coeffs: np.ndarray, E0: float,
                     ndets_max: int, h_el_tol: float = 1e-8, rv_prune_tol: float = 1e-8,
-                    just_singles: bool = False, words_per_det: int = 1):
+                    just_singles: bool = False, words_per_det: int = 1, sort_output: bool = False):
         cw = np.ascontiguousarray(core_words, dtype=np.uint64)
         cc = np.ascontiguousarray(core_coeffs, dtype=np.float64)
         nc = cw.size // words_per_det
-        o = AsciSearchOpts(int(ndets_max), h_el_tol, rv_prune_tol, int(just_singles), 0)
+        o = AsciSearchOpts(int(ndets_max), h_el_tol, rv_prune_tol, int(just_singles), int(sort_output))
         cap = int(ndets_max) + nc + 4096
         stats = np.zeros(8)
         n_out = C.c_int64(0)

@@ -194,3 +194,22 @@ def test_wide_keys_pt2_matches_oracle(ctx, wide):
     e, npt2 = ctx.asci_pt2(port.pack(ca, cb, 128), cc, m["E0"], 1e-16, words_per_det=2)
     eo, no = port.Ham(sp.norb, sp.T, sp.V).asci_pt2(ca, cb, cc, m["E0"], 1e-16)
     assert npt2 == no and abs(e - eo) <= 1e-13 * abs(eo)
+
+
+@pytest.mark.parametrize("name", ["small_cas8", "wide36"])
+def test_sorted_output_is_the_spin_sorted_reference_output(ctx, name, wide):
+    """sort_output = 1 returns the list asci_iter would sort it into (iteration.hpp:117-119):
+    spin_comparator order, alpha-major then beta, for one- and two-word determinants."""
+    if name == "wide36":
+        sp, z, m = wide
+        ca, cb, cc, E0, nmax, wpd, nbits = z["core_alpha"], z["core_beta"], z["core_C"], m["E0"], m["ndets_max"], 2, 128
+    else:
+        sp = W.config(name)
+        ca, cb, cc = _core_from_fci(sp, 30, seed=3)
+        E0, nmax, wpd, nbits = -2.0, 400, 1, 64
+    ctx.upload_integrals(sp.norb, sp.T, sp.V)
+    ref_out, _ = ctx.asci_search(port.pack(ca, cb, nbits), cc, E0, nmax, words_per_det=wpd)
+    out, _ = ctx.asci_search(port.pack(ca, cb, nbits), cc, E0, nmax, words_per_det=wpd, sort_output=True)
+    ra, rb = port.unpack(ref_out, nbits)
+    o = port.spin_sort_order(ra, rb)
+    assert np.array_equal(out, port.pack(ra[o], rb[o], nbits))
