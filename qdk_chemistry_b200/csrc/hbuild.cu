@@ -127,9 +127,34 @@ struct RowArgs {
   // connection_build_utils.hpp:163-199): the diagonal is always kept, an off-diagonal element is
   // dropped only when |h| < thr, and alpha-empty determinants are ordinary determinants
   int pair_rule = 0;
+  // hit lists: the count pass can store the structural connections it finds (chunks of 32 column
+  // slots chained per row), so that the fill pass evaluates them without scanning again
+  int32_t* hit_cols = nullptr;        // [hit_capacity][32] ket indices
+  int32_t* hit_next = nullptr;        // [hit_capacity] next chunk of the row, -1 = last
+  int32_t* hit_head = nullptr;        // [nrows] first chunk of the row
+  unsigned int* hit_cursor = nullptr; // chunks handed out so far (may run past hit_capacity: overflow)
+  unsigned int hit_capacity = 0;
+  const int32_t* struct_cnt = nullptr;  // k_rows_hits: structural row lengths of the count pass
+  int64_t row_stride = 1;               // sampling (estimate pass): row r of the launch is row r * row_stride
 };
 
 // Evaluate up to 32 queued column indices (one per lane) and count / emit the survivors.
+// count pass with hit lists: one chunk per batch, chained to the row's previous chunk
+__device__ __forceinline__ void store_hits(const RowArgs& A, int64_t row, const int32_t* q, int nvalid, int lane,
+                                           int32_t& prev_chunk) {
+  unsigned int c = 0;
+  if (lane == 0) c = atomicAdd(A.hit_cursor, 1u);
+  c = __shfl_sync(0xffffffffu, c, 0);
+  if (c >= A.hit_capacity) return;  // overflow: the host sees the cursor and falls back to the scan
+  if (lane < nvalid) A.hit_cols[size_t(c) * 32 + lane] = q[lane];
+  if (lane == 0) {
+    A.hit_next[c] = -1;
+    if (prev_chunk >= 0) A.hit_next[prev_chunk] = int32_t(c);
+    else A.hit_head[row] = int32_t(c);
+  }
+  prev_chunk = int32_t(c);
+}
+
 template <bool FILL, bool EVAL, bool BLK>
 __device__ __forceinline__ void process_batch(const RowArgs& A, int64_t i, uint64_t ai,
                                               uint64_t bi, const int32_t* q, int nvalid, int lane,
@@ -174,7 +199,7 @@ k_rows(const RowArgs A) {
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   const int64_t row = int64_t(blockIdx.x) * ROW_WARPS + w;
   if (row >= A.nrows) return;
-  const int64_t il = A.row_begin + row;  // index in the bra list
+  const int64_t il = A.row_begin + row * A.row_stride;  // index in the bra list
   const uint64_t ai = BLK ? A.bra_alpha[il] : A.alpha[il], bi = BLK ? A.bra_beta[il] : A.beta[il];
   const int32_t r = BLK ? A.bra_run[il] : A.run_of[il];
   const int64_t i = (BLK && A.rowmap) ? int64_t(A.rowmap[il]) : il;  // index in the common list
@@ -183,6 +208,8 @@ k_rows(const RowArgs A) {
   int32_t cnt = 0;
   int64_t out = FILL ? A.rowptr[row] : 0;
   const unsigned lt = (1u << lane) - 1u;
+  int32_t prev_chunk = -1;
+  const bool keep_hits = !FILL && !EVAL && A.hit_cols != nullptr;
   // enqueue the hits of one ballot; evaluate / count / write 32 at a time with full lanes
   auto push = [&](bool hit, int64_t j) {
     const unsigned m = __ballot_sync(0xffffffffu, hit);
@@ -191,6 +218,7 @@ k_rows(const RowArgs A) {
     qn += __popc(m);
     __syncwarp();
     if (qn >= 32) {
+      if (keep_hits) store_hits(A, row, q, 32, lane, prev_chunk);
       process_batch<FILL, EVAL, BLK>(A, i, ai, bi, q, 32, lane, out, cnt);
       const int rest = qn - 32;
       const int32_t t = (lane < rest) ? q[32 + lane] : 0;
@@ -246,7 +274,34 @@ k_rows(const RowArgs A) {
       }
     }
     flush_group(INT64_MAX);
-    if (qn > 0) process_batch<FILL, EVAL, BLK>(A, i, ai, bi, q, qn, lane, out, cnt);
+    if (qn > 0) {
+      if (keep_hits) store_hits(A, row, q, qn, lane, prev_chunk);
+      process_batch<FILL, EVAL, BLK>(A, i, ai, bi, q, qn, lane, out, cnt);
+    }
+  }
+  if (lane == 0 && A.row_cnt) A.row_cnt[row] = cnt;
+}
+
+// fill pass from the stored hit lists: every chunk is full except the last of a row
+template <bool EVAL, bool BLK>
+__global__ void __launch_bounds__(ROW_WARPS * 32)
+k_rows_hits(const RowArgs A) {
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int64_t row = int64_t(blockIdx.x) * ROW_WARPS + w;
+  if (row >= A.nrows) return;
+  const int64_t il = A.row_begin + row;
+  const uint64_t ai = BLK ? A.bra_alpha[il] : A.alpha[il], bi = BLK ? A.bra_beta[il] : A.beta[il];
+  const int64_t i = (BLK && A.rowmap) ? int64_t(A.rowmap[il]) : il;
+  int32_t remaining = A.struct_cnt[row];
+  int32_t chunk = remaining > 0 ? A.hit_head[row] : -1;
+  int64_t out = A.rowptr[row];
+  int32_t cnt = 0;
+  while (remaining > 0) {
+    const int nvalid = remaining < 32 ? remaining : 32;
+    const int32_t nxt = A.hit_next[chunk];
+    process_batch<true, EVAL, BLK>(A, i, ai, bi, A.hit_cols + size_t(chunk) * 32, nvalid, lane, out, cnt);
+    remaining -= nvalid;
+    chunk = nxt;
   }
   if (lane == 0 && A.row_cnt) A.row_cnt[row] = cnt;
 }
@@ -1119,6 +1174,157 @@ void dets_generate_fci(b2ci_ctx* ctx, int norb, int na, int nb, b2ci_dets* d) {
   d->beta = b.take();
 }
 
+namespace {
+// Row scan of a general (or rectangular-block) list, shared by hbuild_csr and the patched build.
+// Count pass = the scan alone (structural connections, no matrix element); the fill pass
+// evaluates every element ONCE, writes the survivors compacted inside the row's structural
+// slot and records how many there were; rows are packed afterwards only if something was
+// dropped (threshold_parallel, csr_matrix.hpp:317-370).
+// The scan (XOR + popcount over the beta strings of the adjacent runs) is what a general build
+// costs, so it is done once: a sampled estimate pass (every 64th row) sizes a chunk store, the
+// count pass keeps the connections it finds there, and the fill pass evaluates them from the
+// store. If the store turns out too small the fill pass scans again (same result).
+struct RowScanOut {
+  DevBuf<int64_t> rowptr;
+  DevBuf<int32_t> colind;
+  DevBuf<double> nzval;
+  int64_t nnz = 0;
+  size_t ci_cap = 0, nz_cap = 0;  // non-zero: blocks came from the context's slot cache
+};
+template <bool BLK>
+void run_row_scan(b2ci_ctx* ctx, RowArgs A, int64_t nrows, double thr, bool use_slot_cache, RowScanOut& out) {
+  cudaStream_t st = ctx->stream;
+  const unsigned grid = unsigned((nrows + ROW_WARPS - 1) / ROW_WARPS);
+  int64_t nslots = 0;
+  DevBuf<int64_t> slot_ptr(nrows + 1);
+  DevBuf<int32_t> row_cnt(nrows);
+  DevBuf<int32_t> hit_cols, hit_next, hit_head;
+  DevBuf<unsigned int> hit_cursor(1);
+  unsigned int hit_capacity = 0, hit_used = 0;
+  {
+    ScopedTimer t(ctx, "h_build.count", true);
+    // (test hooks: B2CI_HBUILD_HITLIST_MIN = smallest list that uses the store, B2CI_HBUILD_HITLIST_CAP =
+    // its capacity in chunks, to exercise the overflow fallback)
+    const char* env_min = getenv("B2CI_HBUILD_HITLIST_MIN");
+    const int64_t min_rows = env_min ? atoll(env_min) : 4096;
+    const bool want_hits = nrows >= min_rows && !getenv("B2CI_HBUILD_NO_HITLIST");
+    if (want_hits) {
+      // estimate: structural row lengths of every 64th row
+      const int64_t stride = 64, ns = (nrows + stride - 1) / stride;
+      DevBuf<int32_t> scnt(ns);
+      DevBuf<int64_t> sptr(ns + 1);
+      RowArgs S = A;
+      S.row_stride = stride;
+      S.nrows = ns;
+      S.row_cnt = scnt;
+      k_rows<false, false, BLK><<<unsigned((ns + ROW_WARPS - 1) / ROW_WARPS), ROW_WARPS * 32, 0, st>>>(S);
+      ctx->launches++;
+      B2_CHECK_LAUNCH();
+      exclusive_scan_i32_to_i64(ctx, scnt, sptr, ns);
+      int64_t sample = 0;
+      B2_CUDA(cudaMemcpyAsync(&sample, sptr.p + ns, 8, cudaMemcpyDeviceToHost, st));
+      B2_CUDA(cudaStreamSynchronize(st));
+      const double est = double(sample) * double(nrows) / double(ns);
+      const double chunks = est * 1.25 / 32.0 + double(nrows) + 1024.0;  // + one partial chunk per row
+      size_t free_b = 0, total_b = 0;
+      B2_CUDA(cudaMemGetInfo(&free_b, &total_b));
+      // the store (132 B per chunk) must leave room for the matrix itself (12 B per entry)
+      if (chunks < 2.0e9 && chunks * 132.0 + est * 1.25 * 12.0 < 0.8 * double(free_b)) {
+        hit_capacity = unsigned(chunks);
+        if (const char* env_cap = getenv("B2CI_HBUILD_HITLIST_CAP")) hit_capacity = unsigned(std::max<long long>(1, atoll(env_cap)));
+        hit_cols.alloc(size_t(hit_capacity) * 32);
+        hit_next.alloc(hit_capacity);
+        hit_head.alloc(nrows);
+        B2_CUDA(cudaMemsetAsync(hit_cursor, 0, sizeof(unsigned int), st));
+        A.hit_cols = hit_cols;
+        A.hit_next = hit_next;
+        A.hit_head = hit_head;
+        A.hit_cursor = hit_cursor;
+        A.hit_capacity = hit_capacity;
+      }
+    }
+    A.row_cnt = row_cnt;
+    k_rows<false, false, BLK><<<grid, ROW_WARPS * 32, 0, st>>>(A);
+    ctx->launches++;
+    B2_CHECK_LAUNCH();
+    exclusive_scan_i32_to_i64(ctx, row_cnt, slot_ptr, nrows);
+    int64_t* pin = pinned_words(ctx);
+    B2_CUDA(cudaMemcpyAsync(pin, slot_ptr.p + nrows, 8, cudaMemcpyDeviceToHost, st));
+    if (hit_capacity) B2_CUDA(cudaMemcpyAsync(pin + 1, hit_cursor, sizeof(unsigned int), cudaMemcpyDeviceToHost, st));
+    B2_CUDA(cudaStreamSynchronize(st));
+    nslots = pin[0];
+    if (hit_capacity) hit_used = *reinterpret_cast<const unsigned int*>(pin + 1);
+  }
+  const bool from_hits = hit_capacity != 0 && hit_used <= hit_capacity;
+  ctx->timers["h_build.hit_lists"] = from_hits ? 1. : 0.;
+  if (!from_hits) { hit_cols.release(); hit_next.release(); hit_head.release(); }
+  DevBuf<int32_t> colind, kept(nrows);
+  DevBuf<double> nzval;
+  size_t ci_cap = 0, nz_cap = 0;
+  if (use_slot_cache) {
+    colind.p = static_cast<int32_t*>(big_alloc(ctx, 0, size_t(nslots > 0 ? nslots : 1) * sizeof(int32_t), &ci_cap));
+    colind.n = ci_cap / sizeof(int32_t);
+    nzval.p = static_cast<double*>(big_alloc(ctx, 1, size_t(nslots > 0 ? nslots : 1) * sizeof(double), &nz_cap));
+    nzval.n = nz_cap / sizeof(double);
+  } else {
+    colind.alloc(nslots > 0 ? nslots : 1);
+    nzval.alloc(nslots > 0 ? nslots : 1);
+  }
+  {
+    ScopedTimer t(ctx, "h_build.fill", true);
+    A.row_cnt = kept;
+    A.rowptr = slot_ptr;
+    A.colind = colind;
+    A.nzval = nzval;
+    A.struct_cnt = row_cnt;
+    if (from_hits) {
+      if (thr > 0.0) k_rows_hits<true, BLK><<<grid, ROW_WARPS * 32, 0, st>>>(A);
+      else k_rows_hits<false, BLK><<<grid, ROW_WARPS * 32, 0, st>>>(A);
+    } else {
+      A.hit_cols = nullptr;
+      if (thr > 0.0) k_rows<true, true, BLK><<<grid, ROW_WARPS * 32, 0, st>>>(A);
+      else k_rows<true, false, BLK><<<grid, ROW_WARPS * 32, 0, st>>>(A);
+    }
+    ctx->launches++;
+    B2_CHECK_LAUNCH();
+  }
+  int64_t nnz = nslots;
+  out.rowptr.alloc(nrows + 1);
+  if (thr > 0.0) {
+    ScopedTimer t(ctx, "h_build.thresh", true);
+    exclusive_scan_i32_to_i64(ctx, kept, out.rowptr, nrows);
+    int64_t* pin = pinned_words(ctx);
+    B2_CUDA(cudaMemcpyAsync(pin, out.rowptr.p + nrows, 8, cudaMemcpyDeviceToHost, st));
+    B2_CUDA(cudaStreamSynchronize(st));
+    nnz = pin[0];
+    if (nnz != nslots) {
+      DevBuf<int32_t> ci_f(nnz > 0 ? nnz : 1);
+      DevBuf<double> nz_f(nnz > 0 ? nnz : 1);
+      k_compact_rows<<<unsigned((nrows * 32 + ROW_WARPS * 32 - 1) / (ROW_WARPS * 32)), ROW_WARPS * 32, 0, st>>>(
+          nrows, slot_ptr, out.rowptr, colind, nzval, ci_f, nz_f);
+      ctx->launches++;
+      B2_CHECK_LAUNCH();
+      B2_CUDA(cudaStreamSynchronize(st));
+      if (use_slot_cache) {
+        big_release(ctx, 0, colind.take(), ci_cap);
+        big_release(ctx, 1, nzval.take(), nz_cap);
+        ci_cap = nz_cap = 0;
+      }
+      colind = std::move(ci_f);
+      nzval = std::move(nz_f);
+    }
+  } else {
+    out.rowptr = std::move(slot_ptr);
+  }
+  B2_CUDA(cudaStreamSynchronize(st));
+  out.nnz = nnz;
+  out.colind = std::move(colind);
+  out.nzval = std::move(nzval);
+  out.ci_cap = ci_cap;
+  out.nz_cap = nz_cap;
+}
+}  // namespace
+
 void hbuild_csr(b2ci_ctx* ctx, const b2ci_dets* dets, int64_t row_begin, int64_t row_end,
                 double thr, b2ci_csr* out) {
   if (!ctx->ints_dev) throw Error("b2ci_hbuild_csr: integrals not uploaded");
@@ -1501,77 +1707,16 @@ void hbuild_csr(b2ci_ctx* ctx, const b2ci_dets* dets, int64_t row_begin, int64_t
   A.colind = nullptr;
   A.nzval = nullptr;
   A.pair_rule = ctx->generator != 0;
-  const unsigned grid = unsigned((nrows + ROW_WARPS - 1) / ROW_WARPS);
-  // Count pass = the scan alone (structural connections, no matrix element); the fill pass
-  // evaluates every element ONCE, writes the survivors compacted inside the row's structural
-  // slot and records how many there were; rows are packed afterwards only if something was
-  // dropped (threshold_parallel, csr_matrix.hpp:317-370). Evaluating in both passes doubled
-  // the cost of the ASCI builds.
-  int64_t nslots = 0;
-  DevBuf<int64_t> slot_ptr(nrows + 1);
-  {
-    ScopedTimer t(ctx, "h_build.count");
-    DevBuf<int32_t> row_cnt(nrows);
-    A.row_cnt = row_cnt;
-    k_rows<false, false><<<grid, ROW_WARPS * 32, 0, st>>>(A);
-    ctx->launches++;
-    B2_CHECK_LAUNCH();
-    exclusive_scan_i32_to_i64(ctx, row_cnt, slot_ptr, nrows);
-    int64_t* pin = pinned_words(ctx);
-    B2_CUDA(cudaMemcpyAsync(pin, slot_ptr.p + nrows, 8, cudaMemcpyDeviceToHost, st));
-    B2_CUDA(cudaStreamSynchronize(st));
-    nslots = pin[0];
-  }
-  DevBuf<int32_t> colind, kept(nrows);
-  DevBuf<double> nzval;
-  size_t ci_cap = 0, nz_cap = 0;
-  colind.p = static_cast<int32_t*>(big_alloc(ctx, 0, size_t(nslots > 0 ? nslots : 1) * sizeof(int32_t), &ci_cap));
-  colind.n = ci_cap / sizeof(int32_t);
-  nzval.p = static_cast<double*>(big_alloc(ctx, 1, size_t(nslots > 0 ? nslots : 1) * sizeof(double), &nz_cap));
-  nzval.n = nz_cap / sizeof(double);
-  {
-    ScopedTimer t(ctx, "h_build.fill");
-    A.row_cnt = kept;
-    A.rowptr = slot_ptr;
-    A.colind = colind;
-    A.nzval = nzval;
-    if (thr > 0.0) k_rows<true, true><<<grid, ROW_WARPS * 32, 0, st>>>(A);
-    else k_rows<true, false><<<grid, ROW_WARPS * 32, 0, st>>>(A);
-    ctx->launches++;
-    B2_CHECK_LAUNCH();
-  }
-  int64_t nnz = nslots;
-  if (thr > 0.0) {
-    ScopedTimer t(ctx, "h_build.thresh");
-    exclusive_scan_i32_to_i64(ctx, kept, rowptr, nrows);
-    int64_t* pin = pinned_words(ctx);
-    B2_CUDA(cudaMemcpyAsync(pin, rowptr.p + nrows, 8, cudaMemcpyDeviceToHost, st));
-    B2_CUDA(cudaStreamSynchronize(st));
-    nnz = pin[0];
-    if (nnz != nslots) {
-      DevBuf<int32_t> ci_f(nnz > 0 ? nnz : 1);
-      DevBuf<double> nz_f(nnz > 0 ? nnz : 1);
-      k_compact_rows<<<unsigned((nrows * 32 + ROW_WARPS * 32 - 1) / (ROW_WARPS * 32)), ROW_WARPS * 32, 0, st>>>(
-          nrows, slot_ptr, rowptr, colind, nzval, ci_f, nz_f);
-      ctx->launches++;
-      B2_CHECK_LAUNCH();
-      B2_CUDA(cudaStreamSynchronize(st));
-      big_release(ctx, 0, colind.take(), ci_cap);
-      big_release(ctx, 1, nzval.take(), nz_cap);
-      ci_cap = nz_cap = 0;
-      colind = std::move(ci_f);
-      nzval = std::move(nz_f);
-    }
-  } else {
-    rowptr = std::move(slot_ptr);
-  }
-  B2_CUDA(cudaStreamSynchronize(st));
-  out->colind_cap = ci_cap;
-  out->nzval_cap = nz_cap;
-  out->nnz = nnz;
-  out->rowptr = rowptr.take();
-  out->colind = colind.take();
-  out->nzval = nzval.take();
+  // count pass (keeps the connections it finds) + fill pass (evaluates them): run_row_scan
+  ctx->timers["h_build.count"] = ctx->timers["h_build.fill"] = ctx->timers["h_build.thresh"] = 0.;
+  RowScanOut R;
+  run_row_scan<false>(ctx, A, nrows, thr, true, R);
+  out->colind_cap = R.ci_cap;
+  out->nzval_cap = R.nz_cap;
+  out->nnz = R.nnz;
+  out->rowptr = R.rowptr.take();
+  out->colind = R.colind.take();
+  out->nzval = R.nzval.take();
 }
 
 // ------------------------------------------------------------------------------------
@@ -1694,52 +1839,18 @@ void build_block_general(b2ci_ctx* ctx, const DetView& bra, const DetView& ket, 
   A.rowmap = bra.gmap;
   A.colmap = ket.gmap;
   A.pair_rule = ctx->generator != 0;
-  const unsigned grid = unsigned((nrows + ROW_WARPS - 1) / ROW_WARPS);
-  int64_t nslots = 0;
-  DevBuf<int64_t> slot_ptr(nrows + 1);
-  {
-    DevBuf<int32_t> row_cnt(nrows);
-    A.row_cnt = row_cnt;
-    k_rows<false, false, true><<<grid, ROW_WARPS * 32, 0, st>>>(A);
-    ctx->launches++;
-    B2_CHECK_LAUNCH();
-    exclusive_scan_i32_to_i64(ctx, row_cnt, slot_ptr, nrows);
-    B2_CUDA(cudaMemcpyAsync(&nslots, slot_ptr.p + nrows, 8, cudaMemcpyDeviceToHost, st));
-    B2_CUDA(cudaStreamSynchronize(st));
-  }
-  DevBuf<int32_t> colind(nslots > 0 ? nslots : 1), kept(nrows);
-  DevBuf<double> nzval(nslots > 0 ? nslots : 1);
-  A.row_cnt = kept;
-  A.rowptr = slot_ptr;
-  A.colind = colind;
-  A.nzval = nzval;
-  if (thr > 0.0) k_rows<true, true, true><<<grid, ROW_WARPS * 32, 0, st>>>(A);
-  else k_rows<true, false, true><<<grid, ROW_WARPS * 32, 0, st>>>(A);
-  ctx->launches++;
-  B2_CHECK_LAUNCH();
-  int64_t nnz = nslots;
-  if (thr > 0.0) {
-    exclusive_scan_i32_to_i64(ctx, kept, out.rowptr, nrows);
-    B2_CUDA(cudaMemcpyAsync(&nnz, out.rowptr.p + nrows, 8, cudaMemcpyDeviceToHost, st));
-    B2_CUDA(cudaStreamSynchronize(st));
-    if (nnz != nslots) {
-      DevBuf<int32_t> ci_f(nnz > 0 ? nnz : 1);
-      DevBuf<double> nz_f(nnz > 0 ? nnz : 1);
-      k_compact_rows<<<unsigned((nrows * 32 + ROW_WARPS * 32 - 1) / (ROW_WARPS * 32)), ROW_WARPS * 32, 0, st>>>(
-          nrows, slot_ptr, out.rowptr, colind, nzval, ci_f, nz_f);
-      ctx->launches++;
-      B2_CHECK_LAUNCH();
-      B2_CUDA(cudaStreamSynchronize(st));
-      colind = std::move(ci_f);
-      nzval = std::move(nz_f);
-    }
-  } else {
-    out.rowptr = std::move(slot_ptr);
-  }
-  B2_CUDA(cudaStreamSynchronize(st));
-  out.nnz = nnz;
-  out.colind = std::move(colind);
-  out.nzval = std::move(nzval);
+  // the block's own phase times are folded into the patched build's timers by its caller
+  const double t_count = ctx->timers["h_build.count"], t_fill = ctx->timers["h_build.fill"],
+               t_thresh = ctx->timers["h_build.thresh"];
+  RowScanOut R;
+  run_row_scan<true>(ctx, A, nrows, thr, false, R);
+  ctx->timers["h_build.count"] = t_count;
+  ctx->timers["h_build.fill"] = t_fill;
+  ctx->timers["h_build.thresh"] = t_thresh;
+  out.nnz = R.nnz;
+  out.rowptr = std::move(R.rowptr);
+  out.colind = std::move(R.colind);
+  out.nzval = std::move(R.nzval);
 }
 }  // namespace
 

@@ -448,3 +448,36 @@ def test_fci_list_under_pair_rules_takes_the_scan_path(ctx):
     assert np.array_equal(rp, orp) and np.array_equal(ci, oci) and np.array_equal(nz, onz)
     srp, _, _ = port.Ham(sp.norb, sp.T, sp.V).hbuild(a, b, EPS)
     assert rp[-1] >= srp[-1]
+
+
+@pytest.mark.parametrize("mode", ["hits", "overflow", "off"])
+def test_hit_list_fill_equals_rescan_fill(ctx, mode, monkeypatch):
+    """General lists scan once: the count pass stores the connections it finds and the fill pass
+    evaluates them from the store; a store that turns out too small falls back to a second scan.
+    All three ways give the oracle's CSR, for the plain build, a row block and the patched build."""
+    sp, a, b = None, None, None
+    from helpers import generator_case
+    sp, a, b = generator_case("n2_cas10_s2500")
+    monkeypatch.setenv("B2CI_HBUILD_HITLIST_MIN", "1")
+    if mode == "overflow":
+        monkeypatch.setenv("B2CI_HBUILD_HITLIST_CAP", "100")
+    if mode == "off":
+        monkeypatch.setenv("B2CI_HBUILD_NO_HITLIST", "1")
+    ctx.upload_integrals(sp.norb, sp.T, sp.V)
+    h = port.Ham(sp.norb, sp.T, sp.V)
+    d = ctx.upload_dets(port.pack(a, b), 1)
+    for thr in (EPS, 0.0, 1e-2):
+        H = ctx.hbuild(d, thr)
+        assert ctx.timer_ms("h_build.hit_lists") == (1.0 if mode == "hits" else 0.0)
+        rp, ci, nz = H.download()
+        orp, oci, onz = h.hbuild(a, b, thr)
+        assert np.array_equal(rp, orp) and np.array_equal(ci, oci) and np.array_equal(nz, onz)
+        r0, r1 = 700, 1900
+        rpb, cib, nzb = ctx.hbuild(d, thr, (r0, r1)).download()
+        assert np.array_equal(rpb, orp[r0:r1 + 1] - orp[r0]) and np.array_equal(cib, oci[orp[r0]:orp[r1]])
+        assert np.array_equal(nzb, onz[orp[r0]:orp[r1]])
+        keep = np.sort(np.random.default_rng(2).choice(len(a), size=2000, replace=False))
+        d_old = ctx.upload_dets(port.pack(a[keep], b[keep]), 1)
+        Hp, _ = ctx.hbuild_patched(d_old, ctx.hbuild(d_old, thr), d, thr, 0.3)
+        prp, pci, pnz = Hp.download()
+        assert np.array_equal(prp, orp) and np.array_equal(pci, oci) and np.array_equal(pnz, onz)
