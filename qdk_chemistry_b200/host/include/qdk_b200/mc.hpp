@@ -106,6 +106,10 @@ struct CASRDMFunctor {
   }
 };
 
+// core determinants of an ASCI iteration (asci/iteration.hpp:62-100): indices in order of decreasing |c|
+std::vector<int64_t> select_core_indices(const std::vector<double>& X, bool fixed_core, size_t ncdets_max,
+                                         double core_selection_threshold);
+
 // ---- multi-GPU: one process per GPU. Call once per process before run(); the 128-byte id comes
 // from b2ci_comm_unique_id on rank 0 and is distributed by the caller (torch.distributed).
 void set_device(int device);

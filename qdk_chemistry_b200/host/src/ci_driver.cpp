@@ -473,6 +473,42 @@ void reorder_ci_on_alpha(std::vector<Det>& wfn, std::vector<double>& X, size_t n
   std::copy(x2.begin(), x2.end(), X.begin());
 }
 
+}  // namespace
+
+// Indices of the core determinants in order of decreasing |c| (ties: lower index first): the prefix
+// reorder_ci_on_coeff + the core-selection rule of asci_iter keep (asci/iteration.hpp:62-100;
+// fixed: the ncdets_max largest, percentage: the shortest prefix whose weight reaches the threshold).
+std::vector<int64_t> select_core_indices(const std::vector<double>& X, bool fixed_core, size_t ncdets_max,
+                                         double core_selection_threshold) {
+  const size_t n = X.size();
+  std::vector<int64_t> idx(n);
+  std::iota(idx.begin(), idx.end(), 0);
+  auto by_coeff = [&](int64_t i, int64_t j) {
+    const double ci = std::abs(X[size_t(i)]), cj = std::abs(X[size_t(j)]);
+    return ci > cj || (ci == cj && i < j);
+  };
+  size_t K = fixed_core ? std::min<size_t>(ncdets_max, n) : std::min<size_t>(n, 4096);
+  size_t nkeep = 0;
+  for (;;) {
+    if (K < n) std::nth_element(idx.begin(), idx.begin() + int64_t(K), idx.end(), by_coeff);
+    std::sort(idx.begin(), idx.begin() + int64_t(K), by_coeff);
+    if (fixed_core) { nkeep = K; break; }
+    double w = 0.0;
+    nkeep = 0;
+    bool reached = false;
+    for (size_t i = 0; i < K; ++i) {
+      w += X[size_t(idx[i])] * X[size_t(idx[i])];
+      nkeep++;
+      if (w >= core_selection_threshold) { reached = true; break; }
+    }
+    if (reached || K == n) break;
+    K = std::min(n, K * 4);
+  }
+  idx.resize(nkeep);
+  return idx;
+}
+
+namespace {
 struct WallTimer {  // host wall clock of one phase, accumulated into the run statistics
   const char* key;
   std::chrono::steady_clock::time_point t0 = std::chrono::steady_clock::now();
@@ -497,37 +533,11 @@ double asci_iter(CiSession& S, const AsciSettings& a, const McscfSettings& m, in
   // keeps a prefix; only that prefix is ever used, so it is found by selection (nth_element) and
   // sorted alone -- with ties broken by position, the same prefix and order as the stable full
   // sort (1.2 s of host time per iteration at 1e7 determinants otherwise).
-  std::vector<Det> core;
-  std::vector<double> core_X;
-  size_t nkeep = 0;
-  {
-    const size_t n = wfn.size();
-    std::vector<int64_t> idx(n);
-    std::iota(idx.begin(), idx.end(), 0);
-    auto by_coeff = [&](int64_t i, int64_t j) {
-      const double ci = std::abs(X[size_t(i)]), cj = std::abs(X[size_t(j)]);
-      return ci > cj || (ci == cj && i < j);
-    };
-    size_t K = a.fixed_core ? std::min<size_t>(size_t(a.ncdets_max), n) : std::min<size_t>(n, 4096);
-    for (;;) {
-      if (K < n) std::nth_element(idx.begin(), idx.begin() + int64_t(K), idx.end(), by_coeff);
-      std::sort(idx.begin(), idx.begin() + int64_t(K), by_coeff);
-      if (a.fixed_core) { nkeep = K; break; }
-      double w = 0.0;
-      nkeep = 0;
-      bool reached = false;
-      for (size_t i = 0; i < K; ++i) {
-        w += X[size_t(idx[i])] * X[size_t(idx[i])];
-        nkeep++;
-        if (w >= a.core_selection_threshold) { reached = true; break; }
-      }
-      if (reached || K == n) break;
-      K = std::min(n, K * 4);
-    }
-    core.resize(nkeep);
-    core_X.resize(nkeep);
-    for (size_t i = 0; i < nkeep; ++i) { core[i] = wfn[size_t(idx[i])]; core_X[i] = X[size_t(idx[i])]; }
-  }
+  const std::vector<int64_t> top = select_core_indices(X, a.fixed_core, size_t(a.ncdets_max), a.core_selection_threshold);
+  const size_t nkeep = top.size();
+  std::vector<Det> core(nkeep);
+  std::vector<double> core_X(nkeep);
+  for (size_t i = 0; i < nkeep; ++i) { core[i] = wfn[size_t(top[i])]; core_X[i] = X[size_t(top[i])]; }
   if (nkeep > 1) reorder_ci_on_alpha(core, core_X, nkeep);
   std::unordered_map<Det, double, DetHash> old;
   if (a.warm_start_davidson && !old_sorted) {

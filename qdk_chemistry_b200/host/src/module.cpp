@@ -402,6 +402,8 @@ PYBIND11_MODULE(_core, m) {
     io::write_rdms_binary(f, norb, o.data(), norb, t.data(), norb);
   });
 
+  amod.def("select_core_indices", &select_core_indices, py::arg("coefficients"), py::arg("fixed_core"),
+           py::arg("ncdets_max"), py::arg("core_selection_threshold"));
   amod.def("set_device", &set_device, py::arg("device"));
   amod.def("set_communicator", [](const py::bytes& id, int rank, int nranks) { set_communicator(std::string(id), rank, nranks); },
            py::arg("unique_id"), py::arg("rank"), py::arg("nranks"));

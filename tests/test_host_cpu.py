@@ -230,3 +230,23 @@ def test_fcidump_cpp_reads_the_reference_fixture():
     assert abs(T.sum() - (-1.095432762653e+02)) < 1e-9 and abs(V.sum() - 2.701609068389e+02) < 1e-9
     water = W.load_sparse_npz(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "h2o_ccpvdz.ints.npz"))
     assert np.array_equal(T, np.ravel(water.T)) and np.array_equal(V, np.ravel(water.V))
+
+
+def test_core_selection_equals_stable_full_sort():
+    """asci_iter's core set (iteration.hpp:62-100) is found by selection instead of the reference's
+    full sort; the prefix and its order must be those of a stable sort by |c| descending."""
+    from qdk_chemistry_b200 import _core
+    sel = _core.algorithms.select_core_indices
+    rng = np.random.default_rng(11)
+    for n in (1, 2, 37, 5000, 70000):
+        X = rng.normal(size=n) * np.exp(-rng.random(n) * 12)
+        X[rng.integers(0, n, size=n // 5)] = 0.125          # many exact ties
+        X /= np.linalg.norm(X)
+        order = np.argsort(-np.abs(X), kind="stable")
+        for k in (1, 100, 4096, 10 ** 6):
+            assert np.array_equal(sel(X, True, k, 0.0), order[:min(k, n)])
+        for thr in (1e-3, 0.5, 0.95, 0.999999, 1.0):
+            w = np.cumsum(X[order] ** 2)
+            reach = np.nonzero(w >= thr)[0]
+            nkeep = (reach[0] + 1) if len(reach) else n
+            assert np.array_equal(sel(X, False, 0, thr), order[:nkeep])
