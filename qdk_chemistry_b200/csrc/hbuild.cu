@@ -33,6 +33,13 @@ void iota_u32(b2ci_ctx* ctx, uint32_t* v, int64_t n);
 namespace {
 
 constexpr int ROW_WARPS = 8;  // warps (rows) per CTA
+#ifndef B2CI_ROWS_FLAT
+// general-list scan variant: walk 32 adjacent runs as one concatenated sequence. Bit-identical output
+// (parity tests green), but measured SLOWER on the N2 ASCI run to 1e6 determinants (count passes
+// 767 ms against 410-460 ms): the prefix / run-start bookkeeping costs more instructions than the
+// fuller lanes save at these run lengths. Kept for lists with very short runs; off by default.
+#define B2CI_ROWS_FLAT 0
+#endif
 
 __global__ void k_run_flags(const uint64_t* __restrict__ alpha, int64_t n,
                             int32_t* __restrict__ flag) {
@@ -252,16 +259,98 @@ k_rows(const RowArgs A) {
       }
     };
     const int64_t e0 = A.adj_ptr[r], e1 = A.adj_ptr[r + 1];
+#if B2CI_ROWS_FLAT
+    // The scan is bound by instruction issue (ncu: 75 % issue utilisation, 46k warp instructions per
+    // row at 2e5 determinants); with short adjacent runs one run per 32-lane step wastes lanes. In
+    // this variant the runs are taken 32 at a time -- adjacency entries and run bounds loaded by all lanes at once -- and their
+    // determinants are walked as ONE concatenated sequence, 32 positions per step, whatever run
+    // they belong to (run of a position: prefix sums of the run lengths + a bit mask of run starts).
+    for (int64_t eb = e0; eb < e1; eb += 32) {
+      const int nb = int(e1 - eb < 32 ? e1 - eb : 32);
+      uint32_t pk_l = 0;
+      int64_t ks_l = 0;
+      int32_t len_l = 0;
+      if (lane < nb) {
+        pk_l = A.adj[eb + lane];
+        ks_l = A.run_start[pk_l >> 2];
+        len_l = int32_t(A.run_start[(pk_l >> 2) + 1] - ks_l);
+      }
+      int32_t incl = len_l;
+#pragma unroll
+      for (int d = 1; d < 32; d <<= 1) {
+        const int32_t v = __shfl_up_sync(0xffffffffu, incl, d);
+        if (lane >= d) incl += v;
+      }
+      const int32_t off_l = incl - len_l;                       // first position of lane's run
+      const int32_t T = __shfl_sync(0xffffffffu, incl, 31);     // positions in this batch of runs
+      const int da_l = int(pk_l & 3u) * 2;
+      for (int32_t p0 = 0; p0 < T; p0 += 32) {
+        // run of the step's first position, then one more for every run start inside the step
+        const int tb = __popc(__ballot_sync(0xffffffffu, lane < nb && off_l <= p0)) - 1;
+        const int32_t rel = off_l - p0;
+        const unsigned sbit = (lane < nb && lane > tb && rel < 32) ? (1u << rel) : 0u;
+        const unsigned starts = __reduce_or_sync(0xffffffffu, sbit);
+        const int my_run = tb + __popc(starts & (0xFFFFFFFFu >> (31 - lane)));
+        const int64_t ks = __shfl_sync(0xffffffffu, ks_l, my_run);
+        const int32_t off = __shfl_sync(0xffffffffu, off_l, my_run);
+        const int da = __shfl_sync(0xffffffffu, da_l, my_run);
+        const int32_t p = p0 + lane;
+        const bool valid = p < T;
+        const int64_t j = ks + (p - off);
+        bool hit = false;
+        if (valid) hit = (da + __popcll(bi ^ A.beta[j])) <= 4;
+        const int nvalid = T - p0 < 32 ? T - p0 : 32;
+        const int64_t j_first = __shfl_sync(0xffffffffu, j, 0), j_last = __shfl_sync(0xffffffffu, j, nvalid - 1);
+        flush_group(j_first);
+        // beta-group members inside the step's index range: in one of its runs (alpha distance
+        // <= 2, found by the scan) they are stepped over; in a gap between two runs they have to
+        // come out between those runs' hits, so the step is then pushed run by run
+        bool gap = false;
+        while (nextj <= j_last) {
+          if (__ballot_sync(0xffffffffu, valid && j == nextj)) {
+            ++bpos;
+            nextj = bpos < bend ? int64_t(A.bgrp_mem[bpos]) : INT64_MAX;
+          } else {
+            gap = true;
+            break;
+          }
+        }
+        if (!gap) {
+          push(hit, j);
+        } else {
+          const int t_last = __shfl_sync(0xffffffffu, my_run, nvalid - 1);
+          for (int t = tb; t <= t_last; ++t) {
+            const bool mine = valid && my_run == t;
+            const unsigned mm = __ballot_sync(0xffffffffu, mine);
+            const int64_t jf = __shfl_sync(0xffffffffu, j, __ffs(mm) - 1);
+            flush_group(jf);
+            push(hit && mine, j);
+          }
+        }
+      }
+    }
+#else
     for (int64_t e = e0; e < e1; ++e) {
       const uint32_t pk = A.adj[e];
       const int da = int(pk & 3u) * 2;
       const int64_t ks = A.run_start[pk >> 2], ke = A.run_start[(pk >> 2) + 1];
       flush_group(ks);
-      for (int64_t j0 = ks; j0 < ke; j0 += 32) {
-        const int64_t j = j0 + lane;
-        bool hit = false;
-        if (j < ke) hit = (da + __popcll(bi ^ A.beta[j])) <= 4;
-        push(hit, j);
+      {
+        // the hot loop of a general build (876 steps per row at 2e5 determinants, 61 % of the kernel's
+        // instructions): 32-bit positions, one pointer, no bounds test in the full steps
+        const int32_t len = int32_t(ke - ks), j32 = int32_t(ks);
+        const uint64_t* __restrict__ bp = A.beta + ks + lane;
+        const int lim = 4 - da;
+        int32_t base = 0;
+        for (; base + 32 <= len; base += 32) {
+          const bool hit = __popcll(bi ^ __ldg(bp + base)) <= lim;
+          push(hit, j32 + base + lane);
+        }
+        if (base < len) {
+          bool hit = false;
+          if (base + lane < len) hit = __popcll(bi ^ __ldg(bp + base)) <= lim;
+          push(hit, j32 + base + lane);
+        }
       }
       // group members inside this run are at alpha distance <= 2: already covered by the scan
       while (nextj < ke) {
@@ -273,6 +362,7 @@ k_rows(const RowArgs A) {
         if (nin < 32) break;
       }
     }
+#endif
     flush_group(INT64_MAX);
     if (qn > 0) {
       if (keep_hits) store_hits(A, row, q, qn, lane, prev_chunk);
