@@ -149,6 +149,12 @@ def cpu_sample(sp, budget_rows_frac=None, target_seconds=12.0):
     out = {}
     if use_ref:
         hg = ref.HamGen(sp.norb, sp.T, sp.V)
+        # all the host threads this process may use: torchrun exports OMP_NUM_THREADS=1 to its
+        # workers, which would leave the reference arm on one core at N > 1
+        try:
+            ref.set_num_threads(len(os.sched_getaffinity(0)))
+        except (AttributeError, OSError):
+            pass
         cores = ref.num_threads()
         kind = "reference"
 
