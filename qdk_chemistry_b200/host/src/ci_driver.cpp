@@ -313,10 +313,11 @@ class CiSession {
     o.sort_output = 1;  // spin_comparator order, made on the device
     int64_t cap = ndets_max + ncore + 4096, n_out = 0;
     std::vector<Det> out;
+    double stats[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     for (;;) {
       out.resize(size_t(cap));
       const int rc = b2ci_asci_search(ctx_, &o, reinterpret_cast<const uint64_t*>(core), 2, coeffs, ncore, E0,
-                                      reinterpret_cast<uint64_t*>(out.data()), cap, &n_out, nullptr);
+                                      reinterpret_cast<uint64_t*>(out.data()), cap, &n_out, stats);
       if (rc == 4 && n_out > cap) {  // ties at the cut exceed the capacity: retry with the exact size
         cap = n_out;
         continue;
@@ -329,6 +330,9 @@ class CiSession {
     add_timer("asci_sort_acc_ms", {"asci_search.SORT_ACC_DUR"});
     add_timer("asci_topk_ms", {"asci_search.TOPK_DUR"});
     g_stats["asci_last_ncore"] = double(ncore);
+    g_stats["asci_contributions"] += stats[0];       // (determinant, c*h) records generated, all searches
+    g_stats["asci_unique_candidates"] += stats[1];   // after sort + accumulate
+    g_stats["asci_last_key_partitions"] = stats[5];
     g_stats["asci_search_calls"] += 1.0;
     out.resize(size_t(n_out));
     return out;

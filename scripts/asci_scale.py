@@ -42,6 +42,12 @@ except Exception as e:  # report what failed and the statistics so far
 out["wall_s"] = time.perf_counter() - t0
 out.update(alg.last_run_stats())
 out["world"] = world
+# candidates/s of the generator and the bandwidth of the radix sort (12 B per record and
+# pass read + written, 2 * ceil(norb / 8) passes), from the device timers of all searches of the run
+if out.get("asci_contributions") and out.get("asci_pair_ms"):
+    npass = 2 * ((sp.norb + 7) // 8)
+    out["asci_candidates_per_s"] = out["asci_contributions"] / (out["asci_pair_ms"] * 1e-3)
+    out["asci_sort_accumulate_GBps"] = out["asci_contributions"] * 24.0 * npass / (out["asci_sort_acc_ms"] * 1e-3) / 1e9
 if rank == 0:
     print(json.dumps(out))
 if world > 1:
