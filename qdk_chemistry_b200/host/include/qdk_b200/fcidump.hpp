@@ -7,6 +7,7 @@
 #include <cstddef>
 #include <cstdint>
 #include <string>
+#include <utility>
 #include <vector>
 
 namespace qdk_b200::io {
@@ -35,5 +36,21 @@ void write_fcidump(const std::string& fname, const FCIDumpHeader& header, const 
 void read_rdms_binary(const std::string& fname, size_t norb, double* ORDM, size_t LDD1, double* TRDM, size_t LDD2);
 void write_rdms_binary(const std::string& fname, size_t norb, const double* ORDM, size_t LDD1, const double* TRDM,
                        size_t LDD2);
+
+// ---- text wavefunction files (external/macis/include/macis/wavefunction_io.hpp:22-116):
+//   <nstates> <norb> <nalpha> <nbeta>
+//   <coefficient, scientific, 16 digits, width 30> <canonical string: one of 0 u d 2 per orbital>
+// Determinants are (alpha, beta) occupation words, bit p = orbital p, as everywhere on this path.
+std::string to_canonical_string(uint64_t alpha, uint64_t beta, size_t norb);      // sd_operations.hpp:478-498
+std::pair<uint64_t, uint64_t> from_canonical_string(const std::string& str);      // sd_operations.hpp:508-525
+struct WavefunctionFile {
+  size_t nstates = 0, norb = 0, nalpha = 0, nbeta = 0;  // header (informational, like the reference)
+  std::vector<uint64_t> alpha, beta;
+  std::vector<double> coeffs;
+};
+WavefunctionFile read_wavefunction(const std::string& fname);
+// throws "Invalid Wave Function Dimensions" on a size mismatch; writes nothing for an empty list
+void write_wavefunction(const std::string& fname, size_t norb, const std::vector<uint64_t>& alpha,
+                        const std::vector<uint64_t>& beta, const std::vector<double>& coeffs);
 
 }  // namespace qdk_b200::io

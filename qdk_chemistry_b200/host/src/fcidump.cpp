@@ -275,4 +275,61 @@ void write_rdms_binary(const std::string& fname, size_t norb, const double* ORDM
   out.write(reinterpret_cast<const char*>(raw.data()), std::streamsize(n2 * n2 * sizeof(double)));
 }
 
+std::string to_canonical_string(uint64_t alpha, uint64_t beta, size_t norb) {
+  std::string out;
+  out.reserve(norb);
+  for (size_t i = 0; i < norb && i < 64; ++i) {
+    const bool a = (alpha >> i) & 1u, b = (beta >> i) & 1u;
+    out.push_back(a && b ? '2' : a ? 'u' : b ? 'd' : '0');
+  }
+  return out;
+}
+
+std::pair<uint64_t, uint64_t> from_canonical_string(const std::string& str) {
+  uint64_t alpha = 0, beta = 0;
+  for (size_t i = 0; i < str.size() && i < 64; ++i) {
+    if (str[i] == '2') { alpha |= uint64_t(1) << i; beta |= uint64_t(1) << i; }
+    else if (str[i] == 'u') alpha |= uint64_t(1) << i;
+    else if (str[i] == 'd') beta |= uint64_t(1) << i;
+  }
+  return {alpha, beta};
+}
+
+WavefunctionFile read_wavefunction(const std::string& fname) {
+  std::ifstream file(fname);
+  if (!file.is_open()) throw std::runtime_error("Could not open file: " + fname);
+  WavefunctionFile w;
+  std::string line;
+  if (std::getline(file, line)) {
+    std::istringstream ss(line);
+    ss >> w.nstates >> w.norb >> w.nalpha >> w.nbeta;
+  }
+  w.alpha.reserve(w.nstates);
+  w.beta.reserve(w.nstates);
+  w.coeffs.reserve(w.nstates);
+  while (std::getline(file, line)) {
+    std::istringstream ss(line);
+    std::string c, d;
+    if (!(ss >> c >> d)) continue;
+    const auto ab = from_canonical_string(d);
+    w.alpha.push_back(ab.first);
+    w.beta.push_back(ab.second);
+    w.coeffs.push_back(std::stod(c));
+  }
+  return w;
+}
+
+void write_wavefunction(const std::string& fname, size_t norb, const std::vector<uint64_t>& alpha,
+                        const std::vector<uint64_t>& beta, const std::vector<double>& coeffs) {
+  if (alpha.size() != coeffs.size() || beta.size() != coeffs.size())
+    throw std::runtime_error("Invalid Wave Function Dimensions");
+  if (coeffs.empty()) return;
+  std::FILE* fh = std::fopen(fname.c_str(), "w");
+  if (!fh) throw std::runtime_error("Could not open file: " + fname);
+  std::fprintf(fh, "%zu %zu %d %d\n", coeffs.size(), norb, __builtin_popcountll(alpha[0]), __builtin_popcountll(beta[0]));
+  for (size_t i = 0; i < coeffs.size(); ++i)
+    std::fprintf(fh, "%30.16e %s \n", coeffs[i], to_canonical_string(alpha[i], beta[i], norb).c_str());
+  std::fclose(fh);
+}
+
 }  // namespace qdk_b200::io

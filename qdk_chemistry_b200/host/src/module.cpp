@@ -402,6 +402,36 @@ PYBIND11_MODULE(_core, m) {
     io::write_rdms_binary(f, norb, o.data(), norb, t.data(), norb);
   });
 
+  io.def("to_canonical_string", &io::to_canonical_string, py::arg("alpha"), py::arg("beta"), py::arg("norb"));
+  io.def("from_canonical_string", &io::from_canonical_string, py::arg("string"));
+  io.def("read_wavefunction", [](const std::string& f) {
+    const io::WavefunctionFile w = io::read_wavefunction(f);
+    auto u64 = [](const std::vector<uint64_t>& v) {
+      py::array_t<uint64_t> a{py::ssize_t(v.size())};
+      std::memcpy(a.mutable_data(), v.data(), v.size() * 8);
+      return a;
+    };
+    py::array_t<double> c{py::ssize_t(w.coeffs.size())};
+    std::memcpy(c.mutable_data(), w.coeffs.data(), w.coeffs.size() * 8);
+    return py::make_tuple(u64(w.alpha), u64(w.beta), c, py::make_tuple(w.nstates, w.norb, w.nalpha, w.nbeta));
+  });
+  io.def("write_wavefunction", [](const std::string& f, size_t norb, const std::vector<uint64_t>& a,
+                                  const std::vector<uint64_t>& b, const std::vector<double>& c) {
+    io::write_wavefunction(f, norb, a, b, c);
+  }, py::arg("fname"), py::arg("norb"), py::arg("alpha"), py::arg("beta"), py::arg("coeffs"));
+  // Hamiltonian of an FCIDUMP file (what pymacis users start from): (Hamiltonian, nalpha, nbeta)
+  io.def("hamiltonian_from_fcidump", [](const std::string& f) {
+    const io::FCIDumpHeader h = io::fcidump_read_header(f);
+    if (h.norb == 0) throw std::runtime_error("NORB not found or is zero in FCIDUMP header");
+    const size_t n = h.norb;
+    std::vector<double> T(n * n), V(n * n * n * n);
+    double core = 0.;
+    io::read_fcidump_all(f, T.data(), n, V.data(), n, core);
+    auto ham = std::make_shared<data::Hamiltonian>(n, std::move(T), std::move(V), core);
+    const int na = (int(h.nelec) + h.ms2) / 2, nb = (int(h.nelec) - h.ms2) / 2;
+    return py::make_tuple(ham, na, nb);
+  });
+
   amod.def("select_core_indices", &select_core_indices, py::arg("coefficients"), py::arg("fixed_core"),
            py::arg("ncdets_max"), py::arg("core_selection_threshold"));
   amod.def("set_device", &set_device, py::arg("device"));
