@@ -140,3 +140,42 @@ def test_entropies_full_ci_vector_properties(ctx):
     assert np.abs(s2 - s2.T).max() == 0 and np.all(np.diag(s2) == 0) and mi.min() > -1e-12
     H.free()
     dets.free()
+
+
+def test_wfn128_hbuild_rdms_entropies_match_reference_golden():
+    """36 orbitals, wfn_t<128> words: CSR fingerprints (all three generators), RDMs and orbital
+    entropies against data made with the compiled reference's 128-bit instantiation
+    (tests/golden/make_golden_wide_props.py)."""
+    import json
+    import os
+    from helpers import EPS, check_generator_golden
+    g = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+    z, props = np.load(os.path.join(g, "wide36_golden.npz")), np.load(os.path.join(g, "wide36_props.npz"))
+    with open(os.path.join(g, "wide36_props.json")) as fh:
+        meta = json.load(fh)
+    sp = W.config("wide36")
+    a, b = z["run_dets"][:, 0].copy(), z["run_dets"][:, 1].copy()
+    o = port.spin_sort_order(a, b)
+    a, b, C = a[o], b[o], z["run_C"][o]
+    c = device.Context(0)
+    try:
+        c.upload_integrals(sp.norb, sp.T, sp.V)
+        d = c.upload_dets(port.pack(a, b, 128), 2)
+        for gen, rec in meta["csr"].items():
+            c.set_hamiltonian_generator(gen)
+            check_generator_golden(rec, *c.hbuild(d, EPS).download())
+        c.set_hamiltonian_generator("")
+        aa, bb, aaaa, bbbb, aabb = c.form_rdms(d, C, spin_dep=True)
+        ordm, trdm = c.form_rdms(d, C, spin_dep=False)
+        for got, key in ((aa, "ordm_aa"), (bb, "ordm_bb"), (ordm, "ordm")):
+            assert np.abs(got - props[key]).max() < 1e-12
+        step = meta["sample_step"]
+        for got, key in ((aaaa, "aaaa"), (bbbb, "bbbb"), (aabb, "aabb"), (trdm, "trdm")):
+            flat = np.asarray(got).reshape(-1, order="F")
+            assert np.abs(flat[::step] - props[f"{key}_sample"]).max() < 1e-12
+            assert abs(flat.sum() - meta[f"{key}_sum"]) < 1e-9
+        s1, s2, mi = c.form_entropies(d, C)
+        assert np.abs(s1 - props["s1"]).max() < 1e-11 and np.abs(s2 - props["s2"]).max() < 1e-11
+        assert np.abs(mi - props["mi"]).max() < 1e-11
+    finally:
+        c.close()

@@ -323,3 +323,35 @@ def test_port_grow_with_rot_matches_compiled_reference(water):
         # the integrals were rotated: trace of T changes, the Frobenius norm of V does not
         assert not np.allclose(h.T, np.ravel(water.T))
         assert abs(np.linalg.norm(h.V) - np.linalg.norm(np.ravel(water.V))) < 1e-9
+
+
+def test_port_on_wfn128_determinants_matches_compiled_reference():
+    """H build (three generators, bit-exact fingerprints), RDMs and orbital entropies of a
+    36-orbital wavefunction made with the reference's wfn_t<128> instantiation
+    (tests/golden/make_golden_wide_props.py)."""
+    import json
+    from helpers import check_generator_golden
+    g = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+    z, props = np.load(os.path.join(g, "wide36_golden.npz")), np.load(os.path.join(g, "wide36_props.npz"))
+    with open(os.path.join(g, "wide36_props.json")) as fh:
+        meta = json.load(fh)
+    sp = W.config("wide36")
+    a, b = z["run_dets"][:, 0].copy(), z["run_dets"][:, 1].copy()
+    o = port.spin_sort_order(a, b)
+    a, b, C = a[o], b[o], z["run_C"][o]
+    assert len(a) == meta["n"] and (a >> np.uint64(32)).any()
+    h = port.Ham(sp.norb, sp.T, sp.V)
+    for gen, rec in meta["csr"].items():
+        check_generator_golden(rec, *h.hbuild(a, b, EPS, generator=gen))
+    aa, bb, aaaa, bbbb, aabb = port.form_rdms(sp.norb, a, b, C, spin_dep=True)
+    ordm, trdm = port.form_rdms(sp.norb, a, b, C, spin_dep=False)
+    for got, key in ((aa, "ordm_aa"), (bb, "ordm_bb"), (ordm, "ordm")):
+        assert np.abs(got - props[key]).max() < 1e-14
+    step = meta["sample_step"]
+    for got, key in ((aaaa, "aaaa"), (bbbb, "bbbb"), (aabb, "aabb"), (trdm, "trdm")):
+        flat = np.asarray(got).reshape(-1, order="F")
+        assert np.abs(flat[::step] - props[f"{key}_sample"]).max() < 1e-14
+        assert abs(flat.sum() - meta[f"{key}_sum"]) < 1e-11 and abs((flat * flat).sum() - meta[f"{key}_sumsq"]) < 1e-11
+    s1, s2, mi = port.form_entropies(sp.norb, a, b, C)
+    assert np.abs(s1 - props["s1"]).max() < 1e-12 and np.abs(s2 - props["s2"]).max() < 1e-12
+    assert np.abs(mi - props["mi"]).max() < 1e-12
