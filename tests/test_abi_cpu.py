@@ -102,3 +102,59 @@ def test_host_lowest_eigenpair_solver():
             assert abs(lam - w[0]) <= 1e-13 * scale
             assert np.linalg.norm(A @ v - lam * v) <= 1e-12 * scale
             assert abs(np.linalg.norm(v) - 1.0) < 1e-14
+
+
+def test_water_known_answers_of_the_reference_matrix_element_tests(water):
+    """external/macis/tests/double_loop.cxx:59-195 on the water / cc-pVDZ integrals, evaluated with
+    the oracle port AND with the product's own __host__ __device__ Slater-Condon code on the host:
+    HF energy, excited diagonals, Brillouin zeros + hermiticity, MP2 from the same integrals."""
+    n, nocc = water.norb, 5
+    T = np.asarray(water.T).reshape(n, n, order="F")
+    V = np.asarray(water.V).reshape(n, n, n, n, order="F")
+    h = port.Ham(n, water.T, water.V)
+    dev = lambda ba, bb, ka, kb: device.host_matrix_element(n, water.T, water.V, ba, bb, ka, kb)
+    hf = (1 << nocc) - 1
+    text_tol = 1e-6      # testing::ascii_text_tolerance (FCIDUMP text precision)
+    for me in (h.matrix_element, dev):
+        EHF = me(hf, hf, hf, hf)
+        assert abs(EHF + water.core_energy - (-76.0267803489191)) < text_tol
+        s = hf ^ 1 ^ (1 << nocc)                                  # alpha 0 -> nocc
+        assert abs(me(s, hf, s, hf) - (-6.488097259228e+01)) < text_tol
+        d = s ^ 2 ^ (1 << (nocc + 1))                             # same-spin double
+        assert abs(me(d, hf, d, hf) - (-6.314093508151e+01)) < text_tol
+        sb = hf ^ 2 ^ (1 << (nocc + 1))                           # opposite-spin double: alpha 0->5, beta 1->6
+        assert abs(me(s, sb, s, sb) - (-6.304547887231e+01)) < text_tol
+        for i in range(nocc):                                     # Brillouin + hermiticity
+            for a in range(nocc, n):
+                x = hf ^ (1 << i) ^ (1 << a)
+                e1, e2 = me(hf, hf, x, hf), me(x, hf, hf, hf)
+                assert abs(e1) < text_tol and abs(e1 - e2) < 1e-12
+                e1, e2 = me(hf, hf, hf, x), me(hf, x, hf, hf)
+                assert abs(e1) < text_tol and abs(e1 - e2) < 1e-12
+    # MP2 (double_loop.cxx:142-195) needs only the integrals: a check of the (pq|rs) index convention
+    eps = np.array([T[p, p] + sum(2 * V[p, p, i, i] - V[p, i, i, p] for i in range(nocc)) for p in range(n)])
+    emp2 = 0.0
+    for i in range(nocc):
+        for a in range(nocc, n):
+            for j in range(nocc):
+                for b in range(nocc, n):
+                    emp2 -= V[a, i, b, j] * (2 * V[a, i, b, j] - V[b, i, a, j]) / (eps[a] + eps[b] - eps[i] - eps[j])
+    assert abs(emp2 - (-0.203989305096243)) < text_tol
+
+
+def test_fast_diagonals_of_the_search_equal_full_diagonals(water):
+    """fast_diag_single / _ss_double / _os_double (fast_diagonals.ipp:51-127; double_loop.cxx:65-112 asserts
+    equality with matrix_element to 1e-12): every candidate of an ASCI search from the HF determinant
+    carries E0 - <Q|H|Q> computed the fast way."""
+    n = water.norb
+    h = port.Ham(n, water.T, water.V)
+    hf = np.array([31], dtype=np.uint64)
+    E0 = -80.0
+    ka, kb, cm, hd = h.asci_candidates(hf, hf, np.array([1.0]), E0, h_el_tol=1e-10)
+    assert len(ka) > 1000
+    real = np.nonzero(np.isfinite(cm))[0]          # the core determinant itself carries the inf sentinel
+    assert len(real) == len(ka) - 1
+    for k in np.random.default_rng(3).choice(real, 400, replace=False):
+        full = h.matrix_element(ka[k], kb[k], ka[k], kb[k])
+        assert abs((E0 - hd[k]) - full) < 1e-11
+        assert device.host_matrix_element(n, water.T, water.V, ka[k], kb[k], ka[k], kb[k]) == full
