@@ -355,3 +355,22 @@ def test_port_on_wfn128_determinants_matches_compiled_reference():
     s1, s2, mi = port.form_entropies(sp.norb, a, b, C)
     assert np.abs(s1 - props["s1"]).max() < 1e-12 and np.abs(s2 - props["s2"]).max() < 1e-12
     assert np.abs(mi - props["mi"]).max() < 1e-12
+
+
+def _backoff_cases():
+    import json
+    with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "backoff_meta.json")) as fh:
+        return json.load(fh)
+
+
+@pytest.mark.parametrize("case", ["fractional_grow_factor", "forced_backoff", "minimum_grow_factor", "normal_growth",
+                                  "taper"])
+def test_port_growth_backoff_scenarios_match_compiled_reference(water, case):
+    """external/macis/tests/asci.cxx:577-733 (fractional grow factor, forced back-off, minimum grow factor,
+    normal growth) plus a tapered run: size (ties at the cut included) and energy of asci_grow as the
+    compiled reference produces them (tests/golden/make_golden_backoff.py)."""
+    m = _backoff_cases()[case]
+    kw = dict(m["settings"])
+    kw["core_selection_strategy"] = "fixed" if kw["core_selection_strategy"] == 0 else "percentage"
+    E, a, b, X = port.asci_run(port.Ham(water.norb, water.T, water.V), 5, 5, refine=False, **kw)
+    assert len(a) == m["n"] and abs(E - m["E"]) < 1e-8 and abs(X @ X - 1) < 1e-12
