@@ -20,6 +20,11 @@ CASES = {
     "minimum_grow_factor": dict(grow_factor=10.0, ntdets_max=1000, ntdets_min=5, ncdets_max=5, core_selection_strategy=0),
     "normal_growth": dict(grow_factor=8.0, ntdets_max=1000, ntdets_min=100, ncdets_max=1000, core_selection_strategy=0),
     "taper": dict(grow_factor=8.0, taper_grow_factor=2.0, ntdets_max=3000, ntdets_min=100, core_selection_strategy=0),
+    # core-selection strategies (asci.cxx:736-840)
+    "fixed_core_5000": dict(ntdets_max=5000, ncdets_max=100, core_selection_strategy=0),
+    "percentage_core_5000": dict(ntdets_max=5000, ncdets_max=100, core_selection_strategy=1, core_selection_threshold=0.95),
+    "percentage_70": dict(ntdets_max=2000, core_selection_strategy=1, core_selection_threshold=0.7),
+    "percentage_99": dict(ntdets_max=2000, core_selection_strategy=1, core_selection_threshold=0.99),
 }
 meta = {}
 for name, kw in CASES.items():

@@ -364,13 +364,18 @@ def _backoff_cases():
 
 
 @pytest.mark.parametrize("case", ["fractional_grow_factor", "forced_backoff", "minimum_grow_factor", "normal_growth",
-                                  "taper"])
+                                  "taper", "fixed_core_5000", "percentage_core_5000", "percentage_70", "percentage_99"])
 def test_port_growth_backoff_scenarios_match_compiled_reference(water, case):
     """external/macis/tests/asci.cxx:577-733 (fractional grow factor, forced back-off, minimum grow factor,
-    normal growth) plus a tapered run: size (ties at the cut included) and energy of asci_grow as the
-    compiled reference produces them (tests/golden/make_golden_backoff.py)."""
+    normal growth), a tapered run and the core-selection strategies of :736-840: size (ties at the cut
+    included) and energy of asci_grow as the compiled reference produces them
+    (tests/golden/make_golden_backoff.py)."""
     m = _backoff_cases()[case]
     kw = dict(m["settings"])
     kw["core_selection_strategy"] = "fixed" if kw["core_selection_strategy"] == 0 else "percentage"
     E, a, b, X = port.asci_run(port.Ham(water.norb, water.T, water.V), 5, 5, refine=False, **kw)
-    assert len(a) == m["n"] and abs(E - m["E"]) < 1e-8 and abs(X @ X - 1) < 1e-12
+    # percentage_99: the 99 % weight cut falls between two determinants of equal |c| (spin-flip partners);
+    # the reference's unstable std::sort (determinant_sort.hpp:51-52) and the port's stable order keep
+    # different partners in the core, a 5e-7 Eh effect
+    tol = 1e-5 if case == "percentage_99" else 1e-8
+    assert len(a) == m["n"] and abs(E - m["E"]) < tol and abs(X @ X - 1) < 1e-12
