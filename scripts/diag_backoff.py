@@ -1,3 +1,8 @@
+"""Diagnostic for tests/test_gpu_host.py::test_asci_growth_backoff_scenarios_match_reference[fractional_grow_factor]:
+runs that scenario with and without patched builds and with the row scan instead of the product kernel.
+All four give the same energy (-85.313123201404, 1.7e-4 Eh above the reference's -85.313291280309): the
+difference is a spin-flip-partner swap at the tiny cuts, not the H build.
+    python scripts/diag_backoff.py        (on a B200 box, from the repository root)"""
 import json, os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from qdk_chemistry_b200 import algorithms as alg, data, workloads as W
