@@ -158,3 +158,14 @@ def test_fast_diagonals_of_the_search_equal_full_diagonals(water):
         full = h.matrix_element(ka[k], kb[k], ka[k], kb[k])
         assert abs((E0 - hd[k]) - full) < 1e-11
         assert device.host_matrix_element(n, water.T, water.V, ka[k], kb[k], ka[k], kb[k]) == full
+
+
+def test_determinant_width_dispatch():
+    """dispatch_by_norb (macis_base.hpp:80-100, cpp/tests/test_macis_dispatch.cpp:37-49): wfn_t<64> below 32
+    orbitals, wfn_t<128> below 64; wider ladders are not instantiated by this build and say so."""
+    f = device.words_per_det_for_norb
+    assert [f(n) for n in (1, 12, 31)] == [1, 1, 1]
+    assert [f(n) for n in (32, 36, 63)] == [2, 2, 2]
+    for n in (64, 127, 2049):
+        with pytest.raises(ValueError, match="wfn_t<256"):
+            f(n)
