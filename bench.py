@@ -113,6 +113,32 @@ class ClockSampler:
                 "samples": len(sm)}
 
 
+def asci_leg(ntdets=100000):
+    """BASELINE configs[3] workload through the plugin API: N2-like ASCI(14e,26o) grown from the HF determinant
+    to 1e5 determinants (search + H build + Davidson per iteration). Reported next to the headline, never part
+    of it. The unmodified reference ends this growth at E = -21.321911887616803 after 19.2 s on 8 CPU threads
+    (profiles/r01_reference_cpu_asci_n2_14e26o.json)."""
+    from qdk_chemistry_b200 import algorithms as alg, data
+    from qdk_chemistry_b200 import workloads as W
+    sp = W.config("n2_asci26")
+    ham = data.Hamiltonian(sp.T, sp.V, sp.core_energy)
+    calc = alg.create("multi_configuration_calculator", "b200_asci", ntdets_max=int(ntdets), max_refine_iter=0,
+                      ci_residual_tolerance=1e-8)
+    t0 = time.perf_counter()
+    E, w = calc.run(ham, sp.nalpha, sp.nbeta)
+    wall = time.perf_counter() - t0
+    st = alg.last_run_stats()
+    ref_E = -21.321911887616803
+    return {"config": "BASELINE configs[3] workload: N2-like ASCI(14e,26o) grown from HF to 1e5 determinants through "
+                      "the plugin API (wall time includes creating the plugin's CUDA context)",
+            "ndets": int(w.size()), "E": E - sp.core_energy, "E_minus_reference": (E - sp.core_energy) - ref_E,
+            "reference_cpu_seconds_8_threads": 19.2, "wall_s": wall,
+            "asci_iterations": st.get("asci_iterations"), "nnz": st.get("nnz_local"),
+            "h_build_ms": st.get("h_build_ms"), "asci_search_ms": st.get("asci_search_ms"),
+            "davidson_ms": (st.get("davidson_sigma_ms") or 0.0) + (st.get("davidson_other_ms") or 0.0),
+            "davidson_iterations": st.get("davidson_iterations")}
+
+
 def fci_workload(name):
     from qdk_chemistry_b200 import workloads as W
     sp = W.config(name)
@@ -430,6 +456,15 @@ def run_b200(args):
             "e2e_nnz_per_s": a["nnz_total"] / (a["e2e_ms"] * 1e-3), "e2e_ms": a["e2e_ms"],
             "davidson": a.get("davidson")}}
 
+    # configs[3] beside the headline (single GPU only; reported, never required)
+    if args.also and world == 1 and not args.no_asci:
+        try:
+            asci = asci_leg()
+        except Exception as e:
+            asci = {"error": repr(e)[:300]}
+        also = dict(also or {})
+        also["n2_asci26_1e5"] = asci
+
     cpu = None
     if rank == 0 and world == 1 and args.cpu_seconds > 0:
         try:
@@ -501,6 +536,8 @@ def main():
                     choices=["hubbard_4x3", "cr2_cas12", "n2_cas10", "small_cas8", "hubbard_4x2"])
     ap.add_argument("--max-m", type=int, default=100, dest="max_m")
     ap.add_argument("--no-davidson", action="store_false", dest="davidson")
+    ap.add_argument("--no-asci", action="store_true", dest="no_asci",
+                    help="skip the ASCI (BASELINE configs[3]) leg reported under 'also'")
     ap.add_argument("--no-also", action="store_false", dest="also",
                     help="skip the secondary hubbard_4x3 measurement")
     ap.add_argument("--cpu-seconds", type=float, default=12.0, dest="cpu_seconds",
