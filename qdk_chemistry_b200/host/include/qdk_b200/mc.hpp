@@ -106,6 +106,13 @@ struct CASRDMFunctor {
   }
 };
 
+// CIS / CISD determinant spaces of a reference determinant, in the reference's generation order
+// (sd_operations.hpp:60-383: generate_cis_hilbert_space, generate_cisd_hilbert_space): the reference itself,
+// alpha singles, beta singles, [alpha doubles, beta doubles, alpha single x beta single]; inside a spin the
+// virtual index runs outermost. (alpha, beta) occupation words, bit p = orbital p.
+std::vector<std::pair<uint64_t, uint64_t>> generate_cis_hilbert_space(size_t norb, uint64_t alpha, uint64_t beta);
+std::vector<std::pair<uint64_t, uint64_t>> generate_cisd_hilbert_space(size_t norb, uint64_t alpha, uint64_t beta);
+
 // core determinants of an ASCI iteration (asci/iteration.hpp:62-100): indices in order of decreasing |c|
 std::vector<int64_t> select_core_indices(const std::vector<double>& X, bool fixed_core, size_t ncdets_max,
                                          double core_selection_threshold);

@@ -479,6 +479,51 @@ void reorder_ci_on_alpha(std::vector<Det>& wfn, std::vector<double>& X, size_t n
 
 }  // namespace
 
+namespace {
+void occ_vir(size_t norb, uint64_t s, std::vector<unsigned>& occ, std::vector<unsigned>& vir) {
+  occ.clear();
+  vir.clear();
+  for (unsigned p = 0; p < norb && p < 64; ++p) ((s >> p) & 1u ? occ : vir).push_back(p);
+}
+std::vector<uint64_t> spin_singles(size_t norb, uint64_t s) {  // append_singles, sd_operations.hpp:60-75
+  std::vector<unsigned> occ, vir;
+  occ_vir(norb, s, occ, vir);
+  std::vector<uint64_t> out;
+  out.reserve(occ.size() * vir.size());
+  for (unsigned a : vir)
+    for (unsigned i : occ) out.push_back(s ^ (uint64_t(1) << i) ^ (uint64_t(1) << a));
+  return out;
+}
+std::vector<uint64_t> spin_doubles(size_t norb, uint64_t s) {  // append_doubles, sd_operations.hpp:77-98
+  std::vector<unsigned> occ, vir;
+  occ_vir(norb, s, occ, vir);
+  std::vector<uint64_t> out;
+  for (size_t a = 0; a < vir.size(); ++a)
+    for (size_t i = 0; i < occ.size(); ++i)
+      for (size_t b = a + 1; b < vir.size(); ++b)
+        for (size_t j = i + 1; j < occ.size(); ++j)
+          out.push_back(s ^ (uint64_t(1) << occ[i]) ^ (uint64_t(1) << occ[j]) ^ (uint64_t(1) << vir[a]) ^
+                        (uint64_t(1) << vir[b]));
+  return out;
+}
+}  // namespace
+
+std::vector<std::pair<uint64_t, uint64_t>> generate_cis_hilbert_space(size_t norb, uint64_t alpha, uint64_t beta) {
+  std::vector<std::pair<uint64_t, uint64_t>> dets{{alpha, beta}};
+  for (uint64_t a : spin_singles(norb, alpha)) dets.emplace_back(a, beta);
+  for (uint64_t b : spin_singles(norb, beta)) dets.emplace_back(alpha, b);
+  return dets;
+}
+std::vector<std::pair<uint64_t, uint64_t>> generate_cisd_hilbert_space(size_t norb, uint64_t alpha, uint64_t beta) {
+  const std::vector<uint64_t> sa = spin_singles(norb, alpha), sb = spin_singles(norb, beta);
+  std::vector<std::pair<uint64_t, uint64_t>> dets = generate_cis_hilbert_space(norb, alpha, beta);
+  for (uint64_t a : spin_doubles(norb, alpha)) dets.emplace_back(a, beta);
+  for (uint64_t b : spin_doubles(norb, beta)) dets.emplace_back(alpha, b);
+  for (uint64_t a : sa)
+    for (uint64_t b : sb) dets.emplace_back(a, b);
+  return dets;
+}
+
 // Indices of the core determinants in order of decreasing |c| (ties: lower index first): the prefix
 // reorder_ci_on_coeff + the core-selection rule of asci_iter keep (asci/iteration.hpp:62-100;
 // fixed: the ncdets_max largest, percentage: the shortest prefix whose weight reaches the threshold).

@@ -432,6 +432,18 @@ PYBIND11_MODULE(_core, m) {
     return py::make_tuple(ham, na, nb);
   });
 
+  auto det_array = [](const std::vector<std::pair<uint64_t, uint64_t>>& d) {
+    py::array_t<uint64_t> a({py::ssize_t(d.size()), py::ssize_t(2)});
+    auto r = a.mutable_unchecked<2>();
+    for (py::ssize_t i = 0; i < py::ssize_t(d.size()); ++i) { r(i, 0) = d[size_t(i)].first; r(i, 1) = d[size_t(i)].second; }
+    return a;
+  };
+  amod.def("generate_cis_hilbert_space", [det_array](size_t norb, uint64_t a, uint64_t b) {
+    return det_array(generate_cis_hilbert_space(norb, a, b));
+  }, py::arg("norb"), py::arg("alpha"), py::arg("beta"), "(n, 2) array of (alpha, beta) occupation words");
+  amod.def("generate_cisd_hilbert_space", [det_array](size_t norb, uint64_t a, uint64_t b) {
+    return det_array(generate_cisd_hilbert_space(norb, a, b));
+  }, py::arg("norb"), py::arg("alpha"), py::arg("beta"), "(n, 2) array of (alpha, beta) occupation words");
   amod.def("select_core_indices", &select_core_indices, py::arg("coefficients"), py::arg("fixed_core"),
            py::arg("ncdets_max"), py::arg("core_selection_threshold"));
   amod.def("set_device", &set_device, py::arg("device"));

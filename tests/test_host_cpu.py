@@ -283,3 +283,25 @@ def test_hamiltonian_from_fcidump(tmp_path):
     assert (ham.num_active_orbitals(), na, nb) == (6, 3, 3) and ham.get_core_energy() == sp.core_energy
     assert np.allclose(np.ravel(ham.get_one_body_integrals()), np.ravel(sp.T), rtol=0, atol=0)
     assert np.allclose(np.ravel(ham.get_two_body_integrals()), np.ravel(sp.V), rtol=0, atol=0)
+
+
+def test_cis_and_cisd_spaces():
+    """generate_cis_hilbert_space / generate_cisd_hilbert_space (sd_operations.hpp:60-383): sizes of the
+    reference's water test (csr_hamiltonian.cxx:44-47,76: 12636 determinants), generation order, and the
+    same set as the independent enumeration the parity tests use."""
+    from qdk_chemistry_b200 import _core
+    from helpers import cisd_space
+    hf = (1 << 5) - 1
+    d = _core.algorithms.generate_cisd_hilbert_space(24, hf, hf)
+    assert d.shape == (12636, 2) and len({tuple(x) for x in d.tolist()}) == 12636
+    a, b = cisd_space(24, 5, 5)
+    assert sorted(map(tuple, d.tolist())) == list(zip(a.tolist(), b.tolist()))
+    s = _core.algorithms.generate_cis_hilbert_space(24, hf, hf)
+    assert s.shape == (1 + 2 * 5 * 19, 2) and np.array_equal(s, d[: len(s)])
+    # order: the reference first, alpha singles (virtual index outermost) ...
+    assert tuple(d[0]) == (hf, hf)
+    assert tuple(d[1]) == (hf ^ 1 ^ (1 << 5), hf) and tuple(d[2]) == (hf ^ 2 ^ (1 << 5), hf)
+    assert tuple(d[1 + 95]) == (hf, hf ^ 1 ^ (1 << 5))          # ... then beta singles
+    # open-shell reference, small space
+    t = _core.algorithms.generate_cisd_hilbert_space(6, 0b0111, 0b0011)
+    assert len({tuple(x) for x in t.tolist()}) == len(t) == 1 + 9 + 8 + 9 + 6 + 72
