@@ -380,11 +380,21 @@ def asci_grow(ham: Ham, s: dict, E0: float, a, b, X):
     return E0, a, b, X
 
 
-def asci_refine(ham: Ham, s: dict, E0: float, a, b, X):
-    """include/macis/asci/refine.hpp:44-237 without the oscillation/union branch (raises
-    if that branch would be needed so a test never silently diverges)."""
+def asci_refine(ham: Ham, s: dict, E0: float, a, b, X, info: Optional[dict] = None):
+    """include/macis/asci/refine.hpp:44-237, including the oscillation handling: two consecutive sign
+    flips of dE with |dE_prev + dE| < tol diagonalise the union of the last two determinant sets
+    (warm-started from the current vector) and extend the iteration budget (:118-205).
+    ``info`` (optional) receives {"unions": n, "iterations": n}."""
+    a, b, X = _u64(a), _u64(b), np.asarray(X, dtype=np.float64)
     ndets = len(a)
-    for it in range(s["max_refine_iter"]):
+    max_iter = s["max_refine_iter"]
+    max_ext, total_ext = s["max_refine_iter"], 0
+    prev_dE, osc = 0.0, 0
+    prev = None
+    unions = 0
+    it = 0
+    converged = False
+    while it < max_iter:
         E, a, b, X = asci_iter(ham, s, ndets, E0, a, b, X)
         if len(a) != ndets:
             ndets = len(a)
@@ -392,21 +402,56 @@ def asci_refine(ham: Ham, s: dict, E0: float, a, b, X):
                 break
         dE = E - E0
         if abs(dE) < s["refine_energy_tol"]:
-            return E, a, b, X
+            E0 = E
+            converged = True
+            break
+        if it > 0 and prev_dE * dE < 0 and abs(prev_dE + dE) < s["refine_energy_tol"]:
+            osc += 1
+            if osc >= 2 and prev is not None:
+                pa, pb = prev
+                keys = sorted(set(zip(pa.tolist(), pb.tolist())) | set(zip(a.tolist(), b.tolist())))  # spin order
+                ua = np.array([k[0] for k in keys], dtype=np.uint64)
+                ub = np.array([k[1] for k in keys], dtype=np.uint64)
+                cur = {(int(x), int(y)): float(c) for x, y, c in zip(a, b, X)}
+                xu = np.array([cur.get(k, 0.0) for k in keys])
+                E_union, Xu = _selected_ci_diag(ham, ua, ub, s, xu)
+                ext = min(osc, max_ext - total_ext)
+                if ext > 0:
+                    max_iter += ext
+                    total_ext += ext
+                a, b, X = ua, ub, Xu
+                ndets = len(a)
+                E0 = E_union
+                prev, osc, prev_dE = None, 0, 0.0
+                unions += 1
+                it += 1
+                continue
+        else:
+            osc = 0
+        prev_dE = dE
+        prev = (a.copy(), b.copy())
         E0 = E
-    raise RuntimeError("ASCI Refine did not converge")
+        it += 1
+    if info is not None:
+        info.update(unions=unions, iterations=it + (1 if converged else 0), extensions=total_ext)
+    if not converged:
+        msg = "ASCI Refine did not converge"
+        if total_ext > 0:   # the reference's message (refine.hpp:222-231)
+            msg += f" (oscillation detected, {total_ext} extra iterations granted). "
+        raise RuntimeError(msg)
+    return E0, a, b, X
 
 
 def asci_run(ham: Ham, na: int, nb: int, refine: bool = True, **settings):
     s = dict(ASCI_DEFAULTS)
-    s.update(settings)
+    s.update({k: v for k, v in settings.items() if not k.startswith("_")})
     a = np.array([(1 << na) - 1], dtype=np.uint64)
     b = np.array([(1 << nb) - 1], dtype=np.uint64)
     E = ham.matrix_element(a[0], b[0], a[0], b[0])
     X = np.array([1.0])
     E, a, b, X = asci_grow(ham, s, E, a, b, X)
     if refine and s["max_refine_iter"]:
-        E, a, b, X = asci_refine(ham, s, E, a, b, X)
+        E, a, b, X = asci_refine(ham, s, E, a, b, X, settings.get("_info"))
     return E, a, b, X
 
 

@@ -379,3 +379,26 @@ def test_port_growth_backoff_scenarios_match_compiled_reference(water, case):
     # different partners in the core, a 5e-7 Eh effect
     tol = 1e-5 if case == "percentage_99" else 1e-8
     assert len(a) == m["n"] and abs(E - m["E"]) < tol and abs(X @ X - 1) < 1e-12
+
+
+def test_port_refine_oscillation_handling_matches_compiled_reference():
+    """asci_refine's union stabilisation (refine.hpp:118-205): same number of granted extra iterations when
+    the run gives up, same enlarged determinant set size and energy when it converges
+    (tests/golden/make_golden_union.py)."""
+    import json
+    with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "union_meta.json")) as fh:
+        meta = json.load(fh)
+    sp = W.config("wide36")
+    kw = dict(meta["settings"])
+    kw["core_selection_strategy"] = "fixed"
+    m20 = meta["runs"]["20"]
+    info = {}
+    with pytest.raises(RuntimeError) as e:
+        port.asci_run(port.Ham(sp.norb, sp.T, sp.V), sp.nalpha, sp.nbeta, refine=True, max_refine_iter=20, _info=info, **kw)
+    assert not m20["converged"] and "2 extra iterations granted" in m20["message"]
+    assert "2 extra iterations granted" in str(e.value) and info["unions"] == 1
+    m80 = meta["runs"]["80"]
+    info = {}
+    E, a, b, X = port.asci_run(port.Ham(sp.norb, sp.T, sp.V), sp.nalpha, sp.nbeta, refine=True, max_refine_iter=80,
+                               _info=info, **kw)
+    assert m80["converged"] and len(a) == m80["n"] == 624 and abs(E - m80["E"]) < 1e-8 and info["unions"] == 15
