@@ -8,7 +8,10 @@ module; the product (qdk_chemistry_b200/) never does.
 Pinned (tests/test_oracle.py): CSR pattern of the water CISD space against the reference's
 golden rowptr (external/macis/tests/csr_hamiltonian.cxx:76-99), Davidson / ASCI energies
 against external/macis/tests/{davidson,asci}.cxx, and piecewise against oracle/_ref where
-that library is built.
+that library is built. Golden data made with oracle/_ref additionally pins: the three generators'
+pattern rules, wfn_t<128> determinants (search, H build, RDMs, entropies, a whole grow + refine run),
+grow_with_rot, the growth back-off / core-selection scenarios of asci.cxx:577-840 and the refine
+loop's oscillation handling (tests/golden/make_golden_*.py, tests/README.md).
 """
 from __future__ import annotations
 
