@@ -54,6 +54,7 @@ def lib():
         L.ref_csr_nnz.argtypes = [vp]
         L.ref_csr_copy.argtypes = [vp, vp, vp, vp]
         L.ref_csr_free.argtypes = [vp]
+        L.ref_csr_copy_rows.argtypes = [vp, i64, i64, vp, vp, vp]
         L.ref_spmv.restype = dbl
         L.ref_spmv.argtypes = [vp, vp, vp, i32]
         L.ref_csr_diagonal.argtypes = [vp, vp]
@@ -162,6 +163,20 @@ class Csr:
         ci = np.empty(self.nnz, dtype=np.int64)
         nz = np.empty(self.nnz, dtype=np.float64)
         lib().ref_csr_copy(self.h, _p(rp), _p(ci), _p(nz))
+        return rp, ci, nz
+
+    def rowptr(self) -> np.ndarray:
+        rp = np.empty(self.n + 1, dtype=np.int64)
+        lib().ref_csr_copy_rows(self.h, 0, self.n, _p(rp), None, None)
+        return rp
+
+    def rows(self, r0: int, r1: int, rowptr: Optional[np.ndarray] = None):
+        """(local rowptr, colind, nzval) of rows [r0, r1) without copying the whole matrix"""
+        rp = np.empty(r1 - r0 + 1, dtype=np.int64)
+        lib().ref_csr_copy_rows(self.h, r0, r1, _p(rp), None, None)
+        ci = np.empty(int(rp[-1]), dtype=np.int64)
+        nz = np.empty(int(rp[-1]), dtype=np.float64)
+        lib().ref_csr_copy_rows(self.h, r0, r1, None, _p(ci), _p(nz))
         return rp, ci, nz
 
     def spmv(self, x: np.ndarray, nrep: int = 1) -> Tuple[np.ndarray, float]:

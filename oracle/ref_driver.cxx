@@ -419,6 +419,18 @@ void ref_csr_copy(void* m, int64_t* rowptr, int64_t* colind, double* nzval) {
   std::copy(c->colind().begin(), c->colind().end(), colind);
   std::copy(c->nzval().begin(), c->nzval().end(), nzval);
 }
+// rows [r0, r1) of a reference csr_matrix: local row pointer (r1 - r0 + 1 entries starting at
+// 0), column indices and values -- lets a caller fingerprint a matrix too large to copy whole
+void ref_csr_copy_rows(void* m, int64_t r0, int64_t r1, int64_t* rowptr, int64_t* colind,
+                       double* nzval) {
+  auto* c = static_cast<csr_t*>(m);
+  const auto& rp = c->rowptr();
+  const int64_t b = rp[r0], e = rp[r1];
+  if (rowptr)
+    for (int64_t i = r0; i <= r1; ++i) rowptr[i - r0] = rp[i] - b;
+  if (colind) std::copy(c->colind().begin() + b, c->colind().begin() + e, colind);
+  if (nzval) std::copy(c->nzval().begin() + b, c->nzval().begin() + e, nzval);
+}
 void ref_csr_free(void* m) { delete static_cast<csr_t*>(m); }
 
 // sparsexx::spblas::gespmbv, K = 1 (spblas/spmbv.hpp:49-85); returns mean seconds

@@ -22,3 +22,64 @@ def test_n2_asci26_growth_to_2e5_determinants_matches_reference_energy():
     assert abs(E - sp.core_energy - REFERENCE_E_2E5) < 1e-8      # north_star: energies to 1e-8 Eh
     st = alg.last_run_stats()
     assert st["asci_iterations"] == 5 and st["ndets_after_grow"] == 200000
+
+
+# ---------------------------------------------------------------------------------------------------------
+# BASELINE configs[1] / [2] at the size bench.py quotes its numbers on (853,776 determinants): the pattern,
+# the values and the converged energy against the unmodified reference's full symmetric build + davidson
+# (tests/golden/make_golden_fullsize.py -> fullsize_meta.json; mirrors external/macis/tests/csr_hamiltonian.cxx:76-106
+# and davidson.cxx:48-72 at full size).
+# ---------------------------------------------------------------------------------------------------------
+import hashlib
+import json
+import os
+
+import numpy as np
+
+from qdk_chemistry_b200 import device
+
+_EPS = float(np.finfo(np.float64).eps)
+
+
+def _sha(a):
+    return hashlib.sha256(np.ascontiguousarray(a).view(np.uint8)).hexdigest()
+
+
+@pytest.fixture(scope="module")
+def fullsize_meta():
+    with open(os.path.join(os.path.dirname(__file__), "golden", "fullsize_meta.json")) as fh:
+        return json.load(fh)
+
+
+@pytest.mark.parametrize("name", ["hubbard_4x3", "cr2_cas12"])
+def test_benchmarked_matrix_equals_the_reference_build(fullsize_meta, name):
+    g = fullsize_meta[name]
+    sp = W.config(name)
+    ctx = device.Context(0)
+    try:
+        ctx.upload_integrals(sp.norb, sp.T, sp.V)
+        dets = ctx.generate_fci(sp.norb, sp.nalpha, sp.nbeta)
+        assert len(dets) == g["n"]
+        H = ctx.hbuild(dets, _EPS)
+        assert H.nnz == g["nnz"]
+        rp = H.download_rowptr()
+        assert _sha(rp) == g["rowptr_sha256"]                      # per-row counts of the whole matrix
+        # converged energy and iteration count of the reference's davidson on its own matrix
+        E, X, niter, _ = H.davidson(g["davidson_max_m"], g["davidson_tol"])
+        assert abs(E - g["E0_electronic"]) < 1e-8                  # north_star: energies to 1e-8 Eh
+        assert abs(niter - g["davidson_iterations"]) <= 1
+        assert abs(np.linalg.norm(X) - 1.0) < 1e-12
+        H.free()
+        # every block of 33 alpha runs, built as a row block (b2ci_hbuild_csr(row_begin, row_end)): column
+        # indices and matrix elements bit-identical to the reference's rows
+        for blk in g["blocks"]:
+            r0, r1 = blk["row_begin"], blk["row_end"]
+            B = ctx.hbuild(dets, _EPS, (r0, r1))
+            brp, ci, nz = B.download()
+            B.free()
+            assert np.array_equal(brp, rp[r0:r1 + 1] - rp[r0])     # row block == slice of the full build
+            assert ci.size == blk["nnz"]
+            assert _sha(ci) == blk["colind_sha256"], f"{name}: column indices of rows [{r0},{r1}) differ"
+            assert _sha(nz) == blk["nzval_sha256"], f"{name}: matrix elements of rows [{r0},{r1}) differ"
+    finally:
+        ctx.close()
