@@ -442,7 +442,21 @@ int asci_search(b2ci_ctx* ctx, const b2ci_asci_search_opts* o, const uint64_t* c
   if (M_total <= budget) nparts = 1;
   if (const char* env = getenv("B2CI_ASCI_PARTS")) nparts = std::max<int64_t>(1, atoll(env));
   const int nranks = ctx->nranks, rank = ctx->rank;
-  if (nranks > 1) nparts = ((std::max<int64_t>(nparts, nranks) + nranks - 1) / nranks) * nranks;
+  if (nranks > 1) {
+    // the partition count decides which rank owns which key: it must be ONE number. Free memory (and
+    // with it the budget) differs from rank to rank, so the ranks agree on the largest request and
+    // check that they are searching from the same core set.
+    std::vector<int64_t> all_parts, all_m;
+    comm_allgather_i64_host(ctx, nparts, all_parts);
+    comm_allgather_i64_host(ctx, M_total, all_m);
+    for (int r = 0; r < nranks; ++r) {
+      nparts = std::max(nparts, all_parts[r]);
+      if (all_m[r] != M_total)
+        throw Error("b2ci_asci_search: ranks disagree on the contribution count (" + std::to_string(M_total) + " here, " +
+                    std::to_string(all_m[r]) + " on rank " + std::to_string(r) + "): different core sets or integrals");
+    }
+    nparts = ((std::max<int64_t>(nparts, nranks) + nranks - 1) / nranks) * nranks;
+  }
   if (candidates_only && (nparts > 1 || nranks > 1))
     throw Error("b2ci_asci_candidates: the candidate table is only available for single-part searches");
   T["asci_search.nparts"] = double(nparts);

@@ -108,6 +108,9 @@ struct P2P {
   unsigned long long epoch = 0;
   double* fallback = nullptr;  // library-owned gather buffer of the NCCL path
   size_t fallback_cap = 0;
+  unsigned int* err_host = nullptr;  // mapped pinned word: k_wait gave up on peer (value - 1)
+  unsigned int* err_dev = nullptr;
+  unsigned long long timeout_ns = 600ull * 1000000000ull;
 };
 struct IpcPack { cudaIpcMemHandle_t h[3]; };
 
@@ -133,16 +136,29 @@ k_push(const double* __restrict__ local, int64_t nloc, int64_t row0, double* con
     }
   }
 }
-__global__ void k_wait(const unsigned long long* __restrict__ flags, int nranks, unsigned long long epoch) {
+__device__ __forceinline__ unsigned long long global_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+// A peer may legitimately be late (an imbalanced H build ahead of the first sigma), so the wait is
+// long (B2CI_P2P_TIMEOUT_S, default 600 s) and a timeout does not kill the context: it raises a word
+// in mapped host memory, which the host turns into an error at its next exchange / synchronisation.
+__global__ void k_wait(const unsigned long long* __restrict__ flags, int nranks, unsigned long long epoch,
+                       unsigned long long timeout_ns, unsigned int* __restrict__ err) {
   const int r = threadIdx.x;
   if (r >= nranks) return;
-  const long long t0 = clock64();
+  const unsigned long long t0 = global_ns();
   for (;;) {
     unsigned long long f;
     asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(f) : "l"(flags + r) : "memory");
     if (f >= epoch) break;
-    if (clock64() - t0 > 20000000000ll) __trap();  // ~10 s: a peer is gone; fail instead of hanging
-    __nanosleep(64);
+    if (global_ns() - t0 > timeout_ns) {
+      *err = 1u + unsigned(r);
+      __threadfence_system();
+      break;
+    }
+    __nanosleep(128);
   }
 }
 
@@ -150,10 +166,17 @@ P2P* p2p_state(b2ci_ctx* ctx) {
   if (!ctx->p2p) ctx->p2p = new P2P;
   return static_cast<P2P*>(ctx->p2p);
 }
-void p2p_release(b2ci_ctx* ctx, P2P* s) {
+// collective when buffers were exported: a peer may still have them open (cudaFree of an exported
+// allocation before the importer's cudaIpcCloseMemHandle is undefined), so every rank closes what it
+// imported, all ranks meet, and only then are the exported buffers freed
+void p2p_release(b2ci_ctx* ctx, P2P* s, bool collective) {
   cudaStreamSynchronize(ctx->stream);
   for (void* q : s->opened) cudaIpcCloseMemHandle(q);
   s->opened.clear();
+  if (collective && ctx->nccl_comm && !getenv("B2CI_P2P_NO_RELEASE_BARRIER")) {
+    int64_t one = 1;
+    try { comm_allreduce_sum_i64_host(ctx, &one, 1); } catch (...) {}
+  }
   for (int b = 0; b < 2; ++b) {
     if (s->xbuf[b]) cudaFree(s->xbuf[b]);
     if (s->d_peer_x[b]) cudaFree(s->d_peer_x[b]);
@@ -172,7 +195,7 @@ void p2p_release(b2ci_ctx* ctx, P2P* s) {
 void p2p_setup(b2ci_ctx* ctx, P2P* s, size_t n) {
   const int nr = ctx->nranks, me = ctx->rank;
   cudaStream_t st = ctx->stream;
-  p2p_release(ctx, s);
+  p2p_release(ctx, s, s->ok);  // s->ok is all-or-nothing, so every rank takes the same branch
   s->tried = true;
   s->epoch = 0;
   int64_t good = 1;
@@ -235,7 +258,17 @@ void p2p_setup(b2ci_ctx* ctx, P2P* s, size_t n) {
     s->ok = true;
     s->cap = cap;
   } else {
-    p2p_release(ctx, s);
+    p2p_release(ctx, s, true);  // a peer may have opened this rank's buffers before another rank failed
+  }
+  if (s->ok && !s->err_host) {
+    if (cudaHostAlloc(reinterpret_cast<void**>(&s->err_host), sizeof(unsigned int), cudaHostAllocMapped) == cudaSuccess &&
+        cudaHostGetDevicePointer(reinterpret_cast<void**>(&s->err_dev), s->err_host, 0) == cudaSuccess) {
+      *s->err_host = 0u;
+    } else {
+      cudaGetLastError();
+      throw Error("p2p exchange: cannot allocate the mapped error word");
+    }
+    if (const char* env = getenv("B2CI_P2P_TIMEOUT_S")) s->timeout_ns = (unsigned long long)(std::max(1.0, atof(env)) * 1e9);
   }
   ctx->timers["comm.p2p"] = s->ok ? 1. : 0.;
 }
@@ -249,12 +282,18 @@ const double* comm_exchange_rows(b2ci_ctx* ctx, const double* local, const std::
   P2P* s = p2p_state(ctx);
   if (!s->tried || (s->ok && s->cap < n)) p2p_setup(ctx, s, n);  // collective: n is the same everywhere
   if (s->ok) {
+    if (*s->err_host) {
+      const unsigned int who = *s->err_host - 1u;
+      *s->err_host = 0u;
+      throw Error("sigma exchange: rank " + std::to_string(who) + " did not publish its block of the trial vector within " +
+                  std::to_string(s->timeout_ns / 1000000000ull) + " s (B2CI_P2P_TIMEOUT_S)");
+    }
     const unsigned long long e = ++s->epoch;
     const int b = int(e & 1ull);
     const int64_t nloc = off[me + 1] - off[me];
     const int grid = int(std::max<int64_t>(1, std::min<int64_t>(ctx->sm_count, (nloc + PUSH_THREADS - 1) / PUSH_THREADS)));
     k_push<<<grid, PUSH_THREADS, 0, ctx->stream>>>(local, nloc, off[me], s->d_peer_x[b], s->d_peer_flag, nr, me, e, s->done);
-    k_wait<<<1, 32, 0, ctx->stream>>>(s->flags, nr, e);
+    k_wait<<<1, 32, 0, ctx->stream>>>(s->flags, nr, e, s->timeout_ns, s->err_dev);
     ctx->launches += 2;
     B2_CHECK_LAUNCH();
     return s->xbuf[b];
@@ -277,8 +316,9 @@ const double* comm_exchange_rows(b2ci_ctx* ctx, const double* local, const std::
 void comm_destroy(b2ci_ctx* ctx) {
   if (ctx->p2p) {
     P2P* s = static_cast<P2P*>(ctx->p2p);
-    p2p_release(ctx, s);
+    p2p_release(ctx, s, s->ok);
     if (s->fallback) cudaFree(s->fallback);
+    if (s->err_host) cudaFreeHost(s->err_host);
     delete s;
     ctx->p2p = nullptr;
   }

@@ -564,6 +564,14 @@ int davidson(b2ci_ctx* ctx, const b2ci_csr* m, int64_t max_m, double tol, double
     return 0;
   }
   if (max_m < 1) throw Error("Davidson: max_m must be >= 1");
+  if (max_m < 2) {
+    // no iteration can run: report it without touching the caller's guess (the reference throws
+    // "Davidson Did Not Converge!" from davidson.hpp:368 with X as it was)
+    *niter_out = 0;
+    *eig_out = 0.;
+    set_error("Davidson Did Not Converge!");
+    return B2CI_NOT_CONVERGED;
+  }
 
   Work W;
   W.ctx = ctx;

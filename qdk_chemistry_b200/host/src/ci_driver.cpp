@@ -825,6 +825,7 @@ McResult B200Cas::_run_impl(std::shared_ptr<data::Hamiltonian> h, unsigned na, u
   g_stats.clear();
   const auto t0 = std::chrono::steady_clock::now();
   CiSession S(*h);
+  const double launches0 = double(b2ci_ctx_launch_count(S.ctx()));
   std::vector<Det> dets;
   std::vector<double> C;
   const double E = casci(S, *_settings, na, nb, dets, C);
@@ -832,6 +833,7 @@ McResult B200Cas::_run_impl(std::shared_ptr<data::Hamiltonian> h, unsigned na, u
   attach_rdms_spin_dependent(S, *_settings, dets, C, *w);
   attach_entropies(S, *_settings, dets, C, *w);
   g_stats["wall_ms"] = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+  g_stats["launches"] = double(b2ci_ctx_launch_count(S.ctx())) - launches0;
   return {E + h->get_core_energy(), w};
 }
 
@@ -845,6 +847,7 @@ McResult B200Asci::_run_impl(std::shared_ptr<data::Hamiltonian> h, unsigned na, 
   g_stats.clear();
   const auto t0 = std::chrono::steady_clock::now();
   CiSession S(*h);
+  const double launches0 = double(b2ci_ctx_launch_count(S.ctx()));
   const int norb = S.norb();
   // residue arrays hold O(n_e^2) residues per determinant: beyond 60 electrons the reference falls
   // back to the sorted double loop (macis_asci.cpp:32,96-108) and so do its pattern rules
@@ -876,6 +879,7 @@ McResult B200Asci::_run_impl(std::shared_ptr<data::Hamiltonian> h, unsigned na, 
   attach_rdms_spin_dependent(S, *_settings, dets, C, *w);
   attach_entropies(S, *_settings, dets, C, *w);
   g_stats["wall_ms"] = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+  g_stats["launches"] = double(b2ci_ctx_launch_count(S.ctx())) - launches0;
   return {E + h->get_core_energy(), w};
 }
 
@@ -896,6 +900,7 @@ McResult B200Pmc::_run_impl(std::shared_ptr<data::Hamiltonian> h,
   g_stats.clear();
   const auto t0 = std::chrono::steady_clock::now();
   CiSession S(*h);
+  const double launches0 = double(b2ci_ctx_launch_count(S.ctx()));
   std::vector<double> C;
   double E = 0.;
   const int64_t n = int64_t(dets.size());
@@ -917,6 +922,7 @@ McResult B200Pmc::_run_impl(std::shared_ptr<data::Hamiltonian> h,
     w->set_rdms_spin_traced(std::move(one), std::move(two));
   }
   g_stats["wall_ms"] = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+  g_stats["launches"] = double(b2ci_ctx_launch_count(S.ctx())) - launches0;
   return {E + h->get_core_energy(), w};
 }
 

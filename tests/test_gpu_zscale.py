@@ -24,6 +24,21 @@ def test_n2_asci26_growth_to_2e5_determinants_matches_reference_energy():
     assert st["asci_iterations"] == 5 and st["ndets_after_grow"] == 200000
 
 
+# the unmodified reference's asci_grow energies at the sizes BASELINE configs[3] / [4] name (or the largest the CPU
+# reference finishes): profiles/r01_reference_cpu_asci_{n2_14e26o,cr2_24e30o}.json (326 s / 654 s on 8 threads)
+REFERENCE_E_N2_1E6 = -21.93063537575684
+REFERENCE_E_CR2_1E6 = -24.280818571062454
+
+
+@pytest.mark.parametrize("name,E_ref", [("n2_asci26", REFERENCE_E_N2_1E6), ("cr2_asci30", REFERENCE_E_CR2_1E6)])
+def test_asci_growth_to_1e6_determinants_matches_reference_energy(name, E_ref):
+    sp = W.config(name)
+    E, w = alg.create("multi_configuration_calculator", "macis_asci", ntdets_max=1000000, max_refine_iter=0,
+                      ci_residual_tolerance=1e-8).run(data.Hamiltonian(sp.T, sp.V, sp.core_energy), sp.nalpha, sp.nbeta)
+    assert w.size() == 1000000 and abs(w.norm() - 1) < 1e-12
+    assert abs(E - sp.core_energy - E_ref) < 1e-8
+
+
 # ---------------------------------------------------------------------------------------------------------
 # BASELINE configs[1] / [2] at the size bench.py quotes its numbers on (853,776 determinants): the pattern,
 # the values and the converged energy against the unmodified reference's full symmetric build + davidson
