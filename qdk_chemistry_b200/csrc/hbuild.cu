@@ -141,9 +141,16 @@ struct RowArgs {
   int32_t* hit_head = nullptr;        // [nrows] first chunk of the row
   unsigned int* hit_cursor = nullptr; // chunks handed out so far (may run past hit_capacity: overflow)
   unsigned int hit_capacity = 0;
+  const int64_t* bra_run_start = nullptr;  // BLK: first bra determinant of every bra run
+  const int32_t* row_list = nullptr;       // optional: the launch's rows (the rest are taken by the tiled scan)
+  const void* beta_s = nullptr;            // ket beta strings as 32-bit words (norb <= 32), else NULL
   const int32_t* struct_cnt = nullptr;  // k_rows_hits: structural row lengths of the count pass
   int64_t row_stride = 1;               // sampling (estimate pass): row r of the launch is row r * row_stride
 };
+
+template <typename S> __device__ __forceinline__ int popc_s(S x);
+template <> __device__ __forceinline__ int popc_s<uint32_t>(uint32_t x) { return __popc(x); }
+template <> __device__ __forceinline__ int popc_s<uint64_t>(uint64_t x) { return __popcll(x); }
 
 // Evaluate up to 32 queued column indices (one per lane) and count / emit the survivors.
 // count pass with hit lists: one chunk per batch, chained to the row's previous chunk
@@ -199,13 +206,14 @@ __device__ __forceinline__ void process_batch(const RowArgs& A, int64_t i, uint6
 // of) runs two alpha excitations away. Runs are contiguous index ranges and group members are
 // stored in ascending index, so the two streams are merged on the fly: before run r' is
 // scanned, the group members below its first index are emitted. Columns come out ascending.
-template <bool FILL, bool EVAL, bool BLK = false>
+template <bool FILL, bool EVAL, bool BLK = false, typename S = uint64_t>
 __global__ void __launch_bounds__(ROW_WARPS * 32)
 k_rows(const RowArgs A) {
   __shared__ int32_t queue[ROW_WARPS][64];
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-  const int64_t row = int64_t(blockIdx.x) * ROW_WARPS + w;
-  if (row >= A.nrows) return;
+  const int64_t ridx = int64_t(blockIdx.x) * ROW_WARPS + w;
+  if (ridx >= A.nrows) return;
+  const int64_t row = A.row_list ? int64_t(A.row_list[ridx]) : ridx;
   const int64_t il = A.row_begin + row * A.row_stride;  // index in the bra list
   const uint64_t ai = BLK ? A.bra_alpha[il] : A.alpha[il], bi = BLK ? A.bra_beta[il] : A.beta[il];
   const int32_t r = BLK ? A.bra_run[il] : A.run_of[il];
@@ -339,16 +347,18 @@ k_rows(const RowArgs A) {
         // the hot loop of a general build (876 steps per row at 2e5 determinants, 61 % of the kernel's
         // instructions): 32-bit positions, one pointer, no bounds test in the full steps
         const int32_t len = int32_t(ke - ks), j32 = int32_t(ks);
-        const uint64_t* __restrict__ bp = A.beta + ks + lane;
+        // strings narrowed to 32 bits when norb <= 32 (A.beta_s): half the POPC work and traffic
+        const S* __restrict__ bp = (sizeof(S) == 8 ? reinterpret_cast<const S*>(A.beta) : static_cast<const S*>(A.beta_s)) + ks + lane;
+        const S bs = S(bi);
         const int lim = 4 - da;
         int32_t base = 0;
         for (; base + 32 <= len; base += 32) {
-          const bool hit = __popcll(bi ^ __ldg(bp + base)) <= lim;
+          const bool hit = popc_s<S>(bs ^ __ldg(bp + base)) <= lim;
           push(hit, j32 + base + lane);
         }
         if (base < len) {
           bool hit = false;
-          if (base + lane < len) hit = __popcll(bi ^ __ldg(bp + base)) <= lim;
+          if (base + lane < len) hit = popc_s<S>(bs ^ __ldg(bp + base)) <= lim;
           push(hit, j32 + base + lane);
         }
       }
@@ -392,6 +402,300 @@ k_rows_hits(const RowArgs A) {
     process_batch<true, EVAL, BLK>(A, i, ai, bi, A.hit_cols + size_t(chunk) * 32, nvalid, lane, out, cnt);
     remaining -= nvalid;
     chunk = nxt;
+  }
+  if (lane == 0 && A.row_cnt) A.row_cnt[row] = cnt;
+}
+
+// ------------------------------------------------------------------ tiled scan of general lists
+// The warp-per-row scan above spends one instruction stream per (row, 32 strings): every row of an
+// alpha run re-reads the beta strings of the same adjacent runs. Here a warp owns a UNIT of up to
+// 32 consecutive rows of ONE alpha run, one row per lane: the strings of an adjacent run are staged
+// 32 at a time in shared memory and every staged string is tested against the 32 row strings at once
+// (broadcast shared-memory read, one XOR + POPC + compare per lane, one ballot) -- the adjacency
+// walk, the run bounds and the loads are paid once per unit instead of once per row, and the test is
+// the only per-(row, string) work. With norb <= 32 the strings are 32-bit words (half the POPC work;
+// POPC issues at 16 lanes / clock / SM on B200, measured by scripts/micro/popc_rate.cu, and bounds
+// this kernel). A lane's hits ascend in the ket index by construction (runs ascend, strings ascend,
+// the beta-group members of class (c) are merged in before the run they precede): rows need no sort.
+//
+// Connections leave the kernel as a dense stream of (lane mask, ket index) entries per unit -- one
+// entry per tested string that connects to at least one row of the unit, 8 bytes, so the store is
+// bounded by 8 bytes per connection whatever the rows look like -- in chained chunks of TILE_CH
+// entries (one atomic per chunk, warp-uniform). k_tile_gather then deals every row's hits to its
+// slot range of the CSR column array, where k_rows_hits_flat evaluates them in place. If the store
+// overflows the counts are still right and the fill falls back to scanning again.
+constexpr int TILE_CH = 512;  // entries per chunk (4 KiB)
+constexpr int TILE_WARPS = 8;
+struct TileArgs {
+  RowArgs A;
+  const void* beta_s;        // ket beta strings as 32- or 64-bit words
+  const int32_t* unit_row0;  // first local row of every tiled unit
+  const int32_t* unit_len;   // its rows (<= 32)
+  int32_t nunits;
+  uint2* tile_ent;           // [capacity][TILE_CH] (lane mask, ket index)
+  int32_t* tile_next;        // [capacity]
+  int32_t* unit_head;        // [nunits] first chunk (-1: none)
+  int32_t* unit_nent;        // [nunits] entries of the unit (all chunks full but the last)
+  unsigned int* cursor;
+  unsigned int capacity;
+};
+
+template <typename S, bool BLK>
+__global__ void __launch_bounds__(TILE_WARPS * 32)
+k_rows_tile(const TileArgs T) {
+  __shared__ __align__(16) S slab[TILE_WARPS][32];
+  const RowArgs& A = T.A;
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int64_t u = int64_t(blockIdx.x) * TILE_WARPS + w;
+  if (u >= T.nunits) return;
+  const int32_t row0 = T.unit_row0[u], ulen = T.unit_len[u];
+  const bool valid = lane < ulen;
+  const int64_t row = row0 + (valid ? lane : 0);
+  const int64_t il = A.row_begin + row;
+  const uint64_t ai = BLK ? A.bra_alpha[il] : A.alpha[il];  // the same for every row of the unit
+  const S bi = S(BLK ? A.bra_beta[il] : A.beta[il]);
+  const int32_t r = BLK ? A.bra_run[il] : A.run_of[il];
+  const S* __restrict__ beta_s = static_cast<const S*>(T.beta_s);
+  int32_t cnt = 0;                      // this lane's row length
+  int32_t chunk = -1, pos = TILE_CH;    // warp-uniform stream state
+  int32_t nent = 0;
+  uint2* __restrict__ ent = nullptr;    // current chunk
+  auto emit = [&](unsigned m, int32_t j) {  // warp-uniform
+    if (pos == TILE_CH) {
+      unsigned int c = 0;
+      if (lane == 0) c = atomicAdd(T.cursor, 1u);
+      c = __shfl_sync(0xffffffffu, c, 0);
+      const int32_t nc = c < T.capacity ? int32_t(c) : -1;  // overflow: counting goes on, nothing is stored
+      if (lane == 0) {
+        if (chunk >= 0) T.tile_next[chunk] = nc;
+        else if (nent == 0) T.unit_head[u] = nc;
+        if (nc >= 0) T.tile_next[nc] = -1;
+      }
+      chunk = nc;
+      pos = 0;
+      ent = nc >= 0 ? T.tile_ent + size_t(nc) * TILE_CH : nullptr;
+    }
+    if (lane == 0 && ent) ent[pos] = make_uint2(m, unsigned(j));
+    ++pos;
+    ++nent;
+  };
+  if (ai != 0 || A.pair_rule) {
+    const int32_t g = valid ? (BLK ? A.bra_grp[il] : A.bgrp_of[il]) : -1;
+    int64_t bpos = g >= 0 ? A.bgrp_start[g] : 0;
+    const int64_t bend = g >= 0 ? A.bgrp_start[g + 1] : 0;
+    constexpr int32_t NONE = INT32_MAX;
+    int32_t nextj = bpos < bend ? int32_t(A.bgrp_mem[bpos]) : NONE;
+    // class (c): same beta string, alpha double excitation -- members below `bound`, one per lane and round
+    auto flush_group = [&](int32_t bound) {
+      while (__any_sync(0xffffffffu, nextj < bound)) {
+        bool hit = false;
+        const int32_t jm = nextj;
+        if (nextj < bound) {
+          const uint64_t aj = A.alpha[nextj];
+          hit = (aj != 0 || A.pair_rule) && __popcll(ai ^ aj) == 4;
+          ++bpos;
+          nextj = bpos < bend ? int32_t(A.bgrp_mem[bpos]) : NONE;
+        }
+        cnt += hit ? 1 : 0;
+        unsigned m = __ballot_sync(0xffffffffu, hit);
+        while (m) {
+          const int l = __ffs(m) - 1;
+          emit(1u << l, __shfl_sync(0xffffffffu, jm, l));
+          m &= m - 1;
+        }
+      }
+    };
+    const int64_t e0 = A.adj_ptr[r], e1 = A.adj_ptr[r + 1];
+    for (int64_t e = e0; e < e1; ++e) {
+      const uint32_t pk = A.adj[e];
+      const int32_t ks = int32_t(A.run_start[pk >> 2]), ke = int32_t(A.run_start[(pk >> 2) + 1]);
+      flush_group(ks);
+      const int lim = valid ? 4 - int(pk & 3u) * 2 : -1;  // idle lanes never hit
+      const S* __restrict__ bp = beta_s + ks;
+      const int32_t rlen = ke - ks;
+      S mine = lane < rlen ? bp[lane] : S(0);
+      for (int32_t base = 0; base < rlen; base += 32) {
+        __syncwarp();
+        slab[w][lane] = mine;
+        __syncwarp();
+        // the next step's strings are in flight while this step is tested
+        mine = base + 32 + lane < rlen ? bp[base + 32 + lane] : S(0);
+        const int nst = rlen - base < 32 ? rlen - base : 32;
+        const int32_t jb = ks + base;
+        int q = 0;
+        for (; q + 8 <= nst; q += 8) {
+          S st[8];
+          if (sizeof(S) == 4) {
+            const uint4 v0 = *reinterpret_cast<const uint4*>(&slab[w][q]);
+            const uint4 v1 = *reinterpret_cast<const uint4*>(&slab[w][q + 4]);
+            st[0] = S(v0.x); st[1] = S(v0.y); st[2] = S(v0.z); st[3] = S(v0.w);
+            st[4] = S(v1.x); st[5] = S(v1.y); st[6] = S(v1.z); st[7] = S(v1.w);
+          } else {
+#pragma unroll
+            for (int t = 0; t < 8; t += 2) {
+              const ulonglong2 v = *reinterpret_cast<const ulonglong2*>(&slab[w][q + t]);
+              st[t] = S(v.x); st[t + 1] = S(v.y);
+            }
+          }
+#pragma unroll
+          for (int t = 0; t < 8; ++t) {
+            const bool hit = popc_s<S>(bi ^ st[t]) <= lim;
+            if (__any_sync(0xffffffffu, hit)) {  // about every second string connects to some row of the unit
+              cnt += hit ? 1 : 0;
+              emit(__ballot_sync(0xffffffffu, hit), jb + q + t);
+            }
+          }
+        }
+        for (int t = q; t < nst; ++t) {
+          const bool hit = popc_s<S>(bi ^ slab[w][t]) <= lim;
+          if (__any_sync(0xffffffffu, hit)) {
+            cnt += hit ? 1 : 0;
+            emit(__ballot_sync(0xffffffffu, hit), jb + t);
+          }
+        }
+      }
+      // a group member inside this run is at alpha distance <= 2: the scan has it
+      while (nextj < ke) {
+        ++bpos;
+        nextj = bpos < bend ? int32_t(A.bgrp_mem[bpos]) : NONE;
+      }
+    }
+    flush_group(NONE);
+  }
+  if (lane == 0) T.unit_nent[u] = nent;
+  if (valid && A.row_cnt) A.row_cnt[row] = cnt;
+}
+
+// deal the entries of every unit to its rows: hits of row (unit, lane) = ket indices of the entries
+// whose mask has bit `lane`, in stream order, written to the row's slot range of `hits`
+__global__ void __launch_bounds__(TILE_WARPS * 32)
+k_tile_gather(const TileArgs T, const int64_t* __restrict__ slot_ptr, int32_t* __restrict__ hits) {
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int64_t u = int64_t(blockIdx.x) * TILE_WARPS + w;
+  if (u >= T.nunits) return;
+  const int32_t row0 = T.unit_row0[u], ulen = T.unit_len[u];
+  const bool valid = lane < ulen;
+  int32_t* __restrict__ out = hits + (valid ? slot_ptr[row0 + lane] : 0);
+  int32_t remaining = T.unit_nent[u];
+  int32_t c = remaining > 0 ? T.unit_head[u] : -1;
+  const unsigned mybit = 1u << lane;
+  while (remaining > 0 && c >= 0) {
+    const int32_t nin = remaining < TILE_CH ? remaining : TILE_CH;
+    const uint2* __restrict__ src = T.tile_ent + size_t(c) * TILE_CH;
+    for (int32_t b = 0; b < nin; b += 32) {
+      const uint2 e = b + lane < nin ? src[b + lane] : make_uint2(0u, 0u);
+      const int nb = nin - b < 32 ? nin - b : 32;
+      for (int k = 0; k < nb; ++k) {
+        const unsigned mk = __shfl_sync(0xffffffffu, e.x, k);
+        const unsigned jk = __shfl_sync(0xffffffffu, e.y, k);
+        if (mk & mybit) *out++ = int32_t(jk);
+      }
+    }
+    remaining -= nin;
+    c = T.tile_next[c];
+  }
+}
+
+__global__ void k_unit_flags(int64_t nrows, int64_t row_begin, const int32_t* __restrict__ run_ix,
+                             const int64_t* __restrict__ run_first, int32_t* __restrict__ flag) {
+  const int64_t r = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (r >= nrows) return;
+  const int64_t il = row_begin + r;
+  const int32_t run = run_ix[il];
+  flag[r] = (r == 0 || run != run_ix[il - 1] || ((il - run_first[run]) & 31) == 0) ? 1 : 0;
+}
+// per row: is it the first row of a unit (flag), which unit (excl + flag - 1); a unit of fewer than
+// min_rows rows is left to the warp-per-row scan (one lane per row would idle the other lanes)
+__global__ void k_unit_classify(int64_t nrows, const int32_t* __restrict__ flag, const int32_t* __restrict__ excl,
+                                int32_t min_rows, int32_t* __restrict__ tile_flag, int32_t* __restrict__ scan_flag) {
+  const int64_t r = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (r >= nrows) return;
+  // length of the unit r belongs to: distance between the unit starts around r (<= 32 rows either way)
+  int64_t a = r, b = r + 1;
+  while (!flag[a]) --a;
+  while (b < nrows && !flag[b]) ++b;
+  const bool big = b - a >= min_rows;
+  tile_flag[r] = (big && flag[r]) ? 1 : 0;
+  scan_flag[r] = big ? 0 : 1;
+  (void)excl;
+}
+__global__ void k_unit_lists(int64_t nrows, const int32_t* __restrict__ flag, const int32_t* __restrict__ tile_flag,
+                             const int32_t* __restrict__ tile_excl, const int32_t* __restrict__ scan_flag,
+                             const int32_t* __restrict__ scan_excl, int32_t* __restrict__ unit_row0,
+                             int32_t* __restrict__ unit_len, int32_t* __restrict__ unit_head,
+                             int32_t* __restrict__ scan_rows) {
+  const int64_t r = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (r >= nrows) return;
+  if (tile_flag[r]) {
+    int64_t b = r + 1;
+    while (b < nrows && !flag[b]) ++b;
+    const int32_t t = tile_excl[r];
+    unit_row0[t] = int32_t(r);
+    unit_len[t] = int32_t(b - r);
+    unit_head[t] = -1;  // k_rows_tile sets it when the unit produces its first entry
+  }
+  if (scan_flag[r]) scan_rows[scan_excl[r]] = int32_t(r);
+}
+// hits of the warp-per-row scan (chunks of 32 chained per row) to the row's slot range, for the rows of a list
+__global__ void __launch_bounds__(ROW_WARPS * 32)
+k_hits_gather(const RowArgs A, const int64_t* __restrict__ slot_ptr, int32_t* __restrict__ hits) {
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int64_t ridx = int64_t(blockIdx.x) * ROW_WARPS + w;
+  if (ridx >= A.nrows) return;
+  const int64_t row = A.row_list ? int64_t(A.row_list[ridx]) : ridx;
+  int32_t remaining = A.struct_cnt[row];
+  int32_t chunk = remaining > 0 ? A.hit_head[row] : -1;
+  int32_t* __restrict__ out = hits + slot_ptr[row];
+  while (remaining > 0) {
+    const int nvalid = remaining < 32 ? remaining : 32;
+    if (lane < nvalid) out[lane] = A.hit_cols[size_t(chunk) * 32 + lane];
+    out += nvalid;
+    remaining -= nvalid;
+    chunk = A.hit_next[chunk];
+  }
+}
+__global__ void k_narrow_u32(const uint64_t* __restrict__ in, int64_t n, uint32_t* __restrict__ out) {
+  const int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = uint32_t(in[i]);
+}
+
+// fill pass from contiguous hit lists held IN PLACE in the row's slot range of colind
+template <bool EVAL, bool BLK>
+__global__ void __launch_bounds__(ROW_WARPS * 32)
+k_rows_hits_flat(const RowArgs A) {
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int64_t row = int64_t(blockIdx.x) * ROW_WARPS + w;
+  if (row >= A.nrows) return;
+  const int64_t il = A.row_begin + row;
+  const uint64_t ai = BLK ? A.bra_alpha[il] : A.alpha[il], bi = BLK ? A.bra_beta[il] : A.beta[il];
+  const int64_t i = (BLK && A.rowmap) ? int64_t(A.rowmap[il]) : il;
+  const int32_t nhit = A.struct_cnt[row];
+  const int64_t slot = A.rowptr[row];
+  int64_t out = slot;
+  int32_t cnt = 0;
+  for (int32_t t0 = 0; t0 < nhit; t0 += 32) {
+    const int nvalid = nhit - t0 < 32 ? nhit - t0 : 32;
+    // survivors are written at or below the position they were read from, after the whole batch was read
+    const int32_t jraw = lane < nvalid ? A.colind[slot + t0 + lane] : 0;
+    __syncwarp();
+    const bool valid = lane < nvalid;
+    int32_t j = jraw;
+    double v = 0.;
+    bool keep = valid;
+    if (valid) {
+      const uint64_t aj = A.alpha[j], bj = A.beta[j];
+      if (BLK && A.colmap) j = A.colmap[j];
+      v = (i <= int64_t(j)) ? matel(A.I, ai, bi, aj, bj) : matel(A.I, aj, bj, ai, bi);
+      if (EVAL) keep = A.pair_rule ? (i == int64_t(j) || !(fabs(v) < A.thr)) : fabs(v) > A.thr;
+    }
+    const unsigned km = __ballot_sync(0xffffffffu, keep);
+    if (keep) {
+      const int64_t pos = out + __popc(km & ((1u << lane) - 1u));
+      A.colind[pos] = j;
+      A.nzval[pos] = v;
+    }
+    out += __popc(km);
+    cnt += __popc(km);
   }
   if (lane == 0 && A.row_cnt) A.row_cnt[row] = cnt;
 }
@@ -1281,83 +1585,226 @@ struct RowScanOut {
   int64_t nnz = 0;
   size_t ci_cap = 0, nz_cap = 0;  // non-zero: blocks came from the context's slot cache
 };
+// B2CI_HBUILD_TRACE: device time of the scan's kernels, one line per phase
+struct PhaseTrace {
+  cudaStream_t st;
+  bool on;
+  cudaEvent_t a, b;
+  explicit PhaseTrace(cudaStream_t s) : st(s), on(getenv("B2CI_HBUILD_TRACE") != nullptr) {
+    if (on) { cudaEventCreate(&a); cudaEventCreate(&b); }
+  }
+  ~PhaseTrace() { if (on) { cudaEventDestroy(a); cudaEventDestroy(b); } }
+  void begin() { if (on) cudaEventRecord(a, st); }
+  void end(const char* what, double units) {
+    if (!on) return;
+    cudaEventRecord(b, st);
+    cudaEventSynchronize(b);
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, a, b);
+    fprintf(stderr, "[hbuild scan] %-22s %9.3f ms  (%.4g)\n", what, ms, units);
+  }
+};
 template <bool BLK>
-void run_row_scan(b2ci_ctx* ctx, RowArgs A, int64_t nrows, double thr, bool use_slot_cache, RowScanOut& out) {
+void run_row_scan(b2ci_ctx* ctx, RowArgs A, int64_t nrows, int64_t nket, double thr, bool use_slot_cache, RowScanOut& out) {
   cudaStream_t st = ctx->stream;
+  PhaseTrace PT(st);
   const unsigned grid = unsigned((nrows + ROW_WARPS - 1) / ROW_WARPS);
   int64_t nslots = 0;
   DevBuf<int64_t> slot_ptr(nrows + 1);
   DevBuf<int32_t> row_cnt(nrows);
+  // store of the warp-per-row scan (rows of short units)
   DevBuf<int32_t> hit_cols, hit_next, hit_head;
-  DevBuf<unsigned int> hit_cursor(1);
+  DevBuf<unsigned int> cursors(2);  // [0] warp-per-row chunks, [1] tile chunks
   unsigned int hit_capacity = 0, hit_used = 0;
+  // tiled scan (units of >= tile_min rows of one alpha run)
+  DevBuf<int32_t> unit_row0, unit_len, unit_head, unit_nent, scan_rows, tile_next;
+  DevBuf<uint2> tile_ent;
+  unsigned int tile_capacity = 0, tile_used = 0;
+  int32_t ntile = 0;
+  int64_t nscan = nrows;
+  // norb <= 32: beta strings as 32-bit words
+  DevBuf<uint32_t> beta32;
+  const bool w32 = ctx->norb <= 32 && !getenv("B2CI_HBUILD_WIDE_STRINGS");  // (test hook: 64-bit strings)
+  auto launch_scan_count = [&](const RowArgs& R, int64_t nr) {
+    const unsigned g = unsigned((nr + ROW_WARPS - 1) / ROW_WARPS);
+    if (w32) k_rows<false, false, BLK, uint32_t><<<g, ROW_WARPS * 32, 0, st>>>(R);
+    else k_rows<false, false, BLK, uint64_t><<<g, ROW_WARPS * 32, 0, st>>>(R);
+    ctx->launches++;
+    B2_CHECK_LAUNCH();
+  };
+  TileArgs TA;
   {
     ScopedTimer t(ctx, "h_build.count", true);
-    // (test hooks: B2CI_HBUILD_HITLIST_MIN = smallest list that uses the store, B2CI_HBUILD_HITLIST_CAP =
-    // its capacity in chunks, to exercise the overflow fallback)
+    if (w32) {
+      beta32.alloc(nket);
+      k_narrow_u32<<<unsigned((nket + 255) / 256), 256, 0, st>>>(A.beta, nket, beta32);
+      ctx->launches++;
+      B2_CHECK_LAUNCH();
+      A.beta_s = beta32;
+    }
+    // (test hooks: B2CI_HBUILD_HITLIST_MIN = smallest list that keeps the connections of its count pass,
+    // B2CI_HBUILD_HITLIST_CAP / B2CI_HBUILD_TILE_CAP = capacities in chunks, to exercise the overflow fallback,
+    // B2CI_HBUILD_NO_TILE = warp-per-row scan for every row, B2CI_HBUILD_TILE_MIN = smallest tiled unit)
     const char* env_min = getenv("B2CI_HBUILD_HITLIST_MIN");
     const int64_t min_rows = env_min ? atoll(env_min) : 4096;
     const bool want_hits = nrows >= min_rows && !getenv("B2CI_HBUILD_NO_HITLIST");
     if (want_hits) {
-      // estimate: structural row lengths of every 64th row
-      const int64_t stride = 64, ns = (nrows + stride - 1) / stride;
+      // estimate: structural row lengths of every 64th (256th) row
+      const int64_t stride = nrows >= (int64_t(1) << 21) ? 256 : 64, ns = (nrows + stride - 1) / stride;
       DevBuf<int32_t> scnt(ns);
       DevBuf<int64_t> sptr(ns + 1);
       RowArgs S = A;
       S.row_stride = stride;
       S.nrows = ns;
       S.row_cnt = scnt;
-      k_rows<false, false, BLK><<<unsigned((ns + ROW_WARPS - 1) / ROW_WARPS), ROW_WARPS * 32, 0, st>>>(S);
-      ctx->launches++;
-      B2_CHECK_LAUNCH();
+      PT.begin();
+      launch_scan_count(S, ns);
+      PT.end("estimate (rows)", double(ns));
       exclusive_scan_i32_to_i64(ctx, scnt, sptr, ns);
-      int64_t sample = 0;
-      B2_CUDA(cudaMemcpyAsync(&sample, sptr.p + ns, 8, cudaMemcpyDeviceToHost, st));
+      int64_t* pin = pinned_words(ctx);
+      B2_CUDA(cudaMemcpyAsync(pin, sptr.p + ns, 8, cudaMemcpyDeviceToHost, st));
+      // units of the tiled scan: <= 32 consecutive rows of one alpha run, aligned to the run's start
+      const bool want_tile = !getenv("B2CI_HBUILD_NO_TILE");
+      int32_t tile_min = 12;
+      if (const char* env = getenv("B2CI_HBUILD_TILE_MIN")) tile_min = std::max(1, atoi(env));
+      DevBuf<int32_t> uflag, uexcl, tflag, texcl, sflag, sexcl;
+      if (want_tile) {
+        uflag.alloc(nrows); uexcl.alloc(nrows + 1); tflag.alloc(nrows); texcl.alloc(nrows + 1);
+        sflag.alloc(nrows); sexcl.alloc(nrows + 1);
+        const unsigned gr = unsigned((nrows + 255) / 256);
+        k_unit_flags<<<gr, 256, 0, st>>>(nrows, A.row_begin, BLK ? A.bra_run : A.run_of,
+                                         BLK ? A.bra_run_start : A.run_start, uflag);
+        k_unit_classify<<<gr, 256, 0, st>>>(nrows, uflag, uexcl, tile_min, tflag, sflag);
+        ctx->launches += 2;
+        B2_CHECK_LAUNCH();
+        exclusive_scan_i32(ctx, tflag, texcl, nrows);
+        exclusive_scan_i32(ctx, sflag, sexcl, nrows);
+        B2_CUDA(cudaMemcpyAsync(pin + 1, texcl.p + nrows, 4, cudaMemcpyDeviceToHost, st));
+        B2_CUDA(cudaMemcpyAsync(pin + 2, sexcl.p + nrows, 4, cudaMemcpyDeviceToHost, st));
+      }
       B2_CUDA(cudaStreamSynchronize(st));
-      const double est = double(sample) * double(nrows) / double(ns);
-      const double chunks = est * 1.25 / 32.0 + double(nrows) + 1024.0;  // + one partial chunk per row
+      const int64_t sample = pin[0];
+      if (want_tile) {
+        ntile = *reinterpret_cast<const int32_t*>(pin + 1);
+        nscan = *reinterpret_cast<const int32_t*>(pin + 2);
+      }
+      const double est = double(sample) * double(nrows) / double(ns) * 1.25 + 4096.0;
+      const double frac_scan = double(nscan) / double(nrows);
+      // warp-per-row store: 132 B per chunk of 32 connections + one partial chunk per row;
+      // tile store: 8 B per entry, at most one entry per connection, + one partial chunk per unit
+      const double chunks = est * std::min(1.0, 2.0 * frac_scan + 0.01) / 32.0 + double(nscan) + 1024.0;
+      const double tchunks = ntile ? est / double(TILE_CH) + double(ntile) + 1024.0 : 0.0;
       size_t free_b = 0, total_b = 0;
       B2_CUDA(cudaMemGetInfo(&free_b, &total_b));
-      // the store (132 B per chunk) must leave room for the matrix itself (12 B per entry)
-      if (chunks < 2.0e9 && chunks * 132.0 + est * 1.25 * 12.0 < 0.8 * double(free_b)) {
-        hit_capacity = unsigned(chunks);
-        if (const char* env_cap = getenv("B2CI_HBUILD_HITLIST_CAP")) hit_capacity = unsigned(std::max<long long>(1, atoll(env_cap)));
-        hit_cols.alloc(size_t(hit_capacity) * 32);
-        hit_next.alloc(hit_capacity);
-        hit_head.alloc(nrows);
-        B2_CUDA(cudaMemsetAsync(hit_cursor, 0, sizeof(unsigned int), st));
-        A.hit_cols = hit_cols;
-        A.hit_next = hit_next;
-        A.hit_head = hit_head;
-        A.hit_cursor = hit_cursor;
-        A.hit_capacity = hit_capacity;
+      // the stores must leave room for the matrix itself (12 B per entry)
+      if (chunks < 2.0e9 && tchunks < 2.0e9 &&
+          chunks * 132.0 + tchunks * (TILE_CH * 8.0 + 4.0) + est * 12.0 < 0.8 * double(free_b)) {
+        B2_CUDA(cudaMemsetAsync(cursors, 0, 2 * sizeof(unsigned int), st));
+        if (nscan) {
+          hit_capacity = unsigned(chunks);
+          if (const char* env_cap = getenv("B2CI_HBUILD_HITLIST_CAP")) hit_capacity = unsigned(std::max<long long>(1, atoll(env_cap)));
+          hit_cols.alloc(size_t(hit_capacity) * 32);
+          hit_next.alloc(hit_capacity);
+          hit_head.alloc(nrows);
+          A.hit_cols = hit_cols;
+          A.hit_next = hit_next;
+          A.hit_head = hit_head;
+          A.hit_cursor = cursors.p;
+          A.hit_capacity = hit_capacity;
+        }
+        if (ntile) {
+          tile_capacity = unsigned(tchunks);
+          if (const char* env_cap = getenv("B2CI_HBUILD_TILE_CAP")) tile_capacity = unsigned(std::max<long long>(1, atoll(env_cap)));
+          tile_ent.alloc(size_t(tile_capacity) * TILE_CH);
+          tile_next.alloc(tile_capacity);
+          unit_row0.alloc(ntile); unit_len.alloc(ntile); unit_head.alloc(ntile); unit_nent.alloc(ntile);
+        }
+        if (want_tile) {
+          scan_rows.alloc(nscan > 0 ? nscan : 1);
+          if (!ntile) { unit_row0.alloc(1); unit_len.alloc(1); unit_head.alloc(1); }
+          k_unit_lists<<<unsigned((nrows + 255) / 256), 256, 0, st>>>(nrows, uflag, tflag, texcl, sflag, sexcl, unit_row0,
+                                                                      unit_len, unit_head, scan_rows);
+          ctx->launches++;
+          B2_CHECK_LAUNCH();
+        }
+      } else {
+        ntile = 0;
+        nscan = nrows;
       }
     }
     A.row_cnt = row_cnt;
-    k_rows<false, false, BLK><<<grid, ROW_WARPS * 32, 0, st>>>(A);
-    ctx->launches++;
-    B2_CHECK_LAUNCH();
+    if (ntile) {
+      TA.A = A;
+      TA.beta_s = w32 ? static_cast<const void*>(beta32.p) : static_cast<const void*>(A.beta);
+      TA.unit_row0 = unit_row0; TA.unit_len = unit_len; TA.nunits = ntile;
+      TA.tile_ent = tile_ent; TA.tile_next = tile_next; TA.unit_head = unit_head; TA.unit_nent = unit_nent;
+      TA.cursor = cursors.p + 1;
+      TA.capacity = tile_capacity;
+      const unsigned gt = unsigned((ntile + TILE_WARPS - 1) / TILE_WARPS);
+      PT.begin();
+      if (w32) k_rows_tile<uint32_t, BLK><<<gt, TILE_WARPS * 32, 0, st>>>(TA);
+      else k_rows_tile<uint64_t, BLK><<<gt, TILE_WARPS * 32, 0, st>>>(TA);
+      ctx->launches++;
+      B2_CHECK_LAUNCH();
+      PT.end("tiled scan (units)", double(ntile));
+    }
+    if (nscan) {
+      RowArgs R = A;
+      if (ntile) { R.row_list = scan_rows; R.nrows = nscan; }
+      PT.begin();
+      launch_scan_count(R, R.nrows);
+      PT.end("row scan (rows)", double(R.nrows));
+    }
     exclusive_scan_i32_to_i64(ctx, row_cnt, slot_ptr, nrows);
     int64_t* pin = pinned_words(ctx);
     B2_CUDA(cudaMemcpyAsync(pin, slot_ptr.p + nrows, 8, cudaMemcpyDeviceToHost, st));
-    if (hit_capacity) B2_CUDA(cudaMemcpyAsync(pin + 1, hit_cursor, sizeof(unsigned int), cudaMemcpyDeviceToHost, st));
+    B2_CUDA(cudaMemcpyAsync(pin + 1, cursors, 2 * sizeof(unsigned int), cudaMemcpyDeviceToHost, st));
     B2_CUDA(cudaStreamSynchronize(st));
     nslots = pin[0];
-    if (hit_capacity) hit_used = *reinterpret_cast<const unsigned int*>(pin + 1);
+    hit_used = reinterpret_cast<const unsigned int*>(pin + 1)[0];
+    tile_used = reinterpret_cast<const unsigned int*>(pin + 1)[1];
   }
-  const bool from_hits = hit_capacity != 0 && hit_used <= hit_capacity;
+  const bool from_hits = (hit_capacity != 0 || tile_capacity != 0) && hit_used <= hit_capacity && tile_used <= tile_capacity &&
+                         (nscan == 0 || hit_capacity != 0) && (ntile == 0 || tile_capacity != 0);
   ctx->timers["h_build.hit_lists"] = from_hits ? 1. : 0.;
-  if (!from_hits) { hit_cols.release(); hit_next.release(); hit_head.release(); }
+  ctx->timers["h_build.tile_units"] = double(ntile);
+  ctx->timers["h_build.scan_rows"] = double(nscan);
+  ctx->timers["h_build.tile_chunks"] = double(tile_used);
+  if (!from_hits) { hit_cols.release(); hit_next.release(); hit_head.release(); tile_ent.release(); tile_next.release(); }
   DevBuf<int32_t> colind, kept(nrows);
   DevBuf<double> nzval;
   size_t ci_cap = 0, nz_cap = 0;
   if (use_slot_cache) {
     colind.p = static_cast<int32_t*>(big_alloc(ctx, 0, size_t(nslots > 0 ? nslots : 1) * sizeof(int32_t), &ci_cap));
     colind.n = ci_cap / sizeof(int32_t);
+  } else {
+    colind.alloc(nslots > 0 ? nslots : 1);
+  }
+  A.struct_cnt = row_cnt;
+  if (from_hits) {
+    // connections -> the rows' slot ranges of the column array (ket indices, ascending); the stores go
+    // back before the value array is allocated
+    ScopedTimer t(ctx, "h_build.count", true);
+    PT.begin();
+    if (ntile) {
+      k_tile_gather<<<unsigned((ntile + TILE_WARPS - 1) / TILE_WARPS), TILE_WARPS * 32, 0, st>>>(TA, slot_ptr, colind);
+      ctx->launches++;
+      B2_CHECK_LAUNCH();
+    }
+    if (nscan) {
+      RowArgs R = A;
+      if (ntile) { R.row_list = scan_rows; R.nrows = nscan; }
+      k_hits_gather<<<unsigned((R.nrows + ROW_WARPS - 1) / ROW_WARPS), ROW_WARPS * 32, 0, st>>>(R, slot_ptr, colind);
+      ctx->launches++;
+      B2_CHECK_LAUNCH();
+    }
+    PT.end("gather (connections)", double(nslots));
+    hit_cols.release(); hit_next.release(); hit_head.release(); tile_ent.release(); tile_next.release();
+  }
+  if (use_slot_cache) {
     nzval.p = static_cast<double*>(big_alloc(ctx, 1, size_t(nslots > 0 ? nslots : 1) * sizeof(double), &nz_cap));
     nzval.n = nz_cap / sizeof(double);
   } else {
-    colind.alloc(nslots > 0 ? nslots : 1);
     nzval.alloc(nslots > 0 ? nslots : 1);
   }
   {
@@ -1366,10 +1813,12 @@ void run_row_scan(b2ci_ctx* ctx, RowArgs A, int64_t nrows, double thr, bool use_
     A.rowptr = slot_ptr;
     A.colind = colind;
     A.nzval = nzval;
-    A.struct_cnt = row_cnt;
+    A.row_list = nullptr;
+    A.nrows = nrows;
+    PT.begin();
     if (from_hits) {
-      if (thr > 0.0) k_rows_hits<true, BLK><<<grid, ROW_WARPS * 32, 0, st>>>(A);
-      else k_rows_hits<false, BLK><<<grid, ROW_WARPS * 32, 0, st>>>(A);
+      if (thr > 0.0) k_rows_hits_flat<true, BLK><<<grid, ROW_WARPS * 32, 0, st>>>(A);
+      else k_rows_hits_flat<false, BLK><<<grid, ROW_WARPS * 32, 0, st>>>(A);
     } else {
       A.hit_cols = nullptr;
       if (thr > 0.0) k_rows<true, true, BLK><<<grid, ROW_WARPS * 32, 0, st>>>(A);
@@ -1377,6 +1826,7 @@ void run_row_scan(b2ci_ctx* ctx, RowArgs A, int64_t nrows, double thr, bool use_
     }
     ctx->launches++;
     B2_CHECK_LAUNCH();
+    PT.end(from_hits ? "fill from connections" : "fill by rescan", double(nslots));
   }
   int64_t nnz = nslots;
   out.rowptr.alloc(nrows + 1);
@@ -1751,6 +2201,29 @@ void hbuild_csr(b2ci_ctx* ctx, const b2ci_dets* dets, int64_t row_begin, int64_t
     return;
   }
   build_adjacency(2);
+  if (trace) {
+    // shape of a general list: how the rows are distributed over alpha runs of which length
+    std::vector<int64_t> rs(size_t(nruns) + 1);
+    B2_CUDA(cudaMemcpyAsync(rs.data(), run_start.p, (size_t(nruns) + 1) * 8, cudaMemcpyDeviceToHost, st));
+    int64_t nadj_h = 0;
+    B2_CUDA(cudaMemcpyAsync(&nadj_h, adj_ptr.p + nruns, 8, cudaMemcpyDeviceToHost, st));
+    B2_CUDA(cudaStreamSynchronize(st));
+    const int64_t edges[] = {1, 2, 4, 8, 16, 32, 64, 128, 256, 1024, 4096, int64_t(1) << 40};
+    int64_t rows_in[12] = {0}, runs_in[12] = {0};
+    for (int32_t r = 0; r < nruns; ++r) {
+      const int64_t len = rs[size_t(r) + 1] - rs[r];
+      int b = 0;
+      while (len > edges[b]) ++b;
+      rows_in[b] += len;
+      runs_in[b] += 1;
+    }
+    fprintf(stderr, "[hbuild] general list: n = %lld, alpha runs = %d, run adjacency entries = %lld\n", (long long)n, nruns,
+            (long long)nadj_h);
+    for (int b = 0; b < 12; ++b)
+      if (runs_in[b])
+        fprintf(stderr, "[hbuild]   runs of length <= %-6lld : %8lld runs, %9lld rows (%.1f %%)\n",
+                (long long)std::min<int64_t>(edges[b], n), (long long)runs_in[b], (long long)rows_in[b], 100.0 * rows_in[b] / n);
+  }
 
   // ---- general lists: determinants grouped by beta string (stable radix sort of the indices)
   DevBuf<int32_t> bgrp_of(n);
@@ -1800,7 +2273,7 @@ void hbuild_csr(b2ci_ctx* ctx, const b2ci_dets* dets, int64_t row_begin, int64_t
   // count pass (keeps the connections it finds) + fill pass (evaluates them): run_row_scan
   ctx->timers["h_build.count"] = ctx->timers["h_build.fill"] = ctx->timers["h_build.thresh"] = 0.;
   RowScanOut R;
-  run_row_scan<false>(ctx, A, nrows, thr, true, R);
+  run_row_scan<false>(ctx, A, nrows, n, thr, true, R);
   out->colind_cap = R.ci_cap;
   out->nzval_cap = R.nz_cap;
   out->nnz = R.nnz;
@@ -1925,6 +2398,7 @@ void build_block_general(b2ci_ctx* ctx, const DetView& bra, const DetView& ket, 
   A.bra_alpha = bra.alpha;
   A.bra_beta = bra.beta;
   A.bra_run = bra_run;
+  A.bra_run_start = bra_run_start;
   A.bra_grp = bra_grp;
   A.rowmap = bra.gmap;
   A.colmap = ket.gmap;
@@ -1933,7 +2407,7 @@ void build_block_general(b2ci_ctx* ctx, const DetView& bra, const DetView& ket, 
   const double t_count = ctx->timers["h_build.count"], t_fill = ctx->timers["h_build.fill"],
                t_thresh = ctx->timers["h_build.thresh"];
   RowScanOut R;
-  run_row_scan<true>(ctx, A, nrows, thr, false, R);
+  run_row_scan<true>(ctx, A, nrows, nk, thr, false, R);
   ctx->timers["h_build.count"] = t_count;
   ctx->timers["h_build.fill"] = t_fill;
   ctx->timers["h_build.thresh"] = t_thresh;

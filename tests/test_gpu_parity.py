@@ -450,17 +450,26 @@ def test_fci_list_under_pair_rules_takes_the_scan_path(ctx):
     assert rp[-1] >= srp[-1]
 
 
-@pytest.mark.parametrize("mode", ["hits", "overflow", "off"])
+@pytest.mark.parametrize("mode", ["hits", "overflow", "tile_overflow", "no_tile", "tile_all", "wide", "off"])
 def test_hit_list_fill_equals_rescan_fill(ctx, mode, monkeypatch):
-    """General lists scan once: the count pass stores the connections it finds and the fill pass
-    evaluates them from the store; a store that turns out too small falls back to a second scan.
-    All three ways give the oracle's CSR, for the plain build, a row block and the patched build."""
+    """General lists scan once: the count pass stores the connections it finds (the tiled scan for units of
+    12+ rows of one alpha run, the warp-per-row scan for the rest) and the fill pass evaluates them from the
+    store; a store that turns out too small falls back to a second scan. Every way gives the oracle's CSR,
+    for the plain build, a row block and the patched build."""
     sp, a, b = None, None, None
     from helpers import generator_case
     sp, a, b = generator_case("n2_cas10_s2500")
     monkeypatch.setenv("B2CI_HBUILD_HITLIST_MIN", "1")
     if mode == "overflow":
         monkeypatch.setenv("B2CI_HBUILD_HITLIST_CAP", "100")
+    if mode == "tile_overflow":
+        monkeypatch.setenv("B2CI_HBUILD_TILE_CAP", "1")
+    if mode == "no_tile":
+        monkeypatch.setenv("B2CI_HBUILD_NO_TILE", "1")
+    if mode == "tile_all":
+        monkeypatch.setenv("B2CI_HBUILD_TILE_MIN", "1")
+    if mode == "wide":
+        monkeypatch.setenv("B2CI_HBUILD_WIDE_STRINGS", "1")
     if mode == "off":
         monkeypatch.setenv("B2CI_HBUILD_NO_HITLIST", "1")
     ctx.upload_integrals(sp.norb, sp.T, sp.V)
@@ -468,7 +477,13 @@ def test_hit_list_fill_equals_rescan_fill(ctx, mode, monkeypatch):
     d = ctx.upload_dets(port.pack(a, b), 1)
     for thr in (EPS, 0.0, 1e-2):
         H = ctx.hbuild(d, thr)
-        assert ctx.timer_ms("h_build.hit_lists") == (1.0 if mode == "hits" else 0.0)
+        assert ctx.timer_ms("h_build.hit_lists") == (0.0 if mode in ("overflow", "tile_overflow", "off") else 1.0)
+        if mode in ("hits", "wide"):
+            assert ctx.timer_ms("h_build.tile_units") > 0 and ctx.timer_ms("h_build.scan_rows") > 0
+        if mode == "tile_all":
+            assert ctx.timer_ms("h_build.scan_rows") == 0
+        if mode == "no_tile":
+            assert ctx.timer_ms("h_build.tile_units") == 0
         rp, ci, nz = H.download()
         orp, oci, onz = h.hbuild(a, b, thr)
         assert np.array_equal(rp, orp) and np.array_equal(ci, oci) and np.array_equal(nz, onz)
