@@ -175,8 +175,17 @@ void sym_eig_lowest(int n, const double* A, int lda, double* lambda, double* vec
     const int m = n - i - 1;  // reflector acts on rows i+1 .. n-1
     double* x = &M(i + 1, i);
     const double alpha = x[0];
+    // ||x(1:)||: scaled sum of squares (one pass for the scale, one for the sum) -- std::hypot per
+    // element made this the most expensive line of the whole reduction
+    double xmax = 0.0;
+    for (int k = 1; k < m; ++k) xmax = std::max(xmax, std::fabs(x[k]));
     double xnorm = 0.0;
-    for (int k = 1; k < m; ++k) xnorm = std::hypot(xnorm, x[k]);
+    if (xmax > 0.0) {
+      const double inv = 1.0 / xmax;
+      double ss = 0.0;
+      for (int k = 1; k < m; ++k) { const double t = x[k] * inv; ss += t * t; }
+      xnorm = xmax * std::sqrt(ss);
+    }
     d[i] = M(i, i);
     if (xnorm == 0.0) {
       tau[i] = 0.0;
@@ -274,8 +283,11 @@ void sym_eig_lowest(int n, const double* A, int lda, double* lambda, double* vec
     y[n - 1] /= dd[n - 1];  // backward: U^-1
     if (n > 1) y[n - 2] = (y[n - 2] - du[n - 2] * y[n - 1]) / dd[n - 2];
     for (int i = n - 3; i >= 0; --i) y[i] = (y[i] - du[i] * y[i + 1] - du2[i] * y[i + 2]) / dd[i];
-    double nrm = 0.0;
-    for (int i = 0; i < n; ++i) nrm = std::hypot(nrm, y[i]);
+    double ymax = 0.0;
+    for (int i = 0; i < n; ++i) ymax = std::max(ymax, std::fabs(y[i]));
+    double ss = 0.0;
+    for (int i = 0; i < n; ++i) { const double t = y[i] / ymax; ss += t * t; }
+    const double nrm = ymax * std::sqrt(ss);
     for (int i = 0; i < n; ++i) y[i] /= nrm;
   }
   // ---- back-transformation x = H_0 H_1 ... H_{n-2} y
@@ -289,7 +301,8 @@ void sym_eig_lowest(int n, const double* A, int lda, double* lambda, double* vec
     for (int k = 0; k < m; ++k) y[i + 1 + k] -= s * v[k];
   }
   double nrm = 0.0;
-  for (int i = 0; i < n; ++i) nrm = std::hypot(nrm, y[i]);
+  for (int i = 0; i < n; ++i) nrm += y[i] * y[i];  // y has unit norm up to rounding here
+  nrm = std::sqrt(nrm);
   for (int i = 0; i < n; ++i) vec[i] = y[i] / nrm;
   // Rayleigh quotient of the back-transformed vector: second-order accurate in the vector error
   double num = 0.0;
@@ -306,10 +319,27 @@ namespace {
 constexpr int DOT_THREADS = 256;
 constexpr int DOT_CG = 8;  // columns per register group
 
+// Last-CTA-done reduction: after a CTA has written its partial sums it takes a ticket; the CTA that draws the
+// last one adds the partials up in CTA order (a fixed order: results do not depend on scheduling) and
+// re-arms the counter. Saves the separate reduction launch after every dot product / norm of the solver.
+__device__ __forceinline__ bool last_cta_done(unsigned int* counter, unsigned int nctas) {
+  __shared__ bool is_last;
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const unsigned int t = atomicAdd(counter, 1u);
+    is_last = t == nctas - 1;
+    if (is_last) *counter = 0u;
+  }
+  __syncthreads();
+  if (is_last) __threadfence();
+  return is_last;
+}
 // partial[b*k + j] = sum over the rows of CTA b of A[i + j*ld] * w[i]
 __global__ void __launch_bounds__(DOT_THREADS)
 k_multi_dot(int64_t N, int k, const double* __restrict__ A, int64_t ld,
-            const double* __restrict__ w, double* __restrict__ partial) {
+            const double* __restrict__ w, double* __restrict__ partial, unsigned int* __restrict__ counter,
+            double* __restrict__ out) {
   __shared__ double red[DOT_CG][DOT_THREADS / 32];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int64_t stride = int64_t(gridDim.x) * DOT_THREADS;
@@ -341,6 +371,13 @@ k_multi_dot(int64_t N, int k, const double* __restrict__ A, int64_t ld,
     }
     __syncthreads();
   }
+  if (counter && last_cta_done(counter, gridDim.x * gridDim.y)) {
+    for (int j = threadIdx.x; j < k; j += DOT_THREADS) {
+      double s = 0.;
+      for (unsigned b = 0; b < gridDim.x; ++b) s += partial[int64_t(b) * k + j];
+      out[j] = s;
+    }
+  }
 }
 __global__ void k_reduce_partials(int nblocks, int k, const double* __restrict__ partial,
                                   double* __restrict__ out) {
@@ -351,20 +388,50 @@ __global__ void k_reduce_partials(int nblocks, int k, const double* __restrict__
   out[j] = s;
 }
 // w[i] -= sum_j V[i + j*ld] * h[j]
+// w -= V h; with nrm_partial: also ||w_new||^2 (per-CTA partials, summed by the last CTA into nrm_out[0])
 __global__ void __launch_bounds__(256)
 k_project_out(int64_t N, int k, const double* __restrict__ V, int64_t ld,
-              const double* __restrict__ h, double* __restrict__ w) {
+              const double* __restrict__ h, double* __restrict__ w, double* __restrict__ nrm_partial,
+              unsigned int* __restrict__ counter, double* __restrict__ nrm_out) {
   extern __shared__ double hs[];
+  __shared__ double red[8];
   for (int j = threadIdx.x; j < k; j += blockDim.x) hs[j] = h[j];
   __syncthreads();
   const int64_t stride = int64_t(gridDim.x) * blockDim.x;
+  double nrm = 0.;
   for (int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < N; i += stride) {
     double s = 0.;
     for (int j = 0; j < k; ++j) s = fma(V[i + int64_t(j) * ld], hs[j], s);
-    w[i] -= s;
+    const double wi = w[i] - s;
+    w[i] = wi;
+    nrm = fma(wi, wi, nrm);
+  }
+  if (!nrm_partial) return;
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) nrm += __shfl_down_sync(0xffffffffu, nrm, d);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = nrm;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double s = 0.;
+    for (int wv = 0; wv < 8; ++wv) s += red[wv];
+    nrm_partial[blockIdx.x] = s;
+  }
+  if (last_cta_done(counter, gridDim.x) && threadIdx.x == 0) {
+    double s = 0.;
+    for (unsigned b = 0; b < gridDim.x; ++b) s += nrm_partial[b];
+    nrm_out[0] = s;
   }
 }
 __global__ void k_scale(int64_t N, double a, double* __restrict__ w) {
+  const int64_t stride = int64_t(gridDim.x) * blockDim.x;
+  for (int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < N; i += stride) w[i] *= a;
+}
+// w /= sqrt(nrm2[0]) with the squared norm on the device (left alone when the norm is not above min_norm:
+// the host sees the same number and takes the reference's fallback)
+__global__ void k_scale_by_norm(int64_t N, const double* __restrict__ nrm2, double min_norm, double* __restrict__ w) {
+  const double nrm = sqrt(nrm2[0]);
+  if (!(nrm > min_norm)) return;
+  const double a = 1.0 / nrm;
   const int64_t stride = int64_t(gridDim.x) * blockDim.x;
   for (int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < N; i += stride) w[i] *= a;
 }
@@ -377,7 +444,8 @@ __global__ void k_set_unit(int64_t N, int64_t row0, int64_t idx, double* __restr
 __global__ void __launch_bounds__(256)
 k_residual(int64_t N, int k, const double* __restrict__ V, const double* __restrict__ AV,
            int64_t ld, const double* __restrict__ c, double lam, const double* __restrict__ D,
-           double* __restrict__ X, double* __restrict__ Wout, double* __restrict__ partial) {
+           double* __restrict__ X, double* __restrict__ Wout, double* __restrict__ partial,
+           unsigned int* __restrict__ counter, double* __restrict__ out) {
   extern __shared__ double cs[];
   __shared__ double red[8];
   for (int j = threadIdx.x; j < k; j += blockDim.x) cs[j] = c[j];
@@ -406,6 +474,11 @@ k_residual(int64_t N, int k, const double* __restrict__ V, const double* __restr
     for (int wv = 0; wv < 8; ++wv) s += red[wv];
     partial[blockIdx.x] = s;
   }
+  if (last_cta_done(counter, gridDim.x) && threadIdx.x == 0) {
+    double s = 0.;
+    for (unsigned b = 0; b < gridDim.x; ++b) s += partial[b];
+    out[0] = s;
+  }
 }
 // extract_diagonal_elements: first entry of the row whose column is the row's global index
 __global__ void k_diag(int64_t nrows, int64_t row_begin, const int64_t* __restrict__ rowptr,
@@ -426,15 +499,16 @@ struct Work {
   int nblocks;   // CTAs of the reductions (one partial per CTA)
   int nstream;   // CTAs of the streaming updates
   DevBuf<double> partial, small;  // small: k-sized device scratch
+  DevBuf<double> scal;            // [0] ||r||^2 of the residual, [1] ||w||^2 after the second projection
+  DevBuf<unsigned int> counter;   // ticket counter of the last-CTA reductions (re-armed by the kernels)
   std::vector<double> host_small;
 };
 
+// out (device, k doubles) = A(:, 0:k)^T w, all-reduced over the ranks; host_out: also copied back (synchronises)
 void dots(Work& W, int k, const double* A, const double* w, double* host_out) {
   b2ci_ctx* ctx = W.ctx;
   const dim3 grid(W.nblocks, unsigned(std::min(8, (k + DOT_CG - 1) / DOT_CG)));
-  k_multi_dot<<<grid, DOT_THREADS, 0, ctx->stream>>>(W.N, k, A, W.ld, w, W.partial);
-  ctx->launches++;
-  k_reduce_partials<<<(k + 127) / 128, 128, 0, ctx->stream>>>(W.nblocks, k, W.partial, W.small);
+  k_multi_dot<<<grid, DOT_THREADS, 0, ctx->stream>>>(W.N, k, A, W.ld, w, W.partial, W.counter, W.small);
   ctx->launches++;
   B2_CHECK_LAUNCH();
   if (ctx->nranks > 1) comm_allreduce_sum(ctx, W.small, k);
@@ -448,11 +522,26 @@ double norm2(Work& W, const double* w) {
   dots(W, 1, w, w, &s);
   return std::sqrt(s);
 }
-void project(Work& W, int k, const double* V, double* w) {
+// w -= V (V^T w); with_norm: ||w_new||^2 lands in W.scal[1] (all-reduced)
+void project(Work& W, int k, const double* V, double* w, bool with_norm = false) {
   b2ci_ctx* ctx = W.ctx;
   dots(W, k, V, w, nullptr);  // h stays on the device (W.small)
-  k_project_out<<<W.nstream, 256, size_t(k) * 8, ctx->stream>>>(W.N, k, V, W.ld, W.small, w);
+  k_project_out<<<W.nstream, 256, size_t(k) * 8, ctx->stream>>>(W.N, k, V, W.ld, W.small, w,
+                                                               with_norm ? W.partial.p : nullptr, W.counter,
+                                                               W.scal.p + 1);
   ctx->launches++;
+  B2_CHECK_LAUNCH();
+  if (with_norm && ctx->nranks > 1) comm_allreduce_sum(ctx, W.scal.p + 1, 1);
+}
+// the CGS2 step of gram_schmidt queued without touching the host: two projections, the norm of the result
+// in W.scal[1], the vector scaled on the device when the norm is usable. The caller reads W.scal back at
+// its next synchronisation and finishes with gram_schmidt_fallback if the norm was not above min_norm.
+constexpr double GS_MIN_NORM = 1e-12;
+void gram_schmidt_queue(Work& W, int k, const double* V, double* w) {
+  project(W, k, V, w);
+  project(W, k, V, w, true);
+  k_scale_by_norm<<<W.nstream, 256, 0, W.ctx->stream>>>(W.N, W.scal.p + 1, GS_MIN_NORM, w);
+  W.ctx->launches++;
   B2_CHECK_LAUNCH();
 }
 void scale(Work& W, double a, double* w) {
@@ -460,6 +549,7 @@ void scale(Work& W, double a, double* w) {
   W.ctx->launches++;
   B2_CHECK_LAUNCH();
 }
+void gram_schmidt_fallback(Work& W, int k, const double* V, double* w, int64_t row0, int64_t Nglobal);
 // gram_schmidt (davidson.hpp:185-238)
 void gram_schmidt(Work& W, int k, const double* V, double* w, int64_t row0, int64_t Nglobal) {
   const double min_norm = 1e-12;
@@ -475,6 +565,12 @@ void gram_schmidt(Work& W, int k, const double* V, double* w, int64_t row0, int6
     scale(W, 1. / nrm, w);
     return;
   }
+  gram_schmidt_fallback(W, k, V, w, row0, Nglobal);
+}
+// davidson.hpp:216-237: canonical unit vectors, one after the other, until one survives the projection
+void gram_schmidt_fallback(Work& W, int k, const double* V, double* w, int64_t row0, int64_t Nglobal) {
+  const double min_norm = 1e-12;
+  double nrm = 0.;
   for (int64_t idx = 0; idx < Nglobal; ++idx) {
     k_set_unit<<<W.nblocks, 256, 0, W.ctx->stream>>>(W.N, row0, idx, w);
     W.ctx->launches++;
@@ -581,6 +677,9 @@ int davidson(b2ci_ctx* ctx, const b2ci_csr* m, int64_t max_m, double tol, double
   W.nstream = (int)std::max<int64_t>(1, std::min<int64_t>(int64_t(ctx->sm_count) * 16, (Nloc + 255) / 256));
   W.partial.alloc(std::max(size_t(W.nblocks) * (max_m + 2), size_t(W.nstream)));
   W.small.alloc(max_m + 2);
+  W.scal.alloc(2);
+  W.counter.alloc(1);
+  B2_CUDA(cudaMemsetAsync(W.counter, 0, sizeof(unsigned int), st));
   const int64_t ld = W.ld;
 
   // The reference allocates N x (max_m + 1) for V and AV up front (davidson.hpp:293-294).
@@ -631,27 +730,33 @@ int davidson(b2ci_ctx* ctx, const b2ci_csr* m, int64_t max_m, double tol, double
       lam = LAM[0];
       B2_CUDA(cudaMemcpyAsync(cdev, Cw.data(), size_t(k) * 8, cudaMemcpyHostToDevice, st));
     }
-    double res_nrm;
+    // residual, preconditioned correction and its orthogonalisation are queued back to back; ||r||^2 and the
+    // norm after the second projection come back in ONE synchronisation (the orthogonalisation of an
+    // iteration that turns out converged is a few passes over V of wasted device time, never used)
+    double res_nrm, gs_nrm;
+    double* R = V + (i + 1) * ld;
     {
       DeferredScope t(timers, "davidson.RES_DUR");
-      double* R = V + (i + 1) * ld;
       k_residual<<<W.nstream, 256, size_t(k) * 8, st>>>(Nloc, k, V, AV, ld, cdev, lam, D,
-                                                        xfull + row0, R, W.partial);
-      ctx->launches++;
-      k_reduce_partials<<<1, 128, 0, st>>>(W.nstream, 1, W.partial, W.small);
+                                                        xfull + row0, R, W.partial, W.counter, W.scal.p);
       ctx->launches++;
       B2_CHECK_LAUNCH();
-      if (ctx->nranks > 1) comm_allreduce_sum(ctx, W.small, 1);
-      double s = 0.;
-      B2_CUDA(cudaMemcpyAsync(&s, W.small, 8, cudaMemcpyDeviceToHost, st));
+      if (ctx->nranks > 1) comm_allreduce_sum(ctx, W.scal, 1);
+    }
+    {
+      DeferredScope t(timers, "davidson.GS_DUR");
+      gram_schmidt_queue(W, k, V, R);
+      double* pin = reinterpret_cast<double*>(pinned_words(ctx));
+      B2_CUDA(cudaMemcpyAsync(pin, W.scal, 16, cudaMemcpyDeviceToHost, st));
       B2_CUDA(cudaStreamSynchronize(st));
-      res_nrm = std::sqrt(s);
+      res_nrm = std::sqrt(pin[0]);
+      gs_nrm = std::sqrt(pin[1]);
     }
     if (trace) { trace[2 * (i - 1)] = lam; trace[2 * (i - 1) + 1] = res_nrm; }
     if (res_nrm < tol) { converged = true; break; }
-    {
+    if (!(gs_nrm > GS_MIN_NORM)) {
       DeferredScope t(timers, "davidson.GS_DUR");
-      gram_schmidt(W, k, V, V + (i + 1) * ld, row0, N);
+      gram_schmidt_fallback(W, k, V, R, row0, N);
     }
   }
   // X (local rows live in xfull + row0) -> host, full vector on every rank

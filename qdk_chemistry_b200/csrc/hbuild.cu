@@ -1006,9 +1006,24 @@ struct GroupOut {
   unsigned ltmask;  // lanes of this group below this lane (warp-wide bit positions)
   unsigned gmask;   // lanes of this group
   int lig;          // lane index inside the group
+  int ndrop;        // DENSE: elements this lane wrote that fail the threshold
 };
-template <bool EVAL, int G>
-__device__ __forceinline__ void emit(GroupOut<G>& O, double thr, bool act, int32_t j, double v) {
+// DENSE (lists whose integrals are dense, i.e. next to nothing fails |h| > thr): every element goes to
+// its STRUCTURAL position -- the active lanes of a step are a prefix of the group, `nact` of them --
+// so a step is two stores and an add: no ballot, no prefix count, no branch. Elements that fail the
+// threshold are only counted; if the build finds any, one filtering pass packs the rows afterwards.
+template <bool EVAL, int G, bool DENSE>
+__device__ __forceinline__ void emit(GroupOut<G>& O, double thr, bool act, int nact, int32_t j, double v) {
+  if (DENSE) {
+    if (act) {
+      const int pos = O.rel + O.lig;
+      O.ci[pos] = j;
+      O.nz[pos] = v;
+      if (EVAL && !(fabs(v) > thr)) ++O.ndrop;
+    }
+    O.rel += nact;
+    return;
+  }
   const bool keep = act && (EVAL ? (fabs(v) > thr) : true);
   const unsigned m = __ballot_sync(0xffffffffu, keep);
   if (m == 0xffffffffu) {  // every lane of the warp survives (the common case): no prefix count
@@ -1032,7 +1047,7 @@ struct __align__(8) OsRec {
   uint32_t w;
 };
 
-template <bool EVAL, int G, bool SLICES>
+template <bool EVAL, int G, bool SLICES, bool DENSE = false>
 __global__ void __launch_bounds__(PW * 32, B2CI_PROD_MINB)
 k_rows_product(const ProdArgs A) {
   constexpr int RPW = 32 / G, RPC = PW * RPW;
@@ -1098,6 +1113,7 @@ k_rows_product(const ProdArgs A) {
   __builtin_assume(__isGlobal(O.ci));
   __builtin_assume(__isGlobal(O.nz));
   O.rel = 0;
+  O.ndrop = 0;
   const unsigned ltg = (1u << l) - 1u;   // lanes of the group below this lane (group-relative)
   const int gshift = gid * G;
   O.ltmask = ltg << gshift;
@@ -1105,6 +1121,7 @@ k_rows_product(const ProdArgs A) {
   O.gmask = (G == 32 ? 0xffffffffu : ((1u << (G & 31)) - 1u)) << gshift;
   const unsigned lt = (1u << lane) - 1u;
   const int len2pad = (len2max + G - 1) / G * G;  // records per row incl. padding (<= smem_r)
+  const int len2r = rowvalid ? len2 : 0;
   if (warp_active) {
     // ---- single-excitation elements and B2 records of this row
     for (int s = l; s < ns; s += G) {
@@ -1194,7 +1211,7 @@ k_rows_product(const ProdArgs A) {
             const int so = __shfl_sync(0xffffffffu, sing_l ? sord_l : -1, src & 31);
             if (so >= 0) v = sa[so];
           }
-          emit<EVAL, G>(O, A.thr, act, int32_t((r2t >> 2) * nb + k), v);
+          emit<EVAL, G, DENSE>(O, A.thr, act, rowvalid ? min(G, f - u0) : 0, int32_t((r2t >> 2) * nb + k), v);
         }
       }
       if (f >= nv) break;
@@ -1221,7 +1238,7 @@ k_rows_product(const ProdArgs A) {
               double v = __hiloint2double(__double2hiint(vr) ^ int(((w << 14) & 0x80000000u) ^ asign),
                                           __double2loint(vr));
               if (w & (1u << 16)) v = vself;
-              emit<EVAL, G>(O, A.thr, w != 0xFFFFFFFFu, int32_t(base + (w >> 18)), v);
+              emit<EVAL, G, DENSE>(O, A.thr, w != 0xFFFFFFFFu, min(G, max(0, len2r - u * G)), int32_t(base + (w >> 18)), v);
             }
           }
         } else {
@@ -1232,7 +1249,7 @@ k_rows_product(const ProdArgs A) {
             const double vr = SLICES ? Va[off] : ldg(Va + off);
             double v = __hiloint2double(__double2hiint(vr) ^ int((br.w & 0x80000000u) ^ asign), __double2loint(vr));
             if (br.w & (1u << 30)) v = vself;
-            emit<EVAL, G>(O, A.thr, act, int32_t(base + br.k2), v);
+            emit<EVAL, G, DENSE>(O, A.thr, act, min(G, max(0, len2r - t0)), int32_t(base + br.k2), v);
           }
         }
       } else {
@@ -1264,7 +1281,7 @@ k_rows_product(const ProdArgs A) {
               else if (db == 1) v = act ? sb[t2run + __popc(g01 & O.ltmask)] : 0.;
               else v = dgv;
               t2run += __popc(g01);
-              emit<EVAL, G>(O, A.thr, act, int32_t(base + (bpk >> 2)), v);
+              emit<EVAL, G, DENSE>(O, A.thr, act, rowvalid ? min(G, max(0, len4 - (c0 + u * G))) : 0, int32_t(base + (bpk >> 2)), v);
             }
           }
         }
@@ -1273,7 +1290,460 @@ k_rows_product(const ProdArgs A) {
     }
     sord0 += __popc(gm);
   }
+  if (DENSE && EVAL) {
+    int nd = O.ndrop;
+#pragma unroll
+    for (int d = G / 2; d > 0; d >>= 1) nd += __shfl_xor_sync(0xffffffffu, nd, d);
+    O.rel -= nd;
+  }
   if (rowvalid && l == 0) A.row_cnt[row] = O.rel;
+}
+
+// ------------------------------------------------------------------ dense fill of uniform lists
+// Full-CI lists are uniform: every beta string has the same number of neighbours at distance <= 2
+// (len2) and <= 4 (len4), so every row of an alpha run has the SAME output layout -- the segment of
+// adjacency entry e starts at the same offset in all of them. k_rows_dense uses that: per CTA (alpha
+// run r, 32 rows) one warp turns the run's adjacency into two shared-memory tables (live singles,
+// unit entries) with their segment offsets, and then each warp fills one row at a time in three
+// branch-free sweeps with all 32 lanes busy:
+//   singles sweep : flat index f over (live single s, B2 record t): one table read, one record
+//                   read, one integral from the TMA-staged slice, sign flip, two stores
+//   unit sweep    : one entry per lane (same-spin alpha doubles, dead singles)
+//   self sweep    : the B4(k) list (diagonal, beta singles, beta doubles)
+// Elements go to their structural positions; |h| <= thr is only counted (see emit<.., DENSE>), so
+// the inner loop has no ballot, no prefix sum and no data-dependent branch. Used when the integrals
+// are dense (< 2 % of V fails the threshold) and the slices fit; everything else keeps
+// k_rows_product.
+// element stores of the dense fill: address = base + pos (32-bit, unsigned) as ONE mad.wide + st
+__device__ __forceinline__ void st_elem(int32_t* ci, double* nz, uint32_t pos, int32_t col, double v) {
+  asm volatile(
+      "{\n\t.reg .u64 a, b;\n\t"
+      "mad.wide.u32 a, %2, 4, %0;\n\t"
+      "mad.wide.u32 b, %2, 8, %1;\n\t"
+      "st.global.u32 [a], %3;\n\t"
+      "st.global.f64 [b], %4;\n\t}"
+      ::"l"(ci), "l"(nz), "r"(pos), "r"(col), "d"(v));
+}
+struct DenseArgs {
+  ProdArgs P;
+  int len2, len4;  // uniform beta adjacency lengths
+  int tab_max;     // table entries per run (capacity)
+  int per_row;     // doubles of (sa | sb) per row in `sab`
+  uint32_t* desc;  // [nruns_blk][desc_max]: per output position (outside the self segment) entry << 4 | record t << 16
+  int tab_off;     // byte offset of the table in the CTA's shared memory
+  int rec_stride;  // records per beta string: len2 + 2 (neutral record, sa record)
+  int desc_max;    // row length rounded up to 4 (16-byte rows for the bulk copy)
+  uint4* tab;      // [nruns_blk][tab_max]: live singles first, unit entries behind them
+  int* tab_cnt;    // [nruns_blk][4]: live singles, units, offset of the self segment, row length
+  uint2* rec;      // [nb][len2]: B2 records in the sweep's form (+ padding)
+  double* sab;     // [nruns_blk * nb][per_row]: single-excitation elements of every row (alpha | beta)
+  int64_t run0;    // first alpha run of the row block
+};
+#ifndef B2CI_DENSE_WARPS
+#define B2CI_DENSE_WARPS 8
+#endif
+#ifndef B2CI_DENSE_ROWS
+#define B2CI_DENSE_ROWS 16
+#endif
+#ifndef B2CI_DENSE_MINB
+#define B2CI_DENSE_MINB 3
+#endif
+constexpr int DW = B2CI_DENSE_WARPS;     // warps per CTA
+constexpr int DROWS = B2CI_DENSE_ROWS;   // rows per CTA
+
+// ---- pre-passes of the dense fill (each O(rows x singles) or smaller, fully parallel) -------------------
+// tables of one alpha run: where every adjacency entry's segment starts in a row (the same in all rows)
+__global__ void __launch_bounds__(128)
+k_dense_tables(const DenseArgs D, int64_t nruns_blk) {
+  const ProdArgs& A = D.P;
+  const int lane = threadIdx.x & 31;
+  const int64_t rl = (int64_t(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+  if (rl >= nruns_blk) return;
+  const uint32_t r = uint32_t(D.run0 + rl);
+  const uint32_t nb = uint32_t(A.nb);
+  uint4* __restrict__ tab = D.tab + size_t(rl) * D.tab_max;
+  int* __restrict__ cnt = D.tab_cnt + size_t(rl) * 4;
+  const int64_t E0 = A.cptr[r], E1 = A.cptr[r + 1];
+  const unsigned lt = (1u << lane) - 1u;
+  int off0 = 0, nseg0 = 0, nunit0 = 0, sord0 = 0, nseg_total = 0;
+  for (int64_t eb = E0; eb < E1; eb += 32) {  // number of live singles (units are stored behind them)
+    const bool ev = eb + lane < E1;
+    const uint32_t r2t = ev ? A.crec[eb + lane].r2t : 2u;
+    nseg_total += __popc(__ballot_sync(0xffffffffu, ev && (r2t & 3u) == 1u));
+  }
+  int self_off = 0;
+  for (int64_t eb = E0; eb < E1; eb += 32) {
+    const bool ev = eb + lane < E1;
+    ARec a; a.r2t = 2u; a.meta = 0u;
+    double cv = 0.;
+    if (ev) { a = A.crec[eb + lane]; cv = A.cval[eb + lane]; }
+    const int kind = int(a.r2t & 3u);
+    const bool is_sing = ev && ((a.meta >> 18) & 1u);
+    const int len = !ev ? 0 : (kind == 0 ? D.len4 : (kind == 1 ? D.len2 : 1));
+    int incl = len;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      const int v = __shfl_up_sync(0xffffffffu, incl, d);
+      if (lane >= d) incl += v;
+    }
+    const int off = off0 + incl - len;
+    const unsigned m1 = __ballot_sync(0xffffffffu, ev && kind == 1);
+    const unsigned m2 = __ballot_sync(0xffffffffu, ev && kind == 2);
+    const unsigned m0 = __ballot_sync(0xffffffffu, ev && kind == 0);
+    const unsigned mg = __ballot_sync(0xffffffffu, is_sing);
+    const int so = sord0 + __popc(mg & lt);
+    const uint32_t r2 = a.r2t >> 2;
+    uint32_t* __restrict__ desc = D.desc + size_t(rl) * D.desc_max;
+    // every entry has the form {column base, -, byte offset of the value's home in shared memory, w}: pass 1
+    // reads value = *(home + record offset) and flips its sign by (record ^ w) -- the same code for all kinds
+    if (ev && kind == 1) {
+      // live single: home = its integral slice; w = record shift (0: the row is the bra, r < r2; 15: the
+      // ket) | slice index << 8 | sign of the alpha single << 31
+      const int e = nseg0 + __popc(m1 & lt);
+      tab[e] = make_uint4(r2 * nb, 0u, uint32_t(32 + size_t(so) * A.I.n2p * 8),
+                          (r < r2 ? 0u : 15u) | (uint32_t(so) << 8) | (((a.meta >> 16) & 1u) << 31));
+      for (int t = 0; t < D.len2; ++t) desc[off + t] = (uint32_t(e) << 4) | (uint32_t(t) << 16);
+    } else if (ev && kind == 2) {
+      // unit entry, two slots: {column base, -, home = the second slot, 0} {value}; it pairs with the row's
+      // neutral record (t = len2: column k, offset 0, no sign). A dead single's value is the row's sa[so]:
+      // slice index in w, paired with the record t = len2 + 1 whose same-beta flag selects sa.
+      const int e = nseg_total + 2 * (nunit0 + __popc(m2 & lt));
+      tab[e] = make_uint4(r2 * nb, 0u, uint32_t(D.tab_off + size_t(e + 1) * 16), is_sing ? uint32_t(so) << 8 : 0u);
+      tab[e + 1] = make_uint4(uint32_t(__double2loint(cv)), uint32_t(__double2hiint(cv)), 0u, 0u);
+      desc[off] = (uint32_t(e) << 4) | (uint32_t(D.len2 + (is_sing ? 1 : 0)) << 16);
+    }
+    if (m0) self_off = __shfl_sync(0xffffffffu, off, __ffs(m0) - 1);
+    off0 += __shfl_sync(0xffffffffu, incl, 31);
+    nseg0 += __popc(m1);
+    nunit0 += __popc(m2);
+    sord0 += __popc(mg);
+  }
+  if (lane == 0) { cnt[0] = nseg0; cnt[1] = nunit0; cnt[2] = self_off; cnt[3] = off0; }
+}
+// B2 records of every beta string in the form the singles sweep reads:
+//   x = k2, y = 8 * offset when the row is the bra | 8 * offset when it is the ket << 15 | is_self << 30 | sign << 31
+__global__ void k_dense_rec(const DenseArgs D) {
+  const ProdArgs& A = D.P;
+  const int64_t idx = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (idx >= A.nb * D.rec_stride) return;
+  const int64_t k = idx / D.rec_stride;
+  const int t = int(idx - k * D.rec_stride);
+  if (t >= D.len2) {  // the neutral record of unit entries / the record that selects sa[so]
+    D.rec[idx] = make_uint2(uint32_t(k), t == D.len2 ? 0u : (1u << 30));
+    return;
+  }
+  const B2Rec br = A.b2rec[k * D.len2 + t];  // uniform lists: b2_ptr[k] == k * len2
+  const uint32_t o0 = br.pk & 0xFFFu, o1 = (br.pk >> 12) & 0xFFFu;
+  const bool up = (br.pk >> 26) & 1u;  // k2 > k
+  D.rec[idx] = make_uint2(br.k2, ((up ? o0 : o1) << 3) | ((up ? o1 : o0) << 18) | (((br.pk >> 25) & 1u) << 30) |
+                                     (((br.pk >> 24) & 1u) << 31));
+}
+// single-excitation elements of every row: leading sum + the other spin's V_red terms in ascending orbital
+// order (the reference's order of additions, matrix_elements.hpp:176-186)
+constexpr int SAB_ROWS = 64;  // rows of one alpha run per CTA
+template <typename S, bool SMEM>
+__global__ void __launch_bounds__(256)
+k_dense_sab(const DenseArgs D, int64_t nrows_tot, unsigned inv_per) {
+  // CTA = (alpha run, 64 consecutive beta strings); one item (row, q) per thread and step. The gathers of
+  // V_red (8 bytes per lane, all over the n^3 table) run at two sectors per clock through L1 and were this
+  // kernel's whole cost: the table is staged in shared memory once per CTA instead (SMEM; n <= 18).
+  // Strings as S (32-bit words when norb <= 32).
+  extern __shared__ double s_vr[];
+  const ProdArgs& A = D.P;
+  const int n = A.I.n;
+  const size_t n2 = size_t(n) * n;
+  if (SMEM) {
+    for (int i = threadIdx.x; i < n * n * n; i += blockDim.x) s_vr[i] = A.I.Vr[i];
+    __syncthreads();
+  }
+  const unsigned per = unsigned(D.per_row);
+  const uint32_t r = uint32_t(D.run0 + blockIdx.y);
+  const unsigned k0 = blockIdx.x * SAB_ROWS;
+  const unsigned nrows_cta = min(unsigned(SAB_ROWS), unsigned(A.nb) - k0);
+  const int64_t sp = A.sptr[r];
+  const unsigned ns = unsigned(A.sptr[r + 1] - sp);
+  const S abits = S(A.run_alpha[r]);
+  for (unsigned f = threadIdx.x; f < nrows_cta * per; f += blockDim.x) {
+    const unsigned j = __umulhi(f, inv_per);  // f / per
+    const unsigned q = f - j * per;
+    const unsigned k = k0 + j;
+    const int64_t rowl = int64_t(blockIdx.y) * A.nb + k;
+    if (rowl >= nrows_tot) continue;
+    double out = 0.;
+    uint32_t m = 0u;
+    double h = 0.;
+    S bits = 0;
+    bool live = false;
+    if (q < unsigned(A.smem_a)) {
+      if (q < ns) {
+        m = A.smeta[sp + q];
+        h = A.slead[sp + q];
+        bits = S(A.tmpl_beta[k]);
+        live = true;
+      }
+    } else if (q - unsigned(A.smem_a) < unsigned(D.len2)) {
+      const int64_t e = int64_t(k) * D.len2 + (q - A.smem_a);
+      m = A.b2_meta[e];
+      h = A.b2_val[e];
+      bits = abits;
+      live = true;  // (the self slot is never read)
+    }
+    if (live) {
+      // the other spin's V_red terms in ascending orbital order (the reference's order of additions)
+      const size_t vo = ((m >> 8) & 0xFFu) * n + (m & 0xFFu) * n2;
+      const double* Vr = SMEM ? s_vr + vo : A.I.Vr + vo;
+      for (S qq = bits; qq; qq &= qq - 1) {
+        const int p = (sizeof(S) == 4 ? __ffs(int(qq)) : __ffsll((long long)qq)) - 1;
+        h += SMEM ? Vr[p] : ldg(Vr + p);
+      }
+      out = flip_sign_if(h, m >> 16);
+    }
+    D.sab[rowl * per + q] = out;
+  }
+}
+
+__device__ __forceinline__ double lds_f64(uint32_t saddr) {
+  double v;
+  asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(saddr));
+  return v;
+}
+template <bool EVAL>
+__global__ void __launch_bounds__(DW * 32, B2CI_DENSE_MINB)
+k_rows_dense(const DenseArgs D) {
+  const ProdArgs& A = D.P;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  // layout: [mbarrier 16 B][pad 16 B][slices][table: uint4 x tab_max][desc: u32 x desc_max]
+  //         [rec: DROWS x len2 x 8 B, padded][sab: DROWS x per_row]
+  uint64_t* bar = reinterpret_cast<uint64_t*>(smem_raw);
+  double* slices = reinterpret_cast<double*>(smem_raw + 32);
+  uint4* tab = reinterpret_cast<uint4*>(slices + size_t(A.nslice_max) * A.I.n2p);
+  uint32_t* desc = reinterpret_cast<uint32_t*>(tab + D.tab_max);
+  uint2* recs = reinterpret_cast<uint2*>(desc + D.desc_max);
+  const int len2 = D.len2, len4 = D.len4;
+  const int rstride = D.rec_stride;
+  const size_t rec_bytes_max = (size_t(DROWS) * rstride * 8 + 15) & ~size_t(15);
+  double* sab = reinterpret_cast<double*>(reinterpret_cast<unsigned char*>(recs) + rec_bytes_max);
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int64_t cpr = (A.nb + DROWS - 1) / DROWS;  // chunks per run
+  const int64_t rl = blockIdx.x / cpr;              // run of the block, local
+  const uint32_t r = uint32_t(D.run0 + rl);
+  const int64_t k0 = (blockIdx.x % cpr) * DROWS;
+  const uint64_t ai = A.run_alpha[r];
+  const uint32_t nb = uint32_t(A.nb);
+  const int n = A.I.n;
+  const int nrows_cta = int(min(int64_t(DROWS), int64_t(nb) - k0));
+  if (ai == 0) {  // alpha-empty determinants are skipped (uniform over the CTA)
+    for (int j = threadIdx.x; j < nrows_cta; j += blockDim.x) {
+      const int64_t i = int64_t(r) * nb + k0 + j;
+      if (i >= A.row_begin && i < A.row_begin + A.nrows) A.row_cnt[i - A.row_begin] = 0;
+    }
+    return;
+  }
+  if (threadIdx.x == 0) mbar_init(bar, 1);
+  __syncthreads();
+  if (w == 0) {
+    // ---- everything the CTA reads comes in by bulk (TMA) copies: the integral slices of the run's live
+    // singles, the run's tables and position descriptors, the B2 records and the single-excitation
+    // elements of its rows
+    const int64_t sp = A.sptr[r];
+    const int ns = int(A.sptr[r + 1] - sp);
+    const uint32_t bytes = uint32_t(A.I.n2p) * 8u;
+    const uint32_t tab_bytes = uint32_t(D.tab_max) * 16u;
+    const uint32_t desc_bytes = uint32_t(D.desc_max) * 4u;
+    const uint32_t rec_bytes = uint32_t((size_t(nrows_cta) * rstride * 8 + 15) & ~size_t(15));
+    const uint32_t sab_bytes = uint32_t(size_t(nrows_cta) * D.per_row * 8);
+    int mine = 0;
+    for (int q = lane; q < ns; q += 32) mine += ((A.smeta[sp + q] >> 17) & 1u) ? 0 : 1;
+    const int total = __reduce_add_sync(0xffffffffu, mine);
+    if (lane == 0) {
+      mbar_arrive_expect_tx(bar, uint32_t(total) * bytes + tab_bytes + desc_bytes + rec_bytes + sab_bytes);
+      bulk_g2s(tab, D.tab + size_t(rl) * D.tab_max, tab_bytes, bar);
+      bulk_g2s(desc, D.desc + size_t(rl) * D.desc_max, desc_bytes, bar);
+      bulk_g2s(recs, D.rec + size_t(k0) * rstride, rec_bytes, bar);
+      bulk_g2s(sab, D.sab + (size_t(rl) * nb + k0) * D.per_row, sab_bytes, bar);
+    }
+    __syncwarp();
+    for (int q = lane; q < ns; q += 32) {
+      const uint32_t m = A.smeta[sp + q];
+      if ((m >> 17) & 1u) continue;
+      const size_t pq = ((m >> 8) & 0xFFu) + size_t(m & 0xFFu) * n;
+      bulk_g2s(slices + size_t(q) * A.I.n2p, A.I.Vt + pq * A.I.n2p, bytes, bar);
+    }
+  }
+  // row scalars of the CTA's rows (slot offset, diagonal element): fetched by one thread per row while the
+  // bulk copies are in flight, so that no row starts with a dependent global load
+  __shared__ int64_t s_out0[DROWS];
+  __shared__ double s_diag[DROWS];
+  if (w >= 1 && int(threadIdx.x) - 32 < nrows_cta) {
+    const int j = int(threadIdx.x) - 32;
+    const int64_t i = int64_t(r) * nb + k0 + j;
+    const bool in = i >= A.row_begin && i < A.row_begin + A.nrows;
+    s_out0[j] = in ? A.rowptr[i - A.row_begin] : -1;
+    s_diag[j] = in ? A.diag[i - A.row_begin] : 0.;
+  }
+  const int* __restrict__ cnt = D.tab_cnt + size_t(rl) * 4;
+  const int self_off = cnt[2], row_len = cnt[3];
+  const unsigned lt = (1u << lane) - 1u;
+  const uint32_t s_base = smem_u32(smem_raw), s_tab = smem_u32(tab);
+  __syncthreads();
+  mbar_wait(bar, 0);
+  for (int j = w; j < nrows_cta; j += DW) {
+    const int64_t out0 = s_out0[j];
+    if (out0 < 0) continue;  // outside the row block (warp-uniform)
+    const int64_t row = int64_t(r) * nb + k0 + j - A.row_begin;
+    const uint32_t k = uint32_t(k0 + j);
+    const int64_t b4s = int64_t(k) * len4;  // uniform lists: b4_ptr[k] == k * len4
+    const double dgv = s_diag[j];
+    const uint32_t s_sa = smem_u32(sab + size_t(j) * D.per_row);
+    const double* sb = sab + size_t(j) * D.per_row + A.smem_a;
+    const uint2* rec = recs + size_t(j) * rstride;
+    int ndrop = 0;
+    // the B4(k) list lives in global memory (L2): its first loads are in flight during the first pass
+    constexpr int U4 = 4;
+    uint32_t bpk_n[U4];
+    double bv_n[U4];
+    // ---- pass 2's windows are aligned like pass 1's: absolute position a = out0 + p, 32 per step
+    const int64_t sa0 = out0 + self_off, sa1 = sa0 + len4;     // the self segment, absolute
+    const int64_t sw0 = sa0 & ~int64_t(31);                    // its first window
+#pragma unroll
+    for (int u = 0; u < U4; ++u) {
+      const int64_t t = sw0 + u * 32 + lane - sa0;
+      const int64_t e4 = b4s + min(max(t, int64_t(0)), int64_t(len4 - 1));
+      bpk_n[u] = __ldg(A.b4 + e4);
+      bv_n[u] = ldg(A.b4_val + e4);
+    }
+    // ---- pass 1: every position outside the self segment, in order; each warp store is ONE contiguous,
+    // 128-byte (colind) / 256-byte (nzval) aligned range -- what the store path wants (a store split in
+    // two ranges costs more than twice as much, scripts/micro/store_pattern.cu). Branch-free: singles,
+    // unit doubles and the sa[so] cases differ only in where the value is read from.
+    {
+      const int head = int(out0 & 31);
+      int32_t* ci_row = A.colind + out0;
+      double* nz_row = A.nzval + out0;
+      const uint32_t s_rec = smem_u32(rec);
+#pragma unroll 1
+      for (int half = 0; half < 2; ++half) {
+        const int lo = half == 0 ? 0 : self_off + len4, hi = half == 0 ? self_off : row_len;
+#pragma unroll 4
+        for (int pw = ((lo + head) & ~31) - head; pw < hi; pw += 32) {
+          const int pp = pw + lane;
+          if (pp >= lo && pp < hi) {
+            const uint32_t d = desc[pp];
+            const uint32_t e16 = d & 0xFFF0u;
+            uint4 ent;
+            asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(ent.x), "=r"(ent.y), "=r"(ent.z), "=r"(ent.w) : "r"(s_tab + e16));
+            uint2 rc;
+            asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(rc.x), "=r"(rc.y) : "r"(s_rec + ((d >> 13) & 0x7FFF8u)));
+            // value = *(home + record offset), sign = record ^ entry; the same-beta element of a single (and a
+            // dead single) reads the row's sa[so] instead
+            uint32_t addr = s_base + ent.z + ((rc.y >> (ent.w & 31u)) & 0x7FF8u);
+            uint32_t sg = (rc.y ^ ent.w) & 0x80000000u;
+            if (rc.y & (1u << 30)) {
+              addr = s_sa + ((ent.w >> 5) & 0x7FFF8u);
+              sg = 0u;
+            }
+            const double vr = lds_f64(addr);
+            const double v = __hiloint2double(__double2hiint(vr) ^ int(sg), __double2loint(vr));
+            ci_row[pp] = int32_t(ent.x + rc.x);
+            nz_row[pp] = v;
+            if (EVAL && !(fabs(v) > A.thr)) ++ndrop;
+          }
+        }
+      }
+    }
+    // ---- pass 2: the self segment, same alpha string x B4(k); U4 steps' loads are issued together
+    {
+      const uint32_t base = r * nb;
+      int t2run = 0;
+      for (int64_t aw = sw0; aw < sa1; aw += U4 * 32) {
+        uint32_t bpk_u[U4];
+        double bv_u[U4];
+#pragma unroll
+        for (int u = 0; u < U4; ++u) { bpk_u[u] = bpk_n[u]; bv_u[u] = bv_n[u]; }
+        if (aw + U4 * 32 < sa1) {
+#pragma unroll
+          for (int u = 0; u < U4; ++u) {
+            const int64_t t = aw + (U4 + u) * 32 + lane - sa0;
+            const int64_t e4 = b4s + min(max(t, int64_t(0)), int64_t(len4 - 1));
+            bpk_n[u] = __ldg(A.b4 + e4);
+            bv_n[u] = ldg(A.b4_val + e4);
+          }
+        }
+#pragma unroll
+        for (int u = 0; u < U4; ++u) {
+          const int64_t a = aw + u * 32 + lane;
+          if (aw + u * 32 < sa1) {  // warp-uniform
+            const bool act = a >= sa0 && a < sa1;
+            const uint32_t bpk = bpk_u[u];
+            const int db = int(bpk & 3u);
+            const unsigned g01 = __ballot_sync(0xffffffffu, act && db <= 1);
+            double v;
+            if (db == 2) v = bv_u[u];
+            else if (db == 1) v = act ? sb[t2run + __popc(g01 & lt)] : 0.;
+            else v = dgv;
+            t2run += __popc(g01);
+            if (act) {
+              A.colind[a] = int32_t(base + (bpk >> 2));
+              A.nzval[a] = v;
+              if (EVAL && !(fabs(v) > A.thr)) ++ndrop;
+            }
+          }
+        }
+      }
+    }
+    if (EVAL) ndrop = __reduce_add_sync(0xffffffffu, ndrop);
+    if (lane == 0) A.row_cnt[row] = row_len - ndrop;
+  }
+}
+
+// DENSE builds that did drop elements: pack every row, keeping |h| > thr in order
+__global__ void __launch_bounds__(ROW_WARPS * 32)
+k_compact_rows_filter(int64_t nrows, const int64_t* __restrict__ slot_ptr, const int64_t* __restrict__ rowptr,
+                      const int32_t* __restrict__ ci_in, const double* __restrict__ nz_in, double thr,
+                      int32_t* __restrict__ ci_out, double* __restrict__ nz_out) {
+  const int lane = threadIdx.x & 31;
+  const int64_t row = (int64_t(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+  if (row >= nrows) return;
+  const int64_t src = slot_ptr[row], len = slot_ptr[row + 1] - src;
+  int64_t dst = rowptr[row];
+  for (int64_t t0 = 0; t0 < len; t0 += 32) {
+    const int64_t t = t0 + lane;
+    int32_t c = 0;
+    double v = 0.;
+    if (t < len) { c = ci_in[src + t]; v = nz_in[src + t]; }
+    const bool keep = t < len && fabs(v) > thr;
+    const unsigned m = __ballot_sync(0xffffffffu, keep);
+    if (keep) {
+      const int64_t pos = dst + __popc(m & ((1u << lane) - 1u));
+      ci_out[pos] = c;
+      nz_out[pos] = v;
+    }
+    dst += __popc(m);
+  }
+}
+// shape of a rectangular list: min / max of the beta adjacency lengths and the longest compacted run adjacency
+__global__ void k_shape_minmax(const int64_t* __restrict__ b2_ptr, const int64_t* __restrict__ b4_ptr, int64_t nb,
+                               const int64_t* __restrict__ cptr, const int32_t* __restrict__ run_cnt, int64_t nruns,
+                               int* __restrict__ out /* 6, pre-set */) {
+  const int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i < nb) {
+    const int l2 = int(b2_ptr[i + 1] - b2_ptr[i]), l4 = int(b4_ptr[i + 1] - b4_ptr[i]);
+    atomicMin(out + 0, l2); atomicMax(out + 1, l2);
+    atomicMin(out + 2, l4); atomicMax(out + 3, l4);
+  }
+  if (i < nruns) {
+    atomicMax(out + 4, int(cptr[i + 1] - cptr[i]));
+    // structural row length of the run's rows if the beta lists are uniform (lengths of string 0)
+    const int64_t l2 = b2_ptr[1] - b2_ptr[0], l4 = b4_ptr[1] - b4_ptr[0];
+    const int64_t len = run_cnt[4 * i] * l4 + run_cnt[4 * i + 1] * l2 + run_cnt[4 * i + 2];
+    atomicMax(out + 5, int(min(len, int64_t(INT32_MAX))));
+  }
+}
+__global__ void k_count_small(const double* __restrict__ v, int64_t n, double thr, unsigned int* __restrict__ cnt) {
+  const int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+  const bool small = i < n && !(fabs(v[i]) > thr);
+  const unsigned m = __ballot_sync(0xffffffffu, small);
+  if ((threadIdx.x & 31) == 0 && m) atomicAdd(cnt, unsigned(__popc(m)));
 }
 
 // move the surviving prefix of every structural row slot to its final position
@@ -2006,10 +2476,17 @@ void hbuild_csr(b2ci_ctx* ctx, const b2ci_dets* dets, int64_t row_begin, int64_t
     DevBuf<uint32_t> a_meta(nadj_h > 0 ? nadj_h : 1), b4_meta(nb4_h > 0 ? nb4_h : 1);
     DevBuf<double> a_val(nadj_h > 0 ? nadj_h : 1);
     DevBuf<int32_t> ecnt(nruns), scnt(nruns);
+    DevBuf<unsigned int> small_cnt(1);
+    DevBuf<int> shape(6);
     {
       DeferredScope t(DT, "h_build.setup");
       DevBuf<unsigned char> dead_ov(size_t(ctx->norb) * ctx->norb);
       const int nn = ctx->norb * ctx->norb;
+      // how sparse are the integrals under this threshold? decides between the compacting and the dense fill
+      B2_CUDA(cudaMemsetAsync(small_cnt, 0, sizeof(unsigned int), st));
+      const int64_t n4 = int64_t(nn) * nn;
+      k_count_small<<<unsigned((n4 + 255) / 256), 256, 0, st>>>(ctx->ints.V, n4, thr, small_cnt);
+      ctx->launches++;
       k_dead_ov<<<(nn + 127) / 128, 128, 0, st>>>(ctx->ints, thr, dead_ov);
       k_pair_meta<<<ga, 256, 0, st>>>(ctx->ints, run_alpha, nruns, adj_ptr, adj, thr, dead_ov, a_meta, a_val);
       k_pair_meta<<<gb, 256, 0, st>>>(ctx->ints, dets->beta, int32_t(nb), b2_ptr, b2, thr, nullptr, b2_meta, b2_val);
@@ -2021,6 +2498,12 @@ void hbuild_csr(b2ci_ctx* ctx, const b2ci_dets* dets, int64_t row_begin, int64_t
       B2_CHECK_LAUNCH();
       exclusive_scan_i32_to_i64(ctx, ecnt, cptr, nruns);
       exclusive_scan_i32_to_i64(ctx, scnt, sptr, nruns);
+      const int init[6] = {INT32_MAX, 0, INT32_MAX, 0, 0, 0};
+      B2_CUDA(cudaMemcpyAsync(shape, init, sizeof(init), cudaMemcpyHostToDevice, st));
+      const int64_t nmx = std::max<int64_t>(nb, nruns);
+      k_shape_minmax<<<unsigned((nmx + 255) / 256), 256, 0, st>>>(b2_ptr, b4_ptr, nb, cptr, run_cnt, nruns, shape);
+      ctx->launches++;
+      B2_CHECK_LAUNCH();
     }
     ProdArgs P;
     P.I = ctx->ints;
@@ -2045,6 +2528,8 @@ void hbuild_csr(b2ci_ctx* ctx, const b2ci_dets* dets, int64_t row_begin, int64_t
     DevBuf<int64_t> slot_ptr(nrows + 1);
     DevBuf<int32_t> struct_cnt(nrows);
     int64_t nslots = 0, ncadj = 0, nsing = 0;
+    unsigned int nsmall = 0;
+    int shp[6] = {0, 0, 0, 0, 0, 0};
     int32_t rc[4] = {0, 0, 0, 0};
     int64_t bp[2] = {0, 0}, bq[2] = {0, 0};
     {
@@ -2064,9 +2549,13 @@ void hbuild_csr(b2ci_ctx* ctx, const b2ci_dets* dets, int64_t row_begin, int64_t
       B2_CUDA(cudaMemcpyAsync(pin + 4, run_cnt.p, 16, cudaMemcpyDeviceToHost, st));
       B2_CUDA(cudaMemcpyAsync(pin + 6, b2_ptr.p, 16, cudaMemcpyDeviceToHost, st));
       B2_CUDA(cudaMemcpyAsync(pin + 8, b4_ptr.p, 16, cudaMemcpyDeviceToHost, st));
+      B2_CUDA(cudaMemcpyAsync(pin + 10, small_cnt.p, sizeof(unsigned int), cudaMemcpyDeviceToHost, st));
+      B2_CUDA(cudaMemcpyAsync(pin + 11, shape.p, 6 * sizeof(int), cudaMemcpyDeviceToHost, st));
       mark("metadata + count queued");
       B2_CUDA(cudaStreamSynchronize(st));
       nslots = pin[0]; ncadj = pin[1]; nsing = pin[2];
+      nsmall = *reinterpret_cast<const unsigned int*>(pin + 10);
+      memcpy(shp, pin + 11, 6 * sizeof(int));
       memcpy(rc, pin + 4, 16); memcpy(bp, pin + 6, 16); memcpy(bq, pin + 8, 16);
       mark("metadata + count (sync C)");
     }
@@ -2092,6 +2581,12 @@ void hbuild_csr(b2ci_ctx* ctx, const b2ci_dets* dets, int64_t row_begin, int64_t
     nz_s.p = static_cast<double*>(big_alloc(ctx, 1, size_t(nslots > 0 ? nslots : 1) * sizeof(double), &nz_cap));
     nz_s.n = nz_cap / sizeof(double);
     mark("slot allocation");
+    bool dense = false;
+    DevBuf<uint4> dn_tab;
+    DevBuf<uint32_t> dn_desc;
+    DevBuf<int> dn_cnt;
+    DevBuf<uint2> dn_rec;
+    DevBuf<double> dn_sab;
     {
       DeferredScope t(DT, "h_build.fill");
       P.row_cnt = kept;
@@ -2141,18 +2636,85 @@ void hbuild_csr(b2ci_ctx* ctx, const b2ci_dets* dets, int64_t row_begin, int64_t
         B2_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
         kern<<<grid, PW * 32, smem, st>>>(P);
       };
-      auto launch_g = [&](auto ev, auto sl) {
-        constexpr bool EV = decltype(ev)::value, SL = decltype(sl)::value;
-        if (G == 8) launch(k_rows_product<EV, 8, SL>);
-        else if (G == 16) launch(k_rows_product<EV, 16, SL>);
-        else launch(k_rows_product<EV, 32, SL>);
+      auto launch_g = [&](auto ev, auto sl, auto dn) {
+        constexpr bool EV = decltype(ev)::value, SL = decltype(sl)::value, DN = decltype(dn)::value;
+        if (G == 8) launch(k_rows_product<EV, 8, SL, DN>);
+        else if (G == 16) launch(k_rows_product<EV, 16, SL, DN>);
+        else launch(k_rows_product<EV, 32, SL, DN>);
       };
-      if (thr > 0.0) {
-        if (slices) launch_g(std::true_type{}, std::true_type{});
-        else launch_g(std::true_type{}, std::false_type{});
+      // dense fill (structural positions, drops only counted): when fewer than 2 % of the two-electron
+      // integrals fail the threshold. Sparse models (Hubbard: 99 % zeros) keep the compacting fill, which
+      // writes only what survives.
+      const int64_t n4 = int64_t(ctx->norb) * ctx->norb * ctx->norb * ctx->norb;
+      dense = slices && double(nsmall) < 0.02 * double(n4);
+      // B2CI_HBUILD_DENSE: 0 = compacting fill, 1 = dense emit in the product kernel, 2 (default where it
+      // applies) = the specialised kernel for uniform lists
+      int dense_mode = dense ? 2 : 0;
+      if (const char* env = getenv("B2CI_HBUILD_DENSE")) dense_mode = slices ? atoi(env) : 0;
+      dense = dense_mode != 0;
+      const bool uniform = shp[0] == shp[1] && shp[2] == shp[3] && shp[0] > 0 && ctx->ints.n2p <= 4096;
+      const int dense_per_row = (P.smem_a + P.smem_b + 1) & ~1;  // doubles of (sa | sb) per row, 16-byte multiple
+      // structural row length of the list (uniform): self x len4 + live singles x len2 + units of the longest run
+      const int dense_desc_max = (shp[5] + 3) & ~3;  // longest structural row, 16-byte multiple
+      const size_t dense_smem = 32 + slice_bytes + size_t(2 * shp[4] + 2) * 16 + size_t(dense_desc_max) * 4 +
+                                ((size_t(DROWS) * (shp[0] + 2) * 8 + 15) & ~size_t(15)) + size_t(DROWS) * dense_per_row * sizeof(double);
+      if (dense_mode == 2 && (!uniform || dense_smem > 110 * 1024 || 2 * shp[4] + 2 >= 4095 || shp[0] + 2 >= 4095 ||
+                              nb * dense_per_row >= (int64_t(1) << 24)))
+        dense_mode = 1;
+      ctx->timers["h_build.dense_fill"] = double(dense_mode);
+      if (dense_mode == 2) {
+        DenseArgs DA;
+        DA.P = P;
+        DA.len2 = shp[0];
+        DA.len4 = shp[2];
+        DA.per_row = dense_per_row;
+        DA.run0 = row_begin / nb;
+        const int64_t nrows_tot = nruns_blk * nb;
+        DA.desc_max = dense_desc_max;
+        DA.tab_off = int(32 + slice_bytes);
+        DA.rec_stride = shp[0] + 2;
+        DA.tab_max = 2 * shp[4] + 2;
+        dn_desc.alloc(size_t(nruns_blk) * DA.desc_max);
+        DA.desc = dn_desc;
+        dn_tab.alloc(size_t(nruns_blk) * DA.tab_max);
+        dn_cnt.alloc(size_t(nruns_blk) * 4);
+        dn_rec.alloc(size_t(nb) * DA.rec_stride + 2 * DROWS);  // padding: the last chunk's copy is rounded up to 16 B
+        dn_sab.alloc(size_t(nrows_tot) * DA.per_row);
+        DA.tab = dn_tab; DA.tab_cnt = dn_cnt; DA.rec = dn_rec; DA.sab = dn_sab;
+        k_dense_tables<<<unsigned((nruns_blk * 32 + 127) / 128), 128, 0, st>>>(DA, nruns_blk);
+        k_dense_rec<<<unsigned((nb * DA.rec_stride + 255) / 256), 256, 0, st>>>(DA);
+        {
+          const unsigned inv_per = unsigned((uint64_t(1) << 32) / unsigned(DA.per_row)) + 1u;
+          const dim3 gs(unsigned((nb + SAB_ROWS - 1) / SAB_ROWS), unsigned(nruns_blk));
+          const size_t vr_bytes = size_t(ctx->norb) * ctx->norb * ctx->norb * 8;
+          if (vr_bytes <= 46 * 1024) {
+            if (ctx->norb <= 32) k_dense_sab<uint32_t, true><<<gs, 256, vr_bytes, st>>>(DA, nrows_tot, inv_per);
+            else k_dense_sab<uint64_t, true><<<gs, 256, vr_bytes, st>>>(DA, nrows_tot, inv_per);
+          } else {
+            if (ctx->norb <= 32) k_dense_sab<uint32_t, false><<<gs, 256, 0, st>>>(DA, nrows_tot, inv_per);
+            else k_dense_sab<uint64_t, false><<<gs, 256, 0, st>>>(DA, nrows_tot, inv_per);
+          }
+        }
+        ctx->launches += 3;
+        B2_CHECK_LAUNCH();
+        const int64_t dcpr = (nb + DROWS - 1) / DROWS;
+        const unsigned dgrid = unsigned(nruns_blk * dcpr);
+        auto dl = [&](auto kern) {
+          if (dense_smem > 48 * 1024)
+            B2_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(dense_smem)));
+          B2_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+          kern<<<dgrid, DW * 32, dense_smem, st>>>(DA);
+        };
+        if (thr > 0.0) dl(k_rows_dense<true>);
+        else dl(k_rows_dense<false>);
+      } else if (thr > 0.0) {
+        if (dense) launch_g(std::true_type{}, std::true_type{}, std::true_type{});
+        else if (slices) launch_g(std::true_type{}, std::true_type{}, std::false_type{});
+        else launch_g(std::true_type{}, std::false_type{}, std::false_type{});
       } else {
-        if (slices) launch_g(std::false_type{}, std::true_type{});
-        else launch_g(std::false_type{}, std::false_type{});
+        if (dense) launch_g(std::false_type{}, std::true_type{}, std::true_type{});
+        else if (slices) launch_g(std::false_type{}, std::true_type{}, std::false_type{});
+        else launch_g(std::false_type{}, std::false_type{}, std::false_type{});
       }
       ctx->launches++;
       B2_CHECK_LAUNCH();
@@ -2174,8 +2736,9 @@ void hbuild_csr(b2ci_ctx* ctx, const b2ci_dets* dets, int64_t row_begin, int64_t
         DeferredScope t(DT, "h_build.thresh");
         DevBuf<int32_t> ci_f(nnz > 0 ? nnz : 1);
         DevBuf<double> nz_f(nnz > 0 ? nnz : 1);
-        k_compact_rows<<<unsigned((nrows * 32 + ROW_WARPS * 32 - 1) / (ROW_WARPS * 32)), ROW_WARPS * 32, 0, st>>>(
-            nrows, slot_ptr, rowptr, ci_s, nz_s, ci_f, nz_f);
+        const unsigned gc = unsigned((nrows * 32 + ROW_WARPS * 32 - 1) / (ROW_WARPS * 32));
+        if (dense) k_compact_rows_filter<<<gc, ROW_WARPS * 32, 0, st>>>(nrows, slot_ptr, rowptr, ci_s, nz_s, thr, ci_f, nz_f);
+        else k_compact_rows<<<gc, ROW_WARPS * 32, 0, st>>>(nrows, slot_ptr, rowptr, ci_s, nz_s, ci_f, nz_f);
         ctx->launches++;
         B2_CHECK_LAUNCH();
         B2_CUDA(cudaStreamSynchronize(st));
