@@ -175,17 +175,10 @@ void sym_eig_lowest(int n, const double* A, int lda, double* lambda, double* vec
     const int m = n - i - 1;  // reflector acts on rows i+1 .. n-1
     double* x = &M(i + 1, i);
     const double alpha = x[0];
-    // ||x(1:)||: scaled sum of squares (one pass for the scale, one for the sum) -- std::hypot per
-    // element made this the most expensive line of the whole reduction
-    double xmax = 0.0;
-    for (int k = 1; k < m; ++k) xmax = std::max(xmax, std::fabs(x[k]));
+    // (std::hypot accumulation: slow, but the bits of the Ritz vector decide ties at the ASCI cut in the
+    // natural-orbital runs that are pinned to the reference -- keep them)
     double xnorm = 0.0;
-    if (xmax > 0.0) {
-      const double inv = 1.0 / xmax;
-      double ss = 0.0;
-      for (int k = 1; k < m; ++k) { const double t = x[k] * inv; ss += t * t; }
-      xnorm = xmax * std::sqrt(ss);
-    }
+    for (int k = 1; k < m; ++k) xnorm = std::hypot(xnorm, x[k]);
     d[i] = M(i, i);
     if (xnorm == 0.0) {
       tau[i] = 0.0;
@@ -283,11 +276,8 @@ void sym_eig_lowest(int n, const double* A, int lda, double* lambda, double* vec
     y[n - 1] /= dd[n - 1];  // backward: U^-1
     if (n > 1) y[n - 2] = (y[n - 2] - du[n - 2] * y[n - 1]) / dd[n - 2];
     for (int i = n - 3; i >= 0; --i) y[i] = (y[i] - du[i] * y[i + 1] - du2[i] * y[i + 2]) / dd[i];
-    double ymax = 0.0;
-    for (int i = 0; i < n; ++i) ymax = std::max(ymax, std::fabs(y[i]));
-    double ss = 0.0;
-    for (int i = 0; i < n; ++i) { const double t = y[i] / ymax; ss += t * t; }
-    const double nrm = ymax * std::sqrt(ss);
+    double nrm = 0.0;
+    for (int i = 0; i < n; ++i) nrm = std::hypot(nrm, y[i]);
     for (int i = 0; i < n; ++i) y[i] /= nrm;
   }
   // ---- back-transformation x = H_0 H_1 ... H_{n-2} y
@@ -301,8 +291,7 @@ void sym_eig_lowest(int n, const double* A, int lda, double* lambda, double* vec
     for (int k = 0; k < m; ++k) y[i + 1 + k] -= s * v[k];
   }
   double nrm = 0.0;
-  for (int i = 0; i < n; ++i) nrm += y[i] * y[i];  // y has unit norm up to rounding here
-  nrm = std::sqrt(nrm);
+  for (int i = 0; i < n; ++i) nrm = std::hypot(nrm, y[i]);
   for (int i = 0; i < n; ++i) vec[i] = y[i] / nrm;
   // Rayleigh quotient of the back-transformed vector: second-order accurate in the vector error
   double num = 0.0;
@@ -539,7 +528,10 @@ void project(Work& W, int k, const double* V, double* w, bool with_norm = false)
 constexpr double GS_MIN_NORM = 1e-12;
 void gram_schmidt_queue(Work& W, int k, const double* V, double* w) {
   project(W, k, V, w);
-  project(W, k, V, w, true);
+  project(W, k, V, w);
+  // ||w||^2 by the same dot-product kernel (and summation order) as gram_schmidt's norm2
+  dots(W, 1, w, w, nullptr);
+  B2_CUDA(cudaMemcpyAsync(W.scal.p + 1, W.small.p, 8, cudaMemcpyDeviceToDevice, W.ctx->stream));
   k_scale_by_norm<<<W.nstream, 256, 0, W.ctx->stream>>>(W.N, W.scal.p + 1, GS_MIN_NORM, w);
   W.ctx->launches++;
   B2_CHECK_LAUNCH();
