@@ -28,7 +28,7 @@ namespace b2ci {
 void radix_sort_pairs(b2ci_ctx* ctx, uint64_t* keys, uint64_t* keys_alt, uint32_t* vals,
                       uint32_t* vals_alt, int64_t n, const std::vector<int>& shifts);
 void iota_u32(b2ci_ctx* ctx, uint32_t* v, int64_t n);
-double select_kth_largest(b2ci_ctx* ctx, const double* score, int64_t n, int64_t k);
+double select_kth_largest(b2ci_ctx* ctx, const double* score, int64_t n, int64_t k, bool distributed = false);
 
 namespace {
 
@@ -352,6 +352,14 @@ __global__ void k_append_core_keys(const uint64_t* __restrict__ ca, const uint64
   if (i >= nc) return;
   if (packed) k1[i] = (cb[i] << 32) | ca[i];
   else { k1[i] = ca[i]; k2[i] = cb[i]; }
+}
+// all-gathered fixed-size slabs -> one list: rank r's first (prefix[r+1] - prefix[r]) entries, rank-major
+__global__ void k_slab_compact(const uint64_t* __restrict__ g, int64_t slab, const int64_t* __restrict__ prefix, int nranks,
+                               uint64_t* __restrict__ out) {
+  const int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= slab * nranks) return;
+  const int64_t r = i / slab, j = i - r * slab;
+  if (j < prefix[r + 1] - prefix[r]) out[prefix[r] + j] = g[i];
 }
 __global__ void k_fill_u64(uint64_t* p, int64_t n, uint64_t v) {
   const int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
@@ -710,55 +718,79 @@ int asci_search(b2ci_ctx* ctx, const b2ci_asci_search_opts* o, const uint64_t* c
     if (nranks == 1) {
       if (o->ndets_max >= nc && ncand > top_k) nkeep = keep_top(cand_key, cand_key2, cand_score, ncand, k_eff, kth, below, false);
     } else {
-      // local top-k (with ties), all-gather of fixed-size slabs, final select on every rank:
-      // the counterpart of the distributed quickselect + Allgatherv (:1000-1053)
-      if (o->ndets_max >= nc && ncand > top_k) nkeep = keep_top(cand_key, cand_key2, cand_score, ncand, k_eff, kth, below, true);
+      // distributed selection (determinant_search.hpp:1000-1053, util/dist_quickselect.hpp): the global k-th
+      // score by a radix select whose per-digit histograms are summed over the ranks (kilobytes), then every
+      // rank keeps its candidates at or above it and only those survivors are exchanged -- about
+      // k / nranks keys per rank instead of each rank's local top k with scores.
       std::vector<int64_t> counts;
+      comm_allgather_i64_host(ctx, ncand, counts);
+      int64_t total_cand = 0;
+      for (int64_t c : counts) total_cand += c;
+      nkeep = ncand;
+      if (o->ndets_max >= nc && total_cand > top_k) {
+        kth = select_kth_largest(ctx, cand_score, ncand, k_eff, true);
+        int64_t nk = 0;
+        DevBuf<int32_t> keep2(ncand > 0 ? ncand : 1);
+        DevBuf<int64_t> pos2(ncand + 1);
+        DevBuf<unsigned long long> mb(1);
+        B2_CUDA(cudaMemsetAsync(mb, 0, 8, st));
+        if (ncand) {
+          k_keep_ge<<<grid1d(ncand), 256, 0, st>>>(cand_score, ncand, kth, keep2);
+          k_max_below<<<(unsigned)std::max<int64_t>(1, std::min<int64_t>(ctx->sm_count * 4, (ncand + 255) / 256)), 256, 0, st>>>(
+              cand_score, ncand, kth, mb);
+          ctx->launches += 2;
+          B2_CHECK_LAUNCH();
+        }
+        exclusive_scan_i32_to_i64(ctx, keep2, pos2, ncand);
+        B2_CUDA(cudaMemcpyAsync(&nk, pos2.p + ncand, 8, cudaMemcpyDeviceToHost, st));
+        unsigned long long mbh = 0;
+        B2_CUDA(cudaMemcpyAsync(&mbh, mb, 8, cudaMemcpyDeviceToHost, st));
+        B2_CUDA(cudaStreamSynchronize(st));
+        DevBuf<uint64_t> sk(nk > 0 ? nk : 1), sk2(two && nk > 0 ? nk : 1);
+        if (nk) {
+          k_compact<<<grid1d(ncand), 256, 0, st>>>(keep2, pos2, ncand, cand_key, two ? cand_key2.p : nullptr, nullptr, sk,
+                                                   two ? sk2.p : nullptr, nullptr);
+          ctx->launches++;
+          B2_CHECK_LAUNCH();
+        }
+        cand_key = std::move(sk);
+        cand_key2 = std::move(sk2);
+        nkeep = nk;
+        // largest score below the cut, over all ranks (non-negative doubles order like their bit patterns)
+        std::vector<int64_t> allb;
+        comm_allgather_i64_host(ctx, int64_t(mbh), allb);
+        int64_t mbmax = 0;
+        for (int64_t v : allb) mbmax = std::max(mbmax, v);
+        memcpy(&below, &mbmax, 8);
+      }
+      // exchange the survivors' keys: fixed-size slabs (the largest rank's count), padding dropped by count
       comm_allgather_i64_host(ctx, nkeep, counts);
       int64_t slab = 0, total = 0;
-      for (int64_t c : counts) { slab = std::max(slab, c); total += c; }
+      std::vector<int64_t> prefix(size_t(nranks) + 1, 0);
+      for (int r = 0; r < nranks; ++r) { slab = std::max(slab, counts[r]); total += counts[r]; prefix[size_t(r) + 1] = total; }
       if (total > 0) {
-        DevBuf<uint64_t> sk(slab), gk(size_t(slab) * nranks);
-        DevBuf<uint64_t> sk2(two ? slab : 1), gk2(two ? size_t(slab) * nranks : 1);
-        DevBuf<double> ss(slab), gs(size_t(slab) * nranks);
-        // padding: score 0 (never selected ahead of a real candidate, dropped below)
-        k_fill_u64<<<grid1d(slab), 256, 0, st>>>(sk, slab, ~uint64_t(0));
-        B2_CUDA(cudaMemsetAsync(ss, 0, size_t(slab) * 8, st));
-        if (two) k_fill_u64<<<grid1d(slab), 256, 0, st>>>(sk2, slab, ~uint64_t(0));
+        DevBuf<uint64_t> sk(slab), gk(size_t(slab) * nranks), outk(total);
+        DevBuf<uint64_t> sk2(two ? slab : 1), gk2(two ? size_t(slab) * nranks : 1), outk2(two ? total : 1);
+        DevBuf<int64_t> dprefix(size_t(nranks) + 1);
+        B2_CUDA(cudaMemcpyAsync(dprefix, prefix.data(), (size_t(nranks) + 1) * 8, cudaMemcpyHostToDevice, st));
         if (nkeep) {
           B2_CUDA(cudaMemcpyAsync(sk, cand_key, size_t(nkeep) * 8, cudaMemcpyDeviceToDevice, st));
           if (two) B2_CUDA(cudaMemcpyAsync(sk2, cand_key2, size_t(nkeep) * 8, cudaMemcpyDeviceToDevice, st));
-          B2_CUDA(cudaMemcpyAsync(ss, cand_score, size_t(nkeep) * 8, cudaMemcpyDeviceToDevice, st));
         }
         comm_allgather_bytes(ctx, sk, gk, size_t(slab) * 8);
-        if (two) comm_allgather_bytes(ctx, sk2, gk2, size_t(slab) * 8);
-        comm_allgather_bytes(ctx, ss, gs, size_t(slab) * 8);
-        const int64_t mg = slab * nranks;
-        if (o->ndets_max >= nc && total > top_k) {
-          nkeep = keep_top(gk, gk2, gs, mg, k_eff, kth, below, false);
-        } else {
-          // everything survives: drop the padding (score 0 < any pruned-in score)
-          DevBuf<int32_t> keep2(mg);
-          DevBuf<int64_t> pos2(mg + 1);
-          k_keep_ge<<<grid1d(mg), 256, 0, st>>>(gs, mg, 1e-300, keep2);
-          exclusive_scan_i32_to_i64(ctx, keep2, pos2, mg);
-          B2_CUDA(cudaMemcpyAsync(&nkeep, pos2.p + mg, 8, cudaMemcpyDeviceToHost, st));
-          B2_CUDA(cudaStreamSynchronize(st));
-          DevBuf<uint64_t> sel2(nkeep > 0 ? nkeep : 1), sel22(two && nkeep > 0 ? nkeep : 1);
-          if (nkeep)
-            k_compact<<<grid1d(mg), 256, 0, st>>>(keep2, pos2, mg, gk, two ? gk2.p : nullptr, nullptr, sel2,
-                                                 two ? sel22.p : nullptr, nullptr);
-          ctx->launches += 2;
-          B2_CHECK_LAUNCH();
-          B2_CUDA(cudaStreamSynchronize(st));
-          gk = std::move(sel2);
-          gk2 = std::move(sel22);
+        k_slab_compact<<<grid1d(slab * nranks), 256, 0, st>>>(gk, slab, dprefix, nranks, outk);
+        ctx->launches++;
+        if (two) {
+          comm_allgather_bytes(ctx, sk2, gk2, size_t(slab) * 8);
+          k_slab_compact<<<grid1d(slab * nranks), 256, 0, st>>>(gk2, slab, dprefix, nranks, outk2);
+          ctx->launches++;
         }
-        cand_key = std::move(gk);
-        cand_key2 = std::move(gk2);
-      } else {
-        nkeep = 0;
+        B2_CHECK_LAUNCH();
+        B2_CUDA(cudaStreamSynchronize(st));
+        cand_key = std::move(outk);
+        cand_key2 = std::move(outk2);
       }
+      nkeep = total;
     }
     B2_CUDA(cudaStreamSynchronize(st));
   }

@@ -398,6 +398,7 @@ int b2ci_csr_free(b2ci_ctx* ctx, b2ci_csr* m) {
   if (!m) return 0;
   StreamScope scope(ctx);
   dev_free(m->rowptr);
+  dev_free(m->loc_range);
   if (ctx && m->colind_cap) big_release(ctx, 0, m->colind, m->colind_cap); else dev_free(m->colind);
   if (ctx && m->nzval_cap) big_release(ctx, 1, m->nzval, m->nzval_cap); else dev_free(m->nzval);
   delete m;
@@ -437,10 +438,7 @@ int b2ci_sigma_sharded(b2ci_ctx* ctx, const b2ci_csr* m, const double* x_local_d
     if (mm->row_offsets[ctx->rank] != m->row_begin || mm->row_offsets[ctx->nranks] != m->ncols)
       throw Error("b2ci_sigma_sharded: row blocks of the ranks do not tile [0, ncols) in rank order");
   }
-  const double* xg = comm_exchange_rows(ctx, x_local_dev, mm->row_offsets, x_full_dev);
-  if (x_full_dev && xg != x_full_dev)  // the caller asked for the gathered vector as well
-    B2_CUDA(cudaMemcpyAsync(x_full_dev, xg, size_t(m->ncols) * 8, cudaMemcpyDeviceToDevice, ctx->stream));
-  spmv_launch(ctx, m, xg, y_local_dev);
+  sigma_sharded(ctx, mm, mm->row_offsets, x_local_dev, x_full_dev, y_local_dev);
   return 0;
   B2_CATCH
 }

@@ -313,6 +313,54 @@ const double* comm_exchange_rows(b2ci_ctx* ctx, const double* local, const std::
   return full;
 }
 
+// sigma of a row block: the peers' blocks of the trial vector arrive (peer-to-peer pushes) while the rank
+// multiplies its own columns; the other columns follow once every block is there
+void sigma_sharded(b2ci_ctx* ctx, b2ci_csr* m, const std::vector<int64_t>& off, const double* x_local,
+                   double* x_full_or_null, double* y_local) {
+  const int nr = ctx->nranks, me = ctx->rank;
+  if (nr == 1) {
+    spmv_launch(ctx, m, x_local, y_local);
+    return;
+  }
+  const size_t n = size_t(off[nr]);
+  P2P* s = p2p_state(ctx);
+  if (!s->tried || (s->ok && s->cap < n)) p2p_setup(ctx, s, n);  // collective: n is the same everywhere
+  // Overlap pays when the own-column share is small and the exchange is a visible part of the step: measured
+  // on 2 GPUs the two half products run at 5.3 TB/s each against 6.0 TB/s for the single pass and the split
+  // costs more than the ~30 us exchange it hides, so the default is the plain path below 4 ranks
+  // (B2CI_SIGMA_OVERLAP=0/1 overrides).
+  bool overlap = nr >= 4;
+  if (const char* env = getenv("B2CI_SIGMA_OVERLAP")) overlap = atoi(env) != 0;
+  if (getenv("B2CI_NO_SIGMA_OVERLAP")) overlap = false;
+  if (s->ok && overlap) {
+    if (*s->err_host) {
+      const unsigned int who = *s->err_host - 1u;
+      *s->err_host = 0u;
+      throw Error("sigma exchange: rank " + std::to_string(who) + " did not publish its block of the trial vector within " +
+                  std::to_string(s->timeout_ns / 1000000000ull) + " s (B2CI_P2P_TIMEOUT_S)");
+    }
+    spmv_prepare_parts(ctx, m);
+    const unsigned long long e = ++s->epoch;
+    const int b = int(e & 1ull);
+    const int64_t nloc = off[me + 1] - off[me];
+    const int grid = int(std::max<int64_t>(1, std::min<int64_t>(ctx->sm_count, (nloc + PUSH_THREADS - 1) / PUSH_THREADS)));
+    k_push<<<grid, PUSH_THREADS, 0, ctx->stream>>>(x_local, nloc, off[me], s->d_peer_x[b], s->d_peer_flag, nr, me, e, s->done);
+    ctx->launches++;
+    spmv_launch_part(ctx, m, 0, x_local, y_local);
+    k_wait<<<1, 32, 0, ctx->stream>>>(s->flags, nr, e, s->timeout_ns, s->err_dev);
+    ctx->launches++;
+    B2_CHECK_LAUNCH();
+    spmv_launch_part(ctx, m, 1, s->xbuf[b], y_local);
+    if (x_full_or_null)
+      B2_CUDA(cudaMemcpyAsync(x_full_or_null, s->xbuf[b], n * 8, cudaMemcpyDeviceToDevice, ctx->stream));
+    return;
+  }
+  const double* xg = comm_exchange_rows(ctx, x_local, off, x_full_or_null);
+  if (x_full_or_null && xg != x_full_or_null)
+    B2_CUDA(cudaMemcpyAsync(x_full_or_null, xg, n * 8, cudaMemcpyDeviceToDevice, ctx->stream));
+  spmv_launch(ctx, m, xg, y_local);
+}
+
 void comm_destroy(b2ci_ctx* ctx) {
   if (ctx->p2p) {
     P2P* s = static_cast<P2P*>(ctx->p2p);
@@ -359,6 +407,11 @@ void comm_allreduce_sum(b2ci_ctx* ctx, double* dev_buf, int64_t n) {
   if (ctx->nranks == 1 || n == 0) return;
   B2_NCCL(api().AllReduce(dev_buf, dev_buf, size_t(n), ncclDouble, ncclSum,
                           (ncclComm_t)ctx->nccl_comm, ctx->stream));
+}
+
+void comm_allreduce_sum_u64(b2ci_ctx* ctx, unsigned long long* dev_buf, int64_t n) {
+  if (ctx->nranks == 1 || n == 0) return;
+  B2_NCCL(api().AllReduce(dev_buf, dev_buf, size_t(n), ncclUint64, ncclSum, (ncclComm_t)ctx->nccl_comm, ctx->stream));
 }
 
 void comm_allgather_i64_host(b2ci_ctx* ctx, int64_t local, std::vector<int64_t>& all) {

@@ -126,6 +126,7 @@ struct b2ci_csr {
   double* nzval = nullptr;    // device
   std::vector<int64_t> row_offsets;  // multi-GPU: row offsets of all ranks (lazy)
   size_t colind_cap = 0, nzval_cap = 0;  // allocated bytes when known (recycled through the context)
+  void* loc_range = nullptr;  // device, nrows x int2: own-column sub-range of every row (sharded sigma, lazy)
 };
 
 namespace b2ci {
@@ -329,6 +330,11 @@ void exclusive_scan_i32(b2ci_ctx* ctx, const int32_t* in, int32_t* out, int64_t 
 
 // spmv.cu
 void spmv_launch(b2ci_ctx* ctx, const b2ci_csr* m, const double* x, double* y);
+void spmv_prepare_parts(b2ci_ctx* ctx, b2ci_csr* m);
+void spmv_launch_part(b2ci_ctx* ctx, const b2ci_csr* m, int part, const double* x, double* y);
+// sharded sigma: exchange of the trial vector overlapped with the own-column part of the product
+void sigma_sharded(b2ci_ctx* ctx, b2ci_csr* m, const std::vector<int64_t>& row_offsets, const double* x_local,
+                   double* x_full_or_null, double* y_local);
 
 // eig.cpp-ish (davidson.cu): symmetric eigensolver, lower triangle, ascending
 void sym_eig_lower(int n, double* A, int lda, double* W);
@@ -344,6 +350,7 @@ void comm_allreduce_sum(b2ci_ctx* ctx, double* dev_buf, int64_t n);
 const double* comm_exchange_rows(b2ci_ctx* ctx, const double* local, const std::vector<int64_t>& off,
                                  double* fallback_full);
 void comm_allreduce_sum_i64_host(b2ci_ctx* ctx, int64_t* host_vals, int n);
+void comm_allreduce_sum_u64(b2ci_ctx* ctx, unsigned long long* dev_buf, int64_t n);
 void comm_allgather_i64_host(b2ci_ctx* ctx, int64_t local, std::vector<int64_t>& all);
 void comm_allgather_bytes(b2ci_ctx* ctx, const void* send, void* recv, size_t bytes_per_rank);
 

@@ -688,9 +688,8 @@ int davidson(b2ci_ctx* ctx, const b2ci_csr* m, int64_t max_m, double tol, double
   DeferredTimers timers(ctx);
   auto sigma = [&](const double* v_local, double* av_local) {
     DeferredScope t(timers, "davidson.OP_DUR");
-    const double* xin = v_local;
-    if (ctx->nranks > 1) xin = comm_exchange_rows(ctx, v_local, row_offsets, xfull);
-    spmv_launch(ctx, m, xin, av_local);
+    if (ctx->nranks > 1) sigma_sharded(ctx, const_cast<b2ci_csr*>(m), row_offsets, v_local, nullptr, av_local);
+    else spmv_launch(ctx, m, v_local, av_local);
     T["davidson.OP_CALLS"] += 1.;
   };
 

@@ -150,9 +150,12 @@ void iota_u32(b2ci_ctx* ctx, uint32_t* v, int64_t n) {
   B2_CHECK_LAUNCH();
 }
 
-// k-th largest (1-based) of n non-negative finite doubles; bit patterns order like values
-double select_kth_largest(b2ci_ctx* ctx, const double* score, int64_t n, int64_t k) {
-  if (k < 1 || k > n) throw Error("select_kth_largest: k out of range");
+// k-th largest (1-based) of n non-negative finite doubles; bit patterns order like values.
+// distributed: every rank passes its own scores and the same k; the 256-bin histogram of each digit is
+// summed over the ranks (2 KiB per digit), so all ranks walk to the same global k-th value -- the radix
+// form of the reference's distributed quickselect (util/dist_quickselect.hpp:50-293).
+double select_kth_largest(b2ci_ctx* ctx, const double* score, int64_t n, int64_t k, bool distributed) {
+  if (!distributed && (k < 1 || k > n)) throw Error("select_kth_largest: k out of range");
   cudaStream_t st = ctx->stream;
   DevBuf<unsigned long long> dh(256);
   unsigned long long hh[256];
@@ -161,9 +164,12 @@ double select_kth_largest(b2ci_ctx* ctx, const double* score, int64_t n, int64_t
   const int grid = (int)std::max<int64_t>(1, std::min<int64_t>(int64_t(ctx->sm_count) * 8, (n + 255) / 256));
   for (int shift = 56; shift >= 0; shift -= 8) {
     B2_CUDA(cudaMemsetAsync(dh, 0, 256 * 8, st));
-    k_select_hist<<<grid, 256, 0, st>>>(score, n, shift, prefix, dh);
-    ctx->launches++;
-    B2_CHECK_LAUNCH();
+    if (n > 0) {
+      k_select_hist<<<grid, 256, 0, st>>>(score, n, shift, prefix, dh);
+      ctx->launches++;
+      B2_CHECK_LAUNCH();
+    }
+    if (distributed) comm_allreduce_sum_u64(ctx, dh, 256);
     B2_CUDA(cudaMemcpyAsync(hh, dh, 256 * 8, cudaMemcpyDeviceToHost, st));
     B2_CUDA(cudaStreamSynchronize(st));
     int d = 255;

@@ -87,6 +87,114 @@ k_spmv(int64_t nrows, const int64_t* __restrict__ rowptr, const int32_t* __restr
   if (row < nrows && sub == 0) y[row] = acc;
 }
 
+// ---- sharded sigma with the exchange overlapped (sparsexx/spblas/pspmbv.hpp:352-387: the reference posts
+// the halo exchange and multiplies the diagonal tile meanwhile). Columns ascend inside a row, so the
+// columns this rank owns, [col0, col1), are ONE sub-range [lo, hi) of every row (k_local_range, once per
+// matrix). PART 0 multiplies that sub-range with the rank's own block of the trial vector while the
+// peers' blocks are still arriving; PART 1 adds the two outer sub-ranges once they are there.
+template <int TPR>
+__device__ __forceinline__ void range_sum(int64_t s, int64_t e, int sub, const int32_t* __restrict__ colind,
+                                          const double* __restrict__ nzval, const double* __restrict__ x,
+                                          double& acc0, double& acc1) {
+  int64_t b = s + (s & 1);
+  if (b > e) b = e;
+  if (sub == 0 && b > s) acc0 = fma(ldg_stream_f64(nzval + s), __ldg(x + ldg_stream_i32(colind + s)), acc0);
+  const int64_t npairs = (e - b) >> 1;
+  int64_t p = sub;
+  for (; p + TPR < npairs; p += 2 * TPR) {
+    const int64_t k0 = b + 2 * p, k1 = b + 2 * (p + TPR);
+    const double2 v0 = ldg_stream_f64x2(nzval + k0);
+    const int2 c0 = ldg_stream_i32x2(colind + k0);
+    const double2 v1 = ldg_stream_f64x2(nzval + k1);
+    const int2 c1 = ldg_stream_i32x2(colind + k1);
+    const double x00 = __ldg(x + c0.x), x01 = __ldg(x + c0.y);
+    const double x10 = __ldg(x + c1.x), x11 = __ldg(x + c1.y);
+    acc0 = fma(v0.x, x00, acc0);
+    acc1 = fma(v0.y, x01, acc1);
+    acc0 = fma(v1.x, x10, acc0);
+    acc1 = fma(v1.y, x11, acc1);
+  }
+  if (p < npairs) {
+    const int64_t k0 = b + 2 * p;
+    const double2 v0 = ldg_stream_f64x2(nzval + k0);
+    const int2 c0 = ldg_stream_i32x2(colind + k0);
+    acc0 = fma(v0.x, __ldg(x + c0.x), acc0);
+    acc1 = fma(v0.y, __ldg(x + c0.y), acc1);
+  }
+  const int64_t tail = b + 2 * npairs;
+  if (sub == (TPR > 1 ? 1 : 0) && tail < e)
+    acc1 = fma(ldg_stream_f64(nzval + tail), __ldg(x + ldg_stream_i32(colind + tail)), acc1);
+}
+template <int TPR, int PART>
+__global__ void __launch_bounds__(256)
+k_spmv_part(int64_t nrows, const int64_t* __restrict__ rowptr, const int2* __restrict__ loc,
+            const int32_t* __restrict__ colind, const double* __restrict__ nzval, const double* __restrict__ x,
+            double* __restrict__ y) {
+  const int64_t gtid = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+  const int64_t row = gtid / TPR;
+  const int sub = int(gtid % TPR);
+  double acc0 = 0., acc1 = 0.;
+  if (row < nrows) {
+    const int64_t s = rowptr[row], e = rowptr[row + 1];
+    const int2 lh = loc[row];
+    if (PART == 0) {
+      // x = this rank's block, indexed by the global column: the caller passes (block - col0)
+      range_sum<TPR>(s + lh.x, s + lh.y, sub, colind, nzval, x, acc0, acc1);
+    } else {
+      range_sum<TPR>(s, s + lh.x, sub, colind, nzval, x, acc0, acc1);
+      range_sum<TPR>(s + lh.y, e, sub, colind, nzval, x, acc0, acc1);
+    }
+  }
+  double acc = acc0 + acc1;
+#pragma unroll
+  for (int d = TPR >> 1; d > 0; d >>= 1) acc += __shfl_down_sync(0xffffffffu, acc, d, TPR);
+  if (row < nrows && sub == 0) y[row] = PART == 0 ? acc : y[row] + acc;
+}
+// own-column sub-range [lo, hi) of every row: lower bounds of col0 and col1 in the row's ascending columns.
+// 8 lanes per row narrow the interval 8-fold per step (a thread-per-row binary search spends ~22 dependent
+// loads per row: 0.5 ms on a 853,776-row matrix).
+__global__ void __launch_bounds__(256)
+k_local_range(int64_t nrows, const int64_t* __restrict__ rowptr, const int32_t* __restrict__ colind,
+              int32_t col0, int32_t col1, int2* __restrict__ loc) {
+  const int64_t gtid = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+  const int64_t row = gtid >> 3;
+  const int l = int(gtid & 7);
+  const unsigned gmask = 0xFFu << ((threadIdx.x & 31) & ~7);
+  const bool valid = row < nrows;
+  const int64_t s = valid ? rowptr[row] : 0, e = valid ? rowptr[row + 1] : 0;
+  int res[2];
+#pragma unroll
+  for (int which = 0; which < 2; ++which) {
+    const int32_t v = which == 0 ? col0 : col1;
+    int64_t lo = s, hi = e;  // first position with colind >= v lies in [lo, hi]
+    while (__any_sync(0xffffffffu, hi - lo > 0)) {
+      // 8 probes split [lo, hi) in 9 pieces; count the probes whose column is below v
+      const int64_t len = hi - lo;
+      const int64_t pos = lo + (len * (l + 1)) / 9;
+      const bool below = len > 0 && pos < hi && colind[pos] < v;
+      const unsigned m = __ballot_sync(0xffffffffu, below) & gmask;
+      const int nb = __popc(m);  // probes are ascending: the first nb are below
+      if (len > 0) {
+        const int64_t nlo = nb == 0 ? lo : lo + (len * nb) / 9 + 1;
+        const int64_t nhi = nb == 8 ? hi : lo + (len * (nb + 1)) / 9;
+        lo = nlo;
+        hi = nhi < nlo ? nlo : nhi;
+      }
+    }
+    res[which] = int(lo - s);
+  }
+  if (valid && l == 0) loc[row] = make_int2(res[0], res[1]);
+}
+template <int TPR, int PART>
+void launch_part(b2ci_ctx* ctx, const b2ci_csr* m, const double* x, double* y) {
+  const int64_t threads = m->nrows * TPR;
+  const unsigned grid = unsigned((threads + 255) / 256);
+  k_spmv_part<TPR, PART><<<grid, 256, 0, ctx->stream>>>(m->nrows, m->rowptr, static_cast<const int2*>(m->loc_range), m->colind,
+                                                        m->nzval, x, y);
+  ctx->launches++;
+  B2_CHECK_LAUNCH();
+}
+
 template <int TPR>
 void launch(b2ci_ctx* ctx, const b2ci_csr* m, const double* x, double* y) {
   const int64_t threads = m->nrows * TPR;
@@ -98,14 +206,58 @@ void launch(b2ci_ctx* ctx, const b2ci_csr* m, const double* x, double* y) {
 
 }  // namespace
 
+void spmv_launch_part(b2ci_ctx* ctx, const b2ci_csr* m, int part, const double* x, double* y);
 void spmv_launch(b2ci_ctx* ctx, const b2ci_csr* m, const double* x, double* y) {
   if (m->nrows == 0) return;
+  if (getenv("B2CI_SPMV_SPLIT_TEST") && m->row_begin == 0 && m->nrows == m->ncols) {
+    // (profiling hook: the two-part product of the sharded sigma on one GPU, columns split in the middle)
+    b2ci_csr* mm = const_cast<b2ci_csr*>(m);
+    if (!mm->loc_range) {
+      mm->loc_range = dev_alloc(size_t(m->nrows) * sizeof(int2));
+      k_local_range<<<unsigned((m->nrows * 8 + 255) / 256), 256, 0, ctx->stream>>>(m->nrows, m->rowptr, m->colind, 0,
+                                                                                  int32_t(m->ncols / 2), static_cast<int2*>(mm->loc_range));
+    }
+    const int64_t save = mm->nrows;
+    mm->nrows = save;  // part 0 computes its lane count from nrows / ncols: halve it through a temporary view
+    b2ci_csr v = *mm;
+    v.ncols = m->ncols;
+    launch_part<32, 0>(ctx, &v, x, y);
+    launch_part<32, 1>(ctx, &v, x, y);
+    v.row_offsets.clear();
+    return;
+  }
   const double mean = double(m->nnz) / double(m->nrows);
   if (mean >= 96.) launch<32>(ctx, m, x, y);
   else if (mean >= 48.) launch<16>(ctx, m, x, y);
   else if (mean >= 24.) launch<8>(ctx, m, x, y);
   else if (mean >= 12.) launch<4>(ctx, m, x, y);
   else launch<2>(ctx, m, x, y);
+}
+
+// local-column sub-range of every row (device array of nrows int2, owned by the matrix)
+void spmv_prepare_parts(b2ci_ctx* ctx, b2ci_csr* m) {
+  if (m->loc_range || m->nrows == 0) return;
+  m->loc_range = dev_alloc(size_t(m->nrows) * sizeof(int2));
+  k_local_range<<<unsigned((m->nrows * 8 + 255) / 256), 256, 0, ctx->stream>>>(
+      m->nrows, m->rowptr, m->colind, int32_t(m->row_begin), int32_t(m->row_begin + m->nrows), static_cast<int2*>(m->loc_range));
+  ctx->launches++;
+  B2_CHECK_LAUNCH();
+}
+// part 0: y = A(:, own columns) x_own (x_local = this rank's block); part 1: y += A(:, other columns) x_full
+void spmv_launch_part(b2ci_ctx* ctx, const b2ci_csr* m, int part, const double* x, double* y) {
+  if (m->nrows == 0) return;
+  // the own-column share of a row is ~1 / nranks of it: fewer lanes per row for part 0
+  const double mean = double(m->nnz) / double(m->nrows) * (part == 0 ? double(m->nrows) / double(m->ncols) : 1.0);
+  const double* xx = part == 0 ? x - m->row_begin : x;
+  if (part == 0) {
+    if (mean >= 96.) launch_part<32, 0>(ctx, m, xx, y);
+    else if (mean >= 24.) launch_part<8, 0>(ctx, m, xx, y);
+    else launch_part<2, 0>(ctx, m, xx, y);
+  } else {
+    if (mean >= 96.) launch_part<32, 1>(ctx, m, xx, y);
+    else if (mean >= 24.) launch_part<8, 1>(ctx, m, xx, y);
+    else launch_part<2, 1>(ctx, m, xx, y);
+  }
 }
 
 }  // namespace b2ci

@@ -54,10 +54,21 @@ def main():
     xl = torch.from_numpy(x[r0:r1].copy()).cuda()
     xf = torch.empty(n, dtype=torch.float64, device="cuda")
     yl = torch.empty(r1 - r0, dtype=torch.float64, device="cuda")
+    os.environ["B2CI_SIGMA_OVERLAP"] = "1"   # exercise the overlapped exchange whatever the rank count
     Hloc.sigma_sharded(xl.data_ptr(), xf.data_ptr(), yl.data_ptr())
     torch.cuda.synchronize()
     yref = Hfull.spmv(x)
     out["gather_exact"] = bool(np.array_equal(xf.cpu().numpy(), x))
+    # overlapped exchange: own columns first, the others after the wait -- a different (fixed) association
+    # order of the FP64 sums than the single-GPU kernel, so the bar is the sigma bound of the parity tests:
+    # |dy| <= 1e-13 * sum |h||x| per row
+    bound = 1e-13 * ctx1.upload_csr(rp, ci, np.abs(nz)).spmv(np.abs(x))[r0:r1] + 1e-300
+    out["sigma_within_bound"] = bool(np.all(np.abs(yl.cpu().numpy() - yref[r0:r1]) <= bound))
+    # the plain path (exchange, then one SpMV over all columns) is bit-identical to the single-GPU product
+    os.environ["B2CI_NO_SIGMA_OVERLAP"] = "1"
+    Hloc.sigma_sharded(xl.data_ptr(), xf.data_ptr(), yl.data_ptr())
+    torch.cuda.synchronize()
+    del os.environ["B2CI_NO_SIGMA_OVERLAP"]
     out["sigma_bit_exact"] = bool(np.array_equal(yl.cpu().numpy(), yref[r0:r1]))
     out["p2p"] = ctx.timer_ms("comm.p2p")
     # repeated sigmas with changing vectors (exchange-buffer parity, epochs) and x_full = NULL
@@ -67,7 +78,7 @@ def main():
         xl2 = torch.from_numpy(xr[r0:r1].copy()).cuda()
         Hloc.sigma_sharded(xl2.data_ptr(), 0, yl.data_ptr())
         torch.cuda.synchronize()
-        ok = ok and np.array_equal(yl.cpu().numpy(), Hfull.spmv(xr)[r0:r1])
+        ok = ok and np.allclose(yl.cpu().numpy(), Hfull.spmv(xr)[r0:r1], rtol=0, atol=1e-11)
     out["sigma_repeat_exact"] = bool(ok)
     # the same with the split supplied by the caller (no exchange of block sizes)
     Hloc2 = ctx.hbuild(dets, EPS, (r0, r1))
@@ -75,7 +86,7 @@ def main():
     xf.zero_(); yl.zero_()
     Hloc2.sigma_sharded(xl.data_ptr(), xf.data_ptr(), yl.data_ptr())
     torch.cuda.synchronize()
-    out["sigma_bit_exact"] = bool(out["sigma_bit_exact"] and np.array_equal(yl.cpu().numpy(), yref[r0:r1]))
+    out["sigma_within_bound"] = bool(out["sigma_within_bound"] and np.all(np.abs(yl.cpu().numpy() - yref[r0:r1]) <= bound))
     try:
         Hloc2.set_row_partition([0] + [c + 1 for c in cuts[1:-1]] + [n])
         out["bad_partition_rejected"] = world == 1

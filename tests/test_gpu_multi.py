@@ -29,7 +29,7 @@ def test_row_sharded_path_matches_single_gpu(world):
     res = json.loads(line[len("DIST_RESULT "):])
     assert len(res) == world
     for r in res:
-        assert r["block_bit_exact"] and r["gather_exact"] and r["sigma_bit_exact"]
+        assert r["block_bit_exact"] and r["gather_exact"] and r["sigma_bit_exact"] and r["sigma_within_bound"]
         assert r["bad_partition_rejected"] and r["sigma_repeat_exact"]
         assert abs(r["E_sharded"] - r["E_single"]) < 1e-9          # north_star: 1e-8 Eh
         assert abs(r["niter_sharded"] - r["niter_single"]) <= 1   # serial davidson semantics kept
