@@ -1,6 +1,7 @@
 // extern "C" surface declared in include/b2ci.h. Every entry catches C++ exceptions,
 // records the message for b2ci_last_error() and returns a non-zero status -- there is no
 // CPU fallback behind any of them.
+#include <nvtx3/nvToolsExt.h>
 #include <unordered_map>
 #include <mutex>
 #include <cstring>
@@ -130,9 +131,17 @@ __global__ void k_i64_to_i32(const int64_t* __restrict__ in, int64_t n, int32_t*
 using namespace b2ci;
 
 #define B2_TRY try {
+// profiler range per C-ABI entry, named after the entry (NVTX3 is header-only: a no-op unless a tool such as
+// nsys / ncu --nvtx injects itself). The reference marks the same phases with its h_build / ci_solver / davidson /
+// asci_search loggers (selected_ci_diag.hpp:204-296).
+struct NvtxRange {
+  explicit NvtxRange(const char* name) { nvtxRangePushA(name); }
+  ~NvtxRange() { nvtxRangePop(); }
+};
 #define B2_TRY_CTX(ctx)                                            \
   try {                                                            \
     if (!(ctx)) throw b2ci::Error("null b2ci context");            \
+    NvtxRange _nvtx(__func__);                                     \
     b2ci::StreamScope _scope(ctx);
 #define B2_CATCH                                   \
   }                                                \

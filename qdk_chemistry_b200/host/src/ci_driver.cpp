@@ -10,6 +10,8 @@
 //   asci_iter/grow/refine                      asci/iteration.hpp:50-226, grow.hpp:45-268, refine.hpp:44-237
 //   B200Pmc::_run_impl   pmc_helper::impl      macis_pmc.cpp:36-174
 //   selected_ci_diag                           solvers/selected_ci_diag.hpp:111-311
+#include <cstdarg>
+#include <cstdio>
 #include <algorithm>
 #include <chrono>
 #include <cmath>
@@ -59,6 +61,28 @@ Runtime& runtime() {
   return *r;
 }
 thread_local std::map<std::string, double> g_stats;
+
+// Phase log with the reference's logger names (spdlog loggers h_build / ci_solver / davidson / asci_search /
+// asci_grow / asci_refine: selected_ci_diag.hpp:204-296, sorted_double_loop.hpp:441-448, davidson.hpp:340-344), so
+// that a CPU log of MACIS and a log of this plugin line up. B2CI_LOG=info|trace (stderr); off by default.
+int log_level() {
+  static const int lvl = [] {
+    const char* e = std::getenv("B2CI_LOG");
+    if (!e) return 0;
+    const std::string v(e);
+    return v == "trace" ? 2 : (v == "off" || v == "0" ? 0 : 1);
+  }();
+  return lvl;
+}
+void log_line(int level, const char* logger, const char* fmt, ...) {
+  if (log_level() < level) return;
+  char buf[512];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof(buf), fmt, ap);
+  va_end(ap);
+  std::fprintf(stderr, "[%s] %s\n", logger, buf);
+}
 
 [[noreturn]] void fail(const std::string& what) {
   throw std::runtime_error(what + ": " + b2ci_last_error());
@@ -233,6 +257,27 @@ class CiSession {
     add_timer("davidson_other_ms", {"davidson.RR_DUR", "davidson.RES_DUR", "davidson.GS_DUR"});
     g_stats["davidson_iterations"] += double(niter);
     g_stats["davidson_calls"] += 1.0;
+    log_line(1, "h_build", "SETUP_DUR = %.5e ms, COUNT_DUR = %.5e ms, FILL_DUR = %.5e ms, THRESH_DUR = %.5e ms",
+             b2ci_timer_ms(ctx_, "h_build.setup"), b2ci_timer_ms(ctx_, "h_build.count"), b2ci_timer_ms(ctx_, "h_build.fill"),
+             b2ci_timer_ms(ctx_, "h_build.thresh"));
+    log_line(1, "ci_solver", "NDETS = %lld, NNZ = %lld, H_DUR = %.5e ms, HMEM_LOC = %.2e GiB, H_SPARSE = %.2e %%",
+             (long long)n, (long long)nnz, g_stats["h_build_last_ms"], double(nnz) * 12.0 / 1073741824.0,
+             100.0 * double(nnz) / (double(rows.second - rows.first) * double(n)));
+    log_line(1, "ci_solver", "DAV_NITER = %lld, E0 = %.12e, DAVIDSON_DUR = %.5e ms", (long long)niter, E,
+             b2ci_timer_ms(ctx_, "davidson.OP_DUR") + b2ci_timer_ms(ctx_, "davidson.RR_DUR") +
+                 b2ci_timer_ms(ctx_, "davidson.RES_DUR") + b2ci_timer_ms(ctx_, "davidson.GS_DUR"));
+    log_line(2, "davidson", "OP_DUR = %.5e ms, RR_DUR = %.5e ms, RES_DUR = %.5e ms, GS_DUR = %.5e ms",
+             b2ci_timer_ms(ctx_, "davidson.OP_DUR"), b2ci_timer_ms(ctx_, "davidson.RR_DUR"),
+             b2ci_timer_ms(ctx_, "davidson.RES_DUR"), b2ci_timer_ms(ctx_, "davidson.GS_DUR"));
+    {
+      // sigma of the LAST matrix: time per application and its algorithmic bytes (SURVEY 8(d):
+      // nnz * 12 + (rows + 1) * 8 + N * 8 + rows * 8), so that callers can quote a roofline fraction
+      const double calls = b2ci_timer_ms(ctx_, "davidson.OP_CALLS");
+      const int64_t nrows = rows.second - rows.first;
+      g_stats["sigma_last_ms"] = calls > 0 ? b2ci_timer_ms(ctx_, "davidson.OP_DUR") / calls : 0.0;
+      g_stats["sigma_last_bytes"] = double(nnz) * 12.0 + double(nrows + 1) * 8.0 + double(n) * 8.0 + double(nrows) * 8.0;
+      g_stats["sigma_last_rows"] = double(nrows);
+    }
     if (use_cache) {
       drop_cache();
       cache_H_ = H;
@@ -334,6 +379,10 @@ class CiSession {
     g_stats["asci_unique_candidates"] += stats[1];   // after sort + accumulate
     g_stats["asci_last_key_partitions"] = stats[5];
     g_stats["asci_search_calls"] += 1.0;
+    log_line(1, "asci_search", "NCDETS = %lld, NDETS_MAX = %lld, NCONTRIB = %.0f, NUNIQ = %.0f, NKEEP = %lld, PAIR_DUR = %.5e ms, "
+             "SORT_ACC_DUR = %.5e ms, TOPK_DUR = %.5e ms", (long long)ncore, (long long)ndets_max, stats[0], stats[1],
+             (long long)n_out, b2ci_timer_ms(ctx_, "asci_search.PAIR_DUR"), b2ci_timer_ms(ctx_, "asci_search.SORT_ACC_DUR"),
+             b2ci_timer_ms(ctx_, "asci_search.TOPK_DUR"));
     out.resize(size_t(n_out));
     return out;
   }
@@ -648,6 +697,8 @@ double asci_grow(CiSession& S, const AsciSettings& a, const McscfSettings& m, do
       if (ndets_new <= wfn.size()) break;
     }
     const double E = asci_iter(S, a, gm, int64_t(ndets_new), E0, wfn, X);
+    log_line(1, "asci_grow", "NDETS = %zu (requested %zu), E0 = %.12e, dE = %.5e, GROW_FACTOR = %.4f", wfn.size(), ndets_new, E,
+             E - E0, gf);
     if (wfn.size() < ndets_new) {
       gf = std::max(a.min_grow_factor, gf * a.growth_backoff_rate);
       if (wfn.size() <= prev) break;  // (the reference leaves E0 at its previous value here)
@@ -685,6 +736,7 @@ double asci_refine(CiSession& S, const AsciSettings& a, const McscfSettings& m, 
       if (wfn.size() < size_t(a.ntdets_min)) break;
     }
     const double dE = E - E0;
+    log_line(1, "asci_refine", "ITER = %zu, NDETS = %zu, E0 = %.12e, dE = %.5e", iter, wfn.size(), E, dE);
     if (std::abs(dE) < a.refine_energy_tol) {
       E0 = E;
       converged = true;
@@ -706,6 +758,8 @@ double asci_refine(CiSession& S, const AsciSettings& a, const McscfSettings& m, 
                                              a.min_patch_overlap);
         const size_t ext = std::min(size_t(oscillation), max_ext - total_ext);
         if (ext > 0) { max_iter += ext; total_ext += ext; }
+        g_stats["asci_refine_unions"] += 1.0;
+        g_stats["asci_refine_extensions"] = double(total_ext);
         wfn = std::move(uni);
         X = std::move(Xu);
         ndets = wfn.size();

@@ -48,6 +48,17 @@ if out.get("asci_contributions") and out.get("asci_pair_ms"):
     npass = 2 * ((sp.norb + 7) // 8)
     out["asci_candidates_per_s"] = out["asci_contributions"] / (out["asci_pair_ms"] * 1e-3)
     out["asci_sort_accumulate_GBps"] = out["asci_contributions"] * 24.0 * npass / (out["asci_sort_acc_ms"] * 1e-3) / 1e9
+if out.get("sigma_last_ms"):
+    # sigma on the final matrix as a fraction of the measured HBM copy peak (MEASURED_PEAKS.json)
+    peak = 6550.4
+    try:
+        with open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "MEASURED_PEAKS.json")) as fh:
+            peak = float(json.load(fh)["hbm_gbs"])
+    except OSError:
+        pass
+    gbs = out["sigma_last_bytes"] / (out["sigma_last_ms"] * 1e-3) / 1e9
+    out["sigma_last_GBps"] = gbs
+    out["sigma_last_frac_of_hbm_peak"] = gbs / peak
 if rank == 0:
     print(json.dumps(out))
 if world > 1:

@@ -31,6 +31,9 @@ for name, kw in CASES.items():
     hg = ref.HamGen(water.norb, water.T, water.V)
     E, d, C = hg.asci_run(ref.AsciOpts(max_refine_iter=0, **kw), 5, 5, refine=False)
     meta[name] = dict(settings=kw, n=len(C), E=E, norm=float(C @ C))
+    if len(C) <= 100:  # small enough to keep the wavefunction itself: determinant words (wfn_t<64>) and coefficients
+        meta[name]["dets"] = [int(x) for x in d]
+        meta[name]["coeffs"] = [float(x) for x in C]
     print(name, len(C), E)
 with open(os.path.join(HERE, "backoff_meta.json"), "w") as fh:
     json.dump(meta, fh, indent=1)

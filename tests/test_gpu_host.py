@@ -97,7 +97,17 @@ def test_asci_n2_14e18o_2000_determinants(n2_18, golden_meta, golden_arrays):
     flip = lambda k: ((k & 0xFFFFFFFF) << 32) | (k >> 32)
     # see tests/test_oracle.py::test_n2_14e18o_asci_2000 for the spin-flip-partner rule
     assert len(got) == len(want) == 2000
-    assert all(flip(k) in (want - got) for k in (got - want)) and len(got - want) <= 40
+    swapped = got - want
+    assert all(flip(k) in (want - got) for k in swapped)
+    # tie evidence: a swapped determinant sits at the margin of the wavefunction (its spin-flip partner, of equal
+    # score in exact arithmetic, was the one the reference kept), i.e. in the low-|c| tail
+    coef = dict(zip(port.pack(a, b).tolist(), np.abs(np.asarray(w.get_coefficients())).tolist()))
+    order = sorted(coef.values())
+    tail = order[min(len(order) - 1, 2 * len(swapped) + 200)]
+    assert all(coef[k] <= tail for k in swapped), [(hex(k), coef[k]) for k in swapped if coef[k] > tail]
+    print(f"n2_14e18o ASCI-2000: {len(swapped)} determinants differ from the reference's set, all spin-flip partners "
+          f"from the low-|c| tail (largest |c| among them {max([coef[k] for k in swapped] or [0.0]):.3e})")
+    assert len(swapped) <= 40
     # and against the oracle's outer loop: same energy; the selection again modulo spin-flip
     # partners (their |c| are equal in exact arithmetic, the last bits of two Davidson
     # implementations are not)
@@ -236,6 +246,29 @@ def test_asci_plugin_on_36_orbitals_matches_reference_run():
     assert canon(got) == canon(want)
 
 
+def test_asci_refine_oscillation_union_matches_reference():
+    # asci_refine's oscillation handling in the PRODUCT's host loop (host/src/ci_driver.cpp::asci_refine;
+    # asci/refine.hpp:118-205): on the oscillating 36-orbital run the compiled reference gives up after 2
+    # granted extra iterations with max_refine_iter = 20, and converges at max_refine_iter = 80 after 15 unions
+    # of the last two determinant sets on a 624-determinant set (tests/golden/make_golden_union.py)
+    import json
+    with open(os.path.join(ROOT, "tests", "golden", "union_meta.json")) as fh:
+        meta = json.load(fh)
+    sp = W.config("wide36")
+    kw = dict(meta["settings"])
+    kw["core_selection_strategy"] = "fixed"
+    with pytest.raises(RuntimeError) as e:
+        alg.create(MC, "macis_asci", max_refine_iter=20, **kw).run(_ham(sp), sp.nalpha, sp.nbeta)
+    assert not meta["runs"]["20"]["converged"]
+    assert "2 extra iterations granted" in meta["runs"]["20"]["message"] and "2 extra iterations granted" in str(e.value)
+    m80 = meta["runs"]["80"]
+    E, w = alg.create(MC, "macis_asci", max_refine_iter=80, **kw).run(_ham(sp), sp.nalpha, sp.nbeta)
+    st = alg.last_run_stats()
+    assert m80["converged"] and w.size() == m80["n"] == 624
+    assert abs(E - sp.core_energy - m80["E"]) < 1e-8
+    assert st["asci_refine_unions"] == 15
+
+
 def test_asci_refine_uses_patched_builds_with_identical_results(water, monkeypatch):
     # incremental H build between ASCI iterations (asci/refine.hpp:84-90, selected_ci_diag.hpp:217-256):
     # refine iterations overlap their predecessor by far more than min_patch_overlap
@@ -340,20 +373,50 @@ def test_compute_casci_rdms_functor():
     assert none1 is None and none2 is None and abs(E1 - E0) < 1e-9
 
 
+def _spin_flip(k):
+    return ((k & 0xFFFFFFFF) << 32) | (k >> 32)
+
+
 @pytest.mark.parametrize("case", ["fractional_grow_factor", "forced_backoff", "minimum_grow_factor", "normal_growth",
-                                  "taper"])
+                                  "taper", "fixed_core_5000", "percentage_core_5000", "percentage_70", "percentage_99"])
 def test_asci_growth_backoff_scenarios_match_reference(water, case):
-    # external/macis/tests/asci.cxx:577-733; golden sizes / energies from the compiled reference
+    # external/macis/tests/asci.cxx:577-733 (growth back-off / recovery) and :736-840 (core-selection
+    # strategies), through the plugin; golden sizes (ties at the cut included) and energies from the compiled
+    # reference (tests/golden/make_golden_backoff.py)
     import json
     with open(os.path.join(ROOT, "tests", "golden", "backoff_meta.json")) as fh:
         m = json.load(fh)[case]
     kw = dict(m["settings"])
     kw["core_selection_strategy"] = "fixed" if kw["core_selection_strategy"] == 0 else "percentage"
     E, w = alg.create(MC, "macis_asci", max_refine_iter=0, ci_residual_tolerance=1e-8, **kw).run(_ham(water), 5, 5)
-    # Cuts at 10 / 25 / 63 / 100 determinants from a closed-shell HF start fall between spin-flip partners,
-    # whose |rv| are equal in exact arithmetic: which partner survives is decided by the last bits of the
-    # Davidson vector (the reference's own unstable sort / rounding, see test_asci_n2_14e18o_2000_determinants),
-    # so for that scenario the energy is pinned only to the size of one partner swap (measured 1.7e-4 Eh;
-    # identical with and without patched builds and with the scan instead of the product kernel).
-    tol = 5e-4 if case == "fractional_grow_factor" else 1e-8
-    assert w.size() == m["n"] and abs(E - water.core_energy - m["E"]) < tol and abs(w.norm() - 1) < 1e-12
+    assert w.size() == m["n"] and abs(w.norm() - 1) < 1e-12
+    if case != "fractional_grow_factor":
+        assert abs(E - water.core_energy - m["E"]) < 1e-8
+        return
+    # With grow_factor 2.5 the cuts fall at 10 / 25 / 63 / 100 determinants, from a closed-shell HF start: at the
+    # early cuts spin-flip partners (a, b) / (b, a) of equal score in exact arithmetic straddle the cut, and which one
+    # survives is decided by the last bits of the Davidson vector (the reference's own rounding and unstable sort).
+    # The wavefunctions then differ slightly and the LAST place of the final list can go to a different determinant.
+    # What is asserted instead of a bare tolerance: the two 100-determinant sets differ in at most two places, all
+    # common determinants carry the same |c| to 2e-3, and the energy difference is bounded by the weight of the
+    # determinants that were exchanged (the numbers are printed).
+    a, b = _words(w)
+    ours = dict(zip(port.pack(a, b).tolist(), np.asarray(w.get_coefficients()).tolist()))
+    ref = dict(zip(m["dets"], m["coeffs"]))
+    got, want = set(ours), set(ref)
+    only_ours, only_ref = got - want, want - got
+    assert len(only_ours) == len(only_ref) <= 2
+    assert max(abs(abs(ours[k]) - abs(ref[k])) for k in got & want) < 2e-3
+    rank_ours = {k: r for r, k in enumerate(sorted(ours, key=lambda k: abs(ours[k])))}
+    rank_ref = {k: r for r, k in enumerate(sorted(ref, key=lambda k: abs(ref[k])))}
+    exchanged = sum(ours[k] ** 2 for k in only_ours) + sum(ref[k] ** 2 for k in only_ref)
+    common = max(abs(abs(ours[k]) - abs(ref[k])) for k in got & want)
+    dE = abs(E - water.core_energy - m["E"])
+    print(f"fractional_grow_factor: {len(only_ours)} determinant(s) differ; ranks by |c| (0 = smallest): ours "
+          f"{[rank_ours[k] for k in only_ours]}, reference {[rank_ref[k] for k in only_ref]}; exchanged weight "
+          f"{exchanged:.3e}; max |d|c|| on common determinants {common:.3e}; |dE| {dE:.3e}")
+    # (measured: one determinant differs -- ours keeps the closed-shell double 0b111011 / 0b111011, rank 32 of 100
+    # by |c|, the reference a rank-6 determinant; exchanged weight 3.0e-4, |dE| 1.7e-4)
+    assert dE < 5e-4 and dE < 10 * exchanged + 1e-8
+    if not only_ours:
+        assert dE < 1e-8
