@@ -381,7 +381,7 @@ def run_b200_asci(args):
 def load_traffic(kernel_key):
     """DRAM traffic per launch (dram__bytes_read.sum + dram__bytes_write.sum) of the dominant
     kernels, from the committed `ncu --set full` capture (profiles/r01_traffic.json)."""
-    p = os.path.join(ROOT, "profiles", "r01_traffic.json")
+    p = os.path.join(ROOT, "profiles", "r02_traffic.json")
     try:
         with open(p) as fh:
             return json.load(fh).get(kernel_key)
@@ -590,6 +590,7 @@ def measure(ctx, sp, name, args, world, rank, local_rank, dist, torch, steps, wa
     nnz_local = H.nnz
     group = ctx.timer_ms("h_build.group_width")
     slices = ctx.timer_ms("h_build.smem_slices")
+    dense_mode = int(ctx.timer_ms("h_build.dense_fill"))
 
     res = {"workload": name}
     # ---- e2e leg: same H build through the C ABI with HOST buffers (pinned determinant words,
@@ -624,7 +625,7 @@ def measure(ctx, sp, name, args, world, rank, local_rank, dist, torch, steps, wa
         build_ms=mx(float(np.mean(T["build"]))), sigma_ms=mx(float(np.mean(T["sigma"]))),
         fill_ms=mx(float(np.mean(T["fill"]))), count_ms=mx(float(np.mean(T["count"]))),
         setup_ms=mx(float(np.mean(T["setup"]))), thresh_ms=mx(float(np.mean(T["thresh"]))),
-        launches=int(launches), clocks=clocks, p2p=ctx.timer_ms("comm.p2p"), wall=wall1 - wall0, group=int(group), slices=bool(slices),
+        launches=int(launches), clocks=clocks, p2p=ctx.timer_ms("comm.p2p"), wall=wall1 - wall0, group=int(group), slices=bool(slices), dense=dense_mode,
         # algorithmic bytes per launch on THIS rank
         B_sigma=int(nnz_local * 12 + (nrows + 1) * 8 + n * 8 + nrows * 8),
         B_fill=int(n * 16 + nnz_local * 12 + (nrows + 1) * 8),
@@ -731,8 +732,15 @@ def run_b200(args):
     if rank == 0:
         fill_gbs = m["B_fill"] / (m["fill_ms_local"] * 1e-3) / 1e9
         sig_gbs = m["B_sigma"] / (m["sigma_ms_local"] * 1e-3) / 1e9
-        rect = "k_rows_product<EVAL,G=%d,SLICES=%d> (H-build fill: evaluates and writes the CSR)" % (
-            m["group"], int(m["slices"]))
+        if m.get("dense") == 2:
+            rect = ("k_rows_dense<EVAL> (H-build fill of a uniform list with dense integrals: position-ordered, one "
+                    "contiguous aligned store range per warp instruction; its three pre-pass kernels are inside the "
+                    "timed fill)")
+            rect_key = "k_rows_dense"
+        else:
+            rect = "k_rows_product<EVAL,G=%d,SLICES=%d,DENSE=%d> (H-build fill: evaluates and writes the CSR)" % (
+                m["group"], int(m["slices"]), int(m.get("dense") or 0))
+            rect_key = "k_rows_product"
         line = {
             "metric": "hbuild_nnz_per_s", "value": m["nnz_total"] / (m["build_ms"] * 1e-3), "unit": "nnz/s",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
@@ -748,7 +756,7 @@ def run_b200(args):
             "sigma_iter_ms": m["sigma_ms"], "sigma_nnz_per_s": m["nnz_total"] / (m["sigma_ms"] * 1e-3),
             "roofline": {"kernel": rect, "bound": "hbm", "achieved": fill_gbs, "peak": m["hbm_peak"],
                          "unit": "GB/s", "frac": fill_gbs / m["hbm_peak"],
-                         "traffic": load_traffic("k_rows_product") if args.workload == "cr2_cas12" else None,
+                         "traffic": load_traffic(rect_key) if args.workload == "cr2_cas12" else None,
                          "bytes_per_launch": m["B_fill"], "peak_source": m["peak_src"],
                          "note": "algorithmic bytes = determinants read + CSR (12 B/nnz) + rowptr written by "
                                  "rank 0's launch; duration = CUDA events around the launch on the library stream"},

@@ -408,6 +408,7 @@ int b2ci_csr_free(b2ci_ctx* ctx, b2ci_csr* m) {
   StreamScope scope(ctx);
   dev_free(m->rowptr);
   dev_free(m->loc_range);
+  dev_free(m->bin_list);
   if (ctx && m->colind_cap) big_release(ctx, 0, m->colind, m->colind_cap); else dev_free(m->colind);
   if (ctx && m->nzval_cap) big_release(ctx, 1, m->nzval, m->nzval_cap); else dev_free(m->nzval);
   delete m;

@@ -127,6 +127,10 @@ struct b2ci_csr {
   std::vector<int64_t> row_offsets;  // multi-GPU: row offsets of all ranks (lazy)
   size_t colind_cap = 0, nzval_cap = 0;  // allocated bytes when known (recycled through the context)
   void* loc_range = nullptr;  // device, nrows x int2: own-column sub-range of every row (sharded sigma, lazy)
+  // rows sorted into length classes for the binned SpMV (skewed matrices only; lazy)
+  void* bin_list = nullptr;   // device, nrows x int32: row indices, class after class
+  int64_t bin_off[5] = {0, 0, 0, 0, 0};
+  bool bins_tried = false;
 };
 
 namespace b2ci {

@@ -195,6 +195,73 @@ void launch_part(b2ci_ctx* ctx, const b2ci_csr* m, const double* x, double* y) {
   B2_CHECK_LAUNCH();
 }
 
+// ---- row-binned product for matrices with skewed row lengths (selected-CI lists: a few hundred to several
+// thousand non-zeros per row). One lane count per launch wastes lanes on the short rows and leaves the long
+// ones to a single warp; here the rows are sorted into four length classes once per matrix and every class
+// is multiplied with its own lanes-per-row, rows of a class side by side in a CTA (same life time).
+constexpr int NBINS = 4;
+__host__ __device__ __forceinline__ int bin_of(int64_t len) { return len < 48 ? 0 : (len < 384 ? 1 : (len < 3072 ? 2 : 3)); }
+__global__ void k_bin_flags(int64_t nrows, const int64_t* __restrict__ rowptr, int32_t* __restrict__ flags /* NBINS x nrows */,
+                            unsigned long long* __restrict__ minmax /* [0] min, [1] max */) {
+  const int64_t row = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (row >= nrows) return;
+  const int64_t len = rowptr[row + 1] - rowptr[row];
+  const int b = bin_of(len);
+#pragma unroll
+  for (int k = 0; k < NBINS; ++k) flags[int64_t(k) * nrows + row] = k == b ? 1 : 0;
+  atomicMin(minmax, (unsigned long long)len);
+  atomicMax(minmax + 1, (unsigned long long)len);
+}
+__global__ void k_bin_scatter(int64_t nrows, const int32_t* __restrict__ flags, const int32_t* __restrict__ excl,
+                              int32_t* __restrict__ list) {
+  const int64_t row = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (row < nrows && flags[row]) list[excl[row]] = int32_t(row);
+}
+template <int TPR>
+__global__ void __launch_bounds__(256)
+k_spmv_list(int64_t nlist, const int32_t* __restrict__ list, const int64_t* __restrict__ rowptr,
+            const int32_t* __restrict__ colind, const double* __restrict__ nzval, const double* __restrict__ x,
+            double* __restrict__ y) {
+  const int64_t gtid = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+  const int64_t li = gtid / TPR;
+  const int sub = int(gtid % TPR);
+  double acc0 = 0., acc1 = 0.;
+  int64_t row = 0;
+  if (li < nlist) {
+    row = list[li];
+    range_sum<TPR>(rowptr[row], rowptr[row + 1], sub, colind, nzval, x, acc0, acc1);
+  }
+  double acc = acc0 + acc1;
+#pragma unroll
+  for (int d = TPR >> 1; d > 0; d >>= 1) acc += __shfl_down_sync(0xffffffffu, acc, d, TPR);
+  if (li < nlist && sub == 0) y[row] = acc;
+}
+// rows of 3072 and more non-zeros: one CTA per row, eight warps on consecutive slices of it
+__global__ void __launch_bounds__(256)
+k_spmv_long(int64_t nlist, const int32_t* __restrict__ list, const int64_t* __restrict__ rowptr,
+            const int32_t* __restrict__ colind, const double* __restrict__ nzval, const double* __restrict__ x,
+            double* __restrict__ y) {
+  __shared__ double part[8];
+  const int row = list[blockIdx.x];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int64_t s = rowptr[row], e = rowptr[row + 1];
+  const int64_t chunk = (((e - s) + 7) / 8 + 1) & ~int64_t(1);  // even slice lengths keep the 16-byte alignment pattern
+  const int64_t a = min(e, s + w * chunk), b = min(e, a + chunk);
+  double acc0 = 0., acc1 = 0.;
+  range_sum<32>(a, b, lane, colind, nzval, x, acc0, acc1);
+  double acc = acc0 + acc1;
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) acc += __shfl_down_sync(0xffffffffu, acc, d);
+  if (lane == 0) part[w] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double t = 0.;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) t += part[k];
+    y[row] = t;
+  }
+}
+
 template <int TPR>
 void launch(b2ci_ctx* ctx, const b2ci_csr* m, const double* x, double* y) {
   const int64_t threads = m->nrows * TPR;
@@ -207,8 +274,61 @@ void launch(b2ci_ctx* ctx, const b2ci_csr* m, const double* x, double* y) {
 }  // namespace
 
 void spmv_launch_part(b2ci_ctx* ctx, const b2ci_csr* m, int part, const double* x, double* y);
+// length classes of the rows, built at the first product of a matrix. OFF by default (B2CI_SPMV_BINS=1 turns it
+// on): measured on the N2-like ASCI(14e,26o) matrix of 1e6 determinants (1.33e9 non-zeros, 100 .. 5000 per row) the
+// binned product takes 3.40 ms against 3.27 ms for the single launch -- the row lengths are not what keeps that
+// matrix at 0.75 of the HBM peak (full-CI: 0.92); the scattered 8-byte gathers of x are (one 32-byte L2 sector
+// per gather, 2.7x the matrix bytes over the L2 -> SM path).
+static void prepare_bins(b2ci_ctx* ctx, b2ci_csr* m) {
+  m->bins_tried = true;
+  const char* env = getenv("B2CI_SPMV_BINS");
+  if (m->nrows < 4096 || !env || atoi(env) == 0) return;
+  cudaStream_t st = ctx->stream;
+  const int64_t n = m->nrows;
+  DevBuf<int32_t> flags(size_t(NBINS) * n), excl(n + 1);
+  DevBuf<unsigned long long> mm(2);
+  const unsigned long long init[2] = {~0ull, 0ull};
+  B2_CUDA(cudaMemcpyAsync(mm, init, 16, cudaMemcpyHostToDevice, st));
+  const unsigned g = unsigned((n + 255) / 256);
+  k_bin_flags<<<g, 256, 0, st>>>(n, m->rowptr, flags, mm);
+  ctx->launches++;
+  unsigned long long hmm[2];
+  B2_CUDA(cudaMemcpyAsync(hmm, mm, 16, cudaMemcpyDeviceToHost, st));
+  B2_CUDA(cudaStreamSynchronize(st));
+  const double mean = double(m->nnz) / double(n);
+  // uniform rows (full-CI matrices): the single-launch kernel is already at the roofline
+  if (double(hmm[1]) < 1.5 * mean && double(hmm[0]) > 0.66 * mean) return;
+  int32_t* list = static_cast<int32_t*>(dev_alloc(size_t(n) * sizeof(int32_t)));
+  int64_t off = 0;
+  for (int k = 0; k < NBINS; ++k) {
+    exclusive_scan_i32(ctx, flags.p + size_t(k) * n, excl, n);
+    int32_t cnt = 0;
+    B2_CUDA(cudaMemcpyAsync(&cnt, excl.p + n, 4, cudaMemcpyDeviceToHost, st));
+    k_bin_scatter<<<g, 256, 0, st>>>(n, flags.p + size_t(k) * n, excl, list + off);
+    ctx->launches++;
+    B2_CUDA(cudaStreamSynchronize(st));
+    m->bin_off[k] = off;
+    off += cnt;
+  }
+  m->bin_off[NBINS] = off;
+  m->bin_list = list;
+  B2_CHECK_LAUNCH();
+}
 void spmv_launch(b2ci_ctx* ctx, const b2ci_csr* m, const double* x, double* y) {
   if (m->nrows == 0) return;
+  if (!m->bins_tried) prepare_bins(ctx, const_cast<b2ci_csr*>(m));
+  if (m->bin_list) {
+    const int32_t* L = static_cast<const int32_t*>(m->bin_list);
+    cudaStream_t st = ctx->stream;
+    auto nb = [&](int k) { return m->bin_off[k + 1] - m->bin_off[k]; };
+    if (nb(0)) k_spmv_list<4><<<unsigned((nb(0) * 4 + 255) / 256), 256, 0, st>>>(nb(0), L + m->bin_off[0], m->rowptr, m->colind, m->nzval, x, y);
+    if (nb(1)) k_spmv_list<16><<<unsigned((nb(1) * 16 + 255) / 256), 256, 0, st>>>(nb(1), L + m->bin_off[1], m->rowptr, m->colind, m->nzval, x, y);
+    if (nb(2)) k_spmv_list<32><<<unsigned((nb(2) * 32 + 255) / 256), 256, 0, st>>>(nb(2), L + m->bin_off[2], m->rowptr, m->colind, m->nzval, x, y);
+    if (nb(3)) k_spmv_long<<<unsigned(nb(3)), 256, 0, st>>>(nb(3), L + m->bin_off[3], m->rowptr, m->colind, m->nzval, x, y);
+    ctx->launches += (nb(0) > 0) + (nb(1) > 0) + (nb(2) > 0) + (nb(3) > 0);
+    B2_CHECK_LAUNCH();
+    return;
+  }
   if (getenv("B2CI_SPMV_SPLIT_TEST") && m->row_begin == 0 && m->nrows == m->ncols) {
     // (profiling hook: the two-part product of the sharded sigma on one GPU, columns split in the middle)
     b2ci_csr* mm = const_cast<b2ci_csr*>(m);

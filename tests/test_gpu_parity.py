@@ -178,6 +178,36 @@ def test_sigma_on_uploaded_csr_all_row_shapes(ctx):
         assert np.array_equal(rp2, rp) and np.array_equal(ci2, ci) and np.array_equal(nz2, nz)
 
 
+def test_sigma_row_binned_for_skewed_matrices(ctx, monkeypatch):
+    # selected-CI matrices have skewed row lengths: rows are sorted into four length classes (< 48, < 384, < 3072,
+    # longer) and every class gets its own lanes-per-row (one CTA per row for the longest). Same result as the
+    # oracle and as the single-launch kernel, empty rows and all classes present.
+    rng = np.random.default_rng(11)
+    n = 9000
+    lens = np.concatenate([rng.poisson(7, 3000), rng.poisson(150, 3000), rng.poisson(1200, 2900), rng.integers(3072, 6000, 100)])
+    rng.shuffle(lens)
+    lens[rng.integers(0, n, 40)] = 0
+    rp = np.concatenate([[0], np.cumsum(lens)]).astype(np.int64)
+    ci = np.concatenate([np.sort(rng.choice(n, size=l, replace=False)) for l in lens]).astype(np.int64)
+    nz = rng.normal(size=rp[-1])
+    x = rng.normal(size=n)
+    yo = port.spmv(rp, ci, nz, x)
+    bound = 1e-13 * port.spmv(rp, ci, np.abs(nz), np.abs(x)) + 1e-300
+    monkeypatch.setenv("B2CI_SPMV_BINS", "1")   # off by default (no gain measured on the ASCI matrices, see spmv.cu)
+    M = ctx.upload_csr(rp, ci, nz)
+    launches0 = ctx.launch_count
+    y = M.spmv(x)
+    y2 = M.spmv(x)
+    assert np.all(np.abs(y - yo) <= bound) and np.array_equal(y, y2)
+    monkeypatch.setenv("B2CI_SPMV_BINS", "0")
+    M1 = ctx.upload_csr(rp, ci, nz)
+    l1 = ctx.launch_count
+    y1 = M1.spmv(x)
+    assert ctx.launch_count - l1 == 1                  # the single-launch kernel
+    assert np.all(np.abs(y1 - yo) <= bound)
+    assert ctx.launch_count - launches0 > 8           # binned: preparation + four launches per product
+
+
 def test_diagonal(ctx):
     sp = W.config("small_cas8")
     a, b = port.generate_hilbert_space(sp.norb, sp.nalpha, sp.nbeta)
