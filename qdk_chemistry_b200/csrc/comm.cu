@@ -325,11 +325,10 @@ void sigma_sharded(b2ci_ctx* ctx, b2ci_csr* m, const std::vector<int64_t>& off, 
   const size_t n = size_t(off[nr]);
   P2P* s = p2p_state(ctx);
   if (!s->tried || (s->ok && s->cap < n)) p2p_setup(ctx, s, n);  // collective: n is the same everywhere
-  // Overlap pays when the own-column share is small and the exchange is a visible part of the step: measured
-  // on 2 GPUs the two half products run at 5.3 TB/s each against 6.0 TB/s for the single pass and the split
-  // costs more than the ~30 us exchange it hides, so the default is the plain path below 4 ranks
-  // (B2CI_SIGMA_OVERLAP=0/1 overrides).
-  bool overlap = nr >= 4;
+  // The overlapped form is OFF by default (B2CI_SIGMA_OVERLAP=1 turns it on). Measured on Cr2 CAS(12,12): the two
+  // partial products run at ~5.3 TB/s against 6.0 TB/s for the single pass, which costs more than the ~30-80 us
+  // exchange it hides -- sigma 2.27 vs 1.60 ms on 2 GPUs, 0.508 vs 0.434 ms per Davidson iteration on 8.
+  bool overlap = false;
   if (const char* env = getenv("B2CI_SIGMA_OVERLAP")) overlap = atoi(env) != 0;
   if (getenv("B2CI_NO_SIGMA_OVERLAP")) overlap = false;
   if (s->ok && overlap) {

@@ -70,10 +70,18 @@ template <bool FILL>
 __global__ void __launch_bounds__(256)
 k_string_adjacency(const uint64_t* __restrict__ str, int32_t nstr, int maxd, int skip_zero,
                    int32_t* __restrict__ cnt, int32_t* __restrict__ deg_cnt,
-                   const int64_t* __restrict__ adj_ptr, uint32_t* __restrict__ adj) {
+                   const int64_t* __restrict__ adj_ptr, uint32_t* __restrict__ adj,
+                   int32_t r_lo = 0, int32_t r_hi = INT32_MAX) {
   const int lane = threadIdx.x & 31;
   const int64_t r = (int64_t(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
   if (r >= nstr) return;
+  if (r < r_lo || r >= r_hi) {  // a row block only needs the adjacency of the runs its rows belong to
+    if (!FILL && lane == 0) {
+      cnt[r] = 0;
+      if (deg_cnt) { deg_cnt[3 * r] = 0; deg_cnt[3 * r + 1] = 0; deg_cnt[3 * r + 2] = 0; }
+    }
+    return;
+  }
   const uint64_t a = str[r];
   int64_t out = FILL ? adj_ptr[r] : 0;
   int32_t c = 0, c0 = 0, c2 = 0, c4 = 0;
@@ -2412,7 +2420,17 @@ void hbuild_csr(b2ci_ctx* ctx, const b2ci_dets* dets, int64_t row_begin, int64_t
     adj_ptr.alloc(nruns + 1);
     const unsigned ga = unsigned((int64_t(nruns) * 32 + 255) / 256);
     const int skipz = ctx->generator == 0 ? 1 : 0;
-    k_string_adjacency<false><<<ga, 256, 0, st>>>(run_alpha, nruns, maxd, skipz, acnt, nullptr, nullptr, nullptr);
+    // the runs of the first and the last row of the block bound the runs whose adjacency is needed
+    int32_t r_lo = 0, r_hi = nruns;
+    if (row_begin > 0 || row_end < n) {
+      int32_t h[2] = {0, 0};
+      B2_CUDA(cudaMemcpyAsync(&h[0], run_of.p + row_begin, 4, cudaMemcpyDeviceToHost, st));
+      B2_CUDA(cudaMemcpyAsync(&h[1], run_of.p + (row_end - 1), 4, cudaMemcpyDeviceToHost, st));
+      B2_CUDA(cudaStreamSynchronize(st));
+      r_lo = h[0];
+      r_hi = h[1] + 1;
+    }
+    k_string_adjacency<false><<<ga, 256, 0, st>>>(run_alpha, nruns, maxd, skipz, acnt, nullptr, nullptr, nullptr, r_lo, r_hi);
     ctx->launches++;
     B2_CHECK_LAUNCH();
     exclusive_scan_i32_to_i64(ctx, acnt, adj_ptr, nruns);
@@ -2420,7 +2438,7 @@ void hbuild_csr(b2ci_ctx* ctx, const b2ci_dets* dets, int64_t row_begin, int64_t
     B2_CUDA(cudaMemcpyAsync(&nadj, adj_ptr.p + nruns, 8, cudaMemcpyDeviceToHost, st));
     B2_CUDA(cudaStreamSynchronize(st));
     adj.alloc(nadj > 0 ? nadj : 1);
-    k_string_adjacency<true><<<ga, 256, 0, st>>>(run_alpha, nruns, maxd, skipz, nullptr, nullptr, adj_ptr, adj);
+    k_string_adjacency<true><<<ga, 256, 0, st>>>(run_alpha, nruns, maxd, skipz, nullptr, nullptr, adj_ptr, adj, r_lo, r_hi);
     ctx->launches++;
     B2_CHECK_LAUNCH();
   };
