@@ -1449,64 +1449,110 @@ __global__ void k_dense_rec(const DenseArgs D) {
 // single-excitation elements of every row: leading sum + the other spin's V_red terms in ascending orbital
 // order (the reference's order of additions, matrix_elements.hpp:176-186)
 constexpr int SAB_ROWS = 64;  // rows of one alpha run per CTA
-template <typename S, bool SMEM>
+// occupied orbitals of a string, ascending, into p[]; returns their number (warp-uniform input: no divergence)
+template <typename S, int NT = 0>
+__device__ __forceinline__ int occupied_positions(S bits, int (&p)[16], S& rest) {
+  int n = 0;
+#pragma unroll
+  for (int u = 0; u < (NT > 0 ? NT : 16); ++u) {
+    p[u] = 0;
+    if (bits) {
+      p[u] = (sizeof(S) == 4 ? __ffs(int(bits)) : __ffsll((long long)bits)) - 1;
+      bits &= bits - 1;
+      ++n;
+    }
+  }
+  rest = bits;  // strings with more than 16 electrons: the remainder goes through the generic loop
+  return n;
+}
+// h + the NT terms Vr[p[0]], Vr[p[1]], ... added one after the other (the reference's order of additions)
+template <int NT>
+__device__ __forceinline__ double add_terms(double h, const double* __restrict__ Vr, const int (&p)[16]) {
+#pragma unroll
+  for (int u = 0; u < NT; ++u) h += Vr[p[u]];
+  return h;
+}
+// PART 0: beta-single elements sb(k, t) of all rows of the CTA (positions: the run's alpha string);
+// PART 1: alpha-single elements sa(k, s), one warp per row (positions: the row's beta string).
+// NT = number of electrons of the string that supplies the positions (exact unrolling: the sums are the whole
+// cost of the kernel); NT == 0: any count, generic loops.
+template <typename S, bool SMEM, int PART, int NT>
 __global__ void __launch_bounds__(256)
-k_dense_sab(const DenseArgs D, int64_t nrows_tot, unsigned inv_per) {
-  // CTA = (alpha run, 64 consecutive beta strings); one item (row, q) per thread and step. The gathers of
-  // V_red (8 bytes per lane, all over the n^3 table) run at two sectors per clock through L1 and were this
-  // kernel's whole cost: the table is staged in shared memory once per CTA instead (SMEM; n <= 18).
-  // Strings as S (32-bit words when norb <= 32).
+k_dense_sab(const DenseArgs D, int64_t nrows_tot, unsigned inv_len2) {
+  // CTA = (alpha run, 64 consecutive beta strings). Every element is a leading value plus the other spin's
+  // V_red terms in ascending orbital order (the reference's order of additions, matrix_elements.hpp:176-186).
+  // The orbital positions are the same for all lanes of a step, so they are extracted once and each term is one
+  // shared-memory load + one add per lane. The n^3 table of V_red is staged in shared memory per CTA (SMEM,
+  // n <= 18): 8-byte gathers all over it run at two sectors per clock through L1.
   extern __shared__ double s_vr[];
   const ProdArgs& A = D.P;
   const int n = A.I.n;
-  const size_t n2 = size_t(n) * n;
+  // shared-memory copy with the n-vectors V_red(., v, o) at an ODD stride: lanes read the same orbital of
+  // different (v, o) vectors, and at the natural stride n = 12 those addresses fall on 4 of the 16 8-byte banks
+  const int pad = SMEM ? (n | 1) : n;
   if (SMEM) {
-    for (int i = threadIdx.x; i < n * n * n; i += blockDim.x) s_vr[i] = A.I.Vr[i];
+    for (int i = threadIdx.x; i < n * n * n; i += blockDim.x) s_vr[(i / n) * pad + (i % n)] = A.I.Vr[i];
     __syncthreads();
   }
+  const double* __restrict__ VR = SMEM ? s_vr : A.I.Vr;
   const unsigned per = unsigned(D.per_row);
   const uint32_t r = uint32_t(D.run0 + blockIdx.y);
   const unsigned k0 = blockIdx.x * SAB_ROWS;
   const unsigned nrows_cta = min(unsigned(SAB_ROWS), unsigned(A.nb) - k0);
-  const int64_t sp = A.sptr[r];
-  const unsigned ns = unsigned(A.sptr[r + 1] - sp);
-  const S abits = S(A.run_alpha[r]);
-  for (unsigned f = threadIdx.x; f < nrows_cta * per; f += blockDim.x) {
-    const unsigned j = __umulhi(f, inv_per);  // f / per
-    const unsigned q = f - j * per;
-    const unsigned k = k0 + j;
-    const int64_t rowl = int64_t(blockIdx.y) * A.nb + k;
-    if (rowl >= nrows_tot) continue;
-    double out = 0.;
-    uint32_t m = 0u;
-    double h = 0.;
-    S bits = 0;
-    bool live = false;
-    if (q < unsigned(A.smem_a)) {
-      if (q < ns) {
-        m = A.smeta[sp + q];
-        h = A.slead[sp + q];
-        bits = S(A.tmpl_beta[k]);
-        live = true;
+  const int64_t row_base = int64_t(blockIdx.y) * A.nb + k0;
+  if (row_base >= nrows_tot) return;
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const unsigned len2 = unsigned(D.len2);
+  int pos[16];
+  S rest;
+  if (PART == 0) {
+    const int na = occupied_positions<S, NT>(S(A.run_alpha[r]), pos, rest);
+    for (unsigned f = threadIdx.x; f < nrows_cta * len2; f += blockDim.x) {
+      const unsigned j = __umulhi(f, inv_len2);  // f / len2
+      const unsigned t = f - j * len2;
+      const int64_t e = int64_t(k0 + j) * len2 + t;
+      const uint32_t m = A.b2_meta[e];
+      double h = A.b2_val[e];
+      const double* Vr = VR + (((m >> 8) & 0xFFu) + (m & 0xFFu) * n) * pad;
+      if (NT > 0) {
+        h = add_terms<NT>(h, Vr, pos);
+      } else {
+        for (int u = 0; u < 16; ++u)
+          if (u < na) h += Vr[pos[u]];
+        for (S qq = rest; qq; qq &= qq - 1) h += Vr[(sizeof(S) == 4 ? __ffs(int(qq)) : __ffsll((long long)qq)) - 1];
       }
-    } else if (q - unsigned(A.smem_a) < unsigned(D.len2)) {
-      const int64_t e = int64_t(k) * D.len2 + (q - A.smem_a);
-      m = A.b2_meta[e];
-      h = A.b2_val[e];
-      bits = abits;
-      live = true;  // (the self slot is never read)
+      D.sab[(row_base + j) * per + A.smem_a + t] = flip_sign_if(h, m >> 16);  // (the self slot is never read)
     }
-    if (live) {
-      // the other spin's V_red terms in ascending orbital order (the reference's order of additions)
-      const size_t vo = ((m >> 8) & 0xFFu) * n + (m & 0xFFu) * n2;
-      const double* Vr = SMEM ? s_vr + vo : A.I.Vr + vo;
-      for (S qq = bits; qq; qq &= qq - 1) {
-        const int p = (sizeof(S) == 4 ? __ffs(int(qq)) : __ffsll((long long)qq)) - 1;
-        h += SMEM ? Vr[p] : ldg(Vr + p);
+  } else {
+    const int64_t sp = A.sptr[r];
+    const unsigned ns = unsigned(A.sptr[r + 1] - sp);
+    for (unsigned j = w; j < nrows_cta; j += blockDim.x / 32) {
+      const int nbp = occupied_positions<S, NT>(S(A.tmpl_beta[k0 + j]), pos, rest);
+      for (unsigned q = lane; q < ns; q += 32) {
+        const uint32_t m = A.smeta[sp + q];
+        double h = A.slead[sp + q];
+        const double* Vr = VR + (((m >> 8) & 0xFFu) + (m & 0xFFu) * n) * pad;
+        if (NT > 0) {
+          h = add_terms<NT>(h, Vr, pos);
+        } else {
+          for (int u = 0; u < 16; ++u)
+            if (u < nbp) h += Vr[pos[u]];
+          for (S qq = rest; qq; qq &= qq - 1) h += Vr[(sizeof(S) == 4 ? __ffs(int(qq)) : __ffsll((long long)qq)) - 1];
+        }
+        D.sab[(row_base + j) * per + q] = flip_sign_if(h, m >> 16);
       }
-      out = flip_sign_if(h, m >> 16);
     }
-    D.sab[rowl * per + q] = out;
+  }
+}
+// launch PART with the exact term count when it is 1 .. 12
+template <typename S, bool SMEM, int PART>
+void launch_dense_sab(int nt, dim3 gs, size_t smem, cudaStream_t st, const DenseArgs& DA, int64_t nrows_tot, unsigned inv) {
+  switch (nt) {
+#define B2_SAB_CASE(N) case N: k_dense_sab<S, SMEM, PART, N><<<gs, 256, smem, st>>>(DA, nrows_tot, inv); break;
+    B2_SAB_CASE(1) B2_SAB_CASE(2) B2_SAB_CASE(3) B2_SAB_CASE(4) B2_SAB_CASE(5) B2_SAB_CASE(6)
+    B2_SAB_CASE(7) B2_SAB_CASE(8) B2_SAB_CASE(9) B2_SAB_CASE(10) B2_SAB_CASE(11) B2_SAB_CASE(12)
+#undef B2_SAB_CASE
+    default: k_dense_sab<S, SMEM, PART, 0><<<gs, 256, smem, st>>>(DA, nrows_tot, inv); break;
   }
 }
 
@@ -2548,6 +2594,7 @@ void hbuild_csr(b2ci_ctx* ctx, const b2ci_dets* dets, int64_t row_begin, int64_t
     int64_t nslots = 0, ncadj = 0, nsing = 0;
     unsigned int nsmall = 0;
     int shp[6] = {0, 0, 0, 0, 0, 0};
+    uint64_t first_alpha = 0, first_beta = 0;  // electrons per spin of a full-CI list = popcount of any string
     int32_t rc[4] = {0, 0, 0, 0};
     int64_t bp[2] = {0, 0}, bq[2] = {0, 0};
     {
@@ -2569,11 +2616,15 @@ void hbuild_csr(b2ci_ctx* ctx, const b2ci_dets* dets, int64_t row_begin, int64_t
       B2_CUDA(cudaMemcpyAsync(pin + 8, b4_ptr.p, 16, cudaMemcpyDeviceToHost, st));
       B2_CUDA(cudaMemcpyAsync(pin + 10, small_cnt.p, sizeof(unsigned int), cudaMemcpyDeviceToHost, st));
       B2_CUDA(cudaMemcpyAsync(pin + 11, shape.p, 6 * sizeof(int), cudaMemcpyDeviceToHost, st));
+      B2_CUDA(cudaMemcpyAsync(pin + 15, run_alpha.p + row_begin / nb, 8, cudaMemcpyDeviceToHost, st));
+      B2_CUDA(cudaMemcpyAsync(pin + 16, dets->beta, 8, cudaMemcpyDeviceToHost, st));
       mark("metadata + count queued");
       B2_CUDA(cudaStreamSynchronize(st));
       nslots = pin[0]; ncadj = pin[1]; nsing = pin[2];
       nsmall = *reinterpret_cast<const unsigned int*>(pin + 10);
       memcpy(shp, pin + 11, 6 * sizeof(int));
+      first_alpha = uint64_t(pin[15]);
+      first_beta = uint64_t(pin[16]);
       memcpy(rc, pin + 4, 16); memcpy(bp, pin + 6, 16); memcpy(bq, pin + 8, 16);
       mark("metadata + count (sync C)");
     }
@@ -2702,16 +2753,29 @@ void hbuild_csr(b2ci_ctx* ctx, const b2ci_dets* dets, int64_t row_begin, int64_t
         k_dense_tables<<<unsigned((nruns_blk * 32 + 127) / 128), 128, 0, st>>>(DA, nruns_blk);
         k_dense_rec<<<unsigned((nb * DA.rec_stride + 255) / 256), 256, 0, st>>>(DA);
         {
-          const unsigned inv_per = unsigned((uint64_t(1) << 32) / unsigned(DA.per_row)) + 1u;
+          const unsigned inv_per = unsigned((uint64_t(1) << 32) / unsigned(DA.len2)) + 1u;  // f / len2 by umulhi
           const dim3 gs(unsigned((nb + SAB_ROWS - 1) / SAB_ROWS), unsigned(nruns_blk));
-          const size_t vr_bytes = size_t(ctx->norb) * ctx->norb * ctx->norb * 8;
+          const size_t vr_bytes = size_t(ctx->norb) * ctx->norb * (ctx->norb | 1) * 8;
+          // electrons per spin (all strings of a full-CI list have the same count): exact unrolling of the sums
+          const int na_e = __builtin_popcountll(first_alpha), nb_e = __builtin_popcountll(first_beta);
           if (vr_bytes <= 46 * 1024) {
-            if (ctx->norb <= 32) k_dense_sab<uint32_t, true><<<gs, 256, vr_bytes, st>>>(DA, nrows_tot, inv_per);
-            else k_dense_sab<uint64_t, true><<<gs, 256, vr_bytes, st>>>(DA, nrows_tot, inv_per);
+            if (ctx->norb <= 32) {
+              launch_dense_sab<uint32_t, true, 0>(na_e, gs, vr_bytes, st, DA, nrows_tot, inv_per);
+              launch_dense_sab<uint32_t, true, 1>(nb_e, gs, vr_bytes, st, DA, nrows_tot, inv_per);
+            } else {
+              launch_dense_sab<uint64_t, true, 0>(0, gs, vr_bytes, st, DA, nrows_tot, inv_per);
+              launch_dense_sab<uint64_t, true, 1>(0, gs, vr_bytes, st, DA, nrows_tot, inv_per);
+            }
           } else {
-            if (ctx->norb <= 32) k_dense_sab<uint32_t, false><<<gs, 256, 0, st>>>(DA, nrows_tot, inv_per);
-            else k_dense_sab<uint64_t, false><<<gs, 256, 0, st>>>(DA, nrows_tot, inv_per);
+            if (ctx->norb <= 32) {
+              launch_dense_sab<uint32_t, false, 0>(0, gs, 0, st, DA, nrows_tot, inv_per);
+              launch_dense_sab<uint32_t, false, 1>(0, gs, 0, st, DA, nrows_tot, inv_per);
+            } else {
+              launch_dense_sab<uint64_t, false, 0>(0, gs, 0, st, DA, nrows_tot, inv_per);
+              launch_dense_sab<uint64_t, false, 1>(0, gs, 0, st, DA, nrows_tot, inv_per);
+            }
           }
+          ctx->launches++;
         }
         ctx->launches += 3;
         B2_CHECK_LAUNCH();
