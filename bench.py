@@ -37,6 +37,9 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
+# the CPU legs run OpenMP inside this process: idle worker threads must sleep, not spin, while the GPU legs
+# (host-latency sensitive: ASCI growth through the plugin) run afterwards
+os.environ.setdefault("OMP_WAIT_POLICY", "passive")
 
 EPS = float(np.finfo(np.float64).eps)
 

@@ -361,10 +361,33 @@ k_multi_dot(int64_t N, int k, const double* __restrict__ A, int64_t ld,
     __syncthreads();
   }
   if (counter && last_cta_done(counter, gridDim.x * gridDim.y)) {
-    for (int j = threadIdx.x; j < k; j += DOT_THREADS) {
-      double s = 0.;
-      for (unsigned b = 0; b < gridDim.x; ++b) s += partial[int64_t(b) * k + j];
-      out[j] = s;
+    // sum over the CTAs in CTA order (the order of the former reduction kernel: same bits), with the partials of
+    // 16 columns at a time staged in shared memory by all threads -- a single thread walking gridDim.x dependent
+    // global loads per column was a 30 us tail on every dot product
+    constexpr int JB = 16, MAXB = 320;
+    __shared__ double stage[JB * MAXB];
+    const unsigned nb = gridDim.x;
+    if (nb <= MAXB) {
+      for (int j0 = 0; j0 < k; j0 += JB) {
+        const int nj = min(JB, k - j0);
+        for (unsigned t = threadIdx.x; t < nb * nj; t += DOT_THREADS) {
+          const unsigned b = t / nj, jj = t - b * nj;
+          stage[jj * MAXB + b] = partial[int64_t(b) * k + j0 + jj];
+        }
+        __syncthreads();
+        if (int(threadIdx.x) < nj) {
+          double s = 0.;
+          for (unsigned b = 0; b < nb; ++b) s += stage[threadIdx.x * MAXB + b];
+          out[j0 + threadIdx.x] = s;
+        }
+        __syncthreads();
+      }
+    } else {
+      for (int j = threadIdx.x; j < k; j += DOT_THREADS) {
+        double s = 0.;
+        for (unsigned b = 0; b < nb; ++b) s += partial[int64_t(b) * k + j];
+        out[j] = s;
+      }
     }
   }
 }
@@ -417,7 +440,9 @@ __global__ void k_scale(int64_t N, double a, double* __restrict__ w) {
 }
 // w /= sqrt(nrm2[0]) with the squared norm on the device (left alone when the norm is not above min_norm:
 // the host sees the same number and takes the reference's fallback)
-__global__ void k_scale_by_norm(int64_t N, const double* __restrict__ nrm2, double min_norm, double* __restrict__ w) {
+__global__ void k_scale_by_norm(int64_t N, const double* __restrict__ nrm2, double min_norm, double* __restrict__ w,
+                                double* __restrict__ nrm2_copy) {
+  if (nrm2_copy && blockIdx.x == 0 && threadIdx.x == 0) nrm2_copy[0] = nrm2[0];
   const double nrm = sqrt(nrm2[0]);
   if (!(nrm > min_norm)) return;
   const double a = 1.0 / nrm;
@@ -463,10 +488,20 @@ k_residual(int64_t N, int k, const double* __restrict__ V, const double* __restr
     for (int wv = 0; wv < 8; ++wv) s += red[wv];
     partial[blockIdx.x] = s;
   }
-  if (last_cta_done(counter, gridDim.x) && threadIdx.x == 0) {
+  if (last_cta_done(counter, gridDim.x)) {
+    // (fixed-shape tree over the CTAs' partials; ||r|| only decides convergence, its last bit feeds nothing)
     double s = 0.;
-    for (unsigned b = 0; b < gridDim.x; ++b) s += partial[b];
-    out[0] = s;
+    for (unsigned b = threadIdx.x; b < gridDim.x; b += blockDim.x) s += partial[b];
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) s += __shfl_down_sync(0xffffffffu, s, d);
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      double t = 0.;
+      for (int wv = 0; wv < 8; ++wv) t += red[wv];
+      out[0] = t;
+    }
   }
 }
 // extract_diagonal_elements: first entry of the row whose column is the row's global index
@@ -531,8 +566,7 @@ void gram_schmidt_queue(Work& W, int k, const double* V, double* w) {
   project(W, k, V, w);
   // ||w||^2 by the same dot-product kernel (and summation order) as gram_schmidt's norm2
   dots(W, 1, w, w, nullptr);
-  B2_CUDA(cudaMemcpyAsync(W.scal.p + 1, W.small.p, 8, cudaMemcpyDeviceToDevice, W.ctx->stream));
-  k_scale_by_norm<<<W.nstream, 256, 0, W.ctx->stream>>>(W.N, W.scal.p + 1, GS_MIN_NORM, w);
+  k_scale_by_norm<<<W.nstream, 256, 0, W.ctx->stream>>>(W.N, W.small.p, GS_MIN_NORM, w, W.scal.p + 1);
   W.ctx->launches++;
   B2_CHECK_LAUNCH();
 }
