@@ -33,13 +33,6 @@ void iota_u32(b2ci_ctx* ctx, uint32_t* v, int64_t n);
 namespace {
 
 constexpr int ROW_WARPS = 8;  // warps (rows) per CTA
-#ifndef B2CI_ROWS_FLAT
-// general-list scan variant: walk 32 adjacent runs as one concatenated sequence. Bit-identical output
-// (parity tests green), but measured SLOWER on the N2 ASCI run to 1e6 determinants (count passes
-// 767 ms against 410-460 ms): the prefix / run-start bookkeeping costs more instructions than the
-// fuller lanes save at these run lengths. Kept for lists with very short runs; off by default.
-#define B2CI_ROWS_FLAT 0
-#endif
 
 __global__ void k_run_flags(const uint64_t* __restrict__ alpha, int64_t n,
                             int32_t* __restrict__ flag) {
@@ -152,7 +145,7 @@ struct RowArgs {
   const int64_t* bra_run_start = nullptr;  // BLK: first bra determinant of every bra run
   const int32_t* row_list = nullptr;       // optional: the launch's rows (the rest are taken by the tiled scan)
   const void* beta_s = nullptr;            // ket beta strings as 32-bit words (norb <= 32), else NULL
-  const int32_t* struct_cnt = nullptr;  // k_rows_hits: structural row lengths of the count pass
+  const int32_t* struct_cnt = nullptr;  // gathers and k_rows_hits_flat: structural row lengths of the count pass
   int64_t row_stride = 1;               // sampling (estimate pass): row r of the launch is row r * row_stride
 };
 
@@ -275,77 +268,6 @@ k_rows(const RowArgs A) {
       }
     };
     const int64_t e0 = A.adj_ptr[r], e1 = A.adj_ptr[r + 1];
-#if B2CI_ROWS_FLAT
-    // The scan is bound by instruction issue (ncu: 75 % issue utilisation, 46k warp instructions per
-    // row at 2e5 determinants); with short adjacent runs one run per 32-lane step wastes lanes. In
-    // this variant the runs are taken 32 at a time -- adjacency entries and run bounds loaded by all lanes at once -- and their
-    // determinants are walked as ONE concatenated sequence, 32 positions per step, whatever run
-    // they belong to (run of a position: prefix sums of the run lengths + a bit mask of run starts).
-    for (int64_t eb = e0; eb < e1; eb += 32) {
-      const int nb = int(e1 - eb < 32 ? e1 - eb : 32);
-      uint32_t pk_l = 0;
-      int64_t ks_l = 0;
-      int32_t len_l = 0;
-      if (lane < nb) {
-        pk_l = A.adj[eb + lane];
-        ks_l = A.run_start[pk_l >> 2];
-        len_l = int32_t(A.run_start[(pk_l >> 2) + 1] - ks_l);
-      }
-      int32_t incl = len_l;
-#pragma unroll
-      for (int d = 1; d < 32; d <<= 1) {
-        const int32_t v = __shfl_up_sync(0xffffffffu, incl, d);
-        if (lane >= d) incl += v;
-      }
-      const int32_t off_l = incl - len_l;                       // first position of lane's run
-      const int32_t T = __shfl_sync(0xffffffffu, incl, 31);     // positions in this batch of runs
-      const int da_l = int(pk_l & 3u) * 2;
-      for (int32_t p0 = 0; p0 < T; p0 += 32) {
-        // run of the step's first position, then one more for every run start inside the step
-        const int tb = __popc(__ballot_sync(0xffffffffu, lane < nb && off_l <= p0)) - 1;
-        const int32_t rel = off_l - p0;
-        const unsigned sbit = (lane < nb && lane > tb && rel < 32) ? (1u << rel) : 0u;
-        const unsigned starts = __reduce_or_sync(0xffffffffu, sbit);
-        const int my_run = tb + __popc(starts & (0xFFFFFFFFu >> (31 - lane)));
-        const int64_t ks = __shfl_sync(0xffffffffu, ks_l, my_run);
-        const int32_t off = __shfl_sync(0xffffffffu, off_l, my_run);
-        const int da = __shfl_sync(0xffffffffu, da_l, my_run);
-        const int32_t p = p0 + lane;
-        const bool valid = p < T;
-        const int64_t j = ks + (p - off);
-        bool hit = false;
-        if (valid) hit = (da + __popcll(bi ^ A.beta[j])) <= 4;
-        const int nvalid = T - p0 < 32 ? T - p0 : 32;
-        const int64_t j_first = __shfl_sync(0xffffffffu, j, 0), j_last = __shfl_sync(0xffffffffu, j, nvalid - 1);
-        flush_group(j_first);
-        // beta-group members inside the step's index range: in one of its runs (alpha distance
-        // <= 2, found by the scan) they are stepped over; in a gap between two runs they have to
-        // come out between those runs' hits, so the step is then pushed run by run
-        bool gap = false;
-        while (nextj <= j_last) {
-          if (__ballot_sync(0xffffffffu, valid && j == nextj)) {
-            ++bpos;
-            nextj = bpos < bend ? int64_t(A.bgrp_mem[bpos]) : INT64_MAX;
-          } else {
-            gap = true;
-            break;
-          }
-        }
-        if (!gap) {
-          push(hit, j);
-        } else {
-          const int t_last = __shfl_sync(0xffffffffu, my_run, nvalid - 1);
-          for (int t = tb; t <= t_last; ++t) {
-            const bool mine = valid && my_run == t;
-            const unsigned mm = __ballot_sync(0xffffffffu, mine);
-            const int64_t jf = __shfl_sync(0xffffffffu, j, __ffs(mm) - 1);
-            flush_group(jf);
-            push(hit && mine, j);
-          }
-        }
-      }
-    }
-#else
     for (int64_t e = e0; e < e1; ++e) {
       const uint32_t pk = A.adj[e];
       const int da = int(pk & 3u) * 2;
@@ -380,7 +302,6 @@ k_rows(const RowArgs A) {
         if (nin < 32) break;
       }
     }
-#endif
     flush_group(INT64_MAX);
     if (qn > 0) {
       if (keep_hits) store_hits(A, row, q, qn, lane, prev_chunk);
@@ -390,29 +311,6 @@ k_rows(const RowArgs A) {
   if (lane == 0 && A.row_cnt) A.row_cnt[row] = cnt;
 }
 
-// fill pass from the stored hit lists: every chunk is full except the last of a row
-template <bool EVAL, bool BLK>
-__global__ void __launch_bounds__(ROW_WARPS * 32)
-k_rows_hits(const RowArgs A) {
-  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-  const int64_t row = int64_t(blockIdx.x) * ROW_WARPS + w;
-  if (row >= A.nrows) return;
-  const int64_t il = A.row_begin + row;
-  const uint64_t ai = BLK ? A.bra_alpha[il] : A.alpha[il], bi = BLK ? A.bra_beta[il] : A.beta[il];
-  const int64_t i = (BLK && A.rowmap) ? int64_t(A.rowmap[il]) : il;
-  int32_t remaining = A.struct_cnt[row];
-  int32_t chunk = remaining > 0 ? A.hit_head[row] : -1;
-  int64_t out = A.rowptr[row];
-  int32_t cnt = 0;
-  while (remaining > 0) {
-    const int nvalid = remaining < 32 ? remaining : 32;
-    const int32_t nxt = A.hit_next[chunk];
-    process_batch<true, EVAL, BLK>(A, i, ai, bi, A.hit_cols + size_t(chunk) * 32, nvalid, lane, out, cnt);
-    remaining -= nvalid;
-    chunk = nxt;
-  }
-  if (lane == 0 && A.row_cnt) A.row_cnt[row] = cnt;
-}
 
 // ------------------------------------------------------------------ tiled scan of general lists
 // The warp-per-row scan above spends one instruction stream per (row, 32 strings): every row of an
