@@ -342,6 +342,8 @@ struct TileArgs {
   int32_t* tile_next;        // [capacity]
   int32_t* unit_head;        // [nunits] first chunk (-1: none)
   int32_t* unit_nent;        // [nunits] entries of the unit (all chunks full but the last)
+  int32_t* unit_nent_c;      // [nunits] of them class (c) entries (they come first)
+  int32_t* row_cnt_c;        // [nrows] class (c) connections of every row (tiled rows only)
   unsigned int* cursor;
   unsigned int capacity;
 };
@@ -362,60 +364,80 @@ k_rows_tile(const TileArgs T) {
   const S bi = S(BLK ? A.bra_beta[il] : A.beta[il]);
   const int32_t r = BLK ? A.bra_run[il] : A.run_of[il];
   const S* __restrict__ beta_s = static_cast<const S*>(T.beta_s);
-  int32_t cnt = 0;                      // this lane's row length
+  const unsigned lt = (1u << lane) - 1u;
+  int32_t cnt = 0, cnt_c = 0;           // this lane's row: all connections / those of class (c)
   int32_t chunk = -1, pos = TILE_CH;    // warp-uniform stream state
   int32_t nent = 0;
   uint2* __restrict__ ent = nullptr;    // current chunk
-  auto emit = [&](unsigned m, int32_t j) {  // warp-uniform
-    if (pos == TILE_CH) {
-      unsigned int c = 0;
-      if (lane == 0) c = atomicAdd(T.cursor, 1u);
-      c = __shfl_sync(0xffffffffu, c, 0);
-      const int32_t nc = c < T.capacity ? int32_t(c) : -1;  // overflow: counting goes on, nothing is stored
-      if (lane == 0) {
-        if (chunk >= 0) T.tile_next[chunk] = nc;
-        else if (nent == 0) T.unit_head[u] = nc;
-        if (nc >= 0) T.tile_next[nc] = -1;
-      }
-      chunk = nc;
-      pos = 0;
-      ent = nc >= 0 ? T.tile_ent + size_t(nc) * TILE_CH : nullptr;
+  auto new_chunk = [&]() {              // warp-uniform
+    unsigned int c = 0;
+    if (lane == 0) c = atomicAdd(T.cursor, 1u);
+    c = __shfl_sync(0xffffffffu, c, 0);
+    const int32_t nc = c < T.capacity ? int32_t(c) : -1;  // overflow: counting goes on, nothing is stored
+    if (lane == 0) {
+      if (chunk >= 0) T.tile_next[chunk] = nc;
+      else if (nent == 0) T.unit_head[u] = nc;
+      if (nc >= 0) T.tile_next[nc] = -1;
     }
+    chunk = nc;
+    pos = 0;
+    ent = nc >= 0 ? T.tile_ent + size_t(nc) * TILE_CH : nullptr;
+  };
+  auto emit = [&](unsigned m, int32_t j) {  // one entry, warp-uniform
+    if (pos == TILE_CH) new_chunk();
     if (lane == 0 && ent) ent[pos] = make_uint2(m, unsigned(j));
     ++pos;
     ++nent;
   };
+  int32_t nent_c = 0;
   if (ai != 0 || A.pair_rule) {
-    const int32_t g = valid ? (BLK ? A.bra_grp[il] : A.bgrp_of[il]) : -1;
-    int64_t bpos = g >= 0 ? A.bgrp_start[g] : 0;
-    const int64_t bend = g >= 0 ? A.bgrp_start[g + 1] : 0;
-    constexpr int32_t NONE = INT32_MAX;
-    int32_t nextj = bpos < bend ? int32_t(A.bgrp_mem[bpos]) : NONE;
-    // class (c): same beta string, alpha double excitation -- members below `bound`, one per lane and round
-    auto flush_group = [&](int32_t bound) {
-      while (__any_sync(0xffffffffu, nextj < bound)) {
+    // ---- class (c) first: same beta string, alpha double excitation. All rows of the unit share the alpha
+    // string, so row by row the warp walks the row's beta group with one member per LANE (a per-lane walk of 32
+    // different groups ran with 3 of 32 lanes busy and was a third of this kernel's instructions); the hits of a
+    // step leave together as single-row entries. They ascend per row; k_tile_gather merges them with the row's
+    // scan hits, which follow in the stream.
+    const int32_t g_l = valid ? (BLK ? A.bra_grp[il] : A.bgrp_of[il]) : -1;
+    for (int l = 0; l < ulen; ++l) {
+      const int32_t g = __shfl_sync(0xffffffffu, g_l, l);
+      if (g < 0) continue;
+      const int64_t b0 = A.bgrp_start[g], b1 = A.bgrp_start[g + 1];
+      int32_t nrow = 0;
+      for (int64_t p0 = b0; p0 < b1; p0 += 32) {
+        const int64_t p = p0 + lane;
         bool hit = false;
-        const int32_t jm = nextj;
-        if (nextj < bound) {
-          const uint64_t aj = A.alpha[nextj];
+        int32_t j = 0;
+        if (p < b1) {
+          j = int32_t(A.bgrp_mem[p]);
+          const uint64_t aj = A.alpha[j];
           hit = (aj != 0 || A.pair_rule) && __popcll(ai ^ aj) == 4;
-          ++bpos;
-          nextj = bpos < bend ? int32_t(A.bgrp_mem[bpos]) : NONE;
         }
-        cnt += hit ? 1 : 0;
-        unsigned m = __ballot_sync(0xffffffffu, hit);
-        while (m) {
-          const int l = __ffs(m) - 1;
-          emit(1u << l, __shfl_sync(0xffffffffu, jm, l));
-          m &= m - 1;
+        const unsigned m = __ballot_sync(0xffffffffu, hit);
+        if (!m) continue;
+        const int nh = __popc(m);
+        // room for nh entries in the current chunk (else finish it: a chunk is never left partly empty in the
+        // middle of the stream, so pad by splitting the step)
+        int done = 0;
+        while (done < nh) {
+          if (pos == TILE_CH) new_chunk();
+          const int take = min(nh - done, TILE_CH - pos);
+          const int my = __popc(m & lt);
+          if (hit && my >= done && my < done + take && ent) ent[pos + my - done] = make_uint2(1u << l, unsigned(j));
+          pos += take;
+          nent += take;
+          done += take;
         }
+        nrow += nh;
       }
-    };
+      if (lane == l) cnt_c = nrow;
+    }
+    nent_c = nent;
+    cnt = cnt_c;
+    // ---- classes (a) and (b): the beta strings of the adjacent runs (own run: distance <= 4, runs one alpha
+    // single away: distance <= 2), every staged string against the 32 row strings
     const int64_t e0 = A.adj_ptr[r], e1 = A.adj_ptr[r + 1];
     for (int64_t e = e0; e < e1; ++e) {
       const uint32_t pk = A.adj[e];
       const int32_t ks = int32_t(A.run_start[pk >> 2]), ke = int32_t(A.run_start[(pk >> 2) + 1]);
-      flush_group(ks);
       const int lim = valid ? 4 - int(pk & 3u) * 2 : -1;  // idle lanes never hit
       const S* __restrict__ bp = beta_s + ks;
       const int32_t rlen = ke - ks;
@@ -460,46 +482,92 @@ k_rows_tile(const TileArgs T) {
           }
         }
       }
-      // a group member inside this run is at alpha distance <= 2: the scan has it
-      while (nextj < ke) {
-        ++bpos;
-        nextj = bpos < bend ? int32_t(A.bgrp_mem[bpos]) : NONE;
-      }
     }
-    flush_group(NONE);
   }
-  if (lane == 0) T.unit_nent[u] = nent;
+  if (lane == 0) { T.unit_nent[u] = nent; T.unit_nent_c[u] = nent_c; }
   if (valid && A.row_cnt) A.row_cnt[row] = cnt;
+  if (valid && T.row_cnt_c) T.row_cnt_c[row] = cnt_c;
 }
 
-// deal the entries of every unit to its rows: hits of row (unit, lane) = ket indices of the entries
-// whose mask has bit `lane`, in stream order, written to the row's slot range of `hits`
+// deal the entries of every unit to its rows: hits of row (unit, lane) = ket indices of the entries whose mask has
+// bit `lane`, written to the row's slot range of `hits` in ascending order. The stream holds the class (c) entries
+// first: a lane parks its (c) hits at the END of its range and merges them in while it walks the scan entries --
+// in place, because the write position never passes the first unread parked element.
+// 32 x 32 bit transpose across a warp: in, lane l holds brev(row (31 - l)); out, lane l holds the word whose
+// bit k is bit l of row k (five butterfly steps, Hacker's Delight 7-3 in warp form)
+__device__ __forceinline__ unsigned warp_bit_transpose(unsigned x, int lane) {
+  unsigned m = 0x0000FFFFu;
+#pragma unroll
+  for (int j = 16; j; j >>= 1) {
+    const unsigned y = __shfl_xor_sync(0xffffffffu, x, j);
+    if (!(lane & j)) x ^= (x ^ (y >> j)) & m;
+    else x ^= ((y ^ (x >> j)) & m) << j;
+    m ^= m << (j >> 1);
+  }
+  return x;
+}
 __global__ void __launch_bounds__(TILE_WARPS * 32)
 k_tile_gather(const TileArgs T, const int64_t* __restrict__ slot_ptr, int32_t* __restrict__ hits) {
+  __shared__ int32_t jbuf[TILE_WARPS][32];
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   const int64_t u = int64_t(blockIdx.x) * TILE_WARPS + w;
   if (u >= T.nunits) return;
   const int32_t row0 = T.unit_row0[u], ulen = T.unit_len[u];
   const bool valid = lane < ulen;
   int32_t* __restrict__ out = hits + (valid ? slot_ptr[row0 + lane] : 0);
+  const int32_t n_tot = valid ? T.A.struct_cnt[row0 + lane] : 0;
+  const int32_t n_c = valid ? T.row_cnt_c[row0 + lane] : 0;
+  int32_t* __restrict__ park = out + (n_tot - n_c);
   int32_t remaining = T.unit_nent[u];
+  int32_t rem_c = T.unit_nent_c[u];
   int32_t c = remaining > 0 ? T.unit_head[u] : -1;
-  const unsigned mybit = 1u << lane;
+  int32_t o = 0, cp = 0, parked = 0;
+  int32_t cnext = INT32_MAX;  // next parked element (value), loaded when the (c) part is complete
+  bool c_loaded = false;
   while (remaining > 0 && c >= 0) {
     const int32_t nin = remaining < TILE_CH ? remaining : TILE_CH;
     const uint2* __restrict__ src = T.tile_ent + size_t(c) * TILE_CH;
-    for (int32_t b = 0; b < nin; b += 32) {
-      const uint2 e = b + lane < nin ? src[b + lane] : make_uint2(0u, 0u);
-      const int nb = nin - b < 32 ? nin - b : 32;
-      for (int k = 0; k < nb; ++k) {
-        const unsigned mk = __shfl_sync(0xffffffffu, e.x, k);
-        const unsigned jk = __shfl_sync(0xffffffffu, e.y, k);
-        if (mk & mybit) *out++ = int32_t(jk);
+    for (int32_t b = 0; b < nin;) {
+      int nb = nin - b < 32 ? nin - b : 32;
+      const bool cpart = rem_c > 0;        // warp-uniform: a block never straddles the (c) / scan boundary
+      if (cpart && rem_c < nb) nb = rem_c;
+      // lane l takes entry (31 - l) of the block: after the transpose lane l holds, bit k, "entry k is mine"
+      const int kk = 31 - lane;
+      const uint2 e = kk < nb ? src[b + kk] : make_uint2(0u, 0u);
+      __syncwarp();
+      jbuf[w][kk] = int32_t(e.y);
+      __syncwarp();
+      unsigned mine = warp_bit_transpose(__brev(e.x), lane);
+      if (cpart) {
+        while (mine) {
+          const int k = __ffs(mine) - 1;
+          mine &= mine - 1;
+          park[parked++] = jbuf[w][k];
+        }
+        rem_c -= nb;
+      } else {
+        if (!c_loaded) {  // first scan block: the parked list is complete (own writes, same thread)
+          c_loaded = true;
+          cnext = n_c > 0 ? park[0] : INT32_MAX;
+        }
+        while (mine) {
+          const int k = __ffs(mine) - 1;
+          mine &= mine - 1;
+          const int32_t jk = jbuf[w][k];
+          while (cnext < jk) {
+            out[o++] = cnext;
+            ++cp;
+            cnext = cp < n_c ? park[cp] : INT32_MAX;
+          }
+          out[o++] = jk;
+        }
       }
+      b += nb;
     }
     remaining -= nin;
     c = T.tile_next[c];
   }
+  // parked elements left over are already where they belong (o == n_tot - n_c + cp)
 }
 
 __global__ void k_unit_flags(int64_t nrows, int64_t row_begin, const int32_t* __restrict__ run_ix,
@@ -2039,7 +2107,7 @@ void run_row_scan(b2ci_ctx* ctx, RowArgs A, int64_t nrows, int64_t nket, double 
   DevBuf<unsigned int> cursors(2);  // [0] warp-per-row chunks, [1] tile chunks
   unsigned int hit_capacity = 0, hit_used = 0;
   // tiled scan (units of >= tile_min rows of one alpha run)
-  DevBuf<int32_t> unit_row0, unit_len, unit_head, unit_nent, scan_rows, tile_next;
+  DevBuf<int32_t> unit_row0, unit_len, unit_head, unit_nent, unit_nent_c, row_cnt_c, scan_rows, tile_next;
   DevBuf<uint2> tile_ent;
   unsigned int tile_capacity = 0, tile_used = 0;
   int32_t ntile = 0;
@@ -2140,6 +2208,7 @@ void run_row_scan(b2ci_ctx* ctx, RowArgs A, int64_t nrows, int64_t nket, double 
           tile_ent.alloc(size_t(tile_capacity) * TILE_CH);
           tile_next.alloc(tile_capacity);
           unit_row0.alloc(ntile); unit_len.alloc(ntile); unit_head.alloc(ntile); unit_nent.alloc(ntile);
+          unit_nent_c.alloc(ntile); row_cnt_c.alloc(nrows);
         }
         if (want_tile) {
           scan_rows.alloc(nscan > 0 ? nscan : 1);
@@ -2160,6 +2229,7 @@ void run_row_scan(b2ci_ctx* ctx, RowArgs A, int64_t nrows, int64_t nket, double 
       TA.beta_s = w32 ? static_cast<const void*>(beta32.p) : static_cast<const void*>(A.beta);
       TA.unit_row0 = unit_row0; TA.unit_len = unit_len; TA.nunits = ntile;
       TA.tile_ent = tile_ent; TA.tile_next = tile_next; TA.unit_head = unit_head; TA.unit_nent = unit_nent;
+      TA.unit_nent_c = unit_nent_c; TA.row_cnt_c = row_cnt_c;
       TA.cursor = cursors.p + 1;
       TA.capacity = tile_capacity;
       const unsigned gt = unsigned((ntile + TILE_WARPS - 1) / TILE_WARPS);
@@ -2209,6 +2279,7 @@ void run_row_scan(b2ci_ctx* ctx, RowArgs A, int64_t nrows, int64_t nket, double 
     ScopedTimer t(ctx, "h_build.count", true);
     PT.begin();
     if (ntile) {
+      TA.A.struct_cnt = row_cnt;
       k_tile_gather<<<unsigned((ntile + TILE_WARPS - 1) / TILE_WARPS), TILE_WARPS * 32, 0, st>>>(TA, slot_ptr, colind);
       ctx->launches++;
       B2_CHECK_LAUNCH();

@@ -13,8 +13,12 @@ from qdk_chemistry_b200 import algorithms as alg, data, workloads as W  # noqa: 
 
 name, nt = sys.argv[1], int(float(sys.argv[2]))
 kw = {}
+SAVE = None
 for a in sys.argv[3:]:
     k, v = a.split("=")
+    if k == "save":
+        SAVE = v
+        continue
     try:
         kw[k] = int(v)
     except ValueError:
@@ -37,6 +41,10 @@ t0 = time.perf_counter()
 try:
     E, w = c.run(ham, sp.nalpha, sp.nbeta)
     out = {"E": E, "ndets": w.size()}
+    if SAVE and rank == 0:  # determinant words (alpha, beta) and coefficients, for scripts/verify_scale.py
+        import numpy as np
+        np.savez(SAVE, words=w.determinant_words(), coeffs=np.asarray(w.get_coefficients()), E=E - sp.core_energy,
+                 workload=name)
 except Exception as e:  # report what failed and the statistics so far
     out = {"error": str(e)[:300]}
 out["wall_s"] = time.perf_counter() - t0
