@@ -348,6 +348,19 @@ struct TileArgs {
   unsigned int capacity;
 };
 
+// 32 x 32 bit transpose across a warp: in, lane l holds brev(row (31 - l)); out, lane l holds the word whose
+// bit k is bit l of row k (five butterfly steps, Hacker's Delight 7-3 in warp form)
+__device__ __forceinline__ unsigned warp_bit_transpose(unsigned x, int lane) {
+  unsigned m = 0x0000FFFFu;
+#pragma unroll
+  for (int j = 16; j; j >>= 1) {
+    const unsigned y = __shfl_xor_sync(0xffffffffu, x, j);
+    if (!(lane & j)) x ^= (x ^ (y >> j)) & m;
+    else x ^= ((y ^ (x >> j)) & m) << j;
+    m ^= m << (j >> 1);
+  }
+  return x;
+}
 template <typename S, bool BLK>
 __global__ void __launch_bounds__(TILE_WARPS * 32)
 k_rows_tile(const TileArgs T) {
@@ -382,12 +395,6 @@ k_rows_tile(const TileArgs T) {
     chunk = nc;
     pos = 0;
     ent = nc >= 0 ? T.tile_ent + size_t(nc) * TILE_CH : nullptr;
-  };
-  auto emit = [&](unsigned m, int32_t j) {  // one entry, warp-uniform
-    if (pos == TILE_CH) new_chunk();
-    if (lane == 0 && ent) ent[pos] = make_uint2(m, unsigned(j));
-    ++pos;
-    ++nent;
   };
   int32_t nent_c = 0;
   if (ai != 0 || A.pair_rule) {
@@ -450,6 +457,9 @@ k_rows_tile(const TileArgs T) {
         mine = base + 32 + lane < rlen ? bp[base + 32 + lane] : S(0);
         const int nst = rlen - base < 32 ? rlen - base : 32;
         const int32_t jb = ks + base;
+        // bit t of rowbits: string t of the step connects to this lane's row. The per-string work is XOR, POPC,
+        // compare and one predicated OR; votes, counts and stores are paid once per step of 32 strings.
+        unsigned rowbits = 0u;
         int q = 0;
         for (; q + 8 <= nst; q += 8) {
           S st[8];
@@ -465,21 +475,29 @@ k_rows_tile(const TileArgs T) {
               st[t] = S(v.x); st[t + 1] = S(v.y);
             }
           }
+          unsigned g = 0u;
 #pragma unroll
-          for (int t = 0; t < 8; ++t) {
-            const bool hit = popc_s<S>(bi ^ st[t]) <= lim;
-            if (__any_sync(0xffffffffu, hit)) {  // about every second string connects to some row of the unit
-              cnt += hit ? 1 : 0;
-              emit(__ballot_sync(0xffffffffu, hit), jb + q + t);
-            }
-          }
+          for (int t = 0; t < 8; ++t)
+            if (popc_s<S>(bi ^ st[t]) <= lim) g |= 1u << t;
+          rowbits |= g << q;
         }
-        for (int t = q; t < nst; ++t) {
-          const bool hit = popc_s<S>(bi ^ slab[w][t]) <= lim;
-          if (__any_sync(0xffffffffu, hit)) {
-            cnt += hit ? 1 : 0;
-            emit(__ballot_sync(0xffffffffu, hit), jb + t);
-          }
+        for (int t = q; t < nst; ++t)
+          if (popc_s<S>(bi ^ slab[w][t]) <= lim) rowbits |= 1u << t;
+        if (!__any_sync(0xffffffffu, rowbits != 0u)) continue;
+        cnt += __popc(rowbits);
+        // lane t <- the row mask of string t (bit l: row l connects), then the strings that connect to some row
+        // leave as one contiguous run of entries
+        const unsigned smask = warp_bit_transpose(__brev(__shfl_sync(0xffffffffu, rowbits, 31 - lane)), lane);
+        const unsigned nz = __ballot_sync(0xffffffffu, smask != 0u);
+        const int nh = __popc(nz), my = __popc(nz & lt);
+        int done = 0;
+        while (done < nh) {
+          if (pos == TILE_CH) new_chunk();
+          const int take = min(nh - done, TILE_CH - pos);
+          if (smask != 0u && my >= done && my < done + take && ent) ent[pos + my - done] = make_uint2(smask, unsigned(jb + lane));
+          pos += take;
+          nent += take;
+          done += take;
         }
       }
     }
@@ -493,19 +511,6 @@ k_rows_tile(const TileArgs T) {
 // bit `lane`, written to the row's slot range of `hits` in ascending order. The stream holds the class (c) entries
 // first: a lane parks its (c) hits at the END of its range and merges them in while it walks the scan entries --
 // in place, because the write position never passes the first unread parked element.
-// 32 x 32 bit transpose across a warp: in, lane l holds brev(row (31 - l)); out, lane l holds the word whose
-// bit k is bit l of row k (five butterfly steps, Hacker's Delight 7-3 in warp form)
-__device__ __forceinline__ unsigned warp_bit_transpose(unsigned x, int lane) {
-  unsigned m = 0x0000FFFFu;
-#pragma unroll
-  for (int j = 16; j; j >>= 1) {
-    const unsigned y = __shfl_xor_sync(0xffffffffu, x, j);
-    if (!(lane & j)) x ^= (x ^ (y >> j)) & m;
-    else x ^= ((y ^ (x >> j)) & m) << j;
-    m ^= m << (j >> 1);
-  }
-  return x;
-}
 __global__ void __launch_bounds__(TILE_WARPS * 32)
 k_tile_gather(const TileArgs T, const int64_t* __restrict__ slot_ptr, int32_t* __restrict__ hits) {
   __shared__ int32_t jbuf[TILE_WARPS][32];
@@ -672,6 +677,96 @@ k_rows_hits_flat(const RowArgs A) {
     cnt += __popc(km);
   }
   if (lane == 0 && A.row_cnt) A.row_cnt[row] = cnt;
+}
+
+// The same fill with the lanes of a warp kept on ONE excitation class at a time. A row's connections arrive in
+// column order, classes interleaved: evaluated 32 at a time as they come (k_rows_hits_flat) the warp walks every
+// branch of the Slater-Condon dispatch with a third of its lanes (ncu: 11 of 32 threads per instruction, 20 warp
+// instructions per matrix element). Here a batch is only CLASSIFIED (two POPCs); (position, column) pairs queue
+// per class in shared memory and a class is evaluated whenever 32 of its connections are waiting -- opposite-spin
+// doubles, same-spin doubles (spin picked by select) and singles (likewise) each as straight-line code. Values
+// land at their structural position; a dropped element is marked by colind = -1 and k_compact_rows_holes packs
+// the rows that the thresholded build packs anyway. Same functions, same operands: the same bits.
+template <int C, bool EVAL, bool BLK>
+__device__ __forceinline__ bool eval_queued(const RowArgs& A, const uint2 e, const bool act, const uint64_t ai,
+                                            const uint64_t bi, const int64_t i, const int64_t slot) {
+  if (!act) return false;
+  int32_t j = int32_t(e.y);
+  const uint64_t aj = A.alpha[j], bj = A.beta[j];
+  if (BLK && A.colmap) j = A.colmap[j];
+  const bool fwd = i <= int64_t(j);  // bra = the lower determinant index, as the reference's upper triangle
+  const uint64_t bra_a = fwd ? ai : aj, bra_b = fwd ? bi : bj, ket_a = fwd ? aj : ai, ket_b = fwd ? bj : bi;
+  const uint64_t ex_a = ai ^ aj, ex_b = bi ^ bj;
+  double v;
+  if (C == 0) {
+    v = me22(A.I, bra_a, ket_a, ex_a, bra_b, ket_b, ex_b);
+  } else if (C == 1) {
+    const bool sa = ex_a != 0;
+    v = me4(A.I, sa ? bra_a : bra_b, sa ? ket_a : ket_b, sa ? ex_a : ex_b);
+  } else {
+    const int ca = popc64(ex_a), cb = popc64(ex_b);
+    if (ca + cb == 2) {
+      const bool sa = ca == 2;
+      v = me2(A.I, sa ? bra_a : bra_b, sa ? ket_a : ket_b, sa ? ex_a : ex_b, sa ? bra_a : bra_b, sa ? bra_b : bra_a);
+    } else {
+      v = matel(A.I, bra_a, bra_b, ket_a, ket_b);  // the diagonal (once per row)
+    }
+  }
+  bool keep = true;
+  if (EVAL) keep = A.pair_rule ? (i == int64_t(j) || !(fabs(v) < A.thr)) : fabs(v) > A.thr;
+  const int64_t pos = slot + e.x;
+  A.nzval[pos] = v;
+  if (!keep) A.colind[pos] = -1;
+  else if (BLK && A.colmap) A.colind[pos] = j;
+  return !keep;
+}
+constexpr int BIN_WARPS = 8;
+template <bool EVAL, bool BLK>
+__global__ void __launch_bounds__(BIN_WARPS * 32)
+k_rows_hits_binned(const RowArgs A) {
+  __shared__ uint2 queue[BIN_WARPS][3][64];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int64_t row = int64_t(blockIdx.x) * BIN_WARPS + w;
+  if (row >= A.nrows) return;
+  const int64_t il = A.row_begin + row;
+  const uint64_t ai = BLK ? A.bra_alpha[il] : A.alpha[il], bi = BLK ? A.bra_beta[il] : A.beta[il];
+  const int64_t i = (BLK && A.rowmap) ? int64_t(A.rowmap[il]) : il;
+  const int32_t nhit = A.struct_cnt[row];
+  const int64_t slot = A.rowptr[row];
+  const unsigned lt = (1u << lane) - 1u;
+  int qn0 = 0, qn1 = 0, qn2 = 0;
+  int32_t ndrop = 0;
+  for (int32_t t0 = 0; t0 < nhit; t0 += 32) {
+    const int32_t t = t0 + lane;
+    int cls = 3;
+    int32_t j = 0;
+    if (t < nhit) {
+      j = A.colind[slot + t];
+      const int ca = popc64(ai ^ A.alpha[j]), cb = popc64(bi ^ A.beta[j]);
+      cls = (ca == 2 && cb == 2) ? 0 : ((ca + cb == 4) ? 1 : 2);
+    }
+    const unsigned m0 = __ballot_sync(0xffffffffu, cls == 0), m1 = __ballot_sync(0xffffffffu, cls == 1),
+                   m2 = __ballot_sync(0xffffffffu, cls == 2);
+    const uint2 e = make_uint2(unsigned(t), unsigned(j));
+    if (cls == 0) queue[w][0][qn0 + __popc(m0 & lt)] = e;
+    else if (cls == 1) queue[w][1][qn1 + __popc(m1 & lt)] = e;
+    else if (cls == 2) queue[w][2][qn2 + __popc(m2 & lt)] = e;
+    qn0 += __popc(m0); qn1 += __popc(m1); qn2 += __popc(m2);
+    __syncwarp();
+    // (a lane may evaluate one connection of every class in the same step: count, do not OR)
+    if (qn0 >= 32) { qn0 -= 32; ndrop += eval_queued<0, EVAL, BLK>(A, queue[w][0][qn0 + lane], true, ai, bi, i, slot); }
+    if (qn1 >= 32) { qn1 -= 32; ndrop += eval_queued<1, EVAL, BLK>(A, queue[w][1][qn1 + lane], true, ai, bi, i, slot); }
+    if (qn2 >= 32) { qn2 -= 32; ndrop += eval_queued<2, EVAL, BLK>(A, queue[w][2][qn2 + lane], true, ai, bi, i, slot); }
+    __syncwarp();
+  }
+  if (qn0 > 0) ndrop += eval_queued<0, EVAL, BLK>(A, queue[w][0][lane], lane < qn0, ai, bi, i, slot);
+  if (qn1 > 0) ndrop += eval_queued<1, EVAL, BLK>(A, queue[w][1][lane], lane < qn1, ai, bi, i, slot);
+  if (qn2 > 0) ndrop += eval_queued<2, EVAL, BLK>(A, queue[w][2][lane], lane < qn2, ai, bi, i, slot);
+  if (EVAL) {  // this lane's drops -> the row's
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) ndrop += __shfl_xor_sync(0xffffffffu, ndrop, d);
+  }
+  if (lane == 0 && A.row_cnt) A.row_cnt[row] = nhit - ndrop;
 }
 
 // beta groups: determinant indices sorted by beta string (stable), group boundaries
@@ -1766,6 +1861,36 @@ __global__ void k_count_small(const double* __restrict__ v, int64_t n, double th
   if ((threadIdx.x & 31) == 0 && m) atomicAdd(cnt, unsigned(__popc(m)));
 }
 
+// rows filled at their structural positions with the dropped elements marked (colind = -1): pack what is left
+__global__ void __launch_bounds__(ROW_WARPS * 32)
+k_compact_rows_holes(int64_t nrows, const int64_t* __restrict__ slot_ptr, const int64_t* __restrict__ rowptr,
+                     const int32_t* __restrict__ ci_in, const double* __restrict__ nz_in,
+                     int32_t* __restrict__ ci_out, double* __restrict__ nz_out) {
+  const int lane = threadIdx.x & 31;
+  const int64_t row = (int64_t(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+  if (row >= nrows) return;
+  const int64_t src = slot_ptr[row], len = slot_ptr[row + 1] - src;
+  int64_t dst = rowptr[row];
+  if (rowptr[row + 1] - dst == len) {  // nothing dropped in this row
+    for (int64_t t = lane; t < len; t += 32) {
+      ci_out[dst + t] = ci_in[src + t];
+      nz_out[dst + t] = nz_in[src + t];
+    }
+    return;
+  }
+  for (int64_t t0 = 0; t0 < len; t0 += 32) {
+    const int64_t t = t0 + lane;
+    const int32_t c = t < len ? ci_in[src + t] : -1;
+    const bool keep = c >= 0;
+    const unsigned m = __ballot_sync(0xffffffffu, keep);
+    if (keep) {
+      const int64_t pos = dst + __popc(m & ((1u << lane) - 1u));
+      ci_out[pos] = c;
+      nz_out[pos] = nz_in[src + t];
+    }
+    dst += __popc(m);
+  }
+}
 // move the surviving prefix of every structural row slot to its final position
 __global__ void __launch_bounds__(ROW_WARPS * 32)
 k_compact_rows(int64_t nrows, const int64_t* __restrict__ slot_ptr,
@@ -2259,6 +2384,8 @@ void run_row_scan(b2ci_ctx* ctx, RowArgs A, int64_t nrows, int64_t nket, double 
   const bool from_hits = (hit_capacity != 0 || tile_capacity != 0) && hit_used <= hit_capacity && tile_used <= tile_capacity &&
                          (nscan == 0 || hit_capacity != 0) && (ntile == 0 || tile_capacity != 0);
   ctx->timers["h_build.hit_lists"] = from_hits ? 1. : 0.;
+  // B2CI_HBUILD_FLAT_FILL=1: evaluate the connections in arrival order (the former fill; kept for comparison)
+  const bool binned = getenv("B2CI_HBUILD_FLAT_FILL") == nullptr || atoi(getenv("B2CI_HBUILD_FLAT_FILL")) == 0;
   ctx->timers["h_build.tile_units"] = double(ntile);
   ctx->timers["h_build.scan_rows"] = double(nscan);
   ctx->timers["h_build.tile_chunks"] = double(tile_used);
@@ -2309,7 +2436,11 @@ void run_row_scan(b2ci_ctx* ctx, RowArgs A, int64_t nrows, int64_t nket, double 
     A.row_list = nullptr;
     A.nrows = nrows;
     PT.begin();
-    if (from_hits) {
+    if (from_hits && binned) {
+      const unsigned gb = unsigned((nrows + BIN_WARPS - 1) / BIN_WARPS);
+      if (thr > 0.0) k_rows_hits_binned<true, BLK><<<gb, BIN_WARPS * 32, 0, st>>>(A);
+      else k_rows_hits_binned<false, BLK><<<gb, BIN_WARPS * 32, 0, st>>>(A);
+    } else if (from_hits) {
       if (thr > 0.0) k_rows_hits_flat<true, BLK><<<grid, ROW_WARPS * 32, 0, st>>>(A);
       else k_rows_hits_flat<false, BLK><<<grid, ROW_WARPS * 32, 0, st>>>(A);
     } else {
@@ -2333,8 +2464,11 @@ void run_row_scan(b2ci_ctx* ctx, RowArgs A, int64_t nrows, int64_t nket, double 
     if (nnz != nslots) {
       DevBuf<int32_t> ci_f(nnz > 0 ? nnz : 1);
       DevBuf<double> nz_f(nnz > 0 ? nnz : 1);
-      k_compact_rows<<<unsigned((nrows * 32 + ROW_WARPS * 32 - 1) / (ROW_WARPS * 32)), ROW_WARPS * 32, 0, st>>>(
-          nrows, slot_ptr, out.rowptr, colind, nzval, ci_f, nz_f);
+      const unsigned gc = unsigned((nrows * 32 + ROW_WARPS * 32 - 1) / (ROW_WARPS * 32));
+      if (from_hits && binned)
+        k_compact_rows_holes<<<gc, ROW_WARPS * 32, 0, st>>>(nrows, slot_ptr, out.rowptr, colind, nzval, ci_f, nz_f);
+      else
+        k_compact_rows<<<gc, ROW_WARPS * 32, 0, st>>>(nrows, slot_ptr, out.rowptr, colind, nzval, ci_f, nz_f);
       ctx->launches++;
       B2_CHECK_LAUNCH();
       B2_CUDA(cudaStreamSynchronize(st));
@@ -2369,6 +2503,7 @@ void hbuild_csr(b2ci_ctx* ctx, const b2ci_dets* dets, int64_t row_begin, int64_t
   cudaStream_t st = ctx->stream;
   ctx->timers["h_build.setup"] = ctx->timers["h_build.count"] = ctx->timers["h_build.fill"] = 0.;
   ctx->timers["h_build.thresh"] = 0.;
+  ctx->timers["h_build.fill_kernel"] = 0.;
 
   DevBuf<int32_t> run_of(n > 0 ? n : 1);
   DevBuf<int64_t> run_start, adj_ptr;
@@ -2756,8 +2891,11 @@ void hbuild_csr(b2ci_ctx* ctx, const b2ci_dets* dets, int64_t row_begin, int64_t
           B2_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
           kern<<<dgrid, DW * 32, dense_smem, st>>>(DA);
         };
-        if (thr > 0.0) dl(k_rows_dense<true>);
-        else dl(k_rows_dense<false>);
+        {
+          DeferredScope tk(DT, "h_build.fill_kernel");  // the dominant kernel alone (bench.py's roofline line)
+          if (thr > 0.0) dl(k_rows_dense<true>);
+          else dl(k_rows_dense<false>);
+        }
       } else if (thr > 0.0) {
         if (dense) launch_g(std::true_type{}, std::true_type{}, std::true_type{});
         else if (slices) launch_g(std::true_type{}, std::true_type{}, std::false_type{});

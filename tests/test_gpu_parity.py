@@ -480,7 +480,8 @@ def test_fci_list_under_pair_rules_takes_the_scan_path(ctx):
     assert rp[-1] >= srp[-1]
 
 
-@pytest.mark.parametrize("mode", ["hits", "overflow", "tile_overflow", "no_tile", "tile_all", "wide", "off"])
+@pytest.mark.parametrize("mode", ["hits", "overflow", "tile_overflow", "no_tile", "tile_all", "wide", "off",
+                                  "flat_fill"])
 def test_hit_list_fill_equals_rescan_fill(ctx, mode, monkeypatch):
     """General lists scan once: the count pass stores the connections it finds (the tiled scan for units of
     12+ rows of one alpha run, the warp-per-row scan for the rest) and the fill pass evaluates them from the
@@ -502,13 +503,15 @@ def test_hit_list_fill_equals_rescan_fill(ctx, mode, monkeypatch):
         monkeypatch.setenv("B2CI_HBUILD_WIDE_STRINGS", "1")
     if mode == "off":
         monkeypatch.setenv("B2CI_HBUILD_NO_HITLIST", "1")
+    if mode == "flat_fill":  # connections evaluated in arrival order instead of queued per excitation class
+        monkeypatch.setenv("B2CI_HBUILD_FLAT_FILL", "1")
     ctx.upload_integrals(sp.norb, sp.T, sp.V)
     h = port.Ham(sp.norb, sp.T, sp.V)
     d = ctx.upload_dets(port.pack(a, b), 1)
     for thr in (EPS, 0.0, 1e-2):
         H = ctx.hbuild(d, thr)
         assert ctx.timer_ms("h_build.hit_lists") == (0.0 if mode in ("overflow", "tile_overflow", "off") else 1.0)
-        if mode in ("hits", "wide"):
+        if mode in ("hits", "wide", "flat_fill"):
             assert ctx.timer_ms("h_build.tile_units") > 0 and ctx.timer_ms("h_build.scan_rows") > 0
         if mode == "tile_all":
             assert ctx.timer_ms("h_build.scan_rows") == 0
