@@ -145,6 +145,8 @@ struct RowArgs {
   const int64_t* bra_run_start = nullptr;  // BLK: first bra determinant of every bra run
   const int32_t* row_list = nullptr;       // optional: the launch's rows (the rest are taken by the tiled scan)
   const void* beta_s = nullptr;            // ket beta strings as 32-bit words (norb <= 32), else NULL
+  const void* alpha_s = nullptr;           // ket alpha strings likewise (the class-binned fill)
+  const double* diag = nullptr;            // the class-binned fill: diagonal element of every row (k_row_diag)
   const int32_t* struct_cnt = nullptr;  // gathers and k_rows_hits_flat: structural row lengths of the count pass
   int64_t row_stride = 1;               // sampling (estimate pass): row r of the launch is row r * row_stride
 };
@@ -679,6 +681,12 @@ k_rows_hits_flat(const RowArgs A) {
   if (lane == 0 && A.row_cnt) A.row_cnt[row] = cnt;
 }
 
+// ket string j as an S word: from the narrowed copy when there is one
+template <typename S>
+__device__ __forceinline__ S ket_string(const uint64_t* __restrict__ wide, const void* __restrict__ narrow, int32_t j) {
+  if (sizeof(S) == 4) return static_cast<const S*>(narrow)[j];
+  return S(wide[j]);
+}
 // The same fill with the lanes of a warp kept on ONE excitation class at a time. A row's connections arrive in
 // column order, classes interleaved: evaluated 32 at a time as they come (k_rows_hits_flat) the warp walks every
 // branch of the Slater-Condon dispatch with a third of its lanes (ncu: 11 of 32 threads per instruction, 20 warp
@@ -687,29 +695,31 @@ k_rows_hits_flat(const RowArgs A) {
 // doubles, same-spin doubles (spin picked by select) and singles (likewise) each as straight-line code. Values
 // land at their structural position; a dropped element is marked by colind = -1 and k_compact_rows_holes packs
 // the rows that the thresholded build packs anyway. Same functions, same operands: the same bits.
-template <int C, bool EVAL, bool BLK>
-__device__ __forceinline__ bool eval_queued(const RowArgs& A, const uint2 e, const bool act, const uint64_t ai,
-                                            const uint64_t bi, const int64_t i, const int64_t slot) {
-  if (!act) return false;
+template <int C, bool EVAL, bool BLK, typename S>
+__device__ __forceinline__ int eval_queued(const RowArgs& A, const uint2 e, const bool act, const S ai, const S bi,
+                                           const int64_t i, const int64_t row, const int64_t slot) {
+  if (!act) return 0;
   int32_t j = int32_t(e.y);
-  const uint64_t aj = A.alpha[j], bj = A.beta[j];
+  const S aj = ket_string<S>(A.alpha, A.alpha_s, j), bj = ket_string<S>(A.beta, A.beta_s, j);
   if (BLK && A.colmap) j = A.colmap[j];
   const bool fwd = i <= int64_t(j);  // bra = the lower determinant index, as the reference's upper triangle
-  const uint64_t bra_a = fwd ? ai : aj, bra_b = fwd ? bi : bj, ket_a = fwd ? aj : ai, ket_b = fwd ? bj : bi;
-  const uint64_t ex_a = ai ^ aj, ex_b = bi ^ bj;
+  const S bra_a = fwd ? ai : aj, bra_b = fwd ? bi : bj, ket_a = fwd ? aj : ai, ket_b = fwd ? bj : bi;
+  const S ex_a = ai ^ aj, ex_b = bi ^ bj;
   double v;
   if (C == 0) {
-    v = me22(A.I, bra_a, ket_a, ex_a, bra_b, ket_b, ex_b);
+    v = me22<S>(A.I, bra_a, ket_a, ex_a, bra_b, ket_b, ex_b);
   } else if (C == 1) {
     const bool sa = ex_a != 0;
-    v = me4(A.I, sa ? bra_a : bra_b, sa ? ket_a : ket_b, sa ? ex_a : ex_b);
+    v = me4<S>(A.I, sa ? bra_a : bra_b, sa ? ket_a : ket_b, sa ? ex_a : ex_b);
   } else {
-    const int ca = popc64(ex_a), cb = popc64(ex_b);
+    const int ca = popc_w<S>(ex_a), cb = popc_w<S>(ex_b);
     if (ca + cb == 2) {
       const bool sa = ca == 2;
-      v = me2(A.I, sa ? bra_a : bra_b, sa ? ket_a : ket_b, sa ? ex_a : ex_b, sa ? bra_a : bra_b, sa ? bra_b : bra_a);
+      v = me2<S>(A.I, sa ? bra_a : bra_b, sa ? ket_a : ket_b, sa ? ex_a : ex_b, sa ? bra_a : bra_b, sa ? bra_b : bra_a);
+    } else if (ca + cb == 0 && A.diag) {
+      v = A.diag[row];  // k_row_diag: one thread per row instead of one lane of this warp
     } else {
-      v = matel(A.I, bra_a, bra_b, ket_a, ket_b);  // the diagonal (once per row)
+      v = matel(A.I, uint64_t(bra_a), uint64_t(bra_b), uint64_t(ket_a), uint64_t(ket_b));
     }
   }
   bool keep = true;
@@ -718,10 +728,19 @@ __device__ __forceinline__ bool eval_queued(const RowArgs& A, const uint2 e, con
   A.nzval[pos] = v;
   if (!keep) A.colind[pos] = -1;
   else if (BLK && A.colmap) A.colind[pos] = j;
-  return !keep;
+  return keep ? 0 : 1;
+}
+// diagonal elements of the launch's rows, one thread per row (the double loops over the occupied orbitals are
+// ~3,000 dependent instructions: inside the fill they ran on one lane of the row's warp and were a fifth of it)
+template <bool BLK>
+__global__ void k_row_diag(const RowArgs A, double* __restrict__ diag) {
+  const int64_t row = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (row >= A.nrows) return;
+  const int64_t il = A.row_begin + row;
+  diag[row] = me_diag(A.I, BLK ? A.bra_alpha[il] : A.alpha[il], BLK ? A.bra_beta[il] : A.beta[il]);
 }
 constexpr int BIN_WARPS = 8;
-template <bool EVAL, bool BLK>
+template <bool EVAL, bool BLK, typename S>
 __global__ void __launch_bounds__(BIN_WARPS * 32)
 k_rows_hits_binned(const RowArgs A) {
   __shared__ uint2 queue[BIN_WARPS][3][64];
@@ -729,7 +748,7 @@ k_rows_hits_binned(const RowArgs A) {
   const int64_t row = int64_t(blockIdx.x) * BIN_WARPS + w;
   if (row >= A.nrows) return;
   const int64_t il = A.row_begin + row;
-  const uint64_t ai = BLK ? A.bra_alpha[il] : A.alpha[il], bi = BLK ? A.bra_beta[il] : A.beta[il];
+  const S ai = S(BLK ? A.bra_alpha[il] : A.alpha[il]), bi = S(BLK ? A.bra_beta[il] : A.beta[il]);
   const int64_t i = (BLK && A.rowmap) ? int64_t(A.rowmap[il]) : il;
   const int32_t nhit = A.struct_cnt[row];
   const int64_t slot = A.rowptr[row];
@@ -742,7 +761,7 @@ k_rows_hits_binned(const RowArgs A) {
     int32_t j = 0;
     if (t < nhit) {
       j = A.colind[slot + t];
-      const int ca = popc64(ai ^ A.alpha[j]), cb = popc64(bi ^ A.beta[j]);
+      const int ca = popc_w<S>(ai ^ ket_string<S>(A.alpha, A.alpha_s, j)), cb = popc_w<S>(bi ^ ket_string<S>(A.beta, A.beta_s, j));
       cls = (ca == 2 && cb == 2) ? 0 : ((ca + cb == 4) ? 1 : 2);
     }
     const unsigned m0 = __ballot_sync(0xffffffffu, cls == 0), m1 = __ballot_sync(0xffffffffu, cls == 1),
@@ -754,14 +773,14 @@ k_rows_hits_binned(const RowArgs A) {
     qn0 += __popc(m0); qn1 += __popc(m1); qn2 += __popc(m2);
     __syncwarp();
     // (a lane may evaluate one connection of every class in the same step: count, do not OR)
-    if (qn0 >= 32) { qn0 -= 32; ndrop += eval_queued<0, EVAL, BLK>(A, queue[w][0][qn0 + lane], true, ai, bi, i, slot); }
-    if (qn1 >= 32) { qn1 -= 32; ndrop += eval_queued<1, EVAL, BLK>(A, queue[w][1][qn1 + lane], true, ai, bi, i, slot); }
-    if (qn2 >= 32) { qn2 -= 32; ndrop += eval_queued<2, EVAL, BLK>(A, queue[w][2][qn2 + lane], true, ai, bi, i, slot); }
+    if (qn0 >= 32) { qn0 -= 32; ndrop += eval_queued<0, EVAL, BLK, S>(A, queue[w][0][qn0 + lane], true, ai, bi, i, row, slot); }
+    if (qn1 >= 32) { qn1 -= 32; ndrop += eval_queued<1, EVAL, BLK, S>(A, queue[w][1][qn1 + lane], true, ai, bi, i, row, slot); }
+    if (qn2 >= 32) { qn2 -= 32; ndrop += eval_queued<2, EVAL, BLK, S>(A, queue[w][2][qn2 + lane], true, ai, bi, i, row, slot); }
     __syncwarp();
   }
-  if (qn0 > 0) ndrop += eval_queued<0, EVAL, BLK>(A, queue[w][0][lane], lane < qn0, ai, bi, i, slot);
-  if (qn1 > 0) ndrop += eval_queued<1, EVAL, BLK>(A, queue[w][1][lane], lane < qn1, ai, bi, i, slot);
-  if (qn2 > 0) ndrop += eval_queued<2, EVAL, BLK>(A, queue[w][2][lane], lane < qn2, ai, bi, i, slot);
+  if (qn0 > 0) ndrop += eval_queued<0, EVAL, BLK, S>(A, queue[w][0][lane], lane < qn0, ai, bi, i, row, slot);
+  if (qn1 > 0) ndrop += eval_queued<1, EVAL, BLK, S>(A, queue[w][1][lane], lane < qn1, ai, bi, i, row, slot);
+  if (qn2 > 0) ndrop += eval_queued<2, EVAL, BLK, S>(A, queue[w][2][lane], lane < qn2, ai, bi, i, row, slot);
   if (EVAL) {  // this lane's drops -> the row's
 #pragma unroll
     for (int d = 16; d > 0; d >>= 1) ndrop += __shfl_xor_sync(0xffffffffu, ndrop, d);
@@ -2238,7 +2257,7 @@ void run_row_scan(b2ci_ctx* ctx, RowArgs A, int64_t nrows, int64_t nket, double 
   int32_t ntile = 0;
   int64_t nscan = nrows;
   // norb <= 32: beta strings as 32-bit words
-  DevBuf<uint32_t> beta32;
+  DevBuf<uint32_t> beta32, alpha32;
   const bool w32 = ctx->norb <= 32 && !getenv("B2CI_HBUILD_WIDE_STRINGS");  // (test hook: 64-bit strings)
   auto launch_scan_count = [&](const RowArgs& R, int64_t nr) {
     const unsigned g = unsigned((nr + ROW_WARPS - 1) / ROW_WARPS);
@@ -2256,6 +2275,11 @@ void run_row_scan(b2ci_ctx* ctx, RowArgs A, int64_t nrows, int64_t nket, double 
       ctx->launches++;
       B2_CHECK_LAUNCH();
       A.beta_s = beta32;
+      alpha32.alloc(nket);
+      k_narrow_u32<<<unsigned((nket + 255) / 256), 256, 0, st>>>(A.alpha, nket, alpha32);
+      ctx->launches++;
+      B2_CHECK_LAUNCH();
+      A.alpha_s = alpha32;
     }
     // (test hooks: B2CI_HBUILD_HITLIST_MIN = smallest list that keeps the connections of its count pass,
     // B2CI_HBUILD_HITLIST_CAP / B2CI_HBUILD_TILE_CAP = capacities in chunks, to exercise the overflow fallback,
@@ -2427,6 +2451,7 @@ void run_row_scan(b2ci_ctx* ctx, RowArgs A, int64_t nrows, int64_t nket, double 
   } else {
     nzval.alloc(nslots > 0 ? nslots : 1);
   }
+  DevBuf<double> row_diag;
   {
     ScopedTimer t(ctx, "h_build.fill", true);
     A.row_cnt = kept;
@@ -2437,9 +2462,18 @@ void run_row_scan(b2ci_ctx* ctx, RowArgs A, int64_t nrows, int64_t nket, double 
     A.nrows = nrows;
     PT.begin();
     if (from_hits && binned) {
+      row_diag.alloc(nrows > 0 ? nrows : 1);
+      k_row_diag<BLK><<<unsigned((nrows + 127) / 128), 128, 0, st>>>(A, row_diag);
+      A.diag = row_diag;
+      ctx->launches++;
       const unsigned gb = unsigned((nrows + BIN_WARPS - 1) / BIN_WARPS);
-      if (thr > 0.0) k_rows_hits_binned<true, BLK><<<gb, BIN_WARPS * 32, 0, st>>>(A);
-      else k_rows_hits_binned<false, BLK><<<gb, BIN_WARPS * 32, 0, st>>>(A);
+      if (w32) {
+        if (thr > 0.0) k_rows_hits_binned<true, BLK, uint32_t><<<gb, BIN_WARPS * 32, 0, st>>>(A);
+        else k_rows_hits_binned<false, BLK, uint32_t><<<gb, BIN_WARPS * 32, 0, st>>>(A);
+      } else {
+        if (thr > 0.0) k_rows_hits_binned<true, BLK, uint64_t><<<gb, BIN_WARPS * 32, 0, st>>>(A);
+        else k_rows_hits_binned<false, BLK, uint64_t><<<gb, BIN_WARPS * 32, 0, st>>>(A);
+      }
     } else if (from_hits) {
       if (thr > 0.0) k_rows_hits_flat<true, BLK><<<grid, ROW_WARPS * 32, 0, st>>>(A);
       else k_rows_hits_flat<false, BLK><<<grid, ROW_WARPS * 32, 0, st>>>(A);

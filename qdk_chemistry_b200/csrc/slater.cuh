@@ -39,63 +39,80 @@ B2_HD double ldg(const double* p) {
 }
 B2_HD uint64_t low_mask(int k) { return k >= 64 ? ~uint64_t(0) : ((uint64_t(1) << k) - 1); }
 
+// The excitation arithmetic below is templated on the string word: 32-bit words when norb <= 32 (half the
+// integer work of the general-list fill), 64-bit otherwise. The floating-point part is the same either way.
+template <typename Wd> B2_HD int popc_w(Wd x) { return sizeof(Wd) == 4 ?
+#ifdef __CUDA_ARCH__
+  __popc(uint32_t(x))
+#else
+  __builtin_popcount(uint32_t(x))
+#endif
+  : popc64(uint64_t(x)); }
+template <typename Wd> B2_HD int lsb_w(Wd x) { return sizeof(Wd) == 4 ?
+#ifdef __CUDA_ARCH__
+  __ffs(int(uint32_t(x))) - 1
+#else
+  __builtin_ctz(uint32_t(x))
+#endif
+  : lsb64(uint64_t(x)); }
+template <typename Wd> B2_HD Wd low_mask_w(int k) {
+  return k >= int(sizeof(Wd) * 8) ? Wd(~Wd(0)) : Wd((Wd(1) << k) - 1);
+}
+
 // (-1)^(number of occupied orbitals strictly between p and q)
-B2_HD double sx_sign(uint64_t state, unsigned p, unsigned q) {
+template <typename Wd> B2_HD double sx_sign(Wd state, unsigned p, unsigned q) {
   const unsigned lo = p < q ? p : q, hi = p < q ? q : p;
-  const uint64_t mask = state & (low_mask(hi) ^ low_mask(lo + 1));
-  return (popc64(mask) & 1) ? -1. : 1.;
+  const Wd mask = state & (low_mask_w<Wd>(hi) ^ low_mask_w<Wd>(lo + 1));
+  return (popc_w<Wd>(mask) & 1) ? -1. : 1.;
 }
-B2_HD void sx_sign_indices(uint64_t bra, uint64_t ket, uint64_t ex, unsigned& o1, unsigned& v1,
-                           double& sign) {
-  o1 = lsb64(ket & ex);
-  v1 = lsb64(bra & ex);
-  sign = sx_sign(ket, v1, o1);
+template <typename Wd> B2_HD void sx_sign_indices(Wd bra, Wd ket, Wd ex, unsigned& o1, unsigned& v1, double& sign) {
+  o1 = lsb_w<Wd>(ket & ex);
+  v1 = lsb_w<Wd>(bra & ex);
+  sign = sx_sign<Wd>(ket, v1, o1);
 }
-B2_HD void dx_sign_indices(uint64_t bra, uint64_t ket, uint64_t ex, unsigned& o1, unsigned& v1,
-                           unsigned& o2, unsigned& v2, double& sign) {
+template <typename Wd> B2_HD void dx_sign_indices(Wd bra, Wd ket, Wd ex, unsigned& o1, unsigned& v1,
+                                                  unsigned& o2, unsigned& v2, double& sign) {
   double s1, s2;
-  sx_sign_indices(bra, ket, ex, o1, v1, s1);
-  const uint64_t flip = (uint64_t(1) << o1) | (uint64_t(1) << v1);
+  sx_sign_indices<Wd>(bra, ket, ex, o1, v1, s1);
+  const Wd flip = Wd(Wd(1) << o1) | Wd(Wd(1) << v1);
   ket ^= flip;
   ex ^= flip;
-  sx_sign_indices(bra, ket, ex, o2, v2, s2);
+  sx_sign_indices<Wd>(bra, ket, ex, o2, v2, s2);
   sign = s1 * s2;
 }
 
 // same-spin double: sign * (V(v1,o1,v2,o2) - V(v1,o2,v2,o1))
-B2_HD double me4(const IntsView& I, uint64_t bra, uint64_t ket, uint64_t ex) {
+template <typename Wd> B2_HD double me4(const IntsView& I, Wd bra, Wd ket, Wd ex) {
   unsigned o1, v1, o2, v2;
   double sign;
-  dx_sign_indices(bra, ket, ex, o1, v1, o2, v2, sign);
+  dx_sign_indices<Wd>(bra, ket, ex, o1, v1, o2, v2, sign);
   const size_t n = I.n, n2 = n * n, n3 = n2 * n;
   const double g = ldg(I.V + v1 + o1 * n + v2 * n2 + o2 * n3) -
                    ldg(I.V + v1 + o2 * n + v2 * n2 + o1 * n3);
   return sign * g;
 }
 // opposite-spin double: sign_a * sign_b * V(v1,o1,v2,o2)
-B2_HD double me22(const IntsView& I, uint64_t bra_a, uint64_t ket_a, uint64_t ex_a,
-                  uint64_t bra_b, uint64_t ket_b, uint64_t ex_b) {
+template <typename Wd> B2_HD double me22(const IntsView& I, Wd bra_a, Wd ket_a, Wd ex_a, Wd bra_b, Wd ket_b, Wd ex_b) {
   unsigned o1, v1, o2, v2;
   double sa, sb;
-  sx_sign_indices(bra_a, ket_a, ex_a, o1, v1, sa);
-  sx_sign_indices(bra_b, ket_b, ex_b, o2, v2, sb);
+  sx_sign_indices<Wd>(bra_a, ket_a, ex_a, o1, v1, sa);
+  sx_sign_indices<Wd>(bra_b, ket_b, ex_b, o2, v2, sb);
   const size_t n = I.n, n2 = n * n, n3 = n2 * n;
   const double sign = sa * sb;
   return sign * ldg(I.V + v1 + o1 * n + v2 * n2 + o2 * n3);
 }
 // single: sign * (T(v,o) + sum_{p in occ_same, ascending} G_red(p,v,o)
 //                          + sum_{p in occ_other, ascending} V_red(p,v,o))
-B2_HD double me2(const IntsView& I, uint64_t bra, uint64_t ket, uint64_t ex, uint64_t occ_same,
-                 uint64_t occ_othr) {
+template <typename Wd> B2_HD double me2(const IntsView& I, Wd bra, Wd ket, Wd ex, Wd occ_same, Wd occ_othr) {
   unsigned o1, v1;
   double sign;
-  sx_sign_indices(bra, ket, ex, o1, v1, sign);
+  sx_sign_indices<Wd>(bra, ket, ex, o1, v1, sign);
   const size_t n = I.n, n2 = n * n;
   double h_el = ldg(I.T + v1 + o1 * n);
   const double* G = I.G + v1 * n + o1 * n2;
-  for (uint64_t s = occ_same; s; s &= s - 1) h_el += ldg(G + lsb64(s));
+  for (Wd s = occ_same; s; s &= Wd(s - 1)) h_el += ldg(G + lsb_w<Wd>(s));
   const double* Vr = I.Vr + v1 * n + o1 * n2;
-  for (uint64_t s = occ_othr; s; s &= s - 1) h_el += ldg(Vr + lsb64(s));
+  for (Wd s = occ_othr; s; s &= Wd(s - 1)) h_el += ldg(Vr + lsb_w<Wd>(s));
   return sign * h_el;
 }
 B2_HD double me_diag(const IntsView& I, uint64_t occ_a, uint64_t occ_b) {
