@@ -659,6 +659,7 @@ int asci_search(b2ci_ctx* ctx, const b2ci_asci_search_opts* o, const uint64_t* c
         B2_CUDA(cudaStreamSynchronize(st));
       }
     }
+    mark("prune + keep candidates");
   }
 
   if (pt2_out) {
@@ -794,6 +795,7 @@ int asci_search(b2ci_ctx* ctx, const b2ci_asci_search_opts* o, const uint64_t* c
     }
     B2_CUDA(cudaStreamSynchronize(st));
   }
+  mark("top-k");
   if (stats) {
     stats[0] = double(M_sum); stats[1] = double(nseg_sum); stats[2] = kth; stats[3] = below; stats[4] = double(nkeep);
     stats[5] = double(nparts);
@@ -839,11 +841,13 @@ int asci_search(b2ci_ctx* ctx, const b2ci_asci_search_opts* o, const uint64_t* c
       B2_CUDA(cudaMemcpyAsync(h2.data(), k1alt, size_t(total) * 8, cudaMemcpyDeviceToHost, st));
     }
     B2_CUDA(cudaStreamSynchronize(st));
+    mark("output sort + download");
     if (two)
       for (int64_t i = 0; i < total; ++i) { out_words[2 * i] = h1[i]; out_words[2 * i + 1] = h2[i]; }
     else if (wpd == 1) memcpy(out_words, h1.data(), size_t(total) * 8);
     else
       for (int64_t i = 0; i < total; ++i) { out_words[2 * i] = h1[i] & 0xFFFFFFFFull; out_words[2 * i + 1] = h1[i] >> 32; }
+    mark("words to caller");
     return 0;
   }
   if (nkeep) {
