@@ -325,68 +325,116 @@ __device__ __forceinline__ bool last_cta_done(unsigned int* counter, unsigned in
   return is_last;
 }
 // partial[b*k + j] = sum over the rows of CTA b of A[i + j*ld] * w[i]
+// Thread t of CTA b owns rows b*256 + t + s*stride (s = 0, 1, ...) and adds their products in that order: the
+// summation order (and with it every bit of the Rayleigh-Ritz matrix) is fixed by that ownership. What moved is how
+// the operands arrive: one thread issues bulk (TMA) copies of the step's 2 KiB column pieces and of w into a ring
+// of DOT_STAGES shared-memory stages, signalled on mbarriers, so a CTA keeps 4 x 18 KiB in flight instead of the
+// nine 8-byte loads a thread can hold in registers (ncu: 3.0 TB/s, warps waiting on their own loads).
+constexpr int DOT_STAGES = 4;
+constexpr int DOT_STAGE_DOUBLES = (DOT_CG + 1) * DOT_THREADS;  // DOT_CG column pieces + the piece of w
+constexpr size_t DOT_SMEM_BYTES = size_t(DOT_STAGES) * DOT_STAGE_DOUBLES * 8;
 __global__ void __launch_bounds__(DOT_THREADS)
 k_multi_dot(int64_t N, int k, const double* __restrict__ A, int64_t ld,
             const double* __restrict__ w, double* __restrict__ partial, unsigned int* __restrict__ counter,
             double* __restrict__ out) {
+  extern __shared__ __align__(128) double dot_smem[];
   __shared__ double red[DOT_CG][DOT_THREADS / 32];
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int64_t stride = int64_t(gridDim.x) * DOT_THREADS;
-  // column groups are spread over blockIdx.y so that all of them stream concurrently
-  for (int j0 = blockIdx.y * DOT_CG; j0 < k; j0 += gridDim.y * DOT_CG) {
-    double acc[DOT_CG];
+  __shared__ __align__(8) uint64_t full[DOT_STAGES];
+  const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+  const int64_t stride = int64_t(gridDim.x) * DOT_THREADS, row_base = int64_t(blockIdx.x) * DOT_THREADS;
+  const int niter = row_base < N ? int((N - row_base + stride - 1) / stride) : 0;
+  // the columns are split into gridDim.y contiguous ranges, walked DOT_CG columns at a time (a column's sum never
+  // depends on the grouping)
+  const int per_y = (k + int(gridDim.y) - 1) / int(gridDim.y);
+  const int jbeg = int(blockIdx.y) * per_y, jend = min(k, jbeg + per_y);
+  const int nchunks = jend > jbeg ? (jend - jbeg + DOT_CG - 1) / DOT_CG : 0;
+  const int total = nchunks * niter;
+  if (t == 0) {
+    for (int s = 0; s < DOT_STAGES; ++s) mbar_init(&full[s], 1);
+  }
+  __syncthreads();
+  auto issue = [&](int q) {  // thread 0: the copies of step q = (chunk, row step)
+    const int chunk = q / niter, s = q - chunk * niter;
+    const int j0 = jbeg + chunk * DOT_CG, nc = min(DOT_CG, jend - j0);
+    const int64_t r0 = row_base + int64_t(s) * stride;
+    const int64_t left = N - r0;
+    const int nr = left < DOT_THREADS ? int(left) : DOT_THREADS;
+    const uint32_t bytes = uint32_t((nr + 1) & ~1) * 8u;  // 16-byte granules; an odd tail reads the column's padding
+    const int stage = q % DOT_STAGES;
+    double* buf = dot_smem + size_t(stage) * DOT_STAGE_DOUBLES;
+    mbar_arrive_expect_tx(&full[stage], bytes * uint32_t(nc + 1));
+    bulk_g2s(buf + DOT_CG * DOT_THREADS, w + r0, bytes, &full[stage]);
+    for (int c = 0; c < nc; ++c) bulk_g2s(buf + c * DOT_THREADS, A + r0 + int64_t(j0 + c) * ld, bytes, &full[stage]);
+  };
+  if (t == 0)
+    for (int q = 0; q < min(DOT_STAGES, total); ++q) issue(q);
+  double acc[DOT_CG];
 #pragma unroll
-    for (int c = 0; c < DOT_CG; ++c) acc[c] = 0.;
-    const int nc = min(DOT_CG, k - j0);
-    for (int64_t i = int64_t(blockIdx.x) * DOT_THREADS + threadIdx.x; i < N; i += stride) {
-      const double wi = w[i];
+  for (int c = 0; c < DOT_CG; ++c) acc[c] = 0.;
+  for (int q = 0; q < total; ++q) {
+    const int stage = q % DOT_STAGES;
+    mbar_wait(&full[stage], uint32_t(q / DOT_STAGES) & 1u);
+    const int chunk = q / niter, s = q - chunk * niter;
+    const int j0 = jbeg + chunk * DOT_CG, nc = min(DOT_CG, jend - j0);
+    const int64_t r0 = row_base + int64_t(s) * stride;
+    const double* buf = dot_smem + size_t(stage) * DOT_STAGE_DOUBLES;
+    if (r0 + t < N) {
+      const double wi = buf[DOT_CG * DOT_THREADS + t];
 #pragma unroll
       for (int c = 0; c < DOT_CG; ++c)
-        if (c < nc) acc[c] = fma(A[i + int64_t(j0 + c) * ld], wi, acc[c]);
+        if (c < nc) acc[c] = fma(buf[c * DOT_THREADS + t], wi, acc[c]);
     }
+    __syncthreads();  // the stage is read: refill it
+    if (t == 0 && q + DOT_STAGES < total) issue(q + DOT_STAGES);
+    if (s == niter - 1) {  // last row step of this chunk of columns: reduce over the CTA
 #pragma unroll
-    for (int c = 0; c < DOT_CG; ++c) {
-      double v = acc[c];
+      for (int c = 0; c < DOT_CG; ++c) {
+        double v = acc[c];
 #pragma unroll
-      for (int d = 16; d > 0; d >>= 1) v += __shfl_down_sync(0xffffffffu, v, d);
-      if (lane == 0) red[c][warp] = v;
+        for (int d = 16; d > 0; d >>= 1) v += __shfl_down_sync(0xffffffffu, v, d);
+        if (lane == 0) red[c][warp] = v;
+        acc[c] = 0.;
+      }
+      __syncthreads();
+      if (t < nc) {
+        double sum = 0.;
+#pragma unroll
+        for (int wv = 0; wv < DOT_THREADS / 32; ++wv) sum += red[t][wv];
+        partial[int64_t(blockIdx.x) * k + j0 + t] = sum;
+      }
+      __syncthreads();
     }
-    __syncthreads();
-    if (threadIdx.x < nc) {
-      double s = 0.;
-#pragma unroll
-      for (int wv = 0; wv < DOT_THREADS / 32; ++wv) s += red[threadIdx.x][wv];
-      partial[int64_t(blockIdx.x) * k + j0 + threadIdx.x] = s;
-    }
-    __syncthreads();
   }
+  if (niter == 0)  // (a CTA without rows still owns its partials)
+    for (int j = jbeg + t; j < jend; j += DOT_THREADS) partial[int64_t(blockIdx.x) * k + j] = 0.;
   if (counter && last_cta_done(counter, gridDim.x * gridDim.y)) {
     // sum over the CTAs in CTA order (the order of the former reduction kernel: same bits), with the partials of
     // 16 columns at a time staged in shared memory by all threads -- a single thread walking gridDim.x dependent
     // global loads per column was a 30 us tail on every dot product
     constexpr int JB = 16, MAXB = 320;
-    __shared__ double stage[JB * MAXB];
+    static_assert(size_t(JB) * MAXB * 8 <= DOT_SMEM_BYTES, "the staging area reuses the copy ring");
+    double* stage = dot_smem;
     const unsigned nb = gridDim.x;
     if (nb <= MAXB) {
       for (int j0 = 0; j0 < k; j0 += JB) {
         const int nj = min(JB, k - j0);
-        for (unsigned t = threadIdx.x; t < nb * nj; t += DOT_THREADS) {
-          const unsigned b = t / nj, jj = t - b * nj;
+        for (unsigned u = threadIdx.x; u < nb * nj; u += DOT_THREADS) {
+          const unsigned b = u / nj, jj = u - b * nj;
           stage[jj * MAXB + b] = partial[int64_t(b) * k + j0 + jj];
         }
         __syncthreads();
         if (int(threadIdx.x) < nj) {
-          double s = 0.;
-          for (unsigned b = 0; b < nb; ++b) s += stage[threadIdx.x * MAXB + b];
-          out[j0 + threadIdx.x] = s;
+          double sum = 0.;
+          for (unsigned b = 0; b < nb; ++b) sum += stage[threadIdx.x * MAXB + b];
+          out[j0 + threadIdx.x] = sum;
         }
         __syncthreads();
       }
     } else {
       for (int j = threadIdx.x; j < k; j += DOT_THREADS) {
-        double s = 0.;
-        for (unsigned b = 0; b < nb; ++b) s += partial[int64_t(b) * k + j];
-        out[j] = s;
+        double sum = 0.;
+        for (unsigned b = 0; b < nb; ++b) sum += partial[int64_t(b) * k + j];
+        out[j] = sum;
       }
     }
   }
@@ -400,7 +448,9 @@ __global__ void k_reduce_partials(int nblocks, int k, const double* __restrict__
   out[j] = s;
 }
 // w[i] -= sum_j V[i + j*ld] * h[j]
-// w -= V h; with nrm_partial: also ||w_new||^2 (per-CTA partials, summed by the last CTA into nrm_out[0])
+// w -= V h; with nrm_partial: also ||w_new||^2 (per-CTA partials, summed by the last CTA into nrm_out[0]).
+// Two consecutive rows per thread (16-byte loads; ld is a multiple of 16 doubles so every column is 128-byte
+// aligned); each row's sum runs over j in order, whatever the grid.
 __global__ void __launch_bounds__(256)
 k_project_out(int64_t N, int k, const double* __restrict__ V, int64_t ld,
               const double* __restrict__ h, double* __restrict__ w, double* __restrict__ nrm_partial,
@@ -409,14 +459,42 @@ k_project_out(int64_t N, int k, const double* __restrict__ V, int64_t ld,
   __shared__ double red[8];
   for (int j = threadIdx.x; j < k; j += blockDim.x) hs[j] = h[j];
   __syncthreads();
-  const int64_t stride = int64_t(gridDim.x) * blockDim.x;
+  const int64_t stride = int64_t(gridDim.x) * blockDim.x * 2;
   double nrm = 0.;
-  for (int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < N; i += stride) {
-    double s = 0.;
-    for (int j = 0; j < k; ++j) s = fma(V[i + int64_t(j) * ld], hs[j], s);
-    const double wi = w[i] - s;
-    w[i] = wi;
-    nrm = fma(wi, wi, nrm);
+  for (int64_t i = (int64_t(blockIdx.x) * blockDim.x + threadIdx.x) * 2; i < N; i += stride) {
+    if (i + 1 < N) {
+      double s0 = 0., s1 = 0.;
+      int j = 0;
+      for (; j + 8 <= k; j += 8) {  // eight columns in flight per thread
+        double2 v[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) v[u] = *reinterpret_cast<const double2*>(V + i + int64_t(j + u) * ld);
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          const double hj = hs[j + u];
+          s0 = fma(v[u].x, hj, s0);
+          s1 = fma(v[u].y, hj, s1);
+        }
+      }
+      for (; j < k; ++j) {
+        const double2 v = *reinterpret_cast<const double2*>(V + i + int64_t(j) * ld);
+        const double hj = hs[j];
+        s0 = fma(v.x, hj, s0);
+        s1 = fma(v.y, hj, s1);
+      }
+      double2 wi = *reinterpret_cast<const double2*>(w + i);
+      wi.x -= s0;
+      wi.y -= s1;
+      *reinterpret_cast<double2*>(w + i) = wi;
+      nrm = fma(wi.x, wi.x, nrm);
+      nrm = fma(wi.y, wi.y, nrm);
+    } else {
+      double s0 = 0.;
+      for (int j = 0; j < k; ++j) s0 = fma(V[i + int64_t(j) * ld], hs[j], s0);
+      const double wi = w[i] - s0;
+      w[i] = wi;
+      nrm = fma(wi, wi, nrm);
+    }
   }
   if (!nrm_partial) return;
 #pragma unroll
@@ -464,20 +542,41 @@ k_residual(int64_t N, int k, const double* __restrict__ V, const double* __restr
   __shared__ double red[8];
   for (int j = threadIdx.x; j < k; j += blockDim.x) cs[j] = c[j];
   __syncthreads();
-  const int64_t stride = int64_t(gridDim.x) * blockDim.x;
+  const int64_t stride = int64_t(gridDim.x) * blockDim.x * 2;
   double nrm = 0.;
-  for (int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < N; i += stride) {
-    double x = 0., ax = 0.;
-    for (int j = 0; j < k; ++j) {
-      x = fma(V[i + int64_t(j) * ld], cs[j], x);
-      ax = fma(AV[i + int64_t(j) * ld], cs[j], ax);
-    }
+  auto finish = [&](int64_t i, double x, double ax) {
     const double r = ax - lam * x;
     nrm = fma(r, r, nrm);
     double denom = D[i] - lam;
     if (fabs(denom) < 1e-12) denom = (denom >= 0) ? 1e-12 : -1e-12;
     X[i] = x;
     Wout[i] = -r / denom;
+  };
+  // two consecutive rows per thread (16-byte loads of the 128-byte aligned columns); per row the sums run over j
+  // in order, whatever the grid
+  for (int64_t i = (int64_t(blockIdx.x) * blockDim.x + threadIdx.x) * 2; i < N; i += stride) {
+    if (i + 1 < N) {
+      double x0 = 0., x1 = 0., a0 = 0., a1 = 0.;
+#pragma unroll 4
+      for (int j = 0; j < k; ++j) {
+        const double2 v = *reinterpret_cast<const double2*>(V + i + int64_t(j) * ld);
+        const double2 av = *reinterpret_cast<const double2*>(AV + i + int64_t(j) * ld);
+        const double cj = cs[j];
+        x0 = fma(v.x, cj, x0);
+        x1 = fma(v.y, cj, x1);
+        a0 = fma(av.x, cj, a0);
+        a1 = fma(av.y, cj, a1);
+      }
+      finish(i, x0, a0);
+      finish(i + 1, x1, a1);
+    } else {
+      double x = 0., ax = 0.;
+      for (int j = 0; j < k; ++j) {
+        x = fma(V[i + int64_t(j) * ld], cs[j], x);
+        ax = fma(AV[i + int64_t(j) * ld], cs[j], ax);
+      }
+      finish(i, x, ax);
+    }
   }
 #pragma unroll
   for (int d = 16; d > 0; d >>= 1) nrm += __shfl_down_sync(0xffffffffu, nrm, d);
@@ -522,6 +621,7 @@ struct Work {
   int64_t N, ld;
   int nblocks;   // CTAs of the reductions (one partial per CTA)
   int nstream;   // CTAs of the streaming updates
+  int npair;     // CTAs of the two-rows-per-thread kernels: every thread the same number of row pairs, one wave
   DevBuf<double> partial, small;  // small: k-sized device scratch
   DevBuf<double> scal;            // [0] ||r||^2 of the residual, [1] ||w||^2 after the second projection
   DevBuf<unsigned int> counter;   // ticket counter of the last-CTA reductions (re-armed by the kernels)
@@ -532,7 +632,12 @@ struct Work {
 void dots(Work& W, int k, const double* A, const double* w, double* host_out) {
   b2ci_ctx* ctx = W.ctx;
   const dim3 grid(W.nblocks, unsigned(std::min(8, (k + DOT_CG - 1) / DOT_CG)));
-  k_multi_dot<<<grid, DOT_THREADS, 0, ctx->stream>>>(W.N, k, A, W.ld, w, W.partial, W.counter, W.small);
+  static bool smem_set = false;
+  if (!smem_set) {
+    B2_CUDA(cudaFuncSetAttribute(k_multi_dot, cudaFuncAttributeMaxDynamicSharedMemorySize, int(DOT_SMEM_BYTES)));
+    smem_set = true;
+  }
+  k_multi_dot<<<grid, DOT_THREADS, DOT_SMEM_BYTES, ctx->stream>>>(W.N, k, A, W.ld, w, W.partial, W.counter, W.small);
   ctx->launches++;
   B2_CHECK_LAUNCH();
   if (ctx->nranks > 1) comm_allreduce_sum(ctx, W.small, k);
@@ -550,7 +655,7 @@ double norm2(Work& W, const double* w) {
 void project(Work& W, int k, const double* V, double* w, bool with_norm = false) {
   b2ci_ctx* ctx = W.ctx;
   dots(W, k, V, w, nullptr);  // h stays on the device (W.small)
-  k_project_out<<<W.nstream, 256, size_t(k) * 8, ctx->stream>>>(W.N, k, V, W.ld, W.small, w,
+  k_project_out<<<W.npair, 256, size_t(k) * 8, ctx->stream>>>(W.N, k, V, W.ld, W.small, w,
                                                                with_norm ? W.partial.p : nullptr, W.counter,
                                                                W.scal.p + 1);
   ctx->launches++;
@@ -698,10 +803,20 @@ int davidson(b2ci_ctx* ctx, const b2ci_csr* m, int64_t max_m, double tol, double
   Work W;
   W.ctx = ctx;
   W.N = Nloc;
-  W.ld = Nloc > 0 ? Nloc : 1;
+  W.ld = Nloc > 0 ? (Nloc + 15) / 16 * 16 : 16;  // columns start on 128-byte boundaries
+  {
+    // streaming kernels with two rows per thread: as many CTAs as stay resident together, then trimmed so that
+    // every thread walks the same number of row pairs (a last sweep that is 40 % full was 30 % of the time)
+    int per_sm = 0;
+    B2_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_residual, 256, size_t(max_m + 1) * 8));
+    const int64_t resident = int64_t(std::max(1, per_sm)) * ctx->sm_count;
+    const int64_t pairs = std::max<int64_t>(1, (Nloc + 1) / 2);
+    const int64_t sweeps = (pairs + resident * 256 - 1) / (resident * 256);
+    W.npair = int(std::max<int64_t>(1, (pairs + sweeps * 256 - 1) / (sweeps * 256)));
+  }
   W.nblocks = (int)std::max<int64_t>(1, std::min<int64_t>(int64_t(ctx->sm_count) * 2, (Nloc + 255) / 256));
   W.nstream = (int)std::max<int64_t>(1, std::min<int64_t>(int64_t(ctx->sm_count) * 16, (Nloc + 255) / 256));
-  W.partial.alloc(std::max(size_t(W.nblocks) * (max_m + 2), size_t(W.nstream)));
+  W.partial.alloc(std::max(size_t(W.nblocks) * (max_m + 2), size_t(std::max(W.nstream, W.npair))));
   W.small.alloc(max_m + 2);
   W.scal.alloc(2);
   W.counter.alloc(1);
@@ -762,7 +877,7 @@ int davidson(b2ci_ctx* ctx, const b2ci_csr* m, int64_t max_m, double tol, double
     double* R = V + (i + 1) * ld;
     {
       DeferredScope t(timers, "davidson.RES_DUR");
-      k_residual<<<W.nstream, 256, size_t(k) * 8, st>>>(Nloc, k, V, AV, ld, cdev, lam, D,
+      k_residual<<<W.npair, 256, size_t(k) * 8, st>>>(Nloc, k, V, AV, ld, cdev, lam, D,
                                                         xfull + row0, R, W.partial, W.counter, W.scal.p);
       ctx->launches++;
       B2_CHECK_LAUNCH();
