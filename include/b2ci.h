@@ -140,6 +140,14 @@ int b2ci_sigma_sharded(b2ci_ctx* ctx, const b2ci_csr* m, const double* x_local_d
  * it the first b2ci_sigma_sharded / b2ci_davidson call on the block exchanges the block sizes
  * (a host-synchronising all-gather). HOST pointer. */
 int b2ci_csr_set_row_partition(b2ci_ctx* ctx, b2ci_csr* m, const int64_t* row_offsets, int nranks);
+/* Row cuts for a row-sharded build of a selected-CI list: nparts contiguous blocks with about equal numbers of
+ * CONNECTIONS (estimated from the exact degree of nsamples evenly spaced determinants against the whole list), not
+ * of rows -- the head of a spin-sorted ASCI list holds the determinants with the most partners. The reference
+ * tiles rows evenly (sparsexx/matrix_types/dist_sparse_matrix.hpp:83-97, make_dist_csr_hamiltonian); any
+ * contiguous tiling is the same matrix. Deterministic: every rank computes the same cuts from the same list, no
+ * exchange. offsets: HOST, nparts + 1 entries, offsets[0] = 0, offsets[nparts] = n. */
+int b2ci_dets_balanced_partition(b2ci_ctx* ctx, const b2ci_dets* dets, int nparts, int64_t nsamples,
+                                 int64_t* offsets);
 /* extract_diagonal_elements (sparsexx/util/submatrix.hpp:354-383); host output, nrows */
 int b2ci_csr_diagonal(b2ci_ctx* ctx, const b2ci_csr* m, double* D);
 

@@ -73,6 +73,7 @@ def lib():
     L.b2ci_spmv_host.argtypes = [vp, vp, vp, vp]
     L.b2ci_sigma_sharded.argtypes = [vp, vp, vp, vp, vp]
     L.b2ci_csr_set_row_partition.argtypes = [vp, vp, vp, i32]
+    L.b2ci_dets_balanced_partition.argtypes = [vp, vp, i32, i64, vp]
     L.b2ci_csr_diagonal.argtypes = [vp, vp, vp]
     L.b2ci_davidson.argtypes = [vp, vp, i64, dbl, vp, i32, pi64, C.POINTER(dbl), vp]
     L.b2ci_dense_ground_state.argtypes = [vp, vp, C.POINTER(dbl), vp]

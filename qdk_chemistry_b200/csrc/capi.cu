@@ -93,6 +93,7 @@ void integrals_rotate(b2ci_ctx* ctx, const double* C, double* T_out, double* V_o
 void dets_from_words(b2ci_ctx* ctx, const uint64_t* words_host, int wpd, int64_t n, b2ci_dets* d);
 void dets_to_words(b2ci_ctx* ctx, const b2ci_dets* d, uint64_t* words_host, int wpd);
 void dets_generate_fci(b2ci_ctx* ctx, int norb, int na, int nb, b2ci_dets* d);
+void dets_balanced_partition(b2ci_ctx* ctx, const b2ci_dets* dets, int nparts, int64_t nsamples, int64_t* offsets);
 void hbuild_csr(b2ci_ctx* ctx, const b2ci_dets* dets, int64_t row_begin, int64_t row_end, double thr,
                 b2ci_csr* out);
 bool hbuild_csr_patched(b2ci_ctx* ctx, const b2ci_dets* od, const b2ci_csr* oH, const b2ci_dets* nd, double thr,
@@ -461,6 +462,14 @@ int b2ci_csr_set_row_partition(b2ci_ctx* ctx, b2ci_csr* m, const int64_t* row_of
       row_offsets[ctx->rank + 1] != m->row_begin + m->nrows)
     throw Error("b2ci_csr_set_row_partition: offsets do not match this rank's row block");
   m->row_offsets.assign(row_offsets, row_offsets + nranks + 1);
+  return 0;
+  B2_CATCH
+}
+int b2ci_dets_balanced_partition(b2ci_ctx* ctx, const b2ci_dets* dets, int nparts, int64_t nsamples,
+                                 int64_t* offsets) {
+  B2_TRY_CTX(ctx)
+  if (!dets) throw Error("b2ci_dets_balanced_partition: null determinant list");
+  dets_balanced_partition(ctx, dets, nparts, nsamples, offsets);
   return 0;
   B2_CATCH
 }

@@ -2499,6 +2499,105 @@ void run_row_scan(b2ci_ctx* ctx, RowArgs A, int64_t nrows, int64_t nket, double 
 }
 }  // namespace
 
+// ------------------------------------------------------------------ balanced row cuts
+// degree[s] = number of determinants of the list within four spin-orbital substitutions of sample s (itself
+// included): brute force, SAMPLES_PER_CTA bras against a slice of the kets per CTA, so that a ket is loaded
+// once for eight tests.
+namespace {
+constexpr int DEG_SPC = 8;     // samples per CTA
+constexpr int DEG_SLICES = 8;  // ket slices (grid.y)
+__global__ void __launch_bounds__(256)
+k_sample_degree(const uint64_t* __restrict__ alpha, const uint64_t* __restrict__ beta, int64_t n,
+                const int64_t* __restrict__ sample_row, int nsamples, unsigned long long* __restrict__ degree) {
+  __shared__ unsigned int tot[DEG_SPC];
+  const int s0 = blockIdx.x * DEG_SPC;
+  uint64_t sa[DEG_SPC], sb[DEG_SPC];
+  unsigned int cnt[DEG_SPC];
+#pragma unroll
+  for (int u = 0; u < DEG_SPC; ++u) {
+    const int s = min(s0 + u, nsamples - 1);
+    const int64_t r = sample_row[s];
+    sa[u] = alpha[r];
+    sb[u] = beta[r];
+    cnt[u] = 0u;
+  }
+  if (threadIdx.x < DEG_SPC) tot[threadIdx.x] = 0u;
+  __syncthreads();
+  const int64_t per = (n + gridDim.y - 1) / gridDim.y;
+  const int64_t j0 = int64_t(blockIdx.y) * per, j1 = min(n, j0 + per);
+  for (int64_t j = j0 + threadIdx.x; j < j1; j += blockDim.x) {
+    const uint64_t a = alpha[j], b = beta[j];
+#pragma unroll
+    for (int u = 0; u < DEG_SPC; ++u) cnt[u] += (__popcll(sa[u] ^ a) + __popcll(sb[u] ^ b) <= 4) ? 1u : 0u;
+  }
+#pragma unroll
+  for (int u = 0; u < DEG_SPC; ++u) {
+    unsigned int v = cnt[u];
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) v += __shfl_down_sync(0xffffffffu, v, d);
+    if ((threadIdx.x & 31) == 0) atomicAdd(&tot[u], v);
+  }
+  __syncthreads();
+  if (threadIdx.x < DEG_SPC && s0 + threadIdx.x < nsamples)
+    atomicAdd(&degree[s0 + threadIdx.x], (unsigned long long)tot[threadIdx.x]);
+}
+}  // namespace
+
+void dets_balanced_partition(b2ci_ctx* ctx, const b2ci_dets* dets, int nparts, int64_t nsamples, int64_t* offsets) {
+  const int64_t n = dets->n;
+  if (nparts < 1 || !offsets) throw Error("b2ci_dets_balanced_partition: bad arguments");
+  offsets[0] = 0;
+  offsets[nparts] = n;
+  const int64_t base = n / nparts, rem = n % nparts;
+  auto even = [&]() {
+    for (int r = 0; r < nparts; ++r) offsets[r + 1] = offsets[r] + base + (r < rem ? 1 : 0);
+  };
+  nsamples = std::min<int64_t>(std::max<int64_t>(nsamples, 1), 4096);
+  int64_t min_per_part = 1024;  // (test hook: B2CI_BALANCE_MIN = smallest mean block that is balanced)
+  if (const char* env = getenv("B2CI_BALANCE_MIN")) min_per_part = std::max<int64_t>(1, atoll(env));
+  nsamples = std::min(nsamples, std::max<int64_t>(1, n / 4));
+  if (nparts == 1 || n < int64_t(nparts) * min_per_part) { even(); return; }
+  cudaStream_t st = ctx->stream;
+  // segment s = rows [s n / ns, (s + 1) n / ns), sampled at its middle
+  std::vector<int64_t> seg(size_t(nsamples) + 1), rows(static_cast<size_t>(nsamples));
+  for (int64_t s = 0; s <= nsamples; ++s) seg[size_t(s)] = int64_t((__int128)s * n / nsamples);
+  for (int64_t s = 0; s < nsamples; ++s) rows[size_t(s)] = (seg[size_t(s)] + seg[size_t(s) + 1]) / 2;
+  DevBuf<int64_t> d_rows(nsamples);
+  DevBuf<unsigned long long> d_deg(nsamples);
+  B2_CUDA(cudaMemcpyAsync(d_rows, rows.data(), size_t(nsamples) * 8, cudaMemcpyHostToDevice, st));
+  B2_CUDA(cudaMemsetAsync(d_deg, 0, size_t(nsamples) * 8, st));
+  const dim3 grid(unsigned((nsamples + DEG_SPC - 1) / DEG_SPC), DEG_SLICES);
+  k_sample_degree<<<grid, 256, 0, st>>>(dets->alpha, dets->beta, n, d_rows, int(nsamples), d_deg);
+  ctx->launches++;
+  B2_CHECK_LAUNCH();
+  std::vector<unsigned long long> deg(static_cast<size_t>(nsamples));
+  B2_CUDA(cudaMemcpyAsync(deg.data(), d_deg, size_t(nsamples) * 8, cudaMemcpyDeviceToHost, st));
+  B2_CUDA(cudaStreamSynchronize(st));
+  // cost of a row = its connections + a quarter of the mean (the part of the scan that does not depend on hits);
+  // integer arithmetic throughout: every rank must arrive at the same cuts
+  unsigned __int128 sum = 0;
+  for (int64_t s = 0; s < nsamples; ++s) sum += (unsigned __int128)deg[size_t(s)] * (unsigned __int128)(seg[size_t(s) + 1] - seg[size_t(s)]);
+  const unsigned long long floor_cost = (unsigned long long)(sum / (unsigned __int128)n / 4) + 1;
+  std::vector<unsigned __int128> cum(size_t(nsamples) + 1, 0);
+  for (int64_t s = 0; s < nsamples; ++s)
+    cum[size_t(s) + 1] = cum[size_t(s)] + (unsigned __int128)(deg[size_t(s)] + floor_cost) * (unsigned __int128)(seg[size_t(s) + 1] - seg[size_t(s)]);
+  const unsigned __int128 total = cum[size_t(nsamples)];
+  int64_t s = 0;
+  for (int r = 1; r < nparts; ++r) {
+    const unsigned __int128 target = total * (unsigned)r / (unsigned)nparts;
+    while (s + 1 < nsamples && cum[size_t(s) + 1] <= target) ++s;
+    const unsigned __int128 per_row = deg[size_t(s)] + floor_cost;
+    int64_t cut = seg[size_t(s)] + int64_t((target - cum[size_t(s)]) / per_row);
+    cut = std::min(cut, seg[size_t(s) + 1]);
+    cut = std::max(cut, offsets[r - 1]);
+    offsets[r] = std::min(cut, n);
+  }
+  ctx->timers["h_build.partition_max_over_mean_rows"] = 0.;
+  int64_t mx = 0;
+  for (int r = 0; r < nparts; ++r) mx = std::max(mx, offsets[r + 1] - offsets[r]);
+  ctx->timers["h_build.partition_max_over_mean_rows"] = double(mx) * nparts / double(n);
+}
+
 void hbuild_csr(b2ci_ctx* ctx, const b2ci_dets* dets, int64_t row_begin, int64_t row_end,
                 double thr, b2ci_csr* out) {
   if (!ctx->ints_dev) throw Error("b2ci_hbuild_csr: integrals not uploaded");

@@ -106,6 +106,12 @@ class Context:
                                      C.byref(h)))
         return DetList(self, h)
 
+    def balanced_partition(self, dets: "DetList", nparts: int, nsamples: int = 1024) -> np.ndarray:
+        """Row cuts (nparts + 1 offsets) that balance the estimated connections of a selected-CI list."""
+        off = np.zeros(nparts + 1, dtype=np.int64)
+        check(lib().b2ci_dets_balanced_partition(self.h, dets.h, nparts, nsamples, _p(off)))
+        return off
+
     def generate_fci(self, norb: int, nalpha: int, nbeta: int) -> "DetList":
         h = C.c_void_p()
         check(lib().b2ci_dets_generate_fci(self.h, norb, nalpha, nbeta, C.byref(h)))

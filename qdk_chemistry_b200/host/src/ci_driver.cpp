@@ -209,10 +209,20 @@ class CiSession {
   // this call are then kept for the next one. take_dets: the session owns `dets` afterwards.
   double selected_ci_diag(b2ci_dets* dets, int64_t n, double matel_tol, int64_t max_m, double res_tol,
                           std::vector<double>& X, bool use_cache = false, double min_patch_overlap = 0.3,
-                          bool take_dets = false) {
+                          bool take_dets = false, bool balance_rows = false) {
     if (n == 0) throw std::runtime_error("selected_ci_diag: empty determinant list");
     X.resize(size_t(n), 0.0);
-    const auto rows = my_rows(n);
+    // row blocks of the ranks: even row counts for full-CI lists (uniform rows); for selected-CI lists cuts that
+    // balance the estimated connections -- the spin-sorted head of an ASCI list holds the determinants with the
+    // most partners, and with even rows the first rank built and multiplied twice the mean (Cr2 1e7 on 8 GPUs:
+    // 688 ms against ~300 on the others). B2CI_EQUAL_ROWS=1 keeps the even split.
+    std::vector<int64_t> off(size_t(nranks_) + 1, 0);
+    for (int r = 0; r < nranks_; ++r) off[size_t(r) + 1] = row_block(n, r, nranks_).second;
+    if (nranks_ > 1 && balance_rows && !getenv("B2CI_EQUAL_ROWS")) {
+      B2(b2ci_dets_balanced_partition(ctx_, dets, nranks_, 1024, off.data()));
+      g_stats["row_partition_max_over_mean"] = b2ci_timer_ms(ctx_, "h_build.partition_max_over_mean_rows");
+    }
+    const std::pair<int64_t, int64_t> rows{off[size_t(rank_)], off[size_t(rank_) + 1]};
     b2ci_csr* H = nullptr;
     struct DetsGuard {  // frees a taken-over list unless the cache adopts it
       b2ci_ctx* c;
@@ -235,11 +245,8 @@ class CiSession {
       drop_cache();
       B2(b2ci_hbuild_csr(ctx_, dets, rows.first, rows.second, matel_tol, &H));
     }
-    if (nranks_ > 1) {  // every rank knows the split (row_block): no exchange of block sizes
-      std::vector<int64_t> off(size_t(nranks_) + 1, 0);
-      for (int r = 0; r < nranks_; ++r) off[size_t(r) + 1] = row_block(n, r, nranks_).second;
+    if (nranks_ > 1)  // every rank knows the split: no exchange of block sizes
       B2(b2ci_csr_set_row_partition(ctx_, H, off.data(), nranks_));
-    }
     add_timer("h_build_ms", {"h_build.setup", "h_build.count", "h_build.fill", "h_build.thresh"});
     add_timer("h_build_setup_ms", {"h_build.setup"});
     add_timer("h_build_count_ms", {"h_build.count"});
@@ -295,7 +302,8 @@ class CiSession {
     b2ci_dets* d = nullptr;
     B2(b2ci_dets_upload(ctx_, reinterpret_cast<const uint64_t*>(dets.data()), 2, int64_t(dets.size()), &d));
     // the list is handed over: freed there, or adopted by the cache
-    return selected_ci_diag(d, int64_t(dets.size()), matel_tol, max_m, res_tol, X, use_cache, min_patch_overlap, true);
+    // (host lists are the selected-CI lists of the ASCI loop: connection-balanced row blocks)
+    return selected_ci_diag(d, int64_t(dets.size()), matel_tol, max_m, res_tol, X, use_cache, min_patch_overlap, true, true);
   }
   // natural-orbital step of asci_grow (grow.hpp:163-215): spin-traced 1-RDM of the current
   // wavefunction, eigenvectors of -ordm (occupations descending), integrals rotated on the device

@@ -104,8 +104,11 @@ def main():
     Ep, wp = alg.create("multi_configuration_calculator", "macis_cas", ci_residual_tolerance=1e-8).run(
         ham, sp.nalpha, sp.nbeta)
     out.update(E_plugin=Ep - sp.core_energy, plugin_norm=wp.norm(), plugin_ndets=wp.size())
+    # (connection-balanced row blocks for the ASCI lists, which are far below the size where that starts by default)
+    os.environ["B2CI_BALANCE_MIN"] = "16"
     Ea, wa = alg.create("multi_configuration_calculator", "macis_asci", ntdets_max=600,
                         ci_residual_tolerance=1e-8).run(ham, sp.nalpha, sp.nbeta)
+    out["asci_row_partition_max_over_mean"] = alg.last_run_stats().get("row_partition_max_over_mean")
     alg.clear_communicator()
     Ea1, wa1 = alg.create("multi_configuration_calculator", "macis_asci", ntdets_max=600,
                           ci_residual_tolerance=1e-8).run(ham, sp.nalpha, sp.nbeta)

@@ -36,5 +36,7 @@ def test_row_sharded_path_matches_single_gpu(world):
         assert abs(r["overlap"] - 1) < 1e-7 and abs(r["norm"] - 1) < 1e-12
         assert abs(r["E_plugin"] - r["E_single"]) < 1e-8 and abs(r["plugin_norm"] - 1) < 1e-12
         assert abs(r["E_asci_sharded"] - r["E_asci_single"]) < 1e-8 and r["asci_same_dets"]
+        # the sharded ASCI run used connection-balanced (uneven) row blocks
+        assert r["asci_row_partition_max_over_mean"] is not None and r["asci_row_partition_max_over_mean"] >= 1.0
     # every rank holds the same energy bit for bit (replicated Rayleigh-Ritz on all-reduced data)
     assert len({r["E_sharded"] for r in res}) == 1

@@ -529,3 +529,35 @@ def test_hit_list_fill_equals_rescan_fill(ctx, mode, monkeypatch):
         Hp, _ = ctx.hbuild_patched(d_old, ctx.hbuild(d_old, thr), d, thr, 0.3)
         prp, pci, pnz = Hp.download()
         assert np.array_equal(prp, orp) and np.array_equal(pci, oci) and np.array_equal(pnz, onz)
+
+
+def test_balanced_row_partition_evens_out_connections(ctx, monkeypatch):
+    """b2ci_dets_balanced_partition: contiguous row blocks with about equal numbers of connections (the row blocks
+    of a sharded selected-CI build). The cuts tile [0, n), are reproducible (every rank computes its own copy),
+    and the blocks' true nnz -- from the oracle's CSR of the same list -- are closer to the mean than with even
+    row counts. The matrix assembled from the blocks is the oracle's, whatever the cuts."""
+    from helpers import generator_case
+    sp, a, b = generator_case("n2_cas10_s2500")
+    monkeypatch.setenv("B2CI_BALANCE_MIN", "64")
+    ctx.upload_integrals(sp.norb, sp.T, sp.V)
+    d = ctx.upload_dets(port.pack(a, b), 1)
+    n = len(a)
+    orp, oci, onz = port.Ham(sp.norb, sp.T, sp.V).hbuild(a, b, EPS)
+    for nparts in (2, 4, 8):
+        off = ctx.balanced_partition(d, nparts, 256)
+        assert off[0] == 0 and off[-1] == n and np.all(np.diff(off) >= 0)
+        assert np.array_equal(off, ctx.balanced_partition(d, nparts, 256))
+        nnz_bal = np.diff(orp[off])
+        even = np.array([r * (n // nparts) + min(r, n % nparts) for r in range(nparts + 1)])
+        nnz_even = np.diff(orp[even])
+        assert nnz_bal.max() / nnz_bal.mean() <= max(1.10, 0.999 * nnz_even.max() / nnz_even.mean()), (nnz_bal, nnz_even)
+        rp, ci, nz = [], [], []
+        for r in range(nparts):
+            brp, bci, bnz = ctx.hbuild(d, EPS, (int(off[r]), int(off[r + 1]))).download()
+            assert np.array_equal(brp, orp[off[r]:off[r + 1] + 1] - orp[off[r]])
+            ci.append(bci)
+            nz.append(bnz)
+        assert np.array_equal(np.concatenate(ci), oci) and np.array_equal(np.concatenate(nz), onz)
+    # a list too short to be worth balancing: even row counts
+    monkeypatch.setenv("B2CI_BALANCE_MIN", "100000")
+    assert np.array_equal(ctx.balanced_partition(d, 4, 256), [0, 625, 1250, 1875, 2500])
