@@ -390,7 +390,7 @@ def run_b200_asci(args):
 # ---------------------------------------------------------------------------------------
 def load_traffic(kernel_key):
     """DRAM traffic per launch (dram__bytes_read.sum + dram__bytes_write.sum) of the dominant
-    kernels, from the committed `ncu --set full` capture (profiles/r01_traffic.json)."""
+    kernels, from the committed `ncu --set full` capture (profiles/r02_traffic.json)."""
     p = os.path.join(ROOT, "profiles", "r02_traffic.json")
     try:
         with open(p) as fh:

@@ -2277,7 +2277,9 @@ void run_row_scan(b2ci_ctx* ctx, RowArgs A, int64_t nrows, int64_t nket, double 
       B2_CUDA(cudaMemcpyAsync(pin, sptr.p + ns, 8, cudaMemcpyDeviceToHost, st));
       // units of the tiled scan: <= 32 consecutive rows of one alpha run, aligned to the run's start
       const bool want_tile = !getenv("B2CI_HBUILD_NO_TILE");
-      int32_t tile_min = 12;
+      // smallest tiled unit: measured on the 1e6-determinant N2 / Cr2 ASCI lists with the per-step emit of round 2
+      // (tiled + row scan): 3 -> 34.7 / 57.9 ms, 5 -> 35.0 / 58.0, 8 -> 35.4 / 59.3, 12 -> 36.8 / 59.8
+      int32_t tile_min = 4;
       if (const char* env = getenv("B2CI_HBUILD_TILE_MIN")) tile_min = std::max(1, atoi(env));
       DevBuf<int32_t> uflag, uexcl, tflag, texcl, sflag, sexcl;
       if (want_tile) {
