@@ -820,13 +820,18 @@ int asci_search(b2ci_ctx* ctx, const b2ci_asci_search_opts* o, const uint64_t* c
     iota_u32(ctx, idx, total);
     const int ndig = (n + 7) / 8;
     std::vector<int> shifts;
-    std::vector<uint64_t> h1(total), h2(two ? total : 0);
+    // The sorted keys go straight into the caller's array (no zero-filled staging vectors: at 1e7 determinants
+    // their page faults and the extra pass were a third of this phase). wpd == 2 with one-word keys: the packed
+    // words land in the first half and are expanded in place from the back.
+    std::vector<uint64_t> h2;
+    uint64_t* h1 = out_words;
     if (!two) {
       for (int d = 0; d < ndig; ++d) shifts.push_back(32 + 8 * d);  // beta: minor
       for (int d = 0; d < ndig; ++d) shifts.push_back(8 * d);       // alpha: major
       radix_sort_pairs(ctx, k1, k1alt, idx, idx_alt, total, shifts);
-      B2_CUDA(cudaMemcpyAsync(h1.data(), k1, size_t(total) * 8, cudaMemcpyDeviceToHost, st));
+      B2_CUDA(cudaMemcpyAsync(h1, k1, size_t(total) * 8, cudaMemcpyDeviceToHost, st));
     } else {
+      h2.resize(size_t(total));
       for (int d = 0; d < ndig; ++d) shifts.push_back(8 * d);
       B2_CUDA(cudaMemcpyAsync(kw, k2, size_t(total) * 8, cudaMemcpyDeviceToDevice, st));
       radix_sort_pairs(ctx, kw, k1alt, idx, idx_alt, total, shifts);            // by beta
@@ -837,16 +842,16 @@ int asci_search(b2ci_ctx* ctx, const b2ci_asci_search_opts* o, const uint64_t* c
       k_gather_u64<<<grid1d(total), 256, 0, st>>>(k2, idx, total, k1alt);
       ctx->launches++;
       B2_CHECK_LAUNCH();
-      B2_CUDA(cudaMemcpyAsync(h1.data(), kw, size_t(total) * 8, cudaMemcpyDeviceToHost, st));
+      B2_CUDA(cudaMemcpyAsync(h1, kw, size_t(total) * 8, cudaMemcpyDeviceToHost, st));       // alpha words, packed
       B2_CUDA(cudaMemcpyAsync(h2.data(), k1alt, size_t(total) * 8, cudaMemcpyDeviceToHost, st));
     }
     B2_CUDA(cudaStreamSynchronize(st));
     mark("output sort + download");
-    if (two)
-      for (int64_t i = 0; i < total; ++i) { out_words[2 * i] = h1[i]; out_words[2 * i + 1] = h2[i]; }
-    else if (wpd == 1) memcpy(out_words, h1.data(), size_t(total) * 8);
-    else
-      for (int64_t i = 0; i < total; ++i) { out_words[2 * i] = h1[i] & 0xFFFFFFFFull; out_words[2 * i + 1] = h1[i] >> 32; }
+    if (two) {
+      for (int64_t i = total - 1; i >= 0; --i) { const uint64_t a = h1[i]; out_words[2 * i] = a; out_words[2 * i + 1] = h2[size_t(i)]; }
+    } else if (wpd == 2) {
+      for (int64_t i = total - 1; i >= 0; --i) { const uint64_t v = h1[i]; out_words[2 * i] = v & 0xFFFFFFFFull; out_words[2 * i + 1] = v >> 32; }
+    }
     mark("words to caller");
     return 0;
   }
