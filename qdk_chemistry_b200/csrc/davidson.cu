@@ -628,6 +628,9 @@ __global__ void k_diag(int64_t nrows, int64_t row_begin, const int64_t* __restri
   D[r] = d;
 }
 
+// dynamic shared memory of the kernels that keep k coefficients there: rounded up to whole 32-byte groups, the
+// unrolled loops read the coefficients with 16-byte loads (compute-sanitizer: a read 8 bytes past k * 8 for odd k)
+inline size_t coeff_smem(int k) { return (size_t(k) + 4) / 4 * 32; }
 struct Work {
   b2ci_ctx* ctx;
   int64_t N, ld;
@@ -667,7 +670,7 @@ double norm2(Work& W, const double* w) {
 void project(Work& W, int k, const double* V, double* w, bool with_norm = false) {
   b2ci_ctx* ctx = W.ctx;
   dots(W, k, V, w, nullptr);  // h stays on the device (W.small)
-  k_project_out<<<W.npair, 256, size_t(k) * 8, ctx->stream>>>(W.N, k, V, W.ld, W.small, w,
+  k_project_out<<<W.npair, 256, coeff_smem(k), ctx->stream>>>(W.N, k, V, W.ld, W.small, w,
                                                                with_norm ? W.partial.p : nullptr, W.counter,
                                                                W.scal.p + 1);
   ctx->launches++;
@@ -889,7 +892,7 @@ int davidson(b2ci_ctx* ctx, const b2ci_csr* m, int64_t max_m, double tol, double
     double* R = V + (i + 1) * ld;
     {
       DeferredScope t(timers, "davidson.RES_DUR");
-      k_residual<<<W.npair, 256, size_t(k) * 8, st>>>(Nloc, k, V, AV, ld, cdev, lam, D,
+      k_residual<<<W.npair, 256, coeff_smem(k), st>>>(Nloc, k, V, AV, ld, cdev, lam, D,
                                                         xfull + row0, R, W.partial, W.counter, W.scal.p);
       ctx->launches++;
       B2_CHECK_LAUNCH();

@@ -2222,6 +2222,7 @@ void run_row_scan(b2ci_ctx* ctx, RowArgs A, int64_t nrows, int64_t nket, double 
   // store of the warp-per-row scan (rows of short units)
   DevBuf<int32_t> hit_cols, hit_next, hit_head;
   DevBuf<unsigned int> cursors(2);  // [0] warp-per-row chunks, [1] tile chunks
+  B2_CUDA(cudaMemsetAsync(cursors, 0, 2 * sizeof(unsigned int), st));  // (read back below whether or not a store is used)
   unsigned int hit_capacity = 0, hit_used = 0;
   // tiled scan (units of >= tile_min rows of one alpha run)
   DevBuf<int32_t> unit_row0, unit_len, unit_head, unit_nent, unit_nent_c, row_cnt_c, scan_rows, tile_next;
