@@ -324,24 +324,33 @@ __device__ __forceinline__ bool last_cta_done(unsigned int* counter, unsigned in
   if (is_last) __threadfence();
   return is_last;
 }
-// partial[b*k + j] = sum over the rows of CTA b of A[i + j*ld] * w[i]
-// Thread t of CTA b owns rows b*256 + t + s*stride (s = 0, 1, ...) and adds their products in that order: the
-// summation order (and with it every bit of the Rayleigh-Ritz matrix) is fixed by that ownership. What moved is how
-// the operands arrive: one thread issues bulk (TMA) copies of the step's 2 KiB column pieces and of w into a ring
-// of DOT_STAGES shared-memory stages, signalled on mbarriers, so a CTA keeps 4 x 18 KiB in flight instead of the
-// nine 8-byte loads a thread can hold in registers (ncu: 3.0 TB/s, warps waiting on their own loads).
-constexpr int DOT_STAGES = 4;
-constexpr int DOT_STAGE_DOUBLES = (DOT_CG + 1) * DOT_THREADS;  // DOT_CG column pieces + the piece of w
+// partial[b*k + j] = sum over the rows of LOGICAL CTA b of A[i + j*ld] * w[i]
+// Thread t of logical CTA b owns rows b*256 + t + s*stride (s = 0, 1, ...; stride = nlog * 256) and adds their
+// products in that order; its warp's tree, the warp-order sum and the CTA-order sum follow: the summation order (and
+// with it every bit of the Rayleigh-Ritz matrix) is fixed by that ownership. What is free is how the operands
+// arrive and which hardware CTA plays which logical CTA:
+//  * one thread issues bulk (TMA) copies of the step's column pieces and of w into a ring of shared-memory stages,
+//    signalled on mbarriers -- the bytes in flight live in shared memory, not in a thread's registers;
+//  * a hardware CTA plays DOT_LB ADJACENT logical CTAs, so a piece is DOT_LB * 2 KiB of one column. The streaming
+//    kernels of this file showed what the piece size is worth on this HBM: 2 KiB per column and step 3.0 TB/s
+//    (this kernel with DOT_LB = 1, whether fed through registers or TMA), 4 KiB 4.6-5.3 TB/s.
+constexpr int DOT_LB = 2;
+constexpr int DOT_STAGES = 2;
+constexpr int DOT_PTHREADS = DOT_THREADS * DOT_LB;                // threads of a hardware CTA
+constexpr int DOT_STAGE_DOUBLES = (DOT_CG + 1) * DOT_PTHREADS;    // DOT_CG column pieces + the piece of w
 constexpr size_t DOT_SMEM_BYTES = size_t(DOT_STAGES) * DOT_STAGE_DOUBLES * 8;
-__global__ void __launch_bounds__(DOT_THREADS)
+__global__ void __launch_bounds__(DOT_PTHREADS)
 k_multi_dot(int64_t N, int k, const double* __restrict__ A, int64_t ld,
             const double* __restrict__ w, double* __restrict__ partial, unsigned int* __restrict__ counter,
-            double* __restrict__ out) {
+            double* __restrict__ out, int nlog) {
   extern __shared__ __align__(128) double dot_smem[];
-  __shared__ double red[DOT_CG][DOT_THREADS / 32];
+  __shared__ double red[DOT_CG][DOT_PTHREADS / 32];
   __shared__ __align__(8) uint64_t full[DOT_STAGES];
   const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
-  const int64_t stride = int64_t(gridDim.x) * DOT_THREADS, row_base = int64_t(blockIdx.x) * DOT_THREADS;
+  const int lb = t / DOT_THREADS, tl = t - lb * DOT_THREADS;     // logical CTA within the hardware CTA, thread in it
+  const int b = int(blockIdx.x) * DOT_LB + lb;                    // logical CTA
+  const int nlb = min(DOT_LB, nlog - int(blockIdx.x) * DOT_LB);   // logical CTAs this hardware CTA plays
+  const int64_t stride = int64_t(nlog) * DOT_THREADS, row_base = int64_t(blockIdx.x) * DOT_PTHREADS;
   const int niter = row_base < N ? int((N - row_base + stride - 1) / stride) : 0;
   // the columns are split into gridDim.y contiguous ranges, walked DOT_CG columns at a time (a column's sum never
   // depends on the grouping)
@@ -358,13 +367,14 @@ k_multi_dot(int64_t N, int k, const double* __restrict__ A, int64_t ld,
     const int j0 = jbeg + chunk * DOT_CG, nc = min(DOT_CG, jend - j0);
     const int64_t r0 = row_base + int64_t(s) * stride;
     const int64_t left = N - r0;
-    const int nr = left < DOT_THREADS ? int(left) : DOT_THREADS;
+    const int cap = nlb * DOT_THREADS;  // (the rows behind belong to logical CTA 0 of the next step)
+    const int nr = left < cap ? int(left) : cap;
     const uint32_t bytes = uint32_t((nr + 1) & ~1) * 8u;  // 16-byte granules; an odd tail reads the column's padding
     const int stage = q % DOT_STAGES;
     double* buf = dot_smem + size_t(stage) * DOT_STAGE_DOUBLES;
     mbar_arrive_expect_tx(&full[stage], bytes * uint32_t(nc + 1));
-    bulk_g2s(buf + DOT_CG * DOT_THREADS, w + r0, bytes, &full[stage]);
-    for (int c = 0; c < nc; ++c) bulk_g2s(buf + c * DOT_THREADS, A + r0 + int64_t(j0 + c) * ld, bytes, &full[stage]);
+    bulk_g2s(buf + DOT_CG * DOT_PTHREADS, w + r0, bytes, &full[stage]);
+    for (int c = 0; c < nc; ++c) bulk_g2s(buf + c * DOT_PTHREADS, A + r0 + int64_t(j0 + c) * ld, bytes, &full[stage]);
   };
   if (t == 0)
     for (int q = 0; q < min(DOT_STAGES, total); ++q) issue(q);
@@ -378,15 +388,15 @@ k_multi_dot(int64_t N, int k, const double* __restrict__ A, int64_t ld,
     const int j0 = jbeg + chunk * DOT_CG, nc = min(DOT_CG, jend - j0);
     const int64_t r0 = row_base + int64_t(s) * stride;
     const double* buf = dot_smem + size_t(stage) * DOT_STAGE_DOUBLES;
-    if (r0 + t < N) {
-      const double wi = buf[DOT_CG * DOT_THREADS + t];
+    if (lb < nlb && r0 + t < N) {
+      const double wi = buf[DOT_CG * DOT_PTHREADS + t];
 #pragma unroll
       for (int c = 0; c < DOT_CG; ++c)
-        if (c < nc) acc[c] = fma(buf[c * DOT_THREADS + t], wi, acc[c]);
+        if (c < nc) acc[c] = fma(buf[c * DOT_PTHREADS + t], wi, acc[c]);
     }
     __syncthreads();  // the stage is read: refill it
     if (t == 0 && q + DOT_STAGES < total) issue(q + DOT_STAGES);
-    if (s == niter - 1) {  // last row step of this chunk of columns: reduce over the CTA
+    if (s == niter - 1) {  // last row step of this chunk of columns: reduce over every logical CTA
 #pragma unroll
       for (int c = 0; c < DOT_CG; ++c) {
         double v = acc[c];
@@ -396,44 +406,44 @@ k_multi_dot(int64_t N, int k, const double* __restrict__ A, int64_t ld,
         acc[c] = 0.;
       }
       __syncthreads();
-      if (t < nc) {
+      if (tl < nc && lb < nlb) {
         double sum = 0.;
 #pragma unroll
-        for (int wv = 0; wv < DOT_THREADS / 32; ++wv) sum += red[t][wv];
-        partial[int64_t(blockIdx.x) * k + j0 + t] = sum;
+        for (int wv = 0; wv < DOT_THREADS / 32; ++wv) sum += red[tl][lb * (DOT_THREADS / 32) + wv];
+        partial[int64_t(b) * k + j0 + tl] = sum;
       }
       __syncthreads();
     }
   }
-  if (niter == 0)  // (a CTA without rows still owns its partials)
-    for (int j = jbeg + t; j < jend; j += DOT_THREADS) partial[int64_t(blockIdx.x) * k + j] = 0.;
+  if (niter == 0 && lb < nlb)  // (a CTA without rows still owns its partials)
+    for (int j = jbeg + tl; j < jend; j += DOT_THREADS) partial[int64_t(b) * k + j] = 0.;
   if (counter && last_cta_done(counter, gridDim.x * gridDim.y)) {
-    // sum over the CTAs in CTA order (the order of the former reduction kernel: same bits), with the partials of
-    // 16 columns at a time staged in shared memory by all threads -- a single thread walking gridDim.x dependent
+    // sum over the logical CTAs in order (the order of the former reduction kernel: same bits), with the partials
+    // of 16 columns at a time staged in shared memory by all threads -- a single thread walking nlog dependent
     // global loads per column was a 30 us tail on every dot product
     constexpr int JB = 16, MAXB = 320;
     static_assert(size_t(JB) * MAXB * 8 <= DOT_SMEM_BYTES, "the staging area reuses the copy ring");
     double* stage = dot_smem;
-    const unsigned nb = gridDim.x;
+    const unsigned nb = unsigned(nlog);
     if (nb <= MAXB) {
       for (int j0 = 0; j0 < k; j0 += JB) {
         const int nj = min(JB, k - j0);
-        for (unsigned u = threadIdx.x; u < nb * nj; u += DOT_THREADS) {
-          const unsigned b = u / nj, jj = u - b * nj;
-          stage[jj * MAXB + b] = partial[int64_t(b) * k + j0 + jj];
+        for (unsigned u = threadIdx.x; u < nb * nj; u += DOT_PTHREADS) {
+          const unsigned bb = u / nj, jj = u - bb * nj;
+          stage[jj * MAXB + bb] = partial[int64_t(bb) * k + j0 + jj];
         }
         __syncthreads();
         if (int(threadIdx.x) < nj) {
           double sum = 0.;
-          for (unsigned b = 0; b < nb; ++b) sum += stage[threadIdx.x * MAXB + b];
+          for (unsigned bb = 0; bb < nb; ++bb) sum += stage[threadIdx.x * MAXB + bb];
           out[j0 + threadIdx.x] = sum;
         }
         __syncthreads();
       }
     } else {
-      for (int j = threadIdx.x; j < k; j += DOT_THREADS) {
+      for (int j = threadIdx.x; j < k; j += DOT_PTHREADS) {
         double sum = 0.;
-        for (unsigned b = 0; b < nb; ++b) sum += partial[int64_t(b) * k + j];
+        for (unsigned bb = 0; bb < nb; ++bb) sum += partial[int64_t(bb) * k + j];
         out[j] = sum;
       }
     }
@@ -646,13 +656,14 @@ struct Work {
 // out (device, k doubles) = A(:, 0:k)^T w, all-reduced over the ranks; host_out: also copied back (synchronises)
 void dots(Work& W, int k, const double* A, const double* w, double* host_out) {
   b2ci_ctx* ctx = W.ctx;
-  const dim3 grid(W.nblocks, unsigned(std::min(8, (k + DOT_CG - 1) / DOT_CG)));
+  const dim3 grid(unsigned((W.nblocks + DOT_LB - 1) / DOT_LB), unsigned(std::min(8, (k + DOT_CG - 1) / DOT_CG)));
   static bool smem_set = false;
   if (!smem_set) {
     B2_CUDA(cudaFuncSetAttribute(k_multi_dot, cudaFuncAttributeMaxDynamicSharedMemorySize, int(DOT_SMEM_BYTES)));
     smem_set = true;
   }
-  k_multi_dot<<<grid, DOT_THREADS, DOT_SMEM_BYTES, ctx->stream>>>(W.N, k, A, W.ld, w, W.partial, W.counter, W.small);
+  k_multi_dot<<<grid, DOT_PTHREADS, DOT_SMEM_BYTES, ctx->stream>>>(W.N, k, A, W.ld, w, W.partial, W.counter, W.small,
+                                                                  W.nblocks);
   ctx->launches++;
   B2_CHECK_LAUNCH();
   if (ctx->nranks > 1) comm_allreduce_sum(ctx, W.small, k);

@@ -484,15 +484,16 @@ def test_fci_list_under_pair_rules_takes_the_scan_path(ctx):
                                   "flat_fill"])
 def test_hit_list_fill_equals_rescan_fill(ctx, mode, monkeypatch):
     """General lists scan once: the count pass stores the connections it finds (the tiled scan for units of
-    12+ rows of one alpha run, the warp-per-row scan for the rest) and the fill pass evaluates them from the
+    4+ rows of one alpha run, the warp-per-row scan for the rest) and the fill pass evaluates them from the
     store; a store that turns out too small falls back to a second scan. Every way gives the oracle's CSR,
     for the plain build, a row block and the patched build."""
     sp, a, b = None, None, None
     from helpers import generator_case
     sp, a, b = generator_case("n2_cas10_s2500")
     monkeypatch.setenv("B2CI_HBUILD_HITLIST_MIN", "1")
-    if mode == "overflow":
+    if mode == "overflow":  # (units below 12 rows to the warp-per-row scan, so that its store has enough to overflow)
         monkeypatch.setenv("B2CI_HBUILD_HITLIST_CAP", "100")
+        monkeypatch.setenv("B2CI_HBUILD_TILE_MIN", "12")
     if mode == "tile_overflow":
         monkeypatch.setenv("B2CI_HBUILD_TILE_CAP", "1")
     if mode == "no_tile":
