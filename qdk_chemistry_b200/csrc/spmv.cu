@@ -347,6 +347,16 @@ void spmv_launch(b2ci_ctx* ctx, const b2ci_csr* m, const double* x, double* y) {
     return;
   }
   const double mean = double(m->nnz) / double(m->nrows);
+  if (const char* env = getenv("B2CI_SPMV_TPR")) {  // (tuning hook: lanes per row)
+    switch (atoi(env)) {
+      case 2: launch<2>(ctx, m, x, y); return;
+      case 4: launch<4>(ctx, m, x, y); return;
+      case 8: launch<8>(ctx, m, x, y); return;
+      case 16: launch<16>(ctx, m, x, y); return;
+      case 32: launch<32>(ctx, m, x, y); return;
+      default: break;
+    }
+  }
   if (mean >= 96.) launch<32>(ctx, m, x, y);
   else if (mean >= 48.) launch<16>(ctx, m, x, y);
   else if (mean >= 24.) launch<8>(ctx, m, x, y);
