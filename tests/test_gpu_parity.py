@@ -216,6 +216,29 @@ def test_diagonal(ctx):
     assert np.array_equal(H.diagonal(), port.extract_diagonal(rp, ci, nz))
 
 
+def test_diagonal_of_uploaded_matrices_with_unsorted_or_missing_entries(ctx):
+    """extract_diagonal_elements (sparsexx/util/submatrix.hpp:354-383) looks the diagonal up wherever it sits in the
+    row. The device kernel finds it by binary search in the sorted rows every build makes and must still find it in
+    an uploaded matrix whose rows are not sorted; a row without a diagonal entry gives 0."""
+    rng = np.random.default_rng(11)
+    n = 300
+    rp, ci, nz = [0], [], []
+    for i in range(n):
+        cols = set(int(c) for c in rng.choice(n, size=int(rng.integers(1, 40)), replace=False))
+        if i % 7 != 3:
+            cols.add(i)
+        else:
+            cols.discard(i)
+        cols = list(cols)
+        rng.shuffle(cols)                       # unsorted rows
+        ci += cols
+        nz += [float(rng.normal()) for _ in cols]
+        rp.append(len(ci))
+    M = ctx.upload_csr(rp, ci, nz)
+    assert np.array_equal(M.diagonal(), port.extract_diagonal(np.array(rp), np.array(ci), np.array(nz)))
+    assert all(M.diagonal()[i] == 0.0 for i in range(3, n, 7))
+
+
 @pytest.mark.parametrize("name", ["tiny_cas6", "small_cas8", "hubbard_3x2", "hubbard_4x2"])
 def test_davidson_energy_and_iterations(ctx, golden_meta, name):
     sp = W.config(name)
