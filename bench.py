@@ -790,6 +790,17 @@ def run_b200(args):
             "energy_total": (m.get("davidson") or {}).get("E0_total"),
             "wall_s_timed_region": m["wall"],
         }
+        # what keeps the step from scaling with N (max over ranks of every phase; the string-table setup is replicated
+        # on every rank, fill / count / sigma shard with the rows)
+        other_ms = max(0.0, m["build_ms"] - m["setup_ms"] - m["count_ms"] - m["fill_ms"] - m["thresh_ms"])
+        parts = {"replicated_setup_ms": m["setup_ms"], "count_ms": m["count_ms"], "fill_ms": m["fill_ms"],
+                 "thresh_ms": m["thresh_ms"], "host_gaps_ms": other_ms}
+        line["scaling_limiter"] = {
+            "hbuild": dict(parts, largest_non_sharded=max(("replicated_setup_ms", "host_gaps_ms"), key=lambda q: parts[q]),
+                           non_sharded_share=(m["setup_ms"] + other_ms) / m["build_ms"]),
+            "sigma": {"ms": m["sigma_ms"], "exchange": line["sigma_exchange"],
+                      "note": "at N > 1 the product reads the gathered vector; exchange and product run back to back "
+                              "(the overlapped variant measured slower, DESIGN.md section 5)"}}
         g = golden_energy(args.workload)
         dav = m.get("davidson") or {}
         line["parity"] = {
