@@ -657,10 +657,11 @@ struct Work {
 void dots(Work& W, int k, const double* A, const double* w, double* host_out) {
   b2ci_ctx* ctx = W.ctx;
   const dim3 grid(unsigned((W.nblocks + DOT_LB - 1) / DOT_LB), unsigned(std::min(8, (k + DOT_CG - 1) / DOT_CG)));
-  static bool smem_set = false;
-  if (!smem_set) {
+  static bool smem_set[64] = {};  // per device: function attributes belong to the device's instance of the kernel
+  const int dev = ctx->device & 63;
+  if (!smem_set[dev]) {
     B2_CUDA(cudaFuncSetAttribute(k_multi_dot, cudaFuncAttributeMaxDynamicSharedMemorySize, int(DOT_SMEM_BYTES)));
-    smem_set = true;
+    smem_set[dev] = true;
   }
   k_multi_dot<<<grid, DOT_PTHREADS, DOT_SMEM_BYTES, ctx->stream>>>(W.N, k, A, W.ld, w, W.partial, W.counter, W.small,
                                                                   W.nblocks);
