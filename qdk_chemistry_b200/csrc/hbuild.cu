@@ -147,7 +147,7 @@ struct RowArgs {
   const void* beta_s = nullptr;            // ket beta strings as 32-bit words (norb <= 32), else NULL
   const void* alpha_s = nullptr;           // ket alpha strings likewise (the class-binned fill)
   const double* diag = nullptr;            // the class-binned fill: diagonal element of every row (k_row_diag)
-  const int32_t* struct_cnt = nullptr;  // gathers and k_rows_hits_flat: structural row lengths of the count pass
+  const int32_t* struct_cnt = nullptr;  // gathers and the fills from connections: structural row lengths of the count pass
   int64_t row_stride = 1;               // sampling (estimate pass): row r of the launch is row r * row_stride
 };
 
@@ -319,18 +319,20 @@ k_rows(const RowArgs A) {
 // alpha run re-reads the beta strings of the same adjacent runs. Here a warp owns a UNIT of up to
 // 32 consecutive rows of ONE alpha run, one row per lane: the strings of an adjacent run are staged
 // 32 at a time in shared memory and every staged string is tested against the 32 row strings at once
-// (broadcast shared-memory read, one XOR + POPC + compare per lane, one ballot) -- the adjacency
-// walk, the run bounds and the loads are paid once per unit instead of once per row, and the test is
-// the only per-(row, string) work. With norb <= 32 the strings are 32-bit words (half the POPC work;
-// POPC issues at 16 lanes / clock / SM on B200, measured by scripts/micro/popc_rate.cu, and bounds
-// this kernel). A lane's hits ascend in the ket index by construction (runs ascend, strings ascend,
-// the beta-group members of class (c) are merged in before the run they precede): rows need no sort.
+// (broadcast shared-memory read, then per string one XOR + POPC + compare and a predicated OR into
+// the lane's hit word; votes, counts and stores once per step of 32 strings after a warp bit
+// transpose) -- the adjacency walk, the run bounds and the loads are paid once per unit instead of
+// once per row, and the test is the only per-(row, string) work. With norb <= 32 the strings are
+// 32-bit words (half the POPC work; POPC issues at 16 lanes / clock / SM on B200, measured by
+// scripts/micro/popc_rate.cu, and bounds this kernel). A lane's scan hits ascend in the ket index by
+// construction (runs ascend, strings ascend); the beta-group members of class (c) come first in the
+// unit's stream and k_tile_gather merges them into each row: rows need no sort.
 //
 // Connections leave the kernel as a dense stream of (lane mask, ket index) entries per unit -- one
 // entry per tested string that connects to at least one row of the unit, 8 bytes, so the store is
 // bounded by 8 bytes per connection whatever the rows look like -- in chained chunks of TILE_CH
 // entries (one atomic per chunk, warp-uniform). k_tile_gather then deals every row's hits to its
-// slot range of the CSR column array, where k_rows_hits_flat evaluates them in place. If the store
+// slot range of the CSR column array, where k_rows_hits_binned evaluates them in place. If the store
 // overflows the counts are still right and the fill falls back to scanning again.
 constexpr int TILE_CH = 512;  // entries per chunk (4 KiB)
 constexpr int TILE_WARPS = 8;
